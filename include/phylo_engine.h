@@ -1,0 +1,157 @@
+/* phylo_engine.h -- C ABI of the B200-native tree-scoring engine for phylocaml.
+ *
+ * This is the drop-in boundary: the entry points below are what phylocaml's OCaml
+ * `external`s for the Likelihood / NonAdditive / Bitvector / MlModel hot path bind to
+ * (through the thin `value` stubs in stubs/phylo_stubs.c). Plain pointers and sizes only.
+ * All citations are file:line under the reference tree (amnh/phylocaml).
+ *
+ * Conventions
+ *   - Every function returns PHYLO_OK (0) or a negative PHYLO_ERR_* code; the message is
+ *     available from phylo_last_error(). Nothing aborts or exits. The OCaml stubs turn a
+ *     non-zero code into `Failure msg`, the reference's own error convention
+ *     (lib/mlmodel.c:109-121: failwith).
+ *   - An engine handle is bound to ONE CUDA device and is not thread-safe (the reference is
+ *     single-threaded: no caml_enter_blocking_section anywhere). Multi-GPU = one process
+ *     (one handle) per GPU, patterns sharded contiguously, see DESIGN.md.
+ *   - There is no CPU fallback: phylo_engine_create fails when no CUDA device is usable.
+ *   - Matrices are row-major float64, exactly as OCaml Bigarray c_layout holds them
+ *     (lib/mlModel.ml:50-51).
+ *   - "Node slots" 0..capacity-1 name device-resident node data (CLV + scale counters for
+ *     likelihood; state sets for Fitch). Slots 0..T-1 are the tips.
+ */
+#ifndef PHYLO_ENGINE_H
+#define PHYLO_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHYLO_OK 0
+#define PHYLO_ERR_CUDA (-1)     /* a CUDA runtime call failed */
+#define PHYLO_ERR_ARG (-2)      /* bad argument (shape, slot id, NULL, ...) */
+#define PHYLO_ERR_STATE (-3)    /* call order (e.g. score before set_model) */
+#define PHYLO_ERR_DATA (-4)     /* invalid input data (all-zero state mask, ...) */
+#define PHYLO_ERR_NUMERIC (-5)  /* eigen-decomposition failed / complex eigenvalues */
+#define PHYLO_ERR_UNSUPPORTED (-6)
+
+#define PHYLO_SCALE_EXP 256  /* CLVs are rescaled by 2^256 when a site maximum < 2^-256 */
+#define PHYLO_LNL_BLOCK 1024 /* patterns per level-1 block of the site-sum reduction */
+
+typedef struct phylo_engine phylo_engine;
+
+/* One step of a post-order schedule: `parent` = median of `left` and `right`, reached by
+ * branches t_left / t_right (ignored by Fitch). One entry per call Node.median_2 would make
+ * while Tree.post_order_edges walks the tree (lib/tree.ml:171-187, lib/node.ml:183-198).
+ * The reference stores no branch lengths (lib/tree.ml:19-22); they travel here. */
+typedef struct {
+  int32_t parent, left, right, pad_;
+  double t_left, t_right;
+} phylo_op;
+
+/* ----------------------------------------------------------------------- engine ---- */
+int phylo_engine_create(int device, phylo_engine **out);
+void phylo_engine_destroy(phylo_engine *e);
+/* message of the last failed call on `e`; e == NULL: last phylo_engine_create failure */
+const char *phylo_last_error(const phylo_engine *e);
+/* all work is issued on this CUDA stream (a cudaStream_t; NULL = legacy default stream) */
+int phylo_engine_set_stream(phylo_engine *e, void *cuda_stream);
+int phylo_engine_sync(phylo_engine *e);
+/* kernels launched by this engine since creation (bench.py's gpu_launches evidence) */
+uint64_t phylo_engine_launch_count(const phylo_engine *e);
+/* page-locked host memory for Bigarray-backed staging buffers (full-rate H2D/D2H) */
+int phylo_host_alloc(void **out, uint64_t bytes);
+int phylo_host_free(void *p);
+
+/* ---------------------------------------------- MlModel native half (lib/mlmodel.c) ---- */
+/* Replaces diagonalize_sym (lib/mlmodel.c:163-197; OCaml external lib/mlModel.ml:78-79).
+ * In: Q (n*n, symmetric). Out: Q overwritten with U whose ROWS are eigenvectors, D = n*n
+ * matrix with eigenvalues on the diagonal (mlmodel.c:81-88). Host-side, once per model. */
+int phylo_diagonalize_sym(double *Q_inout_U, double *D, int n);
+/* Replaces diagonalize_gtr (lib/mlmodel.c:208-262; lib/mlModel.ml:73-74). In: Q (n*n).
+ * Out: Q overwritten with U, D diagonal matrix, Ui = U^-1, such that Q = U D Ui row-major.
+ * Fails with PHYLO_ERR_NUMERIC on complex eigenvalues (mlmodel.c:248-250). */
+int phylo_diagonalize_gtr(double *Q_inout_U, double *D, double *Ui, int n);
+/* Replace compose_sym / compose_gtr (lib/mlmodel.c:280-302, :325-342; lib/mlModel.ml:83-90):
+ * P = exp(Q t) from the eigensystem, computed by the pt_build kernel. Same special cases:
+ * t == -1.0 -> Q; t < 1e-10 -> I; compose_sym rounds t to float first (mlmodel.c:280).
+ * D is the full n*n matrix. P_out: n*n host buffer. */
+int phylo_compose_sym(phylo_engine *e, const double *U, const double *D, double t, int n,
+                      double *P_out);
+int phylo_compose_gtr(phylo_engine *e, const double *U, const double *D, const double *Ui,
+                      double t, int n, double *P_out);
+
+/* ------------------------------------ Likelihood node data (lib/likelihood_c.ml) ---- */
+/* The model record MlModel.t (lib/mlModel.ml:53-63): S states, K rate classes; u, d (full
+ * S*S), ui (NULL <=> `ui = None`, symmetric); priors[S]; rates[K], probs[K];
+ * pinvar < 0 <=> `pinvar = None`. Rate-scaled lengths t*rates[k] are formed on device. */
+int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U, const double *D,
+                       const double *Ui, const double *priors, const double *rates,
+                       const double *probs, double pinvar);
+/* Tip data: T taxa x N site patterns of state masks (bit i <=> state i possible,
+ * lib/alphabet.ml:193-196), mask_bytes in {1,2,4,8} like the bitvector widths
+ * (lib/bitvector/bv.h:29-55), tip-major. weights: N pattern weights or NULL (all 1).
+ * capacity >= T: number of node slots. A mask with none of the low S bits set is rejected. */
+int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                      const double *weights, int capacity);
+/* Likelihood.median_2 (lib/nodeData.ml:21, lib/likelihood_c.ml:15): CLV of `parent` from its
+ * two children with per-site rescaling. */
+int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int right,
+                      double t_right);
+/* Whole-tree entry point: run the schedule, join across the root edge (a,b) of length
+ * root_t, return lnL. retain != 0 keeps every interior CLV resident for later
+ * phylo_lk_edge_lnl / phylo_lk_get_clv / incremental re-scoring. */
+int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                        double root_t, double *lnl_out);
+/* Likelihood.root_cost / distance_1 (lib/nodeData.ml:29,32): lnL of joining the directed
+ * CLVs a and b across an edge, for n_t candidate lengths (branch-length loop). */
+int phylo_lk_edge_lnl(phylo_engine *e, int a, int b, const double *t, int n_t, double *lnl_out);
+/* Read-back. clv_out: N*K*S doubles [pattern][k][i]; scale_out: N int32 or NULL. */
+int phylo_lk_get_clv(phylo_engine *e, int node, double *clv_out, int32_t *scale_out);
+/* per-pattern ln-likelihoods (unweighted) of the last score_tree / edge_lnl (last t) */
+int phylo_lk_get_site_lnl(phylo_engine *e, double *out);
+/* level-1 block partials of the last evaluation (ceil(N/1024) doubles) and the canonical
+ * reduction of such partials -- what ranks all-gather for a bit-reproducible multi-GPU sum */
+int phylo_lk_get_block_partials(phylo_engine *e, double *out, int64_t *n_out);
+double phylo_reduce_partials(const double *partials, int64_t n);
+
+/* -------------------------- NonAdditive node data / Bitvector (lib/nonAdditive_c.ml) ---- */
+/* T taxa x N characters, one character per element of elt_bytes (W/8, W in {8,16,32,64},
+ * lib/bitvector/bv.h:29-55), n_states = number of usable low bits (vect.msize, bv.h:61).
+ * weights: N non-negative integer-valued doubles (lib/nonAdditive_c.ml:3) or NULL (all 1,
+ * the bv_fitch case). On device the characters live bit-sliced (one 32-bit word per state
+ * plane per 32 characters). An all-zero element is rejected. */
+int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
+                         const void *codes, const double *weights, int capacity);
+/* NonAdditive.median_2 (lib/nonAdditive_c.ml:19-35) == bv_fitch (lib/bitvector/bv.c:148-160;
+ * stub bv_CAML_fitch_median2 :463-480): parent set + cost of this node alone. */
+int phylo_fitch_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *cost_out);
+/* bv_distance (lib/bitvector/bv.c:46-55; stub :455-461) */
+int phylo_fitch_distance(phylo_engine *e, int a, int b, uint64_t *dist_out);
+/* Whole-tree down-pass: sum of interior median costs + root-edge distance. */
+int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a,
+                           int root_b, uint64_t *length_out);
+/* per-node costs of the last score_tree (capacity uint64; Node.cost is node-local,
+ * lib/node.ml:191) */
+int phylo_fitch_get_node_costs(phylo_engine *e, uint64_t *out);
+/* Up-pass / final state sets (Node.final_states, lib/node.ml:260-268 -- TODO in the
+ * reference; rule in DESIGN.md). Requires a preceding down-pass over the same schedule. */
+int phylo_fitch_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b);
+/* which: 0 = preliminary (down-pass) sets, 1 = final sets. out: N elements of elt_bytes. */
+int phylo_fitch_get_states(phylo_engine *e, int node, int which, void *out);
+/* upload one node's preliminary sets (Bitvector.of_array, lib/bitvector/bv.c:305-327) */
+int phylo_fitch_set_states(phylo_engine *e, int node, const void *codes);
+
+/* Bitvector set algebra over node slots (lib/bitvector/bv.c:59-144; stubs :405-453) */
+int phylo_bv_union(phylo_engine *e, int dst, int a, int b);
+int phylo_bv_inter(phylo_engine *e, int dst, int a, int b);
+int phylo_bv_popcount(phylo_engine *e, int a, uint64_t *out);
+int phylo_bv_saturation(phylo_engine *e, int a, uint64_t state_mask, uint64_t *out);
+int phylo_bv_poly_saturation(phylo_engine *e, int a, int n, uint64_t *out);
+int phylo_bv_compare(phylo_engine *e, int a, int b, int *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYLO_ENGINE_H */

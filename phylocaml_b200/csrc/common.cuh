@@ -1,0 +1,57 @@
+// Shared device helpers for the phylocaml B200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace phylo {
+
+constexpr int kSMs = 148;           // B200: 148 SMs; grids are sized in multiples of this
+constexpr int kScaleExp = 256;      // rescale factor 2^256 (spec C.2.4)
+constexpr int kScaleHiThresh = (1023 - kScaleExp) << 20;  // high word of 2^-256
+constexpr int kLnlBlock = 1024;     // patterns per level-1 reduction block
+
+struct __align__(32) d4 {
+  double x, y, z, w;
+};
+
+// 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a): one request moves a thread's
+// whole 4-state fp64 vector. CLVs are streamed: read once, written once per evaluation.
+__device__ __forceinline__ d4 ld256_stream(const double *p) {
+  d4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256(double *p, const d4 &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z),
+               "d"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ int hi32(double v) { return __double2hiint(v); }
+
+// x[j] += x[j+off] for off = 16..1: lane 0 ends with the canonical 32-group fold
+// (oracle/phylo_oracle.c reduce_block).
+__device__ __forceinline__ double warp_fold(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Canonical fold of 1024 values held in shared memory `vals` (zero padded) into one double,
+// returned on thread 0. `wsum` is 32 doubles of scratch. Any block size that is a multiple
+// of 32 works; the result does not depend on it.
+__device__ __forceinline__ double block_fold_1024(const double *vals, double *wsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < 32; g += nwarps) {
+    double v = warp_fold(vals[g * 32 + lane]);
+    if (lane == 0) wsum[g] = v;
+  }
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) r = warp_fold(wsum[lane]);
+  return r;
+}
+
+}  // namespace phylo

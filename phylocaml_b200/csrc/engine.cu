@@ -1,0 +1,1156 @@
+// C ABI implementation (include/phylo_engine.h) of the B200 tree-scoring engine.
+// Host-side handle, device arenas and kernel dispatch; all arithmetic lives in the kernels
+// (lk_kernels.cuh, fitch_kernels.cuh). No CPU fallback anywhere: every entry point that
+// computes launches CUDA kernels on the handle's device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fitch_kernels.cuh"
+#include "lk_kernels.cuh"
+#include "phylo_engine.h"
+
+using namespace phylo;
+
+static std::string g_create_error;
+
+struct LkNode {
+  double *clv = nullptr;
+  int32_t *scale = nullptr;
+  bool valid = false;
+};
+
+struct phylo_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = kSMs;
+
+  // ---- likelihood model (MlModel.t, lib/mlModel.ml:53-63)
+  int S = 0, K = 0;
+  bool sym = false, has_model = false;
+  double pinvar = -1.0;
+  double *dU = nullptr, *dLam = nullptr, *dUi = nullptr, *dPi = nullptr, *dRates = nullptr,
+         *dProbs = nullptr;
+  // ---- likelihood data
+  int T = 0, cap = 0, mask_dev_bytes = 1;
+  int64_t N = 0;
+  void *dTips = nullptr;  // T*N masks, device width
+  void *dInv = nullptr;   // N masks: AND over tips
+  double *dWeights = nullptr;
+  std::vector<LkNode> nodes;
+  double *dP = nullptr;  // transition matrices [branch][K][S][S]
+  size_t capP = 0;       // branches
+  double *dT = nullptr, *hT = nullptr;  // branch lengths (device / pinned)
+  double *dSite = nullptr;
+  double *dPart = nullptr, *dPart2 = nullptr;  // reduction levels
+  int64_t nPart = 0;
+  double *hScalar = nullptr;  // pinned
+  bool lk_evaluated = false;
+
+  // ---- Fitch data
+  int fT = 0, fcap = 0, fNP = 0, fNPdev = 0, felt = 1;
+  int64_t fN = 0, fWords = 0;
+  std::vector<uint32_t *> fPre, fFin;
+  uint32_t **dPreTab = nullptr, **dFinTab = nullptr;
+  bool tabDirty = true;
+  uint32_t *dFW = nullptr;  // integer weights, padded to fWords*32
+  unsigned long long *dCost = nullptr;  // [cap+2]: per-op costs, then total
+  size_t capCost = 0;
+  void *dSched = nullptr;
+  void *hSched = nullptr;
+  size_t capSched = 0;
+  unsigned long long *hCost = nullptr;  // pinned mirror of dCost
+  std::vector<uint64_t> nodeCost;
+  void *dStage = nullptr;  // transcoding staging (one node in reference layout)
+  size_t capStage = 0;
+};
+
+// ----------------------------------------------------------------------- helpers ----
+static int fail(phylo_engine *e, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t err_ = (call);                                                           \
+    if (err_ != cudaSuccess)                                                             \
+      return fail(e, PHYLO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                   \
+  do {                                                                                   \
+    ++e->launches;                                                                       \
+    cudaError_t err_ = cudaGetLastError();                                               \
+    if (err_ != cudaSuccess)                                                             \
+      return fail(e, PHYLO_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                 \
+                  cudaGetErrorString(err_), __FILE__, __LINE__);                         \
+  } while (0)
+
+template <typename T>
+static void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+static int grid_for(int64_t work_items, int per_block, int max_blocks) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------ engine ----
+extern "C" int phylo_engine_create(int device, phylo_engine **out) {
+  phylo_engine *e = nullptr;
+  if (!out) return fail(nullptr, PHYLO_ERR_ARG, "phylo_engine_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t st = cudaGetDeviceCount(&ndev);
+  if (st != cudaSuccess || ndev == 0)
+    return fail(nullptr, PHYLO_ERR_CUDA,
+                "phylo_engine_create: no usable CUDA device (%s); this engine has no CPU fallback",
+                st != cudaSuccess ? cudaGetErrorString(st) : "device count is 0");
+  if (device < 0 || device >= ndev)
+    return fail(nullptr, PHYLO_ERR_ARG, "phylo_engine_create: device %d out of range [0,%d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(nullptr, PHYLO_ERR_UNSUPPORTED,
+                "phylo_engine_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  e = new phylo_engine();
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  if (cudaMallocHost(&e->hScalar, 64) != cudaSuccess) {
+    delete e;
+    return fail(nullptr, PHYLO_ERR_CUDA, "phylo_engine_create: cudaMallocHost failed");
+  }
+  *out = e;
+  return PHYLO_OK;
+}
+
+static void lk_free_data(phylo_engine *e) {
+  for (auto &n : e->nodes) {
+    dfree(n.clv);
+    dfree(n.scale);
+  }
+  e->nodes.clear();
+  dfree(e->dTips);
+  dfree(e->dInv);
+  dfree(e->dWeights);
+  dfree(e->dSite);
+  dfree(e->dPart);
+  dfree(e->dPart2);
+  e->T = 0; e->N = 0; e->cap = 0; e->lk_evaluated = false;
+}
+
+static void fitch_free_data(phylo_engine *e) {
+  for (auto &p : e->fPre) dfree(p);
+  for (auto &p : e->fFin) dfree(p);
+  e->fPre.clear();
+  e->fFin.clear();
+  dfree(e->dPreTab);
+  dfree(e->dFinTab);
+  dfree(e->dFW);
+  e->fT = 0; e->fN = 0; e->fcap = 0;
+}
+
+extern "C" void phylo_engine_destroy(phylo_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  lk_free_data(e);
+  fitch_free_data(e);
+  dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
+  dfree(e->dP); dfree(e->dT);
+  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage);
+  if (e->hT) cudaFreeHost(e->hT);
+  if (e->hScalar) cudaFreeHost(e->hScalar);
+  if (e->hSched) cudaFreeHost(e->hSched);
+  if (e->hCost) cudaFreeHost(e->hCost);
+  delete e;
+}
+
+extern "C" const char *phylo_last_error(const phylo_engine *e) {
+  return e ? e->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int phylo_engine_set_stream(phylo_engine *e, void *s) {
+  if (!e) return PHYLO_ERR_ARG;
+  e->stream = (cudaStream_t)s;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_engine_sync(phylo_engine *e) {
+  if (!e) return PHYLO_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  return PHYLO_OK;
+}
+
+extern "C" uint64_t phylo_engine_launch_count(const phylo_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int phylo_host_alloc(void **out, uint64_t bytes) {
+  if (!out) return PHYLO_ERR_ARG;
+  return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? PHYLO_OK : PHYLO_ERR_CUDA;
+}
+extern "C" int phylo_host_free(void *p) {
+  return cudaFreeHost(p) == cudaSuccess ? PHYLO_OK : PHYLO_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- P(t) plumbing ----
+static int ensure_pt_capacity(phylo_engine *e, size_t branches, int S, int K) {
+  if (branches <= e->capP && e->dP) return PHYLO_OK;
+  size_t nb = std::max(branches, (size_t)64);
+  CK(cudaStreamSynchronize(e->stream));
+  dfree(e->dP);
+  dfree(e->dT);
+  if (e->hT) { cudaFreeHost(e->hT); e->hT = nullptr; }
+  e->capP = 0;
+  CK(cudaMalloc(&e->dP, sizeof(double) * nb * K * S * S));
+  CK(cudaMalloc(&e->dT, sizeof(double) * nb));
+  CK(cudaMallocHost(&e->hT, sizeof(double) * nb));
+  e->capP = nb;
+  return PHYLO_OK;
+}
+
+// launches pt_build for branches [0, nb) whose lengths are already in e->hT
+static int build_pt(phylo_engine *e, int nb) {
+  CK(cudaMemcpyAsync(e->dT, e->hT, sizeof(double) * nb, cudaMemcpyHostToDevice, e->stream));
+  const int threads = std::min(256, std::max(32, ((e->S * e->S + 31) / 32) * 32));
+  pt_build_kernel<<<nb * e->K, threads, sizeof(double) * e->S, e->stream>>>(
+      e->dU, e->dLam, e->sym ? nullptr : e->dUi, e->dRates, e->dT, e->S, e->K, e->dP);
+  LAUNCH_CHECK();
+  return PHYLO_OK;
+}
+
+static int compose_common(phylo_engine *e, const double *U, const double *D, const double *Ui,
+                          double t, int n, double *P_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!U || !D || !P_out || n < 1 || n > 64) return fail(e, PHYLO_ERR_ARG, "compose: bad arguments (n=%d)", n);
+  CK(cudaSetDevice(e->device));
+  double *dbuf = nullptr;
+  const size_t nn = (size_t)n * n;
+  // layout: U | lam | Ui | rate(=1) | t | P
+  CK(cudaMalloc(&dbuf, sizeof(double) * (3 * nn + n + 2)));
+  std::vector<double> h(2 * nn + n + 2);
+  std::memcpy(h.data(), U, sizeof(double) * nn);
+  for (int i = 0; i < n; ++i) h[nn + i] = D[(size_t)i * n + i];
+  if (Ui) std::memcpy(h.data() + nn + n, Ui, sizeof(double) * nn);
+  h[2 * nn + n] = 1.0;
+  h[2 * nn + n + 1] = t;
+  cudaError_t st = cudaMemcpyAsync(dbuf, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess) {
+    const int threads = std::min(256, std::max(32, ((n * n + 31) / 32) * 32));
+    pt_build_kernel<<<1, threads, sizeof(double) * n, e->stream>>>(
+        dbuf, dbuf + nn, Ui ? dbuf + nn + n : nullptr, dbuf + 2 * nn + n, dbuf + 2 * nn + n + 1, n, 1,
+        dbuf + 2 * nn + n + 2);
+    ++e->launches;
+    st = cudaGetLastError();
+  }
+  if (st == cudaSuccess)
+    st = cudaMemcpyAsync(P_out, dbuf + 2 * nn + n + 2, sizeof(double) * nn, cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+  cudaFree(dbuf);
+  if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "compose: %s", cudaGetErrorString(st));
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_compose_sym(phylo_engine *e, const double *U, const double *D, double t, int n,
+                                 double *P_out) {
+  return compose_common(e, U, D, nullptr, t, n, P_out);
+}
+extern "C" int phylo_compose_gtr(phylo_engine *e, const double *U, const double *D, const double *Ui,
+                                 double t, int n, double *P_out) {
+  if (!Ui) return e ? fail(e, PHYLO_ERR_ARG, "compose_gtr: Ui is NULL") : PHYLO_ERR_ARG;
+  return compose_common(e, U, D, Ui, t, n, P_out);
+}
+
+// ------------------------------------------------------------------- likelihood ----
+extern "C" int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U, const double *D,
+                                  const double *Ui, const double *priors, const double *rates,
+                                  const double *probs, double pinvar) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (S < 2 || S > 64 || K < 1 || K > 64 || !U || !D || !priors || !rates || !probs)
+    return fail(e, PHYLO_ERR_ARG, "lk_set_model: bad arguments (S=%d K=%d)", S, K);
+  if (pinvar >= 1.0) return fail(e, PHYLO_ERR_ARG, "lk_set_model: pinvar %g >= 1", pinvar);
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->T > 0 && S != e->S) lk_free_data(e);  // another alphabet: the loaded tips are void
+  if (e->T > 0 && K != e->K) {  // CLV shape changes: drop interior buffers
+    for (auto &n : e->nodes) { dfree(n.clv); dfree(n.scale); n.valid = false; }
+  }
+  for (auto &n : e->nodes) n.valid = false;  // CLVs of the previous model are stale
+  dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
+  dfree(e->dP); e->capP = 0;
+  const size_t ss = (size_t)S * S;
+  std::vector<double> lam(S);
+  for (int i = 0; i < S; ++i) lam[i] = D[(size_t)i * S + i];
+  CK(cudaMalloc(&e->dU, sizeof(double) * ss));
+  CK(cudaMalloc(&e->dLam, sizeof(double) * S));
+  CK(cudaMalloc(&e->dPi, sizeof(double) * S));
+  CK(cudaMalloc(&e->dRates, sizeof(double) * K));
+  CK(cudaMalloc(&e->dProbs, sizeof(double) * K));
+  CK(cudaMemcpy(e->dU, U, sizeof(double) * ss, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->dLam, lam.data(), sizeof(double) * S, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->dPi, priors, sizeof(double) * S, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->dRates, rates, sizeof(double) * K, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->dProbs, probs, sizeof(double) * K, cudaMemcpyHostToDevice));
+  if (Ui) {
+    CK(cudaMalloc(&e->dUi, sizeof(double) * ss));
+    CK(cudaMemcpy(e->dUi, Ui, sizeof(double) * ss, cudaMemcpyHostToDevice));
+  }
+  e->S = S; e->K = K; e->sym = (Ui == nullptr); e->pinvar = pinvar < 0 ? -1.0 : pinvar;
+  e->has_model = true;
+  return PHYLO_OK;
+}
+
+static int dev_mask_bytes(int S) { return S <= 8 ? 1 : (S <= 32 ? 4 : 8); }
+
+template <typename InT>
+static int launch_tips_prepare(phylo_engine *e, const void *raw, unsigned long long *dBad) {
+  const int g = grid_for(e->N, 256, e->sm_count * 8);
+  switch (e->mask_dev_bytes) {
+    case 1:
+      tips_prepare_kernel<InT, uint8_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint8_t *)e->dTips,
+                                                                 (uint8_t *)e->dInv, e->T, e->N, e->S, dBad);
+      break;
+    case 4:
+      tips_prepare_kernel<InT, uint32_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint32_t *)e->dTips,
+                                                                  (uint32_t *)e->dInv, e->T, e->N, e->S, dBad);
+      break;
+    default:
+      tips_prepare_kernel<InT, uint64_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint64_t *)e->dTips,
+                                                                  (uint64_t *)e->dInv, e->T, e->N, e->S, dBad);
+  }
+  LAUNCH_CHECK();
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                 const double *weights, int capacity) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!e->has_model) return fail(e, PHYLO_ERR_STATE, "lk_set_tips: call phylo_lk_set_model first");
+  if (T < 2 || N < 1 || !masks || capacity < T ||
+      !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
+    return fail(e, PHYLO_ERR_ARG, "lk_set_tips: bad arguments (T=%d N=%lld mask_bytes=%d capacity=%d)", T,
+                (long long)N, mask_bytes, capacity);
+  if (mask_bytes * 8 < e->S)
+    return fail(e, PHYLO_ERR_ARG, "lk_set_tips: %d-bit masks cannot hold %d states", mask_bytes * 8, e->S);
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  lk_free_data(e);
+  e->T = T; e->N = N; e->cap = capacity;
+  e->mask_dev_bytes = dev_mask_bytes(e->S);
+  e->nodes.assign(capacity, LkNode());
+  const size_t cells = (size_t)T * N;
+  CK(cudaMalloc(&e->dTips, cells * e->mask_dev_bytes));
+  CK(cudaMalloc(&e->dInv, (size_t)N * e->mask_dev_bytes));
+  void *raw = e->dTips;
+  bool tmp = false;
+  if (mask_bytes != e->mask_dev_bytes) {
+    CK(cudaMalloc(&raw, cells * mask_bytes));
+    tmp = true;
+  }
+  unsigned long long *dBad = nullptr;
+  cudaError_t st = cudaMalloc(&dBad, sizeof(unsigned long long));
+  if (st == cudaSuccess) st = cudaMemsetAsync(dBad, 0, sizeof(unsigned long long), e->stream);
+  if (st == cudaSuccess) st = cudaMemcpyAsync(raw, masks, cells * mask_bytes, cudaMemcpyHostToDevice, e->stream);
+  int rc = PHYLO_OK;
+  if (st == cudaSuccess) {
+    switch (mask_bytes) {
+      case 1: rc = launch_tips_prepare<uint8_t>(e, raw, dBad); break;
+      case 2: rc = launch_tips_prepare<uint16_t>(e, raw, dBad); break;
+      case 4: rc = launch_tips_prepare<uint32_t>(e, raw, dBad); break;
+      default: rc = launch_tips_prepare<uint64_t>(e, raw, dBad);
+    }
+  }
+  unsigned long long bad = 0;
+  if (st == cudaSuccess && rc == PHYLO_OK)
+    st = cudaMemcpyAsync(e->hScalar, dBad, sizeof(bad), cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess && rc == PHYLO_OK) st = cudaStreamSynchronize(e->stream);
+  if (st == cudaSuccess && rc == PHYLO_OK) bad = *(unsigned long long *)e->hScalar;
+  if (tmp) cudaFree(raw);
+  cudaFree(dBad);
+  if (rc != PHYLO_OK) { lk_free_data(e); return rc; }
+  if (st != cudaSuccess) { lk_free_data(e); return fail(e, PHYLO_ERR_CUDA, "lk_set_tips: %s", cudaGetErrorString(st)); }
+  if (bad) {
+    lk_free_data(e);
+    return fail(e, PHYLO_ERR_DATA, "lk_set_tips: %llu tip cells have none of the %d state bits set", bad, e->S);
+  }
+  if (weights) {
+    CK(cudaMalloc(&e->dWeights, sizeof(double) * N));
+    CK(cudaMemcpy(e->dWeights, weights, sizeof(double) * N, cudaMemcpyHostToDevice));
+  }
+  e->nPart = (N + kLnlBlock - 1) / kLnlBlock;
+  CK(cudaMalloc(&e->dPart, sizeof(double) * e->nPart));
+  CK(cudaMalloc(&e->dPart2, sizeof(double) * ((e->nPart + kLnlBlock - 1) / kLnlBlock + 1) * 2));
+  CK(cudaMalloc(&e->dSite, sizeof(double) * N));
+  return PHYLO_OK;
+}
+
+static int lk_ensure_node(phylo_engine *e, int slot) {
+  LkNode &n = e->nodes[slot];
+  if (n.clv) return PHYLO_OK;
+  CK(cudaMalloc(&n.clv, sizeof(double) * (size_t)e->N * e->K * e->S));
+  CK(cudaMalloc(&n.scale, sizeof(int32_t) * (size_t)e->N));
+  return PHYLO_OK;
+}
+
+struct Operand {
+  const void *src;
+  const int32_t *scale;
+  bool tip;
+};
+
+static int lk_operand(phylo_engine *e, int slot, Operand *o, const char *who) {
+  if (slot < 0 || slot >= e->cap) return fail(e, PHYLO_ERR_ARG, "%s: node slot %d out of range [0,%d)", who, slot, e->cap);
+  if (slot < e->T) {
+    o->src = (const char *)e->dTips + (size_t)slot * e->N * e->mask_dev_bytes;
+    o->scale = nullptr;
+    o->tip = true;
+    return PHYLO_OK;
+  }
+  if (!e->nodes[slot].valid) return fail(e, PHYLO_ERR_STATE, "%s: node slot %d has no CLV yet", who, slot);
+  o->src = e->nodes[slot].clv;
+  o->scale = e->nodes[slot].scale;
+  o->tip = false;
+  return PHYLO_OK;
+}
+
+template <int K>
+static void launch_prune4(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
+                          const Operand &r, double *out, int32_t *osc) {
+  constexpr int U = 2;
+  const int g = grid_for(e->N * K, 256 * U, e->sm_count * 4);
+#define P4(LT, RT)                                                                              \
+  prune4_kernel<K, LT, RT, U><<<g, 256, 0, e->stream>>>(Pl, Pr, l.src, l.scale, r.src, r.scale, \
+                                                        out, osc, e->N)
+  if (l.tip && r.tip) P4(true, true);
+  else if (l.tip) P4(true, false);
+  else if (r.tip) P4(false, true);
+  else P4(false, false);
+#undef P4
+}
+
+template <int ST, typename MaskT>
+static cudaError_t launch_prune_any(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
+                                    const Operand &r, double *out, int32_t *osc) {
+  constexpr int TP = 128;
+  const int S = e->S, S4 = (S + 3) & ~3, SP = S | 1;
+  const size_t smem = sizeof(double) * (2 * (size_t)S * S4 + 2 * (size_t)TP * SP);
+  auto kern = prune_any_kernel<ST, MaskT, TP>;
+  cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (st != cudaSuccess) return st;
+  const int per_sm = std::max(1, (int)(200 * 1024 / (smem + 1024)));
+  const int g = grid_for(e->N, TP, e->sm_count * std::min(per_sm, 8));
+  kern<<<g, TP, smem, e->stream>>>(Pl, Pr, l.src, l.scale, l.tip, r.src, r.scale, r.tip, out, osc, e->N, S, e->K);
+  return cudaSuccess;
+}
+
+static int lk_launch_prune(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
+                           const Operand &r, double *out, int32_t *osc) {
+  if (e->S == 4 && (e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8 || e->K == 16)) {
+    switch (e->K) {
+      case 1: launch_prune4<1>(e, Pl, Pr, l, r, out, osc); break;
+      case 2: launch_prune4<2>(e, Pl, Pr, l, r, out, osc); break;
+      case 4: launch_prune4<4>(e, Pl, Pr, l, r, out, osc); break;
+      case 8: launch_prune4<8>(e, Pl, Pr, l, r, out, osc); break;
+      default: launch_prune4<16>(e, Pl, Pr, l, r, out, osc);
+    }
+  } else {
+    cudaError_t st;
+    if (e->S == 20) st = launch_prune_any<20, uint32_t>(e, Pl, Pr, l, r, out, osc);
+    else if (e->S == 61) st = launch_prune_any<61, uint64_t>(e, Pl, Pr, l, r, out, osc);
+    else if (e->mask_dev_bytes == 1) st = launch_prune_any<0, uint8_t>(e, Pl, Pr, l, r, out, osc);
+    else if (e->mask_dev_bytes == 4) st = launch_prune_any<0, uint32_t>(e, Pl, Pr, l, r, out, osc);
+    else st = launch_prune_any<0, uint64_t>(e, Pl, Pr, l, r, out, osc);
+    if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "prune_any setup: %s", cudaGetErrorString(st));
+  }
+  LAUNCH_CHECK();
+  return PHYLO_OK;
+}
+
+template <int K>
+static void launch_root4(phylo_engine *e, const double *Pr, const Operand &a, const Operand &b) {
+  const int g = grid_for(e->nPart, 1, e->sm_count * 4);
+#define R4(AT, BT)                                                                                \
+  root4_kernel<K, AT, BT><<<g, 256, 0, e->stream>>>(Pr, e->dPi, e->dProbs, e->pinvar,             \
+                                                    (const uint8_t *)e->dInv, a.src, a.scale, b.src, \
+                                                    b.scale, e->dWeights, e->dSite, e->dPart, e->N)
+  if (a.tip && b.tip) R4(true, true);
+  else if (a.tip) R4(true, false);
+  else if (b.tip) R4(false, true);
+  else R4(false, false);
+#undef R4
+}
+
+template <int ST, typename MaskT>
+static cudaError_t launch_root_any(phylo_engine *e, const double *Pr, const Operand &a, const Operand &b) {
+  constexpr int TP = 128;
+  const int S = e->S, S4 = (S + 3) & ~3, SP = S | 1;
+  const size_t smem = sizeof(double) * ((size_t)S * S4 + 2 * (size_t)TP * SP + S);
+  auto kern = root_any_kernel<ST, MaskT, TP>;
+  cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (st != cudaSuccess) return st;
+  const int g = grid_for(e->nPart, 1, e->sm_count * 2);
+  kern<<<g, TP, smem, e->stream>>>(Pr, e->dPi, e->dProbs, e->pinvar, (const MaskT *)e->dInv, a.src, a.scale,
+                                   a.tip, b.src, b.scale, b.tip, e->dWeights, e->dSite, e->dPart, e->N, S, e->K);
+  return cudaSuccess;
+}
+
+// root-edge join with transition matrices Pr ([K][S][S] on device) -> *lnl_host (pinned slot)
+static int lk_root_eval(phylo_engine *e, const double *Pr, const Operand &a, const Operand &b, double *slot) {
+  if (e->S == 4 && (e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8 || e->K == 16)) {
+    switch (e->K) {
+      case 1: launch_root4<1>(e, Pr, a, b); break;
+      case 2: launch_root4<2>(e, Pr, a, b); break;
+      case 4: launch_root4<4>(e, Pr, a, b); break;
+      case 8: launch_root4<8>(e, Pr, a, b); break;
+      default: launch_root4<16>(e, Pr, a, b);
+    }
+  } else {
+    cudaError_t st;
+    if (e->S == 20) st = launch_root_any<20, uint32_t>(e, Pr, a, b);
+    else if (e->S == 61) st = launch_root_any<61, uint64_t>(e, Pr, a, b);
+    else if (e->mask_dev_bytes == 1) st = launch_root_any<0, uint8_t>(e, Pr, a, b);
+    else if (e->mask_dev_bytes == 4) st = launch_root_any<0, uint32_t>(e, Pr, a, b);
+    else st = launch_root_any<0, uint64_t>(e, Pr, a, b);
+    if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "root_any setup: %s", cudaGetErrorString(st));
+  }
+  LAUNCH_CHECK();
+  // remaining levels of the canonical reduction
+  const double *cur = e->dPart;
+  int64_t n = e->nPart;
+  double *bufs[2] = {e->dPart2, e->dPart2 + ((e->nPart + kLnlBlock - 1) / kLnlBlock + 1)};
+  int flip = 0;
+  do {
+    const int64_t nb = (n + kLnlBlock - 1) / kLnlBlock;
+    reduce1024_kernel<<<(int)nb, 256, 0, e->stream>>>(cur, n, bufs[flip]);
+    LAUNCH_CHECK();
+    cur = bufs[flip];
+    flip ^= 1;
+    n = nb;
+  } while (n > 1);
+  CK(cudaMemcpyAsync(slot, cur, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int right,
+                                 double t_right) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_median_2: no tips loaded");
+  if (parent < e->T || parent >= e->cap)
+    return fail(e, PHYLO_ERR_ARG, "lk_median_2: parent slot %d must be in [%d,%d)", parent, e->T, e->cap);
+  if (parent == left || parent == right) return fail(e, PHYLO_ERR_ARG, "lk_median_2: parent aliases a child");
+  CK(cudaSetDevice(e->device));
+  Operand l, r;
+  int rc;
+  if ((rc = lk_operand(e, left, &l, "lk_median_2")) != PHYLO_OK) return rc;
+  if ((rc = lk_operand(e, right, &r, "lk_median_2")) != PHYLO_OK) return rc;
+  if ((rc = ensure_pt_capacity(e, 2, e->S, e->K)) != PHYLO_OK) return rc;
+  if ((rc = lk_ensure_node(e, parent)) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));  // hT is about to be rewritten
+  e->hT[0] = t_left;
+  e->hT[1] = t_right;
+  if ((rc = build_pt(e, 2)) != PHYLO_OK) return rc;
+  const size_t pk = (size_t)e->K * e->S * e->S;
+  rc = lk_launch_prune(e, e->dP, e->dP + pk, l, r, e->nodes[parent].clv, e->nodes[parent].scale);
+  if (rc != PHYLO_OK) return rc;
+  e->nodes[parent].valid = true;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                   double root_t, double *lnl_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_score_tree: no tips loaded");
+  if (n_ops < 0 || (n_ops > 0 && !ops) || !lnl_out) return fail(e, PHYLO_ERR_ARG, "lk_score_tree: bad arguments");
+  CK(cudaSetDevice(e->device));
+  int rc;
+  // validate the schedule before touching the device: children must be tips or produced earlier
+  {
+    std::vector<char> ready(e->cap, 0);
+    for (int s = 0; s < e->cap; ++s) ready[s] = (s < e->T) || e->nodes[s].valid;
+    for (int o = 0; o < n_ops; ++o) {
+      const phylo_op &op = ops[o];
+      if (op.parent < e->T || op.parent >= e->cap)
+        return fail(e, PHYLO_ERR_ARG, "lk_score_tree: op %d parent slot %d must be in [%d,%d)", o, op.parent, e->T, e->cap);
+      if (op.left < 0 || op.left >= e->cap || op.right < 0 || op.right >= e->cap || op.left == op.parent ||
+          op.right == op.parent)
+        return fail(e, PHYLO_ERR_ARG, "lk_score_tree: op %d has bad child slots (%d,%d)", o, op.left, op.right);
+      if (!ready[op.left] || !ready[op.right])
+        return fail(e, PHYLO_ERR_ARG, "lk_score_tree: op %d uses a child that is not computed yet (not post-order)", o);
+      ready[op.parent] = 1;
+    }
+    if (root_a < 0 || root_a >= e->cap || root_b < 0 || root_b >= e->cap || !ready[root_a] || !ready[root_b])
+      return fail(e, PHYLO_ERR_ARG, "lk_score_tree: bad root edge (%d,%d)", root_a, root_b);
+  }
+  const int nb = 2 * n_ops + 1;
+  if ((rc = ensure_pt_capacity(e, nb, e->S, e->K)) != PHYLO_OK) return rc;
+  for (int o = 0; o < n_ops; ++o)
+    if ((rc = lk_ensure_node(e, ops[o].parent)) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  for (int o = 0; o < n_ops; ++o) {
+    e->hT[2 * o] = ops[o].t_left;
+    e->hT[2 * o + 1] = ops[o].t_right;
+  }
+  e->hT[2 * n_ops] = root_t;
+  if ((rc = build_pt(e, nb)) != PHYLO_OK) return rc;
+  const size_t pk = (size_t)e->K * e->S * e->S;
+  for (int o = 0; o < n_ops; ++o) {
+    Operand l, r;
+    if ((rc = lk_operand(e, ops[o].left, &l, "lk_score_tree")) != PHYLO_OK) return rc;
+    if ((rc = lk_operand(e, ops[o].right, &r, "lk_score_tree")) != PHYLO_OK) return rc;
+    LkNode &p = e->nodes[ops[o].parent];
+    rc = lk_launch_prune(e, e->dP + (size_t)(2 * o) * pk, e->dP + (size_t)(2 * o + 1) * pk, l, r, p.clv, p.scale);
+    if (rc != PHYLO_OK) return rc;
+    p.valid = true;
+  }
+  Operand a, b;
+  if ((rc = lk_operand(e, root_a, &a, "lk_score_tree")) != PHYLO_OK) return rc;
+  if ((rc = lk_operand(e, root_b, &b, "lk_score_tree")) != PHYLO_OK) return rc;
+  if ((rc = lk_root_eval(e, e->dP + (size_t)(2 * n_ops) * pk, a, b, e->hScalar)) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  *lnl_out = e->hScalar[0];
+  e->lk_evaluated = true;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_edge_lnl(phylo_engine *e, int a_slot, int b_slot, const double *t, int n_t,
+                                 double *lnl_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_edge_lnl: no tips loaded");
+  if (!t || n_t < 1 || !lnl_out) return fail(e, PHYLO_ERR_ARG, "lk_edge_lnl: bad arguments");
+  CK(cudaSetDevice(e->device));
+  Operand a, b;
+  int rc;
+  if ((rc = lk_operand(e, a_slot, &a, "lk_edge_lnl")) != PHYLO_OK) return rc;
+  if ((rc = lk_operand(e, b_slot, &b, "lk_edge_lnl")) != PHYLO_OK) return rc;
+  if ((rc = ensure_pt_capacity(e, n_t, e->S, e->K)) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n_t; ++i) e->hT[i] = t[i];
+  if ((rc = build_pt(e, n_t)) != PHYLO_OK) return rc;
+  const size_t pk = (size_t)e->K * e->S * e->S;
+  for (int i = 0; i < n_t; ++i) {
+    if ((rc = lk_root_eval(e, e->dP + (size_t)i * pk, a, b, e->hScalar)) != PHYLO_OK) return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    lnl_out[i] = e->hScalar[0];
+  }
+  e->lk_evaluated = true;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_get_clv(phylo_engine *e, int node, double *clv_out, int32_t *scale_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_get_clv: no tips loaded");
+  if (node < e->T || node >= e->cap || !e->nodes[node].valid)
+    return fail(e, PHYLO_ERR_ARG, "lk_get_clv: slot %d holds no interior CLV", node);
+  if (!clv_out) return fail(e, PHYLO_ERR_ARG, "lk_get_clv: clv_out is NULL");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(clv_out, e->nodes[node].clv, sizeof(double) * (size_t)e->N * e->K * e->S,
+                     cudaMemcpyDeviceToHost, e->stream));
+  if (scale_out)
+    CK(cudaMemcpyAsync(scale_out, e->nodes[node].scale, sizeof(int32_t) * (size_t)e->N, cudaMemcpyDeviceToHost,
+                       e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_get_site_lnl(phylo_engine *e, double *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!e->lk_evaluated || !out) return fail(e, PHYLO_ERR_STATE, "lk_get_site_lnl: nothing evaluated yet");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(out, e->dSite, sizeof(double) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_get_block_partials(phylo_engine *e, double *out, int64_t *n_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!e->lk_evaluated) return fail(e, PHYLO_ERR_STATE, "lk_get_block_partials: nothing evaluated yet");
+  CK(cudaSetDevice(e->device));
+  if (n_out) *n_out = e->nPart;
+  if (out) {
+    CK(cudaMemcpyAsync(out, e->dPart, sizeof(double) * (size_t)e->nPart, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return PHYLO_OK;
+}
+
+// Host restatement of levels >= 2 of the canonical reduction, used to combine the level-1
+// block partials gathered from several ranks (bit-identical for any rank count).
+static double fold1024_host(const double *v, int64_t n) {
+  double w[32];
+  for (int g = 0; g < 32; ++g) {
+    double y[32];
+    for (int j = 0; j < 32; ++j) {
+      const int64_t idx = (int64_t)g * 32 + j;
+      y[j] = idx < n ? v[idx] : 0.0;
+    }
+    for (int off = 16; off >= 1; off >>= 1)
+      for (int j = 0; j < off; ++j) y[j] = y[j] + y[j + off];
+    w[g] = y[0];
+  }
+  for (int off = 16; off >= 1; off >>= 1)
+    for (int j = 0; j < off; ++j) w[j] = w[j] + w[j + off];
+  return w[0];
+}
+
+extern "C" double phylo_reduce_partials(const double *partials, int64_t n) {
+  if (!partials || n <= 0) return 0.0;
+  std::vector<double> cur(partials, partials + n);
+  while (cur.size() > 1) {
+    const int64_t m = (int64_t)cur.size(), nb = (m + kLnlBlock - 1) / kLnlBlock;
+    std::vector<double> nxt(nb);
+    for (int64_t b = 0; b < nb; ++b)
+      nxt[b] = fold1024_host(cur.data() + b * kLnlBlock, std::min<int64_t>(kLnlBlock, m - b * kLnlBlock));
+    cur.swap(nxt);
+  }
+  return cur[0];
+}
+
+// ------------------------------------------------------------------------ Fitch ----
+static int np_device(int n_states) {
+  static const int sizes[] = {1, 2, 3, 4, 5, 6, 8, 12, 16, 24, 32, 64};
+  for (int s : sizes)
+    if (n_states <= s) return s;
+  return 64;
+}
+
+#define NP_DISPATCH(np, EXPR)                                   \
+  switch (np) {                                                 \
+    case 1: { constexpr int NP = 1; EXPR; } break;              \
+    case 2: { constexpr int NP = 2; EXPR; } break;              \
+    case 3: { constexpr int NP = 3; EXPR; } break;              \
+    case 4: { constexpr int NP = 4; EXPR; } break;              \
+    case 5: { constexpr int NP = 5; EXPR; } break;              \
+    case 6: { constexpr int NP = 6; EXPR; } break;              \
+    case 8: { constexpr int NP = 8; EXPR; } break;              \
+    case 12: { constexpr int NP = 12; EXPR; } break;            \
+    case 16: { constexpr int NP = 16; EXPR; } break;            \
+    case 24: { constexpr int NP = 24; EXPR; } break;            \
+    case 32: { constexpr int NP = 32; EXPR; } break;            \
+    default: { constexpr int NP = 64; EXPR; } break;            \
+  }
+
+static int fitch_ensure(phylo_engine *e, int slot, bool fin) {
+  std::vector<uint32_t *> &v = fin ? e->fFin : e->fPre;
+  if (v[slot]) return PHYLO_OK;
+  CK(cudaMalloc(&v[slot], sizeof(uint32_t) * (size_t)e->fWords * e->fNPdev));
+  e->tabDirty = true;
+  return PHYLO_OK;
+}
+
+static int fitch_sync_tables(phylo_engine *e) {
+  if (!e->tabDirty) return PHYLO_OK;
+  CK(cudaMemcpyAsync(e->dPreTab, e->fPre.data(), sizeof(uint32_t *) * e->fcap, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->dFinTab, e->fFin.data(), sizeof(uint32_t *) * e->fcap, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));  // the std::vector storage is pageable
+  e->tabDirty = false;
+  return PHYLO_OK;
+}
+
+static int fitch_stage(phylo_engine *e, size_t bytes) {
+  if (bytes <= e->capStage) return PHYLO_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  dfree(e->dStage);
+  e->capStage = 0;
+  CK(cudaMalloc(&e->dStage, bytes));
+  e->capStage = bytes;
+  return PHYLO_OK;
+}
+
+static int fitch_cost_capacity(phylo_engine *e, size_t n) {
+  if (n <= e->capCost) return PHYLO_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  dfree(e->dCost);
+  if (e->hCost) { cudaFreeHost(e->hCost); e->hCost = nullptr; }
+  e->capCost = 0;
+  CK(cudaMalloc(&e->dCost, sizeof(unsigned long long) * n));
+  CK(cudaMallocHost(&e->hCost, sizeof(unsigned long long) * n));
+  e->capCost = n;
+  return PHYLO_OK;
+}
+
+static int fitch_sched_capacity(phylo_engine *e, size_t bytes) {
+  if (bytes <= e->capSched) return PHYLO_OK;
+  CK(cudaStreamSynchronize(e->stream));
+  dfree(e->dSched);
+  if (e->hSched) { cudaFreeHost(e->hSched); e->hSched = nullptr; }
+  e->capSched = 0;
+  CK(cudaMalloc(&e->dSched, bytes));
+  CK(cudaMallocHost(&e->hSched, bytes));
+  e->capSched = bytes;
+  return PHYLO_OK;
+}
+
+// encode `count` nodes worth of reference-layout codes (already on device in dStage) into
+// plane buffers; returns the number of empty elements through *bad
+static int fitch_encode(phylo_engine *e, const void *dcodes, uint32_t *dst, unsigned long long *dBad) {
+  const int g = grid_for(e->fWords * 32, 256, e->sm_count * 8);
+  switch (e->felt) {
+    case 1: fitch_encode_kernel<uint8_t><<<g, 256, 0, e->stream>>>((const uint8_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
+    case 2: fitch_encode_kernel<uint16_t><<<g, 256, 0, e->stream>>>((const uint16_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
+    case 4: fitch_encode_kernel<uint32_t><<<g, 256, 0, e->stream>>>((const uint32_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
+    default: fitch_encode_kernel<uint64_t><<<g, 256, 0, e->stream>>>((const uint64_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad);
+  }
+  LAUNCH_CHECK();
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
+                                    const void *codes, const double *weights, int capacity) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (T < 1 || N < 1 || !codes || capacity < T ||
+      !(elt_bytes == 1 || elt_bytes == 2 || elt_bytes == 4 || elt_bytes == 8) || n_states < 1 ||
+      n_states > elt_bytes * 8)
+    return fail(e, PHYLO_ERR_ARG, "fitch_set_tips: bad arguments (T=%d N=%lld elt_bytes=%d n_states=%d capacity=%d)",
+                T, (long long)N, elt_bytes, n_states, capacity);
+  std::vector<uint32_t> hw;
+  if (weights) {
+    hw.assign((size_t)((N + 31) / 32) * 32, 0u);
+    for (int64_t i = 0; i < N; ++i) {
+      const double w = weights[i];
+      if (!(w >= 0.0) || w > 4294967295.0 || w != std::floor(w))
+        return fail(e, PHYLO_ERR_UNSUPPORTED,
+                    "fitch_set_tips: weight[%lld]=%g is not a non-negative integer < 2^32 (needed for exact lengths)",
+                    (long long)i, w);
+      hw[i] = (uint32_t)w;
+    }
+  }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  fitch_free_data(e);
+  e->fT = T; e->fN = N; e->fcap = capacity; e->felt = elt_bytes; e->fNP = n_states;
+  e->fNPdev = np_device(n_states);
+  e->fWords = (N + 31) / 32;
+  e->fPre.assign(capacity, nullptr);
+  e->fFin.assign(capacity, nullptr);
+  e->nodeCost.assign(capacity, 0);
+  CK(cudaMalloc(&e->dPreTab, sizeof(uint32_t *) * capacity));
+  CK(cudaMalloc(&e->dFinTab, sizeof(uint32_t *) * capacity));
+  e->tabDirty = true;
+  int rc;
+  if ((rc = fitch_cost_capacity(e, (size_t)capacity + 4)) != PHYLO_OK) return rc;
+  // upload in chunks of whole taxa through the staging buffer, transcoding on device
+  const size_t row = (size_t)N * elt_bytes;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, ((size_t)256 << 20) / row));
+  if ((rc = fitch_stage(e, row * chunk)) != PHYLO_OK) return rc;
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
+  for (int t0 = 0; t0 < T; t0 += chunk) {
+    const int nt = std::min(chunk, T - t0);
+    CK(cudaMemcpyAsync(e->dStage, (const char *)codes + (size_t)t0 * row, row * nt, cudaMemcpyHostToDevice, e->stream));
+    for (int t = 0; t < nt; ++t) {
+      if ((rc = fitch_ensure(e, t0 + t, false)) != PHYLO_OK) return rc;
+      if ((rc = fitch_encode(e, (const char *)e->dStage + (size_t)t * row, e->fPre[t0 + t], e->dCost)) != PHYLO_OK)
+        return rc;
+    }
+    CK(cudaStreamSynchronize(e->stream));  // staging buffer is reused by the next chunk
+  }
+  CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->hCost[0]) {
+    const unsigned long long bad = e->hCost[0];
+    fitch_free_data(e);
+    return fail(e, PHYLO_ERR_DATA, "fitch_set_tips: %llu characters have an empty state set", bad);
+  }
+  if (weights) {
+    CK(cudaMalloc(&e->dFW, sizeof(uint32_t) * hw.size()));
+    CK(cudaMemcpy(e->dFW, hw.data(), sizeof(uint32_t) * hw.size(), cudaMemcpyHostToDevice));
+  }
+  return PHYLO_OK;
+}
+
+static int fitch_slot_ok(phylo_engine *e, int slot, bool need_data, const char *who) {
+  if (e->fT == 0) return fail(e, PHYLO_ERR_STATE, "%s: no Fitch data loaded", who);
+  if (slot < 0 || slot >= e->fcap) return fail(e, PHYLO_ERR_ARG, "%s: node slot %d out of range [0,%d)", who, slot, e->fcap);
+  if (need_data && !e->fPre[slot]) return fail(e, PHYLO_ERR_STATE, "%s: node slot %d holds no state sets", who, slot);
+  return PHYLO_OK;
+}
+
+static int fitch_pair(phylo_engine *e, int parent, int left, int right, bool store, uint64_t *out) {
+  int rc;
+  const char *who = store ? "fitch_median_2" : "fitch_distance";
+  if ((rc = fitch_slot_ok(e, left, true, who)) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, right, true, who)) != PHYLO_OK) return rc;
+  if (store) {
+    if ((rc = fitch_slot_ok(e, parent, false, who)) != PHYLO_OK) return rc;
+    if (parent < e->fT) return fail(e, PHYLO_ERR_ARG, "%s: parent slot %d is a tip", who, parent);
+    if ((rc = fitch_ensure(e, parent, false)) != PHYLO_OK) return rc;
+  }
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
+  const int g = grid_for(e->fWords, 256, e->sm_count * 8);
+  uint32_t *c = store ? e->fPre[parent] : nullptr;
+  const uint32_t *a = e->fPre[left], *b = e->fPre[right];
+  if (store) {
+    NP_DISPATCH(e->fNPdev, (fitch_median2_kernel<NP, true><<<g, 256, 0, e->stream>>>(a, b, c, e->fWords, e->fN, e->dFW, e->dCost)));
+  } else {
+    NP_DISPATCH(e->fNPdev, (fitch_median2_kernel<NP, false><<<g, 256, 0, e->stream>>>(a, b, c, e->fWords, e->fN, e->dFW, e->dCost)));
+  }
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (out) *out = e->hCost[0];
+  if (store) e->nodeCost[parent] = e->hCost[0];
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *cost_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  return fitch_pair(e, parent, left, right, true, cost_out);
+}
+
+extern "C" int phylo_fitch_distance(phylo_engine *e, int a, int b, uint64_t *dist_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  return fitch_pair(e, -1, a, b, false, dist_out);
+}
+
+static int fitch_check_schedule(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                const char *who) {
+  if (e->fT == 0) return fail(e, PHYLO_ERR_STATE, "%s: no Fitch data loaded", who);
+  if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(e, PHYLO_ERR_ARG, "%s: bad arguments", who);
+  std::vector<char> ready(e->fcap, 0);
+  for (int s = 0; s < e->fcap; ++s) ready[s] = e->fPre[s] != nullptr && (s < e->fT);
+  for (int s = e->fT; s < e->fcap; ++s) ready[s] = e->fPre[s] != nullptr;  // earlier medians stay usable
+  for (int o = 0; o < n_ops; ++o) {
+    const phylo_op &op = ops[o];
+    if (op.parent < e->fT || op.parent >= e->fcap)
+      return fail(e, PHYLO_ERR_ARG, "%s: op %d parent slot %d must be in [%d,%d)", who, o, op.parent, e->fT, e->fcap);
+    if (op.left < 0 || op.left >= e->fcap || op.right < 0 || op.right >= e->fcap || op.left == op.parent ||
+        op.right == op.parent)
+      return fail(e, PHYLO_ERR_ARG, "%s: op %d has bad child slots (%d,%d)", who, o, op.left, op.right);
+    if (!ready[op.left] || !ready[op.right])
+      return fail(e, PHYLO_ERR_ARG, "%s: op %d uses a child that is not computed yet (not post-order)", who, o);
+    ready[op.parent] = 1;
+  }
+  if (root_a < 0 || root_a >= e->fcap || root_b < 0 || root_b >= e->fcap || !ready[root_a] || !ready[root_b])
+    return fail(e, PHYLO_ERR_ARG, "%s: bad root edge (%d,%d)", who, root_a, root_b);
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                      uint64_t *length_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = fitch_check_schedule(e, ops, n_ops, root_a, root_b, "fitch_score_tree")) != PHYLO_OK) return rc;
+  if (!length_out) return fail(e, PHYLO_ERR_ARG, "fitch_score_tree: length_out is NULL");
+  CK(cudaSetDevice(e->device));
+  for (int o = 0; o < n_ops; ++o)
+    if ((rc = fitch_ensure(e, ops[o].parent, false)) != PHYLO_OK) return rc;
+  if ((rc = fitch_sync_tables(e)) != PHYLO_OK) return rc;
+  if ((rc = fitch_cost_capacity(e, (size_t)n_ops + 4)) != PHYLO_OK) return rc;
+  if ((rc = fitch_sched_capacity(e, sizeof(FitchStep) * (size_t)(n_ops + 1))) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  FitchStep *hs = (FitchStep *)e->hSched;
+  for (int o = 0; o < n_ops; ++o) hs[o] = FitchStep{ops[o].parent, ops[o].left, ops[o].right};
+  CK(cudaMemcpyAsync(e->dSched, hs, sizeof(FitchStep) * (size_t)n_ops, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long) * (size_t)(n_ops + 2), e->stream));
+  const int g = grid_for(e->fWords, 128, e->sm_count * 16);
+  const size_t smem = sizeof(unsigned long long) * (size_t)(n_ops + 1);
+  NP_DISPATCH(e->fNPdev, (fitch_tree_kernel<NP><<<g, 128, smem, e->stream>>>(
+                             e->dPreTab, (const FitchStep *)e->dSched, n_ops, root_a, root_b, e->fWords, e->fN,
+                             e->dFW, e->dCost, e->dCost + n_ops + 1)));
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long) * (size_t)(n_ops + 2), cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *length_out = e->hCost[n_ops + 1];
+  for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[o];
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_get_node_costs(phylo_engine *e, uint64_t *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->fT == 0 || !out) return fail(e, PHYLO_ERR_STATE, "fitch_get_node_costs: no Fitch data loaded");
+  for (int s = 0; s < e->fcap; ++s) out[s] = e->nodeCost[s];
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if (e->fT == 0) return fail(e, PHYLO_ERR_STATE, "fitch_uppass: no Fitch data loaded");
+  if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(e, PHYLO_ERR_ARG, "fitch_uppass: bad arguments");
+  if ((rc = fitch_slot_ok(e, root_a, true, "fitch_uppass")) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, root_b, true, "fitch_uppass")) != PHYLO_OK) return rc;
+  std::vector<int> parent_of(e->fcap, -1);
+  for (int o = 0; o < n_ops; ++o) {
+    const phylo_op &op = ops[o];
+    if ((rc = fitch_slot_ok(e, op.parent, true, "fitch_uppass (run the down-pass first)")) != PHYLO_OK) return rc;
+    if ((rc = fitch_slot_ok(e, op.left, true, "fitch_uppass")) != PHYLO_OK) return rc;
+    if ((rc = fitch_slot_ok(e, op.right, true, "fitch_uppass")) != PHYLO_OK) return rc;
+    parent_of[op.left] = op.parent;
+    parent_of[op.right] = op.parent;
+  }
+  CK(cudaSetDevice(e->device));
+  for (int o = 0; o < n_ops; ++o)
+    if ((rc = fitch_ensure(e, ops[o].parent, true)) != PHYLO_OK) return rc;
+  if ((rc = fitch_sync_tables(e)) != PHYLO_OK) return rc;
+  if ((rc = fitch_sched_capacity(e, sizeof(FitchUpStep) * (size_t)(n_ops + 1))) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  FitchUpStep *hs = (FitchUpStep *)e->hSched;
+  for (int o = 0; o < n_ops; ++o) {  // reverse order: parents first
+    const phylo_op &op = ops[n_ops - 1 - o];
+    const bool at_root = (op.parent == root_a || op.parent == root_b);
+    hs[o] = FitchUpStep{op.parent, at_root ? -1 : parent_of[op.parent], op.left, op.right};
+    if (!at_root && parent_of[op.parent] < 0)
+      return fail(e, PHYLO_ERR_ARG, "fitch_uppass: node %d has no parent in the schedule and is not on the root edge", op.parent);
+  }
+  if (n_ops > 0) {
+    CK(cudaMemcpyAsync(e->dSched, hs, sizeof(FitchUpStep) * (size_t)n_ops, cudaMemcpyHostToDevice, e->stream));
+    const int g = grid_for(e->fWords, 128, e->sm_count * 16);
+    NP_DISPATCH(e->fNPdev, (fitch_uppass_kernel<NP><<<g, 128, 0, e->stream>>>(
+                               e->dPreTab, e->dFinTab, (const FitchUpStep *)e->dSched, n_ops, root_a, root_b, e->fWords)));
+    LAUNCH_CHECK();
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_get_states(phylo_engine *e, int node, int which, void *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = fitch_slot_ok(e, node, true, "fitch_get_states")) != PHYLO_OK) return rc;
+  if (!out) return fail(e, PHYLO_ERR_ARG, "fitch_get_states: out is NULL");
+  // leaves keep their observed sets as final sets
+  const uint32_t *src = (which == 1 && e->fFin[node]) ? e->fFin[node] : e->fPre[node];
+  if (which == 1 && !e->fFin[node] && node >= e->fT)
+    return fail(e, PHYLO_ERR_STATE, "fitch_get_states: no final sets for node %d (run fitch_uppass)", node);
+  CK(cudaSetDevice(e->device));
+  const size_t row = (size_t)e->fN * e->felt;
+  if ((rc = fitch_stage(e, row)) != PHYLO_OK) return rc;
+  const int g = grid_for(e->fWords * 32, 256, e->sm_count * 8);
+  switch (e->felt) {
+    case 1: fitch_decode_kernel<uint8_t><<<g, 256, 0, e->stream>>>(src, (uint8_t *)e->dStage, e->fN, e->fWords, e->fNPdev); break;
+    case 2: fitch_decode_kernel<uint16_t><<<g, 256, 0, e->stream>>>(src, (uint16_t *)e->dStage, e->fN, e->fWords, e->fNPdev); break;
+    case 4: fitch_decode_kernel<uint32_t><<<g, 256, 0, e->stream>>>(src, (uint32_t *)e->dStage, e->fN, e->fWords, e->fNPdev); break;
+    default: fitch_decode_kernel<uint64_t><<<g, 256, 0, e->stream>>>(src, (uint64_t *)e->dStage, e->fN, e->fWords, e->fNPdev);
+  }
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out, e->dStage, row, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_set_states(phylo_engine *e, int node, const void *codes) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = fitch_slot_ok(e, node, false, "fitch_set_states")) != PHYLO_OK) return rc;
+  if (!codes) return fail(e, PHYLO_ERR_ARG, "fitch_set_states: codes is NULL");
+  CK(cudaSetDevice(e->device));
+  const size_t row = (size_t)e->fN * e->felt;
+  if ((rc = fitch_stage(e, row)) != PHYLO_OK) return rc;
+  if ((rc = fitch_ensure(e, node, false)) != PHYLO_OK) return rc;
+  if ((rc = fitch_cost_capacity(e, 4)) != PHYLO_OK) return rc;
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
+  CK(cudaMemcpyAsync(e->dStage, codes, row, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = fitch_encode(e, e->dStage, e->fPre[node], e->dCost)) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  return PHYLO_OK;
+}
+
+// ------------------------------------------------------------ bitvector set algebra ----
+static int bv_binop(phylo_engine *e, int dst, int a, int b, bool is_union) {
+  int rc;
+  const char *who = is_union ? "bv_union" : "bv_inter";
+  if ((rc = fitch_slot_ok(e, a, true, who)) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, b, true, who)) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, dst, false, who)) != PHYLO_OK) return rc;
+  CK(cudaSetDevice(e->device));
+  if ((rc = fitch_ensure(e, dst, false)) != PHYLO_OK) return rc;
+  const int64_t n = e->fWords * e->fNPdev;
+  const int g = grid_for(n, 256, e->sm_count * 8);
+  if (is_union) bv_binop_kernel<true><<<g, 256, 0, e->stream>>>(e->fPre[a], e->fPre[b], e->fPre[dst], n);
+  else bv_binop_kernel<false><<<g, 256, 0, e->stream>>>(e->fPre[a], e->fPre[b], e->fPre[dst], n);
+  LAUNCH_CHECK();
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_bv_union(phylo_engine *e, int dst, int a, int b) {
+  if (!e) return PHYLO_ERR_ARG;
+  return bv_binop(e, dst, a, b, true);
+}
+extern "C" int phylo_bv_inter(phylo_engine *e, int dst, int a, int b) {
+  if (!e) return PHYLO_ERR_ARG;
+  return bv_binop(e, dst, a, b, false);
+}
+
+static int bv_count(phylo_engine *e, int a, int mode, uint64_t mask, int n, uint64_t *out, const char *who) {
+  int rc;
+  if ((rc = fitch_slot_ok(e, a, true, who)) != PHYLO_OK) return rc;
+  if (!out) return fail(e, PHYLO_ERR_ARG, "%s: out is NULL", who);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
+  const int g = grid_for(e->fWords, 256, e->sm_count * 8);
+  bv_count_kernel<<<g, 256, 0, e->stream>>>(e->fPre[a], e->fWords, e->fN, e->fNPdev, mode, mask, n, e->dCost);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *out = e->hCost[0];
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_bv_popcount(phylo_engine *e, int a, uint64_t *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  return bv_count(e, a, 0, 0, 0, out, "bv_popcount");
+}
+extern "C" int phylo_bv_saturation(phylo_engine *e, int a, uint64_t state_mask, uint64_t *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  return bv_count(e, a, 1, state_mask, 0, out, "bv_saturation");
+}
+extern "C" int phylo_bv_poly_saturation(phylo_engine *e, int a, int n, uint64_t *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->fT && n > e->felt * 8) {  // lib/bitvector/bv.c:137: n > WIDTH counts nothing
+    if (out) *out = 0;
+    return PHYLO_OK;
+  }
+  return bv_count(e, a, 2, 0, n, out, "bv_poly_saturation");
+}
+
+extern "C" int phylo_bv_compare(phylo_engine *e, int a, int b, int *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = fitch_slot_ok(e, a, true, "bv_compare")) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, b, true, "bv_compare")) != PHYLO_OK) return rc;
+  if (!out) return fail(e, PHYLO_ERR_ARG, "bv_compare: out is NULL");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(e->dCost, 0xff, sizeof(unsigned long long), e->stream));
+  const int g = grid_for(e->fWords, 256, e->sm_count * 8);
+  bv_firstdiff_kernel<<<g, 256, 0, e->stream>>>(e->fPre[a], e->fPre[b], e->fWords, e->fN, e->fNPdev, e->dCost);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const unsigned long long first = e->hCost[0];
+  if (first == ~0ull) { *out = 0; return PHYLO_OK; }
+  // fetch the two differing elements: planes of the word holding `first`
+  const int64_t w = (int64_t)(first / 32);
+  const int bit = (int)(first % 32);
+  std::vector<uint32_t> pa(e->fNPdev), pb(e->fNPdev);
+  CK(cudaMemcpy(pa.data(), e->fPre[a] + w * e->fNPdev, sizeof(uint32_t) * e->fNPdev, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pb.data(), e->fPre[b] + w * e->fNPdev, sizeof(uint32_t) * e->fNPdev, cudaMemcpyDeviceToHost));
+  uint64_t ea = 0, eb = 0;
+  for (int s = 0; s < e->fNPdev; ++s) {
+    ea |= (uint64_t)((pa[s] >> bit) & 1u) << s;
+    eb |= (uint64_t)((pb[s] >> bit) & 1u) << s;
+  }
+  *out = ea > eb ? 1 : -1;  // lib/bitvector/bv.c:82-84
+  return PHYLO_OK;
+}

@@ -1,0 +1,337 @@
+// Fitch / non-additive parsimony and bitvector set-algebra kernels.
+//
+// Device layout: characters are bit-sliced. For each run of 32 characters
+// ("word" w) and each state plane s < NP there is one 32-bit word buf[w*NP + s] whose bit c
+// says "state s is in the set of character 32*w + c". DNA (NP=4) is therefore 16 bytes per
+// 32 characters = 0.5 B/char and one 128-bit access per thread.
+//
+// The rule is the reference's bv_fitch (lib/bitvector/bv.c:148-160; same rule in
+// lib/nonAdditive_c.ml:19-35):  m = a & b;  m == 0 ? (a | b, cost+1) : (m, cost+0),
+// evaluated for 32 characters at once:  any = OR_s(a_s & b_s);  r_s = (a_s & b_s) | (~any &
+// (a_s | b_s));  cost += popc(~any & valid).
+#pragma once
+#include "common.cuh"
+
+namespace phylo {
+
+template <int NP>
+struct Planes {
+  uint32_t v[NP];
+};
+
+template <int NP>
+__device__ __forceinline__ Planes<NP> ld_planes(const uint32_t *buf, int64_t w) {
+  Planes<NP> r;
+  if (NP == 4) {
+    const uint4 t = *(const uint4 *)(buf + w * 4);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int s = 0; s < NP; ++s) r.v[s] = buf[w * NP + s];
+  }
+  return r;
+}
+template <int NP>
+__device__ __forceinline__ void st_planes(uint32_t *buf, int64_t w, const Planes<NP> &r) {
+  if (NP == 4) {
+    *(uint4 *)(buf + w * 4) = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else {
+#pragma unroll
+    for (int s = 0; s < NP; ++s) buf[w * NP + s] = r.v[s];
+  }
+}
+
+__device__ __forceinline__ uint32_t valid_mask(int64_t w, int64_t N) {
+  const int64_t rem = N - w * 32;
+  return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+// returns the changed-character mask
+template <int NP>
+__device__ __forceinline__ uint32_t fitch_rule(const Planes<NP> &a, const Planes<NP> &b,
+                                               Planes<NP> &c) {
+  uint32_t any = 0;
+#pragma unroll
+  for (int s = 0; s < NP; ++s) any |= a.v[s] & b.v[s];
+#pragma unroll
+  for (int s = 0; s < NP; ++s) c.v[s] = (a.v[s] & b.v[s]) | (~any & (a.v[s] | b.v[s]));
+  return ~any;
+}
+
+__device__ __forceinline__ unsigned long long weighted_cost(uint32_t chg, int64_t w,
+                                                            const uint32_t *__restrict__ wt) {
+  unsigned long long c = 0;
+  while (chg) {
+    const int bit = __ffs(chg) - 1;
+    chg &= chg - 1;
+    c += wt[w * 32 + bit];
+  }
+  return c;
+}
+
+__device__ __forceinline__ void block_add_u64(unsigned long long v, unsigned long long *dst) {
+  // warp shuffle -> one shared atomic per warp -> one global atomic per CTA (exact integers)
+  __shared__ unsigned long long acc;
+  if (threadIdx.x == 0) acc = 0;
+  __syncthreads();
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(&acc, v);
+  __syncthreads();
+  if (threadIdx.x == 0 && acc) atomicAdd(dst, acc);
+}
+
+// ------------------------------------------------------- per-node median / distance ----
+// STORE=true: bv_fitch (writes the parent set); STORE=false: bv_distance
+// (lib/bitvector/bv.c:46-55). One thread per 32-character word, grid-strided.
+template <int NP, bool STORE>
+__global__ void __launch_bounds__(256)
+fitch_median2_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                     uint32_t *__restrict__ c, int64_t nwords, int64_t N,
+                     const uint32_t *__restrict__ wt, unsigned long long *__restrict__ cost) {
+  unsigned long long local = 0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    const Planes<NP> pa = ld_planes<NP>(a, w), pb = ld_planes<NP>(b, w);
+    Planes<NP> pc;
+    const uint32_t chg = fitch_rule<NP>(pa, pb, pc) & valid_mask(w, N);
+    if (STORE) st_planes<NP>(c, w, pc);
+    local += wt ? weighted_cost(chg, w, wt) : (unsigned long long)__popc(chg);
+  }
+  block_add_u64(local, cost);
+}
+
+// run-time plane count (any alphabet up to 64 states)
+template <bool STORE>
+__global__ void __launch_bounds__(256)
+fitch_median2_dyn_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                         uint32_t *__restrict__ c, int64_t nwords, int64_t N, int NP,
+                         const uint32_t *__restrict__ wt, unsigned long long *__restrict__ cost) {
+  unsigned long long local = 0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t any = 0;
+    for (int s = 0; s < NP; ++s) any |= a[w * NP + s] & b[w * NP + s];
+    if (STORE)
+      for (int s = 0; s < NP; ++s) {
+        const uint32_t x = a[w * NP + s], y = b[w * NP + s];
+        c[w * NP + s] = (x & y) | (~any & (x | y));
+      }
+    const uint32_t chg = ~any & valid_mask(w, N);
+    local += wt ? weighted_cost(chg, w, wt) : (unsigned long long)__popc(chg);
+  }
+  block_add_u64(local, cost);
+}
+
+// ---------------------------------------------------------------- whole-tree down-pass ----
+// One launch for the entire post-order schedule: every thread carries its 32-character
+// column through all n_ops medians and the root-edge join. A child that is an interior node
+// was written earlier by this same thread, so no inter-thread synchronisation is needed and
+// the re-read is served by L2. Node sets are written once (needed by the up-pass and by
+// get_states). sched[o] = {parent, left, right} slot ids; slots -> buffers through `bufs`.
+struct FitchStep {
+  int parent, left, right;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(128)
+fitch_tree_kernel(uint32_t *const *__restrict__ bufs, const FitchStep *__restrict__ sched, int n_ops,
+                  int root_a, int root_b, int64_t nwords, int64_t N,
+                  const uint32_t *__restrict__ wt, unsigned long long *__restrict__ node_cost,
+                  unsigned long long *__restrict__ total) {
+  extern __shared__ unsigned long long sh_cost[];  // n_ops + 1 per-CTA partial costs
+  for (int o = threadIdx.x; o <= n_ops; o += blockDim.x) sh_cost[o] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x; w0 < nwords;
+       w0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t w = w0 + threadIdx.x;
+    const bool act = w < nwords;
+    const uint32_t valid = act ? valid_mask(w, N) : 0u;
+    for (int o = 0; o <= n_ops; ++o) {
+      int il, ir, ip = -1;
+      if (o < n_ops) {
+        const FitchStep st = sched[o];
+        il = st.left; ir = st.right; ip = st.parent;
+      } else {
+        il = root_a; ir = root_b;
+      }
+      unsigned long long c = 0;
+      if (act) {
+        const Planes<NP> pa = ld_planes<NP>(bufs[il], w), pb = ld_planes<NP>(bufs[ir], w);
+        Planes<NP> pc;
+        const uint32_t chg = fitch_rule<NP>(pa, pb, pc) & valid;
+        if (ip >= 0) st_planes<NP>(bufs[ip], w, pc);
+        c = wt ? weighted_cost(chg, w, wt) : (unsigned long long)__popc(chg);
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+      if (lane == 0 && c) atomicAdd(&sh_cost[o], c);
+    }
+  }
+  __syncthreads();
+  unsigned long long t = 0;
+  for (int o = threadIdx.x; o <= n_ops; o += blockDim.x) {
+    const unsigned long long c = sh_cost[o];
+    if (c) {
+      atomicAdd(&node_cost[o], c);
+      t += c;
+    }
+  }
+  if (t) atomicAdd(total, t);
+}
+
+// ------------------------------------------------------------------------- up-pass ----
+// Final sets, walking the schedule backwards (parents before children). Rule (SURVEY.md
+// section 8 a11; the reference leaves Node.final_states TODO, lib/node.ml:260-268), per character
+// with parent-final A, prelim P, child prelims L, R:
+//   (P & A) == A -> A;  else (L & R) == 0 -> P | A;  else P | (A & (L | R)).
+// The two ends of the root edge take A = root set = (a & b) if non-empty else (a | b).
+// up[o] = {node, parent_or_-1, left, right}; leaves keep their observed sets.
+struct FitchUpStep {
+  int node, parent, left, right;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(128)
+fitch_uppass_kernel(uint32_t *const *__restrict__ prelim, uint32_t *const *__restrict__ fin,
+                    const FitchUpStep *__restrict__ up, int n_up, int root_a, int root_b,
+                    int64_t nwords) {
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    Planes<NP> rootset;
+    {
+      const Planes<NP> a = ld_planes<NP>(prelim[root_a], w), b = ld_planes<NP>(prelim[root_b], w);
+      fitch_rule<NP>(a, b, rootset);
+    }
+    for (int o = 0; o < n_up; ++o) {
+      const FitchUpStep st = up[o];
+      const Planes<NP> P = ld_planes<NP>(prelim[st.node], w);
+      const Planes<NP> L = ld_planes<NP>(prelim[st.left], w), R = ld_planes<NP>(prelim[st.right], w);
+      const Planes<NP> A = st.parent < 0 ? rootset : ld_planes<NP>(fin[st.parent], w);
+      uint32_t notsub = 0, lr = 0;
+#pragma unroll
+      for (int s = 0; s < NP; ++s) {
+        notsub |= A.v[s] & ~P.v[s];
+        lr |= L.v[s] & R.v[s];
+      }
+      Planes<NP> F;
+#pragma unroll
+      for (int s = 0; s < NP; ++s) {
+        const uint32_t f2 = P.v[s] | A.v[s];
+        const uint32_t f3 = P.v[s] | (A.v[s] & (L.v[s] | R.v[s]));
+        F.v[s] = (~notsub & A.v[s]) | (notsub & ((~lr & f2) | (lr & f3)));
+      }
+      st_planes<NP>(fin[st.node], w, F);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- layout transcoding ----
+// reference layout (one character per W-bit element, lib/bitvector/bv.h:29-55) <-> planes.
+// A warp turns 32 consecutive elements into NP plane words with NP ballots.
+template <typename Elt>
+__global__ void __launch_bounds__(256)
+fitch_encode_kernel(const Elt *__restrict__ codes, uint32_t *__restrict__ buf, int64_t N,
+                    int64_t nwords, int NP, unsigned long long *__restrict__ n_bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long bad = 0;
+  for (int64_t w = warp0; w < nwords; w += nwarps) {
+    const int64_t c = w * 32 + lane;
+    const uint64_t e = c < N ? (uint64_t)codes[c] : 0;
+    const uint64_t keep = NP >= 64 ? ~0ull : ((1ull << NP) - 1);
+    if (c < N && (e & keep) == 0) ++bad;
+    uint32_t mine = 0, mine2 = 0;
+    for (int s = 0; s < NP; ++s) {
+      const uint32_t bits = __ballot_sync(0xffffffffu, (e >> s) & 1);
+      if ((s & 31) == lane) {
+        if (s < 32) mine = bits; else mine2 = bits;
+      }
+    }
+    if (lane < NP) buf[w * NP + lane] = mine;
+    if (lane + 32 < NP) buf[w * NP + 32 + lane] = mine2;
+  }
+  if (bad) atomicAdd(n_bad, bad);
+}
+
+template <typename Elt>
+__global__ void __launch_bounds__(256)
+fitch_decode_kernel(const uint32_t *__restrict__ buf, Elt *__restrict__ codes, int64_t N,
+                    int64_t nwords, int NP) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp0; w < nwords; w += nwarps) {
+    uint64_t e = 0;
+    for (int s = 0; s < NP; ++s) e |= (uint64_t)((buf[w * NP + s] >> lane) & 1u) << s;
+    const int64_t c = w * 32 + lane;
+    if (c < N) codes[c] = (Elt)e;
+  }
+}
+
+// ------------------------------------------------------------------ bitvector set ops ----
+// bv_union / bv_inter (lib/bitvector/bv.c:93-99, :112-118): plane-wise OR / AND.
+template <bool UNION>
+__global__ void __launch_bounds__(256)
+bv_binop_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                uint32_t *__restrict__ c, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    c[i] = UNION ? (a[i] | b[i]) : (a[i] & b[i]);
+}
+
+// mode 0: bv_popcount (bv.c:102-108): total number of set state bits.
+// mode 1: bv_saturation (bv.c:121-129): characters whose set intersects `mask`.
+// mode 2: bv_poly_saturation (bv.c:133-144): characters with exactly `n` states set.
+__global__ void __launch_bounds__(256)
+bv_count_kernel(const uint32_t *__restrict__ a, int64_t nwords, int64_t N, int NP, int mode,
+                unsigned long long mask, int n, unsigned long long *__restrict__ out) {
+  unsigned long long local = 0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t valid = valid_mask(w, N);
+    if (mode == 0) {
+      for (int s = 0; s < NP; ++s) local += __popc(a[w * NP + s] & valid);
+    } else if (mode == 1) {
+      uint32_t hit = 0;
+      for (int s = 0; s < NP; ++s)
+        if ((mask >> s) & 1) hit |= a[w * NP + s];
+      local += __popc(hit & valid);
+    } else {
+      // per-character population count across planes: bit-serial counter in 7 bit-planes
+      uint32_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int s = 0; s < NP; ++s) {
+        uint32_t carry = a[w * NP + s];
+        for (int bpl = 0; bpl < 7 && carry; ++bpl) {
+          const uint32_t t = cnt[bpl] & carry;
+          cnt[bpl] ^= carry;
+          carry = t;
+        }
+      }
+      uint32_t eq = valid;
+      for (int bpl = 0; bpl < 7; ++bpl) eq &= ((n >> bpl) & 1) ? cnt[bpl] : ~cnt[bpl];
+      local += __popc(eq);
+    }
+  }
+  block_add_u64(local, out);
+}
+
+// bv_compare (lib/bitvector/bv.c:72-89): lexicographic over characters on the element
+// values. Finds the first differing character index (min-reduce); the host finishes.
+__global__ void __launch_bounds__(256)
+bv_firstdiff_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, int64_t nwords,
+                    int64_t N, int NP, unsigned long long *__restrict__ first) {
+  unsigned long long best = ~0ull;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+       w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t diff = 0;
+    for (int s = 0; s < NP; ++s) diff |= a[w * NP + s] ^ b[w * NP + s];
+    diff &= valid_mask(w, N);
+    if (diff) best = min(best, (unsigned long long)(w * 32 + (__ffs(diff) - 1)));
+  }
+  if (best != ~0ull) atomicMin(first, best);
+}
+
+}  // namespace phylo

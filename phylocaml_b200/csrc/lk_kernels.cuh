@@ -1,0 +1,531 @@
+// Likelihood kernels: P(t) construction, Felsenstein pruning update with per-site rescaling,
+// root-edge site log-likelihood with the canonical site-sum reduction.
+//
+// Data layout in HBM: CLV[node][pattern][k][i] fp64 -- pattern-major, the K*S
+// entries of one pattern contiguous (DNA+G4: 128 B = one cache line); scale[node][pattern]
+// int32; tips stay as state masks (1 B per pattern for S<=8).
+//
+// The arithmetic follows SURVEY.md Appendix C.2 / oracle/phylo_oracle.c; the reference
+// itself has no pruning code (lib/likelihood_c.ml:1-33 is all TODO) -- only P(t)
+// (lib/mlmodel.c:280-342), which pt_build_kernel reproduces including its special cases.
+#pragma once
+#include "common.cuh"
+
+namespace phylo {
+
+// ------------------------------------------------------------------------- pt_build ----
+// P[(b*K+k)][i][j] = sum_m U[i][m] * (exp(lam[m]*tau) * Ui[m][j]),  tau = tlen[b]*rates[k]
+// (gtr, lib/mlmodel.c:325-342) or with U^T in place of U and Ui (sym, :280-302, where tau is
+// first rounded to float as the reference's `const float t` does). tau == -1 -> Q,
+// tau < 1e-10 -> identity. One CTA per (branch, rate class); latency-bound, tiny.
+__global__ void pt_build_kernel(const double *__restrict__ U, const double *__restrict__ lam,
+                                const double *__restrict__ Ui, const double *__restrict__ rates,
+                                const double *__restrict__ tlen, int S, int K,
+                                double *__restrict__ P) {
+  extern __shared__ double sh_e[];
+  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  const bool sym = (Ui == nullptr);
+  double tau = tlen[b] * rates[k];
+  if (sym) tau = (double)(float)tau;
+  const int mode = (tau == -1.0) ? 2 : (tau >= 1e-10 ? 1 : 0);
+  for (int m = threadIdx.x; m < S; m += blockDim.x)
+    sh_e[m] = (mode == 2) ? lam[m] : exp(lam[m] * tau);
+  __syncthreads();
+  double *out = P + (size_t)blockIdx.x * S * S;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, j = idx % S;
+    double acc;
+    if (mode == 0) {
+      acc = (i == j) ? 1.0 : 0.0;
+    } else {
+      acc = 0.0;
+      if (sym) {
+        for (int m = 0; m < S; ++m) acc += U[m * S + i] * (sh_e[m] * U[m * S + j]);
+      } else {
+        for (int m = 0; m < S; ++m) acc += U[i * S + m] * (sh_e[m] * Ui[m * S + j]);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------- 4-state pruning update ----
+// Thread q owns item q = pattern*K + k: the 4 states of one rate class of one pattern, i.e.
+// 32 contiguous bytes, so every warp request is one fully used 1 KB run (256-bit accesses).
+// k = q % K is loop-invariant (the grid stride is a multiple of K), so the two 4x4 P
+// matrices of that rate class stay in registers for the whole kernel. A tip child costs one
+// byte per pattern; its contribution sum_{j in mask} P[i][j] comes from a 16-entry table in
+// shared memory built once per CTA (identical summation order to the oracle).
+// Per-site rescale: the K lanes of a pattern agree by xor-shuffle on max(high word); values
+// are >= 0 so comparing high words as integers is the same test as max < 2^-256.
+template <int K, bool LTIP, bool RTIP, int U>
+__global__ void __launch_bounds__(256)
+prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
+              const void *__restrict__ lsrc, const int32_t *__restrict__ lsc,
+              const void *__restrict__ rsrc, const int32_t *__restrict__ rsc,
+              double *__restrict__ out, int32_t *__restrict__ osc, int64_t N) {
+  static_assert(K == 1 || K == 2 || K == 4 || K == 8 || K == 16, "K must divide the warp");
+  __shared__ d4 tabL[LTIP ? K * 16 : 1];
+  __shared__ d4 tabR[RTIP ? K * 16 : 1];
+  const int k = threadIdx.x % K;
+  double pl[16], pr[16];
+  if (!LTIP) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) pl[e] = Pl[k * 16 + e];
+  }
+  if (!RTIP) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) pr[e] = Pr[k * 16 + e];
+  }
+  if (LTIP || RTIP) {
+    for (int e = threadIdx.x; e < K * 16; e += blockDim.x) {
+      const int kk = e >> 4, m = e & 15;
+      if (LTIP) {
+        double v[4];
+        for (int i = 0; i < 4; ++i) {
+          double a = 0.0;
+          for (int j = 0; j < 4; ++j)
+            if ((m >> j) & 1) a += Pl[kk * 16 + i * 4 + j];
+          v[i] = a;
+        }
+        tabL[e] = d4{v[0], v[1], v[2], v[3]};
+      }
+      if (RTIP) {
+        double v[4];
+        for (int i = 0; i < 4; ++i) {
+          double a = 0.0;
+          for (int j = 0; j < 4; ++j)
+            if ((m >> j) & 1) a += Pr[kk * 16 + i * 4 + j];
+          v[i] = a;
+        }
+        tabR[e] = d4{v[0], v[1], v[2], v[3]};
+      }
+    }
+    __syncthreads();
+  }
+
+  const int64_t total = N * K;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+  const double *lclv = (const double *)lsrc, *rclv = (const double *)rsrc;
+  const uint8_t *ltip = (const uint8_t *)lsrc, *rtip = (const uint8_t *)rsrc;
+
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U; base < total; base += stride) {
+    d4 l[U], r[U];
+    int sc[U];
+    bool act[U];
+    // ---- issue every load of this iteration first (memory-level parallelism)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = base + (int64_t)u * blockDim.x + threadIdx.x;
+      act[u] = q < total;
+      const int64_t p = q / K;
+      sc[u] = 0;
+      if (act[u]) {
+        if (LTIP) {
+          l[u] = tabL[k * 16 + (ltip[p] & 15)];
+        } else {
+          l[u] = ld256_stream(lclv + q * 4);
+          if (k == 0) sc[u] += lsc[p];
+        }
+        if (RTIP) {
+          r[u] = tabR[k * 16 + (rtip[p] & 15)];
+        } else {
+          r[u] = ld256_stream(rclv + q * 4);
+          if (k == 0) sc[u] += rsc[p];
+        }
+      } else {
+        l[u] = d4{0, 0, 0, 0};
+        r[u] = d4{0, 0, 0, 0};
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = base + (int64_t)u * blockDim.x + threadIdx.x;
+      double x[4], y[4];
+      if (LTIP) {
+        x[0] = l[u].x; x[1] = l[u].y; x[2] = l[u].z; x[3] = l[u].w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          x[i] = ((pl[i * 4 + 0] * l[u].x + pl[i * 4 + 1] * l[u].y) + pl[i * 4 + 2] * l[u].z) +
+                 pl[i * 4 + 3] * l[u].w;
+      }
+      if (RTIP) {
+        y[0] = r[u].x; y[1] = r[u].y; y[2] = r[u].z; y[3] = r[u].w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          y[i] = ((pr[i * 4 + 0] * r[u].x + pr[i * 4 + 1] * r[u].y) + pr[i * 4 + 2] * r[u].z) +
+                 pr[i * 4 + 3] * r[u].w;
+      }
+      d4 v{x[0] * y[0], x[1] * y[1], x[2] * y[2], x[3] * y[3]};
+      int h = max(max(hi32(v.x), hi32(v.y)), max(hi32(v.z), hi32(v.w)));
+#pragma unroll
+      for (int off = K / 2; off >= 1; off >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, off));
+      const bool rescale = h < kScaleHiThresh;
+      if (rescale) {
+        const double f = 0x1p+256;
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+      }
+      if (act[u]) {
+        st256(out + q * 4, v);
+        if (k == 0) osc[q / K] = sc[u] + (rescale ? 1 : 0);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------- 4-state root-edge lnL ----
+// site likelihood l_s = sum_k probs[k] sum_i pi_i La[k,i] (sum_j P_k[i,j] Lb[k,j]); then
+// ln l_s - c_s*256 ln2 (or the +pinvar form), times the pattern weight, folded per block of
+// 1024 patterns in the canonical shape. One CTA per 1024-pattern block (grid-strided).
+template <int K, bool ATIP, bool BTIP>
+__global__ void __launch_bounds__(256)
+root4_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
+             const double *__restrict__ probs, double pinvar, const uint8_t *__restrict__ inv,
+             const void *__restrict__ asrc, const int32_t *__restrict__ asc,
+             const void *__restrict__ bsrc, const int32_t *__restrict__ bsc,
+             const double *__restrict__ weights, double *__restrict__ site_lnl,
+             double *__restrict__ partials, int64_t N) {
+  __shared__ double vals[kLnlBlock];
+  __shared__ double wsum[32];
+  const int k = threadIdx.x % K;
+  double pm[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) pm[e] = Proot[k * 16 + e];
+  const double pi0 = pi[0], pi1 = pi[1], pi2 = pi[2], pi3 = pi[3], pk = probs[k];
+  const int64_t nblocks = (N + kLnlBlock - 1) / kLnlBlock;
+  const double *aclv = (const double *)asrc, *bclv = (const double *)bsrc;
+  const uint8_t *atip = (const uint8_t *)asrc, *btip = (const uint8_t *)bsrc;
+
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    for (int it = 0; it < kLnlBlock * K; it += blockDim.x) {
+      const int ql = it + threadIdx.x;
+      const int plocal = ql / K;
+      const int64_t p = blk * kLnlBlock + plocal;
+      const bool act = p < N;
+      d4 a{0, 0, 0, 0}, b{0, 0, 0, 0};
+      int c = 0;
+      if (act) {
+        const int64_t q = p * K + k;
+        if (ATIP) {
+          const int m = atip[p];
+          a = d4{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
+        } else {
+          a = ld256_stream(aclv + q * 4);
+          if (k == 0) c += asc[p];
+        }
+        if (BTIP) {
+          const int m = btip[p];
+          b = d4{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
+        } else {
+          b = ld256_stream(bclv + q * 4);
+          if (k == 0) c += bsc[p];
+        }
+      }
+      double y0 = ((pm[0] * b.x + pm[1] * b.y) + pm[2] * b.z) + pm[3] * b.w;
+      double y1 = ((pm[4] * b.x + pm[5] * b.y) + pm[6] * b.z) + pm[7] * b.w;
+      double y2 = ((pm[8] * b.x + pm[9] * b.y) + pm[10] * b.z) + pm[11] * b.w;
+      double y3 = ((pm[12] * b.x + pm[13] * b.y) + pm[14] * b.z) + pm[15] * b.w;
+      double lk = (((pi0 * a.x) * y0 + (pi1 * a.y) * y1) + (pi2 * a.z) * y2) + (pi3 * a.w) * y3;
+      double l = pk * lk;
+#pragma unroll
+      for (int off = 1; off < K; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+      if (k == 0) {
+        double wl = 0.0;
+        if (act) {
+          double lnl;
+          if (pinvar >= 0.0) {
+            const int m = inv[p];
+            const double pv = (m & 1 ? pi0 : 0.0) + (m & 2 ? pi1 : 0.0) + (m & 4 ? pi2 : 0.0) +
+                              (m & 8 ? pi3 : 0.0);
+            lnl = log((1.0 - pinvar) * ldexp(l, -kScaleExp * c) + pinvar * pv);
+          } else {
+            lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
+          }
+          if (site_lnl) site_lnl[p] = lnl;
+          wl = (weights ? weights[p] : 1.0) * lnl;
+        }
+        vals[plocal] = wl;
+      }
+    }
+    __syncthreads();
+    const double r = block_fold_1024(vals, wsum);
+    if (threadIdx.x == 0) partials[blk] = r;
+    __syncthreads();
+  }
+}
+
+// One more level of the canonical reduction: out[b] = fold(in[b*1024 .. b*1024+1023]).
+__global__ void __launch_bounds__(256)
+reduce1024_kernel(const double *__restrict__ in, int64_t n, double *__restrict__ out) {
+  __shared__ double vals[kLnlBlock];
+  __shared__ double wsum[32];
+  const int64_t lo = (int64_t)blockIdx.x * kLnlBlock;
+  for (int i = threadIdx.x; i < kLnlBlock; i += blockDim.x) vals[i] = (lo + i < n) ? in[lo + i] : 0.0;
+  __syncthreads();
+  const double r = block_fold_1024(vals, wsum);
+  if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+
+// -------------------------------------------------- any-S pruning update (20, 61, ...) ----
+// One CTA = a tile of TP patterns (one per thread), looping over rate classes. Per class the
+// two transition matrices (stored transposed, rows padded to a multiple of 4, so a thread
+// fetches P[i..i+3][j] with one broadcast 32-byte read) and the two child tiles are staged in
+// shared memory with coalesced loads; each thread then pulls its own child row into
+// registers and runs 4 independent fp64 FMA chains per matrix row block. Rows in shared
+// memory are padded to an odd number of doubles (conflict-free 64-bit column access).
+// ST > 0: compile-time S (child row in registers); ST == 0: run-time S (row read from smem).
+template <typename MaskT>
+__device__ __forceinline__ void stage_tile(double *tile, int SP, const void *src, bool tip, int S,
+                                           int K, int k, int64_t p0, int np) {
+  if (tip) {
+    const MaskT *m = (const MaskT *)src;
+    for (int idx = threadIdx.x; idx < np * S; idx += blockDim.x) {
+      const int r = idx / S, j = idx - r * S;
+      tile[r * SP + j] = (double)((m[p0 + r] >> j) & 1);
+    }
+  } else {
+    const double *clv = (const double *)src;
+    for (int idx = threadIdx.x; idx < np * S; idx += blockDim.x) {
+      const int r = idx / S, j = idx - r * S;
+      tile[r * SP + j] = clv[((p0 + r) * K + k) * S + j];
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_pt(double *pt, const double *P, int S, int S4) {
+  // pt[j*S4 + i] = P[i][j], zero padded in i
+  for (int idx = threadIdx.x; idx < S * S4; idx += blockDim.x) {
+    const int j = idx / S4, i = idx - j * S4;
+    pt[idx] = (i < S) ? P[i * S + j] : 0.0;
+  }
+}
+
+// y[i0..i0+3] = sum_j P[i][j] * row[j]. With a compile-time S the j loop is fully unrolled so
+// the child row really lives in registers (a partially unrolled loop would index it
+// dynamically and push it to local memory).
+template <int ST>
+__device__ __forceinline__ void matvec4(const double *pt, int S, int S4, int i0, const double *rowreg,
+                                        const double *rowsm, double acc[4]) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+  if constexpr (ST > 0) {
+    constexpr int S4c = (ST + 3) & ~3;
+    const double *pp = pt + i0;
+#pragma unroll
+    for (int j = 0; j < ST; ++j) {
+      const double a = rowreg[j];
+      const double2 p01 = *(const double2 *)(pp + j * S4c);
+      const double2 p23 = *(const double2 *)(pp + j * S4c + 2);
+      acc[0] += p01.x * a;
+      acc[1] += p01.y * a;
+      acc[2] += p23.x * a;
+      acc[3] += p23.y * a;
+    }
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < S; ++j) {
+      const double a = rowsm[j];
+      const double2 p01 = *(const double2 *)(pt + j * S4 + i0);
+      const double2 p23 = *(const double2 *)(pt + j * S4 + i0 + 2);
+      acc[0] += p01.x * a;
+      acc[1] += p01.y * a;
+      acc[2] += p23.x * a;
+      acc[3] += p23.y * a;
+    }
+  }
+}
+
+template <int ST, typename MaskT, int TP>
+__global__ void __launch_bounds__(TP)
+prune_any_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
+                 const void *__restrict__ lsrc, const int32_t *__restrict__ lsc, bool ltip,
+                 const void *__restrict__ rsrc, const int32_t *__restrict__ rsc, bool rtip,
+                 double *__restrict__ out, int32_t *__restrict__ osc, int64_t N, int S, int K) {
+  extern __shared__ __align__(16) double smem[];
+  const int SS = ST > 0 ? ST : S;
+  const int S4 = (SS + 3) & ~3, SP = SS | 1;
+  double *ptl = smem, *ptr_ = ptl + SS * S4, *tl = ptr_ + SS * S4, *tr = tl + TP * SP;
+  const int64_t ntiles = (N + TP - 1) / TP;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t p0 = tile * TP;
+    const int np = (int)min((int64_t)TP, N - p0);
+    const bool act = threadIdx.x < np;
+    int hmax = (int)0x80000000;
+    for (int k = 0; k < K; ++k) {
+      __syncthreads();  // previous class / tile fully consumed
+      stage_pt(ptl, Pl + (size_t)k * SS * SS, SS, S4);
+      stage_pt(ptr_, Pr + (size_t)k * SS * SS, SS, S4);
+      stage_tile<MaskT>(tl, SP, lsrc, ltip, SS, K, k, p0, np);
+      stage_tile<MaskT>(tr, SP, rsrc, rtip, SS, K, k, p0, np);
+      __syncthreads();
+      double *myl = tl + threadIdx.x * SP, *myr = tr + threadIdx.x * SP;
+      double row[ST > 0 ? ST : 1];
+      if (act) {
+        if (ST > 0) {
+#pragma unroll
+          for (int j = 0; j < ST; ++j) row[j] = myl[j];
+        }
+        // x_i overwrite this thread's own left row in shared memory (it is in registers
+        // by now); the products x_i*y_i then overwrite its right row, which becomes the
+        // output tile for the coalesced store below.
+        if (ST > 0) {
+          for (int i0 = 0; i0 < SS; i0 += 4) {
+            double acc[4];
+            matvec4<ST>(ptl, SS, S4, i0, row, myl, acc);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i0 + u < SS) myl[i0 + u] = acc[u];
+          }
+#pragma unroll
+          for (int j = 0; j < ST; ++j) row[j] = myr[j];
+          for (int i0 = 0; i0 < SS; i0 += 4) {
+            double acc[4];
+            matvec4<ST>(ptr_, SS, S4, i0, row, myr, acc);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i0 + u < SS) {
+                const double v = myl[i0 + u] * acc[u];
+                myr[i0 + u] = v;
+                hmax = max(hmax, hi32(v));
+              }
+          }
+        }
+      }
+      if (ST == 0) {
+        // run-time S: results cannot overwrite the rows they are computed from, so they go
+        // to global directly (each thread its own pattern row; L2 absorbs the stride)
+        if (act) {
+          double *o = out + ((p0 + threadIdx.x) * K + k) * SS;
+          for (int i0 = 0; i0 < SS; i0 += 4) {
+            double ax[4], ay[4];
+            matvec4<0>(ptl, SS, S4, i0, nullptr, myl, ax);
+            matvec4<0>(ptr_, SS, S4, i0, nullptr, myr, ay);
+            for (int u = 0; u < 4; ++u)
+              if (i0 + u < SS) {
+                const double v = ax[u] * ay[u];
+                o[i0 + u] = v;
+                hmax = max(hmax, hi32(v));
+              }
+          }
+        }
+      } else {
+        __syncthreads();
+        // coalesced store of the output tile (held in the right-child tile)
+        for (int idx = threadIdx.x; idx < np * SS; idx += blockDim.x) {
+          const int r = idx / SS, j = idx - r * SS;
+          out[((p0 + r) * K + k) * SS + j] = tr[r * SP + j];
+        }
+      }
+    }
+    __syncthreads();  // this CTA's global writes visible to its own threads
+    if (act) {
+      const int64_t p = p0 + threadIdx.x;
+      int c = (ltip ? 0 : lsc[p]) + (rtip ? 0 : rsc[p]);
+      if (hmax < kScaleHiThresh) {  // rare: rescale the K*S entries in place
+        double *o = out + p * K * SS;
+        for (int e = 0; e < K * SS; ++e) o[e] *= 0x1p+256;
+        c += 1;
+      }
+      osc[p] = c;
+    }
+  }
+}
+
+template <int ST, typename MaskT, int TP>
+__global__ void __launch_bounds__(TP)
+root_any_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
+                const double *__restrict__ probs, double pinvar, const MaskT *__restrict__ inv,
+                const void *__restrict__ asrc, const int32_t *__restrict__ asc, bool atip,
+                const void *__restrict__ bsrc, const int32_t *__restrict__ bsc, bool btip,
+                const double *__restrict__ weights, double *__restrict__ site_lnl,
+                double *__restrict__ partials, int64_t N, int S, int K) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double vals[kLnlBlock];
+  __shared__ double wsum[32];
+  const int SS = ST > 0 ? ST : S;
+  const int S4 = (SS + 3) & ~3, SP = SS | 1;
+  double *pt = smem, *ta = pt + SS * S4, *tb = ta + TP * SP, *spi = tb + TP * SP;
+  for (int i = threadIdx.x; i < SS; i += blockDim.x) spi[i] = pi[i];
+  const int64_t nblocks = (N + kLnlBlock - 1) / kLnlBlock;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    for (int sub = 0; sub < kLnlBlock / TP; ++sub) {
+      const int64_t p0 = blk * kLnlBlock + (int64_t)sub * TP;
+      const int np = (int)max((int64_t)0, min((int64_t)TP, N - p0));
+      const bool act = threadIdx.x < np;
+      double l = 0.0;
+      for (int k = 0; k < K; ++k) {
+        __syncthreads();
+        stage_pt(pt, Proot + (size_t)k * SS * SS, SS, S4);
+        stage_tile<MaskT>(ta, SP, asrc, atip, SS, K, k, p0, np);
+        stage_tile<MaskT>(tb, SP, bsrc, btip, SS, K, k, p0, np);
+        __syncthreads();
+        if (act) {
+          const double *mya = ta + threadIdx.x * SP, *myb = tb + threadIdx.x * SP;
+          double row[ST > 0 ? ST : 1];
+          if (ST > 0) {
+#pragma unroll
+            for (int j = 0; j < ST; ++j) row[j] = myb[j];
+          }
+          double lk = 0.0;
+          for (int i0 = 0; i0 < SS; i0 += 4) {
+            double acc[4];
+            matvec4<ST>(pt, SS, S4, i0, row, myb, acc);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i0 + u < SS) lk += (spi[i0 + u] * mya[i0 + u]) * acc[u];
+          }
+          l += probs[k] * lk;
+        }
+      }
+      double wl = 0.0;
+      if (act) {
+        const int64_t p = p0 + threadIdx.x;
+        const int c = (atip ? 0 : asc[p]) + (btip ? 0 : bsc[p]);
+        double lnl;
+        if (pinvar >= 0.0) {
+          const MaskT m = inv[p];
+          double pv = 0.0;
+          for (int i = 0; i < SS; ++i)
+            if ((m >> i) & 1) pv += spi[i];
+          lnl = log((1.0 - pinvar) * ldexp(l, -kScaleExp * c) + pinvar * pv);
+        } else {
+          lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
+        }
+        if (site_lnl) site_lnl[p] = lnl;
+        wl = (weights ? weights[p] : 1.0) * lnl;
+      }
+      vals[sub * TP + threadIdx.x] = wl;
+    }
+    __syncthreads();
+    const double r = block_fold_1024(vals, wsum);
+    if (threadIdx.x == 0) partials[blk] = r;
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------- tip preparation ----
+// Converts raw tip masks of any element width to the device width, masks off bits >= S,
+// counts invalid (empty) masks and builds the per-pattern AND over all tips (used by the
+// invariant-sites term).
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256)
+tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, OutT *__restrict__ inv,
+                    int T, int64_t N, int S, unsigned long long *__restrict__ n_bad) {
+  const uint64_t keep = (S >= 64) ? ~0ull : ((1ull << S) - 1);
+  unsigned long long bad = 0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t all = keep;
+    for (int t = 0; t < T; ++t) {
+      const uint64_t m = (uint64_t)in[(int64_t)t * N + p] & keep;
+      out[(int64_t)t * N + p] = (OutT)m;
+      if (m == 0) ++bad;
+      all &= m;
+    }
+    inv[p] = (OutT)all;
+  }
+  if (bad) atomicAdd(n_bad, bad);
+}
+
+}  // namespace phylo

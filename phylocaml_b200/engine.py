@@ -1,0 +1,338 @@
+"""ctypes binding of the C ABI in include/phylo_engine.h (libphyloc_b200.so).
+
+This is the same surface the OCaml stubs (stubs/phylo_stubs.c) bind; Python is only the
+harness language of this repository (tests, bench). There is no fallback of any kind: if the
+shared library is missing, importing `load()` raises; if no CUDA device is usable,
+`Engine()` raises with the library's own message.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libphyloc_b200.so")
+
+OP_DTYPE = np.dtype(
+    [("parent", "<i4"), ("left", "<i4"), ("right", "<i4"), ("pad_", "<i4"),
+     ("t_left", "<f8"), ("t_right", "<f8")], align=True)
+assert OP_DTYPE.itemsize == 32
+
+PHYLO_OK = 0
+ERR_NAMES = {-1: "PHYLO_ERR_CUDA", -2: "PHYLO_ERR_ARG", -3: "PHYLO_ERR_STATE", -4: "PHYLO_ERR_DATA",
+             -5: "PHYLO_ERR_NUMERIC", -6: "PHYLO_ERR_UNSUPPORTED"}
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+_i64 = C.c_int64
+_u64p = C.POINTER(C.c_uint64)
+
+# name -> (restype, argtypes); every symbol include/phylo_engine.h declares
+SIGNATURES = {
+    "phylo_engine_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "phylo_engine_destroy": (None, [_vp]),
+    "phylo_last_error": (C.c_char_p, [_vp]),
+    "phylo_engine_set_stream": (C.c_int, [_vp, _vp]),
+    "phylo_engine_sync": (C.c_int, [_vp]),
+    "phylo_engine_launch_count": (C.c_uint64, [_vp]),
+    "phylo_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
+    "phylo_host_free": (C.c_int, [_vp]),
+    "phylo_diagonalize_sym": (C.c_int, [_dp, _dp, C.c_int]),
+    "phylo_diagonalize_gtr": (C.c_int, [_dp, _dp, _dp, C.c_int]),
+    "phylo_compose_sym": (C.c_int, [_vp, _dp, _dp, C.c_double, C.c_int, _dp]),
+    "phylo_compose_gtr": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
+    "phylo_lk_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
+    "phylo_lk_set_tips": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int]),
+    "phylo_lk_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]),
+    "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
+    "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
+    "phylo_lk_get_clv": (C.c_int, [_vp, C.c_int, _dp, _vp]),
+    "phylo_lk_get_site_lnl": (C.c_int, [_vp, _dp]),
+    "phylo_lk_get_block_partials": (C.c_int, [_vp, _dp, C.POINTER(_i64)]),
+    "phylo_reduce_partials": (C.c_double, [_dp, _i64]),
+    "phylo_fitch_set_tips": (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, _vp, _dp, C.c_int]),
+    "phylo_fitch_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _u64p]),
+    "phylo_fitch_distance": (C.c_int, [_vp, C.c_int, C.c_int, _u64p]),
+    "phylo_fitch_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _u64p]),
+    "phylo_fitch_get_node_costs": (C.c_int, [_vp, _u64p]),
+    "phylo_fitch_uppass": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "phylo_fitch_get_states": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "phylo_fitch_set_states": (C.c_int, [_vp, C.c_int, _vp]),
+    "phylo_bv_union": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "phylo_bv_inter": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "phylo_bv_popcount": (C.c_int, [_vp, C.c_int, _u64p]),
+    "phylo_bv_saturation": (C.c_int, [_vp, C.c_int, C.c_uint64, _u64p]),
+    "phylo_bv_poly_saturation": (C.c_int, [_vp, C.c_int, C.c_int, _u64p]),
+    "phylo_bv_compare": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+}
+
+_lib = None
+
+
+class PhyloError(RuntimeError):
+    """A C-ABI call returned non-zero (the OCaml stubs raise `Failure msg` for the same)."""
+
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERR_NAMES.get(code, str(code)), msg))
+        self.code = code
+
+
+def load():
+    """dlopen the product library and declare every entry point. Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _p(a, typ=_vp):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def make_ops(parent, left, right, t_left=None, t_right=None):
+    ops = np.zeros(len(parent), dtype=OP_DTYPE)
+    ops["parent"], ops["left"], ops["right"] = parent, left, right
+    ops["t_left"] = 0.0 if t_left is None else t_left
+    ops["t_right"] = 0.0 if t_right is None else t_right
+    return ops
+
+
+def diagonalize(Q, sym):
+    """MlModel.diagonalize (lib/mlModel.ml:554-583): returns (U, D, Ui or None)."""
+    lib = load()
+    n = Q.shape[0]
+    U = np.array(Q, dtype=np.float64, order="C", copy=True)
+    D = np.zeros((n, n))
+    if sym:
+        rc = lib.phylo_diagonalize_sym(_p(U, _dp), _p(D, _dp), n)
+        Ui = None
+    else:
+        Ui = np.zeros((n, n))
+        rc = lib.phylo_diagonalize_gtr(_p(U, _dp), _p(D, _dp), _p(Ui, _dp), n)
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "diagonalize failed (complex eigenvalues / not convergent / NaN)")
+    return U, D, Ui
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory from phylo_host_alloc."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = _vp()
+    rc = lib.phylo_host_alloc(C.byref(ptr), max(nbytes, 1))
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "phylo_host_alloc(%d bytes) failed" % nbytes)
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = ptr.value
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    ptr = _PINNED.pop(arr.ctypes.data, None)
+    if ptr is not None:
+        load().phylo_host_free(_vp(ptr))
+
+
+class Engine:
+    """One engine handle = one GPU. Thin, 1:1 over the C ABI."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.phylo_engine_create(device, C.byref(h))
+        if rc != PHYLO_OK:
+            raise PhyloError(rc, self.lib.phylo_last_error(None).decode())
+        self.h = h
+        self.lk_shape = None
+        self.fitch_shape = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phylo_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != PHYLO_OK:
+            raise PhyloError(rc, self.lib.phylo_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.phylo_engine_set_stream(self.h, _vp(cuda_stream_ptr)))
+
+    def sync(self):
+        self._ck(self.lib.phylo_engine_sync(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.phylo_engine_launch_count(self.h))
+
+    # ---- MlModel
+    def compose(self, U, D, Ui, t):
+        U, D = _f64(U), _f64(D)
+        n = U.shape[0]
+        P = np.empty((n, n))
+        if Ui is None:
+            self._ck(self.lib.phylo_compose_sym(self.h, _p(U, _dp), _p(D, _dp), float(t), n, _p(P, _dp)))
+        else:
+            Ui = _f64(Ui)
+            self._ck(self.lib.phylo_compose_gtr(self.h, _p(U, _dp), _p(D, _dp), _p(Ui, _dp), float(t), n,
+                                                _p(P, _dp)))
+        return P
+
+    # ---- Likelihood
+    def lk_set_model(self, model):
+        S, K = int(model["S"]), int(model["K"])
+        U, D = _f64(model["U"]), _f64(model["D"])
+        if D.ndim == 1:
+            D = _f64(np.diag(D))
+        Ui = model.get("Ui")
+        Ui = None if Ui is None else _f64(Ui)
+        pi, rates, probs = _f64(model["pi"]), _f64(model["rates"]), _f64(model["probs"])
+        pinvar = model.get("pinvar")
+        pinvar = -1.0 if pinvar is None else float(pinvar)
+        self._ck(self.lib.phylo_lk_set_model(self.h, S, K, _p(U, _dp), _p(D, _dp), _p(Ui, _dp), _p(pi, _dp),
+                                             _p(rates, _dp), _p(probs, _dp), pinvar))
+        self.S, self.K = S, K
+
+    def lk_set_tips(self, tips, weights=None, capacity=None):
+        tips = np.ascontiguousarray(tips)
+        T, N = tips.shape
+        capacity = 2 * T if capacity is None else capacity
+        w = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_lk_set_tips(self.h, T, N, _p(tips), tips.dtype.itemsize, _p(w, _dp), capacity))
+        self.lk_shape = (T, N, capacity)
+
+    def lk_median_2(self, parent, left, t_left, right, t_right):
+        self._ck(self.lib.phylo_lk_median_2(self.h, parent, left, float(t_left), right, float(t_right)))
+
+    def lk_score_tree(self, ops, root_a, root_b, root_t):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        out = C.c_double()
+        self._ck(self.lib.phylo_lk_score_tree(self.h, _p(ops), len(ops), root_a, root_b, float(root_t),
+                                              C.byref(out)))
+        return out.value
+
+    def lk_edge_lnl(self, a, b, ts):
+        ts = _f64(np.atleast_1d(ts))
+        out = np.empty(ts.size)
+        self._ck(self.lib.phylo_lk_edge_lnl(self.h, a, b, _p(ts, _dp), ts.size, _p(out, _dp)))
+        return out
+
+    def lk_get_clv(self, node):
+        T, N, _ = self.lk_shape
+        clv = np.empty((N, self.K, self.S))
+        sc = np.empty(N, dtype=np.int32)
+        self._ck(self.lib.phylo_lk_get_clv(self.h, node, _p(clv, _dp), _p(sc)))
+        return clv, sc
+
+    def lk_get_site_lnl(self):
+        out = np.empty(self.lk_shape[1])
+        self._ck(self.lib.phylo_lk_get_site_lnl(self.h, _p(out, _dp)))
+        return out
+
+    def lk_get_block_partials(self):
+        n = _i64()
+        self._ck(self.lib.phylo_lk_get_block_partials(self.h, None, C.byref(n)))
+        out = np.empty(n.value)
+        self._ck(self.lib.phylo_lk_get_block_partials(self.h, _p(out, _dp), C.byref(n)))
+        return out
+
+    def reduce_partials(self, partials):
+        partials = _f64(partials)
+        return self.lib.phylo_reduce_partials(_p(partials, _dp), partials.size)
+
+    # ---- NonAdditive / Bitvector
+    def fitch_set_tips(self, codes, n_states, weights=None, capacity=None):
+        codes = np.ascontiguousarray(codes)
+        T, N = codes.shape
+        capacity = 2 * T if capacity is None else capacity
+        w = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_fitch_set_tips(self.h, T, N, codes.dtype.itemsize, n_states, _p(codes),
+                                               _p(w, _dp), capacity))
+        self.fitch_shape = (T, N, capacity)
+        self.fitch_dtype = codes.dtype
+
+    def fitch_median_2(self, parent, left, right):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_fitch_median_2(self.h, parent, left, right, C.byref(out)))
+        return out.value
+
+    def fitch_distance(self, a, b):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_fitch_distance(self.h, a, b, C.byref(out)))
+        return out.value
+
+    def fitch_score_tree(self, ops, root_a, root_b):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_fitch_score_tree(self.h, _p(ops), len(ops), root_a, root_b, C.byref(out)))
+        return out.value
+
+    def fitch_get_node_costs(self):
+        out = np.zeros(self.fitch_shape[2], dtype=np.uint64)
+        self._ck(self.lib.phylo_fitch_get_node_costs(self.h, _p(out, _u64p)))
+        return out
+
+    def fitch_uppass(self, ops, root_a, root_b):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        self._ck(self.lib.phylo_fitch_uppass(self.h, _p(ops), len(ops), root_a, root_b))
+
+    def fitch_get_states(self, node, final=False):
+        out = np.empty(self.fitch_shape[1], dtype=self.fitch_dtype)
+        self._ck(self.lib.phylo_fitch_get_states(self.h, node, 1 if final else 0, _p(out)))
+        return out
+
+    def fitch_set_states(self, node, codes):
+        codes = np.ascontiguousarray(codes, dtype=self.fitch_dtype)
+        assert codes.size == self.fitch_shape[1]
+        self._ck(self.lib.phylo_fitch_set_states(self.h, node, _p(codes)))
+
+    def bv_union(self, dst, a, b):
+        self._ck(self.lib.phylo_bv_union(self.h, dst, a, b))
+
+    def bv_inter(self, dst, a, b):
+        self._ck(self.lib.phylo_bv_inter(self.h, dst, a, b))
+
+    def bv_popcount(self, a):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_bv_popcount(self.h, a, C.byref(out)))
+        return out.value
+
+    def bv_saturation(self, a, state_mask):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_bv_saturation(self.h, a, int(state_mask), C.byref(out)))
+        return out.value
+
+    def bv_poly_saturation(self, a, n):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_bv_poly_saturation(self.h, a, int(n), C.byref(out)))
+        return out.value
+
+    def bv_compare(self, a, b):
+        out = C.c_int()
+        self._ck(self.lib.phylo_bv_compare(self.h, a, b, C.byref(out)))
+        return out.value

@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on the same
+seeded inputs. Tolerances: Fitch sets/lengths and scale counters bit-exact; lnL <= 1e-9
+relative (BASELINE.json north_star); CLV entries <= 1e-12 relative; P(t) <= 1e-12 absolute."""
+import numpy as np
+import pytest
+
+from helpers import aa_model, codon_model, dna_gtr_g4, mask_dtype, rel_err, setup_lk
+from phylocaml_b200 import engine, mlmodel, tree
+
+pytestmark = pytest.mark.gpu
+
+LNL_RTOL = 1e-9
+CLV_RTOL = 1e-12
+PT_ATOL = 1e-12
+
+
+# ------------------------------------------------------------------------- P(t) ----
+@pytest.mark.parametrize("t", [0.1, 0.5, 2.0, 100.0, -1.0, 0.0, 1e-11, 2.2250738585072014e-308])
+def test_compose_gtr_matches_oracle(eng, oracle, t):
+    m = dna_gtr_g4()
+    P = eng.compose(m["U"], m["D"], m["Ui"], t)
+    assert np.abs(P - oracle.compose(m["U"], m["D"], m["Ui"], t)).max() <= PT_ATOL
+
+
+@pytest.mark.parametrize("S,t", [(20, 0.3), (61, 0.05), (61, 1.7)])
+def test_compose_large_alphabets(eng, oracle, S, t):
+    m = aa_model(1) if S == 20 else codon_model()
+    P = eng.compose(m["U"], m["D"], m["Ui"], t)
+    assert np.abs(P - oracle.compose(m["U"], m["D"], m["Ui"], t)).max() <= PT_ATOL
+    assert np.abs(P.sum(1) - 1).max() < 1e-12
+
+
+@pytest.mark.parametrize("t", [0.1, 0.37, -1.0, 0.0])
+def test_compose_sym_float_quirk(eng, oracle, t):
+    # lib/mlmodel.c:280: compose_sym takes `float t`
+    m = mlmodel.create(("K2P", 0.4), 4)
+    assert m["Ui"] is None
+    P = eng.compose(m["U"], m["D"], None, t)
+    assert np.abs(P - oracle.compose(m["U"], m["D"], None, t)).max() <= PT_ATOL
+
+
+# ------------------------------------------------------------------- likelihood ----
+def _check_lk(eng, oracle, model, T, N, seed=1, weights=None, tree_kind="random", mean_bl=0.1,
+              check_clv=True):
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(T, N, model, seed, tree_kind, mean_bl)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, weights=weights, capacity=n_nodes)
+    lnl = eng.lk_score_tree(ops, ra, rb, rt)
+    want = oracle.lk_score_tree(model, tips, weights, ops, n_nodes, ra, rb, rt, want_clv=check_clv)
+    assert np.isfinite(lnl)
+    assert rel_err(lnl, want["lnl"]) <= LNL_RTOL, (lnl, want["lnl"])
+    site = eng.lk_get_site_lnl()
+    assert np.abs(site - want["site_lnl"]).max() <= 1e-9 * np.abs(want["site_lnl"]).max()
+    if check_clv:
+        for op in ops[[0, len(ops) // 2, len(ops) - 1]]:
+            clv, sc = eng.lk_get_clv(int(op["parent"]))
+            w = want["clv"][op["parent"]]
+            assert np.array_equal(sc, want["scale"][op["parent"]])
+            assert np.abs(clv - w).max() <= CLV_RTOL * np.abs(w).max()
+    return lnl, want
+
+
+def test_lk_dna_cfg1(eng, oracle):
+    """BASELINE config 1: DNA GTR+G4, 16 taxa x 10k sites."""
+    _check_lk(eng, oracle, dna_gtr_g4(), 16, 10000)
+
+
+def test_lk_dna_ref_literal_rates(eng, oracle):
+    """lib/mlModel.ml:93-99 literal Gamma rates: r0 = 0 => identity P for class 0."""
+    m = dna_gtr_g4(rates="ref_literal")
+    assert m["rates"][0] == 0.0
+    _check_lk(eng, oracle, m, 12, 3000)
+
+
+@pytest.mark.parametrize("N", [1, 31, 1024, 1025, 4097])
+def test_lk_dna_ragged_sizes(eng, oracle, N):
+    _check_lk(eng, oracle, dna_gtr_g4(), 8, N, seed=7)
+
+
+@pytest.mark.parametrize("K", [1, 2, 8])
+def test_lk_dna_other_rate_counts(eng, oracle, K):
+    sv = ("gamma", K, 0.8) if K > 1 else None
+    m = mlmodel.create(("HKY85", 2.0), 4, pi=[0.1, 0.2, 0.3, 0.4], site_var=sv)
+    _check_lk(eng, oracle, m, 10, 2500, seed=3)
+
+
+def test_lk_dna_k3_uses_generic_kernel(eng, oracle):
+    m = mlmodel.create(("GTR", [1.0, 2.5, 0.8, 1.2, 3.0]), 4, pi=[0.3, 0.2, 0.25, 0.25],
+                       site_var=("gamma", 3, 0.6))
+    _check_lk(eng, oracle, m, 9, 1500, seed=5)
+
+
+def test_lk_dna_weights(eng, oracle):
+    rng = np.random.default_rng(11)
+    _check_lk(eng, oracle, dna_gtr_g4(), 16, 5000, weights=rng.integers(1, 50, 5000).astype(float))
+
+
+def test_lk_dna_pinvar(eng, oracle):
+    _check_lk(eng, oracle, dna_gtr_g4(pinvar=0.2), 12, 4000)
+
+
+def test_lk_dna_rescaling_deep_tree(eng, oracle):
+    """A 400-taxon caterpillar drives site maxima below 2^-256: scale counters must match
+    bit-for-bit and lnL stay finite."""
+    lnl, want = _check_lk(eng, oracle, dna_gtr_g4(), 400, 600, tree_kind="caterpillar", mean_bl=0.6)
+    assert want["scale"].max() >= 1, "test must actually trigger rescaling"
+
+
+def test_lk_jc69_sym_path(eng, oracle):
+    m = mlmodel.create(("JC69",), 4, site_var=("gamma", 4, 1.0))
+    _check_lk(eng, oracle, m, 14, 3000)
+
+
+def test_lk_five_state_dynamic_kernel(eng, oracle):
+    """gap as a 5th state (lib/mlModel.ml:108-113): S=5 goes through the run-time-S kernel."""
+    m = mlmodel.create(("F81",), 5, pi=[0.2, 0.2, 0.25, 0.25, 0.1], site_var=("gamma", 4, 0.5))
+    _check_lk(eng, oracle, m, 10, 2000)
+
+
+def test_lk_aa_20_state(eng, oracle):
+    """BASELINE config 4 shape (reduced): 20 states, K=4."""
+    _check_lk(eng, oracle, aa_model(4), 16, 3000)
+
+
+def test_lk_codon_61_state(eng, oracle):
+    """BASELINE config 5 shape (reduced): 61 states, K=1."""
+    _check_lk(eng, oracle, codon_model(), 12, 1500, mean_bl=0.05)
+
+
+def test_lk_median_2_per_node_matches_score_tree(eng, oracle):
+    """API-fidelity path: one phylo_lk_median_2 per node == the whole-tree entry point."""
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(12, 2000, model, seed=9)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    whole = eng.lk_score_tree(ops, ra, rb, rt)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    for op in ops:
+        eng.lk_median_2(int(op["parent"]), int(op["left"]), op["t_left"], int(op["right"]), op["t_right"])
+    per_node = eng.lk_edge_lnl(ra, rb, [rt])[0]
+    assert per_node == whole  # same kernels, same order: bit-identical
+
+
+def test_lk_pulley_principle(eng):
+    """Reversible model: lnL is the same at every root edge (independent property pin)."""
+    model = dna_gtr_g4()
+    tr = tree.random_tree(10, 21)
+    tips = tree.evolve_tips(tr, model, 1500, 22)
+    eng.lk_set_model(model)
+    vals = []
+    for e in tr.edges():
+        ops, ra, rb, rt, n_nodes = tree.schedule(tr, root_edge=e)
+        eng.lk_set_tips(tips, capacity=n_nodes)
+        vals.append(eng.lk_score_tree(ops, ra, rb, rt))
+    assert max(vals) - min(vals) <= 1e-9 * abs(vals[0])
+
+
+def test_lk_edge_lnl_many_lengths(eng, oracle):
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(10, 1200, model, seed=13)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    eng.lk_score_tree(ops, ra, rb, rt)
+    ts = [1e-4, 0.01, 0.1, 0.5, 2.0]
+    got = eng.lk_edge_lnl(ra, rb, ts)
+    for t, g in zip(ts, got):
+        w = oracle.lk_score_tree(model, tips, None, ops, n_nodes, ra, rb, t)["lnl"]
+        assert rel_err(g, w) <= LNL_RTOL
+
+
+def test_lk_block_partials_shard_invariance(eng):
+    """Splitting the patterns in 1024-aligned shards and reducing the gathered level-1
+    partials reproduces the single-engine lnL bit-for-bit (what N ranks do)."""
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(8, 5000, model, seed=17)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    whole = eng.lk_score_tree(ops, ra, rb, rt)
+    assert eng.reduce_partials(eng.lk_get_block_partials()) == whole
+    parts = []
+    for lo, hi in [(0, 2048), (2048, 3072), (3072, 5000)]:
+        eng.lk_set_tips(np.ascontiguousarray(tips[:, lo:hi]), capacity=n_nodes)
+        eng.lk_score_tree(ops, ra, rb, rt)
+        parts.append(eng.lk_get_block_partials())
+    assert eng.reduce_partials(np.concatenate(parts)) == whole
+
+
+def test_lk_rejects_empty_mask(eng):
+    model = dna_gtr_g4()
+    tips = np.ones((4, 100), dtype=np.uint8)
+    tips[2, 17] = 0
+    eng.lk_set_model(model)
+    with pytest.raises(engine.PhyloError) as ei:
+        eng.lk_set_tips(tips)
+    assert ei.value.code == -4
+
+
+def test_lk_rejects_non_postorder(eng):
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(8, 64, model, seed=2)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    with pytest.raises(engine.PhyloError):
+        eng.lk_score_tree(ops[::-1].copy(), ra, rb, rt)
+
+
+def test_lk_wide_masks_are_converted(eng, oracle):
+    """uint32 tip masks for a 4-state model (bv32-style input) give the same lnL."""
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(8, 700, model, seed=4)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    a = eng.lk_score_tree(ops, ra, rb, rt)
+    eng.lk_set_tips(tips.astype(np.uint32) | 16, capacity=n_nodes)  # stray gap bit is ignored
+    assert eng.lk_score_tree(ops, ra, rb, rt) == a
+
+
+# ------------------------------------------------------------------------ Fitch ----
+def _fitch_setup(T, N, n_states, dtype, seed=1):
+    tr = tree.random_tree(T, seed)
+    ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+    chars = tree.random_fitch_chars(T, N, n_states, seed + 5, dtype=dtype)
+    return ops, ra, rb, n_nodes, chars
+
+
+@pytest.mark.parametrize("T,N", [(16, 10000), (64, 100003), (5, 31), (3, 1), (64, 32)])
+def test_fitch_tree_length_and_sets_bit_exact(eng, oracle, T, N):
+    ops, ra, rb, n_nodes, chars = _fitch_setup(T, N, 4, np.uint8)
+    eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+    length = eng.fitch_score_tree(ops, ra, rb)
+    want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, want_sets=True)
+    assert length == want["length"]
+    costs = eng.fitch_get_node_costs()
+    for op in ops:
+        p = int(op["parent"])
+        assert costs[p] == want["node_cost"][p]
+        assert np.array_equal(eng.fitch_get_states(p), want["prelim"][p])
+    for t in range(T):
+        assert np.array_equal(eng.fitch_get_states(t), chars[t])
+
+
+@pytest.mark.parametrize("dtype,n_states", [(np.uint8, 5), (np.uint8, 6), (np.uint8, 8), (np.uint16, 11),
+                                            (np.uint32, 22), (np.uint32, 32), (np.uint64, 40),
+                                            (np.uint64, 64)])
+def test_fitch_all_widths(eng, oracle, dtype, n_states):
+    """W in {8,16,32,64} (lib/bitvector/bv.h:29-55) and plane counts up to 64."""
+    ops, ra, rb, n_nodes, chars = _fitch_setup(12, 3001, n_states, dtype, seed=3)
+    eng.fitch_set_tips(chars, n_states, capacity=n_nodes)
+    length = eng.fitch_score_tree(ops, ra, rb)
+    want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, want_sets=True)
+    assert length == want["length"]
+    p = int(ops[-1]["parent"])
+    assert np.array_equal(eng.fitch_get_states(p), want["prelim"][p])
+
+
+def test_fitch_median_2_and_distance_per_node(eng, oracle):
+    """NonAdditive.median_2 / bv_fitch per node, then bv_distance at the root edge."""
+    ops, ra, rb, n_nodes, chars = _fitch_setup(20, 5000, 4, np.uint8, seed=8)
+    eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+    sets = {t: chars[t] for t in range(20)}
+    total = 0
+    for op in ops:
+        p, l, r = int(op["parent"]), int(op["left"]), int(op["right"])
+        cost = eng.fitch_median_2(p, l, r)
+        c, k = oracle.fitch_median2(sets[l], sets[r])
+        sets[p] = c
+        assert cost == k
+        assert np.array_equal(eng.fitch_get_states(p), c)
+        total += cost
+    d = eng.fitch_distance(ra, rb)
+    assert d == oracle.fitch_distance(sets[ra], sets[rb])
+    assert total + d == eng.fitch_score_tree(ops, ra, rb)
+
+
+def test_fitch_weighted(eng, oracle):
+    ops, ra, rb, n_nodes, chars = _fitch_setup(16, 7000, 4, np.uint8, seed=4)
+    w = np.random.default_rng(2).integers(0, 9, 7000).astype(float)
+    eng.fitch_set_tips(chars, 4, weights=w, capacity=n_nodes)
+    assert eng.fitch_score_tree(ops, ra, rb) == oracle.fitch_score_tree(chars, w, ops, n_nodes, ra, rb)["length"]
+    with pytest.raises(engine.PhyloError):
+        eng.fitch_set_tips(chars, 4, weights=w + 0.5, capacity=n_nodes)
+
+
+def test_fitch_uppass_final_sets(eng, oracle):
+    ops, ra, rb, n_nodes, chars = _fitch_setup(24, 4099, 4, np.uint8, seed=6)
+    eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+    eng.fitch_score_tree(ops, ra, rb)
+    eng.fitch_uppass(ops, ra, rb)
+    want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, want_sets=True)
+    fin = oracle.fitch_uppass(24, want["prelim"], ops, ra, rb)
+    for v in range(n_nodes):
+        assert np.array_equal(eng.fitch_get_states(v, final=True), fin[v]), v
+
+
+def test_fitch_rejects_empty_character(eng):
+    chars = np.ones((4, 50), dtype=np.uint8)
+    chars[1, 3] = 0
+    with pytest.raises(engine.PhyloError) as ei:
+        eng.fitch_set_tips(chars, 4)
+    assert ei.value.code == -4
+
+
+def test_bv_set_algebra(eng, oracle):
+    """bv_union/inter/popcount/saturation/poly_saturation/compare (lib/bitvector/bv.c:59-144)."""
+    rng = np.random.default_rng(5)
+    N = 3333
+    chars = rng.integers(1, 64, size=(3, N)).astype(np.uint8)
+    chars[2] = chars[0]
+    eng.fitch_set_tips(chars, 6, capacity=8)
+    a, b = chars[0], chars[1]
+    eng.bv_union(4, 0, 1)
+    eng.bv_inter(5, 0, 1)
+    assert np.array_equal(eng.fitch_get_states(4), a | b)
+    assert np.array_equal(eng.fitch_get_states(5), a & b)
+    pop = np.array([bin(int(x)).count("1") for x in a])
+    assert eng.bv_popcount(0) == int(pop.sum())
+    assert eng.bv_saturation(0, 0b101) == int(((a & 0b101) != 0).sum())
+    for n in range(0, 8):
+        assert eng.bv_poly_saturation(0, n) == int((pop == n).sum())
+    assert eng.bv_compare(0, 2) == 0
+    first = int(np.nonzero(a != b)[0][0])
+    assert eng.bv_compare(0, 1) == (1 if a[first] > b[first] else -1)
+    assert eng.bv_compare(1, 0) == -eng.bv_compare(0, 1)
+    # Bitvector.of_array on an interior slot, then the union laws of test/bitvectorTest.ml:44-57
+    eng.fitch_set_states(6, b)
+    eng.bv_union(7, 6, 6)
+    assert np.array_equal(eng.fitch_get_states(7), b)
