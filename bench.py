@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 tree-scoring engine (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dna|fitch|aa|codon]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # CPU arm: oracle/_ref + oracle port, all cores
+
+A "step" is one full evaluation of the hot path on one batch of synthetic input:
+  dna   (default; BASELINE config 3) DNA GTR+G4 full-tree pruning + root lnL, 256 taxa x 4M
+        site patterns, sharded contiguously over the ranks (total fixed => "strong").
+  fitch (BASELINE config 2) Fitch down-pass length, 64 taxa x 1M characters (and x64M).
+  aa / codon (BASELINE configs 4 / 5) 20-state +G4 and 61-state pruning.
+One JSON line on stdout (rank 0). PyTorch is used for events, NCCL and nothing else.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GTR_CO = [1.0, 2.5, 0.8, 1.2, 3.0]
+GTR_PI = [0.30, 0.20, 0.25, 0.25]
+BASE_PATTERNS = 65536  # evolved once, tiled to the workload size
+
+WORKLOADS = {
+    # name: (T, N_total, S, K, cpu_sample_patterns)
+    "dna": dict(T=256, N=4_000_000, S=4, K=4, cpu_sample=131072,
+                name="DNA GTR+G4 full-tree pruning, 256 taxa x 4M site patterns"),
+    "aa": dict(T=128, N=500_000, S=20, K=4, cpu_sample=8192,
+               name="AA 20-state +G4 pruning, 128 taxa x 500k patterns"),
+    "codon": dict(T=64, N=200_000, S=61, K=1, cpu_sample=4096,
+                  name="Codon 61-state pruning, 64 taxa x 200k patterns"),
+    "fitch": dict(T=64, N=1_000_000, S=4, K=1, cpu_sample=1_000_000,
+                  name="Fitch/non-additive parsimony length, 64 taxa x 1M bit-packed DNA characters"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_model(wl):
+    from phylocaml_b200 import mlmodel
+
+    if wl["S"] == 4:
+        return mlmodel.create(("GTR", GTR_CO), 4, pi=GTR_PI, site_var=("gamma", wl["K"], 0.5))
+    if wl["S"] == 20:
+        R, pi = mlmodel.synthetic_reversible(20, 4)
+        return mlmodel.create(("Const", R), 20, pi=pi, site_var=("gamma", wl["K"], 0.5))
+    R, pi = mlmodel.gy94(2.0, 0.5, 5)
+    return mlmodel.create(("Const", R), 61, pi=pi)
+
+
+def mask_dtype(S):
+    return np.uint8 if S <= 8 else (np.uint32 if S <= 32 else np.uint64)
+
+
+def shard_bounds(N, world, rank, align=1024):
+    blocks = (N + align - 1) // align
+    per, rem = divmod(blocks, world)
+    lo_b = rank * per + min(rank, rem)
+    hi_b = lo_b + per + (1 if rank < rem else 0)
+    return min(lo_b * align, N), min(hi_b * align, N)
+
+
+def lk_bytes(T, S, K, tip_bytes):
+    """SURVEY.md 8(d) per-node streaming model, bytes per pattern per launch."""
+    C = S * K * 8
+    return dict(prune_inner_inner=3 * C + 12, prune_tip_inner=2 * C + tip_bytes + 8,
+                prune_tip_tip=C + 2 * tip_bytes + 4, root_lnl=2 * C + 8,
+                tree=(2 * T - 3) * C + T * tip_bytes + (2 * T - 3) * 4)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def build_tips(tree_mod, tr, model, T, n_local, S, rank):
+    """Evolve BASE_PATTERNS realistic patterns down the tree once, tile to the shard size, into
+    page-locked host memory (the e2e leg uploads from there)."""
+    from phylocaml_b200 import engine
+
+    base_n = min(BASE_PATTERNS, max(n_local, 1))
+    base = tree_mod.evolve_tips(tr, model, base_n, seed=3, dtype=mask_dtype(S))
+    base = np.roll(base, 997 * rank, axis=1)
+    tips = engine.pinned_empty((T, n_local), mask_dtype(S))
+    for lo in range(0, n_local, base_n):
+        hi = min(n_local, lo + base_n)
+        tips[:, lo:hi] = base[:, :hi - lo]
+    return tips
+
+
+def run_reference(args, wl):
+    """CPU arm: the reference's own C where it exists (bv_fitch / bv_distance from oracle/_ref
+    for Fitch), otherwise the oracle port of the path (pruning: the reference has no pruning
+    loop, lib/likelihood_c.ml:1-33), with all host threads, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    from phylocaml_b200 import tree as tree_mod
+
+    cores = os.cpu_count() or 1
+    orc = Oracle()
+    T, S, K = wl["T"], wl["S"], wl["K"]
+    tr = tree_mod.random_tree(T, seed=1)
+    ops, ra, rb, rt, n_nodes = tree_mod.schedule(tr)
+    ns = wl["cpu_sample"]
+    times = []
+    if args.workload == "fitch":
+        chars = tree_mod.random_fitch_chars(T, ns, 4, seed=5)
+        fn = lambda: orc.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, nthreads=cores)["length"]
+        units, metric, unit, kind = (T - 1) * ns, "fitch_char_ops_per_s", "char-ops/s", "port"
+        sample = "64 taxa x %d chars, W=8 one char per byte (bv.c layout), %d pthreads" % (ns, cores)
+    else:
+        model = make_model(wl)
+        tips = tree_mod.evolve_tips(tr, model, min(ns, BASE_PATTERNS), seed=3, dtype=mask_dtype(S))
+        tips = np.tile(tips, (1, (ns + tips.shape[1] - 1) // tips.shape[1]))[:, :ns].copy()
+        fn = lambda: orc.lk_score_tree(model, tips, None, ops, n_nodes, ra, rb, rt, nthreads=cores)["lnl"]
+        units, metric, unit, kind = (T - 1) * ns, "clv_site_updates_per_s", "site-updates/s", "port"
+        sample = "%d taxa x %d patterns (of %d), oracle C port -O2 no-FMA, %d pthreads" % (T, ns, wl["N"], cores)
+    for _ in range(args.warmup):
+        fn()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = units * args.steps / total
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.workload != "fitch" else "u8",
+        "data": "synthetic", "config": {"workload": wl["name"], "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(wl, workload, tr, ops, ra, rb, rt, n_nodes, model, tips_sample, site_gpu):
+    from oracle.oracle import Oracle
+
+    cores = os.cpu_count() or 1
+    orc = Oracle()
+    T = wl["T"]
+    ns = tips_sample.shape[1]
+    best, res = None, None
+    t_all = time.perf_counter()
+    for _ in range(3):
+        t0 = time.perf_counter()
+        if workload == "fitch":
+            res = orc.fitch_score_tree(tips_sample, None, ops, n_nodes, ra, rb, nthreads=cores)
+        else:
+            res = orc.lk_score_tree(model, tips_sample, None, ops, n_nodes, ra, rb, rt, nthreads=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        if time.perf_counter() - t_all > 25:
+            break
+    unit = "char-ops/s" if workload == "fitch" else "site-updates/s"
+    out = {"value": (T - 1) * ns / best, "unit": unit, "cores": cores, "kind": "port",
+           "sample": "first %d of this rank's patterns, best of <=3 passes, oracle C port with %d pthreads"
+                     % (ns, cores)}
+    check = None
+    if workload != "fitch" and site_gpu is not None:
+        ref = res["site_lnl"]
+        check = float(np.max(np.abs(site_gpu[:ns] - ref)) / np.max(np.abs(ref)))
+    return out, check, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dna", choices=sorted(WORKLOADS))
+    ap.add_argument("--patterns", type=int, default=0, help="override the total pattern count")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    wl = dict(WORKLOADS[args.workload])
+    if args.patterns:
+        wl["N"] = args.patterns
+
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+
+    from phylocaml_b200 import engine, tree as tree_mod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = peaks()
+
+    T, S, K = wl["T"], wl["S"], wl["K"]
+    n_total = wl["N"] * (world if args.scaling == "weak" else 1)
+    lo, hi = shard_bounds(n_total, world, rank)
+    n_local = hi - lo
+    tr = tree_mod.random_tree(T, seed=1)
+    ops, ra, rb, rt, n_nodes = tree_mod.schedule(tr)
+    eng = engine.Engine(local)
+    launches0 = eng.launch_count
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "fitch":
+        model = None
+        tips = engine.pinned_empty((T, n_local), np.uint8)
+        base = tree_mod.random_fitch_chars(T, min(n_local, 1 << 20), 4, seed=5 + rank)
+        for a in range(0, n_local, base.shape[1]):
+            b = min(n_local, a + base.shape[1])
+            tips[:, a:b] = base[:, :b - a]
+        eng.fitch_set_tips(tips, 4, capacity=n_nodes)
+        acc = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+        def step():
+            v = eng.fitch_score_tree(ops, ra, rb)
+            if world > 1:
+                acc[0] = v
+                dist.all_reduce(acc)
+                return int(acc.item())
+            return v
+
+        def e2e_step():
+            eng.fitch_set_tips(tips, 4, capacity=n_nodes)
+            return step()
+
+        metric, unit, dtype = "fitch_char_ops_per_s", "char-ops/s", "u32 (bit-sliced state planes)"
+        units_per_step = (T - 1) * n_total
+        kbytes = {"fitch_tree": (2 * T - 1) * 0.5}  # compulsory: every node set moved once
+        h2d = tips.nbytes
+    else:
+        model = make_model(wl)
+        tips = build_tips(tree_mod, tr, model, T, n_local, S, rank)
+        eng.lk_set_model(model)
+        eng.lk_set_tips(tips, capacity=n_nodes)
+        acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+        def step():
+            v = eng.lk_score_tree(ops, ra, rb, rt)
+            if world > 1:
+                acc[0] = v
+                dist.all_reduce(acc)  # the path's only exchange: one fp64 scalar
+                return float(acc.item())
+            return v
+
+        def e2e_step():
+            eng.lk_set_tips(tips, capacity=n_nodes)
+            return step()
+
+        metric, unit, dtype = "clv_site_updates_per_s", "site-updates/s", "f64"
+        units_per_step = (T - 1) * n_total
+        kbytes = lk_bytes(T, S, K, tips.dtype.itemsize)
+        h2d = tips.nbytes + ops.nbytes
+
+    for _ in range(args.warmup):
+        result = step()
+    eng.profile(True, reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        result = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    prof = eng.profile_get()
+    eng.profile(False)
+    launches = eng.launch_count - launches0
+    step_launches = (eng.launch_count - launches0) // (args.steps + args.warmup)
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = units_per_step * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel class (CUDA events on the launching stream)
+    roof, kernels = None, {}
+    tot_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    for name, (kms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        per_launch_ms = kms / n
+        entry = {"launches_per_step": n / args.steps, "avg_us": 1e3 * per_launch_ms,
+                 "share_of_kernel_time": kms / tot_kernel_ms}
+        if name in kbytes:
+            by = kbytes[name] * n_local
+            entry["algorithmic_bytes_per_launch"] = by
+            entry["achieved_gbs"] = by / (per_launch_ms * 1e-3) / 1e9
+            entry["frac"] = entry["achieved_gbs"] / hbm_peak
+            if roof is None:
+                traffic = None
+                tpath = os.path.join(ROOT, "profiles", "traffic.json")
+                if os.path.exists(tpath):
+                    with open(tpath) as f:
+                        tj = json.load(f)
+                    t = tj.get(name)
+                    if t and t.get("patterns"):
+                        traffic = t["dram_bytes_per_launch"] * n_local / t["patterns"]
+                roof = {"bound": "hbm", "kernel": name, "achieved": entry["achieved_gbs"], "peak": hbm_peak,
+                        "unit": "GB/s", "frac": entry["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "bytes_model": "SURVEY 8(d) per-node streaming" if args.workload != "fitch"
+                        else "compulsory (tree-fused: every node set moved once)"}
+        kernels[name] = entry
+    if args.workload != "fitch":
+        step_bytes = kbytes["tree"] * n_local
+        roof_step = {"algorithmic_bytes_per_step": step_bytes,
+                     "achieved_gbs": step_bytes / (ms * 1e-3 / args.steps) / 1e9}
+        roof_step["frac"] = roof_step["achieved_gbs"] / hbm_peak
+    else:
+        roof_step = None
+
+    # ---- e2e: host buffers in, scalar out, through the C ABI, every step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.e2e_steps):
+        result_e2e = e2e_step()
+    e1.record()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_val = units_per_step * args.e2e_steps / (float(tms.item()) * 1e-3)
+    e2e = {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+           "ms_per_step": float(tms.item()) / args.e2e_steps, "steps": args.e2e_steps}
+
+    # ---- CPU baseline + correctness spot check (rank 0, N=1 only)
+    cpu, check = None, {"result": result, "result_e2e": result_e2e}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = min(wl["cpu_sample"], n_local)
+        sample = np.ascontiguousarray(tips[:, :ns])
+        site = eng.lk_get_site_lnl() if args.workload != "fitch" else None
+        cpu, err, res = cpu_baseline(wl, args.workload, tr, ops, ra, rb, rt, n_nodes, model, sample, site)
+        if args.workload == "fitch":
+            if ns == n_local:
+                check["oracle_length"] = res["length"]
+                check["bit_exact"] = bool(res["length"] == result)
+        else:
+            check["site_lnl_max_rel_err_vs_oracle_on_sample"] = err
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": wl["name"], "taxa": T, "patterns_total": n_total,
+                       "patterns_per_gpu": n_local, "states": S, "rate_classes": K,
+                       "tree": "random topology seed 1, Exp(0.1) branch lengths",
+                       "tips": "evolved under the model (65536 patterns, tiled), 1% missing"
+                       if args.workload != "fitch" else "random DNA singletons + 2% two-state ambiguity",
+                       "l2": "inputs exceed L2 (working set %.1f GB per GPU)" %
+                             ((kbytes.get("tree", 64) * n_local) / 1e9),
+                       "sharding": "contiguous 1024-aligned pattern slabs, one process per GPU",
+                       "collective": "allreduce of one scalar per step" if world > 1 else "none"},
+            "roofline": roof, "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(step_launches * args.steps),
+            "gpu_launches_total_incl_warmup": int(launches), "clocks": clocks, "check": check,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,14 @@ int phylo_engine_set_stream(phylo_engine *e, void *cuda_stream);
 int phylo_engine_sync(phylo_engine *e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches evidence) */
 uint64_t phylo_engine_launch_count(const phylo_engine *e);
+/* CUDA-event profiler: while enabled, every kernel launch is bracketed by an event pair on
+ * the engine's stream and its duration accumulated per kernel class (0 <= class <
+ * phylo_kernel_class_count()). bench.py's roofline figures come from here. */
+int phylo_engine_profile(phylo_engine *e, int enable);
+int phylo_engine_profile_reset(phylo_engine *e);
+int phylo_engine_profile_get(phylo_engine *e, int kernel_class, double *ms_total, uint64_t *launches);
+int phylo_kernel_class_count(void);
+const char *phylo_kernel_class_name(int kernel_class);
 /* page-locked host memory for Bigarray-backed staging buffers (full-rate H2D/D2H) */
 int phylo_host_alloc(void **out, uint64_t bytes);
 int phylo_host_free(void *p);
@@ -100,7 +108,7 @@ int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int 
 int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int right,
                       double t_right);
 /* Whole-tree entry point: run the schedule, join across the root edge (a,b) of length
- * root_t, return lnL. retain != 0 keeps every interior CLV resident for later
+ * root_t, return lnL. Every interior CLV stays resident in its slot for later
  * phylo_lk_edge_lnl / phylo_lk_get_clv / incremental re-scoring. */
 int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                         double root_t, double *lnl_out);

@@ -26,12 +26,28 @@ struct LkNode {
   bool valid = false;
 };
 
+// kernel classes for the CUDA-event profiler (phylo_engine_profile_*)
+enum KClass {
+  KC_PT_BUILD = 0, KC_PRUNE_II, KC_PRUNE_TI, KC_PRUNE_TT, KC_ROOT, KC_REDUCE, KC_TIPS_PREPARE,
+  KC_FITCH_TREE, KC_FITCH_NODE, KC_FITCH_UPPASS, KC_FITCH_TRANSCODE, KC_BV, KC_COUNT
+};
+static const char *kClassNames[KC_COUNT] = {
+    "pt_build", "prune_inner_inner", "prune_tip_inner", "prune_tip_tip", "root_lnl", "reduce1024",
+    "tips_prepare", "fitch_tree", "fitch_median2", "fitch_uppass", "fitch_transcode", "bv_setops"};
+
 struct phylo_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
   int sm_count = kSMs;
+
+  // ---- profiler: one CUDA-event pair around every launch while enabled
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<int> prof_pending;  // class of pair i (events 2i, 2i+1)
+  double prof_ms[KC_COUNT] = {0};
+  uint64_t prof_n[KC_COUNT] = {0};
 
   // ---- likelihood model (MlModel.t, lib/mlModel.ml:53-63)
   int S = 0, K = 0;
@@ -100,6 +116,40 @@ static int fail(phylo_engine *e, int code, const char *fmt, ...) {
       return fail(e, PHYLO_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                 \
                   cudaGetErrorString(err_), __FILE__, __LINE__);                         \
   } while (0)
+
+// RAII: records an event pair on the engine's stream around the launches in its scope
+struct ProfScope {
+  phylo_engine *e;
+  int idx = -1;
+  ProfScope(phylo_engine *e_, int cls) : e(e_) {
+    if (!e->prof_on) return;
+    idx = (int)e->prof_pending.size();
+    while (e->prof_pool.size() < (size_t)(2 * idx + 2)) {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess) { idx = -1; return; }
+      e->prof_pool.push_back(ev);
+    }
+    e->prof_pending.push_back(cls);
+    cudaEventRecord(e->prof_pool[2 * idx], e->stream);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(e->prof_pool[2 * idx + 1], e->stream);
+  }
+};
+
+// fold finished event pairs into the per-class totals (call after a stream sync)
+static void prof_resolve(phylo_engine *e) {
+  if (e->prof_pending.empty()) return;
+  cudaStreamSynchronize(e->stream);
+  for (size_t i = 0; i < e->prof_pending.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->prof_pool[2 * i], e->prof_pool[2 * i + 1]) == cudaSuccess) {
+      e->prof_ms[e->prof_pending[i]] += ms;
+      e->prof_n[e->prof_pending[i]] += 1;
+    }
+  }
+  e->prof_pending.clear();
+}
 
 template <typename T>
 static void dfree(T *&p) {
@@ -180,6 +230,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
   dfree(e->dCost); dfree(e->dSched); dfree(e->dStage);
+  for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->hT) cudaFreeHost(e->hT);
   if (e->hScalar) cudaFreeHost(e->hScalar);
   if (e->hSched) cudaFreeHost(e->hSched);
@@ -205,6 +256,34 @@ extern "C" int phylo_engine_sync(phylo_engine *e) {
 }
 
 extern "C" uint64_t phylo_engine_launch_count(const phylo_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int phylo_engine_profile(phylo_engine *e, int enable) {
+  if (!e) return PHYLO_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  prof_resolve(e);
+  e->prof_on = enable != 0;
+  return PHYLO_OK;
+}
+extern "C" int phylo_engine_profile_reset(phylo_engine *e) {
+  if (!e) return PHYLO_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  prof_resolve(e);
+  for (int c = 0; c < KC_COUNT; ++c) { e->prof_ms[c] = 0; e->prof_n[c] = 0; }
+  return PHYLO_OK;
+}
+extern "C" int phylo_engine_profile_get(phylo_engine *e, int kernel_class, double *ms_total, uint64_t *launches) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (kernel_class < 0 || kernel_class >= KC_COUNT) return fail(e, PHYLO_ERR_ARG, "profile_get: class %d out of range", kernel_class);
+  CK(cudaSetDevice(e->device));
+  prof_resolve(e);
+  if (ms_total) *ms_total = e->prof_ms[kernel_class];
+  if (launches) *launches = e->prof_n[kernel_class];
+  return PHYLO_OK;
+}
+extern "C" int phylo_kernel_class_count(void) { return KC_COUNT; }
+extern "C" const char *phylo_kernel_class_name(int kernel_class) {
+  return (kernel_class >= 0 && kernel_class < KC_COUNT) ? kClassNames[kernel_class] : nullptr;
+}
 
 extern "C" int phylo_host_alloc(void **out, uint64_t bytes) {
   if (!out) return PHYLO_ERR_ARG;
@@ -234,6 +313,7 @@ static int ensure_pt_capacity(phylo_engine *e, size_t branches, int S, int K) {
 static int build_pt(phylo_engine *e, int nb) {
   CK(cudaMemcpyAsync(e->dT, e->hT, sizeof(double) * nb, cudaMemcpyHostToDevice, e->stream));
   const int threads = std::min(256, std::max(32, ((e->S * e->S + 31) / 32) * 32));
+  ProfScope prof(e, KC_PT_BUILD);
   pt_build_kernel<<<nb * e->K, threads, sizeof(double) * e->S, e->stream>>>(
       e->dU, e->dLam, e->sym ? nullptr : e->dUi, e->dRates, e->dT, e->S, e->K, e->dP);
   LAUNCH_CHECK();
@@ -326,6 +406,7 @@ static int dev_mask_bytes(int S) { return S <= 8 ? 1 : (S <= 32 ? 4 : 8); }
 template <typename InT>
 static int launch_tips_prepare(phylo_engine *e, const void *raw, unsigned long long *dBad) {
   const int g = grid_for(e->N, 256, e->sm_count * 8);
+  ProfScope prof(e, KC_TIPS_PREPARE);
   switch (e->mask_dev_bytes) {
     case 1:
       tips_prepare_kernel<InT, uint8_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint8_t *)e->dTips,
@@ -355,13 +436,27 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     return fail(e, PHYLO_ERR_ARG, "lk_set_tips: %d-bit masks cannot hold %d states", mask_bytes * 8, e->S);
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  lk_free_data(e);
-  e->T = T; e->N = N; e->cap = capacity;
-  e->mask_dev_bytes = dev_mask_bytes(e->S);
-  e->nodes.assign(capacity, LkNode());
+  // same shape as what is loaded: keep every device allocation (tips, CLV arena, reduction
+  // scratch) and only refresh the contents -- a tree-search loop re-uploads often
+  const bool reuse = e->dTips && e->T == T && e->N == N && e->cap == capacity &&
+                     e->mask_dev_bytes == dev_mask_bytes(e->S) && (weights != nullptr) == (e->dWeights != nullptr);
   const size_t cells = (size_t)T * N;
-  CK(cudaMalloc(&e->dTips, cells * e->mask_dev_bytes));
-  CK(cudaMalloc(&e->dInv, (size_t)N * e->mask_dev_bytes));
+  if (reuse) {
+    for (auto &n : e->nodes) n.valid = false;
+    e->lk_evaluated = false;
+  } else {
+    lk_free_data(e);
+    e->T = T; e->N = N; e->cap = capacity;
+    e->mask_dev_bytes = dev_mask_bytes(e->S);
+    e->nodes.assign(capacity, LkNode());
+    CK(cudaMalloc(&e->dTips, cells * e->mask_dev_bytes));
+    CK(cudaMalloc(&e->dInv, (size_t)N * e->mask_dev_bytes));
+    if (weights) CK(cudaMalloc(&e->dWeights, sizeof(double) * N));
+    e->nPart = (N + kLnlBlock - 1) / kLnlBlock;
+    CK(cudaMalloc(&e->dPart, sizeof(double) * e->nPart));
+    CK(cudaMalloc(&e->dPart2, sizeof(double) * ((e->nPart + kLnlBlock - 1) / kLnlBlock + 1) * 2));
+    CK(cudaMalloc(&e->dSite, sizeof(double) * N));
+  }
   void *raw = e->dTips;
   bool tmp = false;
   if (mask_bytes != e->mask_dev_bytes) {
@@ -372,6 +467,8 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
   cudaError_t st = cudaMalloc(&dBad, sizeof(unsigned long long));
   if (st == cudaSuccess) st = cudaMemsetAsync(dBad, 0, sizeof(unsigned long long), e->stream);
   if (st == cudaSuccess) st = cudaMemcpyAsync(raw, masks, cells * mask_bytes, cudaMemcpyHostToDevice, e->stream);
+  if (st == cudaSuccess && weights)
+    st = cudaMemcpyAsync(e->dWeights, weights, sizeof(double) * N, cudaMemcpyHostToDevice, e->stream);
   int rc = PHYLO_OK;
   if (st == cudaSuccess) {
     switch (mask_bytes) {
@@ -394,14 +491,6 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     lk_free_data(e);
     return fail(e, PHYLO_ERR_DATA, "lk_set_tips: %llu tip cells have none of the %d state bits set", bad, e->S);
   }
-  if (weights) {
-    CK(cudaMalloc(&e->dWeights, sizeof(double) * N));
-    CK(cudaMemcpy(e->dWeights, weights, sizeof(double) * N, cudaMemcpyHostToDevice));
-  }
-  e->nPart = (N + kLnlBlock - 1) / kLnlBlock;
-  CK(cudaMalloc(&e->dPart, sizeof(double) * e->nPart));
-  CK(cudaMalloc(&e->dPart2, sizeof(double) * ((e->nPart + kLnlBlock - 1) / kLnlBlock + 1) * 2));
-  CK(cudaMalloc(&e->dSite, sizeof(double) * N));
   return PHYLO_OK;
 }
 
@@ -466,6 +555,7 @@ static cudaError_t launch_prune_any(phylo_engine *e, const double *Pl, const dou
 
 static int lk_launch_prune(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
                            const Operand &r, double *out, int32_t *osc) {
+  ProfScope prof(e, (l.tip && r.tip) ? KC_PRUNE_TT : ((l.tip || r.tip) ? KC_PRUNE_TI : KC_PRUNE_II));
   if (e->S == 4 && (e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8 || e->K == 16)) {
     switch (e->K) {
       case 1: launch_prune4<1>(e, Pl, Pr, l, r, out, osc); break;
@@ -517,6 +607,8 @@ static cudaError_t launch_root_any(phylo_engine *e, const double *Pr, const Oper
 
 // root-edge join with transition matrices Pr ([K][S][S] on device) -> *lnl_host (pinned slot)
 static int lk_root_eval(phylo_engine *e, const double *Pr, const Operand &a, const Operand &b, double *slot) {
+  {
+  ProfScope prof(e, KC_ROOT);
   if (e->S == 4 && (e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8 || e->K == 16)) {
     switch (e->K) {
       case 1: launch_root4<1>(e, Pr, a, b); break;
@@ -535,6 +627,8 @@ static int lk_root_eval(phylo_engine *e, const double *Pr, const Operand &a, con
     if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "root_any setup: %s", cudaGetErrorString(st));
   }
   LAUNCH_CHECK();
+  }
+  ProfScope prof(e, KC_REDUCE);
   // remaining levels of the canonical reduction
   const double *cur = e->dPart;
   int64_t n = e->nPart;
@@ -630,6 +724,7 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
   CK(cudaStreamSynchronize(e->stream));
   *lnl_out = e->hScalar[0];
   e->lk_evaluated = true;
+  if (e->prof_on) prof_resolve(e);
   return PHYLO_OK;
 }
 
@@ -805,6 +900,7 @@ static int fitch_sched_capacity(phylo_engine *e, size_t bytes) {
 // plane buffers; returns the number of empty elements through *bad
 static int fitch_encode(phylo_engine *e, const void *dcodes, uint32_t *dst, unsigned long long *dBad) {
   const int g = grid_for(e->fWords * 32, 256, e->sm_count * 8);
+  ProfScope prof(e, KC_FITCH_TRANSCODE);
   switch (e->felt) {
     case 1: fitch_encode_kernel<uint8_t><<<g, 256, 0, e->stream>>>((const uint8_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
     case 2: fitch_encode_kernel<uint16_t><<<g, 256, 0, e->stream>>>((const uint16_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
@@ -900,12 +996,15 @@ static int fitch_pair(phylo_engine *e, int parent, int left, int right, bool sto
   const int g = grid_for(e->fWords, 256, e->sm_count * 8);
   uint32_t *c = store ? e->fPre[parent] : nullptr;
   const uint32_t *a = e->fPre[left], *b = e->fPre[right];
+  {
+  ProfScope prof(e, KC_FITCH_NODE);
   if (store) {
     NP_DISPATCH(e->fNPdev, (fitch_median2_kernel<NP, true><<<g, 256, 0, e->stream>>>(a, b, c, e->fWords, e->fN, e->dFW, e->dCost)));
   } else {
     NP_DISPATCH(e->fNPdev, (fitch_median2_kernel<NP, false><<<g, 256, 0, e->stream>>>(a, b, c, e->fWords, e->fN, e->dFW, e->dCost)));
   }
   LAUNCH_CHECK();
+  }
   CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   if (out) *out = e->hCost[0];
@@ -965,15 +1064,19 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
   CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long) * (size_t)(n_ops + 2), e->stream));
   const int g = grid_for(e->fWords, 128, e->sm_count * 16);
   const size_t smem = sizeof(unsigned long long) * (size_t)(n_ops + 1);
+  {
+  ProfScope prof(e, KC_FITCH_TREE);
   NP_DISPATCH(e->fNPdev, (fitch_tree_kernel<NP><<<g, 128, smem, e->stream>>>(
                              e->dPreTab, (const FitchStep *)e->dSched, n_ops, root_a, root_b, e->fWords, e->fN,
                              e->dFW, e->dCost, e->dCost + n_ops + 1)));
   LAUNCH_CHECK();
+  }
   CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long) * (size_t)(n_ops + 2), cudaMemcpyDeviceToHost,
                      e->stream));
   CK(cudaStreamSynchronize(e->stream));
   *length_out = e->hCost[n_ops + 1];
   for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[o];
+  if (e->prof_on) prof_resolve(e);
   return PHYLO_OK;
 }
 
@@ -1017,6 +1120,7 @@ extern "C" int phylo_fitch_uppass(phylo_engine *e, const phylo_op *ops, int n_op
   if (n_ops > 0) {
     CK(cudaMemcpyAsync(e->dSched, hs, sizeof(FitchUpStep) * (size_t)n_ops, cudaMemcpyHostToDevice, e->stream));
     const int g = grid_for(e->fWords, 128, e->sm_count * 16);
+    ProfScope prof(e, KC_FITCH_UPPASS);
     NP_DISPATCH(e->fNPdev, (fitch_uppass_kernel<NP><<<g, 128, 0, e->stream>>>(
                                e->dPreTab, e->dFinTab, (const FitchUpStep *)e->dSched, n_ops, root_a, root_b, e->fWords)));
     LAUNCH_CHECK();
@@ -1038,6 +1142,8 @@ extern "C" int phylo_fitch_get_states(phylo_engine *e, int node, int which, void
   const size_t row = (size_t)e->fN * e->felt;
   if ((rc = fitch_stage(e, row)) != PHYLO_OK) return rc;
   const int g = grid_for(e->fWords * 32, 256, e->sm_count * 8);
+  {
+  ProfScope prof(e, KC_FITCH_TRANSCODE);
   switch (e->felt) {
     case 1: fitch_decode_kernel<uint8_t><<<g, 256, 0, e->stream>>>(src, (uint8_t *)e->dStage, e->fN, e->fWords, e->fNPdev); break;
     case 2: fitch_decode_kernel<uint16_t><<<g, 256, 0, e->stream>>>(src, (uint16_t *)e->dStage, e->fN, e->fWords, e->fNPdev); break;
@@ -1045,6 +1151,7 @@ extern "C" int phylo_fitch_get_states(phylo_engine *e, int node, int which, void
     default: fitch_decode_kernel<uint64_t><<<g, 256, 0, e->stream>>>(src, (uint64_t *)e->dStage, e->fN, e->fWords, e->fNPdev);
   }
   LAUNCH_CHECK();
+  }
   CK(cudaMemcpyAsync(out, e->dStage, row, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return PHYLO_OK;

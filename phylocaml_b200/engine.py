@@ -35,6 +35,11 @@ SIGNATURES = {
     "phylo_engine_set_stream": (C.c_int, [_vp, _vp]),
     "phylo_engine_sync": (C.c_int, [_vp]),
     "phylo_engine_launch_count": (C.c_uint64, [_vp]),
+    "phylo_engine_profile": (C.c_int, [_vp, C.c_int]),
+    "phylo_engine_profile_reset": (C.c_int, [_vp]),
+    "phylo_engine_profile_get": (C.c_int, [_vp, C.c_int, _dp, _u64p]),
+    "phylo_kernel_class_count": (C.c_int, []),
+    "phylo_kernel_class_name": (C.c_char_p, [C.c_int]),
     "phylo_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "phylo_host_free": (C.c_int, [_vp]),
     "phylo_diagonalize_sym": (C.c_int, [_dp, _dp, C.c_int]),
@@ -189,6 +194,21 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.phylo_engine_launch_count(self.h))
+
+    def profile(self, enable=True, reset=False):
+        if reset:
+            self._ck(self.lib.phylo_engine_profile_reset(self.h))
+        self._ck(self.lib.phylo_engine_profile(self.h, 1 if enable else 0))
+
+    def profile_get(self):
+        """{kernel class name: (total ms, launches)} accumulated while profiling was on."""
+        out = {}
+        for c in range(self.lib.phylo_kernel_class_count()):
+            ms, n = C.c_double(), C.c_uint64()
+            self._ck(self.lib.phylo_engine_profile_get(self.h, c, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[self.lib.phylo_kernel_class_name(c).decode()] = (ms.value, int(n.value))
+        return out
 
     # ---- MlModel
     def compose(self, U, D, Ui, t):
