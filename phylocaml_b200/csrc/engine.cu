@@ -523,18 +523,28 @@ static int lk_operand(phylo_engine *e, int slot, Operand *o, const char *who) {
   return PHYLO_OK;
 }
 
+// persistent-style grid: as many CTAs as fit on the chip at once (148 SMs x occupancy),
+// each grid-striding over the items
+template <typename Kern>
+static int resident_grid(phylo_engine *e, Kern kern, int threads, size_t smem, int64_t needed) {
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(needed, (int64_t)e->sm_count * occ));
+}
+
 template <int K>
 static void launch_prune4(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
                           const Operand &r, double *out, int32_t *osc) {
-  constexpr int U = 2;
-  const int g = grid_for(e->N * K, 256 * U, e->sm_count * 4);
-#define P4(LT, RT)                                                                              \
-  prune4_kernel<K, LT, RT, U><<<g, 256, 0, e->stream>>>(Pl, Pr, l.src, l.scale, r.src, r.scale, \
-                                                        out, osc, e->N)
-  if (l.tip && r.tip) P4(true, true);
-  else if (l.tip) P4(true, false);
-  else if (r.tip) P4(false, true);
-  else P4(false, false);
+#define P4(LT, RT, U)                                                                           \
+  do {                                                                                          \
+    auto kern = prune4_kernel<K, LT, RT, U>;                                                    \
+    const int g = resident_grid(e, kern, 256, 0, (e->N * K + 256 * U - 1) / (256 * U));         \
+    kern<<<g, 256, 0, e->stream>>>(Pl, Pr, l.src, l.scale, r.src, r.scale, out, osc, e->N);     \
+  } while (0)
+  if (l.tip && r.tip) P4(true, true, 4);
+  else if (l.tip) P4(true, false, 4);
+  else if (r.tip) P4(false, true, 4);
+  else P4(false, false, 2);
 #undef P4
 }
 
@@ -933,16 +943,23 @@ extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_b
   }
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  fitch_free_data(e);
-  e->fT = T; e->fN = N; e->fcap = capacity; e->felt = elt_bytes; e->fNP = n_states;
-  e->fNPdev = np_device(n_states);
-  e->fWords = (N + 31) / 32;
-  e->fPre.assign(capacity, nullptr);
-  e->fFin.assign(capacity, nullptr);
-  e->nodeCost.assign(capacity, 0);
-  CK(cudaMalloc(&e->dPreTab, sizeof(uint32_t *) * capacity));
-  CK(cudaMalloc(&e->dFinTab, sizeof(uint32_t *) * capacity));
-  e->tabDirty = true;
+  // same shape as what is loaded: keep the plane buffers and tables, refresh contents only
+  const bool reuse = e->fT == T && e->fN == N && e->fcap == capacity && e->felt == elt_bytes &&
+                     e->fNP == n_states && e->dPreTab && (weights != nullptr) == (e->dFW != nullptr);
+  if (reuse) {
+    std::fill(e->nodeCost.begin(), e->nodeCost.end(), 0);
+  } else {
+    fitch_free_data(e);
+    e->fT = T; e->fN = N; e->fcap = capacity; e->felt = elt_bytes; e->fNP = n_states;
+    e->fNPdev = np_device(n_states);
+    e->fWords = (N + 31) / 32;
+    e->fPre.assign(capacity, nullptr);
+    e->fFin.assign(capacity, nullptr);
+    e->nodeCost.assign(capacity, 0);
+    CK(cudaMalloc(&e->dPreTab, sizeof(uint32_t *) * capacity));
+    CK(cudaMalloc(&e->dFinTab, sizeof(uint32_t *) * capacity));
+    e->tabDirty = true;
+  }
   int rc;
   if ((rc = fitch_cost_capacity(e, (size_t)capacity + 4)) != PHYLO_OK) return rc;
   // upload in chunks of whole taxa through the staging buffer, transcoding on device
@@ -958,7 +975,7 @@ extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_b
       if ((rc = fitch_encode(e, (const char *)e->dStage + (size_t)t * row, e->fPre[t0 + t], e->dCost)) != PHYLO_OK)
         return rc;
     }
-    CK(cudaStreamSynchronize(e->stream));  // staging buffer is reused by the next chunk
+    if (t0 + chunk < T) CK(cudaStreamSynchronize(e->stream));  // staging buffer is reused by the next chunk
   }
   CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -968,7 +985,7 @@ extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_b
     return fail(e, PHYLO_ERR_DATA, "fitch_set_tips: %llu characters have an empty state set", bad);
   }
   if (weights) {
-    CK(cudaMalloc(&e->dFW, sizeof(uint32_t) * hw.size()));
+    if (!e->dFW) CK(cudaMalloc(&e->dFW, sizeof(uint32_t) * hw.size()));
     CK(cudaMemcpy(e->dFW, hw.data(), sizeof(uint32_t) * hw.size(), cudaMemcpyHostToDevice));
   }
   return PHYLO_OK;

@@ -111,39 +111,42 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
 
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U; base < total; base += stride) {
     d4 l[U], r[U];
-    int sc[U];
+    int ml[U], mr[U], sc[U];
     bool act[U];
-    // ---- issue every load of this iteration first (memory-level parallelism)
+    // ---- phase 1: issue every global load of this iteration back to back (tip bytes, CLV
+    // vectors, scale counters) so their latencies overlap; nothing here depends on a load
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t q = base + (int64_t)u * blockDim.x + threadIdx.x;
       act[u] = q < total;
       const int64_t p = q / K;
       sc[u] = 0;
+      ml[u] = mr[u] = 0;
+      l[u] = d4{0, 0, 0, 0};
+      r[u] = d4{0, 0, 0, 0};
       if (act[u]) {
         if (LTIP) {
-          l[u] = tabL[k * 16 + (ltip[p] & 15)];
+          ml[u] = ltip[p];
         } else {
           l[u] = ld256_stream(lclv + q * 4);
-          if (k == 0) sc[u] += lsc[p];
+          if (k == 0) sc[u] = lsc[p];
         }
         if (RTIP) {
-          r[u] = tabR[k * 16 + (rtip[p] & 15)];
+          mr[u] = rtip[p];
         } else {
           r[u] = ld256_stream(rclv + q * 4);
           if (k == 0) sc[u] += rsc[p];
         }
-      } else {
-        l[u] = d4{0, 0, 0, 0};
-        r[u] = d4{0, 0, 0, 0};
       }
     }
+    // ---- phase 2: table lookups for tip children, contraction, rescale, store
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t q = base + (int64_t)u * blockDim.x + threadIdx.x;
       double x[4], y[4];
       if (LTIP) {
-        x[0] = l[u].x; x[1] = l[u].y; x[2] = l[u].z; x[3] = l[u].w;
+        const d4 t = tabL[k * 16 + (ml[u] & 15)];
+        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -151,7 +154,8 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
                  pl[i * 4 + 3] * l[u].w;
       }
       if (RTIP) {
-        y[0] = r[u].x; y[1] = r[u].y; y[2] = r[u].z; y[3] = r[u].w;
+        const d4 t = tabR[k * 16 + (mr[u] & 15)];
+        y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w;
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)

@@ -35,3 +35,13 @@ def setup_lk(T, N, model, seed=1, tree_kind="random", mean_bl=0.1, missing=0.01)
 
 def rel_err(a, b):
     return abs(a - b) / max(abs(b), 1e-300)
+
+
+def dna_gtr_g4_numpy(diag):
+    """Same DNA GTR+G4 record as dna_gtr_g4() but with the eigensystem from `diag` (e.g.
+    numpy LAPACK), so that oracle-only tests do not depend on the product's own solver."""
+    pi = mlmodel.priors(GTR_PI, 4)
+    Q = mlmodel.m_gtr(pi, GTR_CO, 4)
+    U, D, Ui = diag(Q, False)
+    return dict(S=4, K=4, Q=Q, U=U, D=D, Ui=Ui, pi=pi, rates=mlmodel.gamma_rates_yang_mean(0.5, 4),
+                probs=np.full(4, 0.25), pinvar=None)

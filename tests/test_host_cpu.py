@@ -1,0 +1,159 @@
+"""CPU tests of the host side of the product: the C-ABI library loads and exports every
+symbol include/phylo_engine.h declares, the host-only entry points (eigen-decomposition,
+partial reduction) are right, the engine refuses to run without a GPU, and the harness
+helpers mirror the reference's conventions. No compute kernels are launched here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from phylocaml_b200 import engine, mlmodel, tree
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "phylo_engine.h")) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(phylo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = engine.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), name
+    # and the ctypes table binds exactly the declared surface
+    assert sorted(engine.SIGNATURES) == declared
+
+
+def test_library_has_sm100a_code_only(built):
+    out = subprocess.run(["cuobjdump", "--list-elf", engine.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_does_not_link_the_oracle(built):
+    out = subprocess.run(["ldd", engine.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "_ref" not in out
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "phylocaml_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    txt = f.read()
+                assert "import oracle" not in txt and "from oracle" not in txt, fn
+                assert "liboracle" not in txt and "phylo_oracle.h" not in txt, fn
+
+
+def test_engine_create_fails_loudly_without_gpu(built):
+    lib = engine.load()
+    h = ctypes.c_void_p()
+    rc = lib.phylo_engine_create(0, ctypes.byref(h))
+    if rc == 0:
+        lib.phylo_engine_destroy(h)
+        pytest.skip("a GPU is present")
+    assert rc == -1 and h.value is None
+    assert b"no CPU fallback" in lib.phylo_last_error(None)
+    with pytest.raises(engine.PhyloError):
+        engine.Engine(0)
+
+
+# ------------------------------------------------------------- eigen-decomposition ----
+@pytest.mark.parametrize("case", ["dna_gtr", "dna_f81", "aa20", "codon61"])
+def test_diagonalize_gtr_reproduces_reference_P(built, oracle, case):
+    """phylo_diagonalize_gtr (Jacobi on the symmetrised generator) vs the reference's LAPACK
+    path (lib/mlmodel.c:208-262): eigenvector scaling differs, P(t) must not."""
+    g = np.load(os.path.join(GOLD, "compose_ref.npz"))
+    Q = g[case + "_Q"]
+    U, D, Ui = engine.diagonalize(Q, False)
+    assert np.abs(U @ D @ Ui - Q).max() <= 1e-13 * np.abs(Q).max() * Q.shape[0]
+    assert np.abs(U @ Ui - np.eye(Q.shape[0])).max() <= 1e-12
+    for t, P in zip(g[case + "_t"], g[case + "_P"]):
+        got = oracle.compose(U, D, Ui, t)
+        assert np.abs(got - P).max() <= 1e-12, (case, t)
+
+
+@pytest.mark.parametrize("case", ["dna_jc69", "dna_k2p", "five_jc69"])
+def test_diagonalize_sym_reproduces_reference_P(built, oracle, case):
+    g = np.load(os.path.join(GOLD, "compose_ref.npz"))
+    Q = g[case + "_Q"]
+    U, D, Ui = engine.diagonalize(Q, True)
+    assert Ui is None
+    assert np.abs(U.T @ D @ U - Q).max() <= 1e-13  # rows of U are the eigenvectors (mlmodel.c:155-158)
+    assert np.all(np.diff(np.diag(D)) >= 0)        # ascending like dsyev
+    for t, P in zip(g[case + "_t"], g[case + "_P"]):
+        assert np.abs(oracle.compose(U, D, None, t) - P).max() <= 1e-12
+
+
+def test_diagonalize_errors(built):
+    Q = np.zeros((4, 4))
+    Q[0, 1] = np.nan
+    with pytest.raises(engine.PhyloError) as ei:
+        engine.diagonalize(Q, False)
+    assert ei.value.code == -5
+    # a rotation generator has complex eigenvalues: the reference fails ("Imaginary
+    # eigenvalues", lib/mlmodel.c:248-250); so do we
+    R = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]]) - np.eye(3)
+    with pytest.raises(engine.PhyloError):
+        engine.diagonalize(R, False)
+
+
+def test_reduce_partials_matches_oracle(built, oracle):
+    eng_lib = engine.load()
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 1024, 1025, 3907, 1024 * 1024 + 3):
+        v = rng.normal(-1e4, 50.0, n)
+        got = eng_lib.phylo_reduce_partials(v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n)
+        assert got == oracle.reduce(v), n
+
+
+# ---------------------------------------------------------------- harness mirrors ----
+def test_q_builders_follow_mlmodel_ml():
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    for Q in (mlmodel.m_jc69(4), mlmodel.m_k2p(0.5, 4), mlmodel.m_f81(pi, 4), mlmodel.m_hky85(pi, 2.0, 4),
+              mlmodel.m_f84(pi, 1.5, 4), mlmodel.m_tn93(pi, 2.0, 3.0, 4),
+              mlmodel.m_gtr(pi, [1.0, 2.5, 0.8, 1.2, 3.0], 4)):
+        assert np.abs(Q.sum(1)).max() < 1e-14            # rows sum to 0
+    for Q in (mlmodel.m_f81(pi, 4), mlmodel.m_gtr(pi, [1.0, 2.5, 0.8, 1.2, 3.0], 4)):
+        assert abs(-(np.diag(Q) * pi).sum() - 1.0) < 1e-14   # mean rate 1 (mlModel.ml:204-213)
+        F = pi[:, None] * Q
+        assert np.abs(F - F.T).max() < 1e-15                 # reversible: q_ij = c_ij pi_j
+    with pytest.raises(ValueError):                          # mlModel.ml:392-395
+        mlmodel.m_gtr(pi, [1.0, 2.0], 4)
+    p = mlmodel.priors([0.5, 0.5, 0.0, 0.0], 4)              # clamp 1e-13 + renormalise (:697-712)
+    assert p.min() > 0 and abs(p.sum() - 1) < 1e-15
+    r = mlmodel.gamma_rates_yang_mean(0.5, 4)
+    assert abs(r.mean() - 1.0) < 1e-12
+    assert mlmodel.gamma_rates_ref_literal(0.5, 4)[0] == 0.0  # mlModel.ml:93-99: p = 0/k
+
+
+@pytest.mark.parametrize("T", [2, 3, 10, 50])
+def test_tree_and_schedule_invariants(T):
+    """2T-3 edges / 2T-2 nodes (test/treeTest.ml:52-59, lib/tree.ml:552-568); the schedule
+    has T-2 medians in post-order, whatever the root edge."""
+    tr = tree.random_tree(T, seed=T)
+    assert len(tr.edges()) == 2 * T - 3
+    assert len(tr.adj) == 2 * T - 2
+    for e in tr.edges()[:5]:
+        ops, ra, rb, rt, n_nodes = tree.schedule(tr, root_edge=e)
+        assert len(ops) == T - 2 and n_nodes == 2 * T - 2 and rt == tr.length(*e)
+        done = set(range(T))
+        for op in ops:
+            assert int(op["left"]) in done and int(op["right"]) in done and int(op["parent"]) >= T
+            done.add(int(op["parent"]))
+        assert ra in done and rb in done
+
+
+def test_shard_bounds_cover_and_align():
+    import bench
+
+    for N, world in ((4_000_000, 8), (4_000_000, 3), (1000, 4), (1, 2)):
+        spans = [bench.shard_bounds(N, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == N
+        for (a, b), (c, d) in zip(spans, spans[1:]):
+            assert b == c and (b % 1024 == 0 or b == N)

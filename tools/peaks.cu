@@ -1,0 +1,99 @@
+// Micro-benchmarks for the roofline denominators that MEASURED_PEAKS.json does not carry:
+// pure-read, pure-write and copy HBM bandwidth with 256-bit accesses, and the fp64 FMA peak.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/peaks tools/peaks.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct __align__(32) d4 { double x, y, z, w; };
+__device__ __forceinline__ d4 ld256(const double *p) {
+  d4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256(double *p, d4 v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+template <int U>
+__global__ void __launch_bounds__(256) k_copy(const double *a, double *b, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n4; base += stride) {
+    d4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (base + u * blockDim.x < n4) v[u] = ld256(a + 4 * (base + u * blockDim.x));
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (base + u * blockDim.x < n4) st256(b + 4 * (base + u * blockDim.x), v[u]);
+  }
+}
+template <int U>
+__global__ void __launch_bounds__(256) k_read(const double *a, double *out, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+  double acc = 0;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n4; base += stride) {
+    d4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (base + u * blockDim.x < n4) v[u] = ld256(a + 4 * (base + u * blockDim.x)); else v[u] = d4{0,0,0,0};
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc += v[u].x + v[u].y + v[u].z + v[u].w;
+  }
+  if (acc == 1.2345) out[0] = acc;
+}
+template <int U>
+__global__ void __launch_bounds__(256) k_write(double *b, int64_t n4, double val) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n4; base += stride) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (base + u * blockDim.x < n4) st256(b + 4 * (base + u * blockDim.x), d4{val, val, val, val});
+  }
+}
+__global__ void __launch_bounds__(256) k_dfma(double *out, int iters, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 1.2345) out[0] = s;
+}
+template <typename F>
+float best_ms(F f, int reps = 10) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < reps + 2; ++r) {
+    cudaEventRecord(e0);
+    f();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (r >= 2 && ms < best) best = ms;
+  }
+  return best;
+}
+int main() {
+  const int64_t bytes = (int64_t)2 << 30, n4 = bytes / 32;
+  double *a, *b;
+  cudaMalloc(&a, bytes); cudaMalloc(&b, bytes);
+  cudaMemset(a, 0, bytes); cudaMemset(b, 0, bytes);
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  printf("{\"sms\": %d", sms);
+  for (int occ : {2, 4, 8}) {
+    const int g = sms * occ;
+    float c = best_ms([&] { k_copy<4><<<g, 256>>>(a, b, n4); });
+    float r = best_ms([&] { k_read<4><<<g, 256>>>(a, b, n4); });
+    float w = best_ms([&] { k_write<4><<<g, 256>>>(b, n4, 1.0); });
+    printf(", \"copy_gbs_occ%d\": %.1f, \"read_gbs_occ%d\": %.1f, \"write_gbs_occ%d\": %.1f", occ, 2.0 * bytes / c / 1e6, occ, bytes / r / 1e6, occ, bytes / w / 1e6);
+  }
+  float m = best_ms([&] { cudaMemsetAsync(b, 1, bytes); });
+  printf(", \"memset_gbs\": %.1f", bytes / m / 1e6);
+  float mc = best_ms([&] { cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice); });
+  printf(", \"memcpy_d2d_gbs\": %.1f", 2.0 * bytes / mc / 1e6);
+  const int iters = 20000;
+  float f = best_ms([&] { k_dfma<<<sms * 8, 256>>>(b, iters, 1.0000001, 1e-9); }, 5);
+  printf(", \"fp64_fma_tflops\": %.2f}\n", 2.0 * 8 * iters * (double)sms * 8 * 256 / f / 1e9);
+  return 0;
+}
