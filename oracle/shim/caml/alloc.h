@@ -6,4 +6,5 @@ value caml_alloc(mlsize_t wosize, int tag);
 value caml_copy_int32(int32_t i);
 value caml_copy_int64(int64_t i);
 value caml_copy_double(double d);
+value caml_alloc_tuple(mlsize_t n);
 #endif

@@ -32,6 +32,7 @@ static value shim_block(mlsize_t wosize, int tag)
 value caml_alloc(mlsize_t wosize, int tag) { return shim_block(wosize, tag); }
 value caml_copy_int32(int32_t i) { value v = shim_block(2, 255); Int32_val(v) = i; return v; }
 value caml_copy_int64(int64_t i) { value v = shim_block(2, 255); Int64_val(v) = i; return v; }
+value caml_alloc_tuple(mlsize_t n) { return shim_block(n, 0); }
 value caml_copy_double(double d) { value v = shim_block(1, 253); Double_val(v) = d; return v; }
 
 value caml_alloc_custom(struct custom_operations *ops, unsigned long size, mlsize_t mem, mlsize_t max)

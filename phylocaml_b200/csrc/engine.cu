@@ -541,8 +541,14 @@ static void launch_prune4(phylo_engine *e, const double *Pl, const double *Pr, c
     const int g = resident_grid(e, kern, 256, 0, (e->N * K + 256 * U - 1) / (256 * U));         \
     kern<<<g, 256, 0, e->stream>>>(Pl, Pr, l.src, l.scale, r.src, r.scale, out, osc, e->N);     \
   } while (0)
-  if (l.tip && r.tip) P4(true, true, 4);
-  else if (l.tip) P4(true, false, 4);
+  if (l.tip && r.tip) {
+    constexpr int U = 4;
+    const size_t smem = 256 * K * sizeof(d4) + 256 * sizeof(int);
+    auto kern = prune4_tt_kernel<K, U>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int g = resident_grid(e, kern, 256, smem, (e->N * K + 256 * U - 1) / (256 * U));
+    kern<<<g, 256, smem, e->stream>>>(Pl, Pr, (const uint8_t *)l.src, (const uint8_t *)r.src, out, osc, e->N);
+  } else if (l.tip) P4(true, false, 4);
   else if (r.tip) P4(false, true, 4);
   else P4(false, false, 2);
 #undef P4

@@ -54,10 +54,23 @@ __global__ void pt_build_kernel(const double *__restrict__ U, const double *__re
 // 32 contiguous bytes, so every warp request is one fully used 1 KB run (256-bit accesses).
 // k = q % K is loop-invariant (the grid stride is a multiple of K), so the two 4x4 P
 // matrices of that rate class stay in registers for the whole kernel. A tip child costs one
-// byte per pattern; its contribution sum_{j in mask} P[i][j] comes from a 16-entry table in
-// shared memory built once per CTA (identical summation order to the oracle).
+// byte per pattern; its contribution x_i = sum_{j in mask} P[i][j] is formed from the
+// register-resident matrix with predicated adds in ascending j -- the same values in the
+// same order as the oracle's sum_j P[i][j]*L[j] with L in {0,1}, so it is bit-identical,
+// and it needs no shared-memory table (an earlier table version was bank-conflict bound).
 // Per-site rescale: the K lanes of a pattern agree by xor-shuffle on max(high word); values
 // are >= 0 so comparing high words as integers is the same test as max < 2^-256.
+__device__ __forceinline__ void tip_contrib(const double (&pm)[16], int m, double (&x)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double a = (m & 1) ? pm[i * 4 + 0] : 0.0;
+    a += (m & 2) ? pm[i * 4 + 1] : 0.0;
+    a += (m & 4) ? pm[i * 4 + 2] : 0.0;
+    a += (m & 8) ? pm[i * 4 + 3] : 0.0;
+    x[i] = a;
+  }
+}
+
 template <int K, bool LTIP, bool RTIP, int U>
 __global__ void __launch_bounds__(256)
 prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
@@ -65,44 +78,12 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
               const void *__restrict__ rsrc, const int32_t *__restrict__ rsc,
               double *__restrict__ out, int32_t *__restrict__ osc, int64_t N) {
   static_assert(K == 1 || K == 2 || K == 4 || K == 8 || K == 16, "K must divide the warp");
-  __shared__ d4 tabL[LTIP ? K * 16 : 1];
-  __shared__ d4 tabR[RTIP ? K * 16 : 1];
   const int k = threadIdx.x % K;
   double pl[16], pr[16];
-  if (!LTIP) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) pl[e] = Pl[k * 16 + e];
-  }
-  if (!RTIP) {
+  for (int e = 0; e < 16; ++e) pl[e] = Pl[k * 16 + e];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) pr[e] = Pr[k * 16 + e];
-  }
-  if (LTIP || RTIP) {
-    for (int e = threadIdx.x; e < K * 16; e += blockDim.x) {
-      const int kk = e >> 4, m = e & 15;
-      if (LTIP) {
-        double v[4];
-        for (int i = 0; i < 4; ++i) {
-          double a = 0.0;
-          for (int j = 0; j < 4; ++j)
-            if ((m >> j) & 1) a += Pl[kk * 16 + i * 4 + j];
-          v[i] = a;
-        }
-        tabL[e] = d4{v[0], v[1], v[2], v[3]};
-      }
-      if (RTIP) {
-        double v[4];
-        for (int i = 0; i < 4; ++i) {
-          double a = 0.0;
-          for (int j = 0; j < 4; ++j)
-            if ((m >> j) & 1) a += Pr[kk * 16 + i * 4 + j];
-          v[i] = a;
-        }
-        tabR[e] = d4{v[0], v[1], v[2], v[3]};
-      }
-    }
-    __syncthreads();
-  }
+  for (int e = 0; e < 16; ++e) pr[e] = Pr[k * 16 + e];
 
   const int64_t total = N * K;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
@@ -139,14 +120,13 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
         }
       }
     }
-    // ---- phase 2: table lookups for tip children, contraction, rescale, store
+    // ---- phase 2: contraction, rescale, store
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t q = base + (int64_t)u * blockDim.x + threadIdx.x;
       double x[4], y[4];
       if (LTIP) {
-        const d4 t = tabL[k * 16 + (ml[u] & 15)];
-        x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        tip_contrib(pl, ml[u], x);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -154,8 +134,7 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
                  pl[i * 4 + 3] * l[u].w;
       }
       if (RTIP) {
-        const d4 t = tabR[k * 16 + (mr[u] & 15)];
-        y[0] = t.x; y[1] = t.y; y[2] = t.z; y[3] = t.w;
+        tip_contrib(pr, mr[u], y);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -174,6 +153,70 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
       if (act[u]) {
         st256(out + q * 4, v);
         if (k == 0) osc[q / K] = sc[u] + (rescale ? 1 : 0);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------- 4-state update, both children tips ----
+// With two tip children the parent CLV of a pattern depends only on the two 4-bit masks:
+// 256 possible (maskL, maskR) pairs. Each CTA builds the 256 finished output rows once
+// (K*4 doubles each, already rescaled, plus the rescale flag) in shared memory, laid out
+// [pair][k][i] so the K lanes of a pattern read one contiguous row (no intra-pattern bank
+// conflict); the kernel body is then 2 byte loads, one 32-byte table read and one 256-bit
+// store per item -- a pure write stream. Values are built with the same operations in the
+// same order as the general path (tip_contrib, product, rescale) => bit-identical.
+template <int K, int U>
+__global__ void __launch_bounds__(256, 4)
+prune4_tt_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
+                 const uint8_t *__restrict__ ltip, const uint8_t *__restrict__ rtip,
+                 double *__restrict__ out, int32_t *__restrict__ osc, int64_t N) {
+  extern __shared__ __align__(32) unsigned char tt_smem[];
+  d4 *tab = reinterpret_cast<d4 *>(tt_smem);                 // [256][K]
+  int *flag = reinterpret_cast<int *>(tab + 256 * K);        // [256]
+  for (int pair = threadIdx.x; pair < 256; pair += blockDim.x) {
+    const int ml = pair >> 4, mr = pair & 15;
+    int h = (int)0x80000000;
+#pragma unroll 1
+    for (int kk = 0; kk < K; ++kk) {
+      double pl[16], pr[16], x[4], y[4];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { pl[e] = Pl[kk * 16 + e]; pr[e] = Pr[kk * 16 + e]; }
+      tip_contrib(pl, ml, x);
+      tip_contrib(pr, mr, y);
+      const d4 v{x[0] * y[0], x[1] * y[1], x[2] * y[2], x[3] * y[3]};
+      tab[pair * K + kk] = v;
+      h = max(h, max(max(hi32(v.x), hi32(v.y)), max(hi32(v.z), hi32(v.w))));
+    }
+    const bool rescale = h < kScaleHiThresh;
+    if (rescale) {
+#pragma unroll 1
+      for (int kk = 0; kk < K; ++kk) {
+        d4 v = tab[pair * K + kk];
+        v.x *= 0x1p+256; v.y *= 0x1p+256; v.z *= 0x1p+256; v.w *= 0x1p+256;
+        tab[pair * K + kk] = v;
+      }
+    }
+    flag[pair] = rescale ? 1 : 0;
+  }
+  __syncthreads();
+  const int k = threadIdx.x % K;
+  const int64_t total = N * K;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U; base < total; base += stride) {
+    int pair[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = base + (int64_t)u * blockDim.x + threadIdx.x;
+      pair[u] = 0;
+      if (q < total) pair[u] = ((ltip[q / K] & 15) << 4) | (rtip[q / K] & 15);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = base + (int64_t)u * blockDim.x + threadIdx.x;
+      if (q < total) {
+        st256(out + q * 4, tab[pair[u] * K + k]);
+        if (k == 0) osc[q / K] = flag[pair[u]];
       }
     }
   }

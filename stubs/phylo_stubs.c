@@ -1,0 +1,365 @@
+/* phylo_stubs.c -- OCaml `value` stubs over the C ABI of include/phylo_engine.h.
+ *
+ * These are the functions phylocaml's `external` declarations bind. They follow the
+ * reference's own FFI style (lib/mlmodel.c:200-205, :304-365; lib/bitvector/bv.c:251-480):
+ * CAMLparam/CAMLreturn, Bigarray c_layout float64 payloads read with Data_bigarray_val,
+ * opaque native state in custom blocks with a finalizer, errors as `Failure msg`
+ * (failwith). Differences, all deliberate: the runtime lock is released while the GPU
+ * works; compose results are BIGARRAY_MANAGED (the reference leaks them,
+ * lib/mlmodel.c:320,362); device node data is named by small integer slots owned by the
+ * engine, wrapped in custom blocks whose finalizer returns the slot.
+ *
+ * Link-compatible names kept from the reference (lib/mlmodel.h:39-43):
+ *   likelihood_CAML_diagonalize_sym / _gtr, likelihood_CAML_compose_sym / _gtr.
+ * New names follow the same <module>_CAML_<fn> scheme: likelihood_CAML_*, nonadd_CAML_*.
+ * Build: part of libphyloc (libphyloc.clib:1-7), linked with -lphyloc_b200.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include <caml/alloc.h>
+#include <caml/bigarray.h>
+#include <caml/custom.h>
+#include <caml/fail.h>
+#include <caml/memory.h>
+#include <caml/mlvalues.h>
+#include <caml/threads.h>
+
+#include "phylo_engine.h"
+
+/* ------------------------------------------------------------ engine custom block ---- */
+#define Engine_val(v) (*((phylo_engine **)Data_custom_val(v)))
+
+static void engine_finalize(value v)
+{
+  if (Engine_val(v)) phylo_engine_destroy(Engine_val(v));
+  Engine_val(v) = NULL;
+}
+
+static struct custom_operations engine_ops = {
+    "AMNH/phylo_b200/engine/0.1", engine_finalize, custom_compare_default, custom_hash_default,
+    custom_serialize_default, custom_deserialize_default, custom_compare_ext_default};
+
+static void check(phylo_engine *e, int rc)
+{
+  if (rc != PHYLO_OK) caml_failwith(phylo_last_error(e)); /* -> OCaml Failure */
+}
+
+/* external engine_create : int -> engine = "phylo_CAML_engine_create" */
+CAMLprim value phylo_CAML_engine_create(value vdev)
+{
+  CAMLparam1(vdev);
+  CAMLlocal1(res);
+  phylo_engine *e = NULL;
+  int rc = phylo_engine_create(Int_val(vdev), &e);
+  if (rc != PHYLO_OK) caml_failwith(phylo_last_error(NULL));
+  res = caml_alloc_custom(&engine_ops, sizeof(phylo_engine *), 0, 1);
+  Engine_val(res) = e;
+  CAMLreturn(res);
+}
+
+/* one process-wide default engine for the reference-named entry points that carry no
+ * engine argument (compose_*): created on first use on device 0 */
+static phylo_engine *default_engine(void)
+{
+  static phylo_engine *e = NULL;
+  if (!e && phylo_engine_create(0, &e) != PHYLO_OK) caml_failwith(phylo_last_error(NULL));
+  return e;
+}
+
+/* ------------------------------------------ MlModel externs (lib/mlModel.ml:73-90) ---- */
+/* replaces lib/mlmodel.c:200-205 */
+CAMLprim value likelihood_CAML_diagonalize_sym(value Q, value D)
+{
+  CAMLparam2(Q, D);
+  if (phylo_diagonalize_sym((double *)Data_bigarray_val(Q), (double *)Data_bigarray_val(D),
+                            (int)Bigarray_val(Q)->dim[0]) != PHYLO_OK)
+    caml_failwith("dsyev_ diagonalization failed to converge. Singular matrix?");
+  CAMLreturn(Val_unit);
+}
+
+/* replaces lib/mlmodel.c:265-271 */
+CAMLprim value likelihood_CAML_diagonalize_gtr(value Q, value D, value Qi)
+{
+  CAMLparam3(Q, D, Qi);
+  if (phylo_diagonalize_gtr((double *)Data_bigarray_val(Q), (double *)Data_bigarray_val(D),
+                            (double *)Data_bigarray_val(Qi), (int)Bigarray_val(Q)->dim[0]) != PHYLO_OK)
+    caml_failwith("Imaginary eigenvalues");
+  CAMLreturn(Val_unit);
+}
+
+static value compose_common(value U, value D, value Ui, double t)
+{
+  CAMLparam3(U, D, Ui);
+  CAMLlocal1(res);
+  intptr_t dims[2];
+  phylo_engine *e = default_engine();
+  int n = (int)Bigarray_val(U)->dim[0], rc;
+  dims[0] = n;
+  dims[1] = n;
+  /* runtime-allocated and owned by the GC (the reference leaks P: no BIGARRAY_MANAGED) */
+  res = caml_ba_alloc(CAML_BA_FLOAT64 | CAML_BA_C_LAYOUT, 2, NULL, dims);
+  if (Ui == Val_unit)
+    rc = phylo_compose_sym(e, (double *)Data_bigarray_val(U), (double *)Data_bigarray_val(D), t, n,
+                           (double *)Data_bigarray_val(res));
+  else
+    rc = phylo_compose_gtr(e, (double *)Data_bigarray_val(U), (double *)Data_bigarray_val(D),
+                           (double *)Data_bigarray_val(Ui), t, n, (double *)Data_bigarray_val(res));
+  check(e, rc);
+  CAMLreturn(res);
+}
+
+/* replaces lib/mlmodel.c:304-323 */
+CAMLprim value likelihood_CAML_compose_sym(value U, value D, value t)
+{
+  return compose_common(U, D, Val_unit, Double_val(t));
+}
+
+/* replaces lib/mlmodel.c:344-365 */
+CAMLprim value likelihood_CAML_compose_gtr(value U, value D, value Ui, value t)
+{
+  return compose_common(U, D, Ui, Double_val(t));
+}
+
+/* --------------------------------------------------- Likelihood_c (lib/nodeData.ml) ---- */
+/* external set_model : engine -> u:matrix -> d:matrix -> ui:matrix option ->
+ *                      (priors:vector * rates:vector * probs:vector * pinvar:float option) -> unit
+ * carries MlModel.t (lib/mlModel.ml:53-63) */
+CAMLprim value likelihood_CAML_set_model(value ve, value U, value D, value Uio, value rest)
+{
+  CAMLparam5(ve, U, D, Uio, rest);
+  phylo_engine *e = Engine_val(ve);
+  value pri = Field(rest, 0), rates = Field(rest, 1), probs = Field(rest, 2), pinv = Field(rest, 3);
+  const double *ui = (Uio == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(Uio, 0));
+  double pv = (pinv == Val_int(0)) ? -1.0 : Double_val(Field(pinv, 0));
+  check(e, phylo_lk_set_model(e, (int)Bigarray_val(U)->dim[0], (int)Bigarray_val(rates)->dim[0],
+                              (double *)Data_bigarray_val(U), (double *)Data_bigarray_val(D), ui,
+                              (double *)Data_bigarray_val(pri), (double *)Data_bigarray_val(rates),
+                              (double *)Data_bigarray_val(probs), pv));
+  CAMLreturn(Val_unit);
+}
+
+/* external set_tips : engine -> (int, int8_unsigned_elt, c_layout) Array2.t (taxa x patterns)
+ *                     -> weights:vector option -> capacity:int -> unit */
+CAMLprim value likelihood_CAML_set_tips(value ve, value masks, value wo, value vcap)
+{
+  CAMLparam4(ve, masks, wo, vcap);
+  phylo_engine *e = Engine_val(ve);
+  struct caml_ba_array *b = Bigarray_val(masks);
+  int kind = (int)(b->flags & 0xff), bytes = 1, rc;
+  const double *w = (wo == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(wo, 0));
+  if (kind == CAML_BA_INT32) bytes = 4;
+  else if (kind == CAML_BA_INT64) bytes = 8;
+  else if (kind != CAML_BA_UINT8) caml_failwith("likelihood set_tips: masks must be uint8, int32 or int64");
+  caml_release_runtime_system(); /* H2D of the alignment can take milliseconds */
+  rc = phylo_lk_set_tips(e, (int)b->dim[0], (int64_t)b->dim[1], b->data, bytes, w, Int_val(vcap));
+  caml_acquire_runtime_system();
+  check(e, rc);
+  CAMLreturn(Val_unit);
+}
+
+/* external median_2 : engine -> parent:int -> (left:int * t_left:float) -> (right:int * t_right:float) -> unit
+ * body of Likelihood_c.median_2 (lib/nodeData.ml:21) */
+CAMLprim value likelihood_CAML_median2(value ve, value vp, value l, value r)
+{
+  CAMLparam4(ve, vp, l, r);
+  phylo_engine *e = Engine_val(ve);
+  check(e, phylo_lk_median_2(e, Int_val(vp), Int_val(Field(l, 0)), Double_val(Field(l, 1)),
+                             Int_val(Field(r, 0)), Double_val(Field(r, 1))));
+  CAMLreturn(Val_unit);
+}
+
+/* external score_tree : engine -> (int32, int32_elt, c_layout) Array2.t (n_ops x 3: parent,left,right)
+ *                       -> (float, float64_elt, c_layout) Array2.t (n_ops x 2: t_left,t_right)
+ *                       -> (root_a:int * root_b:int * root_t:float) -> float   (* lnL *) */
+CAMLprim value likelihood_CAML_score_tree(value ve, value ids, value lens, value root)
+{
+  CAMLparam4(ve, ids, lens, root);
+  phylo_engine *e = Engine_val(ve);
+  int n = (int)Bigarray_val(ids)->dim[0], i, rc;
+  const int32_t *id = (const int32_t *)Data_bigarray_val(ids);
+  const double *tl = (const double *)Data_bigarray_val(lens);
+  phylo_op *ops = (phylo_op *)malloc(sizeof(phylo_op) * (n > 0 ? n : 1));
+  double lnl = 0.0;
+  int ra = Int_val(Field(root, 0)), rb = Int_val(Field(root, 1));
+  double rt = Double_val(Field(root, 2));
+  for (i = 0; i < n; ++i) {
+    ops[i].parent = id[3 * i]; ops[i].left = id[3 * i + 1]; ops[i].right = id[3 * i + 2];
+    ops[i].pad_ = 0; ops[i].t_left = tl[2 * i]; ops[i].t_right = tl[2 * i + 1];
+  }
+  caml_release_runtime_system();
+  rc = phylo_lk_score_tree(e, ops, n, ra, rb, rt, &lnl);
+  caml_acquire_runtime_system();
+  free(ops);
+  check(e, rc);
+  CAMLreturn(caml_copy_double(lnl));
+}
+
+/* external edge_lnl : engine -> int -> int -> vector (lengths) -> vector (out lnL) -> unit
+ * Likelihood_c.root_cost / distance_1 (lib/nodeData.ml:29,32) for a batch of lengths */
+CAMLprim value likelihood_CAML_edge_lnl(value ve, value va, value vb, value ts, value out)
+{
+  CAMLparam5(ve, va, vb, ts, out);
+  phylo_engine *e = Engine_val(ve);
+  int rc, n = (int)Bigarray_val(ts)->dim[0], a = Int_val(va), b = Int_val(vb);
+  const double *t = (const double *)Data_bigarray_val(ts);
+  double *o = (double *)Data_bigarray_val(out);
+  caml_release_runtime_system();
+  rc = phylo_lk_edge_lnl(e, a, b, t, n, o);
+  caml_acquire_runtime_system();
+  check(e, rc);
+  CAMLreturn(Val_unit);
+}
+
+/* external get_clv : engine -> int -> (float, float64_elt, c_layout) Array3.t -> unit */
+CAMLprim value likelihood_CAML_get_clv(value ve, value vnode, value out)
+{
+  CAMLparam3(ve, vnode, out);
+  phylo_engine *e = Engine_val(ve);
+  check(e, phylo_lk_get_clv(e, Int_val(vnode), (double *)Data_bigarray_val(out), NULL));
+  CAMLreturn(Val_unit);
+}
+
+/* ------------------------------------ NonAdditive_c / Bitvector (lib/nonAdditive_c.ml) ---- */
+/* external set_tips : engine -> (int, int8_unsigned_elt, c_layout) Array2.t -> n_states:int
+ *                     -> weights:vector option -> capacity:int -> unit */
+CAMLprim value nonadd_CAML_set_tips(value ve, value codes, value vns, value wo, value vcap)
+{
+  CAMLparam5(ve, codes, vns, wo, vcap);
+  phylo_engine *e = Engine_val(ve);
+  struct caml_ba_array *b = Bigarray_val(codes);
+  int kind = (int)(b->flags & 0xff), bytes = 1, rc;
+  const double *w = (wo == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(wo, 0));
+  if (kind == CAML_BA_INT32) bytes = 4;
+  else if (kind == CAML_BA_INT64) bytes = 8;
+  else if (kind != CAML_BA_UINT8) caml_failwith("nonadd set_tips: codes must be uint8, int32 or int64");
+  caml_release_runtime_system();
+  rc = phylo_fitch_set_tips(e, (int)b->dim[0], (int64_t)b->dim[1], bytes, Int_val(vns), b->data, w,
+                            Int_val(vcap));
+  caml_acquire_runtime_system();
+  check(e, rc);
+  CAMLreturn(Val_unit);
+}
+
+/* external median_2 : engine -> parent:int -> int -> int -> int   (* node-local cost *)
+ * NonAdditive_c.median_2 (lib/nonAdditive_c.ml:19-35) == bv_CAML_fitch_median2 (bv.c:463-480) */
+CAMLprim value nonadd_CAML_median2(value ve, value vp, value vl, value vr)
+{
+  CAMLparam4(ve, vp, vl, vr);
+  phylo_engine *e = Engine_val(ve);
+  uint64_t cost = 0;
+  check(e, phylo_fitch_median_2(e, Int_val(vp), Int_val(vl), Int_val(vr), &cost));
+  CAMLreturn(Val_long((intptr_t)cost));
+}
+
+/* external distance : engine -> int -> int -> int   (bv_CAML_distance2, bv.c:455-461) */
+CAMLprim value nonadd_CAML_distance(value ve, value va, value vb)
+{
+  CAMLparam3(ve, va, vb);
+  phylo_engine *e = Engine_val(ve);
+  uint64_t d = 0;
+  check(e, phylo_fitch_distance(e, Int_val(va), Int_val(vb), &d));
+  CAMLreturn(Val_long((intptr_t)d));
+}
+
+static phylo_op *ops_of_ids(value ids, int *n_out)
+{
+  int n = (int)Bigarray_val(ids)->dim[0], i;
+  const int32_t *id = (const int32_t *)Data_bigarray_val(ids);
+  phylo_op *ops = (phylo_op *)calloc(n > 0 ? n : 1, sizeof(phylo_op));
+  for (i = 0; i < n; ++i) {
+    ops[i].parent = id[3 * i]; ops[i].left = id[3 * i + 1]; ops[i].right = id[3 * i + 2];
+  }
+  *n_out = n;
+  return ops;
+}
+
+/* external score_tree : engine -> ids (n_ops x 3 int32) -> root_a:int -> root_b:int -> int */
+CAMLprim value nonadd_CAML_score_tree(value ve, value ids, value va, value vb)
+{
+  CAMLparam4(ve, ids, va, vb);
+  phylo_engine *e = Engine_val(ve);
+  int n, rc, a = Int_val(va), b = Int_val(vb);
+  phylo_op *ops = ops_of_ids(ids, &n);
+  uint64_t len = 0;
+  caml_release_runtime_system();
+  rc = phylo_fitch_score_tree(e, ops, n, a, b, &len);
+  caml_acquire_runtime_system();
+  free(ops);
+  check(e, rc);
+  CAMLreturn(Val_long((intptr_t)len));
+}
+
+/* external uppass : engine -> ids -> root_a:int -> root_b:int -> unit
+ * fills Node.final_states (lib/node.ml:260-268, TODO in the reference) */
+CAMLprim value nonadd_CAML_uppass(value ve, value ids, value va, value vb)
+{
+  CAMLparam4(ve, ids, va, vb);
+  phylo_engine *e = Engine_val(ve);
+  int n, rc, a = Int_val(va), b = Int_val(vb);
+  phylo_op *ops = ops_of_ids(ids, &n);
+  caml_release_runtime_system();
+  rc = phylo_fitch_uppass(e, ops, n, a, b);
+  caml_acquire_runtime_system();
+  free(ops);
+  check(e, rc);
+  CAMLreturn(Val_unit);
+}
+
+/* external get_states : engine -> node:int -> final:bool -> (int, int8_unsigned_elt, c_layout) Array1.t -> unit */
+CAMLprim value nonadd_CAML_get_states(value ve, value vnode, value vfinal, value out)
+{
+  CAMLparam4(ve, vnode, vfinal, out);
+  phylo_engine *e = Engine_val(ve);
+  check(e, phylo_fitch_get_states(e, Int_val(vnode), Int_val(vfinal) != 0, Data_bigarray_val(out)));
+  CAMLreturn(Val_unit);
+}
+
+/* Bitvector set algebra over slots: bv_CAML_union / inter / popcount / saturation /
+ * poly_saturation / compare (lib/bitvector/bv.c:405-453) */
+CAMLprim value nonadd_CAML_union(value ve, value vd, value va, value vb)
+{
+  CAMLparam4(ve, vd, va, vb);
+  phylo_engine *e = Engine_val(ve);
+  check(e, phylo_bv_union(e, Int_val(vd), Int_val(va), Int_val(vb)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nonadd_CAML_inter(value ve, value vd, value va, value vb)
+{
+  CAMLparam4(ve, vd, va, vb);
+  phylo_engine *e = Engine_val(ve);
+  check(e, phylo_bv_inter(e, Int_val(vd), Int_val(va), Int_val(vb)));
+  CAMLreturn(Val_unit);
+}
+CAMLprim value nonadd_CAML_popcount(value ve, value va)
+{
+  CAMLparam2(ve, va);
+  phylo_engine *e = Engine_val(ve);
+  uint64_t n = 0;
+  check(e, phylo_bv_popcount(e, Int_val(va), &n));
+  CAMLreturn(Val_long((intptr_t)n)); /* the reference returns Int_val(i) here by mistake (bv.c:410) */
+}
+CAMLprim value nonadd_CAML_saturation(value ve, value va, value vmask)
+{
+  CAMLparam3(ve, va, vmask);
+  phylo_engine *e = Engine_val(ve);
+  uint64_t n = 0;
+  check(e, phylo_bv_saturation(e, Int_val(va), (uint64_t)Long_val(vmask), &n));
+  CAMLreturn(Val_long((intptr_t)n));
+}
+CAMLprim value nonadd_CAML_poly_saturation(value ve, value va, value vn)
+{
+  CAMLparam3(ve, va, vn);
+  phylo_engine *e = Engine_val(ve);
+  uint64_t n = 0;
+  check(e, phylo_bv_poly_saturation(e, Int_val(va), Int_val(vn), &n));
+  CAMLreturn(Val_long((intptr_t)n));
+}
+CAMLprim value nonadd_CAML_compare(value ve, value va, value vb)
+{
+  CAMLparam3(ve, va, vb);
+  phylo_engine *e = Engine_val(ve);
+  int r = 0;
+  check(e, phylo_bv_compare(e, Int_val(va), Int_val(vb), &r));
+  CAMLreturn(Val_int(r));
+}
