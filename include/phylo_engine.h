@@ -60,6 +60,15 @@ int phylo_engine_set_stream(phylo_engine *e, void *cuda_stream);
 int phylo_engine_sync(phylo_engine *e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches evidence) */
 uint64_t phylo_engine_launch_count(const phylo_engine *e);
+/* Engine options. PHYLO_OPT_FUSED_TREE (default 1): phylo_lk_score_tree evaluates eligible
+ * schedules (4 states, K in {1,2,4,8}, plain tree) with the single-launch tree-fused kernel;
+ * 0 = one kernel per node. PHYLO_OPT_RETAIN_CLV (default 1): every interior CLV of a
+ * score_tree call is left in its node slot (for phylo_lk_get_clv / edge_lnl / incremental
+ * re-scoring); 0 = lnL only, the tree-fused kernel then writes no CLV at all. */
+#define PHYLO_OPT_FUSED_TREE 1
+#define PHYLO_OPT_RETAIN_CLV 2
+int phylo_engine_set_option(phylo_engine *e, int option, int64_t value);
+int phylo_engine_get_option(phylo_engine *e, int option, int64_t *value);
 /* CUDA-event profiler: while enabled, every kernel launch is bracketed by an event pair on
  * the engine's stream and its duration accumulated per kernel class (0 <= class <
  * phylo_kernel_class_count()). bench.py's roofline figures come from here. */

@@ -14,6 +14,7 @@
 
 #include "fitch_kernels.cuh"
 #include "lk_kernels.cuh"
+#include "lk_tree_kernel.cuh"
 #include "phylo_engine.h"
 
 using namespace phylo;
@@ -28,11 +29,11 @@ struct LkNode {
 
 // kernel classes for the CUDA-event profiler (phylo_engine_profile_*)
 enum KClass {
-  KC_PT_BUILD = 0, KC_PRUNE_II, KC_PRUNE_TI, KC_PRUNE_TT, KC_ROOT, KC_REDUCE, KC_TIPS_PREPARE,
+  KC_PT_BUILD = 0, KC_TREE_FUSED, KC_PRUNE_II, KC_PRUNE_TI, KC_PRUNE_TT, KC_ROOT, KC_REDUCE, KC_TIPS_PREPARE,
   KC_FITCH_TREE, KC_FITCH_NODE, KC_FITCH_UPPASS, KC_FITCH_TRANSCODE, KC_BV, KC_COUNT
 };
 static const char *kClassNames[KC_COUNT] = {
-    "pt_build", "prune_inner_inner", "prune_tip_inner", "prune_tip_tip", "root_lnl", "reduce1024",
+    "pt_build", "tree_fused", "prune_inner_inner", "prune_tip_inner", "prune_tip_tip", "root_lnl", "reduce1024",
     "tips_prepare", "fitch_tree", "fitch_median2", "fitch_uppass", "fitch_transcode", "bv_setops"};
 
 struct phylo_engine {
@@ -58,7 +59,17 @@ struct phylo_engine {
   // ---- likelihood data
   int T = 0, cap = 0, mask_dev_bytes = 1;
   int64_t N = 0;
-  void *dTips = nullptr;  // T*N masks, device width
+  bool opt_fused = true, opt_retain = true;
+  int64_t tipStride = 0;  // elements per tip row (N rounded up to 1024)
+  double **dNodeClv = nullptr;   // device tables of node buffers (tree-fused kernel)
+  int32_t **dNodeSc = nullptr;
+  bool nodeTabDirty = true;
+  void *dProg = nullptr, *hProg = nullptr;
+  size_t capProg = 0;
+  void *dRaw = nullptr;   // raw tip upload staging (kept across set_tips calls)
+  size_t capRaw = 0;
+  unsigned long long *dBad = nullptr;
+  void *dTips = nullptr;  // T*tipStride masks, device width
   void *dInv = nullptr;   // N masks: AND over tips
   double *dWeights = nullptr;
   std::vector<LkNode> nodes;
@@ -164,6 +175,8 @@ static int grid_for(int64_t work_items, int per_block, int max_blocks) {
   return (int)g;
 }
 
+static int lk_finish_reduce(phylo_engine *e, double *slot);
+
 // ------------------------------------------------------------------------ engine ----
 extern "C" int phylo_engine_create(int device, phylo_engine **out) {
   phylo_engine *e = nullptr;
@@ -202,6 +215,9 @@ static void lk_free_data(phylo_engine *e) {
   }
   e->nodes.clear();
   dfree(e->dTips);
+  dfree(e->dNodeClv);
+  dfree(e->dNodeSc);
+  e->nodeTabDirty = true;
   dfree(e->dInv);
   dfree(e->dWeights);
   dfree(e->dSite);
@@ -229,7 +245,8 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage);
+  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad);
+  if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->hT) cudaFreeHost(e->hT);
   if (e->hScalar) cudaFreeHost(e->hScalar);
@@ -310,12 +327,12 @@ static int ensure_pt_capacity(phylo_engine *e, size_t branches, int S, int K) {
 }
 
 // launches pt_build for branches [0, nb) whose lengths are already in e->hT
-static int build_pt(phylo_engine *e, int nb) {
+static int build_pt(phylo_engine *e, int nb, int interleave = 0) {
   CK(cudaMemcpyAsync(e->dT, e->hT, sizeof(double) * nb, cudaMemcpyHostToDevice, e->stream));
   const int threads = std::min(256, std::max(32, ((e->S * e->S + 31) / 32) * 32));
   ProfScope prof(e, KC_PT_BUILD);
   pt_build_kernel<<<nb * e->K, threads, sizeof(double) * e->S, e->stream>>>(
-      e->dU, e->dLam, e->sym ? nullptr : e->dUi, e->dRates, e->dT, e->S, e->K, e->dP);
+      e->dU, e->dLam, e->sym ? nullptr : e->dUi, e->dRates, e->dT, e->S, e->K, e->dP, interleave);
   LAUNCH_CHECK();
   return PHYLO_OK;
 }
@@ -340,7 +357,7 @@ static int compose_common(phylo_engine *e, const double *U, const double *D, con
     const int threads = std::min(256, std::max(32, ((n * n + 31) / 32) * 32));
     pt_build_kernel<<<1, threads, sizeof(double) * n, e->stream>>>(
         dbuf, dbuf + nn, Ui ? dbuf + nn + n : nullptr, dbuf + 2 * nn + n, dbuf + 2 * nn + n + 1, n, 1,
-        dbuf + 2 * nn + n + 2);
+        dbuf + 2 * nn + n + 2, 0);
     ++e->launches;
     st = cudaGetLastError();
   }
@@ -409,15 +426,15 @@ static int launch_tips_prepare(phylo_engine *e, const void *raw, unsigned long l
   ProfScope prof(e, KC_TIPS_PREPARE);
   switch (e->mask_dev_bytes) {
     case 1:
-      tips_prepare_kernel<InT, uint8_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint8_t *)e->dTips,
+      tips_prepare_kernel<InT, uint8_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint8_t *)e->dTips, e->tipStride,
                                                                  (uint8_t *)e->dInv, e->T, e->N, e->S, dBad);
       break;
     case 4:
-      tips_prepare_kernel<InT, uint32_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint32_t *)e->dTips,
+      tips_prepare_kernel<InT, uint32_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint32_t *)e->dTips, e->tipStride,
                                                                   (uint32_t *)e->dInv, e->T, e->N, e->S, dBad);
       break;
     default:
-      tips_prepare_kernel<InT, uint64_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint64_t *)e->dTips,
+      tips_prepare_kernel<InT, uint64_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint64_t *)e->dTips, e->tipStride,
                                                                   (uint64_t *)e->dInv, e->T, e->N, e->S, dBad);
   }
   LAUNCH_CHECK();
@@ -449,7 +466,13 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     e->T = T; e->N = N; e->cap = capacity;
     e->mask_dev_bytes = dev_mask_bytes(e->S);
     e->nodes.assign(capacity, LkNode());
-    CK(cudaMalloc(&e->dTips, cells * e->mask_dev_bytes));
+    e->tipStride = ((N + kLnlBlock - 1) / kLnlBlock) * kLnlBlock;
+    CK(cudaMalloc(&e->dTips, (size_t)T * e->tipStride * e->mask_dev_bytes));
+    // padding cells read as "all states" (never used in a sum, but keeps them harmless)
+    CK(cudaMemset(e->dTips, 0xff, (size_t)T * e->tipStride * e->mask_dev_bytes));
+    CK(cudaMalloc(&e->dNodeClv, sizeof(double *) * capacity));
+    CK(cudaMalloc(&e->dNodeSc, sizeof(int32_t *) * capacity));
+    e->nodeTabDirty = true;
     CK(cudaMalloc(&e->dInv, (size_t)N * e->mask_dev_bytes));
     if (weights) CK(cudaMalloc(&e->dWeights, sizeof(double) * N));
     e->nPart = (N + kLnlBlock - 1) / kLnlBlock;
@@ -457,15 +480,17 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     CK(cudaMalloc(&e->dPart2, sizeof(double) * ((e->nPart + kLnlBlock - 1) / kLnlBlock + 1) * 2));
     CK(cudaMalloc(&e->dSite, sizeof(double) * N));
   }
-  void *raw = e->dTips;
-  bool tmp = false;
-  if (mask_bytes != e->mask_dev_bytes) {
-    CK(cudaMalloc(&raw, cells * mask_bytes));
-    tmp = true;
+  // the raw upload lands in a staging buffer; tips_prepare writes the padded device rows
+  if (cells * mask_bytes > e->capRaw) {
+    dfree(e->dRaw);
+    e->capRaw = 0;
+    CK(cudaMalloc(&e->dRaw, cells * mask_bytes));
+    e->capRaw = cells * mask_bytes;
   }
-  unsigned long long *dBad = nullptr;
-  cudaError_t st = cudaMalloc(&dBad, sizeof(unsigned long long));
-  if (st == cudaSuccess) st = cudaMemsetAsync(dBad, 0, sizeof(unsigned long long), e->stream);
+  if (!e->dBad) CK(cudaMalloc(&e->dBad, sizeof(unsigned long long)));
+  void *raw = e->dRaw;
+  unsigned long long *dBad = e->dBad;
+  cudaError_t st = cudaMemsetAsync(dBad, 0, sizeof(unsigned long long), e->stream);
   if (st == cudaSuccess) st = cudaMemcpyAsync(raw, masks, cells * mask_bytes, cudaMemcpyHostToDevice, e->stream);
   if (st == cudaSuccess && weights)
     st = cudaMemcpyAsync(e->dWeights, weights, sizeof(double) * N, cudaMemcpyHostToDevice, e->stream);
@@ -483,8 +508,6 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     st = cudaMemcpyAsync(e->hScalar, dBad, sizeof(bad), cudaMemcpyDeviceToHost, e->stream);
   if (st == cudaSuccess && rc == PHYLO_OK) st = cudaStreamSynchronize(e->stream);
   if (st == cudaSuccess && rc == PHYLO_OK) bad = *(unsigned long long *)e->hScalar;
-  if (tmp) cudaFree(raw);
-  cudaFree(dBad);
   if (rc != PHYLO_OK) { lk_free_data(e); return rc; }
   if (st != cudaSuccess) { lk_free_data(e); return fail(e, PHYLO_ERR_CUDA, "lk_set_tips: %s", cudaGetErrorString(st)); }
   if (bad) {
@@ -499,6 +522,7 @@ static int lk_ensure_node(phylo_engine *e, int slot) {
   if (n.clv) return PHYLO_OK;
   CK(cudaMalloc(&n.clv, sizeof(double) * (size_t)e->N * e->K * e->S));
   CK(cudaMalloc(&n.scale, sizeof(int32_t) * (size_t)e->N));
+  e->nodeTabDirty = true;
   return PHYLO_OK;
 }
 
@@ -511,7 +535,7 @@ struct Operand {
 static int lk_operand(phylo_engine *e, int slot, Operand *o, const char *who) {
   if (slot < 0 || slot >= e->cap) return fail(e, PHYLO_ERR_ARG, "%s: node slot %d out of range [0,%d)", who, slot, e->cap);
   if (slot < e->T) {
-    o->src = (const char *)e->dTips + (size_t)slot * e->N * e->mask_dev_bytes;
+    o->src = (const char *)e->dTips + (size_t)slot * e->tipStride * e->mask_dev_bytes;
     o->scale = nullptr;
     o->tip = true;
     return PHYLO_OK;
@@ -644,8 +668,12 @@ static int lk_root_eval(phylo_engine *e, const double *Pr, const Operand &a, con
   }
   LAUNCH_CHECK();
   }
+  return lk_finish_reduce(e, slot);
+}
+
+// remaining levels of the canonical reduction over the level-1 partials, then D2H of the sum
+static int lk_finish_reduce(phylo_engine *e, double *slot) {
   ProfScope prof(e, KC_REDUCE);
-  // remaining levels of the canonical reduction
   const double *cur = e->dPart;
   int64_t n = e->nPart;
   double *bufs[2] = {e->dPart2, e->dPart2 + ((e->nPart + kLnlBlock - 1) / kLnlBlock + 1)};
@@ -659,6 +687,227 @@ static int lk_root_eval(phylo_engine *e, const double *Pr, const Operand &a, con
     n = nb;
   } while (n > 1);
   CK(cudaMemcpyAsync(slot, cur, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_engine_set_option(phylo_engine *e, int option, int64_t value) {
+  if (!e) return PHYLO_ERR_ARG;
+  switch (option) {
+    case PHYLO_OPT_FUSED_TREE: e->opt_fused = value != 0; return PHYLO_OK;
+    case PHYLO_OPT_RETAIN_CLV: e->opt_retain = value != 0; return PHYLO_OK;
+    default: return fail(e, PHYLO_ERR_ARG, "set_option: unknown option %d", option);
+  }
+}
+extern "C" int phylo_engine_get_option(phylo_engine *e, int option, int64_t *value) {
+  if (!e || !value) return PHYLO_ERR_ARG;
+  switch (option) {
+    case PHYLO_OPT_FUSED_TREE: *value = e->opt_fused; return PHYLO_OK;
+    case PHYLO_OPT_RETAIN_CLV: *value = e->opt_retain; return PHYLO_OK;
+    default: return fail(e, PHYLO_ERR_ARG, "get_option: unknown option %d", option);
+  }
+}
+
+struct FusedPlan {
+  std::vector<TreeInstr> prog;  // n_instr steps + the root step
+  std::vector<double> tlen;     // 2*n_instr + 1 branch lengths in program order
+  int depth = 0;
+};
+
+// Re-derives a depth-first order of the (already validated, post-order) schedule in which
+// the child with the larger stack need is evaluated first, and assigns every operand one of
+// TIP / STORED / CUR (just computed, in registers) / POP (parked on the stack).
+// Returns false when the schedule is not a plain tree (a result used twice or never).
+static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt,
+                             FusedPlan &pl) {
+  const int cap = e->cap, T = e->T;
+  if (n_ops > 100000) return false;
+  std::vector<int> producer(cap, -1), uses(cap, 0), need(cap, 0);
+  for (int o = 0; o < n_ops; ++o) {
+    if (producer[ops[o].parent] != -1) return false;
+    producer[ops[o].parent] = o;
+    ++uses[ops[o].left];
+    ++uses[ops[o].right];
+  }
+  ++uses[ra];
+  ++uses[rb];
+  if (ra == rb) return false;
+  for (int s = 0; s < cap; ++s)
+    if (producer[s] >= 0 && uses[s] != 1) return false;
+  auto computed = [&](int s) { return producer[s] >= 0; };
+  for (int o = 0; o < n_ops; ++o) {
+    const int l = ops[o].left, r = ops[o].right, p = ops[o].parent;
+    const bool cl = computed(l), cr = computed(r);
+    if (cl && cr) need[p] = need[l] == need[r] ? need[l] + 1 : std::max(need[l], need[r]);
+    else need[p] = cl ? need[l] : (cr ? need[r] : 0);
+  }
+  bool live = false;
+  int depth = 0, maxdepth = 0;
+  auto kind = [&](int child, bool both, int first, int &idx) {
+    idx = child;
+    if (child < T) return (int)OPK_TIP;
+    if (!computed(child)) return (int)OPK_STORED;
+    return (both && child == first) ? (int)OPK_POP : (int)OPK_CUR;
+  };
+  // iterative post-order with explicit frames (caterpillars are thousands deep)
+  struct Frame { int slot, stage; };
+  auto emit_subtree = [&](int root) {
+    if (!computed(root)) return;
+    std::vector<Frame> st;
+    st.push_back({root, 0});
+    while (!st.empty()) {
+      Frame &f = st.back();
+      const phylo_op &op = ops[producer[f.slot]];
+      const bool cl = computed(op.left), cr = computed(op.right);
+      const int first = (cl && cr) ? (need[op.left] >= need[op.right] ? op.left : op.right)
+                                   : (cl ? op.left : (cr ? op.right : -1));
+      const int second = (cl && cr) ? (first == op.left ? op.right : op.left) : -1;
+      if (f.stage == 0) {
+        f.stage = 1;
+        if (first >= 0) { st.push_back({first, 0}); continue; }
+      }
+      if (f.stage == 1) {
+        f.stage = 2;
+        if (second >= 0) { st.push_back({second, 0}); continue; }
+      }
+      TreeInstr in{};
+      in.lkind = kind(op.left, cl && cr, first, in.lidx);
+      in.rkind = kind(op.right, cl && cr, first, in.ridx);
+      in.push_first = (!cl && !cr && live) ? 1 : 0;
+      in.out_slot = op.parent;
+      if (in.push_first) maxdepth = std::max(maxdepth, ++depth);
+      if (in.lkind == OPK_POP || in.rkind == OPK_POP) --depth;
+      live = true;
+      pl.prog.push_back(in);
+      pl.tlen.push_back(op.t_left);
+      pl.tlen.push_back(op.t_right);
+      st.pop_back();
+    }
+  };
+  const bool ca = computed(ra), cb = computed(rb);
+  const int first = (ca && cb) ? (need[ra] >= need[rb] ? ra : rb) : -1;
+  if (ca && cb) {
+    emit_subtree(first);
+    emit_subtree(first == ra ? rb : ra);
+  } else {
+    emit_subtree(ra);
+    emit_subtree(rb);
+  }
+  TreeInstr root{};
+  root.lkind = kind(ra, ca && cb, first, root.lidx);
+  root.rkind = kind(rb, ca && cb, first, root.ridx);
+  root.push_first = 0;
+  root.out_slot = -1;
+  // a stored/tip operand on one side and a computed one on the other: the computed one is CUR
+  pl.prog.push_back(root);
+  pl.tlen.push_back(rt);
+  pl.depth = std::max(maxdepth, 1);
+  return (int)pl.prog.size() == n_ops + 1;
+}
+
+static size_t tree_smem_bytes(int K, int R, int T, int depth) {
+  const size_t tile = (size_t)kTreeThreads * R / K;
+  return (size_t)kLnlBlock * 8 + 32 * 8 + (2 + kRing + 2) * 8 + (size_t)kRing * 2 * 16 * K * 8 +
+         (size_t)depth * R * kTreeThreads * (sizeof(d4) + sizeof(int)) + 128 + 2 * (size_t)T * tile;
+}
+
+template <int K, int R>
+static cudaError_t launch_tree(phylo_engine *e, const TreeArgs &args, size_t smem, bool retain) {
+  const int64_t nblocks = (e->N + kLnlBlock - 1) / kLnlBlock;
+  const int g = (int)std::min<int64_t>(nblocks, e->sm_count);
+  cudaError_t st;
+  if (retain) {
+    auto kern = lk_tree4_kernel<K, R, true>;
+    if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
+    kern<<<g, kTreeThreads, smem, e->stream>>>(args);
+  } else {
+    auto kern = lk_tree4_kernel<K, R, false>;
+    if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
+    kern<<<g, kTreeThreads, smem, e->stream>>>(args);
+  }
+  return cudaSuccess;
+}
+
+// returns PHYLO_OK with *done = true when the fused kernel handled the evaluation
+static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt,
+                               bool *done) {
+  *done = false;
+  if (!e->opt_fused || e->S != 4 || e->mask_dev_bytes != 1) return PHYLO_OK;
+  if (!(e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8)) return PHYLO_OK;
+  FusedPlan pl;
+  if (!build_fused_plan(e, ops, n_ops, ra, rb, rt, pl)) return PHYLO_OK;
+  const size_t kMaxSmem = 227 * 1024;
+  int R = 2;
+  if ((kTreeThreads * R / e->K) > kLnlBlock || tree_smem_bytes(e->K, R, e->T, pl.depth) > kMaxSmem) R = 1;
+  const size_t smem = tree_smem_bytes(e->K, R, e->T, pl.depth);
+  if (smem > kMaxSmem || (kTreeThreads * R / e->K) < 16) return PHYLO_OK;  // per-node kernels instead
+  int rc;
+  const int nb = 2 * n_ops + 1;
+  if ((rc = ensure_pt_capacity(e, nb, e->S, e->K)) != PHYLO_OK) return rc;
+  if (e->opt_retain)
+    for (int o = 0; o < n_ops; ++o)
+      if ((rc = lk_ensure_node(e, ops[o].parent)) != PHYLO_OK) return rc;
+  const size_t pbytes = sizeof(TreeInstr) * pl.prog.size();
+  if (pbytes > e->capProg) {
+    CK(cudaStreamSynchronize(e->stream));
+    dfree(e->dProg);
+    if (e->hProg) { cudaFreeHost(e->hProg); e->hProg = nullptr; }
+    e->capProg = 0;
+    CK(cudaMalloc(&e->dProg, pbytes * 2));
+    CK(cudaMallocHost(&e->hProg, pbytes * 2));
+    e->capProg = pbytes * 2;
+  }
+  CK(cudaStreamSynchronize(e->stream));  // pinned staging (hT, hProg) is about to be rewritten
+  if (e->nodeTabDirty) {
+    std::vector<double *> hc(e->cap);
+    std::vector<int32_t *> hs(e->cap);
+    for (int s = 0; s < e->cap; ++s) { hc[s] = e->nodes[s].clv; hs[s] = e->nodes[s].scale; }
+    CK(cudaMemcpy(e->dNodeClv, hc.data(), sizeof(double *) * e->cap, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->dNodeSc, hs.data(), sizeof(int32_t *) * e->cap, cudaMemcpyHostToDevice));
+    e->nodeTabDirty = false;
+  }
+  std::memcpy(e->hProg, pl.prog.data(), pbytes);
+  std::memcpy(e->hT, pl.tlen.data(), sizeof(double) * nb);
+  CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = build_pt(e, nb, 1)) != PHYLO_OK) return rc;
+  TreeArgs a;
+  a.prog = (const TreeInstr *)e->dProg;
+  a.n_instr = n_ops;
+  a.P = e->dP;
+  a.tips = (const uint8_t *)e->dTips;
+  a.tip_stride = e->tipStride;
+  a.T = e->T;
+  a.N = e->N;
+  a.node_clv = e->dNodeClv;
+  a.node_sc = e->dNodeSc;
+  a.pi = e->dPi;
+  a.probs = e->dProbs;
+  a.pinvar = e->pinvar;
+  a.inv = (const uint8_t *)e->dInv;
+  a.weights = e->dWeights;
+  a.site_lnl = e->dSite;
+  a.partials = e->dPart;
+  a.stack_depth = pl.depth;
+  cudaError_t st = cudaSuccess;
+  {
+    ProfScope prof(e, KC_TREE_FUSED);
+#define TREE(KK)                                                                    \
+  st = (R == 2) ? launch_tree<KK, 2>(e, a, smem, e->opt_retain) : launch_tree<KK, 1>(e, a, smem, e->opt_retain)
+    switch (e->K) {
+      case 1: st = launch_tree<1, 1>(e, a, smem, e->opt_retain); break;
+      case 2: TREE(2); break;
+      case 4: TREE(4); break;
+      default: TREE(8);
+    }
+#undef TREE
+    if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch setup: %s", cudaGetErrorString(st));
+    LAUNCH_CHECK();
+  }
+  if (e->opt_retain)
+    for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = true;
+  else
+    for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = false;
+  if ((rc = lk_finish_reduce(e, e->hScalar)) != PHYLO_OK) return rc;
+  *done = true;
   return PHYLO_OK;
 }
 
@@ -711,6 +960,17 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
     }
     if (root_a < 0 || root_a >= e->cap || root_b < 0 || root_b >= e->cap || !ready[root_a] || !ready[root_b])
       return fail(e, PHYLO_ERR_ARG, "lk_score_tree: bad root edge (%d,%d)", root_a, root_b);
+  }
+  {
+    bool done = false;
+    if ((rc = lk_score_tree_fused(e, ops, n_ops, root_a, root_b, root_t, &done)) != PHYLO_OK) return rc;
+    if (done) {
+      CK(cudaStreamSynchronize(e->stream));
+      *lnl_out = e->hScalar[0];
+      e->lk_evaluated = true;
+      if (e->prof_on) prof_resolve(e);
+      return PHYLO_OK;
+    }
   }
   const int nb = 2 * n_ops + 1;
   if ((rc = ensure_pt_capacity(e, nb, e->S, e->K)) != PHYLO_OK) return rc;

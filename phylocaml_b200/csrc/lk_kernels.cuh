@@ -21,7 +21,7 @@ namespace phylo {
 __global__ void pt_build_kernel(const double *__restrict__ U, const double *__restrict__ lam,
                                 const double *__restrict__ Ui, const double *__restrict__ rates,
                                 const double *__restrict__ tlen, int S, int K,
-                                double *__restrict__ P) {
+                                double *__restrict__ P, int interleave) {
   extern __shared__ double sh_e[];
   const int b = blockIdx.x / K, k = blockIdx.x % K;
   const bool sym = (Ui == nullptr);
@@ -31,7 +31,9 @@ __global__ void pt_build_kernel(const double *__restrict__ U, const double *__re
   for (int m = threadIdx.x; m < S; m += blockDim.x)
     sh_e[m] = (mode == 2) ? lam[m] : exp(lam[m] * tau);
   __syncthreads();
-  double *out = P + (size_t)blockIdx.x * S * S;
+  // interleave (4-state tree-fused kernel): per branch [e/2][k][e%2] so the K lanes of a
+  // pattern read adjacent 16-byte chunks of shared memory; otherwise [k][i][j]
+  double *out = interleave ? P + (size_t)b * K * S * S : P + (size_t)blockIdx.x * S * S;
   for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
     const int i = idx / S, j = idx % S;
     double acc;
@@ -45,7 +47,7 @@ __global__ void pt_build_kernel(const double *__restrict__ U, const double *__re
         for (int m = 0; m < S; ++m) acc += U[i * S + m] * (sh_e[m] * Ui[m * S + j]);
       }
     }
-    out[idx] = acc;
+    out[interleave ? ((idx >> 1) * K + k) * 2 + (idx & 1) : idx] = acc;
   }
 }
 
@@ -552,13 +554,15 @@ root_any_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
 }
 
 // ----------------------------------------------------------------- tip preparation ----
-// Converts raw tip masks of any element width to the device width, masks off bits >= S,
+// Converts raw tip masks of any element width to the device width (rows padded to
+// out_stride elements so bulk-TMA tile loads stay aligned and in bounds), masks off bits >= S,
 // counts invalid (empty) masks and builds the per-pattern AND over all tips (used by the
 // invariant-sites term).
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
-tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, OutT *__restrict__ inv,
-                    int T, int64_t N, int S, unsigned long long *__restrict__ n_bad) {
+tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, int64_t out_stride,
+                    OutT *__restrict__ inv, int T, int64_t N, int S,
+                    unsigned long long *__restrict__ n_bad) {
   const uint64_t keep = (S >= 64) ? ~0ull : ((1ull << S) - 1);
   unsigned long long bad = 0;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N;
@@ -566,7 +570,7 @@ tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, OutT *__
     uint64_t all = keep;
     for (int t = 0; t < T; ++t) {
       const uint64_t m = (uint64_t)in[(int64_t)t * N + p] & keep;
-      out[(int64_t)t * N + p] = (OutT)m;
+      out[(int64_t)t * out_stride + p] = (OutT)m;
       if (m == 0) ++bad;
       all &= m;
     }

@@ -35,6 +35,8 @@ SIGNATURES = {
     "phylo_engine_set_stream": (C.c_int, [_vp, _vp]),
     "phylo_engine_sync": (C.c_int, [_vp]),
     "phylo_engine_launch_count": (C.c_uint64, [_vp]),
+    "phylo_engine_set_option": (C.c_int, [_vp, C.c_int, _i64]),
+    "phylo_engine_get_option": (C.c_int, [_vp, C.c_int, C.POINTER(_i64)]),
     "phylo_engine_profile": (C.c_int, [_vp, C.c_int]),
     "phylo_engine_profile_reset": (C.c_int, [_vp]),
     "phylo_engine_profile_get": (C.c_int, [_vp, C.c_int, _dp, _u64p]),
@@ -194,6 +196,16 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.phylo_engine_launch_count(self.h))
+
+    OPT_FUSED_TREE, OPT_RETAIN_CLV = 1, 2
+
+    def set_option(self, option, value):
+        self._ck(self.lib.phylo_engine_set_option(self.h, option, int(value)))
+
+    def get_option(self, option):
+        v = _i64()
+        self._ck(self.lib.phylo_engine_get_option(self.h, option, C.byref(v)))
+        return v.value
 
     def profile(self, enable=True, reset=False):
         if reset:

@@ -325,3 +325,97 @@ def test_bv_set_algebra(eng, oracle):
     eng.fitch_set_states(6, b)
     eng.bv_union(7, 6, 6)
     assert np.array_equal(eng.fitch_get_states(7), b)
+
+
+# ------------------------------------------------------------ tree-fused kernel ----
+def _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused, retain, weights=None):
+    eng.set_option(eng.OPT_FUSED_TREE, fused)
+    eng.set_option(eng.OPT_RETAIN_CLV, retain)
+    try:
+        eng.lk_set_model(model)
+        eng.lk_set_tips(tips, weights=weights, capacity=n_nodes)
+        before = eng.profile_get().get("tree_fused", (0, 0))[1]
+        lnl = eng.lk_score_tree(ops, ra, rb, rt)
+        used_fused = eng.profile_get().get("tree_fused", (0, 0))[1] > before
+        return lnl, used_fused
+    finally:
+        eng.set_option(eng.OPT_FUSED_TREE, 1)
+        eng.set_option(eng.OPT_RETAIN_CLV, 1)
+
+
+@pytest.mark.parametrize("T,N,kind", [(16, 10000, "random"), (64, 3000, "random"), (200, 700, "caterpillar"),
+                                      (3, 50, "random"), (2, 33, "random"), (40, 1, "random")])
+def test_fused_tree_equals_per_node_path_bitwise(eng, oracle, T, N, kind):
+    """The single-launch tree-fused kernel and the one-kernel-per-node path run the same
+    arithmetic in the same order: lnL, site lnL, CLVs and scale counters are bit-identical;
+    both are within 1e-9 of the oracle."""
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(T, N, model, seed=31, tree_kind=kind, mean_bl=0.3)
+    eng.profile(True)
+    try:
+        a, fa = _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=1)
+        site_a = eng.lk_get_site_lnl()
+        clv_a = [eng.lk_get_clv(int(op["parent"])) for op in ops[-3:]]
+        b, fb = _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused=0, retain=1)
+        site_b = eng.lk_get_site_lnl()
+        clv_b = [eng.lk_get_clv(int(op["parent"])) for op in ops[-3:]]
+        c, fc = _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=0)
+    finally:
+        eng.profile(False)
+    assert fa and fc and not fb
+    assert a == b == c
+    assert np.array_equal(site_a, site_b)
+    for (ca, sa), (cb, sb) in zip(clv_a, clv_b):
+        assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
+    want = oracle.lk_score_tree(model, tips, None, ops, n_nodes, ra, rb, rt)["lnl"]
+    assert rel_err(a, want) <= LNL_RTOL
+
+
+@pytest.mark.parametrize("K", [1, 2, 8])
+def test_fused_tree_other_rate_counts(eng, oracle, K):
+    sv = ("gamma", K, 0.8) if K > 1 else None
+    m = mlmodel.create(("HKY85", 2.0), 4, pi=[0.1, 0.2, 0.3, 0.4], site_var=sv)
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(20, 2100, m, seed=5)
+    eng.profile(True)
+    try:
+        a, fa = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=1)
+        b, fb = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=0, retain=1)
+    finally:
+        eng.profile(False)
+    assert fa and not fb and a == b
+    assert rel_err(a, oracle.lk_score_tree(m, tips, None, ops, n_nodes, ra, rb, rt)["lnl"]) <= LNL_RTOL
+
+
+def test_fused_tree_no_retain_leaves_no_clvs(eng):
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(10, 500, model, seed=2)
+    _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=0)
+    with pytest.raises(engine.PhyloError):
+        eng.lk_get_clv(int(ops[0]["parent"]))
+
+
+def test_fused_tree_incremental_rescoring_from_stored_clvs(eng, oracle):
+    """After a full evaluation, change one branch and re-evaluate only the path from that
+    branch to the root edge: the other operands are CLVs already resident in HBM (OPK_STORED).
+    Result == full re-evaluation of the modified tree."""
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(24, 3000, model, seed=12)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    eng.lk_score_tree(ops, ra, rb, rt)
+    ops2 = ops.copy()
+    i0 = 4
+    ops2[i0]["t_left"] *= 3.0
+    # path from op i0's parent up to its root end
+    parent_of = {int(o["left"]): j for j, o in enumerate(ops2)}
+    parent_of.update({int(o["right"]): j for j, o in enumerate(ops2)})
+    path, j = [i0], i0
+    while int(ops2[j]["parent"]) in parent_of:
+        j = parent_of[int(ops2[j]["parent"])]
+        path.append(j)
+    sub = ops2[sorted(path)]
+    inc = eng.lk_score_tree(sub, ra, rb, rt)
+    full = oracle.lk_score_tree(model, tips, None, ops2, n_nodes, ra, rb, rt)["lnl"]
+    assert rel_err(inc, full) <= LNL_RTOL
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    assert eng.lk_score_tree(ops2, ra, rb, rt) == inc

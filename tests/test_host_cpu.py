@@ -157,3 +157,25 @@ def test_shard_bounds_cover_and_align():
         assert spans[0][0] == 0 and spans[-1][1] == N
         for (a, b), (c, d) in zip(spans, spans[1:]):
             assert b == c and (b % 1024 == 0 or b == N)
+
+
+def test_ocaml_stubs_compile_and_cover_the_plugin_surface(tmp_path):
+    """stubs/phylo_stubs.c compiles against the (fake) caml headers and defines the stubs the
+    reference's externs name (lib/mlmodel.h:39-43) plus one stub per new external in ocaml/."""
+    obj = tmp_path / "phylo_stubs.o"
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-fPIC", "-I" + os.path.join(ROOT, "oracle", "shim"),
+                    "-I" + os.path.join(ROOT, "include"), "-c", os.path.join(ROOT, "stubs", "phylo_stubs.c"),
+                    "-o", str(obj)], check=True)
+    syms = subprocess.run(["nm", str(obj)], capture_output=True, text=True).stdout
+    defined = set(re.findall(r" T (\w+)", syms))
+    for name in ("likelihood_CAML_compose_gtr", "likelihood_CAML_compose_sym",
+                 "likelihood_CAML_diagonalize_gtr", "likelihood_CAML_diagonalize_sym"):
+        assert name in defined, name
+    externs = set()
+    for fn in ("likelihood_c.ml", "nonAdditive_c.ml"):
+        with open(os.path.join(ROOT, "ocaml", fn)) as f:
+            externs |= set(re.findall(r'=\s*"(\w+_CAML_\w+)"', f.read()))
+    assert externs and externs <= defined, externs - defined
+    # every C-ABI function the stubs call is declared in the header
+    called = set(re.findall(r" U (phylo_\w+)", syms))
+    assert called and called <= set(_declared_symbols())
