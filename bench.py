@@ -75,12 +75,16 @@ def shard_bounds(N, world, rank, align=1024):
     return min(lo_b * align, N), min(hi_b * align, N)
 
 
-def lk_bytes(T, S, K, tip_bytes):
-    """SURVEY.md 8(d) per-node streaming model, bytes per pattern per launch."""
+def lk_bytes(T, S, K, tip_bytes, mode="pernode"):
+    """Algorithmic bytes per pattern per launch. Per-node kernels: SURVEY.md 8(d) streaming
+    model. Tree-fused kernel: compulsory traffic -- every interior CLV (+ scale counter)
+    written once and every tip cell read once when CLVs are retained; tips only otherwise."""
     C = S * K * 8
-    return dict(prune_inner_inner=3 * C + 12, prune_tip_inner=2 * C + tip_bytes + 8,
-                prune_tip_tip=C + 2 * tip_bytes + 4, root_lnl=2 * C + 8,
-                tree=(2 * T - 3) * C + T * tip_bytes + (2 * T - 3) * 4)
+    d = dict(prune_inner_inner=3 * C + 12, prune_tip_inner=2 * C + tip_bytes + 8,
+             prune_tip_tip=C + 2 * tip_bytes + 4, root_lnl=2 * C + 8,
+             tree=(2 * T - 3) * C + T * tip_bytes + (2 * T - 3) * 4)
+    d["tree_fused"] = (T - 2) * (C + 4) + T * tip_bytes if mode == "fused" else T * tip_bytes
+    return d
 
 
 class ClockSampler:
@@ -234,6 +238,10 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fused", choices=["fused", "fused-lnl", "pernode"],
+                    help="likelihood path: tree-fused kernel keeping every CLV (default), tree-fused "
+                         "lnL-only (no CLV written), or one streaming kernel per node")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other modes")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     wl = dict(WORKLOADS[args.workload])
@@ -302,6 +310,12 @@ def main():
         model = make_model(wl)
         tips = build_tips(tree_mod, tr, model, T, n_local, S, rank)
         eng.lk_set_model(model)
+
+        def set_mode(mode):
+            eng.set_option(eng.OPT_FUSED_TREE, 0 if mode == "pernode" else 1)
+            eng.set_option(eng.OPT_RETAIN_CLV, 0 if mode == "fused-lnl" else 1)
+
+        set_mode(args.mode)
         eng.lk_set_tips(tips, capacity=n_nodes)
         acc = torch.zeros(1, dtype=torch.float64, device="cuda")
 
@@ -319,7 +333,7 @@ def main():
 
         metric, unit, dtype = "clv_site_updates_per_s", "site-updates/s", "f64"
         units_per_step = (T - 1) * n_total
-        kbytes = lk_bytes(T, S, K, tips.dtype.itemsize)
+        kbytes = lk_bytes(T, S, K, tips.dtype.itemsize, args.mode)
         h2d = tips.nbytes + ops.nbytes
 
     for _ in range(args.warmup):
@@ -368,12 +382,15 @@ def main():
                         traffic = t["dram_bytes_per_launch"] * n_local / t["patterns"]
                 roof = {"bound": "hbm", "kernel": name, "achieved": entry["achieved_gbs"], "peak": hbm_peak,
                         "unit": "GB/s", "frac": entry["frac"], "traffic": traffic, "peak_source": peak_src,
-                        "bytes_model": "SURVEY 8(d) per-node streaming" if args.workload != "fitch"
+                        "bytes_model": ("compulsory (tree-fused: each interior CLV + scale counter written once, "
+                                        "tips read once)" if name == "tree_fused" else
+                                        "SURVEY 8(d) per-node streaming") if args.workload != "fitch"
                         else "compulsory (tree-fused: every node set moved once)"}
         kernels[name] = entry
     if args.workload != "fitch":
         step_bytes = kbytes["tree"] * n_local
-        roof_step = {"algorithmic_bytes_per_step": step_bytes,
+        roof_step = {"bytes_model": "SURVEY 8(d) per-node streaming (what a kernel-per-node engine must move)",
+                     "algorithmic_bytes_per_step": step_bytes,
                      "achieved_gbs": step_bytes / (ms * 1e-3 / args.steps) / 1e9}
         roof_step["frac"] = roof_step["achieved_gbs"] / hbm_peak
     else:
@@ -394,6 +411,32 @@ def main():
     e2e_val = units_per_step * args.e2e_steps / (float(tms.item()) * 1e-3)
     e2e = {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
            "ms_per_step": float(tms.item()) / args.e2e_steps, "steps": args.e2e_steps}
+
+    # ---- the other likelihood modes, briefly (same inputs, same timing method)
+    modes = None
+    if args.workload != "fitch" and not args.no_other_modes:
+        modes = {args.mode: {"value": value, "ms_per_step": ms / args.steps, "lnl": result}}
+        for m in ("fused", "fused-lnl", "pernode"):
+            if m == args.mode:
+                continue
+            set_mode(m)
+            for _ in range(2):
+                r_m = step()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nm = max(3, args.steps // 4)
+            barrier()
+            m0.record()
+            for _ in range(nm):
+                r_m = step()
+            m1.record()
+            barrier()
+            tm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            modes[m] = {"value": units_per_step * nm / (float(tm.item()) * 1e-3),
+                        "ms_per_step": float(tm.item()) / nm, "lnl": r_m}
+        set_mode(args.mode)
+        step()  # leave the engine's site lnL / CLVs in the primary mode's state
 
     # ---- CPU baseline + correctness spot check (rank 0, N=1 only)
     cpu, check = None, {"result": result, "result_e2e": result_e2e}
@@ -423,6 +466,7 @@ def main():
                              ((kbytes.get("tree", 64) * n_local) / 1e9),
                        "sharding": "contiguous 1024-aligned pattern slabs, one process per GPU",
                        "collective": "allreduce of one scalar per step" if world > 1 else "none"},
+            "mode": args.mode if args.workload != "fitch" else None, "modes": modes,
             "roofline": roof, "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(step_launches * args.steps),
             "gpu_launches_total_incl_warmup": int(launches), "clocks": clocks, "check": check,

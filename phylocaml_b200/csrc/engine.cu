@@ -804,24 +804,28 @@ static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_o
   return (int)pl.prog.size() == n_ops + 1;
 }
 
-static size_t tree_smem_bytes(int K, int R, int T, int depth) {
-  const size_t tile = (size_t)kTreeThreads * R / K;
-  return (size_t)kLnlBlock * 8 + 32 * 8 + (2 + kRing + 2) * 8 + (size_t)kRing * 2 * 16 * K * 8 +
-         (size_t)depth * R * kTreeThreads * (sizeof(d4) + sizeof(int)) + 128 + 2 * (size_t)T * tile;
+static size_t tree_smem_bytes(int K, int T, int depth, int n_steps) {
+  const size_t tile = (size_t)kTreeThreads / K;
+  return (size_t)kLnlBlock * 8 + 32 * 8 + 4 * 8 + (size_t)depth * kTreeThreads * (sizeof(d4) + sizeof(int)) +
+         (size_t)(n_steps + 1) * sizeof(TreeInstr) + 128 + 2 * (size_t)T * tile;
 }
 
-template <int K, int R>
+template <int K>
 static cudaError_t launch_tree(phylo_engine *e, const TreeArgs &args, size_t smem, bool retain) {
   const int64_t nblocks = (e->N + kLnlBlock - 1) / kLnlBlock;
-  const int g = (int)std::min<int64_t>(nblocks, e->sm_count);
   cudaError_t st;
+  int occ = 1;
   if (retain) {
-    auto kern = lk_tree4_kernel<K, R, true>;
+    auto kern = lk_tree4_kernel<K, true>;
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTreeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    const int g = (int)std::min<int64_t>(nblocks, (int64_t)e->sm_count * occ);
     kern<<<g, kTreeThreads, smem, e->stream>>>(args);
   } else {
-    auto kern = lk_tree4_kernel<K, R, false>;
+    auto kern = lk_tree4_kernel<K, false>;
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTreeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    const int g = (int)std::min<int64_t>(nblocks, (int64_t)e->sm_count * occ);
     kern<<<g, kTreeThreads, smem, e->stream>>>(args);
   }
   return cudaSuccess;
@@ -836,10 +840,8 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   FusedPlan pl;
   if (!build_fused_plan(e, ops, n_ops, ra, rb, rt, pl)) return PHYLO_OK;
   const size_t kMaxSmem = 227 * 1024;
-  int R = 2;
-  if ((kTreeThreads * R / e->K) > kLnlBlock || tree_smem_bytes(e->K, R, e->T, pl.depth) > kMaxSmem) R = 1;
-  const size_t smem = tree_smem_bytes(e->K, R, e->T, pl.depth);
-  if (smem > kMaxSmem || (kTreeThreads * R / e->K) < 16) return PHYLO_OK;  // per-node kernels instead
+  const size_t smem = tree_smem_bytes(e->K, e->T, pl.depth, (int)pl.prog.size());
+  if (smem > kMaxSmem) return PHYLO_OK;  // very deep / very wide trees: per-node kernels instead
   int rc;
   const int nb = 2 * n_ops + 1;
   if ((rc = ensure_pt_capacity(e, nb, e->S, e->K)) != PHYLO_OK) return rc;
@@ -865,6 +867,12 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     CK(cudaMemcpy(e->dNodeSc, hs.data(), sizeof(int32_t *) * e->cap, cudaMemcpyHostToDevice));
     e->nodeTabDirty = false;
   }
+  for (auto &in : pl.prog) {
+    in.out_clv = (e->opt_retain && in.out_slot >= 0) ? e->nodes[in.out_slot].clv : nullptr;
+    in.out_sc = (e->opt_retain && in.out_slot >= 0) ? e->nodes[in.out_slot].scale : nullptr;
+    in.l_clv = in.lkind == OPK_STORED ? e->nodes[in.lidx].clv : nullptr;
+    in.r_clv = in.rkind == OPK_STORED ? e->nodes[in.ridx].clv : nullptr;
+  }
   std::memcpy(e->hProg, pl.prog.data(), pbytes);
   std::memcpy(e->hT, pl.tlen.data(), sizeof(double) * nb);
   CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
@@ -877,7 +885,6 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   a.tip_stride = e->tipStride;
   a.T = e->T;
   a.N = e->N;
-  a.node_clv = e->dNodeClv;
   a.node_sc = e->dNodeSc;
   a.pi = e->dPi;
   a.probs = e->dProbs;
@@ -890,15 +897,12 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   cudaError_t st = cudaSuccess;
   {
     ProfScope prof(e, KC_TREE_FUSED);
-#define TREE(KK)                                                                    \
-  st = (R == 2) ? launch_tree<KK, 2>(e, a, smem, e->opt_retain) : launch_tree<KK, 1>(e, a, smem, e->opt_retain)
     switch (e->K) {
-      case 1: st = launch_tree<1, 1>(e, a, smem, e->opt_retain); break;
-      case 2: TREE(2); break;
-      case 4: TREE(4); break;
-      default: TREE(8);
+      case 1: st = launch_tree<1>(e, a, smem, e->opt_retain); break;
+      case 2: st = launch_tree<2>(e, a, smem, e->opt_retain); break;
+      case 4: st = launch_tree<4>(e, a, smem, e->opt_retain); break;
+      default: st = launch_tree<8>(e, a, smem, e->opt_retain);
     }
-#undef TREE
     if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch setup: %s", cudaGetErrorString(st));
     LAUNCH_CHECK();
   }
