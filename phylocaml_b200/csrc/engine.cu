@@ -69,6 +69,7 @@ struct phylo_engine {
   void *dRaw = nullptr;   // raw tip upload staging (kept across set_tips calls)
   size_t capRaw = 0;
   unsigned long long *dBad = nullptr;
+  uint8_t *dTips4 = nullptr;  // 4-state only: nibble-packed copy of dTips for the tree-fused kernel
   void *dTips = nullptr;  // T*tipStride masks, device width
   void *dInv = nullptr;   // N masks: AND over tips
   double *dWeights = nullptr;
@@ -215,6 +216,7 @@ static void lk_free_data(phylo_engine *e) {
   }
   e->nodes.clear();
   dfree(e->dTips);
+  dfree(e->dTips4);
   dfree(e->dNodeClv);
   dfree(e->dNodeSc);
   e->nodeTabDirty = true;
@@ -470,6 +472,7 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     CK(cudaMalloc(&e->dTips, (size_t)T * e->tipStride * e->mask_dev_bytes));
     // padding cells read as "all states" (never used in a sum, but keeps them harmless)
     CK(cudaMemset(e->dTips, 0xff, (size_t)T * e->tipStride * e->mask_dev_bytes));
+    if (e->S == 4) CK(cudaMalloc(&e->dTips4, (size_t)T * e->tipStride / 2));
     CK(cudaMalloc(&e->dNodeClv, sizeof(double *) * capacity));
     CK(cudaMalloc(&e->dNodeSc, sizeof(int32_t *) * capacity));
     e->nodeTabDirty = true;
@@ -502,6 +505,13 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
       case 4: rc = launch_tips_prepare<uint32_t>(e, raw, dBad); break;
       default: rc = launch_tips_prepare<uint64_t>(e, raw, dBad);
     }
+  }
+  if (st == cudaSuccess && rc == PHYLO_OK && e->dTips4) {
+    ProfScope prof(e, KC_TIPS_PREPARE);
+    tips_pack4_kernel<<<grid_for((int64_t)T * e->tipStride / 2, 256, e->sm_count * 8), 256, 0, e->stream>>>(
+        (const uint8_t *)e->dTips, e->dTips4, T, N, e->tipStride);
+    ++e->launches;
+    st = cudaGetLastError();
   }
   unsigned long long bad = 0;
   if (st == cudaSuccess && rc == PHYLO_OK)
@@ -770,12 +780,13 @@ static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_o
         if (second >= 0) { st.push_back({second, 0}); continue; }
       }
       TreeInstr in{};
-      in.lkind = kind(op.left, cl && cr, first, in.lidx);
-      in.rkind = kind(op.right, cl && cr, first, in.ridx);
-      in.push_first = (!cl && !cr && live) ? 1 : 0;
+      const int lk = kind(op.left, cl && cr, first, in.lidx);
+      const int rk = kind(op.right, cl && cr, first, in.ridx);
+      const int push_first = (!cl && !cr && live) ? 1 : 0;
+      in.kinds = lk | (rk << 2) | (push_first << 4);
       in.out_slot = op.parent;
-      if (in.push_first) maxdepth = std::max(maxdepth, ++depth);
-      if (in.lkind == OPK_POP || in.rkind == OPK_POP) --depth;
+      if (push_first) maxdepth = std::max(maxdepth, ++depth);
+      if (lk == OPK_POP || rk == OPK_POP) --depth;
       live = true;
       pl.prog.push_back(in);
       pl.tlen.push_back(op.t_left);
@@ -793,9 +804,11 @@ static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_o
     emit_subtree(rb);
   }
   TreeInstr root{};
-  root.lkind = kind(ra, ca && cb, first, root.lidx);
-  root.rkind = kind(rb, ca && cb, first, root.ridx);
-  root.push_first = 0;
+  {
+    const int lk = kind(ra, ca && cb, first, root.lidx);
+    const int rk = kind(rb, ca && cb, first, root.ridx);
+    root.kinds = lk | (rk << 2);
+  }
   root.out_slot = -1;
   // a stored/tip operand on one side and a computed one on the other: the computed one is CUR
   pl.prog.push_back(root);
@@ -805,9 +818,9 @@ static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_o
 }
 
 static size_t tree_smem_bytes(int K, int T, int depth, int n_steps) {
-  const size_t tile = (size_t)kTreeThreads / K;
-  return (size_t)kLnlBlock * 8 + 32 * 8 + 4 * 8 + (size_t)depth * kTreeThreads * (sizeof(d4) + sizeof(int)) +
-         (size_t)(n_steps + 1) * sizeof(TreeInstr) + 128 + 2 * (size_t)T * tile;
+  const size_t tile = (size_t)kTreeR * kTreeThreads / K;
+  return 2 * tile * 8 + 32 * 8 + 4 * 8 + (size_t)depth * kTreeR * kTreeThreads * (sizeof(d4) + sizeof(int)) +
+         (size_t)(n_steps + 2) * sizeof(TreeInstr) + 128 + 2 * (size_t)T * (tile / 2);
 }
 
 template <int K>
@@ -835,7 +848,7 @@ static cudaError_t launch_tree(phylo_engine *e, const TreeArgs &args, size_t sme
 static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt,
                                bool *done) {
   *done = false;
-  if (!e->opt_fused || e->S != 4 || e->mask_dev_bytes != 1) return PHYLO_OK;
+  if (!e->opt_fused || e->S != 4 || e->mask_dev_bytes != 1 || !e->dTips4) return PHYLO_OK;
   if (!(e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8)) return PHYLO_OK;
   FusedPlan pl;
   if (!build_fused_plan(e, ops, n_ops, ra, rb, rt, pl)) return PHYLO_OK;
@@ -870,8 +883,6 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   for (auto &in : pl.prog) {
     in.out_clv = (e->opt_retain && in.out_slot >= 0) ? e->nodes[in.out_slot].clv : nullptr;
     in.out_sc = (e->opt_retain && in.out_slot >= 0) ? e->nodes[in.out_slot].scale : nullptr;
-    in.l_clv = in.lkind == OPK_STORED ? e->nodes[in.lidx].clv : nullptr;
-    in.r_clv = in.rkind == OPK_STORED ? e->nodes[in.ridx].clv : nullptr;
   }
   std::memcpy(e->hProg, pl.prog.data(), pbytes);
   std::memcpy(e->hT, pl.tlen.data(), sizeof(double) * nb);
@@ -881,10 +892,11 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   a.prog = (const TreeInstr *)e->dProg;
   a.n_instr = n_ops;
   a.P = e->dP;
-  a.tips = (const uint8_t *)e->dTips;
+  a.tips4 = e->dTips4;
   a.tip_stride = e->tipStride;
   a.T = e->T;
   a.N = e->N;
+  a.node_clv = e->dNodeClv;
   a.node_sc = e->dNodeSc;
   a.pi = e->dPi;
   a.probs = e->dProbs;

@@ -579,4 +579,19 @@ tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, int64_t 
   if (bad) atomicAdd(n_bad, bad);
 }
 
+// Two 4-bit masks per byte (even pattern in the low nibble) for the tree-fused kernel's tip
+// tiles; cells beyond N read as "all states".
+__global__ void __launch_bounds__(256)
+tips_pack4_kernel(const uint8_t *__restrict__ tips, uint8_t *__restrict__ tips4, int T, int64_t N,
+                  int64_t stride) {
+  const int64_t half = stride / 2, total = (int64_t)T * half;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / half, b = i - t * half, p = 2 * b;
+    const int lo = p < N ? (tips[t * stride + p] & 15) : 15;
+    const int hi = p + 1 < N ? (tips[t * stride + p + 1] & 15) : 15;
+    tips4[i] = (uint8_t)(lo | (hi << 4));
+  }
+}
+
 }  // namespace phylo

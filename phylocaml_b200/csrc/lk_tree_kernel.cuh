@@ -7,13 +7,14 @@
 // (3 CLV moves per update), HBM sees at most ONE write per update (RETAIN: every interior
 // CLV is still produced in its slot for later incremental use) or nothing but the tips.
 //
-// Execution model (v2, after profiling v1 -- see profiles/README.md):
-//   * thread = one (pattern, rate class); CTA = 256 threads = a tile of 256/K patterns;
-//     two CTAs per SM (<= 128 registers) so 16 warps hide the fp64 / shared-memory latency;
+// Execution model (v5, after profiling v1..v4 -- see profiles/README.md):
+//   * thread = one rate class of R=2 patterns; CTA = 128 threads = a tile of 256/K patterns;
+//     four CTAs per SM. Two patterns per thread halve the transition-matrix traffic into
+//     registers (the L1 write-back pipe was the limiter at R=1) and double the ILP;
 //   * warps run FREE through the schedule: there is no CTA barrier per step. The only
 //     barriers are one per tile (tip buffer hand-over) and one per 1024-pattern block
 //     (canonical site-sum fold);
-//   * tip masks of a tile ([T rows] x [TILE patterns] bytes) are staged by bulk-TMA
+//   * tip masks of a tile ([T rows] x [TILE patterns], two 4-bit masks per byte) are staged by bulk-TMA
 //     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), double buffered so the
 //     next tile's tips land while this tile is computed;
 //   * the transition matrices of a step are read through L1 (k-interleaved layout: the K
@@ -31,22 +32,18 @@ namespace phylo {
 
 enum : int { OPK_TIP = 0, OPK_CUR = 1, OPK_POP = 2, OPK_STORED = 3 };
 
-// One step of the compiled schedule, 64 bytes, everything the kernel needs without a
-// dependent table lookup.
+// One step of the compiled schedule: 32 bytes, read from shared memory one step ahead.
 struct __align__(16) TreeInstr {
-  int lkind, rkind;      // OPK_*
+  int kinds;             // lkind | rkind << 2 | push_first << 4
   int lidx, ridx;        // tip row (OPK_TIP) or node slot (OPK_STORED)
-  int push_first;        // park the running CLV on the stack before this step
   int out_slot;          // node slot that receives the result, or -1
-  int pad0, pad1;
   double *out_clv;       // RETAIN: where the result goes (NULL = nowhere)
   int32_t *out_sc;
-  const double *l_clv;   // OPK_STORED operands: resident CLV / scale arrays
-  const double *r_clv;
 };
-static_assert(sizeof(TreeInstr) == 64, "TreeInstr is four 16-byte words");
+static_assert(sizeof(TreeInstr) == 32, "TreeInstr is two 16-byte words");
 
-constexpr int kTreeThreads = 256;
+constexpr int kTreeThreads = 128;
+constexpr int kTreeR = 2;         // patterns per thread
 constexpr int kTreePrefetch = 4;  // steps of look-ahead for the transition matrices
 
 // ---- mbarrier / bulk-TMA primitives (sm_90+ PTX, SASS: SYNCS / UBLKCP)
@@ -84,53 +81,37 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 
 // Transition matrices are stored k-interleaved by pt_build_kernel(interleave=1): element
 // e (= i*4+j) of rate class k sits at [e/2][k][e%2]. `pk` points at this thread's k.
-// x[i] = sum_j P[i][j] v[j]
 template <int K>
-__device__ __forceinline__ void apply_inner(const double *__restrict__ pk, const d4 &v, double (&x)[4]) {
-  double pm[16];
+__device__ __forceinline__ void load_matrix(const double *__restrict__ pk, double (&pm)[16]) {
 #pragma unroll
   for (int ep = 0; ep < 8; ++ep) {
     const double2 t = __ldg(reinterpret_cast<const double2 *>(pk + ep * K * 2));
     pm[2 * ep] = t.x;
     pm[2 * ep + 1] = t.y;
   }
+}
+// x[i] = sum_j P[i][j] v[j]  (same expression as prune4_kernel => same bits)
+__device__ __forceinline__ void matvec(const double (&pm)[16], const d4 &v, double (&x)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     x[i] = ((pm[i * 4 + 0] * v.x + pm[i * 4 + 1] * v.y) + pm[i * 4 + 2] * v.z) + pm[i * 4 + 3] * v.w;
 }
-
-// x[i] = sum_{j in mask} P[i][j] (ascending j); one-hot masks take column j directly
-template <int K>
-__device__ __forceinline__ void apply_tip(const double *__restrict__ pk, int m, double (&x)[4]) {
-  m &= 15;
-  if (__popc(m) == 1) {
-    const int j = __ffs(m) - 1;
-    const double *c = pk + (j >> 1) * K * 2 + (j & 1);  // element (i, j) is at c[i * 4K]
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = __ldg(c + i * 4 * K);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const double2 p01 = __ldg(reinterpret_cast<const double2 *>(pk + (2 * i) * K * 2));
-      const double2 p23 = __ldg(reinterpret_cast<const double2 *>(pk + (2 * i + 1) * K * 2));
-      double acc = (m & 1) ? p01.x : 0.0;
-      acc += (m & 2) ? p01.y : 0.0;
-      acc += (m & 4) ? p23.x : 0.0;
-      acc += (m & 8) ? p23.y : 0.0;
-      x[i] = acc;
-    }
-  }
+// a tip enters as a 0/1 vector: sum_j P[i][j]*L_j reproduces the ascending-j sum over the
+// mask bit for bit
+__device__ __forceinline__ d4 mask_vec(int m) {
+  return d4{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
 }
 
 struct TreeArgs {
-  const TreeInstr *prog;   // n_instr steps + 1 root step (kinds/idx only)
+  const TreeInstr *prog;   // n_instr steps + 1 root step
   int n_instr;
   const double *P;         // [2*n_instr + 1][16*K] k-interleaved
-  const uint8_t *tips;     // [T][tip_stride]
-  int64_t tip_stride;
+  const uint8_t *tips4;    // [T][tip_stride/2]: two 4-bit masks per byte (even pattern = low nibble)
+  int64_t tip_stride;      // patterns per row (multiple of 1024)
   int T;
   int64_t N;
-  int32_t *const *node_sc; // per slot: scale counters of OPK_STORED operands
+  double *const *node_clv; // per slot: OPK_STORED operands
+  int32_t *const *node_sc;
   const double *pi, *probs;
   double pinvar;
   const uint8_t *inv;
@@ -140,33 +121,29 @@ struct TreeArgs {
   int stack_depth;
 };
 
-// operand vector of one step: tips become 0/1 vectors (so x_i = sum_j P[i][j]*L_j reproduces
-// the ascending-j sum over the mask bit-for-bit), CUR is the running CLV, POP comes off the
-// shared-memory stack, STORED streams from HBM.
-__device__ __forceinline__ d4 mask_vec(int m) {
-  return d4{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
-}
-
 template <int K, bool RETAIN>
-__global__ void __launch_bounds__(kTreeThreads, 2) lk_tree4_kernel(const TreeArgs a) {
-  constexpr int NT = kTreeThreads;
-  constexpr int TILE = NT / K;              // patterns per tile
+__global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArgs a) {
+  constexpr int NT = kTreeThreads, R = kTreeR;
+  constexpr int HALF = NT / K;              // patterns per r-slice of the tile
+  constexpr int TILE = R * HALF;            // patterns per tile
   constexpr int TILES = kLnlBlock / TILE;   // tiles per 1024-pattern reduction block
+  constexpr int GROUPS = TILE / 32;         // 32-pattern fold groups per tile
   constexpr int PM = 16 * K;                // doubles per transition matrix set (all k)
-  static_assert(TILE >= 16 && kLnlBlock % TILE == 0, "tile must divide the reduction block");
+  constexpr int TROW = TILE / 2;            // bytes per tip row of a tile (nibble packed)
+  static_assert(TILE % 32 == 0 && kLnlBlock % TILE == 0 && TROW % 16 == 0, "tile shape");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *vals = reinterpret_cast<double *>(smem_raw);                       // [1024]
-  double *wsum = vals + kLnlBlock;                                           // [32]
+  double *stage = reinterpret_cast<double *>(smem_raw);                      // [2][TILE] site values
+  double *wsum = stage + 2 * TILE;                                           // [32] group sums
   uint64_t *tipbar = reinterpret_cast<uint64_t *>(wsum + 32);                // [2] (+2 pad)
-  d4 *stack = reinterpret_cast<d4 *>(tipbar + 4);                            // [depth][NT]
-  int *stack_sc = reinterpret_cast<int *>(stack + (size_t)a.stack_depth * NT);  // [depth][NT]
-  int4 *sprog = reinterpret_cast<int4 *>(stack_sc + (size_t)a.stack_depth * NT);  // [n_steps][4]
-  uint8_t *tipbuf = reinterpret_cast<uint8_t *>(sprog + 4 * (size_t)(a.n_instr + 1));
+  d4 *stack = reinterpret_cast<d4 *>(tipbar + 4);                            // [depth][R][NT]
+  int *stack_sc = reinterpret_cast<int *>(stack + (size_t)a.stack_depth * R * NT);
+  int4 *sprog = reinterpret_cast<int4 *>(stack_sc + (size_t)a.stack_depth * R * NT);  // [n_steps][2]
+  uint8_t *tipbuf = reinterpret_cast<uint8_t *>(sprog + 2 * (size_t)(a.n_instr + 2));
   tipbuf = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tipbuf) + 127) & ~(uintptr_t)127);
-  const size_t tipbuf_bytes = (size_t)a.T * TILE;                            // per buffer
+  const size_t tipbuf_bytes = (size_t)a.T * TROW;                            // per buffer
 
-  const int tid = threadIdx.x, k = tid % K, pl = tid / K, lane = tid & 31;
+  const int tid = threadIdx.x, k = tid % K, pl = tid / K, lane = tid & 31, warp = tid >> 5;
   const int n_steps = a.n_instr + 1;  // + root step
   const int64_t nblocks = (a.N + kLnlBlock - 1) / kLnlBlock;
 
@@ -176,16 +153,18 @@ __global__ void __launch_bounds__(kTreeThreads, 2) lk_tree4_kernel(const TreeArg
     fence_mbar_init();
   }
   // the compiled schedule lives in shared memory for the whole kernel
-  for (int i = tid; i < 4 * n_steps; i += NT) sprog[i] = __ldg(reinterpret_cast<const int4 *>(a.prog) + i);
+  for (int i = tid; i < 2 * n_steps; i += NT) sprog[i] = __ldg(reinterpret_cast<const int4 *>(a.prog) + i);
+  if (tid < 2) sprog[2 * n_steps + tid] = make_int4(0, 0, 0, 0);  // harmless word past the end
   __syncthreads();
 
   const double pi0 = a.pi[0], pi1 = a.pi[1], pi2 = a.pi[2], pi3 = a.pi[3], pk_prob = a.probs[k];
   const double *Pk = a.P + k * 2;  // this thread's rate class inside every matrix set
   d4 *mystack = stack + tid;
   int *mystack_sc = stack_sc + tid;
+  // nibble of pattern (pl + r*HALF) inside a tip row of the tile
+  const int tb_off0 = pl >> 1, tb_off1 = (pl + HALF) >> 1, tb_sh = (pl & 1) * 4;  // HALF is even
 
-  // warp 0 stages the tip rows of one tile
-  auto issue_tips = [&](int64_t p0, int buf) {
+  auto issue_tips = [&](int64_t p0, int buf) {  // warp 0 stages the tip rows of one tile
     if (tid < 32) {
       if (tid == 0) {
         fence_proxy_async();
@@ -193,201 +172,212 @@ __global__ void __launch_bounds__(kTreeThreads, 2) lk_tree4_kernel(const TreeArg
       }
       __syncwarp();
       for (int t = tid; t < a.T; t += 32)
-        bulk_g2s(tipbuf + (size_t)buf * tipbuf_bytes + (size_t)t * TILE, a.tips + (size_t)t * a.tip_stride + p0,
-                 TILE, &tipbar[buf]);
+        bulk_g2s(tipbuf + (size_t)buf * tipbuf_bytes + (size_t)t * TROW,
+                 a.tips4 + ((size_t)t * a.tip_stride + p0) / 2, TROW, &tipbar[buf]);
+    }
+  };
+  // canonical level-1 fold of one finished tile: GROUPS warps fold 32 consecutive patterns each
+  auto fold_tile = [&](int sub_done, int sbuf) {
+    for (int g = warp; g < GROUPS; g += NT / 32) {
+      const double v = warp_fold(stage[sbuf * TILE + g * 32 + lane]);
+      if (lane == 0) wsum[sub_done * GROUPS + g] = v;
     }
   };
 
-  uint32_t tile_seq = 0;  // tiles processed by this CTA (tip double-buffer phase)
+  uint32_t tile_seq = 0;  // tiles processed by this CTA (double-buffer phase)
   if ((int64_t)blockIdx.x < nblocks) issue_tips((int64_t)blockIdx.x * kLnlBlock, 0);
 
   for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-    for (int i = tid; i < kLnlBlock; i += NT) vals[i] = 0.0;
+    if (tid < 32) wsum[tid] = 0.0;
     const int64_t blk_p0 = blk * kLnlBlock;
     const int tiles_here = (int)min((int64_t)TILES, (a.N - blk_p0 + TILE - 1) / TILE);
     for (int sub = 0; sub < tiles_here; ++sub, ++tile_seq) {
       const int64_t p0 = blk_p0 + (int64_t)sub * TILE;
-      const int64_t p = p0 + pl;
-      const bool active = p < a.N;
-      const int64_t item_off = (p * K + k) * 4;  // this thread's doubles inside any CLV array
       const int buf = tile_seq & 1;
       __syncthreads();  // every warp has finished the previous tile: buffer buf^1 is free
+      if (sub > 0) fold_tile(sub - 1, buf ^ 1);
       {
         int64_t np0 = -1;
         if (sub + 1 < tiles_here) np0 = p0 + TILE;
         else if (blk + gridDim.x < nblocks) np0 = (blk + gridDim.x) * kLnlBlock;
         if (np0 >= 0) issue_tips(np0, buf ^ 1);
       }
-      // warm L1 with the matrices of the first steps
-      if (lane < 2 * K) {
+      if (lane < 2 * K) {  // warm L1 with the matrices of the first steps
         for (int s = 0; s < kTreePrefetch && s < n_steps; ++s)
           prefetch_l1(a.P + (size_t)(2 * s) * PM + lane * 16);
       }
       mbar_wait(&tipbar[buf], (tile_seq >> 1) & 1);
-      const uint8_t *tb = tipbuf + (size_t)buf * tipbuf_bytes + pl;
+      const uint8_t *tb = tipbuf + (size_t)buf * tipbuf_bytes;
 
-      d4 cur{0, 0, 0, 0};
-      int cur_sc = 0, sp = 0;  // sp counts stack entries in units of NT elements
+      int64_t pat[R], item_off[R];
+      bool active[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        pat[r] = p0 + pl + r * HALF;
+        active[r] = pat[r] < a.N;
+        item_off[r] = (pat[r] * K + k) * 4;  // this thread's doubles inside any CLV array
+      }
+      d4 cur[R];
+      int cur_sc[R], sp = 0;  // sp in units of elements (R*NT per stack level)
+#pragma unroll
+      for (int r = 0; r < R; ++r) { cur[r] = d4{0, 0, 0, 0}; cur_sc[r] = 0; }
 
       // software pipeline: while step s computes, the words of step s+1 are read from shared
-      // memory and, once they have landed, its tip masks -- a step starts with everything but
-      // its matrices in registers
-      int4 iw = sprog[0];    // lkind, rkind, lidx, ridx   (idx: tip row | node slot)
-      int4 iw2 = sprog[1];   // push_first, out_slot, -, -
-      int ml = tb[(size_t)((iw.x == OPK_TIP) ? iw.z : 0) * TILE];
-      int mr = tb[(size_t)((iw.y == OPK_TIP) ? iw.w : 0) * TILE];
-      const double *pm_ = Pk;                                       // matrices of this step
+      // memory and, once landed, its tip masks; a step starts with all but its matrices
+      int4 iw = sprog[0];  // kinds, lidx, ridx, out_slot
+      int mlb0, mlb1, mrb0, mrb1;  // raw tip bytes of (left,right) x (r=0,1)
+      {
+        const int lrow = ((iw.x & 3) == OPK_TIP) ? iw.y : 0, rrow = (((iw.x >> 2) & 3) == OPK_TIP) ? iw.z : 0;
+        mlb0 = tb[lrow * TROW + tb_off0]; mlb1 = tb[lrow * TROW + tb_off1];
+        mrb0 = tb[rrow * TROW + tb_off0]; mrb1 = tb[rrow * TROW + tb_off1];
+      }
+      const double *pm_ = Pk;                                                  // matrices of this step
       const double *pf_ = a.P + (size_t)(2 * kTreePrefetch) * PM + lane * 16;  // L1 prefetch cursor
 
       for (int step = 0; step < a.n_instr; ++step, pm_ += 2 * PM, pf_ += 2 * PM) {
-        // ---- matrix loads first: they depend on nothing but the step and the (already
-        // present) tip masks. A tip operand whose mask is one-hot in EVERY lane of the warp
-        // (warp-uniform vote: no divergence) only needs column j of its matrix.
-        const int lkind = iw.x, rkind = iw.y;
-        const int mlc = ml & 15, mrc = mr & 15;
-        const bool lcol = (lkind == OPK_TIP) && __all_sync(0xffffffffu, __popc(mlc) == 1);
-        const bool rcol = (rkind == OPK_TIP) && __all_sync(0xffffffffu, __popc(mrc) == 1);
-        double pml[16], pmr[16];
-        if (lcol) {
-          const int j = __ffs(mlc) - 1;
-          const double *c = pm_ + (j >> 1) * K * 2 + (j & 1);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pml[i] = __ldg(c + i * 4 * K);
-        } else {
-#pragma unroll
-          for (int ep = 0; ep < 8; ++ep) {
-            const double2 t = __ldg(reinterpret_cast<const double2 *>(pm_ + ep * K * 2));
-            pml[2 * ep] = t.x; pml[2 * ep + 1] = t.y;
-          }
-        }
-        if (rcol) {
-          const int j = __ffs(mrc) - 1;
-          const double *c = pm_ + PM + (j >> 1) * K * 2 + (j & 1);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pmr[i] = __ldg(c + i * 4 * K);
-        } else {
-#pragma unroll
-          for (int ep = 0; ep < 8; ++ep) {
-            const double2 t = __ldg(reinterpret_cast<const double2 *>(pm_ + PM + ep * K * 2));
-            pmr[2 * ep] = t.x; pmr[2 * ep + 1] = t.y;
-          }
-        }
+        double pm[16];
+        load_matrix<K>(pm_, pm);  // left matrix: depends on nothing but the step
         if (lane < 2 * K && step + kTreePrefetch < n_steps) prefetch_l1(pf_);
-        const int lidx = iw.z, ridx = iw.w, push = iw2.x;
-        const int4 ow = RETAIN ? sprog[4 * step + 2] : make_int4(0, 0, 0, 0);  // out_clv, out_sc
-        const int4 nw = sprog[4 * step + 4], nw2 = sprog[4 * step + 5];       // next step's words
+        const int lkind = iw.x & 3, rkind = (iw.x >> 2) & 3, push = iw.x & 16, lidx = iw.y, ridx = iw.z;
+        const int4 ow = RETAIN ? sprog[2 * step + 1] : make_int4(0, 0, 0, 0);  // out_clv, out_sc
+        const int4 nw = sprog[2 * step + 2];                                   // next step's word
         if (push) {
-          mystack[sp] = cur;
-          mystack_sc[sp] = cur_sc;
-          sp += NT;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            mystack[sp + r * NT] = cur[r];
+            mystack_sc[sp + r * NT] = cur_sc[r];
+          }
+          sp += R * NT;
         }
-        // ---- operand vectors
-        d4 lv, rv;
-        int sc = 0;
-        if (lkind == OPK_TIP) lv = mask_vec(ml);
-        else if (lkind == OPK_CUR) { lv = cur; sc = cur_sc; }
-        else if (lkind == OPK_POP) { sp -= NT; lv = mystack[sp]; sc = mystack_sc[sp]; }
-        else {
-          lv = d4{0, 0, 0, 0};
-          const int4 sw = sprog[4 * step + 3];
-          const double *src = reinterpret_cast<const double *>(((uint64_t)(uint32_t)sw.y << 32) | (uint32_t)sw.x);
-          if (active) { lv = ld256_stream(src + item_off); sc = a.node_sc[lidx][p]; }
+        // ---- left operand vectors and x = P_l * lv
+        d4 lv[R];
+        int sc[R];
+        if (lkind == OPK_TIP) {
+          lv[0] = mask_vec(mlb0 >> tb_sh); lv[1] = mask_vec(mlb1 >> tb_sh);
+          sc[0] = sc[1] = 0;
+        } else if (lkind == OPK_CUR) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) { lv[r] = cur[r]; sc[r] = cur_sc[r]; }
+        } else if (lkind == OPK_POP) {
+          sp -= R * NT;
+#pragma unroll
+          for (int r = 0; r < R; ++r) { lv[r] = mystack[sp + r * NT]; sc[r] = mystack_sc[sp + r * NT]; }
+        } else {
+          const double *src = a.node_clv[lidx];
+          const int32_t *ssc = a.node_sc[lidx];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            lv[r] = d4{0, 0, 0, 0}; sc[r] = 0;
+            if (active[r]) { lv[r] = ld256_stream(src + item_off[r]); sc[r] = ssc[pat[r]]; }
+          }
         }
-        if (rkind == OPK_TIP) rv = mask_vec(mr);
-        else if (rkind == OPK_CUR) { rv = cur; sc += cur_sc; }
-        else if (rkind == OPK_POP) { sp -= NT; rv = mystack[sp]; sc += mystack_sc[sp]; }
-        else {
-          rv = d4{0, 0, 0, 0};
-          const int4 sw = sprog[4 * step + 3];
-          const double *src = reinterpret_cast<const double *>(((uint64_t)(uint32_t)sw.w << 32) | (uint32_t)sw.z);
-          if (active) { rv = ld256_stream(src + item_off); sc += a.node_sc[ridx][p]; }
+        double x[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) matvec(pm, lv[r], x[r]);
+        // ---- right matrix into the same registers, right operand vectors, y = P_r * rv
+        load_matrix<K>(pm_ + PM, pm);
+        d4 rv[R];
+        if (rkind == OPK_TIP) {
+          rv[0] = mask_vec(mrb0 >> tb_sh); rv[1] = mask_vec(mrb1 >> tb_sh);
+        } else if (rkind == OPK_CUR) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) { rv[r] = cur[r]; sc[r] += cur_sc[r]; }
+        } else if (rkind == OPK_POP) {
+          sp -= R * NT;
+#pragma unroll
+          for (int r = 0; r < R; ++r) { rv[r] = mystack[sp + r * NT]; sc[r] += mystack_sc[sp + r * NT]; }
+        } else {
+          const double *src = a.node_clv[ridx];
+          const int32_t *ssc = a.node_sc[ridx];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            rv[r] = d4{0, 0, 0, 0};
+            if (active[r]) { rv[r] = ld256_stream(src + item_off[r]); sc[r] += ssc[pat[r]]; }
+          }
         }
-        // next step's tip masks (its words have landed by now); consumed one iteration later
-        ml = tb[(size_t)((nw.x == OPK_TIP) ? nw.z : 0) * TILE];
-        mr = tb[(size_t)((nw.y == OPK_TIP) ? nw.w : 0) * TILE];
+        // next step's tip bytes (its word has landed by now); consumed one iteration later
+        {
+          const int lrow = ((nw.x & 3) == OPK_TIP) ? nw.y : 0, rrow = (((nw.x >> 2) & 3) == OPK_TIP) ? nw.z : 0;
+          mlb0 = tb[lrow * TROW + tb_off0]; mlb1 = tb[lrow * TROW + tb_off1];
+          mrb0 = tb[rrow * TROW + tb_off0]; mrb1 = tb[rrow * TROW + tb_off1];
+        }
         iw = nw;
-        iw2 = nw2;
-        // ---- the update itself: straight-line fp64 (column fast path: x_i = P[i][j])
-        double x[4], y[4];
-        if (lcol) {
+        double *oc = reinterpret_cast<double *>(((uint64_t)(uint32_t)ow.y << 32) | (uint32_t)ow.x);
+        int32_t *os = reinterpret_cast<int32_t *>(((uint64_t)(uint32_t)ow.w << 32) | (uint32_t)ow.z);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[i] = pml[i];
-        } else {
+        for (int r = 0; r < R; ++r) {
+          double y[4];
+          matvec(pm, rv[r], y);
+          d4 v{x[r][0] * y[0], x[r][1] * y[1], x[r][2] * y[2], x[r][3] * y[3]};
+          int h = max(max(hi32(v.x), hi32(v.y)), max(hi32(v.z), hi32(v.w)));
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            x[i] = ((pml[i * 4 + 0] * lv.x + pml[i * 4 + 1] * lv.y) + pml[i * 4 + 2] * lv.z) + pml[i * 4 + 3] * lv.w;
-        }
-        if (rcol) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = pmr[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            y[i] = ((pmr[i * 4 + 0] * rv.x + pmr[i * 4 + 1] * rv.y) + pmr[i * 4 + 2] * rv.z) + pmr[i * 4 + 3] * rv.w;
-        }
-        d4 v{x[0] * y[0], x[1] * y[1], x[2] * y[2], x[3] * y[3]};
-        int h = max(max(hi32(v.x), hi32(v.y)), max(hi32(v.z), hi32(v.w)));
-#pragma unroll
-        for (int off = K / 2; off >= 1; off >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, off));
-        if (h < kScaleHiThresh) {
-          v.x *= 0x1p+256; v.y *= 0x1p+256; v.z *= 0x1p+256; v.w *= 0x1p+256;
-          ++sc;
-        }
-        cur = v;
-        cur_sc = sc;
-        if (RETAIN) {
-          double *oc = reinterpret_cast<double *>(((uint64_t)(uint32_t)ow.y << 32) | (uint32_t)ow.x);
-          int32_t *os = reinterpret_cast<int32_t *>(((uint64_t)(uint32_t)ow.w << 32) | (uint32_t)ow.z);
-          if (oc != nullptr && active) {
-            st256(oc + item_off, v);
-            if (k == 0) os[p] = sc;
+          for (int off = K / 2; off >= 1; off >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, off));
+          if (h < kScaleHiThresh) {
+            v.x *= 0x1p+256; v.y *= 0x1p+256; v.z *= 0x1p+256; v.w *= 0x1p+256;
+            ++sc[r];
+          }
+          cur[r] = v;
+          cur_sc[r] = sc[r];
+          if (RETAIN) {
+            if (oc != nullptr && active[r]) {
+              st256(oc + item_off[r], v);
+              if (k == 0) os[pat[r]] = sc[r];
+            }
           }
         }
       }
       // ---- root-edge join (root4_kernel's arithmetic): P applies to the b side only.
-      // iw / ml / mr already hold the root step (fetched by the last iteration).
+      // iw and the tip bytes already hold the root step (fetched by the last iteration).
       {
-        const int4 sw = sprog[4 * a.n_instr + 3];
-        d4 av{0, 0, 0, 0}, bv{0, 0, 0, 0};
-        int c = 0;
-        // the POP operand (if any) was pushed before the CUR one was computed
-        if (iw.x == OPK_TIP) av = mask_vec(ml);
-        else if (iw.x == OPK_CUR) { av = cur; c += cur_sc; }
-        else if (iw.x == OPK_POP) { av = mystack[sp - NT]; c += mystack_sc[sp - NT]; }
-        else if (active) {
-          const double *src = reinterpret_cast<const double *>(((uint64_t)(uint32_t)sw.y << 32) | (uint32_t)sw.x);
-          av = ld256_stream(src + item_off); c += a.node_sc[iw.z][p];
-        }
-        if (iw.y == OPK_TIP) bv = mask_vec(mr);
-        else if (iw.y == OPK_CUR) { bv = cur; c += cur_sc; }
-        else if (iw.y == OPK_POP) { bv = mystack[sp - NT]; c += mystack_sc[sp - NT]; }
-        else if (active) {
-          const double *src = reinterpret_cast<const double *>(((uint64_t)(uint32_t)sw.w << 32) | (uint32_t)sw.z);
-          bv = ld256_stream(src + item_off); c += a.node_sc[iw.w][p];
-        }
-        double y[4];
-        apply_inner<K>(pm_, bv, y);
-        const double lk = (((pi0 * av.x) * y[0] + (pi1 * av.y) * y[1]) + (pi2 * av.z) * y[2]) + (pi3 * av.w) * y[3];
-        double l = pk_prob * lk;
+        const int akind = iw.x & 3, bkind = (iw.x >> 2) & 3;
+        double pm[16];
+        load_matrix<K>(pm_, pm);
 #pragma unroll
-        for (int off = 1; off < K; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-        if (k == 0 && active) {
-          double lnl;
-          if (a.pinvar >= 0.0) {
-            const int m = a.inv[p];
-            const double pv = (m & 1 ? pi0 : 0.0) + (m & 2 ? pi1 : 0.0) + (m & 4 ? pi2 : 0.0) + (m & 8 ? pi3 : 0.0);
-            lnl = log((1.0 - a.pinvar) * ldexp(l, -kScaleExp * c) + a.pinvar * pv);
-          } else {
-            lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
+        for (int r = 0; r < R; ++r) {
+          d4 av{0, 0, 0, 0}, bv{0, 0, 0, 0};
+          int c = 0;
+          // the POP operand (if any) was pushed before the CUR one was computed
+          if (akind == OPK_TIP) av = mask_vec((r ? mlb1 : mlb0) >> tb_sh);
+          else if (akind == OPK_CUR) { av = cur[r]; c += cur_sc[r]; }
+          else if (akind == OPK_POP) { av = mystack[sp - R * NT + r * NT]; c += mystack_sc[sp - R * NT + r * NT]; }
+          else if (active[r]) { av = ld256_stream(a.node_clv[iw.y] + item_off[r]); c += a.node_sc[iw.y][pat[r]]; }
+          if (bkind == OPK_TIP) bv = mask_vec((r ? mrb1 : mrb0) >> tb_sh);
+          else if (bkind == OPK_CUR) { bv = cur[r]; c += cur_sc[r]; }
+          else if (bkind == OPK_POP) { bv = mystack[sp - R * NT + r * NT]; c += mystack_sc[sp - R * NT + r * NT]; }
+          else if (active[r]) { bv = ld256_stream(a.node_clv[iw.z] + item_off[r]); c += a.node_sc[iw.z][pat[r]]; }
+          double y[4];
+          matvec(pm, bv, y);
+          const double lk = (((pi0 * av.x) * y[0] + (pi1 * av.y) * y[1]) + (pi2 * av.z) * y[2]) + (pi3 * av.w) * y[3];
+          double l = pk_prob * lk;
+#pragma unroll
+          for (int off = 1; off < K; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+          if (k == 0) {
+            double wl = 0.0;
+            if (active[r]) {
+              const int64_t p = pat[r];
+              double lnl;
+              if (a.pinvar >= 0.0) {
+                const int m = a.inv[p];
+                const double pv = (m & 1 ? pi0 : 0.0) + (m & 2 ? pi1 : 0.0) + (m & 4 ? pi2 : 0.0) + (m & 8 ? pi3 : 0.0);
+                lnl = log((1.0 - a.pinvar) * ldexp(l, -kScaleExp * c) + a.pinvar * pv);
+              } else {
+                lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
+              }
+              if (a.site_lnl) a.site_lnl[p] = lnl;
+              wl = (a.weights ? a.weights[p] : 1.0) * lnl;
+            }
+            stage[buf * TILE + pl + r * HALF] = wl;
           }
-          if (a.site_lnl) a.site_lnl[p] = lnl;
-          vals[sub * TILE + pl] = (a.weights ? a.weights[p] : 1.0) * lnl;
         }
       }
     }
     __syncthreads();
-    const double rsum = block_fold_1024(vals, wsum);
-    if (tid == 0) a.partials[blk] = rsum;
+    fold_tile(tiles_here - 1, (tile_seq - 1) & 1);
+    __syncthreads();
+    if (warp == 0) {
+      const double rsum = warp_fold(wsum[lane]);
+      if (lane == 0) a.partials[blk] = rsum;
+    }
     __syncthreads();
   }
 }
