@@ -81,6 +81,16 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 
 // Transition matrices are stored k-interleaved by pt_build_kernel(interleave=1): element
 // e (= i*4+j) of rate class k sits at [e/2][k][e%2]. `pk` points at this thread's k.
+// A "half" is two rows of the 4x4 matrix (8 doubles, 4 x LDG.128): h = 0 -> rows 0,1.
+template <int K>
+__device__ __forceinline__ void load_half(const double *__restrict__ pk, int h, double (&pm)[8]) {
+#pragma unroll
+  for (int ep = 0; ep < 4; ++ep) {
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(pk + (h * 4 + ep) * K * 2));
+    pm[2 * ep] = t.x;
+    pm[2 * ep + 1] = t.y;
+  }
+}
 template <int K>
 __device__ __forceinline__ void load_matrix(const double *__restrict__ pk, double (&pm)[16]) {
 #pragma unroll
@@ -90,16 +100,21 @@ __device__ __forceinline__ void load_matrix(const double *__restrict__ pk, doubl
     pm[2 * ep + 1] = t.y;
   }
 }
-// x[i] = sum_j P[i][j] v[j]  (same expression as prune4_kernel => same bits)
+// two rows: x[i] = sum_j P[i][j] v[j]  (same expression as prune4_kernel => same bits)
+__device__ __forceinline__ void matvec_half(const double (&pm)[8], const d4 &v, double &x0, double &x1) {
+  x0 = ((pm[0] * v.x + pm[1] * v.y) + pm[2] * v.z) + pm[3] * v.w;
+  x1 = ((pm[4] * v.x + pm[5] * v.y) + pm[6] * v.z) + pm[7] * v.w;
+}
 __device__ __forceinline__ void matvec(const double (&pm)[16], const d4 &v, double (&x)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     x[i] = ((pm[i * 4 + 0] * v.x + pm[i * 4 + 1] * v.y) + pm[i * 4 + 2] * v.z) + pm[i * 4 + 3] * v.w;
 }
 // a tip enters as a 0/1 vector: sum_j P[i][j]*L_j reproduces the ascending-j sum over the
-// mask bit for bit
+// mask bit for bit. 1.0 = 0x3FF00000'00000000: built with integer ops, no I2F.
 __device__ __forceinline__ d4 mask_vec(int m) {
-  return d4{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
+  return d4{__hiloint2double((m & 1) * 0x3FF00000, 0), __hiloint2double(((m >> 1) & 1) * 0x3FF00000, 0),
+            __hiloint2double(((m >> 2) & 1) * 0x3FF00000, 0), __hiloint2double(((m >> 3) & 1) * 0x3FF00000, 0)};
 }
 
 struct TreeArgs {
@@ -233,12 +248,15 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
       }
       const double *pm_ = Pk;                                                  // matrices of this step
       const double *pf_ = a.P + (size_t)(2 * kTreePrefetch) * PM + lane * 16;  // L1 prefetch cursor
+      // rolling half-matrix pipeline: while one half (2 rows) is being multiplied, the load of
+      // the half needed next is already in flight -- across sides and across steps
+      double hA[8], hB[8];
+      load_half<K>(pm_, 0, hA);
+      load_half<K>(pm_, 1, hB);
 
       for (int step = 0; step < a.n_instr; ++step, pm_ += 2 * PM, pf_ += 2 * PM) {
-        double pm[16];
-        load_matrix<K>(pm_, pm);  // left matrix: depends on nothing but the step
-        if (lane < 2 * K && step + kTreePrefetch < n_steps) prefetch_l1(pf_);
         const int lkind = iw.x & 3, rkind = (iw.x >> 2) & 3, push = iw.x & 16, lidx = iw.y, ridx = iw.z;
+        if (lane < 2 * K && step + kTreePrefetch < n_steps) prefetch_l1(pf_);
         const int4 ow = RETAIN ? sprog[2 * step + 1] : make_int4(0, 0, 0, 0);  // out_clv, out_sc
         const int4 nw = sprog[2 * step + 2];                                   // next step's word
         if (push) {
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
           }
           sp += R * NT;
         }
-        // ---- left operand vectors and x = P_l * lv
+        // ---- left operand vectors
         d4 lv[R];
         int sc[R];
         if (lkind == OPK_TIP) {
@@ -271,11 +289,15 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
             if (active[r]) { lv[r] = ld256_stream(src + item_off[r]); sc[r] = ssc[pat[r]]; }
           }
         }
+        // ---- x = P_l * lv, half by half; each finished half is refilled with P_r at once
         double x[R][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) matvec(pm, lv[r], x[r]);
-        // ---- right matrix into the same registers, right operand vectors, y = P_r * rv
-        load_matrix<K>(pm_ + PM, pm);
+        for (int r = 0; r < R; ++r) matvec_half(hA, lv[r], x[r][0], x[r][1]);
+        load_half<K>(pm_ + PM, 0, hA);
+#pragma unroll
+        for (int r = 0; r < R; ++r) matvec_half(hB, lv[r], x[r][2], x[r][3]);
+        load_half<K>(pm_ + PM, 1, hB);
+        // ---- right operand vectors
         d4 rv[R];
         if (rkind == OPK_TIP) {
           rv[0] = mask_vec(mrb0 >> tb_sh); rv[1] = mask_vec(mrb1 >> tb_sh);
@@ -302,25 +324,39 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
           mrb0 = tb[rrow * TROW + tb_off0]; mrb1 = tb[rrow * TROW + tb_off1];
         }
         iw = nw;
+        // ---- y = P_r * rv and the products; freed halves are refilled with the NEXT step's
+        // left matrix (the root matrix after the last step)
+        d4 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          double y0, y1;
+          matvec_half(hA, rv[r], y0, y1);
+          v[r].x = x[r][0] * y0; v[r].y = x[r][1] * y1;
+        }
+        load_half<K>(pm_ + 2 * PM, 0, hA);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          double y2, y3;
+          matvec_half(hB, rv[r], y2, y3);
+          v[r].z = x[r][2] * y2; v[r].w = x[r][3] * y3;
+        }
+        load_half<K>(pm_ + 2 * PM, 1, hB);
         double *oc = reinterpret_cast<double *>(((uint64_t)(uint32_t)ow.y << 32) | (uint32_t)ow.x);
         int32_t *os = reinterpret_cast<int32_t *>(((uint64_t)(uint32_t)ow.w << 32) | (uint32_t)ow.z);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          double y[4];
-          matvec(pm, rv[r], y);
-          d4 v{x[r][0] * y[0], x[r][1] * y[1], x[r][2] * y[2], x[r][3] * y[3]};
-          int h = max(max(hi32(v.x), hi32(v.y)), max(hi32(v.z), hi32(v.w)));
+          int h = max(max(hi32(v[r].x), hi32(v[r].y)), max(hi32(v[r].z), hi32(v[r].w)));
 #pragma unroll
           for (int off = K / 2; off >= 1; off >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, off));
           if (h < kScaleHiThresh) {
-            v.x *= 0x1p+256; v.y *= 0x1p+256; v.z *= 0x1p+256; v.w *= 0x1p+256;
+            v[r].x *= 0x1p+256; v[r].y *= 0x1p+256; v[r].z *= 0x1p+256; v[r].w *= 0x1p+256;
             ++sc[r];
           }
-          cur[r] = v;
+          cur[r] = v[r];
           cur_sc[r] = sc[r];
           if (RETAIN) {
             if (oc != nullptr && active[r]) {
-              st256(oc + item_off[r], v);
+              st256(oc + item_off[r], v[r]);
               if (k == 0) os[pat[r]] = sc[r];
             }
           }
@@ -330,8 +366,6 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
       // iw and the tip bytes already hold the root step (fetched by the last iteration).
       {
         const int akind = iw.x & 3, bkind = (iw.x >> 2) & 3;
-        double pm[16];
-        load_matrix<K>(pm_, pm);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           d4 av{0, 0, 0, 0}, bv{0, 0, 0, 0};
@@ -346,7 +380,8 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
           else if (bkind == OPK_POP) { bv = mystack[sp - R * NT + r * NT]; c += mystack_sc[sp - R * NT + r * NT]; }
           else if (active[r]) { bv = ld256_stream(a.node_clv[iw.z] + item_off[r]); c += a.node_sc[iw.z][pat[r]]; }
           double y[4];
-          matvec(pm, bv, y);
+          matvec_half(hA, bv, y[0], y[1]);  // hA/hB hold the root matrix (loaded by the last step)
+          matvec_half(hB, bv, y[2], y[3]);
           const double lk = (((pi0 * av.x) * y[0] + (pi1 * av.y) * y[1]) + (pi2 * av.z) * y[2]) + (pi3 * av.w) * y[3];
           double l = pk_prob * lk;
 #pragma unroll
