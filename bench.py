@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dna", choices=sorted(WORKLOADS))
     ap.add_argument("--patterns", type=int, default=0, help="override the total pattern count")
+    ap.add_argument("--taxa", type=int, default=0, help="override the number of taxa")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -247,6 +248,10 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.patterns:
         wl["N"] = args.patterns
+    if args.taxa:
+        wl["T"] = args.taxa
+    if args.patterns or args.taxa:
+        wl["name"] += " [overridden: %d taxa x %d patterns]" % (wl["T"], wl["N"])
 
     if args.impl == "reference":
         run_reference(args, wl)

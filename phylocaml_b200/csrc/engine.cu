@@ -717,19 +717,23 @@ extern "C" int phylo_engine_get_option(phylo_engine *e, int option, int64_t *val
   }
 }
 
+// A schedule compiled for the tree-fused kernels: one step per median in an order that keeps
+// the running result in registers, every operand tagged TIP / STORED / CUR / POP.
+struct PlanStep {
+  int lkind, rkind, lidx, ridx, push_first, out_slot;
+  double t_left, t_right;
+};
 struct FusedPlan {
-  std::vector<TreeInstr> prog;  // n_instr steps + the root step
-  std::vector<double> tlen;     // 2*n_instr + 1 branch lengths in program order
-  int depth = 0;
+  std::vector<PlanStep> steps;  // n_ops medians + the root-edge join (out_slot = -1)
+  int depth = 0;                // stack levels needed
 };
 
 // Re-derives a depth-first order of the (already validated, post-order) schedule in which
 // the child with the larger stack need is evaluated first, and assigns every operand one of
 // TIP / STORED / CUR (just computed, in registers) / POP (parked on the stack).
 // Returns false when the schedule is not a plain tree (a result used twice or never).
-static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt,
+static bool build_fused_plan(int cap, int T, const phylo_op *ops, int n_ops, int ra, int rb, double rt,
                              FusedPlan &pl) {
-  const int cap = e->cap, T = e->T;
   if (n_ops > 100000) return false;
   std::vector<int> producer(cap, -1), uses(cap, 0), need(cap, 0);
   for (int o = 0; o < n_ops; ++o) {
@@ -779,18 +783,17 @@ static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_o
         f.stage = 2;
         if (second >= 0) { st.push_back({second, 0}); continue; }
       }
-      TreeInstr in{};
-      const int lk = kind(op.left, cl && cr, first, in.lidx);
-      const int rk = kind(op.right, cl && cr, first, in.ridx);
-      const int push_first = (!cl && !cr && live) ? 1 : 0;
-      in.kinds = lk | (rk << 2) | (push_first << 4);
+      PlanStep in{};
+      in.lkind = kind(op.left, cl && cr, first, in.lidx);
+      in.rkind = kind(op.right, cl && cr, first, in.ridx);
+      in.push_first = (!cl && !cr && live) ? 1 : 0;
       in.out_slot = op.parent;
-      if (push_first) maxdepth = std::max(maxdepth, ++depth);
-      if (lk == OPK_POP || rk == OPK_POP) --depth;
+      in.t_left = op.t_left;
+      in.t_right = op.t_right;
+      if (in.push_first) maxdepth = std::max(maxdepth, ++depth);
+      if (in.lkind == OPK_POP || in.rkind == OPK_POP) --depth;
       live = true;
-      pl.prog.push_back(in);
-      pl.tlen.push_back(op.t_left);
-      pl.tlen.push_back(op.t_right);
+      pl.steps.push_back(in);
       st.pop_back();
     }
   };
@@ -803,18 +806,14 @@ static bool build_fused_plan(const phylo_engine *e, const phylo_op *ops, int n_o
     emit_subtree(ra);
     emit_subtree(rb);
   }
-  TreeInstr root{};
-  {
-    const int lk = kind(ra, ca && cb, first, root.lidx);
-    const int rk = kind(rb, ca && cb, first, root.ridx);
-    root.kinds = lk | (rk << 2);
-  }
+  PlanStep root{};
+  root.lkind = kind(ra, ca && cb, first, root.lidx);
+  root.rkind = kind(rb, ca && cb, first, root.ridx);
   root.out_slot = -1;
-  // a stored/tip operand on one side and a computed one on the other: the computed one is CUR
-  pl.prog.push_back(root);
-  pl.tlen.push_back(rt);
+  root.t_left = root.t_right = rt;
+  pl.steps.push_back(root);
   pl.depth = std::max(maxdepth, 1);
-  return (int)pl.prog.size() == n_ops + 1;
+  return (int)pl.steps.size() == n_ops + 1;
 }
 
 static size_t tree_smem_bytes(int K, int T, int depth, int n_steps) {
@@ -851,9 +850,9 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   if (!e->opt_fused || e->S != 4 || e->mask_dev_bytes != 1 || !e->dTips4) return PHYLO_OK;
   if (!(e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8)) return PHYLO_OK;
   FusedPlan pl;
-  if (!build_fused_plan(e, ops, n_ops, ra, rb, rt, pl)) return PHYLO_OK;
+  if (!build_fused_plan(e->cap, e->T, ops, n_ops, ra, rb, rt, pl)) return PHYLO_OK;
   const size_t kMaxSmem = 227 * 1024;
-  const size_t smem = tree_smem_bytes(e->K, e->T, pl.depth, (int)pl.prog.size());
+  const size_t smem = tree_smem_bytes(e->K, e->T, pl.depth, (int)pl.steps.size());
   if (smem > kMaxSmem) return PHYLO_OK;  // very deep / very wide trees: per-node kernels instead
   int rc;
   const int nb = 2 * n_ops + 1;
@@ -861,7 +860,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   if (e->opt_retain)
     for (int o = 0; o < n_ops; ++o)
       if ((rc = lk_ensure_node(e, ops[o].parent)) != PHYLO_OK) return rc;
-  const size_t pbytes = sizeof(TreeInstr) * pl.prog.size();
+  const size_t pbytes = sizeof(TreeInstr) * pl.steps.size();
   if (pbytes > e->capProg) {
     CK(cudaStreamSynchronize(e->stream));
     dfree(e->dProg);
@@ -880,12 +879,22 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     CK(cudaMemcpy(e->dNodeSc, hs.data(), sizeof(int32_t *) * e->cap, cudaMemcpyHostToDevice));
     e->nodeTabDirty = false;
   }
-  for (auto &in : pl.prog) {
-    in.out_clv = (e->opt_retain && in.out_slot >= 0) ? e->nodes[in.out_slot].clv : nullptr;
-    in.out_sc = (e->opt_retain && in.out_slot >= 0) ? e->nodes[in.out_slot].scale : nullptr;
+  {
+    TreeInstr *hp = (TreeInstr *)e->hProg;
+    for (size_t i = 0; i < pl.steps.size(); ++i) {
+      const PlanStep &st = pl.steps[i];
+      TreeInstr in{};
+      in.kinds = st.lkind | (st.rkind << 2) | (st.push_first << 4);
+      in.lidx = st.lidx;
+      in.ridx = st.ridx;
+      in.out_slot = st.out_slot;
+      in.out_clv = (e->opt_retain && st.out_slot >= 0) ? e->nodes[st.out_slot].clv : nullptr;
+      in.out_sc = (e->opt_retain && st.out_slot >= 0) ? e->nodes[st.out_slot].scale : nullptr;
+      hp[i] = in;
+      if (i + 1 < pl.steps.size()) { e->hT[2 * i] = st.t_left; e->hT[2 * i + 1] = st.t_right; }
+      else e->hT[2 * i] = st.t_left;
+    }
   }
-  std::memcpy(e->hProg, pl.prog.data(), pbytes);
-  std::memcpy(e->hT, pl.tlen.data(), sizeof(double) * nb);
   CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
   if ((rc = build_pt(e, nb, 1)) != PHYLO_OK) return rc;
   TreeArgs a;
