@@ -78,6 +78,7 @@ struct phylo_engine {
   size_t capP = 0;       // branches
   double *dT = nullptr, *hT = nullptr;  // branch lengths (device / pinned)
   double *dSite = nullptr;
+  double *dGroups = nullptr;                   // per-32-pattern sums (tree-fused kernel)
   double *dPart = nullptr, *dPart2 = nullptr;  // reduction levels
   int64_t nPart = 0;
   double *hScalar = nullptr;  // pinned
@@ -224,6 +225,7 @@ static void lk_free_data(phylo_engine *e) {
   dfree(e->dWeights);
   dfree(e->dSite);
   dfree(e->dPart);
+  dfree(e->dGroups);
   dfree(e->dPart2);
   e->T = 0; e->N = 0; e->cap = 0; e->lk_evaluated = false;
 }
@@ -480,6 +482,7 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     if (weights) CK(cudaMalloc(&e->dWeights, sizeof(double) * N));
     e->nPart = (N + kLnlBlock - 1) / kLnlBlock;
     CK(cudaMalloc(&e->dPart, sizeof(double) * e->nPart));
+    CK(cudaMalloc(&e->dGroups, sizeof(double) * e->nPart * 32));
     CK(cudaMalloc(&e->dPart2, sizeof(double) * ((e->nPart + kLnlBlock - 1) / kLnlBlock + 1) * 2));
     CK(cudaMalloc(&e->dSite, sizeof(double) * N));
   }
@@ -818,28 +821,31 @@ static bool build_fused_plan(int cap, int T, const phylo_op *ops, int n_ops, int
 
 static size_t tree_smem_bytes(int K, int T, int depth, int n_steps) {
   const size_t tile = (size_t)kTreeR * kTreeThreads / K;
-  return 2 * tile * 8 + 32 * 8 + 4 * 8 + (size_t)depth * kTreeR * kTreeThreads * (sizeof(d4) + sizeof(int)) +
+  return 2 * tile * 8 + 4 * 8 + (size_t)depth * kTreeR * kTreeThreads * (sizeof(d4) + sizeof(int)) +
          (size_t)(n_steps + 2) * sizeof(TreeInstr) + 128 + 2 * (size_t)T * (tile / 2);
 }
 
 template <int K>
 static cudaError_t launch_tree(phylo_engine *e, const TreeArgs &args, size_t smem, bool retain) {
-  const int64_t nblocks = (e->N + kLnlBlock - 1) / kLnlBlock;
+  const int64_t tile = (int64_t)kTreeR * kTreeThreads / K, ntiles = (e->N + tile - 1) / tile;
   cudaError_t st;
   int occ = 1;
   if (retain) {
     auto kern = lk_tree4_kernel<K, true>;
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTreeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-    const int g = (int)std::min<int64_t>(nblocks, (int64_t)e->sm_count * occ);
+    const int g = (int)std::min<int64_t>(ntiles, (int64_t)e->sm_count * occ);
     kern<<<g, kTreeThreads, smem, e->stream>>>(args);
   } else {
     auto kern = lk_tree4_kernel<K, false>;
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTreeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-    const int g = (int)std::min<int64_t>(nblocks, (int64_t)e->sm_count * occ);
+    const int g = (int)std::min<int64_t>(ntiles, (int64_t)e->sm_count * occ);
     kern<<<g, kTreeThreads, smem, e->stream>>>(args);
   }
+  if ((st = cudaGetLastError()) != cudaSuccess) return st;
+  fold_groups_kernel<<<(int)e->nPart, 32, 0, e->stream>>>(e->dGroups, (e->N + 31) / 32, e->dPart);
+  ++e->launches;
   return cudaSuccess;
 }
 
@@ -913,7 +919,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   a.inv = (const uint8_t *)e->dInv;
   a.weights = e->dWeights;
   a.site_lnl = e->dSite;
-  a.partials = e->dPart;
+  a.groups = e->dGroups;
   a.stack_depth = pl.depth;
   cudaError_t st = cudaSuccess;
   {

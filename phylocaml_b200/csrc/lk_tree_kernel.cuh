@@ -132,7 +132,7 @@ struct TreeArgs {
   const uint8_t *inv;
   const double *weights;
   double *site_lnl;
-  double *partials;
+  double *groups;          // [ceil(N/32)] sums of 32 consecutive weighted site lnL (canonical level 0)
   int stack_depth;
 };
 
@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
   constexpr int NT = kTreeThreads, R = kTreeR;
   constexpr int HALF = NT / K;              // patterns per r-slice of the tile
   constexpr int TILE = R * HALF;            // patterns per tile
-  constexpr int TILES = kLnlBlock / TILE;   // tiles per 1024-pattern reduction block
   constexpr int GROUPS = TILE / 32;         // 32-pattern fold groups per tile
   constexpr int PM = 16 * K;                // doubles per transition matrix set (all k)
   constexpr int TROW = TILE / 2;            // bytes per tip row of a tile (nibble packed)
@@ -149,8 +148,7 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stage = reinterpret_cast<double *>(smem_raw);                      // [2][TILE] site values
-  double *wsum = stage + 2 * TILE;                                           // [32] group sums
-  uint64_t *tipbar = reinterpret_cast<uint64_t *>(wsum + 32);                // [2] (+2 pad)
+  uint64_t *tipbar = reinterpret_cast<uint64_t *>(stage + 2 * TILE);         // [2] (+2 pad)
   d4 *stack = reinterpret_cast<d4 *>(tipbar + 4);                            // [depth][R][NT]
   int *stack_sc = reinterpret_cast<int *>(stack + (size_t)a.stack_depth * R * NT);
   int4 *sprog = reinterpret_cast<int4 *>(stack_sc + (size_t)a.stack_depth * R * NT);  // [n_steps][2]
@@ -160,7 +158,7 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
 
   const int tid = threadIdx.x, k = tid % K, pl = tid / K, lane = tid & 31, warp = tid >> 5;
   const int n_steps = a.n_instr + 1;  // + root step
-  const int64_t nblocks = (a.N + kLnlBlock - 1) / kLnlBlock;
+  const int64_t ntiles = (a.N + TILE - 1) / TILE;
 
   if (tid == 0) {
     mbar_init(&tipbar[0], 1);
@@ -191,32 +189,29 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
                  a.tips4 + ((size_t)t * a.tip_stride + p0) / 2, TROW, &tipbar[buf]);
     }
   };
-  // canonical level-1 fold of one finished tile: GROUPS warps fold 32 consecutive patterns each
-  auto fold_tile = [&](int sub_done, int sbuf) {
+  // canonical level 0 for a finished tile: each group of 32 consecutive patterns is folded
+  // by one warp. Runs at the start of the NEXT tile (after its barrier), off the critical path.
+  auto fold_tile = [&](int64_t done_tile, int sbuf) {
     for (int g = warp; g < GROUPS; g += NT / 32) {
       const double v = warp_fold(stage[sbuf * TILE + g * 32 + lane]);
-      if (lane == 0) wsum[sub_done * GROUPS + g] = v;
+      if (lane == 0) a.groups[done_tile * GROUPS + g] = v;
     }
   };
 
+  // work unit = one tile; each resident CTA owns a contiguous run of tiles (adjacent tiles
+  // keep the tip reads and CLV writes of a CTA in the same DRAM pages)
+  const int64_t per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_lo = (int64_t)blockIdx.x * per_cta, tile_hi = min(ntiles, tile_lo + per_cta);
   uint32_t tile_seq = 0;  // tiles processed by this CTA (double-buffer phase)
-  if ((int64_t)blockIdx.x < nblocks) issue_tips((int64_t)blockIdx.x * kLnlBlock, 0);
+  if (tile_lo < tile_hi) issue_tips(tile_lo * TILE, 0);
 
-  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-    if (tid < 32) wsum[tid] = 0.0;
-    const int64_t blk_p0 = blk * kLnlBlock;
-    const int tiles_here = (int)min((int64_t)TILES, (a.N - blk_p0 + TILE - 1) / TILE);
-    for (int sub = 0; sub < tiles_here; ++sub, ++tile_seq) {
-      const int64_t p0 = blk_p0 + (int64_t)sub * TILE;
+  for (int64_t tile = tile_lo; tile < tile_hi; ++tile, ++tile_seq) {
+    {
+      const int64_t p0 = tile * TILE;
       const int buf = tile_seq & 1;
       __syncthreads();  // every warp has finished the previous tile: buffer buf^1 is free
-      if (sub > 0) fold_tile(sub - 1, buf ^ 1);
-      {
-        int64_t np0 = -1;
-        if (sub + 1 < tiles_here) np0 = p0 + TILE;
-        else if (blk + gridDim.x < nblocks) np0 = (blk + gridDim.x) * kLnlBlock;
-        if (np0 >= 0) issue_tips(np0, buf ^ 1);
-      }
+      if (tile_seq > 0) fold_tile(tile - 1, buf ^ 1);
+      if (tile + 1 < tile_hi) issue_tips((tile + 1) * TILE, buf ^ 1);
       if (lane < 2 * K) {  // warm L1 with the matrices of the first steps
         for (int s = 0; s < kTreePrefetch && s < n_steps; ++s)
           prefetch_l1(a.P + (size_t)(2 * s) * PM + lane * 16);
@@ -406,15 +401,17 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
         }
       }
     }
-    __syncthreads();
-    fold_tile(tiles_here - 1, (tile_seq - 1) & 1);
-    __syncthreads();
-    if (warp == 0) {
-      const double rsum = warp_fold(wsum[lane]);
-      if (lane == 0) a.partials[blk] = rsum;
-    }
-    __syncthreads();
   }
+  __syncthreads();
+  if (tile_seq > 0) fold_tile(tile_hi - 1, (tile_seq - 1) & 1);  // the last tile of this CTA
+}
+
+// canonical level 1: partial[b] = fold of the 32 group sums of block b (groups past N are 0)
+__global__ void __launch_bounds__(32) fold_groups_kernel(const double *__restrict__ groups, int64_t n_groups,
+                                                         double *__restrict__ partials) {
+  const int64_t g = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const double v = warp_fold(g < n_groups ? groups[g] : 0.0);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
 }
 
 }  // namespace phylo
