@@ -1155,7 +1155,10 @@ static int np_device(int n_states) {
 static int fitch_ensure(phylo_engine *e, int slot, bool fin) {
   std::vector<uint32_t *> &v = fin ? e->fFin : e->fPre;
   if (v[slot]) return PHYLO_OK;
-  CK(cudaMalloc(&v[slot], sizeof(uint32_t) * (size_t)e->fWords * e->fNPdev));
+  // padded to whole 32-word tiles so the TMA-staged tree kernel can bulk-copy full tile rows
+  const size_t words_pad = (size_t)((e->fWords + 31) / 32) * 32;
+  CK(cudaMalloc(&v[slot], sizeof(uint32_t) * words_pad * e->fNPdev));
+  CK(cudaMemsetAsync(v[slot], 0, sizeof(uint32_t) * words_pad * e->fNPdev, e->stream));
   e->tabDirty = true;
   return PHYLO_OK;
 }
@@ -1370,18 +1373,20 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
     if ((rc = fitch_ensure(e, ops[o].parent, false)) != PHYLO_OK) return rc;
   if ((rc = fitch_sync_tables(e)) != PHYLO_OK) return rc;
   if ((rc = fitch_cost_capacity(e, (size_t)n_ops + 4)) != PHYLO_OK) return rc;
-  if ((rc = fitch_sched_capacity(e, sizeof(FitchStep) * (size_t)(n_ops + 1))) != PHYLO_OK) return rc;
+  if ((rc = fitch_sched_capacity(e, sizeof(FitchStep) * (size_t)(n_ops + 2))) != PHYLO_OK)
+    return rc;
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long) * (size_t)(n_ops + 2), e->stream));
+
   FitchStep *hs = (FitchStep *)e->hSched;
   for (int o = 0; o < n_ops; ++o) hs[o] = FitchStep{ops[o].parent, ops[o].left, ops[o].right};
   CK(cudaMemcpyAsync(e->dSched, hs, sizeof(FitchStep) * (size_t)n_ops, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long) * (size_t)(n_ops + 2), e->stream));
   const int g = grid_for(e->fWords, 128, e->sm_count * 16);
-  const size_t smem = sizeof(unsigned long long) * (size_t)(n_ops + 1);
+  const size_t smem2 = sizeof(unsigned long long) * (size_t)(n_ops + 1);
   {
   ProfScope prof(e, KC_FITCH_TREE);
-  NP_DISPATCH(e->fNPdev, (fitch_tree_kernel<NP><<<g, 128, smem, e->stream>>>(
-                             e->dPreTab, (const FitchStep *)e->dSched, n_ops, root_a, root_b, e->fWords, e->fN,
+  NP_DISPATCH(e->fNPdev, (fitch_tree_kernel<NP><<<g, 128, smem2, e->stream>>>(
+                             e->dPreTab, (const FitchStep *)e->dSched, n_ops, root_a, root_b, e->fT, e->fWords, e->fN,
                              e->dFW, e->dCost, e->dCost + n_ops + 1)));
   LAUNCH_CHECK();
   }

@@ -136,7 +136,7 @@ struct FitchStep {
 template <int NP>
 __global__ void __launch_bounds__(128)
 fitch_tree_kernel(uint32_t *const *__restrict__ bufs, const FitchStep *__restrict__ sched, int n_ops,
-                  int root_a, int root_b, int64_t nwords, int64_t N,
+                  int root_a, int root_b, int n_tips, int64_t nwords, int64_t N,
                   const uint32_t *__restrict__ wt, unsigned long long *__restrict__ node_cost,
                   unsigned long long *__restrict__ total) {
   extern __shared__ unsigned long long sh_cost[];  // n_ops + 1 per-CTA partial costs
@@ -148,6 +148,9 @@ fitch_tree_kernel(uint32_t *const *__restrict__ bufs, const FitchStep *__restric
     const int64_t w = w0 + threadIdx.x;
     const bool act = w < nwords;
     const uint32_t valid = act ? valid_mask(w, N) : 0u;
+    // (Measured alternatives, all slower than this plain walk: staging the tile's tip rows in
+    // shared memory by bulk-TMA or cp.async and walking a compiled stack schedule on chip;
+    // prefetching every tip row towards L2 first. See profiles/README.md.)
     for (int o = 0; o <= n_ops; ++o) {
       int il, ir, ip = -1;
       if (o < n_ops) {

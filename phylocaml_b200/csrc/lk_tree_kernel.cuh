@@ -30,8 +30,6 @@
 
 namespace phylo {
 
-enum : int { OPK_TIP = 0, OPK_CUR = 1, OPK_POP = 2, OPK_STORED = 3 };
-
 // One step of the compiled schedule: 32 bytes, read from shared memory one step ahead.
 struct __align__(16) TreeInstr {
   int kinds;             // lkind | rkind << 2 | push_first << 4
@@ -45,39 +43,6 @@ static_assert(sizeof(TreeInstr) == 32, "TreeInstr is two 16-byte words");
 constexpr int kTreeThreads = 128;
 constexpr int kTreeR = 2;         // patterns per thread
 constexpr int kTreePrefetch = 4;  // steps of look-ahead for the transition matrices
-
-// ---- mbarrier / bulk-TMA primitives (sm_90+ PTX, SASS: SYNCS / UBLKCP)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Transition matrices are stored k-interleaved by pt_build_kernel(interleave=1): element
 // e (= i*4+j) of rate class k sits at [e/2][k][e%2]. `pk` points at this thread's k.
