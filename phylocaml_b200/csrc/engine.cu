@@ -606,6 +606,22 @@ static cudaError_t launch_prune_any(phylo_engine *e, const double *Pl, const dou
   return cudaSuccess;
 }
 
+// fp64 tensor-core path for S = 20 / 61; returns false when the A fragments of all K rate
+// classes do not fit in shared memory (then the FMA kernel above is used)
+template <int S, typename MaskT>
+static bool launch_prune_mma(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
+                             const Operand &r, double *out, int32_t *osc, cudaError_t *st) {
+  constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4;
+  const size_t smem = sizeof(double) * 2 * (size_t)e->K * MT * KS * 32;
+  if (smem > 200 * 1024) return false;
+  auto kern = prune_mma_kernel<S, MaskT>;
+  *st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (*st != cudaSuccess) return true;
+  const int g = resident_grid(e, kern, 256, smem, (e->N + 63) / 64);
+  kern<<<g, 256, smem, e->stream>>>(Pl, Pr, l.src, l.scale, l.tip, r.src, r.scale, r.tip, out, osc, e->N, e->K);
+  return true;
+}
+
 static int lk_launch_prune(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
                            const Operand &r, double *out, int32_t *osc) {
   ProfScope prof(e, (l.tip && r.tip) ? KC_PRUNE_TT : ((l.tip || r.tip) ? KC_PRUNE_TI : KC_PRUNE_II));
@@ -619,7 +635,9 @@ static int lk_launch_prune(phylo_engine *e, const double *Pl, const double *Pr, 
     }
   } else {
     cudaError_t st;
-    if (e->S == 20) st = launch_prune_any<20, uint32_t>(e, Pl, Pr, l, r, out, osc);
+    if (e->S == 20 && launch_prune_mma<20, uint32_t>(e, Pl, Pr, l, r, out, osc, &st)) {}
+    else if (e->S == 61 && launch_prune_mma<61, uint64_t>(e, Pl, Pr, l, r, out, osc, &st)) {}
+    else if (e->S == 20) st = launch_prune_any<20, uint32_t>(e, Pl, Pr, l, r, out, osc);
     else if (e->S == 61) st = launch_prune_any<61, uint64_t>(e, Pl, Pr, l, r, out, osc);
     else if (e->mask_dev_bytes == 1) st = launch_prune_any<0, uint8_t>(e, Pl, Pr, l, r, out, osc);
     else if (e->mask_dev_bytes == 4) st = launch_prune_any<0, uint32_t>(e, Pl, Pr, l, r, out, osc);
