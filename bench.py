@@ -333,8 +333,14 @@ def main():
             return v
 
         def e2e_step():
-            eng.lk_set_tips(tips, capacity=n_nodes)
-            return step()
+            # host buffers in, scalar out: upload (pinned -> HBM, overlapped slab by slab with
+            # the scoring) + full evaluation + lnL read-back, through one C-ABI call
+            v = eng.lk_score_alignment(tips, ops, ra, rb, rt, capacity=n_nodes)
+            if world > 1:
+                acc[0] = v
+                dist.all_reduce(acc)
+                return float(acc.item())
+            return v
 
         metric, unit, dtype = "clv_site_updates_per_s", "site-updates/s", "f64"
         units_per_step = (T - 1) * n_total

@@ -121,6 +121,12 @@ int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int 
  * phylo_lk_edge_lnl / phylo_lk_get_clv / incremental re-scoring. */
 int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                         double root_t, double *lnl_out);
+/* phylo_lk_set_tips + phylo_lk_score_tree in one call for an alignment that is still in host
+ * memory: the upload is cut into pattern slabs on a second stream and each slab is scored
+ * (tree-fused kernel) while the next one is still crossing PCIe. Same result, bit for bit. */
+int phylo_lk_score_alignment(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                             const double *weights, int capacity, const phylo_op *ops, int n_ops,
+                             int root_a, int root_b, double root_t, double *lnl_out);
 /* Likelihood.root_cost / distance_1 (lib/nodeData.ml:29,32): lnL of joining the directed
  * CLVs a and b across an edge, for n_t candidate lengths (branch-length loop). */
 int phylo_lk_edge_lnl(phylo_engine *e, int a, int b, const double *t, int n_t, double *lnl_out);

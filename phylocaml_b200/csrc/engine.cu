@@ -66,6 +66,10 @@ struct phylo_engine {
   bool nodeTabDirty = true;
   void *dProg = nullptr, *hProg = nullptr;
   size_t capProg = 0;
+  cudaStream_t copyStream = nullptr;   // H2D of alignment slabs, overlapped with compute
+  cudaStream_t auxStream = nullptr;    // odd slabs compute here so slab kernels overlap their tails
+  cudaEvent_t auxDone = nullptr;
+  std::vector<cudaEvent_t> slabEvents;
   void *dRaw = nullptr;   // raw tip upload staging (kept across set_tips calls)
   size_t capRaw = 0;
   unsigned long long *dBad = nullptr;
@@ -252,6 +256,10 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
+  for (auto ev : e->slabEvents) cudaEventDestroy(ev);
+  if (e->copyStream) cudaStreamDestroy(e->copyStream);
+  if (e->auxStream) cudaStreamDestroy(e->auxStream);
+  if (e->auxDone) cudaEventDestroy(e->auxDone);
   if (e->hT) cudaFreeHost(e->hT);
   if (e->hScalar) cudaFreeHost(e->hScalar);
   if (e->hSched) cudaFreeHost(e->hSched);
@@ -425,40 +433,40 @@ extern "C" int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U
 static int dev_mask_bytes(int S) { return S <= 8 ? 1 : (S <= 32 ? 4 : 8); }
 
 template <typename InT>
-static int launch_tips_prepare(phylo_engine *e, const void *raw, unsigned long long *dBad) {
-  const int g = grid_for(e->N, 256, e->sm_count * 8);
+static int launch_tips_prepare(phylo_engine *e, const void *raw, unsigned long long *dBad, int64_t p_lo, int64_t p_hi,
+                               cudaStream_t cs) {
+  const int g = grid_for(p_hi - p_lo, 256, e->sm_count * 8);
   ProfScope prof(e, KC_TIPS_PREPARE);
   switch (e->mask_dev_bytes) {
     case 1:
-      tips_prepare_kernel<InT, uint8_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint8_t *)e->dTips, e->tipStride,
-                                                                 (uint8_t *)e->dInv, e->T, e->N, e->S, dBad);
+      tips_prepare_kernel<InT, uint8_t><<<g, 256, 0, cs>>>((const InT *)raw, (uint8_t *)e->dTips, e->tipStride,
+                                                                 (uint8_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi);
       break;
     case 4:
-      tips_prepare_kernel<InT, uint32_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint32_t *)e->dTips, e->tipStride,
-                                                                  (uint32_t *)e->dInv, e->T, e->N, e->S, dBad);
+      tips_prepare_kernel<InT, uint32_t><<<g, 256, 0, cs>>>((const InT *)raw, (uint32_t *)e->dTips, e->tipStride,
+                                                                  (uint32_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi);
       break;
     default:
-      tips_prepare_kernel<InT, uint64_t><<<g, 256, 0, e->stream>>>((const InT *)raw, (uint64_t *)e->dTips, e->tipStride,
-                                                                  (uint64_t *)e->dInv, e->T, e->N, e->S, dBad);
+      tips_prepare_kernel<InT, uint64_t><<<g, 256, 0, cs>>>((const InT *)raw, (uint64_t *)e->dTips, e->tipStride,
+                                                                  (uint64_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi);
   }
   LAUNCH_CHECK();
   return PHYLO_OK;
 }
 
-extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
-                                 const double *weights, int capacity) {
-  if (!e) return PHYLO_ERR_ARG;
-  if (!e->has_model) return fail(e, PHYLO_ERR_STATE, "lk_set_tips: call phylo_lk_set_model first");
+// validation + (re)allocation for an alignment of this shape; keeps every device allocation
+// when the shape is unchanged (a tree-search loop re-uploads often)
+static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                            const double *weights, int capacity, const char *who) {
+  if (!e->has_model) return fail(e, PHYLO_ERR_STATE, "%s: call phylo_lk_set_model first", who);
   if (T < 2 || N < 1 || !masks || capacity < T ||
       !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
-    return fail(e, PHYLO_ERR_ARG, "lk_set_tips: bad arguments (T=%d N=%lld mask_bytes=%d capacity=%d)", T,
+    return fail(e, PHYLO_ERR_ARG, "%s: bad arguments (T=%d N=%lld mask_bytes=%d capacity=%d)", who, T,
                 (long long)N, mask_bytes, capacity);
   if (mask_bytes * 8 < e->S)
-    return fail(e, PHYLO_ERR_ARG, "lk_set_tips: %d-bit masks cannot hold %d states", mask_bytes * 8, e->S);
+    return fail(e, PHYLO_ERR_ARG, "%s: %d-bit masks cannot hold %d states", who, mask_bytes * 8, e->S);
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  // same shape as what is loaded: keep every device allocation (tips, CLV arena, reduction
-  // scratch) and only refresh the contents -- a tree-search loop re-uploads often
   const bool reuse = e->dTips && e->T == T && e->N == N && e->cap == capacity &&
                      e->mask_dev_bytes == dev_mask_bytes(e->S) && (weights != nullptr) == (e->dWeights != nullptr);
   const size_t cells = (size_t)T * N;
@@ -494,40 +502,59 @@ extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *
     e->capRaw = cells * mask_bytes;
   }
   if (!e->dBad) CK(cudaMalloc(&e->dBad, sizeof(unsigned long long)));
-  void *raw = e->dRaw;
-  unsigned long long *dBad = e->dBad;
-  cudaError_t st = cudaMemsetAsync(dBad, 0, sizeof(unsigned long long), e->stream);
-  if (st == cudaSuccess) st = cudaMemcpyAsync(raw, masks, cells * mask_bytes, cudaMemcpyHostToDevice, e->stream);
-  if (st == cudaSuccess && weights)
-    st = cudaMemcpyAsync(e->dWeights, weights, sizeof(double) * N, cudaMemcpyHostToDevice, e->stream);
-  int rc = PHYLO_OK;
-  if (st == cudaSuccess) {
-    switch (mask_bytes) {
-      case 1: rc = launch_tips_prepare<uint8_t>(e, raw, dBad); break;
-      case 2: rc = launch_tips_prepare<uint16_t>(e, raw, dBad); break;
-      case 4: rc = launch_tips_prepare<uint32_t>(e, raw, dBad); break;
-      default: rc = launch_tips_prepare<uint64_t>(e, raw, dBad);
-    }
+  CK(cudaMemsetAsync(e->dBad, 0, sizeof(unsigned long long), e->stream));
+  if (weights) CK(cudaMemcpyAsync(e->dWeights, weights, sizeof(double) * N, cudaMemcpyHostToDevice, e->stream));
+  return PHYLO_OK;
+}
+
+// patterns [p_lo, p_hi) of the host alignment -> device: H2D on `copy` (NULL: the engine's
+// own stream), then mask conversion / validation / nibble packing on the engine's stream
+static int lk_upload_slab(phylo_engine *e, const void *masks, int mask_bytes, int64_t p_lo, int64_t p_hi,
+                          cudaStream_t copy, cudaEvent_t ready, cudaStream_t cs) {
+  const size_t pitch = (size_t)e->N * mask_bytes;
+  CK(cudaMemcpy2DAsync((char *)e->dRaw + (size_t)p_lo * mask_bytes, pitch, (const char *)masks + (size_t)p_lo * mask_bytes,
+                       pitch, (size_t)(p_hi - p_lo) * mask_bytes, e->T, cudaMemcpyHostToDevice, copy ? copy : cs));
+  if (copy) {
+    CK(cudaEventRecord(ready, copy));
+    CK(cudaStreamWaitEvent(cs, ready, 0));
   }
-  if (st == cudaSuccess && rc == PHYLO_OK && e->dTips4) {
+  int rc;
+  switch (mask_bytes) {
+    case 1: rc = launch_tips_prepare<uint8_t>(e, e->dRaw, e->dBad, p_lo, p_hi, cs); break;
+    case 2: rc = launch_tips_prepare<uint16_t>(e, e->dRaw, e->dBad, p_lo, p_hi, cs); break;
+    case 4: rc = launch_tips_prepare<uint32_t>(e, e->dRaw, e->dBad, p_lo, p_hi, cs); break;
+    default: rc = launch_tips_prepare<uint64_t>(e, e->dRaw, e->dBad, p_lo, p_hi, cs);
+  }
+  if (rc != PHYLO_OK) return rc;
+  if (e->dTips4) {
     ProfScope prof(e, KC_TIPS_PREPARE);
-    tips_pack4_kernel<<<grid_for((int64_t)T * e->tipStride / 2, 256, e->sm_count * 8), 256, 0, e->stream>>>(
-        (const uint8_t *)e->dTips, e->dTips4, T, N, e->tipStride);
-    ++e->launches;
-    st = cudaGetLastError();
-  }
-  unsigned long long bad = 0;
-  if (st == cudaSuccess && rc == PHYLO_OK)
-    st = cudaMemcpyAsync(e->hScalar, dBad, sizeof(bad), cudaMemcpyDeviceToHost, e->stream);
-  if (st == cudaSuccess && rc == PHYLO_OK) st = cudaStreamSynchronize(e->stream);
-  if (st == cudaSuccess && rc == PHYLO_OK) bad = *(unsigned long long *)e->hScalar;
-  if (rc != PHYLO_OK) { lk_free_data(e); return rc; }
-  if (st != cudaSuccess) { lk_free_data(e); return fail(e, PHYLO_ERR_CUDA, "lk_set_tips: %s", cudaGetErrorString(st)); }
-  if (bad) {
-    lk_free_data(e);
-    return fail(e, PHYLO_ERR_DATA, "lk_set_tips: %llu tip cells have none of the %d state bits set", bad, e->S);
+    const int64_t b_lo = p_lo / 2, b_hi = (p_hi >= e->N) ? e->tipStride / 2 : p_hi / 2;
+    tips_pack4_kernel<<<grid_for((int64_t)e->T * (b_hi - b_lo), 256, e->sm_count * 8), 256, 0, cs>>>(
+        (const uint8_t *)e->dTips, e->dTips4, e->T, e->N, e->tipStride, b_lo, b_hi);
+    LAUNCH_CHECK();
   }
   return PHYLO_OK;
+}
+
+// reads back the invalid-mask counter (call after a stream sync)
+static int lk_check_bad(phylo_engine *e, const char *who) {
+  CK(cudaMemcpyAsync(e->hScalar + 1, e->dBad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const unsigned long long bad = *(unsigned long long *)(e->hScalar + 1);
+  if (bad) {
+    lk_free_data(e);
+    return fail(e, PHYLO_ERR_DATA, "%s: %llu tip cells have none of the %d state bits set", who, bad, e->S);
+  }
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                 const double *weights, int capacity) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = lk_prepare_shape(e, T, N, masks, mask_bytes, weights, capacity, "lk_set_tips")) != PHYLO_OK) return rc;
+  if ((rc = lk_upload_slab(e, masks, mask_bytes, 0, N, nullptr, nullptr, e->stream)) != PHYLO_OK) { lk_free_data(e); return rc; }
+  return lk_check_bad(e, "lk_set_tips");
 }
 
 static int lk_ensure_node(phylo_engine *e, int slot) {
@@ -844,8 +871,11 @@ static size_t tree_smem_bytes(int K, int T, int depth, int n_steps) {
 }
 
 template <int K>
-static cudaError_t launch_tree(phylo_engine *e, const TreeArgs &args, size_t smem, bool retain) {
-  const int64_t tile = (int64_t)kTreeR * kTreeThreads / K, ntiles = (e->N + tile - 1) / tile;
+static cudaError_t launch_tree(phylo_engine *e, TreeArgs args, size_t smem, bool retain, int64_t tile_begin,
+                               int64_t tile_end, cudaStream_t cs) {
+  args.tile_begin = tile_begin;
+  args.tile_end = tile_end;
+  const int64_t ntiles = tile_end - tile_begin;
   cudaError_t st;
   int occ = 1;
   if (retain) {
@@ -853,23 +883,33 @@ static cudaError_t launch_tree(phylo_engine *e, const TreeArgs &args, size_t sme
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTreeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
     const int g = (int)std::min<int64_t>(ntiles, (int64_t)e->sm_count * occ);
-    kern<<<g, kTreeThreads, smem, e->stream>>>(args);
+    kern<<<g, kTreeThreads, smem, cs>>>(args);
   } else {
     auto kern = lk_tree4_kernel<K, false>;
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return st;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTreeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
     const int g = (int)std::min<int64_t>(ntiles, (int64_t)e->sm_count * occ);
-    kern<<<g, kTreeThreads, smem, e->stream>>>(args);
+    kern<<<g, kTreeThreads, smem, cs>>>(args);
   }
-  if ((st = cudaGetLastError()) != cudaSuccess) return st;
-  fold_groups_kernel<<<(int)e->nPart, 32, 0, e->stream>>>(e->dGroups, (e->N + 31) / 32, e->dPart);
   ++e->launches;
-  return cudaSuccess;
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_tree_k(phylo_engine *e, const TreeArgs &a, size_t smem, int64_t tile_begin, int64_t tile_end,
+                                 cudaStream_t cs) {
+  switch (e->K) {
+    case 1: return launch_tree<1>(e, a, smem, e->opt_retain, tile_begin, tile_end, cs);
+    case 2: return launch_tree<2>(e, a, smem, e->opt_retain, tile_begin, tile_end, cs);
+    case 4: return launch_tree<4>(e, a, smem, e->opt_retain, tile_begin, tile_end, cs);
+    default: return launch_tree<8>(e, a, smem, e->opt_retain, tile_begin, tile_end, cs);
+  }
 }
 
 // returns PHYLO_OK with *done = true when the fused kernel handled the evaluation
+// host_masks != NULL: the alignment is still on the host; it is uploaded in slabs on a second
+// stream while earlier slabs are already being scored (phylo_lk_score_alignment)
 static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt,
-                               bool *done) {
+                               bool *done, const void *host_masks = nullptr, int mask_bytes = 0) {
   *done = false;
   if (!e->opt_fused || e->S != 4 || e->mask_dev_bytes != 1 || !e->dTips4) return PHYLO_OK;
   if (!(e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8)) return PHYLO_OK;
@@ -939,16 +979,45 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   a.site_lnl = e->dSite;
   a.groups = e->dGroups;
   a.stack_depth = pl.depth;
-  cudaError_t st = cudaSuccess;
-  {
+  const int64_t tile = (int64_t)kTreeR * kTreeThreads / e->K, ntiles = (e->N + tile - 1) / tile;
+  if (!host_masks) {
     ProfScope prof(e, KC_TREE_FUSED);
-    switch (e->K) {
-      case 1: st = launch_tree<1>(e, a, smem, e->opt_retain); break;
-      case 2: st = launch_tree<2>(e, a, smem, e->opt_retain); break;
-      case 4: st = launch_tree<4>(e, a, smem, e->opt_retain); break;
-      default: st = launch_tree<8>(e, a, smem, e->opt_retain);
+    cudaError_t st = launch_tree_k(e, a, smem, 0, ntiles, e->stream);
+    if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch: %s", cudaGetErrorString(st));
+  } else {
+    // slabs of whole 1024-pattern blocks: >= ~2 waves of tiles each, at most 16 slabs
+    const int64_t blocks = e->nPart;
+    int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(16, blocks / 256));
+    if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    if (!e->auxStream) CK(cudaStreamCreateWithFlags(&e->auxStream, cudaStreamNonBlocking));
+    if (!e->auxDone) CK(cudaEventCreateWithFlags(&e->auxDone, cudaEventDisableTiming));
+    while ((int)e->slabEvents.size() < nslab + 1) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->slabEvents.push_back(ev);
     }
-    if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch setup: %s", cudaGetErrorString(st));
+    // the aux stream starts after the set-up work already queued on the engine's stream
+    // (program upload, pt_build, weights); the copy stream needs nothing: the staging buffer is
+    // idle (the engine's stream was synchronised above)
+    CK(cudaEventRecord(e->slabEvents[nslab], e->stream));
+    CK(cudaStreamWaitEvent(e->auxStream, e->slabEvents[nslab], 0));
+    for (int sidx = 0; sidx < nslab; ++sidx) {
+      // consecutive slabs alternate between two compute streams so that the tail of one
+      // slab's kernel overlaps the head of the next
+      cudaStream_t cs = (sidx & 1) ? e->auxStream : e->stream;
+      const int64_t b_lo = blocks * sidx / nslab, b_hi = blocks * (sidx + 1) / nslab;
+      const int64_t p_lo = b_lo * kLnlBlock, p_hi = std::min<int64_t>(e->N, b_hi * kLnlBlock);
+      if ((rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, e->copyStream, e->slabEvents[sidx], cs)) != PHYLO_OK)
+        return rc;
+      cudaError_t st = launch_tree_k(e, a, smem, p_lo / tile, (p_hi + tile - 1) / tile, cs);
+      if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch: %s", cudaGetErrorString(st));
+    }
+    CK(cudaEventRecord(e->auxDone, e->auxStream));
+    CK(cudaStreamWaitEvent(e->stream, e->auxDone, 0));
+  }
+  {
+    ProfScope prof(e, KC_REDUCE);
+    fold_groups_kernel<<<(int)e->nPart, 32, 0, e->stream>>>(e->dGroups, (e->N + 31) / 32, e->dPart);
     LAUNCH_CHECK();
   }
   if (e->opt_retain)
@@ -985,6 +1054,27 @@ extern "C" int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t
   return PHYLO_OK;
 }
 
+// children must be tips or CLVs that exist (resident or produced earlier in the schedule)
+static int lk_validate_schedule(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                const char *who) {
+  std::vector<char> ready(e->cap, 0);
+  for (int s = 0; s < e->cap; ++s) ready[s] = (s < e->T) || e->nodes[s].valid;
+  for (int o = 0; o < n_ops; ++o) {
+    const phylo_op &op = ops[o];
+    if (op.parent < e->T || op.parent >= e->cap)
+      return fail(e, PHYLO_ERR_ARG, "%s: op %d parent slot %d must be in [%d,%d)", who, o, op.parent, e->T, e->cap);
+    if (op.left < 0 || op.left >= e->cap || op.right < 0 || op.right >= e->cap || op.left == op.parent ||
+        op.right == op.parent)
+      return fail(e, PHYLO_ERR_ARG, "%s: op %d has bad child slots (%d,%d)", who, o, op.left, op.right);
+    if (!ready[op.left] || !ready[op.right])
+      return fail(e, PHYLO_ERR_ARG, "%s: op %d uses a child that is not computed yet (not post-order)", who, o);
+    ready[op.parent] = 1;
+  }
+  if (root_a < 0 || root_a >= e->cap || root_b < 0 || root_b >= e->cap || !ready[root_a] || !ready[root_b])
+    return fail(e, PHYLO_ERR_ARG, "%s: bad root edge (%d,%d)", who, root_a, root_b);
+  return PHYLO_OK;
+}
+
 extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                                    double root_t, double *lnl_out) {
   if (!e) return PHYLO_ERR_ARG;
@@ -992,24 +1082,7 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
   if (n_ops < 0 || (n_ops > 0 && !ops) || !lnl_out) return fail(e, PHYLO_ERR_ARG, "lk_score_tree: bad arguments");
   CK(cudaSetDevice(e->device));
   int rc;
-  // validate the schedule before touching the device: children must be tips or produced earlier
-  {
-    std::vector<char> ready(e->cap, 0);
-    for (int s = 0; s < e->cap; ++s) ready[s] = (s < e->T) || e->nodes[s].valid;
-    for (int o = 0; o < n_ops; ++o) {
-      const phylo_op &op = ops[o];
-      if (op.parent < e->T || op.parent >= e->cap)
-        return fail(e, PHYLO_ERR_ARG, "lk_score_tree: op %d parent slot %d must be in [%d,%d)", o, op.parent, e->T, e->cap);
-      if (op.left < 0 || op.left >= e->cap || op.right < 0 || op.right >= e->cap || op.left == op.parent ||
-          op.right == op.parent)
-        return fail(e, PHYLO_ERR_ARG, "lk_score_tree: op %d has bad child slots (%d,%d)", o, op.left, op.right);
-      if (!ready[op.left] || !ready[op.right])
-        return fail(e, PHYLO_ERR_ARG, "lk_score_tree: op %d uses a child that is not computed yet (not post-order)", o);
-      ready[op.parent] = 1;
-    }
-    if (root_a < 0 || root_a >= e->cap || root_b < 0 || root_b >= e->cap || !ready[root_a] || !ready[root_b])
-      return fail(e, PHYLO_ERR_ARG, "lk_score_tree: bad root edge (%d,%d)", root_a, root_b);
-  }
+  if ((rc = lk_validate_schedule(e, ops, n_ops, root_a, root_b, "lk_score_tree")) != PHYLO_OK) return rc;
   {
     bool done = false;
     if ((rc = lk_score_tree_fused(e, ops, n_ops, root_a, root_b, root_t, &done)) != PHYLO_OK) return rc;
@@ -1047,6 +1120,32 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
   if ((rc = lk_operand(e, root_b, &b, "lk_score_tree")) != PHYLO_OK) return rc;
   if ((rc = lk_root_eval(e, e->dP + (size_t)(2 * n_ops) * pk, a, b, e->hScalar)) != PHYLO_OK) return rc;
   CK(cudaStreamSynchronize(e->stream));
+  *lnl_out = e->hScalar[0];
+  e->lk_evaluated = true;
+  if (e->prof_on) prof_resolve(e);
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_score_alignment(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                        const double *weights, int capacity, const phylo_op *ops, int n_ops,
+                                        int root_a, int root_b, double root_t, double *lnl_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (n_ops < 0 || (n_ops > 0 && !ops) || !lnl_out) return fail(e, PHYLO_ERR_ARG, "lk_score_alignment: bad arguments");
+  int rc;
+  if ((rc = lk_prepare_shape(e, T, N, masks, mask_bytes, weights, capacity, "lk_score_alignment")) != PHYLO_OK) return rc;
+  if ((rc = lk_validate_schedule(e, ops, n_ops, root_a, root_b, "lk_score_alignment")) != PHYLO_OK) return rc;
+  bool done = false;
+  if ((rc = lk_score_tree_fused(e, ops, n_ops, root_a, root_b, root_t, &done, masks, mask_bytes)) != PHYLO_OK) {
+    lk_free_data(e);
+    return rc;
+  }
+  if (!done) {  // not eligible for the fused kernel: plain upload, then the per-node path
+    if ((rc = lk_upload_slab(e, masks, mask_bytes, 0, N, nullptr, nullptr, e->stream)) != PHYLO_OK) { lk_free_data(e); return rc; }
+    if ((rc = lk_check_bad(e, "lk_score_alignment")) != PHYLO_OK) return rc;
+    return phylo_lk_score_tree(e, ops, n_ops, root_a, root_b, root_t, lnl_out);
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  if ((rc = lk_check_bad(e, "lk_score_alignment")) != PHYLO_OK) return rc;
   *lnl_out = e->hScalar[0];
   e->lk_evaluated = true;
   if (e->prof_on) prof_resolve(e);

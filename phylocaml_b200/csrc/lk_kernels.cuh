@@ -672,10 +672,11 @@ template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, int64_t out_stride,
                     OutT *__restrict__ inv, int T, int64_t N, int S,
-                    unsigned long long *__restrict__ n_bad) {
+                    unsigned long long *__restrict__ n_bad, int64_t p_lo, int64_t p_hi) {
+  // patterns [p_lo, p_hi): a slab of the alignment (the whole of it for a plain set_tips)
   const uint64_t keep = (S >= 64) ? ~0ull : ((1ull << S) - 1);
   unsigned long long bad = 0;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N;
+  for (int64_t p = p_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < p_hi;
        p += (int64_t)gridDim.x * blockDim.x) {
     uint64_t all = keep;
     for (int t = 0; t < T; ++t) {
@@ -690,17 +691,17 @@ tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, int64_t 
 }
 
 // Two 4-bit masks per byte (even pattern in the low nibble) for the tree-fused kernel's tip
-// tiles; cells beyond N read as "all states".
+// tiles; cells beyond N read as "all states". Bytes [b_lo, b_hi) of every row.
 __global__ void __launch_bounds__(256)
 tips_pack4_kernel(const uint8_t *__restrict__ tips, uint8_t *__restrict__ tips4, int T, int64_t N,
-                  int64_t stride) {
-  const int64_t half = stride / 2, total = (int64_t)T * half;
+                  int64_t stride, int64_t b_lo, int64_t b_hi) {
+  const int64_t half = stride / 2, span = b_hi - b_lo, total = (int64_t)T * span;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = i / half, b = i - t * half, p = 2 * b;
+    const int64_t t = i / span, b = b_lo + (i - t * span), p = 2 * b;
     const int lo = p < N ? (tips[t * stride + p] & 15) : 15;
     const int hi = p + 1 < N ? (tips[t * stride + p + 1] & 15) : 15;
-    tips4[i] = (uint8_t)(lo | (hi << 4));
+    tips4[t * half + b] = (uint8_t)(lo | (hi << 4));
   }
 }
 

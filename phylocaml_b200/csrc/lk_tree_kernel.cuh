@@ -99,6 +99,7 @@ struct TreeArgs {
   double *site_lnl;
   double *groups;          // [ceil(N/32)] sums of 32 consecutive weighted site lnL (canonical level 0)
   int stack_depth;
+  int64_t tile_begin, tile_end;  // tiles this launch covers (a slab of the alignment)
 };
 
 template <int K, bool RETAIN>
@@ -165,8 +166,9 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
 
   // work unit = one tile; each resident CTA owns a contiguous run of tiles (adjacent tiles
   // keep the tip reads and CLV writes of a CTA in the same DRAM pages)
-  const int64_t per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
-  const int64_t tile_lo = (int64_t)blockIdx.x * per_cta, tile_hi = min(ntiles, tile_lo + per_cta);
+  const int64_t slab_end = min(ntiles, a.tile_end);
+  const int64_t per_cta = (slab_end - a.tile_begin + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_lo = a.tile_begin + (int64_t)blockIdx.x * per_cta, tile_hi = min(slab_end, tile_lo + per_cta);
   uint32_t tile_seq = 0;  // tiles processed by this CTA (double-buffer phase)
   if (tile_lo < tile_hi) issue_tips(tile_lo * TILE, 0);
 

@@ -52,6 +52,8 @@ SIGNATURES = {
     "phylo_lk_set_tips": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int]),
     "phylo_lk_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]),
     "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
+    "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
+                                           C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "phylo_lk_get_clv": (C.c_int, [_vp, C.c_int, _dp, _vp]),
     "phylo_lk_get_site_lnl": (C.c_int, [_vp, _dp]),
@@ -266,6 +268,19 @@ class Engine:
         out = C.c_double()
         self._ck(self.lib.phylo_lk_score_tree(self.h, _p(ops), len(ops), root_a, root_b, float(root_t),
                                               C.byref(out)))
+        return out.value
+
+    def lk_score_alignment(self, tips, ops, root_a, root_b, root_t, weights=None, capacity=None):
+        """set_tips + score_tree with the upload overlapped with the scoring."""
+        tips = np.ascontiguousarray(tips)
+        T, N = tips.shape
+        capacity = 2 * T if capacity is None else capacity
+        w = None if weights is None else _f64(weights)
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        out = C.c_double()
+        self._ck(self.lib.phylo_lk_score_alignment(self.h, T, N, _p(tips), tips.dtype.itemsize, _p(w, _dp), capacity,
+                                                   _p(ops), len(ops), root_a, root_b, float(root_t), C.byref(out)))
+        self.lk_shape = (T, N, capacity)
         return out.value
 
     def lk_edge_lnl(self, a, b, ts):

@@ -419,3 +419,29 @@ def test_fused_tree_incremental_rescoring_from_stored_clvs(eng, oracle):
     assert rel_err(inc, full) <= LNL_RTOL
     eng.lk_set_tips(tips, capacity=n_nodes)
     assert eng.lk_score_tree(ops2, ra, rb, rt) == inc
+
+
+@pytest.mark.parametrize("N", [700, 300000, 600001])
+def test_lk_score_alignment_pipelined_equals_two_calls(eng, N):
+    """phylo_lk_score_alignment (slab-pipelined upload + fused scoring) == set_tips + score_tree,
+    bit for bit, for sizes below and above the slab threshold, with weights."""
+    model = dna_gtr_g4()
+    tr = tree.random_tree(12, 3)
+    ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+    base = tree.evolve_tips(tr, model, 5000, seed=4)
+    tips = np.ascontiguousarray(np.tile(base, (1, N // 5000 + 1))[:, :N])
+    w = np.random.default_rng(1).integers(1, 4, N).astype(float)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, weights=w, capacity=n_nodes)
+    two = eng.lk_score_tree(ops, ra, rb, rt)
+    clv_two = eng.lk_get_clv(int(ops[-1]["parent"]))
+    eng.lk_set_tips(np.ascontiguousarray(tips[:, ::-1]), weights=w, capacity=n_nodes)  # clobber device state
+    one = eng.lk_score_alignment(tips, ops, ra, rb, rt, weights=w, capacity=n_nodes)
+    clv_one = eng.lk_get_clv(int(ops[-1]["parent"]))
+    assert one == two
+    assert np.array_equal(clv_one[0], clv_two[0]) and np.array_equal(clv_one[1], clv_two[1])
+    bad = tips.copy()
+    bad[3, N // 2] = 0
+    with pytest.raises(engine.PhyloError) as ei:
+        eng.lk_score_alignment(bad, ops, ra, rb, rt, capacity=n_nodes)
+    assert ei.value.code == -4
