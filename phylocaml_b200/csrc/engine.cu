@@ -324,8 +324,8 @@ extern "C" int phylo_host_free(void *p) {
 
 // ---------------------------------------------------------------- P(t) plumbing ----
 static int ensure_pt_capacity(phylo_engine *e, size_t branches, int S, int K) {
-  if (branches <= e->capP && e->dP) return PHYLO_OK;
-  size_t nb = std::max(branches, (size_t)64);
+  if (branches + 1 <= e->capP && e->dP) return PHYLO_OK;
+  size_t nb = std::max(branches + 1, (size_t)64);  // +1: the fused kernel copies matrix sets in pairs
   CK(cudaStreamSynchronize(e->stream));
   dfree(e->dP);
   dfree(e->dT);
@@ -867,7 +867,8 @@ static bool build_fused_plan(int cap, int T, const phylo_op *ops, int n_ops, int
 static size_t tree_smem_bytes(int K, int T, int depth, int n_steps) {
   const size_t tile = (size_t)kTreeR * kTreeThreads / K;
   return 2 * tile * 8 + 4 * 8 + (size_t)depth * kTreeR * kTreeThreads * (sizeof(d4) + sizeof(int)) +
-         (size_t)(n_steps + 2) * sizeof(TreeInstr) + 128 + 2 * (size_t)T * (tile / 2);
+         (size_t)(n_steps + 2) * sizeof(TreeInstr) + (size_t)(kTreeThreads / 32) * 2 * 2 * 16 * K * 8 + 128 +
+         (size_t)T * (tile / 2);
 }
 
 template <int K>

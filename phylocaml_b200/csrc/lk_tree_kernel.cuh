@@ -17,9 +17,11 @@
 //   * tip masks of a tile ([T rows] x [TILE patterns], two 4-bit masks per byte) are staged by bulk-TMA
 //     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), double buffered so the
 //     next tile's tips land while this tile is computed;
-//   * the transition matrices of a step are read through L1 (k-interleaved layout: the K
-//     lanes of a pattern read adjacent 16-byte chunks, all patterns the same address) and
-//     software-prefetched a few steps ahead (prefetch.global.L1);
+//   * the transition matrices of a step (1 KB for K=4, k-interleaved so the K lanes of a
+//     pattern read adjacent 16-byte chunks) are copied by each warp into its own
+//     double-buffered shared-memory slot with cp.async one step ahead. (They were first read
+//     through L1 with prefetch.global.L1 -- but with 4 CTAs x 52 KB the carve-out leaves no L1:
+//     29 % of the sectors missed to L2 and the first use of each matrix stalled.)
 //   * retained CLVs leave as 256-bit stores, 1 KB contiguous per warp.
 //
 // Arithmetic and its order are those of prune4_kernel / root4_kernel (=> same bits); a
@@ -51,7 +53,7 @@ template <int K>
 __device__ __forceinline__ void load_half(const double *__restrict__ pk, int h, double (&pm)[8]) {
 #pragma unroll
   for (int ep = 0; ep < 4; ++ep) {
-    const double2 t = __ldg(reinterpret_cast<const double2 *>(pk + (h * 4 + ep) * K * 2));
+    const double2 t = *reinterpret_cast<const double2 *>(pk + (h * 4 + ep) * K * 2);
     pm[2 * ep] = t.x;
     pm[2 * ep + 1] = t.y;
   }
@@ -118,9 +120,10 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
   d4 *stack = reinterpret_cast<d4 *>(tipbar + 4);                            // [depth][R][NT]
   int *stack_sc = reinterpret_cast<int *>(stack + (size_t)a.stack_depth * R * NT);
   int4 *sprog = reinterpret_cast<int4 *>(stack_sc + (size_t)a.stack_depth * R * NT);  // [n_steps][2]
-  uint8_t *tipbuf = reinterpret_cast<uint8_t *>(sprog + 2 * (size_t)(a.n_instr + 2));
+  double *pring = reinterpret_cast<double *>(sprog + 2 * (size_t)(a.n_instr + 2));     // [warps][2][2*PM]
+  uint8_t *tipbuf = reinterpret_cast<uint8_t *>(pring + (size_t)(NT / 32) * 2 * 2 * PM);
   tipbuf = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tipbuf) + 127) & ~(uintptr_t)127);
-  const size_t tipbuf_bytes = (size_t)a.T * TROW;                            // per buffer
+  const size_t tipbuf_bytes = (size_t)a.T * TROW;
 
   const int tid = threadIdx.x, k = tid % K, pl = tid / K, lane = tid & 31, warp = tid >> 5;
   const int n_steps = a.n_instr + 1;  // + root step
@@ -137,22 +140,28 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
   __syncthreads();
 
   const double pi0 = a.pi[0], pi1 = a.pi[1], pi2 = a.pi[2], pi3 = a.pi[3], pk_prob = a.probs[k];
-  const double *Pk = a.P + k * 2;  // this thread's rate class inside every matrix set
+  double *myring = pring + (size_t)warp * 2 * 2 * PM;  // this warp's two matrix slots
+  // copy the two matrix sets of `step` (contiguous in a.P) into ring slot `slot`
+  auto fetch_matrices = [&](int step, int slot) {
+    const double *src = a.P + (size_t)(2 * step) * PM;
+    double *dst = myring + (size_t)slot * 2 * PM;
+    for (int c = lane; c < PM; c += 32) cp_async16(dst + 2 * c, src + 2 * c);
+    cp_async_commit();
+  };
   d4 *mystack = stack + tid;
   int *mystack_sc = stack_sc + tid;
   // nibble of pattern (pl + r*HALF) inside a tip row of the tile
   const int tb_off0 = pl >> 1, tb_off1 = (pl + HALF) >> 1, tb_sh = (pl & 1) * 4;  // HALF is even
 
-  auto issue_tips = [&](int64_t p0, int buf) {  // warp 0 stages the tip rows of one tile
+  auto issue_tips = [&](int64_t p0) {  // warp 0 stages the tip rows of one tile (bulk-TMA)
     if (tid < 32) {
       if (tid == 0) {
         fence_proxy_async();
-        mbar_expect_tx(&tipbar[buf], (uint32_t)tipbuf_bytes);
+        mbar_expect_tx(&tipbar[0], (uint32_t)tipbuf_bytes);
       }
       __syncwarp();
       for (int t = tid; t < a.T; t += 32)
-        bulk_g2s(tipbuf + (size_t)buf * tipbuf_bytes + (size_t)t * TROW,
-                 a.tips4 + ((size_t)t * a.tip_stride + p0) / 2, TROW, &tipbar[buf]);
+        bulk_g2s(tipbuf + (size_t)t * TROW, a.tips4 + ((size_t)t * a.tip_stride + p0) / 2, TROW, &tipbar[0]);
     }
   };
   // canonical level 0 for a finished tile: each group of 32 consecutive patterns is folded
@@ -169,22 +178,18 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
   const int64_t slab_end = min(ntiles, a.tile_end);
   const int64_t per_cta = (slab_end - a.tile_begin + gridDim.x - 1) / gridDim.x;
   const int64_t tile_lo = a.tile_begin + (int64_t)blockIdx.x * per_cta, tile_hi = min(slab_end, tile_lo + per_cta);
-  uint32_t tile_seq = 0;  // tiles processed by this CTA (double-buffer phase)
-  if (tile_lo < tile_hi) issue_tips(tile_lo * TILE, 0);
+  uint32_t tile_seq = 0;  // tiles processed by this CTA
 
   for (int64_t tile = tile_lo; tile < tile_hi; ++tile, ++tile_seq) {
     {
       const int64_t p0 = tile * TILE;
-      const int buf = tile_seq & 1;
-      __syncthreads();  // every warp has finished the previous tile: buffer buf^1 is free
+      const int buf = tile_seq & 1;  // site-value staging buffer of this tile
+      __syncthreads();  // every warp has finished the previous tile: the tip buffer is free
+      issue_tips(p0);
       if (tile_seq > 0) fold_tile(tile - 1, buf ^ 1);
-      if (tile + 1 < tile_hi) issue_tips((tile + 1) * TILE, buf ^ 1);
-      if (lane < 2 * K) {  // warm L1 with the matrices of the first steps
-        for (int s = 0; s < kTreePrefetch && s < n_steps; ++s)
-          prefetch_l1(a.P + (size_t)(2 * s) * PM + lane * 16);
-      }
-      mbar_wait(&tipbar[buf], (tile_seq >> 1) & 1);
-      const uint8_t *tb = tipbuf + (size_t)buf * tipbuf_bytes;
+      fetch_matrices(0, 0);  // matrices of step 0 while the tips are in flight
+      mbar_wait(&tipbar[0], tile_seq & 1);
+      const uint8_t *tb = tipbuf;
 
       int64_t pat[R], item_off[R];
       bool active[R];
@@ -208,17 +213,23 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
         mlb0 = tb[lrow * TROW + tb_off0]; mlb1 = tb[lrow * TROW + tb_off1];
         mrb0 = tb[rrow * TROW + tb_off0]; mrb1 = tb[rrow * TROW + tb_off1];
       }
-      const double *pm_ = Pk;                                                  // matrices of this step
-      const double *pf_ = a.P + (size_t)(2 * kTreePrefetch) * PM + lane * 16;  // L1 prefetch cursor
-      // rolling half-matrix pipeline: while one half (2 rows) is being multiplied, the load of
-      // the half needed next is already in flight -- across sides and across steps
+      // rolling half-matrix pipeline over the warp's shared-memory slots: slot (step & 1)
+      // holds this step's two matrix sets; the copy of the next step's is issued first
       double hA[8], hB[8];
-      load_half<K>(pm_, 0, hA);
-      load_half<K>(pm_, 1, hB);
+      cp_async_wait<0>();
+      __syncwarp();
+      {
+        const double *pm0 = myring + k * 2;
+        load_half<K>(pm0, 0, hA);
+        load_half<K>(pm0, 1, hB);
+      }
 
-      for (int step = 0; step < a.n_instr; ++step, pm_ += 2 * PM, pf_ += 2 * PM) {
+      for (int step = 0; step < a.n_instr; ++step) {
+        __syncwarp();                               // all lanes are done with slot (step+1)&1
+        fetch_matrices(step + 1, (step + 1) & 1);   // the root's matrix after the last step
+        const double *pm_ = myring + (size_t)(step & 1) * 2 * PM + k * 2;
+        const double *pn_ = myring + (size_t)((step + 1) & 1) * 2 * PM + k * 2;
         const int lkind = iw.x & 3, rkind = (iw.x >> 2) & 3, push = iw.x & 16, lidx = iw.y, ridx = iw.z;
-        if (lane < 2 * K && step + kTreePrefetch < n_steps) prefetch_l1(pf_);
         const int4 ow = RETAIN ? sprog[2 * step + 1] : make_int4(0, 0, 0, 0);  // out_clv, out_sc
         const int4 nw = sprog[2 * step + 2];                                   // next step's word
         if (push) {
@@ -295,14 +306,16 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
           matvec_half(hA, rv[r], y0, y1);
           v[r].x = x[r][0] * y0; v[r].y = x[r][1] * y1;
         }
-        load_half<K>(pm_ + 2 * PM, 0, hA);
+        cp_async_wait<0>();  // next step's matrices have landed in the other slot
+        __syncwarp();
+        load_half<K>(pn_, 0, hA);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           double y2, y3;
           matvec_half(hB, rv[r], y2, y3);
           v[r].z = x[r][2] * y2; v[r].w = x[r][3] * y3;
         }
-        load_half<K>(pm_ + 2 * PM, 1, hB);
+        load_half<K>(pn_, 1, hB);
         double *oc = reinterpret_cast<double *>(((uint64_t)(uint32_t)ow.y << 32) | (uint32_t)ow.x);
         int32_t *os = reinterpret_cast<int32_t *>(((uint64_t)(uint32_t)ow.w << 32) | (uint32_t)ow.z);
 #pragma unroll
