@@ -61,7 +61,8 @@ int phylo_engine_sync(phylo_engine *e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches evidence) */
 uint64_t phylo_engine_launch_count(const phylo_engine *e);
 /* Engine options. PHYLO_OPT_FUSED_TREE (default 1): phylo_lk_score_tree evaluates eligible
- * schedules (4 states, K in {1,2,4,8}, plain tree) with the single-launch tree-fused kernel;
+ * schedules (4 states, K in {1,2,4,8}, plain tree) with a single-launch tree-fused kernel
+ * (warp-autonomous kernel for K <= 4, tile kernel otherwise); 2 = tile kernel only;
  * 0 = one kernel per node. PHYLO_OPT_RETAIN_CLV (default 1): every interior CLV of a
  * score_tree call is left in its node slot (for phylo_lk_get_clv / edge_lnl / incremental
  * re-scoring); 0 = lnL only, the tree-fused kernel then writes no CLV at all. */

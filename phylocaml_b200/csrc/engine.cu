@@ -2,6 +2,7 @@
 // Host-side handle, device arenas and kernel dispatch; all arithmetic lives in the kernels
 // (lk_kernels.cuh, fitch_kernels.cuh). No CPU fallback anywhere: every entry point that
 // computes launches CUDA kernels on the handle's device.
+#include <cuda.h>  // CUtensorMap types only; the driver entry point is resolved at run time
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -15,6 +16,7 @@
 #include "fitch_kernels.cuh"
 #include "lk_kernels.cuh"
 #include "lk_tree_kernel.cuh"
+#include "lk_treew_kernel.cuh"
 #include "phylo_engine.h"
 
 using namespace phylo;
@@ -59,7 +61,15 @@ struct phylo_engine {
   // ---- likelihood data
   int T = 0, cap = 0, mask_dev_bytes = 1;
   int64_t N = 0;
-  bool opt_fused = true, opt_retain = true;
+  int opt_fused = 1;  // 0 = one kernel per node, 1 = tree-fused (warp-autonomous where eligible), 2 = tile kernel only
+  bool opt_retain = true;
+  // TMA tensor maps of the node CLVs (warp-autonomous tree kernel stores through them)
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn encodeTiled = nullptr;
+  CUtensorMap *dTmaps = nullptr;  // [cap]
+  bool tmapDirty = true;
   int64_t tipStride = 0;  // elements per tip row (N rounded up to 1024)
   double **dNodeClv = nullptr;   // device tables of node buffers (tree-fused kernel)
   int32_t **dNodeSc = nullptr;
@@ -206,6 +216,14 @@ extern "C" int phylo_engine_create(int device, phylo_engine **out) {
   e = new phylo_engine();
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
+  {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      e->encodeTiled = (phylo_engine::EncodeTiledFn)fn;
+    cudaGetLastError();
+  }
   if (cudaMallocHost(&e->hScalar, 64) != cudaSuccess) {
     delete e;
     return fail(nullptr, PHYLO_ERR_CUDA, "phylo_engine_create: cudaMallocHost failed");
@@ -224,7 +242,9 @@ static void lk_free_data(phylo_engine *e) {
   dfree(e->dTips4);
   dfree(e->dNodeClv);
   dfree(e->dNodeSc);
+  dfree(e->dTmaps);
   e->nodeTabDirty = true;
+  e->tmapDirty = true;
   dfree(e->dInv);
   dfree(e->dWeights);
   dfree(e->dSite);
@@ -485,7 +505,9 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
     if (e->S == 4) CK(cudaMalloc(&e->dTips4, (size_t)T * e->tipStride / 2));
     CK(cudaMalloc(&e->dNodeClv, sizeof(double *) * capacity));
     CK(cudaMalloc(&e->dNodeSc, sizeof(int32_t *) * capacity));
+    CK(cudaMalloc(&e->dTmaps, sizeof(CUtensorMap) * capacity));
     e->nodeTabDirty = true;
+    e->tmapDirty = true;
     CK(cudaMalloc(&e->dInv, (size_t)N * e->mask_dev_bytes));
     if (weights) CK(cudaMalloc(&e->dWeights, sizeof(double) * N));
     e->nPart = (N + kLnlBlock - 1) / kLnlBlock;
@@ -563,6 +585,7 @@ static int lk_ensure_node(phylo_engine *e, int slot) {
   CK(cudaMalloc(&n.clv, sizeof(double) * (size_t)e->N * e->K * e->S));
   CK(cudaMalloc(&n.scale, sizeof(int32_t) * (size_t)e->N));
   e->nodeTabDirty = true;
+  e->tmapDirty = true;
   return PHYLO_OK;
 }
 
@@ -751,7 +774,7 @@ static int lk_finish_reduce(phylo_engine *e, double *slot) {
 extern "C" int phylo_engine_set_option(phylo_engine *e, int option, int64_t value) {
   if (!e) return PHYLO_ERR_ARG;
   switch (option) {
-    case PHYLO_OPT_FUSED_TREE: e->opt_fused = value != 0; return PHYLO_OK;
+    case PHYLO_OPT_FUSED_TREE: e->opt_fused = (value == 2) ? 2 : (value != 0); return PHYLO_OK;
     case PHYLO_OPT_RETAIN_CLV: e->opt_retain = value != 0; return PHYLO_OK;
     default: return fail(e, PHYLO_ERR_ARG, "set_option: unknown option %d", option);
   }
@@ -906,6 +929,78 @@ static cudaError_t launch_tree_k(phylo_engine *e, const TreeArgs &a, size_t smem
   }
 }
 
+// ---- warp-autonomous tree kernel (lk_treew_kernel.cuh): geometry and launch
+struct TreeWGeom {
+  int warps = 0;     // warps per CTA
+  size_t smem = 0;   // dynamic shared memory per CTA
+};
+static TreeWGeom treew_geometry(const phylo_engine *e, int depth, int n_steps, bool retain) {
+  TreeWGeom g;
+  const size_t kMaxSmem = 227 * 1024, fixed = treew_prog_bytes(n_steps) + 1024;  // +1024: manual alignment
+  const size_t wb = treew_warp_bytes(e->K, e->T, depth, retain);
+  if (fixed + wb > kMaxSmem) return g;
+  int w = (int)std::min<size_t>(kTreeWMaxWarps, (kMaxSmem - fixed) / wb);
+  // few groups (small alignments): spread them over the SMs instead of filling CTAs
+  const int64_t ngroups = (e->N + 31) / 32;
+  w = (int)std::max<int64_t>(1, std::min<int64_t>(w, (ngroups + e->sm_count - 1) / e->sm_count));
+  g.warps = w;
+  g.smem = fixed + (size_t)w * wb;
+  return g;
+}
+
+template <int K>
+static cudaError_t launch_treew(phylo_engine *e, TreeArgs args, const TreeWGeom &geo, bool retain, int64_t g_begin,
+                                int64_t g_end, cudaStream_t cs) {
+  args.tile_begin = g_begin;
+  args.tile_end = g_end;
+  const int64_t ctas = (g_end - g_begin + geo.warps - 1) / geo.warps;
+  const int g = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, e->sm_count));
+  cudaError_t st;
+  if (retain) {
+    auto kern = lk_treew_kernel<K, true>;
+    if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem)) != cudaSuccess) return st;
+    kern<<<g, geo.warps * 32, geo.smem, cs>>>(args);
+  } else {
+    auto kern = lk_treew_kernel<K, false>;
+    if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem)) != cudaSuccess) return st;
+    kern<<<g, geo.warps * 32, geo.smem, cs>>>(args);
+  }
+  ++e->launches;
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_treew_k(phylo_engine *e, const TreeArgs &a, const TreeWGeom &geo, int64_t g_begin, int64_t g_end,
+                                  cudaStream_t cs) {
+  switch (e->K) {
+    case 1: return launch_treew<1>(e, a, geo, e->opt_retain, g_begin, g_end, cs);
+    case 2: return launch_treew<2>(e, a, geo, e->opt_retain, g_begin, g_end, cs);
+    default: return launch_treew<4>(e, a, geo, e->opt_retain, g_begin, g_end, cs);
+  }
+}
+
+// (re)builds the TMA tensor maps of all allocated node CLVs: [N rows][4K doubles], box =
+// 32 rows, swizzle = row bytes (128/64/32)
+static int lk_build_tmaps(phylo_engine *e) {
+  std::vector<CUtensorMap> h(e->cap);
+  std::memset(h.data(), 0, sizeof(CUtensorMap) * e->cap);
+  const CUtensorMapSwizzle swz = e->K == 4 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                           : (e->K == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  for (int s = 0; s < e->cap; ++s) {
+    if (!e->nodes[s].clv) continue;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(4 * e->K), (cuuint64_t)e->N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(32 * e->K)};
+    const cuuint32_t box[2] = {(cuuint32_t)(4 * e->K), 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = e->encodeTiled(&h[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, e->nodes[s].clv, gdim, gstride, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, PHYLO_ERR_CUDA, "cuTensorMapEncodeTiled failed for node slot %d (CUresult %d)", s, (int)r);
+  }
+  CK(cudaMemcpy(e->dTmaps, h.data(), sizeof(CUtensorMap) * e->cap, cudaMemcpyHostToDevice));
+  e->tmapDirty = false;
+  return PHYLO_OK;
+}
+
 // returns PHYLO_OK with *done = true when the fused kernel handled the evaluation
 // host_masks != NULL: the alignment is still on the host; it is uploaded in slabs on a second
 // stream while earlier slabs are already being scored (phylo_lk_score_alignment)
@@ -917,7 +1012,13 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   FusedPlan pl;
   if (!build_fused_plan(e->cap, e->T, ops, n_ops, ra, rb, rt, pl)) return PHYLO_OK;
   const size_t kMaxSmem = 227 * 1024;
-  const size_t smem = tree_smem_bytes(e->K, e->T, pl.depth, (int)pl.steps.size());
+  // warp-autonomous kernel (thread = pattern) for K <= 4; the tile kernel (thread = pattern x
+  // rate class) for K = 8, or when a warp's working set does not fit
+  TreeWGeom geo;
+  if (e->opt_fused == 1 && e->K <= 4 && e->encodeTiled)
+    geo = treew_geometry(e, pl.depth, (int)pl.steps.size(), e->opt_retain);
+  const bool useW = geo.warps > 0;
+  const size_t smem = useW ? geo.smem : tree_smem_bytes(e->K, e->T, pl.depth, (int)pl.steps.size());
   if (smem > kMaxSmem) return PHYLO_OK;  // very deep / very wide trees: per-node kernels instead
   int rc;
   const int nb = 2 * n_ops + 1;
@@ -944,6 +1045,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     CK(cudaMemcpy(e->dNodeSc, hs.data(), sizeof(int32_t *) * e->cap, cudaMemcpyHostToDevice));
     e->nodeTabDirty = false;
   }
+  if (useW && e->opt_retain && e->tmapDirty && (rc = lk_build_tmaps(e)) != PHYLO_OK) return rc;
   {
     TreeInstr *hp = (TreeInstr *)e->hProg;
     for (size_t i = 0; i < pl.steps.size(); ++i) {
@@ -953,7 +1055,9 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
       in.lidx = st.lidx;
       in.ridx = st.ridx;
       in.out_slot = st.out_slot;
-      in.out_clv = (e->opt_retain && st.out_slot >= 0) ? e->nodes[st.out_slot].clv : nullptr;
+      in.out_clv = (e->opt_retain && st.out_slot >= 0)
+                       ? (useW ? reinterpret_cast<double *>(e->dTmaps + st.out_slot) : e->nodes[st.out_slot].clv)
+                       : nullptr;
       in.out_sc = (e->opt_retain && st.out_slot >= 0) ? e->nodes[st.out_slot].scale : nullptr;
       hp[i] = in;
       if (i + 1 < pl.steps.size()) { e->hT[2 * i] = st.t_left; e->hT[2 * i + 1] = st.t_right; }
@@ -961,7 +1065,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     }
   }
   CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
-  if ((rc = build_pt(e, nb, 1)) != PHYLO_OK) return rc;
+  if ((rc = build_pt(e, nb, useW ? 0 : 1)) != PHYLO_OK) return rc;
   TreeArgs a;
   a.prog = (const TreeInstr *)e->dProg;
   a.n_instr = n_ops;
@@ -980,10 +1084,10 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   a.site_lnl = e->dSite;
   a.groups = e->dGroups;
   a.stack_depth = pl.depth;
-  const int64_t tile = (int64_t)kTreeR * kTreeThreads / e->K, ntiles = (e->N + tile - 1) / tile;
+  const int64_t tile = useW ? 32 : (int64_t)kTreeR * kTreeThreads / e->K, ntiles = (e->N + tile - 1) / tile;
   if (!host_masks) {
     ProfScope prof(e, KC_TREE_FUSED);
-    cudaError_t st = launch_tree_k(e, a, smem, 0, ntiles, e->stream);
+    cudaError_t st = useW ? launch_treew_k(e, a, geo, 0, ntiles, e->stream) : launch_tree_k(e, a, smem, 0, ntiles, e->stream);
     if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch: %s", cudaGetErrorString(st));
   } else {
     // slabs of whole 1024-pattern blocks: >= ~2 waves of tiles each, at most 16 slabs
@@ -1010,7 +1114,8 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
       const int64_t p_lo = b_lo * kLnlBlock, p_hi = std::min<int64_t>(e->N, b_hi * kLnlBlock);
       if ((rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, e->copyStream, e->slabEvents[sidx], cs)) != PHYLO_OK)
         return rc;
-      cudaError_t st = launch_tree_k(e, a, smem, p_lo / tile, (p_hi + tile - 1) / tile, cs);
+      cudaError_t st = useW ? launch_treew_k(e, a, geo, p_lo / tile, (p_hi + tile - 1) / tile, cs)
+                            : launch_tree_k(e, a, smem, p_lo / tile, (p_hi + tile - 1) / tile, cs);
       if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch: %s", cudaGetErrorString(st));
     }
     CK(cudaEventRecord(e->auxDone, e->auxStream));

@@ -691,17 +691,20 @@ tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, int64_t 
 }
 
 // Two 4-bit masks per byte (even pattern in the low nibble) for the tree-fused kernel's tip
-// tiles; cells beyond N read as "all states". Bytes [b_lo, b_hi) of every row.
+// tiles; cells beyond N read as "all states". Bytes [b_lo, b_hi) of every row. Output is
+// group-major: [group of 32 patterns][T][16 bytes], so the tips a warp/tile needs are one
+// contiguous run (a single bulk-TMA copy).
 __global__ void __launch_bounds__(256)
 tips_pack4_kernel(const uint8_t *__restrict__ tips, uint8_t *__restrict__ tips4, int T, int64_t N,
                   int64_t stride, int64_t b_lo, int64_t b_hi) {
-  const int64_t half = stride / 2, span = b_hi - b_lo, total = (int64_t)T * span;
+  // b_lo, b_hi are multiples of 16 (whole groups); thread i writes output byte i of the slab
+  const int64_t g_lo = b_lo >> 4, total = (b_hi - b_lo) * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = i / span, b = b_lo + (i - t * span), p = 2 * b;
+    const int64_t gt = i >> 4, g = g_lo + gt / T, t = gt % T, p = 2 * ((g << 4) + (i & 15));
     const int lo = p < N ? (tips[t * stride + p] & 15) : 15;
     const int hi = p + 1 < N ? (tips[t * stride + p + 1] & 15) : 15;
-    tips4[t * half + b] = (uint8_t)(lo | (hi << 4));
+    tips4[(g_lo << 4) * T + i] = (uint8_t)(lo | (hi << 4));
   }
 }
 

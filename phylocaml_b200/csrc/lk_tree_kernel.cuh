@@ -88,7 +88,7 @@ struct TreeArgs {
   const TreeInstr *prog;   // n_instr steps + 1 root step
   int n_instr;
   const double *P;         // [2*n_instr + 1][16*K] k-interleaved
-  const uint8_t *tips4;    // [T][tip_stride/2]: two 4-bit masks per byte (even pattern = low nibble)
+  const uint8_t *tips4;    // [tip_stride/32][T][16]: groups of 32 patterns, two 4-bit masks per byte (even pattern = low nibble)
   int64_t tip_stride;      // patterns per row (multiple of 1024)
   int T;
   int64_t N;
@@ -151,17 +151,15 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
   d4 *mystack = stack + tid;
   int *mystack_sc = stack_sc + tid;
   // nibble of pattern (pl + r*HALF) inside a tip row of the tile
-  const int tb_off0 = pl >> 1, tb_off1 = (pl + HALF) >> 1, tb_sh = (pl & 1) * 4;  // HALF is even
+  // (tips are group-major: [group of 32 patterns][T rows][16 bytes])
+  const int tb_off0 = (pl >> 5) * a.T * 16 + ((pl & 31) >> 1);
+  const int tb_off1 = ((pl + HALF) >> 5) * a.T * 16 + (((pl + HALF) & 31) >> 1), tb_sh = (pl & 1) * 4;  // HALF is even
 
-  auto issue_tips = [&](int64_t p0) {  // warp 0 stages the tip rows of one tile (bulk-TMA)
-    if (tid < 32) {
-      if (tid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(&tipbar[0], (uint32_t)tipbuf_bytes);
-      }
-      __syncwarp();
-      for (int t = tid; t < a.T; t += 32)
-        bulk_g2s(tipbuf + (size_t)t * TROW, a.tips4 + ((size_t)t * a.tip_stride + p0) / 2, TROW, &tipbar[0]);
+  auto issue_tips = [&](int64_t p0) {  // one bulk-TMA copy stages the tip rows of a tile
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&tipbar[0], (uint32_t)tipbuf_bytes);
+      bulk_g2s(tipbuf, a.tips4 + (size_t)(p0 / 32) * a.T * 16, (uint32_t)tipbuf_bytes, &tipbar[0]);
     }
   };
   // canonical level 0 for a finished tile: each group of 32 consecutive patterns is folded
@@ -210,8 +208,8 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
       int mlb0, mlb1, mrb0, mrb1;  // raw tip bytes of (left,right) x (r=0,1)
       {
         const int lrow = ((iw.x & 3) == OPK_TIP) ? iw.y : 0, rrow = (((iw.x >> 2) & 3) == OPK_TIP) ? iw.z : 0;
-        mlb0 = tb[lrow * TROW + tb_off0]; mlb1 = tb[lrow * TROW + tb_off1];
-        mrb0 = tb[rrow * TROW + tb_off0]; mrb1 = tb[rrow * TROW + tb_off1];
+        mlb0 = tb[lrow * 16 + tb_off0]; mlb1 = tb[lrow * 16 + tb_off1];
+        mrb0 = tb[rrow * 16 + tb_off0]; mrb1 = tb[rrow * 16 + tb_off1];
       }
       // rolling half-matrix pipeline over the warp's shared-memory slots: slot (step & 1)
       // holds this step's two matrix sets; the copy of the next step's is issued first
@@ -293,8 +291,8 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
         // next step's tip bytes (its word has landed by now); consumed one iteration later
         {
           const int lrow = ((nw.x & 3) == OPK_TIP) ? nw.y : 0, rrow = (((nw.x >> 2) & 3) == OPK_TIP) ? nw.z : 0;
-          mlb0 = tb[lrow * TROW + tb_off0]; mlb1 = tb[lrow * TROW + tb_off1];
-          mrb0 = tb[rrow * TROW + tb_off0]; mrb1 = tb[rrow * TROW + tb_off1];
+          mlb0 = tb[lrow * 16 + tb_off0]; mlb1 = tb[lrow * 16 + tb_off1];
+          mrb0 = tb[rrow * 16 + tb_off0]; mrb1 = tb[rrow * 16 + tb_off1];
         }
         iw = nw;
         // ---- y = P_r * rv and the products; freed halves are refilled with the NEXT step's

@@ -360,13 +360,20 @@ def test_fused_tree_equals_per_node_path_bitwise(eng, oracle, T, N, kind):
         site_b = eng.lk_get_site_lnl()
         clv_b = [eng.lk_get_clv(int(op["parent"])) for op in ops[-3:]]
         c, fc = _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=0)
+        site_c = eng.lk_get_site_lnl()
+        # fused=2: the tile kernel (thread = pattern x rate class) instead of the warp-autonomous one
+        d, fd = _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused=2, retain=1)
+        site_d = eng.lk_get_site_lnl()
+        clv_d = [eng.lk_get_clv(int(op["parent"])) for op in ops[-3:]]
+        f, ff = _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused=2, retain=0)
     finally:
         eng.profile(False)
-    assert fa and fc and not fb
-    assert a == b == c
-    assert np.array_equal(site_a, site_b)
-    for (ca, sa), (cb, sb) in zip(clv_a, clv_b):
+    assert fa and fc and fd and ff and not fb
+    assert a == b == c == d == f
+    assert np.array_equal(site_a, site_b) and np.array_equal(site_a, site_c) and np.array_equal(site_a, site_d)
+    for (ca, sa), (cb, sb), (cd, sd) in zip(clv_a, clv_b, clv_d):
         assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
+        assert np.array_equal(ca, cd) and np.array_equal(sa, sd)
     want = oracle.lk_score_tree(model, tips, None, ops, n_nodes, ra, rb, rt)["lnl"]
     assert rel_err(a, want) <= LNL_RTOL
 
@@ -379,10 +386,15 @@ def test_fused_tree_other_rate_counts(eng, oracle, K):
     eng.profile(True)
     try:
         a, fa = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=1)
+        clv_a = [eng.lk_get_clv(int(op["parent"])) for op in ops]
         b, fb = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=0, retain=1)
+        clv_b = [eng.lk_get_clv(int(op["parent"])) for op in ops]
+        c, fc = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=2, retain=1)
     finally:
         eng.profile(False)
-    assert fa and not fb and a == b
+    assert fa and fc and not fb and a == b == c
+    for (ca, sa), (cb, sb) in zip(clv_a, clv_b):
+        assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
     assert rel_err(a, oracle.lk_score_tree(m, tips, None, ops, n_nodes, ra, rb, rt)["lnl"]) <= LNL_RTOL
 
 
