@@ -10,10 +10,10 @@
 // LSU work per update, no shuffles (the K rate classes of a pattern sit in one thread, so
 // the rescale test and the root mixture are plain register code).
 //
-//   * a warp is a self-contained worker: own tip buffers (bulk-TMA, double buffered, one
-//     contiguous T*16-byte copy per group thanks to the group-major tip layout), own
-//     mbarriers, own matrix ring (cp.async, one step ahead), own CLV stack, own store
-//     staging. There is NO CTA-wide barrier after the prologue;
+//   * a warp is a self-contained worker: own tip buffer (bulk-TMA, one contiguous T*16-byte
+//     copy per group thanks to the group-major tip layout, requested as soon as the previous
+//     group's last tip byte is in registers), own mbarrier, own matrix ring (cp.async, two
+//     steps ahead), own CLV stack, own store staging. There is NO CTA-wide barrier after the prologue;
 //   * retained CLVs leave through TMA tensor stores: each lane writes its pattern's K*32
 //     bytes into the warp's staging tile with the 128/64/32-byte swizzle (conflict-free
 //     STS.128), one lane issues cp.async.bulk.tensor.2d (un-swizzles, clips rows >= N). The
@@ -29,16 +29,17 @@
 
 namespace phylo {
 
-constexpr int kTreeWMaxWarps = 8;
+constexpr int kTreeWMaxWarps = 9;   // 9 warps x 224 registers fill the register file
+constexpr int kTreeWSlots = 3;      // matrix ring: the copy runs two steps ahead
 
 // bytes of shared memory one warp needs (multiple of 1024 so staging tiles stay 1024-aligned)
 __host__ __device__ inline size_t treew_warp_bytes(int K, int T, int depth, bool retain) {
   size_t b = retain ? (size_t)32 * 32 * K : 0;       // store staging tile (swizzled)
-  b += 2 * (size_t)T * 16;                            // tip buffers
-  b += 2 * 2 * (size_t)K * 128;                       // matrix ring: 2 slots x 2 sides
+  b += (size_t)T * 16;                                // tip buffer
+  b += kTreeWSlots * 2 * (size_t)K * 128;             // matrix ring: slots x 2 sides
   b += (size_t)depth * 2 * K * 32 * 16;               // CLV stack
   b += (size_t)depth * 32 * 4;                        // scale-counter stack
-  b += 64;                                            // 2 mbarriers (+pad)
+  b += 64;                                            // mbarrier (+pad)
   return (b + 1023) & ~(size_t)1023;
 }
 __host__ __device__ inline size_t treew_prog_bytes(int n_steps) {
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
   const size_t wbytes = treew_warp_bytes(K, a.T, a.stack_depth, RETAIN);
   unsigned char *wb = base + treew_prog_bytes(n_steps) + (size_t)warp * wbytes;
   unsigned char *ostage = wb;                                           // [32 rows][32K bytes], swizzled
-  uint8_t *tipbuf = wb + (RETAIN ? 32 * 32 * K : 0);                    // [2][T*16]
+  uint8_t *tipbuf = wb + (RETAIN ? 32 * 32 * K : 0);                    // [T*16]
   const uint32_t tip_bytes = (uint32_t)a.T * 16;
-  double2 *ring = reinterpret_cast<double2 *>(tipbuf + 2 * (size_t)tip_bytes);  // [2][2][K][8]
-  double2 *stack = ring + 2 * 2 * K * 8;                                // [depth][CH][32]
+  double2 *ring = reinterpret_cast<double2 *>(tipbuf + (size_t)tip_bytes);  // [slots][2][K][8]
+  double2 *stack = ring + kTreeWSlots * 2 * K * 8;                      // [depth][CH][32]
   int *stack_sc = reinterpret_cast<int *>(stack + (size_t)a.stack_depth * CH * 32);  // [depth][32]
   uint64_t *bar = reinterpret_cast<uint64_t *>(stack_sc + (size_t)a.stack_depth * 32);
 
@@ -89,7 +90,6 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
   if (threadIdx.x < 2) sprog[2 * n_steps + threadIdx.x] = make_int4(0, 0, 0, 0);  // harmless word past the end
   if (lane == 0) {
     mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
     fence_mbar_init();
   }
   __syncthreads();  // the only CTA-wide barrier
@@ -108,35 +108,37 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
 #pragma unroll
   for (int k = 0; k < K; ++k) prob[k] = a.probs[k];
 
-  auto issue_tips = [&](int64_t g, int buf) {
+  auto issue_tips = [&](int64_t g) {
     if (lane == 0) {
       fence_proxy_async();
-      mbar_expect_tx(&bar[buf], tip_bytes);
-      bulk_g2s(tipbuf + (size_t)buf * tip_bytes, a.tips4 + (size_t)g * tip_bytes, tip_bytes, &bar[buf]);
+      mbar_expect_tx(&bar[0], tip_bytes);
+      bulk_g2s(tipbuf, a.tips4 + (size_t)g * tip_bytes, tip_bytes, &bar[0]);
     }
   };
-  // both matrix sets of `step` (contiguous in a.P, [side][k][4][4]) -> ring slot
-  auto fetch_matrices = [&](int step, int slot) {
-    const double2 *src = reinterpret_cast<const double2 *>(a.P) + (size_t)step * (2 * K * 8);
-    double2 *dst = ring + slot * (2 * K * 8);
+  // both matrix sets of `step` (contiguous in a.P, [side][k][4][4]) -> ring slot step % slots.
+  // Always commits a group (an empty one past the root step) so wait_group counts stay uniform.
+  auto fetch_matrices = [&](int step) {
+    if (step <= a.n_instr) {
+      const double2 *src = reinterpret_cast<const double2 *>(a.P) + (size_t)step * (2 * K * 8);
+      double2 *dst = ring + (step % kTreeWSlots) * (2 * K * 8);
 #pragma unroll
-    for (int c = lane; c < 2 * K * 8; c += 32) cp_async16(dst + c, src + c);
+      for (int c = lane; c < 2 * K * 8; c += 32) cp_async16(dst + c, src + c);
+    }
     cp_async_commit();
   };
   const int tb_byte = lane >> 1, tb_sh = (lane & 1) * 4;
   const int swz = (lane >> SWZ_SHIFT) & (CH - 1);
 
-  issue_tips(g_lo, 0);
+  issue_tips(g_lo);
   uint32_t seq = 0;
   for (int64_t g = g_lo; g < g_hi; ++g, ++seq) {
-    const int buf = seq & 1;
-    __syncwarp();  // every lane is done with the other tip buffer and with ring slot 0
-    if (g + 1 < g_hi) issue_tips(g + 1, buf ^ 1);
-    fetch_matrices(0, 0);
+    __syncwarp();  // every lane is done with the previous group's last ring slot
+    fetch_matrices(0);
+    fetch_matrices(1);
     const int64_t pat = g * 32 + lane;
     const bool active = pat < a.N;
-    mbar_wait(&bar[buf], (seq >> 1) & 1);
-    const uint8_t *tb = tipbuf + (size_t)buf * tip_bytes;
+    mbar_wait(&bar[0], seq & 1);
+    const uint8_t *tb = tipbuf;
 
     d4 cur[K];
 #pragma unroll
@@ -150,13 +152,16 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
       ml = tb[lrow * 16 + tb_byte];
       mr = tb[rrow * 16 + tb_byte];
     }
-    cp_async_wait<0>();
-    __syncwarp();
+    cp_async_wait<1>();  // step 0's matrices have landed
+    if (a.n_instr == 0) {  // two-taxon tree: the root's tip bytes are already in registers
+      __syncwarp();
+      if (g + 1 < g_hi) issue_tips(g + 1);
+    }
 
     for (int step = 0; step < a.n_instr; ++step) {
-      __syncwarp();  // all lanes have finished reading ring slot (step+1)&1
-      fetch_matrices(step + 1, (step + 1) & 1);  // the root's matrix after the last step
-      const double2 *pmL = ring + (step & 1) * (2 * K * 8), *pmR = pmL + K * 8;
+      __syncwarp();  // all lanes have finished step-1: its ring slot is free, this step's copies are visible
+      fetch_matrices(step + 2);  // two steps ahead (the root's matrix counts as step n_instr)
+      const double2 *pmL = ring + (step % kTreeWSlots) * (2 * K * 8), *pmR = pmL + K * 8;
       const int lkind = iw.x & 3, rkind = (iw.x >> 2) & 3, push = iw.x & 16, lidx = iw.y, ridx = iw.z;
       const int4 ow = RETAIN ? sprog[2 * step + 1] : make_int4(0, 0, 0, 0);  // tensor map, out_sc
       const int4 nw = sprog[2 * step + 2];                                   // next step's word
@@ -175,9 +180,21 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
       int sc = 0;
       auto side = [&](int kind, int idx, int mbyte, const double2 *pm, double (&o)[K][4]) {
         if (kind == OPK_TIP) {
-          const d4 t = mask_vec(mbyte >> tb_sh);
+          const int m = (mbyte >> tb_sh) & 15;
+          if (__all_sync(0xffffffffu, (m & (m - 1)) == 0)) {
+            // every lane's tip is a single state j: P L is column j of P, read directly (4 distinct
+            // words of one 32-byte row per request: one wavefront, no arithmetic). 0/1 products and
+            // additions of +0 are exact, so this is the general expression bit for bit.
+            const double *col = reinterpret_cast<const double *>(pm) + (__ffs(m) - 1);
 #pragma unroll
-          for (int k = 0; k < K; ++k) matvec_u(pm + k * 8, t, o[k]);
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[k][i] = col[k * 16 + i * 4];
+          } else {
+            const d4 t = mask_vec(m);
+#pragma unroll
+            for (int k = 0; k < K; ++k) matvec_u(pm + k * 8, t, o[k]);
+          }
         } else if (kind == OPK_CUR) {
 #pragma unroll
           for (int k = 0; k < K; ++k) matvec_u(pm + k * 8, cur[k], o[k]);
@@ -212,6 +229,10 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
         mr = tb[rrow * 16 + tb_byte];
       }
       iw = nw;
+      if (step + 1 == a.n_instr) {  // the root's tip bytes are in registers: the tip buffer is free
+        __syncwarp();
+        if (g + 1 < g_hi) issue_tips(g + 1);  // lands while the last step and the root join run
+      }
       if (h < kScaleHiThresh) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -241,12 +262,12 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
           if (active) os[pat] = sc;
         }
       }
-      cp_async_wait<0>();  // next step's matrices have landed (visible after the __syncwarp)
+      cp_async_wait<1>();  // next step's matrices have landed (visible after the __syncwarp)
     }
     __syncwarp();
     // ---- root-edge join (root4_kernel's arithmetic): P applies to the b side only
     {
-      const double2 *pm = ring + (a.n_instr & 1) * (2 * K * 8);
+      const double2 *pm = ring + (a.n_instr % kTreeWSlots) * (2 * K * 8);
       const int akind = iw.x & 3, bkind = (iw.x >> 2) & 3;
       int c = 0;
       double l = 0.0, lk[K];
