@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,6 +70,8 @@ struct phylo_engine {
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeTiledFn encodeTiled = nullptr;
   CUtensorMap *dTmaps = nullptr;  // [cap]
+  void *dSpill = nullptr;         // deep stack levels of the warp-autonomous tree kernel
+  size_t capSpill = 0;
   bool tmapDirty = true;
   int64_t tipStride = 0;  // elements per tip row (N rounded up to 1024)
   double **dNodeClv = nullptr;   // device tables of node buffers (tree-fused kernel)
@@ -273,7 +276,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad);
+  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -933,11 +936,24 @@ static cudaError_t launch_tree_k(phylo_engine *e, const TreeArgs &a, size_t smem
 struct TreeWGeom {
   int warps = 0;     // warps per CTA
   size_t smem = 0;   // dynamic shared memory per CTA
+  int slev = kTreeWSmemLevels, obufs = 1, interleave = 1;
 };
+// experiment knob: PHYLO_TREEW_TUNE="slev,obufs,interleave" (defaults are the measured best)
+static void treew_tune(TreeWGeom &g) {
+  const char *t = getenv("PHYLO_TREEW_TUNE");
+  if (!t) return;
+  int a = g.slev, b = g.obufs, c = g.interleave;
+  if (sscanf(t, "%d,%d,%d", &a, &b, &c) >= 1) {
+    g.slev = std::max(1, a);
+    g.obufs = (b == 1) ? 1 : 2;
+    g.interleave = c != 0;
+  }
+}
 static TreeWGeom treew_geometry(const phylo_engine *e, int depth, int n_steps, bool retain) {
   TreeWGeom g;
+  treew_tune(g);
   const size_t kMaxSmem = 227 * 1024, fixed = treew_prog_bytes(n_steps) + 1024;  // +1024: manual alignment
-  const size_t wb = treew_warp_bytes(e->K, e->T, depth, retain);
+  const size_t wb = treew_warp_bytes(e->K, e->T, depth, retain, g.slev, g.obufs);
   if (fixed + wb > kMaxSmem) return g;
   int w = (int)std::min<size_t>(kTreeWMaxWarps, (kMaxSmem - fixed) / wb);
   // few groups (small alignments): spread them over the SMs instead of filling CTAs
@@ -1084,6 +1100,22 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   a.site_lnl = e->dSite;
   a.groups = e->dGroups;
   a.stack_depth = pl.depth;
+  a.spill = nullptr;
+  if (useW) {
+    // two regions: consecutive slabs of phylo_lk_score_alignment run on two streams
+    const size_t region = treew_spill_bytes(e->K, pl.depth, geo.slev) * kTreeWMaxWarps * (size_t)e->sm_count, need = 2 * region;
+    a.smem_levels = geo.slev;
+    a.obufs = geo.obufs;
+    a.interleave = geo.interleave;
+    if (need > e->capSpill) {
+      CK(cudaStreamSynchronize(e->stream));
+      dfree(e->dSpill);
+      e->capSpill = 0;
+      CK(cudaMalloc(&e->dSpill, need));
+      e->capSpill = need;
+    }
+    a.spill = (double2 *)e->dSpill;
+  }
   const int64_t tile = useW ? 32 : (int64_t)kTreeR * kTreeThreads / e->K, ntiles = (e->N + tile - 1) / tile;
   if (!host_masks) {
     ProfScope prof(e, KC_TREE_FUSED);
@@ -1114,6 +1146,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
       const int64_t p_lo = b_lo * kLnlBlock, p_hi = std::min<int64_t>(e->N, b_hi * kLnlBlock);
       if ((rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, e->copyStream, e->slabEvents[sidx], cs)) != PHYLO_OK)
         return rc;
+      if (useW) a.spill = (double2 *)((char *)e->dSpill + (size_t)(sidx & 1) * (e->capSpill / 2));
       cudaError_t st = useW ? launch_treew_k(e, a, geo, p_lo / tile, (p_hi + tile - 1) / tile, cs)
                             : launch_tree_k(e, a, smem, p_lo / tile, (p_hi + tile - 1) / tile, cs);
       if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch: %s", cudaGetErrorString(st));

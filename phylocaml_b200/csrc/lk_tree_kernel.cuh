@@ -101,6 +101,8 @@ struct TreeArgs {
   double *site_lnl;
   double *groups;          // [ceil(N/32)] sums of 32 consecutive weighted site lnL (canonical level 0)
   int stack_depth;
+  double2 *spill;          // warp-autonomous kernel: global scratch for deep stack levels
+  int smem_levels, obufs, interleave;  // warp-autonomous kernel: stack levels in smem, staging tiles (1|2), group order
   int64_t tile_begin, tile_end;  // tiles this launch covers (a slab of the alignment)
 };
 

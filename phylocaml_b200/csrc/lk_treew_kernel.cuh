@@ -19,7 +19,9 @@
 //     STS.128), one lane issues cp.async.bulk.tensor.2d (un-swizzles, clips rows >= N). The
 //     LSU sees 1 wavefront per 128 bytes stored; an ordinary st.global at a 128-byte lane
 //     stride would cost one per 32 bytes and split every line over 4 instructions;
-//   * CLV stack in shared memory as 16-byte chunks [level][chunk][lane] (conflict-free).
+//   * CLV stack in shared memory as 16-byte chunks [level][chunk][lane] (conflict-free); only
+//     the first two levels -- deeper ones are rare (a tree needs level l about 4^-l as often)
+//     and live in a small L2-resident global scratch, which buys a ninth warp per SM;
 //
 // Arithmetic and its order are those of prune4_kernel / root4_kernel / lk_tree4_kernel
 // (same expressions => same bits): x_i = ((P_i0 v_0 + P_i1 v_1) + P_i2 v_2) + P_i3 v_3, the
@@ -29,18 +31,24 @@
 
 namespace phylo {
 
-constexpr int kTreeWMaxWarps = 9;   // 9 warps x 224 registers fill the register file
+constexpr int kTreeWMaxWarps = 12;  // 12 warps x 168 registers fill the register file
 constexpr int kTreeWSlots = 3;      // matrix ring: the copy runs two steps ahead
+constexpr int kTreeWSmemLevels = 2; // CLV stack levels kept in shared memory; deeper (rare) ones go to an L2-resident scratch
 
 // bytes of shared memory one warp needs (multiple of 1024 so staging tiles stay 1024-aligned)
-__host__ __device__ inline size_t treew_warp_bytes(int K, int T, int depth, bool retain) {
-  size_t b = retain ? (size_t)32 * 32 * K : 0;       // store staging tile (swizzled)
+__host__ __device__ inline size_t treew_warp_bytes(int K, int T, int depth, bool retain, int slev, int obufs) {
+  if (depth > slev) depth = slev;
+  size_t b = retain ? (size_t)obufs * 32 * 32 * K : 0;  // store staging tiles (swizzled)
   b += (size_t)T * 16;                                // tip buffer
   b += kTreeWSlots * 2 * (size_t)K * 128;             // matrix ring: slots x 2 sides
   b += (size_t)depth * 2 * K * 32 * 16;               // CLV stack
   b += (size_t)depth * 32 * 4;                        // scale-counter stack
   b += 64;                                            // mbarrier (+pad)
   return (b + 1023) & ~(size_t)1023;
+}
+// bytes of global scratch one warp needs for the stack levels beyond kTreeWSmemLevels
+__host__ __device__ inline size_t treew_spill_bytes(int K, int depth, int slev) {
+  return depth > slev ? (size_t)(depth - slev) * (2 * K * 32 * 16 + 128) : 0;
 }
 __host__ __device__ inline size_t treew_prog_bytes(int n_steps) {
   return (((size_t)(n_steps + 1) * sizeof(TreeInstr)) + 1023) & ~(size_t)1023;
@@ -53,6 +61,7 @@ __device__ __forceinline__ void tma_store_2d(const void *tmap, const void *smem,
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // x = P v for one rate class; pm = 8 double2 (row-major 4x4), warp-uniform address
@@ -76,15 +85,19 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int n_steps = a.n_instr + 1;  // + root step
   int4 *sprog = reinterpret_cast<int4 *>(base);
-  const size_t wbytes = treew_warp_bytes(K, a.T, a.stack_depth, RETAIN);
+  const size_t wbytes = treew_warp_bytes(K, a.T, a.stack_depth, RETAIN, a.smem_levels, a.obufs);
   unsigned char *wb = base + treew_prog_bytes(n_steps) + (size_t)warp * wbytes;
-  unsigned char *ostage = wb;                                           // [32 rows][32K bytes], swizzled
-  uint8_t *tipbuf = wb + (RETAIN ? 32 * 32 * K : 0);                    // [T*16]
+  unsigned char *ostage = wb;                                           // [2][32 rows][32K bytes], swizzled
+  uint8_t *tipbuf = wb + (RETAIN ? a.obufs * 32 * 32 * K : 0);          // [T*16]
   const uint32_t tip_bytes = (uint32_t)a.T * 16;
   double2 *ring = reinterpret_cast<double2 *>(tipbuf + (size_t)tip_bytes);  // [slots][2][K][8]
-  double2 *stack = ring + kTreeWSlots * 2 * K * 8;                      // [depth][CH][32]
-  int *stack_sc = reinterpret_cast<int *>(stack + (size_t)a.stack_depth * CH * 32);  // [depth][32]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(stack_sc + (size_t)a.stack_depth * 32);
+  const int slev = min(a.stack_depth, a.smem_levels);
+  double2 *stack = ring + kTreeWSlots * 2 * K * 8;                      // [slev][CH][32]
+  int *stack_sc = reinterpret_cast<int *>(stack + (size_t)slev * CH * 32);  // [slev][32]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(stack_sc + (size_t)slev * 32);
+  // levels >= slev: this warp's slice of the global scratch, per level [CH][32] chunks + [32] counters
+  constexpr int SPILL_LEVEL = CH * 32 + 8;  // in double2 units
+  double2 *spill = a.spill + ((size_t)blockIdx.x * kTreeWMaxWarps + warp) * (treew_spill_bytes(K, a.stack_depth, a.smem_levels) / 16);
 
   for (int i = threadIdx.x; i < 2 * n_steps; i += blockDim.x) sprog[i] = __ldg(reinterpret_cast<const int4 *>(a.prog) + i);
   if (threadIdx.x < 2) sprog[2 * n_steps + threadIdx.x] = make_int4(0, 0, 0, 0);  // harmless word past the end
@@ -94,12 +107,24 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
   }
   __syncthreads();  // the only CTA-wide barrier
 
-  // this warp's contiguous run of 32-pattern groups
+  // the CTA owns a contiguous run of 32-pattern groups; its warps take them round-robin, so at
+  // any time the CTA's stores go to neighbouring 4K-byte pieces of a node array
   const int64_t ngroups = (a.N + 31) / 32;
   const int64_t g_end = min(ngroups, a.tile_end);
-  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, nw_total = (int64_t)gridDim.x * nwarps;
-  const int64_t per = (g_end - a.tile_begin + nw_total - 1) / nw_total;
-  const int64_t g_lo = a.tile_begin + gw * per, g_hi = min(g_end, g_lo + per);
+  int64_t g_lo, g_hi;
+  int g_step;
+  if (a.interleave) {
+    const int64_t per = (g_end - a.tile_begin + gridDim.x - 1) / gridDim.x;
+    g_lo = a.tile_begin + (int64_t)blockIdx.x * per + warp;
+    g_hi = min(g_end, a.tile_begin + ((int64_t)blockIdx.x + 1) * per);
+    g_step = nwarps;
+  } else {
+    const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, nw_total = (int64_t)gridDim.x * nwarps;
+    const int64_t per = (g_end - a.tile_begin + nw_total - 1) / nw_total;
+    g_lo = a.tile_begin + gw * per;
+    g_hi = min(g_end, g_lo + per);
+    g_step = 1;
+  }
   if (g_lo >= g_hi) return;
 
   double pi[4], prob[K];
@@ -131,7 +156,8 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
 
   issue_tips(g_lo);
   uint32_t seq = 0;
-  for (int64_t g = g_lo; g < g_hi; ++g, ++seq) {
+  uint32_t nstore = 0;  // retained tiles issued so far (staging buffer parity)
+  for (int64_t g = g_lo; g < g_hi; g += g_step, ++seq) {
     __syncwarp();  // every lane is done with the previous group's last ring slot
     fetch_matrices(0);
     fetch_matrices(1);
@@ -155,7 +181,7 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
     cp_async_wait<1>();  // step 0's matrices have landed
     if (a.n_instr == 0) {  // two-taxon tree: the root's tip bytes are already in registers
       __syncwarp();
-      if (g + 1 < g_hi) issue_tips(g + 1);
+      if (g + g_step < g_hi) issue_tips(g + g_step);
     }
 
     for (int step = 0; step < a.n_instr; ++step) {
@@ -166,12 +192,22 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
       const int4 ow = RETAIN ? sprog[2 * step + 1] : make_int4(0, 0, 0, 0);  // tensor map, out_sc
       const int4 nw = sprog[2 * step + 2];                                   // next step's word
       if (push) {
+        if (sp < slev) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          stack[(sp * CH + 2 * k) * 32 + lane] = make_double2(cur[k].x, cur[k].y);
-          stack[(sp * CH + 2 * k + 1) * 32 + lane] = make_double2(cur[k].z, cur[k].w);
+          for (int k = 0; k < K; ++k) {
+            stack[(sp * CH + 2 * k) * 32 + lane] = make_double2(cur[k].x, cur[k].y);
+            stack[(sp * CH + 2 * k + 1) * 32 + lane] = make_double2(cur[k].z, cur[k].w);
+          }
+          stack_sc[sp * 32 + lane] = cur_sc;
+        } else {
+          double2 *lv = spill + (size_t)(sp - slev) * SPILL_LEVEL;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            lv[(2 * k) * 32 + lane] = make_double2(cur[k].x, cur[k].y);
+            lv[(2 * k + 1) * 32 + lane] = make_double2(cur[k].z, cur[k].w);
+          }
+          reinterpret_cast<int *>(lv + CH * 32)[lane] = cur_sc;
         }
-        stack_sc[sp * 32 + lane] = cur_sc;
         ++sp;
       }
       // ---- x = P_l L_l, y = P_r L_r for every rate class. Each operand kind has its own
@@ -201,12 +237,22 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
           sc += cur_sc;
         } else if (kind == OPK_POP) {
           --sp;
+          if (sp < slev) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const double2 u = stack[(sp * CH + 2 * k) * 32 + lane], w = stack[(sp * CH + 2 * k + 1) * 32 + lane];
-            matvec_u(pm + k * 8, d4{u.x, u.y, w.x, w.y}, o[k]);
+            for (int k = 0; k < K; ++k) {
+              const double2 u = stack[(sp * CH + 2 * k) * 32 + lane], w = stack[(sp * CH + 2 * k + 1) * 32 + lane];
+              matvec_u(pm + k * 8, d4{u.x, u.y, w.x, w.y}, o[k]);
+            }
+            sc += stack_sc[sp * 32 + lane];
+          } else {
+            const double2 *lv = spill + (size_t)(sp - slev) * SPILL_LEVEL;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              const double2 u = lv[(2 * k) * 32 + lane], w = lv[(2 * k + 1) * 32 + lane];
+              matvec_u(pm + k * 8, d4{u.x, u.y, w.x, w.y}, o[k]);
+            }
+            sc += reinterpret_cast<const int *>(lv + CH * 32)[lane];
           }
-          sc += stack_sc[sp * 32 + lane];
         } else {
           const double *src = a.node_clv[idx] + pat * (4 * K);
 #pragma unroll
@@ -231,7 +277,7 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
       iw = nw;
       if (step + 1 == a.n_instr) {  // the root's tip bytes are in registers: the tip buffer is free
         __syncwarp();
-        if (g + 1 < g_hi) issue_tips(g + 1);  // lands while the last step and the root join run
+        if (g + g_step < g_hi) issue_tips(g + g_step);  // lands while the last step and the root join run
       }
       if (h < kScaleHiThresh) {
 #pragma unroll
@@ -245,9 +291,14 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
         const uint64_t tmap = ((uint64_t)(uint32_t)ow.y << 32) | (uint32_t)ow.x;
         if (tmap != 0) {
           int32_t *os = reinterpret_cast<int32_t *>(((uint64_t)(uint32_t)ow.w << 32) | (uint32_t)ow.z);
-          if (lane == 0) bulk_wait_read0();  // the previous tile has left the staging buffer
+          if (lane == 0) {  // the tile that used this staging buffer last has left it
+            if (a.obufs == 2) bulk_wait_read1();
+            else bulk_wait_read0();
+          }
           __syncwarp();
-          unsigned char *row = ostage + lane * (32 * K);
+          unsigned char *obuf = ostage + (nstore & (a.obufs - 1)) * (32 * 32 * K);
+          ++nstore;
+          unsigned char *row = obuf + lane * (32 * K);
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             *reinterpret_cast<double2 *>(row + (((2 * k) ^ swz) << 4)) = make_double2(cur[k].x, cur[k].y);
@@ -256,7 +307,7 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(reinterpret_cast<const void *>(tmap), ostage, 0, (int)(g * 32));
+            tma_store_2d(reinterpret_cast<const void *>(tmap), obuf, 0, (int)(g * 32));
             bulk_commit();
           }
           if (active) os[pat] = sc;
@@ -271,6 +322,9 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
       const int akind = iw.x & 3, bkind = (iw.x >> 2) & 3;
       int c = 0;
       double l = 0.0, lk[K];
+      // stack top (a POP operand of the root step), wherever it lives
+      const double2 *top = (sp - 1 < slev) ? stack + (size_t)max(sp - 1, 0) * CH * 32 : spill + (size_t)(sp - 1 - slev) * SPILL_LEVEL;
+      const int *top_sc = (sp - 1 < slev) ? stack_sc + max(sp - 1, 0) * 32 : reinterpret_cast<const int *>(spill + (size_t)(sp - 1 - slev) * SPILL_LEVEL + CH * 32);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         d4 av{0, 0, 0, 0}, bv{0, 0, 0, 0};
@@ -278,13 +332,13 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
         if (akind == OPK_TIP) av = mask_vec(ml >> tb_sh);
         else if (akind == OPK_CUR) av = cur[k];
         else if (akind == OPK_POP) {
-          const double2 u = stack[((sp - 1) * CH + 2 * k) * 32 + lane], w = stack[((sp - 1) * CH + 2 * k + 1) * 32 + lane];
+          const double2 u = top[(2 * k) * 32 + lane], w = top[(2 * k + 1) * 32 + lane];
           av = d4{u.x, u.y, w.x, w.y};
         } else if (active) av = ld256_stream(a.node_clv[iw.y] + pat * (4 * K) + 4 * k);
         if (bkind == OPK_TIP) bv = mask_vec(mr >> tb_sh);
         else if (bkind == OPK_CUR) bv = cur[k];
         else if (bkind == OPK_POP) {
-          const double2 u = stack[((sp - 1) * CH + 2 * k) * 32 + lane], w = stack[((sp - 1) * CH + 2 * k + 1) * 32 + lane];
+          const double2 u = top[(2 * k) * 32 + lane], w = top[(2 * k + 1) * 32 + lane];
           bv = d4{u.x, u.y, w.x, w.y};
         } else if (active) bv = ld256_stream(a.node_clv[iw.z] + pat * (4 * K) + 4 * k);
         double y[4];
@@ -292,10 +346,10 @@ __global__ void __launch_bounds__(kTreeWMaxWarps * 32, 1) lk_treew_kernel(const 
         lk[k] = prob[k] * ((((pi[0] * av.x) * y[0] + (pi[1] * av.y) * y[1]) + (pi[2] * av.z) * y[2]) + (pi[3] * av.w) * y[3]);
       }
       if (akind == OPK_CUR) c += cur_sc;
-      else if (akind == OPK_POP) c += stack_sc[(sp - 1) * 32 + lane];
+      else if (akind == OPK_POP) c += top_sc[lane];
       else if (akind == OPK_STORED && active) c += a.node_sc[iw.y][pat];
       if (bkind == OPK_CUR) c += cur_sc;
-      else if (bkind == OPK_POP) c += stack_sc[(sp - 1) * 32 + lane];
+      else if (bkind == OPK_POP) c += top_sc[lane];
       else if (bkind == OPK_STORED && active) c += a.node_sc[iw.z][pat];
       if (K == 1) l = lk[0];
       else if (K == 2) l = lk[0] + lk[1];
