@@ -243,6 +243,8 @@ def main():
                     help="likelihood path: tree-fused kernel keeping every CLV (default), tree-fused "
                          "lnL-only (no CLV written), or one streaming kernel per node")
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other modes")
+    ap.add_argument("--fitch-kernel", default="auto", choices=["auto", "tile", "regwalk", "l2"],
+                    help="whole-tree Fitch kernel (PHYLO_OPT_FITCH_WALK)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     wl = dict(WORKLOADS[args.workload])
@@ -292,6 +294,7 @@ def main():
         for a in range(0, n_local, base.shape[1]):
             b = min(n_local, a + base.shape[1])
             tips[:, a:b] = base[:, :b - a]
+        eng.set_option(eng.OPT_FITCH_WALK, {"auto": 1, "tile": 3, "regwalk": 2, "l2": 0}[args.fitch_kernel])
         eng.fitch_set_tips(tips, 4, capacity=n_nodes)
         acc = torch.zeros(1, dtype=torch.int64, device="cuda")
 

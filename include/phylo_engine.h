@@ -68,6 +68,12 @@ uint64_t phylo_engine_launch_count(const phylo_engine *e);
  * re-scoring); 0 = lnL only, the tree-fused kernel then writes no CLV at all. */
 #define PHYLO_OPT_FUSED_TREE 1
 #define PHYLO_OPT_RETAIN_CLV 2
+/* PHYLO_OPT_FITCH_WALK selects the whole-tree Fitch kernel: 1 (default) = automatic (on-chip
+ * tile kernel for small 4-plane alignments, register walk otherwise); 3 = on-chip tile kernel
+ * (4 planes: level-parallel medians out of shared memory, results published by the last CTA);
+ * 2 = register walk (compiled depth-first plan, tips prefetched several medians ahead, up to
+ * 8 planes); 0 = L2 walk (re-reads its own earlier writes through L2, any plane count). */
+#define PHYLO_OPT_FITCH_WALK 3
 int phylo_engine_set_option(phylo_engine *e, int option, int64_t value);
 int phylo_engine_get_option(phylo_engine *e, int option, int64_t *value);
 /* CUDA-event profiler: while enabled, every kernel launch is bracketed by an event pair on

@@ -62,6 +62,11 @@ struct phylo_engine {
   // ---- likelihood data
   int T = 0, cap = 0, mask_dev_bytes = 1;
   int64_t N = 0;
+  int opt_fitch_walk = 1;  // Fitch tree kernel: 0 = L2 walk, 1 = auto, 2 = register walk, 3 = on-chip tiles
+  unsigned long long *dAcc = nullptr;  // tile kernel accumulators (all zero between calls)
+  size_t capAcc = 0, tileSmem = 0;
+  int tileOcc = 1;
+  bool tileWeighted = false;
   int opt_fused = 1;  // 0 = one kernel per node, 1 = tree-fused (warp-autonomous where eligible), 2 = tile kernel only
   bool opt_retain = true;
   // TMA tensor maps of the node CLVs (warp-autonomous tree kernel stores through them)
@@ -181,6 +186,12 @@ static void prof_resolve(phylo_engine *e) {
   e->prof_pending.clear();
 }
 
+// per-call variant: event pairs are only folded once a few thousand are pending (or when the
+// totals are read), so small evaluations do not pay an event synchronisation each
+static void prof_resolve_lazy(phylo_engine *e) {
+  if (e->prof_pending.size() >= 4096) prof_resolve(e);
+}
+
 template <typename T>
 static void dfree(T *&p) {
   if (p) cudaFree(p);
@@ -276,7 +287,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill);
+  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -779,6 +790,7 @@ extern "C" int phylo_engine_set_option(phylo_engine *e, int option, int64_t valu
   switch (option) {
     case PHYLO_OPT_FUSED_TREE: e->opt_fused = (value == 2) ? 2 : (value != 0); return PHYLO_OK;
     case PHYLO_OPT_RETAIN_CLV: e->opt_retain = value != 0; return PHYLO_OK;
+    case PHYLO_OPT_FITCH_WALK: e->opt_fitch_walk = (value < 0 || value > 3) ? 1 : (int)value; return PHYLO_OK;
     default: return fail(e, PHYLO_ERR_ARG, "set_option: unknown option %d", option);
   }
 }
@@ -787,6 +799,7 @@ extern "C" int phylo_engine_get_option(phylo_engine *e, int option, int64_t *val
   switch (option) {
     case PHYLO_OPT_FUSED_TREE: *value = e->opt_fused; return PHYLO_OK;
     case PHYLO_OPT_RETAIN_CLV: *value = e->opt_retain; return PHYLO_OK;
+    case PHYLO_OPT_FITCH_WALK: *value = e->opt_fitch_walk; return PHYLO_OK;
     default: return fail(e, PHYLO_ERR_ARG, "get_option: unknown option %d", option);
   }
 }
@@ -821,6 +834,10 @@ static bool build_fused_plan(int cap, int T, const phylo_op *ops, int n_ops, int
   if (ra == rb) return false;
   for (int s = 0; s < cap; ++s)
     if (producer[s] >= 0 && uses[s] != 1) return false;
+  // an op that reads a slot which a LATER op overwrites means "the old contents": only the
+  // sequential per-node path honours that
+  for (int o = 0; o < n_ops; ++o)
+    if (producer[ops[o].left] > o || producer[ops[o].right] > o) return false;
   auto computed = [&](int s) { return producer[s] >= 0; };
   for (int o = 0; o < n_ops; ++o) {
     const int l = ops[o].left, r = ops[o].right, p = ops[o].parent;
@@ -1229,7 +1246,7 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
       CK(cudaStreamSynchronize(e->stream));
       *lnl_out = e->hScalar[0];
       e->lk_evaluated = true;
-      if (e->prof_on) prof_resolve(e);
+      if (e->prof_on) prof_resolve_lazy(e);
       return PHYLO_OK;
     }
   }
@@ -1261,7 +1278,7 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
   CK(cudaStreamSynchronize(e->stream));
   *lnl_out = e->hScalar[0];
   e->lk_evaluated = true;
-  if (e->prof_on) prof_resolve(e);
+  if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }
 
@@ -1287,7 +1304,7 @@ extern "C" int phylo_lk_score_alignment(phylo_engine *e, int T, int64_t N, const
   if ((rc = lk_check_bad(e, "lk_score_alignment")) != PHYLO_OK) return rc;
   *lnl_out = e->hScalar[0];
   e->lk_evaluated = true;
-  if (e->prof_on) prof_resolve(e);
+  if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }
 
@@ -1618,6 +1635,133 @@ static int fitch_check_schedule(phylo_engine *e, const phylo_op *ops, int n_ops,
   return PHYLO_OK;
 }
 
+// Characters per tree evaluation below which the on-chip tile kernel is used in auto mode
+// (measured cross-over with the register walk, profiles/README.md).
+static const int64_t kFitchTileMaxWords = 1 << 18;
+
+// On-chip tile kernel (fitch_tile_kernel): level-sorted program, results straight into mapped
+// host memory. Returns PHYLO_OK with *done = false when the schedule does not fit.
+static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                 uint64_t *length_out, bool *done) {
+  *done = false;
+  const int n_tot = n_ops + 1;  // + root-edge join
+  // operands: >= 0 = index into the tile's input rows; < 0 = -1 - (op that produces it)
+  std::vector<int> produced(e->fcap, -1), in_index(e->fcap, -1), inputs;
+  struct Raw { int l, r, out_slot; };
+  std::vector<Raw> raw(n_tot);
+  auto operand = [&](int slot) {
+    if (produced[slot] >= 0) return -1 - produced[slot];
+    if (in_index[slot] < 0) { in_index[slot] = (int)inputs.size(); inputs.push_back(slot); }
+    return in_index[slot];
+  };
+  std::vector<int> size(n_tot, 1), consumer(n_tot, -1);
+  for (int o = 0; o < n_tot; ++o) {
+    raw[o].l = operand(o < n_ops ? ops[o].left : root_a);
+    raw[o].r = operand(o < n_ops ? ops[o].right : root_b);
+    raw[o].out_slot = o < n_ops ? ops[o].parent : -1;
+    for (int c : {raw[o].l, raw[o].r})
+      if (c < 0) {
+        if (consumer[-1 - c] >= 0) return PHYLO_OK;  // a result used twice: not a forest, other kernels handle it
+        consumer[-1 - c] = o;
+        size[o] += size[-1 - c];
+      }
+    if (o < n_ops) produced[ops[o].parent] = o;
+  }
+  const int n_in = (int)inputs.size();
+  const bool weighted = e->dFW != nullptr;
+  const size_t smem = (size_t)(n_in + n_tot) * 512 + (size_t)(n_tot + 1) * (sizeof(FitchTileOp) + (weighted ? 256 : 128)) +
+                      (size_t)n_in * 8;
+  if (smem > 200 * 1024) return PHYLO_OK;
+  // Cut the forest into whole subtrees of at most `cap` medians (phase 1, dealt to the warps,
+  // largest first to the least loaded warp); what is above the cut runs on warp 0 (phase 2).
+  const int cap = std::max(4, (n_tot + kFitchTileWarps - 1) / kFitchTileWarps);
+  std::vector<int> task_of(n_tot, -1);  // -1: phase 2; else the phase-1 task (= its top op)
+  for (int o = n_tot - 1; o >= 0; --o) {  // consumers have larger indices: parents are visited first
+    if (consumer[o] >= 0 && task_of[consumer[o]] >= 0) task_of[o] = task_of[consumer[o]];
+    else if (size[o] <= cap) task_of[o] = o;
+  }
+  std::vector<int> tasks;
+  for (int o = 0; o < n_tot; ++o)
+    if (task_of[o] == o) tasks.push_back(o);
+  std::sort(tasks.begin(), tasks.end(), [&](int x, int y) { return size[x] != size[y] ? size[x] > size[y] : x < y; });
+  std::vector<int> load(kFitchTileWarps, 0), warp_of_task(n_tot, 0);
+  for (int t : tasks) {
+    const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    warp_of_task[t] = w;
+    load[w] += size[t];
+  }
+  // program order: phase-1 ops of warp 0, 1, ... (each in schedule order), then phase 2
+  std::vector<int> order, pos(n_tot), tstart(kFitchTileWarps + 2, 0);
+  order.reserve(n_tot);
+  for (int w = 0; w <= kFitchTileWarps; ++w) {
+    tstart[w] = (int)order.size();
+    for (int o = 0; o < n_tot; ++o) {
+      const bool mine = w < kFitchTileWarps ? (task_of[o] >= 0 && warp_of_task[task_of[o]] == w) : task_of[o] < 0;
+      if (mine) { pos[o] = (int)order.size(); order.push_back(o); }
+    }
+  }
+  tstart[kFitchTileWarps + 1] = (int)order.size();
+  int rc;
+  const size_t blob = sizeof(FitchTileOp) * n_tot + 8 * (size_t)n_in + 4 * (size_t)(kFitchTileWarps + 2) + 64;
+  if ((rc = fitch_sched_capacity(e, blob)) != PHYLO_OK) return rc;
+  if ((rc = fitch_cost_capacity(e, (size_t)n_tot + 4)) != PHYLO_OK) return rc;
+  if ((size_t)n_tot + 2 > e->capAcc) {
+    CK(cudaStreamSynchronize(e->stream));
+    dfree(e->dAcc);
+    e->capAcc = 0;
+    CK(cudaMalloc(&e->dAcc, sizeof(unsigned long long) * ((size_t)n_tot + 2) * 2));
+    CK(cudaMemset(e->dAcc, 0, sizeof(unsigned long long) * ((size_t)n_tot + 2) * 2));
+    e->capAcc = ((size_t)n_tot + 2) * 2;
+  }
+  CK(cudaStreamSynchronize(e->stream));  // pinned staging is about to be rewritten
+  char *hb = (char *)e->hSched;
+  FitchTileOp *hops = (FitchTileOp *)hb;
+  const uint32_t **hin = (const uint32_t **)(hb + sizeof(FitchTileOp) * n_tot);
+  int *hlev = (int *)(hb + sizeof(FitchTileOp) * n_tot + 8 * (size_t)n_in);
+  for (int i = 0; i < n_tot; ++i) {
+    const Raw &rw = raw[order[i]];
+    hops[i].l_off = 512u * (uint32_t)(rw.l >= 0 ? rw.l : n_in + pos[-1 - rw.l]);
+    hops[i].r_off = 512u * (uint32_t)(rw.r >= 0 ? rw.r : n_in + pos[-1 - rw.r]);
+    hops[i].out = rw.out_slot >= 0 ? e->fPre[rw.out_slot] : nullptr;
+  }
+  for (int i = 0; i < n_in; ++i) hin[i] = e->fPre[inputs[i]];
+  for (int w = 0; w < kFitchTileWarps + 2; ++w) hlev[w] = tstart[w];
+  CK(cudaMemcpyAsync(e->dSched, hb, blob - 64, cudaMemcpyHostToDevice, e->stream));
+  FitchTileArgs a;
+  char *db = (char *)e->dSched;
+  a.ops = (const FitchTileOp *)db;
+  a.in_ptr = (const uint32_t *const *)(db + sizeof(FitchTileOp) * n_tot);
+  a.task_start = (const int *)(db + sizeof(FitchTileOp) * n_tot + 8 * (size_t)n_in);
+  a.n_in = n_in; a.n_ops = n_tot;
+  a.nwords = e->fWords; a.N = e->fN; a.wt = e->dFW;
+  a.acc = e->dAcc;
+  CK(cudaHostGetDevicePointer((void **)&a.host_out, e->hCost, 0));
+  {
+    ProfScope prof(e, KC_FITCH_TREE);
+    auto kern = weighted ? fitch_tile_kernel<unsigned long long> : fitch_tile_kernel<uint32_t>;
+    if (e->tileSmem != smem || e->tileWeighted != weighted) {  // attribute + occupancy are looked up once per program shape
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      int q = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 256, smem) != cudaSuccess || q < 1) q = 1;
+      e->tileSmem = smem;
+      e->tileWeighted = weighted;
+      e->tileOcc = q;
+    }
+    // whole waves: every CTA gets the same number of tiles (+-1)
+    const int64_t ntiles = (e->fWords + 31) / 32, maxg = (int64_t)e->sm_count * e->tileOcc;
+    const int64_t waves = (ntiles + maxg - 1) / maxg;
+    const int g = (int)((ntiles + waves - 1) / waves);
+    kern<<<g, 256, smem, e->stream>>>(a);
+    LAUNCH_CHECK();
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  *length_out = e->hCost[n_tot];
+  for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[pos[o]];
+  if (e->prof_on) prof_resolve_lazy(e);
+  *done = true;
+  return PHYLO_OK;
+}
+
 extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                                       uint64_t *length_out) {
   if (!e) return PHYLO_ERR_ARG;
@@ -1627,12 +1771,74 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
   CK(cudaSetDevice(e->device));
   for (int o = 0; o < n_ops; ++o)
     if ((rc = fitch_ensure(e, ops[o].parent, false)) != PHYLO_OK) return rc;
+  if (e->fNPdev == 4 && (e->opt_fitch_walk == 3 || (e->opt_fitch_walk == 1 && e->fWords <= kFitchTileMaxWords))) {
+    bool done = false;
+    if ((rc = fitch_score_tree_tile(e, ops, n_ops, root_a, root_b, length_out, &done)) != PHYLO_OK) return rc;
+    if (done) return PHYLO_OK;
+  }
   if ((rc = fitch_sync_tables(e)) != PHYLO_OK) return rc;
   if ((rc = fitch_cost_capacity(e, (size_t)n_ops + 4)) != PHYLO_OK) return rc;
-  if ((rc = fitch_sched_capacity(e, sizeof(FitchStep) * (size_t)(n_ops + 2))) != PHYLO_OK)
+  if ((rc = fitch_sched_capacity(e, sizeof(FitchInstr) * (size_t)(n_ops + 2))) != PHYLO_OK)
     return rc;
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long) * (size_t)(n_ops + 2), e->stream));
+
+  // register-walk kernel: compiled depth-first plan, tips prefetched D steps ahead
+  FusedPlan pl;
+  const bool walk = e->opt_fitch_walk != 0 && e->fNPdev <= 8 &&
+                    build_fused_plan(e->fcap, e->fT, ops, n_ops, root_a, root_b, 0.0, pl);
+  size_t smem_walk = 0;
+  if (walk) {
+    const size_t ns = pl.steps.size();
+    smem_walk = ns * sizeof(FitchInstr) + (ns + (ns & 1)) * sizeof(unsigned long long) +
+                (size_t)pl.depth * e->fNPdev * 128 * sizeof(uint32_t);
+  }
+  if (walk && smem_walk <= 200 * 1024) {
+    const int ns = (int)pl.steps.size();
+    FitchInstr *hp = (FitchInstr *)e->hSched;  // capacity: sizeof(FitchInstr) * (n_ops + 2) ensured below
+    for (int i = 0; i < ns; ++i) {
+      const PlanStep &st = pl.steps[i];
+      FitchInstr in{};
+      const int lk = (st.lkind == OPK_STORED) ? OPK_TIP : st.lkind, rk = (st.rkind == OPK_STORED) ? OPK_TIP : st.rkind;
+      in.kinds = lk | (rk << 2) | (st.push_first << 4);
+      in.l = (lk == OPK_TIP) ? e->fPre[st.lidx] : nullptr;
+      in.r = (rk == OPK_TIP) ? e->fPre[st.ridx] : nullptr;
+      in.out = st.out_slot >= 0 ? e->fPre[st.out_slot] : nullptr;
+      hp[i] = in;
+    }
+    CK(cudaMemcpyAsync(e->dSched, hp, sizeof(FitchInstr) * (size_t)ns, cudaMemcpyHostToDevice, e->stream));
+    const int g = grid_for(e->fWords, 128, e->sm_count * 16);
+    {
+      ProfScope prof(e, KC_FITCH_TREE);
+#define FITCH_WALK(NPV, DV)                                                                                         \
+  {                                                                                                                 \
+    auto kern = fitch_treep_kernel<NPV, DV>;                                                                        \
+    if (smem_walk > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_walk)); \
+    kern<<<g, 128, smem_walk, e->stream>>>((const FitchInstr *)e->dSched, ns, pl.depth, e->fWords, e->fN, e->dFW,   \
+                                           e->dCost, e->dCost + n_ops + 1);                                        \
+  }
+      switch (e->fNPdev) {
+        case 1: FITCH_WALK(1, 8) break;
+        case 2: FITCH_WALK(2, 8) break;
+        case 3: FITCH_WALK(3, 8) break;
+        case 4: FITCH_WALK(4, 8) break;
+        case 5: FITCH_WALK(5, 4) break;
+        case 6: FITCH_WALK(6, 4) break;
+        default: FITCH_WALK(8, 4) break;
+      }
+#undef FITCH_WALK
+      ++e->launches;
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long) * (size_t)(n_ops + 2), cudaMemcpyDeviceToHost,
+                       e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *length_out = e->hCost[n_ops + 1];
+    for (int i = 0; i < ns; ++i)
+      if (pl.steps[i].out_slot >= 0) e->nodeCost[pl.steps[i].out_slot] = e->hCost[i];
+    if (e->prof_on) prof_resolve_lazy(e);
+    return PHYLO_OK;
+  }
 
   FitchStep *hs = (FitchStep *)e->hSched;
   for (int o = 0; o < n_ops; ++o) hs[o] = FitchStep{ops[o].parent, ops[o].left, ops[o].right};
@@ -1651,7 +1857,7 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
   CK(cudaStreamSynchronize(e->stream));
   *length_out = e->hCost[n_ops + 1];
   for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[o];
-  if (e->prof_on) prof_resolve(e);
+  if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }
 

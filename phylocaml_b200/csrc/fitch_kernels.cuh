@@ -184,6 +184,246 @@ fitch_tree_kernel(uint32_t *const *__restrict__ bufs, const FitchStep *__restric
   if (t) atomicAdd(total, t);
 }
 
+// ------------------------------------------------ whole-tree down-pass, register walk ----
+// Latency-optimised variant (default for <= 8 planes): the schedule is compiled on the host
+// into a depth-first plan (build_fused_plan, shared with the likelihood tree kernels) whose
+// operands are GLOBAL (a tip or a set that already exists in HBM), CUR (the previous result,
+// still in registers) or POP (parked on a per-thread shared-memory stack). A thread never
+// re-reads what it wrote, so the only loads left are the tips -- and those do not depend on
+// any computation: they are issued D steps ahead into a register ring, D*2 128-bit loads in
+// flight per thread instead of the 2 (behind two dependent pointer loads) of
+// fitch_tree_kernel. At 1 M characters (31 k columns, ~7 warps per SM) that is the
+// difference between a latency-bound 50 us and a bandwidth-shaped walk.
+struct __align__(16) FitchInstr {
+  int kinds;            // lkind | rkind << 2 | push_first << 4   (OPK_TIP doubles as "global operand")
+  int pad_;
+  const uint32_t *l, *r;  // global operands
+  uint32_t *out;          // parent set, or NULL (root-edge join)
+};
+static_assert(sizeof(FitchInstr) == 32, "FitchInstr is two 16-byte words");
+
+template <int NP, int D>
+__global__ void __launch_bounds__(128)
+fitch_treep_kernel(const FitchInstr *__restrict__ prog, int n_steps, int depth, int64_t nwords, int64_t N,
+                   const uint32_t *__restrict__ wt, unsigned long long *__restrict__ node_cost,
+                   unsigned long long *__restrict__ total) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  FitchInstr *sprog = reinterpret_cast<FitchInstr *>(fsm);                                 // [n_steps]
+  unsigned long long *sh_cost = reinterpret_cast<unsigned long long *>(sprog + n_steps);   // [n_steps]
+  uint32_t *stack = reinterpret_cast<uint32_t *>(sh_cost + n_steps + (n_steps & 1));       // [depth][NP][128]
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 2 * n_steps; i += blockDim.x)
+    reinterpret_cast<int4 *>(sprog)[i] = __ldg(reinterpret_cast<const int4 *>(prog) + i);
+  for (int o = tid; o < n_steps; o += blockDim.x) sh_cost[o] = 0;
+  __syncthreads();
+  auto ldg_planes = [&](const uint32_t *buf, int64_t w) {
+    Planes<NP> r;
+    if (NP == 4) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4 *>(buf + w * 4));
+      r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int s = 0; s < NP; ++s) r.v[s] = __ldg(buf + w * NP + s);
+    }
+    return r;
+  };
+  for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x; w0 < nwords; w0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t w = w0 + tid;
+    const bool act = w < nwords;
+    const int64_t wc = act ? w : nwords - 1;  // inactive lanes load a valid column and discard it
+    const uint32_t valid = act ? valid_mask(w, N) : 0u;
+    Planes<NP> pl[D], pr[D], cur;
+#pragma unroll
+    for (int s = 0; s < NP; ++s) cur.v[s] = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (i < n_steps) {
+        const FitchInstr in = sprog[i];
+        if ((in.kinds & 3) == OPK_TIP) pl[i] = ldg_planes(in.l, wc);
+        if (((in.kinds >> 2) & 3) == OPK_TIP) pr[i] = ldg_planes(in.r, wc);
+      }
+    }
+    int sp = 0;
+    for (int base = 0; base < n_steps; base += D) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int step = base + i;
+        if (step < n_steps) {
+          const FitchInstr in = sprog[step];
+          const int lkind = in.kinds & 3, rkind = (in.kinds >> 2) & 3;
+          if (in.kinds & 16) {
+#pragma unroll
+            for (int s = 0; s < NP; ++s) stack[(sp * NP + s) * 128 + tid] = cur.v[s];
+            ++sp;
+          }
+          Planes<NP> a, b, c;
+          if (lkind == OPK_TIP) a = pl[i];
+          else if (lkind == OPK_CUR) a = cur;
+          else {
+            --sp;
+#pragma unroll
+            for (int s = 0; s < NP; ++s) a.v[s] = stack[(sp * NP + s) * 128 + tid];
+          }
+          if (rkind == OPK_TIP) b = pr[i];
+          else if (rkind == OPK_CUR) b = cur;
+          else {
+            --sp;
+#pragma unroll
+            for (int s = 0; s < NP; ++s) b.v[s] = stack[(sp * NP + s) * 128 + tid];
+          }
+          const uint32_t chg = fitch_rule<NP>(a, b, c) & valid;
+          if (in.out != nullptr && act) st_planes<NP>(in.out, w, c);
+          cur = c;
+          if (wt) {
+            unsigned long long cw = weighted_cost(chg, wc, wt);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) cw += __shfl_down_sync(0xffffffffu, cw, off);
+            if (lane == 0 && cw) atomicAdd(&sh_cost[step], cw);
+          } else {
+            const unsigned cs = __reduce_add_sync(0xffffffffu, (unsigned)__popc(chg));
+            if (lane == 0 && cs) atomicAdd(&sh_cost[step], (unsigned long long)cs);
+          }
+          if (step + D < n_steps) {  // refill this ring position with the operands of step + D
+            const FitchInstr nx = sprog[step + D];
+            if ((nx.kinds & 3) == OPK_TIP) pl[i] = ldg_planes(nx.l, wc);
+            if (((nx.kinds >> 2) & 3) == OPK_TIP) pr[i] = ldg_planes(nx.r, wc);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long t = 0;
+  for (int o = tid; o < n_steps; o += blockDim.x) {
+    const unsigned long long c = sh_cost[o];
+    if (c) {
+      atomicAdd(&node_cost[o], c);
+      t += c;
+    }
+  }
+  if (t) atomicAdd(total, t);
+}
+
+// ----------------------------------------------- whole-tree down-pass, on-chip tiles ----
+// Latency-optimised variant for 4 state planes (DNA) and alignments too small to hide a
+// 60-deep dependent walk behind other warps (BASELINE config 2: 1 M characters = 31 k
+// columns). A CTA owns a tile of 32 columns; ALL input sets of the tile (tips and sets
+// already resident) are fetched at once with cp.async (n_in independent 512-byte rows in
+// flight per CTA), then the medians are evaluated out of shared memory in two phases: the
+// host cuts the tree into whole subtrees of at most ~n/8 medians, deals them to the 8 warps
+// (phase 1; a lane only ever touches its own column, so a warp runs its list without any
+// synchronisation), and the few medians above the cut run on warp 0 after ONE __syncthreads
+// (phase 2). (A first version synchronised once per tree level: 27 barriers for the bench
+// tree, 12 k cycles per tile.) Results go to shared memory (for the parent) and to HBM (once).
+// The last CTA to finish publishes the per-op costs and the length straight into mapped
+// host memory and re-zeroes the accumulators: one kernel launch is the whole call.
+constexpr int kFitchTileWarps = 8;
+struct __align__(16) FitchTileOp {
+  uint32_t l_off, r_off;  // byte offsets of the operands' rows in the tile table (inputs first, then op results)
+  uint32_t *out;          // parent set in HBM, or NULL (root-edge join)
+};
+struct FitchTileArgs {
+  const uint32_t *const *in_ptr;   // [n_in]
+  const FitchTileOp *ops;          // [n_ops] sorted by level, the root join last
+  const int *task_start;           // [kFitchTileWarps + 2]: phase-1 op ranges per warp, then the phase-2 range
+  int n_in, n_ops;
+  int64_t nwords, N;
+  const uint32_t *wt;
+  unsigned long long *acc;         // [n_ops + 2]: per-op costs, total, CTA counter (all zero between calls)
+  unsigned long long *host_out;    // mapped host memory [n_ops + 1]: per-op costs, total
+};
+
+// CNT = uint32_t (unweighted: <= 32 per tile and op) or unsigned long long (weighted)
+template <typename CNT>
+__global__ void __launch_bounds__(256)
+fitch_tile_kernel(const FitchTileArgs a) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  unsigned char *table = tsm;                                                              // [n_in + n_ops][32] uint4
+  FitchTileOp *sops = reinterpret_cast<FitchTileOp *>(table + (size_t)(a.n_in + a.n_ops) * 512);  // [n_ops]
+  // per-lane cost counters [n_ops][32]: plain read-modify-write by the owning lane -- no warp
+  // reduction and no atomics on the per-level critical path (an op always maps to one warp)
+  CNT *sh_cnt = reinterpret_cast<CNT *>(sops + a.n_ops);
+  const uint32_t **sin = reinterpret_cast<const uint32_t **>(sh_cnt + (size_t)(a.n_ops + (a.n_ops & 1)) * 32);  // [n_in]
+  __shared__ bool is_last;
+  __shared__ int stask[kFitchTileWarps + 2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFitchTileWarps;
+  for (int i = tid; i < a.n_ops; i += blockDim.x) sops[i] = a.ops[i];
+  for (int i = tid; i < a.n_ops * 32; i += blockDim.x) sh_cnt[i] = 0;
+  for (int i = tid; i < a.n_in; i += blockDim.x) sin[i] = a.in_ptr[i];
+  if (tid < kFitchTileWarps + 2) stask[tid] = a.task_start[tid];
+  __syncthreads();
+  const int64_t ntiles = (a.nwords + 31) / 32;
+  unsigned char *mine = table + lane * 16;                 // this lane's column inside any table row
+  unsigned char *res0 = mine + (size_t)a.n_in * 512;       // ... inside op 0's result row
+  const int p1_lo = stask[warp], p1_hi = stask[warp + 1], p2_lo = stask[kFitchTileWarps], p2_hi = stask[kFitchTileWarps + 1];
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t w = tile * 32 + lane;  // buffers are padded to whole tiles: always in bounds
+    const uint32_t valid = valid_mask(w, a.N);
+    for (int i = warp; i < a.n_in; i += nwarps) cp_async16(mine + i * 512, sin[i] + w * 4);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // a run of ops executed by this warp in order; the next descriptor is fetched one op ahead
+    auto run = [&](int lo, int hi) {
+      if (lo >= hi) return;
+      FitchTileOp op = sops[lo];
+      for (int o = lo; o < hi; ++o) {
+        const FitchTileOp nxt = sops[min(o + 1, hi - 1)];
+        const uint4 ua = *reinterpret_cast<const uint4 *>(mine + op.l_off), ub = *reinterpret_cast<const uint4 *>(mine + op.r_off);
+        Planes<4> pa, pb, pc;
+        pa.v[0] = ua.x; pa.v[1] = ua.y; pa.v[2] = ua.z; pa.v[3] = ua.w;
+        pb.v[0] = ub.x; pb.v[1] = ub.y; pb.v[2] = ub.z; pb.v[3] = ub.w;
+        const uint32_t chg = fitch_rule<4>(pa, pb, pc) & valid;
+        const uint4 uc = make_uint4(pc.v[0], pc.v[1], pc.v[2], pc.v[3]);
+        *reinterpret_cast<uint4 *>(res0 + o * 512) = uc;
+        if (op.out != nullptr) *reinterpret_cast<uint4 *>(op.out + w * 4) = uc;
+        if (sizeof(CNT) == 8) sh_cnt[o * 32 + lane] += (CNT)weighted_cost(chg, w, a.wt);
+        else sh_cnt[o * 32 + lane] += (CNT)__popc(chg);
+        op = nxt;
+      }
+    };
+    run(p1_lo, p1_hi);
+    __syncthreads();
+    if (warp == 0) run(p2_lo, p2_hi);
+    __syncthreads();  // the table is rewritten by the next tile's inputs
+  }
+  // per-op totals: one warp per op folds its 32 lane counters
+  unsigned long long t = 0;
+  for (int o = warp; o < a.n_ops; o += nwarps) {
+    unsigned long long c;
+    if (sizeof(CNT) == 8) {
+      c = sh_cnt[o * 32 + lane];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+    } else {
+      c = __reduce_add_sync(0xffffffffu, (unsigned)sh_cnt[o * 32 + lane]);
+    }
+    if (lane == 0 && c) {
+      atomicAdd(&a.acc[o], c);
+      t += c;
+    }
+  }
+  if (lane == 0 && t) atomicAdd(&a.acc[a.n_ops], t);
+  // ---- last CTA publishes to mapped host memory and restores the all-zero invariant.
+  // bar.sync orders the CTA's atomics before thread 0's fence + counter increment
+  // (cumulativity), so only one thread pays for the fence.
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    is_last = atomicAdd(&a.acc[a.n_ops + 1], 1ull) == (unsigned long long)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int o = tid; o <= a.n_ops; o += blockDim.x) {
+      a.host_out[o] = __ldcg(&a.acc[o]);
+      a.acc[o] = 0;
+    }
+    if (tid == 0) a.acc[a.n_ops + 1] = 0;
+    __threadfence_system();
+  }
+}
+
 // ------------------------------------------------------------------------- up-pass ----
 // Final sets, walking the schedule backwards (parents before children). Rule (SURVEY.md
 // section 8 a11; the reference leaves Node.final_states TODO, lib/node.ml:260-268), per character

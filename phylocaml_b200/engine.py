@@ -199,7 +199,7 @@ class Engine:
     def launch_count(self):
         return int(self.lib.phylo_engine_launch_count(self.h))
 
-    OPT_FUSED_TREE, OPT_RETAIN_CLV = 1, 2
+    OPT_FUSED_TREE, OPT_RETAIN_CLV, OPT_FITCH_WALK = 1, 2, 3
 
     def set_option(self, option, value):
         self._ck(self.lib.phylo_engine_set_option(self.h, option, int(value)))

@@ -223,8 +223,16 @@ def _fitch_setup(T, N, n_states, dtype, seed=1):
     return ops, ra, rb, n_nodes, chars
 
 
-@pytest.mark.parametrize("T,N", [(16, 10000), (64, 100003), (5, 31), (3, 1), (64, 32)])
-def test_fitch_tree_length_and_sets_bit_exact(eng, oracle, T, N):
+@pytest.fixture(params=[1, 3, 2, 0], ids=["auto", "tile", "regwalk", "l2walk"])
+def fitch_walk(eng, request):
+    """All whole-tree Fitch kernels: automatic choice, on-chip tiles, register walk, L2 walk."""
+    eng.set_option(eng.OPT_FITCH_WALK, request.param)
+    yield request.param
+    eng.set_option(eng.OPT_FITCH_WALK, 1)
+
+
+@pytest.mark.parametrize("T,N", [(16, 10000), (64, 100003), (5, 31), (3, 1), (64, 32), (2, 77)])
+def test_fitch_tree_length_and_sets_bit_exact(eng, oracle, fitch_walk, T, N):
     ops, ra, rb, n_nodes, chars = _fitch_setup(T, N, 4, np.uint8)
     eng.fitch_set_tips(chars, 4, capacity=n_nodes)
     length = eng.fitch_score_tree(ops, ra, rb)
@@ -242,7 +250,7 @@ def test_fitch_tree_length_and_sets_bit_exact(eng, oracle, T, N):
 @pytest.mark.parametrize("dtype,n_states", [(np.uint8, 5), (np.uint8, 6), (np.uint8, 8), (np.uint16, 11),
                                             (np.uint32, 22), (np.uint32, 32), (np.uint64, 40),
                                             (np.uint64, 64)])
-def test_fitch_all_widths(eng, oracle, dtype, n_states):
+def test_fitch_all_widths(eng, oracle, fitch_walk, dtype, n_states):
     """W in {8,16,32,64} (lib/bitvector/bv.h:29-55) and plane counts up to 64."""
     ops, ra, rb, n_nodes, chars = _fitch_setup(12, 3001, n_states, dtype, seed=3)
     eng.fitch_set_tips(chars, n_states, capacity=n_nodes)
@@ -272,7 +280,7 @@ def test_fitch_median_2_and_distance_per_node(eng, oracle):
     assert total + d == eng.fitch_score_tree(ops, ra, rb)
 
 
-def test_fitch_weighted(eng, oracle):
+def test_fitch_weighted(eng, oracle, fitch_walk):
     ops, ra, rb, n_nodes, chars = _fitch_setup(16, 7000, 4, np.uint8, seed=4)
     w = np.random.default_rng(2).integers(0, 9, 7000).astype(float)
     eng.fitch_set_tips(chars, 4, weights=w, capacity=n_nodes)
@@ -281,7 +289,27 @@ def test_fitch_weighted(eng, oracle):
         eng.fitch_set_tips(chars, 4, weights=w + 0.5, capacity=n_nodes)
 
 
-def test_fitch_uppass_final_sets(eng, oracle):
+def test_fitch_caterpillar_and_partial_schedule(eng, oracle, fitch_walk):
+    """A 300-taxon caterpillar (stack-free plan, long dependency chain) and a partial
+    re-evaluation whose other operands are sets already resident from the first call."""
+    T, N = 300, 2500
+    tr = tree.caterpillar_tree(T)
+    ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+    chars = tree.random_fitch_chars(T, N, 4, 11, dtype=np.uint8)
+    eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+    want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, want_sets=True)
+    assert eng.fitch_score_tree(ops, ra, rb) == want["length"]
+    # re-run only the last third of the schedule: earlier parents are read back from HBM
+    cut = 2 * len(ops) // 3
+    tail_cost = sum(int(want["node_cost"][int(op["parent"])]) for op in ops[cut:])
+    d = oracle.fitch_distance(want["prelim"][ra], want["prelim"][rb])
+    assert eng.fitch_score_tree(ops[cut:].copy(), ra, rb) == tail_cost + d
+    for op in ops[-4:]:
+        p = int(op["parent"])
+        assert np.array_equal(eng.fitch_get_states(p), want["prelim"][p])
+
+
+def test_fitch_uppass_final_sets(eng, oracle, fitch_walk):
     ops, ra, rb, n_nodes, chars = _fitch_setup(24, 4099, 4, np.uint8, seed=6)
     eng.fitch_set_tips(chars, 4, capacity=n_nodes)
     eng.fitch_score_tree(ops, ra, rb)
