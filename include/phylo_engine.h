@@ -68,8 +68,9 @@ uint64_t phylo_engine_launch_count(const phylo_engine *e);
  * re-scoring); 0 = lnL only, the tree-fused kernel then writes no CLV at all. */
 #define PHYLO_OPT_FUSED_TREE 1
 #define PHYLO_OPT_RETAIN_CLV 2
-/* PHYLO_OPT_FITCH_WALK selects the whole-tree Fitch kernel: 1 (default) = automatic (on-chip
- * tile kernel for small 4-plane alignments, register walk otherwise); 3 = on-chip tile kernel
+/* PHYLO_OPT_FITCH_WALK selects the whole-tree Fitch kernel: 1 (default) = automatic (below
+ * ~8 M characters the on-chip tile kernel for 4 planes / the register walk for up to 8 planes,
+ * which are latency-optimised; the bandwidth-optimised L2 walk above); 3 = on-chip tile kernel
  * (4 planes: level-parallel medians out of shared memory, results published by the last CTA);
  * 2 = register walk (compiled depth-first plan, tips prefetched several medians ahead, up to
  * 8 planes); 0 = L2 walk (re-reads its own earlier writes through L2, any plane count). */

@@ -1785,7 +1785,8 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
 
   // register-walk kernel: compiled depth-first plan, tips prefetched D steps ahead
   FusedPlan pl;
-  const bool walk = e->opt_fitch_walk != 0 && e->fNPdev <= 8 &&
+  // auto: the register walk only pays where the dependent L2 walk is latency-bound (small alignments)
+  const bool walk = (e->opt_fitch_walk == 2 || (e->opt_fitch_walk == 1 && e->fWords <= kFitchTileMaxWords)) && e->fNPdev <= 8 &&
                     build_fused_plan(e->fcap, e->fT, ops, n_ops, root_a, root_b, 0.0, pl);
   size_t smem_walk = 0;
   if (walk) {
