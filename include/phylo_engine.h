@@ -138,6 +138,20 @@ int phylo_lk_score_alignment(phylo_engine *e, int T, int64_t N, const void *mask
 /* Likelihood.root_cost / distance_1 (lib/nodeData.ml:29,32): lnL of joining the directed
  * CLVs a and b across an edge, for n_t candidate lengths (branch-length loop). */
 int phylo_lk_edge_lnl(phylo_engine *e, int a, int b, const double *t, int n_t, double *lnl_out);
+/* Branch-length loop on the edge (a, b) -- Likelihood.adjust_3 / readjust (lib/nodeData.ml:25,
+ * lib/node.ml:239-256; TODO in lib/likelihood_c.ml:19-24). phylo_lk_edge_prepare builds the
+ * edge's sum table (one CLV-sized array, eigen-space products of the two CLVs) once;
+ * phylo_lk_edge_eval then returns lnL(t) and its first and second derivatives for n_t lengths,
+ * each pass streaming only that table (d1_out / d2_out may be NULL). Values agree with
+ * phylo_lk_edge_lnl to rounding (<= 1e-12 relative). The prepared edge stays valid until the
+ * model or the tips change; re-prepare after the CLVs of a or b change. */
+int phylo_lk_edge_prepare(phylo_engine *e, int a, int b);
+int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, double *lnl_out, double *d1_out,
+                       double *d2_out);
+/* Maximises lnL over the length of edge (a, b) in [t_min, t_max] by safeguarded Newton steps
+ * from t0 (tol: relative step tolerance, <= 0 -> 1e-8; max_iter < 1 -> 50). */
+int phylo_lk_optimize_branch(phylo_engine *e, int a, int b, double t0, double t_min, double t_max,
+                             double tol, int max_iter, double *t_opt, double *lnl_opt, int *iters_out);
 /* Read-back. clv_out: N*K*S doubles [pattern][k][i]; scale_out: N int32 or NULL. */
 int phylo_lk_get_clv(phylo_engine *e, int node, double *clv_out, int32_t *scale_out);
 /* per-pattern ln-likelihoods (unweighted) of the last score_tree / edge_lnl (last t) */

@@ -18,6 +18,7 @@
 #include "lk_kernels.cuh"
 #include "lk_tree_kernel.cuh"
 #include "lk_treew_kernel.cuh"
+#include "lk_edge_kernels.cuh"
 #include "phylo_engine.h"
 
 using namespace phylo;
@@ -33,11 +34,11 @@ struct LkNode {
 // kernel classes for the CUDA-event profiler (phylo_engine_profile_*)
 enum KClass {
   KC_PT_BUILD = 0, KC_TREE_FUSED, KC_PRUNE_II, KC_PRUNE_TI, KC_PRUNE_TT, KC_ROOT, KC_REDUCE, KC_TIPS_PREPARE,
-  KC_FITCH_TREE, KC_FITCH_NODE, KC_FITCH_UPPASS, KC_FITCH_TRANSCODE, KC_BV, KC_COUNT
+  KC_FITCH_TREE, KC_FITCH_NODE, KC_FITCH_UPPASS, KC_FITCH_TRANSCODE, KC_BV, KC_EDGE, KC_COUNT
 };
 static const char *kClassNames[KC_COUNT] = {
     "pt_build", "tree_fused", "prune_inner_inner", "prune_tip_inner", "prune_tip_tip", "root_lnl", "reduce1024",
-    "tips_prepare", "fitch_tree", "fitch_median2", "fitch_uppass", "fitch_transcode", "bv_setops"};
+    "tips_prepare", "fitch_tree", "fitch_median2", "fitch_uppass", "fitch_transcode", "bv_setops", "edge_loop"};
 
 struct phylo_engine {
   int device = 0;
@@ -100,6 +101,12 @@ struct phylo_engine {
   size_t capP = 0;       // branches
   double *dT = nullptr, *hT = nullptr;  // branch lengths (device / pinned)
   double *dSite = nullptr;
+  // branch-length loop (lk_edge_kernels.cuh): eigenvector matrices in the orientation the sum table needs,
+  // the sum table of the prepared edge, per-(t, derivative) block partials
+  double *dUL = nullptr, *dUR = nullptr, *dSum = nullptr, *dEdgePart = nullptr, *dEdgeOut = nullptr, *dEdgeT = nullptr;
+  int32_t *dSumSc = nullptr;
+  bool edge_ready = false;
+  int edge_a = -1, edge_b = -1;
   double *dGroups = nullptr;                   // per-32-pattern sums (tree-fused kernel)
   double *dPart = nullptr, *dPart2 = nullptr;  // reduction levels
   int64_t nPart = 0;
@@ -238,7 +245,7 @@ extern "C" int phylo_engine_create(int device, phylo_engine **out) {
       e->encodeTiled = (phylo_engine::EncodeTiledFn)fn;
     cudaGetLastError();
   }
-  if (cudaMallocHost(&e->hScalar, 64) != cudaSuccess) {
+  if (cudaMallocHost(&e->hScalar, 1024) != cudaSuccess) {
     delete e;
     return fail(nullptr, PHYLO_ERR_CUDA, "phylo_engine_create: cudaMallocHost failed");
   }
@@ -257,6 +264,8 @@ static void lk_free_data(phylo_engine *e) {
   dfree(e->dNodeClv);
   dfree(e->dNodeSc);
   dfree(e->dTmaps);
+  dfree(e->dSum); dfree(e->dSumSc); dfree(e->dEdgePart);
+  e->edge_ready = false;
   e->nodeTabDirty = true;
   e->tmapDirty = true;
   dfree(e->dInv);
@@ -287,7 +296,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc);
+  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -459,6 +468,22 @@ extern "C" int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U
     CK(cudaMalloc(&e->dUi, sizeof(double) * ss));
     CK(cudaMemcpy(e->dUi, Ui, sizeof(double) * ss, cudaMemcpyHostToDevice));
   }
+  {
+    // P = UL diag(e) UR: GTR UL = U, UR = Ui (lib/mlmodel.c:325-342); symmetric UL = U^T, UR = U (:280-302)
+    std::vector<double> ul(ss), ur(ss);
+    for (int i = 0; i < S; ++i)
+      for (int m = 0; m < S; ++m) {
+        ul[(size_t)i * S + m] = Ui ? U[(size_t)i * S + m] : U[(size_t)m * S + i];
+        ur[(size_t)m * S + i] = Ui ? Ui[(size_t)m * S + i] : U[(size_t)m * S + i];
+      }
+    dfree(e->dUL); dfree(e->dUR);
+    CK(cudaMalloc(&e->dUL, sizeof(double) * ss));
+    CK(cudaMalloc(&e->dUR, sizeof(double) * ss));
+    CK(cudaMemcpy(e->dUL, ul.data(), sizeof(double) * ss, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->dUR, ur.data(), sizeof(double) * ss, cudaMemcpyHostToDevice));
+  }
+  dfree(e->dSum); dfree(e->dSumSc);
+  e->edge_ready = false;
   e->S = S; e->K = K; e->sym = (Ui == nullptr); e->pinvar = pinvar < 0 ? -1.0 : pinvar;
   e->has_model = true;
   return PHYLO_OK;
@@ -507,6 +532,7 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
   if (reuse) {
     for (auto &n : e->nodes) n.valid = false;
     e->lk_evaluated = false;
+    e->edge_ready = false;
   } else {
     lk_free_data(e);
     e->T = T; e->N = N; e->cap = capacity;
@@ -1329,6 +1355,135 @@ extern "C" int phylo_lk_edge_lnl(phylo_engine *e, int a_slot, int b_slot, const 
     lnl_out[i] = e->hScalar[0];
   }
   e->lk_evaluated = true;
+  return PHYLO_OK;
+}
+
+// ------------------------------------------------------------ branch-length loop ----
+static const int kEdgeMaxT = 16;  // branch lengths per edge_eval pass
+
+extern "C" int phylo_lk_edge_prepare(phylo_engine *e, int a_slot, int b_slot) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_edge_prepare: no tips loaded");
+  CK(cudaSetDevice(e->device));
+  Operand a, b;
+  int rc;
+  if ((rc = lk_operand(e, a_slot, &a, "lk_edge_prepare")) != PHYLO_OK) return rc;
+  if ((rc = lk_operand(e, b_slot, &b, "lk_edge_prepare")) != PHYLO_OK) return rc;
+  const size_t KS = (size_t)e->K * e->S;
+  if (!e->dSum) {
+    CK(cudaMalloc(&e->dSum, sizeof(double) * (size_t)e->N * KS));
+    CK(cudaMalloc(&e->dSumSc, sizeof(int32_t) * (size_t)e->N));
+  }
+  if (!e->dEdgePart) CK(cudaMalloc(&e->dEdgePart, sizeof(double) * (size_t)e->nPart * 3 * kEdgeMaxT));
+  if (!e->dEdgeOut) CK(cudaMalloc(&e->dEdgeOut, sizeof(double) * 3 * kEdgeMaxT));
+  if (!e->dEdgeT) CK(cudaMalloc(&e->dEdgeT, sizeof(double) * kEdgeMaxT));
+  const size_t mat = 2 * sizeof(double) * (size_t)e->S * e->S;
+  const int stage = mat <= 96 * 1024;
+  const int g = grid_for(e->N * e->K, 128, e->sm_count * 16);
+  {
+    ProfScope prof(e, KC_EDGE);
+#define EDGE_SUM(MT)                                                                                              \
+  {                                                                                                               \
+    auto kern = edge_sumtable_kernel<MT>;                                                                         \
+    if (stage && mat > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mat)); \
+    kern<<<g, 128, stage ? mat : 0, e->stream>>>(a.src, a.scale, a.tip, b.src, b.scale, b.tip, e->dUL, e->dUR, e->dPi, \
+                                                 e->S, e->K, e->N, stage, e->dSum, e->dSumSc);                    \
+  }
+    if (e->mask_dev_bytes == 1) EDGE_SUM(uint8_t)
+    else if (e->mask_dev_bytes == 4) EDGE_SUM(uint32_t)
+    else EDGE_SUM(uint64_t)
+#undef EDGE_SUM
+    LAUNCH_CHECK();
+  }
+  e->edge_ready = true;
+  e->edge_a = a_slot;
+  e->edge_b = b_slot;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, double *lnl_out, double *d1_out,
+                                  double *d2_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!e->edge_ready) return fail(e, PHYLO_ERR_STATE, "lk_edge_eval: call phylo_lk_edge_prepare first");
+  if (!t || n_t < 1 || !lnl_out) return fail(e, PHYLO_ERR_ARG, "lk_edge_eval: bad arguments");
+  if (e->nPart > (int64_t)kLnlBlock * kLnlBlock) return fail(e, PHYLO_ERR_UNSUPPORTED, "lk_edge_eval: more than 2^30 patterns");
+  CK(cudaSetDevice(e->device));
+  const int KS = e->K * e->S;
+  for (int t0 = 0; t0 < n_t; t0 += kEdgeMaxT) {
+    // as many lengths per pass as the coefficient table allows (<= 48 KB of shared memory)
+    const int per = std::max(1, std::min(kEdgeMaxT, (int)(48 * 1024 / (sizeof(double) * 3 * KS))));
+    for (int c0 = t0; c0 < std::min(n_t, t0 + kEdgeMaxT); c0 += per) {
+      const int nc = std::min(per, std::min(n_t, t0 + kEdgeMaxT) - c0);
+      CK(cudaStreamSynchronize(e->stream));  // hT staging
+      for (int i = 0; i < nc; ++i) e->hT[i] = t[c0 + i];
+      CK(cudaMemcpyAsync(e->dEdgeT, e->hT, sizeof(double) * nc, cudaMemcpyHostToDevice, e->stream));
+      const size_t smem = sizeof(double) * 3 * (size_t)KS * nc;
+      const int g = (int)std::min<int64_t>(e->nPart, (int64_t)e->sm_count * 4);
+      {
+        ProfScope prof(e, KC_EDGE);
+        if (e->mask_dev_bytes == 1)
+          edge_eval_kernel<uint8_t><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, e->pinvar,
+                                                              (const uint8_t *)e->dInv, e->dWeights, e->dEdgeT, nc, e->sym, e->S, e->K, e->N, e->dEdgePart);
+        else if (e->mask_dev_bytes == 4)
+          edge_eval_kernel<uint32_t><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, e->pinvar,
+                                                               (const uint32_t *)e->dInv, e->dWeights, e->dEdgeT, nc, e->sym, e->S, e->K, e->N, e->dEdgePart);
+        else
+          edge_eval_kernel<uint64_t><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, e->pinvar,
+                                                               (const uint64_t *)e->dInv, e->dWeights, e->dEdgeT, nc, e->sym, e->S, e->K, e->N, e->dEdgePart);
+        LAUNCH_CHECK();
+        fold_rows_kernel<<<3 * nc, 256, 0, e->stream>>>(e->dEdgePart, e->nPart, e->dEdgeOut);
+        LAUNCH_CHECK();
+      }
+      CK(cudaMemcpyAsync(e->hScalar + 8, e->dEdgeOut, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      for (int i = 0; i < nc; ++i) {
+        lnl_out[c0 + i] = e->hScalar[8 + 3 * i];
+        if (d1_out) d1_out[c0 + i] = e->hScalar[8 + 3 * i + 1];
+        if (d2_out) d2_out[c0 + i] = e->hScalar[8 + 3 * i + 2];
+      }
+    }
+  }
+  if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
+}
+
+// Safeguarded Newton on t -> lnL(t) over [t_min, t_max]: the bracket shrinks with the sign of
+// the first derivative; a Newton step that leaves the bracket (or a non-concave point) is
+// replaced by the bracket's geometric mean. Every iteration is one pass over the sum table.
+extern "C" int phylo_lk_optimize_branch(phylo_engine *e, int a_slot, int b_slot, double t0, double t_min, double t_max,
+                                        double tol, int max_iter, double *t_opt, double *lnl_opt, int *iters_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!(t_min > 0.0) || !(t_max > t_min) || !t_opt) return fail(e, PHYLO_ERR_ARG, "lk_optimize_branch: need 0 < t_min < t_max");
+  int rc;
+  if ((rc = phylo_lk_edge_prepare(e, a_slot, b_slot)) != PHYLO_OK) return rc;
+  double lo = t_min, hi = t_max, t = std::min(std::max(t0, t_min), t_max);
+  double glo = 0.0, ghi = 0.0;  // dlnL/dt at the bracket ends once they have been visited
+  bool has_lo = false, has_hi = false;
+  double lnl = 0.0, d1 = 0.0, d2 = 0.0, best_t = t, best_lnl = -INFINITY;
+  int it = 0;
+  if (tol <= 0.0) tol = 1e-8;
+  if (max_iter < 1) max_iter = 50;
+  for (; it < max_iter; ++it) {
+    if ((rc = phylo_lk_edge_eval(e, &t, 1, &lnl, &d1, &d2)) != PHYLO_OK) return rc;
+    if (lnl > best_lnl) { best_lnl = lnl; best_t = t; }
+    if (d1 > 0.0) { lo = t; glo = d1; has_lo = true; } else { hi = t; ghi = d1; has_hi = true; }
+    double next = (d2 < 0.0) ? t - d1 / d2 : -1.0;  // Newton
+    if (!(next > lo && next < hi)) {
+      if (has_lo && has_hi) {  // regula falsi on the derivative, kept off the ends (Illinois-style damping)
+        next = lo - glo * (hi - lo) / (ghi - glo);
+        const double margin = 0.05 * (hi - lo);
+        next = std::min(std::max(next, lo + margin), hi - margin);
+      } else {
+        next = std::sqrt(lo * hi);  // no sign change seen yet: walk the bracket geometrically
+      }
+    }
+    const bool at_bound = (t <= t_min && d1 <= 0.0) || (t >= t_max && d1 >= 0.0);
+    if (at_bound || std::fabs(next - t) <= tol * std::max(t, 1e-8) || hi - lo <= tol * std::max(lo, 1e-8)) { ++it; break; }
+    t = next;
+  }
+  *t_opt = best_t;
+  if (lnl_opt) *lnl_opt = best_lnl;
+  if (iters_out) *iters_out = it;
   return PHYLO_OK;
 }
 

@@ -1,0 +1,164 @@
+// Branch-length loop on one edge (a, b): Likelihood.adjust / distance_1 (lib/nodeData.ml:25-26,
+// :32 -- the reference leaves them TODO, lib/likelihood_c.ml:19-24; MlModel exposes the
+// eigensystem they need, lib/mlModel.ml:53-63, lib/mlmodel.c:325-342).
+//
+// With P_k(t) = UL diag(exp(lam_m r_k t)) UR (UL = U, UR = Ui for GTR; UL = U^T, UR = U for the
+// symmetric path, lib/mlmodel.c:280-302) the site likelihood on the edge is
+//     l(t) = sum_k p_k sum_m c_km exp(lam_m r_k t),
+//     c_km = (sum_i pi_i a_ki UL[i][m]) * (sum_j UR[m][j] b_kj),
+// so ONE pass over the two CLVs builds the "sum table" c (one CLV-sized array) and every
+// further evaluation of lnL(t), dlnL/dt and d2lnL/dt2 -- for several t at once -- streams
+// that single array: K*S*8 bytes per pattern instead of two CLVs and an S x S product.
+//
+// Sums over patterns use the canonical 1024-block fold so shards combine
+// reproducibly. Values agree with root*_kernel to rounding (different association), not bits.
+#pragma once
+#include "common.cuh"
+
+namespace phylo {
+
+// c[p][k][m]; thread = (pattern, rate class). UL, UR staged in shared memory when they fit.
+template <typename MaskT>
+__global__ void __launch_bounds__(128)
+edge_sumtable_kernel(const void *__restrict__ asrc, const int32_t *__restrict__ asc, bool atip,
+                     const void *__restrict__ bsrc, const int32_t *__restrict__ bsc, bool btip,
+                     const double *__restrict__ UL, const double *__restrict__ UR,
+                     const double *__restrict__ pi, int S, int K, int64_t N, int stage,
+                     double *__restrict__ sum, int32_t *__restrict__ sum_sc) {
+  extern __shared__ __align__(16) double esm[];
+  const double *ul = UL, *ur = UR;
+  if (stage) {
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) { esm[i] = UL[i]; esm[S * S + i] = UR[i]; }
+    __syncthreads();
+    ul = esm;
+    ur = esm + S * S;
+  }
+  const int64_t items = N * K;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < items; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = q / K;
+    const int k = (int)(q - p * K);
+    const double *av = atip ? nullptr : (const double *)asrc + q * S;
+    const double *bv = btip ? nullptr : (const double *)bsrc + q * S;
+    const uint64_t am = atip ? (uint64_t)((const MaskT *)asrc)[p] : 0, bm = btip ? (uint64_t)((const MaskT *)bsrc)[p] : 0;
+    double *out = sum + q * S;
+    for (int m = 0; m < S; ++m) {
+      double A = 0.0, B = 0.0;
+      for (int i = 0; i < S; ++i) {
+        const double ai = atip ? (double)((am >> i) & 1) : __ldg(av + i);
+        const double bi = btip ? (double)((bm >> i) & 1) : __ldg(bv + i);
+        A += (pi[i] * ai) * ul[i * S + m];
+        B += ur[m * S + i] * bi;
+      }
+      out[m] = A * B;
+    }
+    if (k == 0) sum_sc[p] = (atip ? 0 : asc[p]) + (btip ? 0 : bsc[p]);
+  }
+}
+
+// Evaluates n_t branch lengths in one launch. coef[(ti*3 + d)*K*S + k*S + m] = p_k (lam_m r_k)^d
+// exp(lam_m r_k t_ti) is built in shared memory by the CTA itself. Per 1024-pattern block and
+// per (ti, d) one canonical partial: part[((ti*3 + d) * nblocks) + blk] with
+//   d=0: sum w ln(site)   d=1: sum w site'/site   d=2: sum w (site''/site - (site'/site)^2).
+template <typename MaskT>
+__global__ void __launch_bounds__(256)
+edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum_sc,
+                 const double *__restrict__ lam, const double *__restrict__ rates,
+                 const double *__restrict__ probs, const double *__restrict__ pi, double pinvar,
+                 const MaskT *__restrict__ inv, const double *__restrict__ weights,
+                 const double *__restrict__ tlen, int n_t, int sym, int S, int K, int64_t N,
+                 double *__restrict__ part) {
+  extern __shared__ __align__(16) double esm[];
+  __shared__ double vals[3][kLnlBlock];
+  __shared__ double wsum[32];
+  double *coef = esm;  // [n_t][3][K*S]
+  const int KS = K * S;
+  for (int i = threadIdx.x; i < n_t * KS; i += blockDim.x) {
+    const int ti = i / KS, km = i - ti * KS, k = km / S, m = km - k * S;
+    double tau = tlen[ti] * rates[k];
+    if (sym) tau = (double)(float)tau;  // compose_sym's `const float t` (lib/mlmodel.c:280)
+    const double g = lam[m] * rates[k];
+    const double e0 = probs[k] * (tau >= 1e-10 ? exp(lam[m] * tau) : 1.0);  // t < 1e-10 -> identity (:339-341)
+    coef[(ti * 3 + 0) * KS + km] = e0;
+    coef[(ti * 3 + 1) * KS + km] = e0 * g;
+    coef[(ti * 3 + 2) * KS + km] = e0 * g * g;
+  }
+  __syncthreads();
+  const int64_t nblocks = (N + kLnlBlock - 1) / kLnlBlock;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    for (int ti = 0; ti < n_t; ++ti) {
+      const double *c0 = coef + (ti * 3) * KS, *c1 = c0 + KS, *c2 = c1 + KS;
+      for (int sub = 0; sub < kLnlBlock / 256; ++sub) {
+        const int64_t p = blk * kLnlBlock + sub * 256 + threadIdx.x;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (p < N) {
+          const double *c = sum + p * KS;
+          double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+          for (int km = 0; km < KS; ++km) {
+            const double x = __ldg(c + km);
+            l0 += x * c0[km];
+            l1 += x * c1[km];
+            l2 += x * c2[km];
+          }
+          const int sc = sum_sc[p];
+          const double w = weights ? weights[p] : 1.0;
+          if (pinvar >= 0.0) {
+            const uint64_t mk = (uint64_t)inv[p];
+            double pv = 0.0;
+            for (int i = 0; i < S; ++i)
+              if ((mk >> i) & 1) pv += pi[i];
+            const double f = (1.0 - pinvar) * ldexp(1.0, -kScaleExp * sc);
+            const double site = f * l0 + pinvar * pv, r1 = f * l1 / site, r2 = f * l2 / site;
+            v0 = w * log(site);
+            v1 = w * r1;
+            v2 = w * (r2 - r1 * r1);
+          } else {
+            const double r1 = l1 / l0, r2 = l2 / l0;
+            v0 = w * (log(l0) - (double)sc * (kScaleExp * 0.6931471805599453094));
+            v1 = w * r1;
+            v2 = w * (r2 - r1 * r1);
+          }
+        }
+        vals[0][sub * 256 + threadIdx.x] = v0;
+        vals[1][sub * 256 + threadIdx.x] = v1;
+        vals[2][sub * 256 + threadIdx.x] = v2;
+      }
+      __syncthreads();
+      for (int d = 0; d < 3; ++d) {
+        const double r = block_fold_1024(vals[d], wsum);
+        if (threadIdx.x == 0) part[(size_t)(ti * 3 + d) * nblocks + blk] = r;
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// one CTA per row: canonical fold of `n` block partials (levels of 1024) into out[row]
+__global__ void __launch_bounds__(256)
+fold_rows_kernel(const double *__restrict__ part, int64_t n, double *__restrict__ out) {
+  __shared__ double vals[kLnlBlock];
+  __shared__ double lvl[kLnlBlock];
+  __shared__ double wsum[32];
+  const double *row = part + (size_t)blockIdx.x * n;
+  // n <= 1024*1024 partials (2^30 patterns): two levels
+  const int64_t nb = (n + kLnlBlock - 1) / kLnlBlock;
+  for (int64_t b = 0; b < nb; ++b) {
+    for (int i = threadIdx.x; i < kLnlBlock; i += blockDim.x) {
+      const int64_t j = b * kLnlBlock + i;
+      vals[i] = j < n ? row[j] : 0.0;
+    }
+    __syncthreads();
+    const double r = block_fold_1024(vals, wsum);
+    if (threadIdx.x == 0) lvl[b] = r;
+    __syncthreads();
+  }
+  if (nb == 1) {
+    if (threadIdx.x == 0) out[blockIdx.x] = lvl[0];
+    return;
+  }
+  for (int i = threadIdx.x; i < kLnlBlock; i += blockDim.x) vals[i] = i < nb ? lvl[i] : 0.0;
+  __syncthreads();
+  const double r = block_fold_1024(vals, wsum);
+  if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+
+}  // namespace phylo

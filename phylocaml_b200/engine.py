@@ -55,6 +55,10 @@ SIGNATURES = {
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
                                            C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
+    "phylo_lk_edge_prepare": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "phylo_lk_edge_eval": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp]),
+    "phylo_lk_optimize_branch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                           C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
     "phylo_lk_get_clv": (C.c_int, [_vp, C.c_int, _dp, _vp]),
     "phylo_lk_get_site_lnl": (C.c_int, [_vp, _dp]),
     "phylo_lk_get_block_partials": (C.c_int, [_vp, _dp, C.POINTER(_i64)]),
@@ -282,6 +286,25 @@ class Engine:
                                                    _p(ops), len(ops), root_a, root_b, float(root_t), C.byref(out)))
         self.lk_shape = (T, N, capacity)
         return out.value
+
+    def lk_edge_prepare(self, a, b):
+        """Sum table of edge (a, b) for the branch-length loop (Likelihood.adjust_3)."""
+        self._ck(self.lib.phylo_lk_edge_prepare(self.h, a, b))
+
+    def lk_edge_eval(self, ts):
+        """lnL(t), dlnL/dt, d2lnL/dt2 of the prepared edge for every t in ts."""
+        ts = _f64(np.atleast_1d(ts))
+        out = np.empty((3, ts.size))
+        self._ck(self.lib.phylo_lk_edge_eval(self.h, _p(ts, _dp), ts.size, _p(out[0], _dp), _p(out[1], _dp),
+                                             _p(out[2], _dp)))
+        return out[0], out[1], out[2]
+
+    def lk_optimize_branch(self, a, b, t0=0.1, t_min=1e-8, t_max=100.0, tol=1e-9, max_iter=50):
+        """Maximum-likelihood length of edge (a, b): (t_opt, lnL(t_opt), iterations)."""
+        t, l, it = C.c_double(), C.c_double(), C.c_int()
+        self._ck(self.lib.phylo_lk_optimize_branch(self.h, a, b, t0, t_min, t_max, tol, max_iter, C.byref(t),
+                                                   C.byref(l), C.byref(it)))
+        return t.value, l.value, it.value
 
     def lk_edge_lnl(self, a, b, ts):
         ts = _f64(np.atleast_1d(ts))

@@ -215,6 +215,67 @@ def test_lk_wide_masks_are_converted(eng, oracle):
     assert eng.lk_score_tree(ops, ra, rb, rt) == a
 
 
+# ------------------------------------------------- branch-length loop (sum table) ----
+def _edge_models():
+    return [
+        ("gtr_g4", dna_gtr_g4(), 12, 3000),
+        ("gtr_g4_pinvar", dna_gtr_g4(pinvar=0.2), 10, 2500),
+        ("jc69_sym", mlmodel.create(("JC69",), 4, site_var=("gamma", 4, 1.0)), 9, 2000),
+        ("aa20", aa_model(), 8, 700),
+        ("codon61", codon_model(), 6, 300),
+    ]
+
+
+@pytest.mark.parametrize("name,model,T,N", _edge_models(), ids=[m[0] for m in _edge_models()])
+def test_lk_edge_sumtable_values_and_derivatives(eng, oracle, name, model, T, N):
+    """phylo_lk_edge_prepare/_eval: lnL(t) from the sum table == the P-based root join
+    (phylo_lk_edge_lnl, <= 1e-12) == the oracle (<= 1e-9); first and second derivatives match
+    central differences of the P-based value."""
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(T, N, model, seed=21, mean_bl=0.2)
+    w = np.random.default_rng(3).integers(1, 5, N).astype(float)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, weights=w, capacity=n_nodes)
+    eng.lk_score_tree(ops, ra, rb, rt)
+    eng.lk_edge_prepare(ra, rb)
+    ts = np.array([1e-6, 0.003, 0.05, 0.2, rt, 0.9, 3.0, 1e-12])
+    lnl, d1, d2 = eng.lk_edge_eval(ts)
+    direct = eng.lk_edge_lnl(ra, rb, ts)
+    assert np.max(np.abs(lnl - direct) / np.abs(direct)) <= 1e-12
+    for t, v in zip(ts[[2, 4]], lnl[[2, 4]]):
+        assert rel_err(v, oracle.lk_score_tree(model, tips, w, ops, n_nodes, ra, rb, float(t))["lnl"]) <= LNL_RTOL
+    # derivatives: 5-point central differences of the sum-table lnL itself (smooth in t)
+    if model["Ui"] is not None:  # the symmetric path rounds t to float (lib/mlmodel.c:280): not differentiable
+        for i in (2, 3, 5):
+            t, h = ts[i], ts[i] * 1e-3
+            f = eng.lk_edge_eval(np.array([t - 2 * h, t - h, t, t + h, t + 2 * h]))[0]
+            fd1 = (f[0] - 8 * f[1] + 8 * f[3] - f[4]) / (12 * h)
+            fd2 = (-f[0] + 16 * f[1] - 30 * f[2] + 16 * f[3] - f[4]) / (12 * h * h)
+            assert abs(d1[i] - fd1) <= 1e-6 * max(1.0, abs(fd1)), (name, t, d1[i], fd1)
+            assert abs(d2[i] - fd2) <= 1e-4 * max(1.0, abs(fd2)), (name, t, d2[i], fd2)
+
+
+def test_lk_optimize_branch_matches_scalar_minimiser(eng, oracle):
+    """Safeguarded Newton on the device sum table finds the same optimum as a bounded scalar
+    minimiser on the P-based edge likelihood; also on a pendant edge (one side is a tip)."""
+    from scipy.optimize import minimize_scalar
+
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(14, 4000, model, seed=8, mean_bl=0.15)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    eng.lk_score_tree(ops, ra, rb, rt)
+    for a, b in ((ra, rb), (int(ops[-1]["left"]), int(ops[-1]["right"]))):
+        t_opt, l_opt, iters = eng.lk_optimize_branch(a, b, t0=0.5, t_min=1e-8, t_max=50.0, tol=1e-10)
+        res = minimize_scalar(lambda t: -eng.lk_edge_lnl(a, b, [t])[0], bounds=(1e-8, 50.0), method="bounded",
+                              options={"xatol": 1e-10})
+        assert iters <= 30
+        assert l_opt >= -res.fun - 1e-9 * abs(res.fun)
+        assert abs(t_opt - res.x) <= 1e-5 * max(res.x, 1e-3), (t_opt, res.x)
+        # first-order optimality from the engine's own derivative
+        _, d1, d2 = eng.lk_edge_eval([t_opt])
+        assert abs(d1[0]) <= 1e-5 * abs(d2[0]) * max(t_opt, 1e-3) + 1e-6
+
+
 # ------------------------------------------------------------------------ Fitch ----
 def _fitch_setup(T, N, n_states, dtype, seed=1):
     tr = tree.random_tree(T, seed)
