@@ -452,6 +452,56 @@ def main():
         set_mode(args.mode)
         step()  # leave the engine's site lnL / CLVs in the primary mode's state
 
+    # ---- branch-length re-evaluation loop (BASELINE config 5's second half):
+    # 50 evaluations of lnL(t) on the root edge as a Brent/Newton driver would issue them (one
+    # length per call: each depends on the previous result), then 10 re-prunes of the path to
+    # the root after one branch changed, all other CLVs staying resident.
+    branch_loop = None
+    if args.workload != "fitch" and args.mode == "fused" and not args.no_other_modes:
+        def timed(fn, reps):
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for i in range(reps):
+                out = fn(i)
+            b1.record()
+            torch.cuda.synchronize()
+            return b0.elapsed_time(b1) / reps, out
+
+        step()  # every interior CLV resident
+        ts = [rt * f for f in np.geomspace(0.05, 20.0, 50)]
+        prep_ms, _ = timed(lambda i: eng.lk_edge_prepare(ra, rb), 3)
+        eval_ms, last = timed(lambda i: eng.lk_edge_eval([ts[i]]), 50)
+        batch_ms, _ = timed(lambda i: eng.lk_edge_eval(ts[:16]), 3)
+        direct_ms, direct = timed(lambda i: eng.lk_edge_lnl(ra, rb, [ts[min(i, 49)]]), 5)
+        opt_ms, opt = timed(lambda i: eng.lk_optimize_branch(ra, rb, t0=rt), 1)
+        # path from a deep op up to the root end
+        parent_of = {int(o["left"]): j for j, o in enumerate(ops)}
+        parent_of.update({int(o["right"]): j for j, o in enumerate(ops)})
+        depth_of = lambda j: 0 if int(ops[j]["parent"]) not in parent_of else 1 + depth_of(parent_of[int(ops[j]["parent"])])
+        i0 = max(range(len(ops)), key=depth_of)
+        path, j = [i0], i0
+        while int(ops[j]["parent"]) in parent_of:
+            j = parent_of[int(ops[j]["parent"])]
+            path.append(j)
+        sub = ops[sorted(path)].copy()
+
+        def reprune(i):
+            sub[0]["t_left"] = float(ops[i0]["t_left"]) * (1.0 + 0.01 * (i + 1))
+            return eng.lk_score_tree(sub, ra, rb, rt)
+
+        rep_ms, rep_lnl = timed(reprune, 10)
+        branch_loop = {
+            "edge": "root edge", "sumtable_prepare_ms": prep_ms, "lnl_d1_d2_eval_ms": eval_ms, "evals": 50,
+            "eval_16_lengths_one_pass_ms": batch_ms, "p_matrix_edge_lnl_ms": direct_ms,
+            "newton_optimize_ms": opt_ms, "newton_iters": opt[2], "t_opt": opt[0],
+            "reprune_path_ops": len(path), "reprune_ms": rep_ms, "reprunes": 10,
+            "loop_total_ms": prep_ms + 50 * eval_ms + 10 * rep_ms,
+            "note": "per-rank times (no allreduce); sum table = one CLV-sized pass per evaluation",
+        }
+        eng.lk_set_tips(tips, capacity=n_nodes)
+        step()  # restore the unmodified tree's state
+
     # ---- CPU baseline + correctness spot check (rank 0, N=1 only)
     cpu, check = None, {"result": result, "result_e2e": result_e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -482,7 +532,7 @@ def main():
                        "collective": "allreduce of one scalar per step" if world > 1 else "none"},
             "mode": args.mode if args.workload != "fitch" else None, "modes": modes,
             "roofline": roof, "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": e2e, "gpu_launches": int(step_launches * args.steps),
+            "e2e": e2e, "branch_loop": branch_loop, "gpu_launches": int(step_launches * args.steps),
             "gpu_launches_total_incl_warmup": int(launches), "clocks": clocks, "check": check,
         }
         print(json.dumps(line))

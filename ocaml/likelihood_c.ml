@@ -20,6 +20,9 @@ external set_model_ : engine -> matrix -> matrix -> matrix option
 external set_tips_ : engine -> masks -> vector option -> int -> unit = "likelihood_CAML_set_tips"
 external median2_ : engine -> int -> (int * float) -> (int * float) -> unit = "likelihood_CAML_median2"
 external edge_lnl_ : engine -> int -> int -> vector -> vector -> unit = "likelihood_CAML_edge_lnl"
+external optimize_branch_ : engine -> int -> int -> (float * float * float * float) -> float * float
+                           = "likelihood_CAML_optimize_branch"
+external edge_eval_ : engine -> int -> int -> vector -> matrix -> unit = "likelihood_CAML_edge_eval"
 external score_tree_ :
   engine -> (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array2.t -> matrix
   -> (int * int * float) -> float = "likelihood_CAML_score_tree"
@@ -74,8 +77,16 @@ let median_n model prev a = function
   | [b] -> median_2 model prev a b
   | _ -> failwith "Likelihood_c.median_n: binary trees only"
 
-let adjust_3 _ _ t _ _ _ = t, IntSet.empty   (* branch optimisation: see SURVEY 8(f) rank 2 *)
-let adjust_n _ _ t _ = t, IntSet.empty
+(* readjust node n (= median of a and b) against its third neighbour c: the branch above n
+   takes its maximum-likelihood length (device sum table + safeguarded Newton). All of n's
+   characters count as changed when the length moved. *)
+let adjust_3 _model _codes n _a _b c =
+  let t, _lnl = optimize_branch_ n.eng n.slot c.slot (n.branch, 1e-8, 100.0, 1e-8) in
+  if abs_float (t -. n.branch) <= 1e-8 *. n.branch then n, IntSet.empty
+  else { n with branch = t; lnl = None }, n.codes
+let adjust_n model codes n = function
+  | [a; b; c] -> adjust_3 model codes n a b c
+  | _ -> n, IntSet.empty
 
 (* root edge (a,b) with length t: -lnL (a cost to minimise) *)
 let distance_1 _model a b =

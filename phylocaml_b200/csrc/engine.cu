@@ -1411,7 +1411,7 @@ extern "C" int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, dou
   const int KS = e->K * e->S;
   for (int t0 = 0; t0 < n_t; t0 += kEdgeMaxT) {
     // as many lengths per pass as the coefficient table allows (<= 48 KB of shared memory)
-    const int per = std::max(1, std::min(kEdgeMaxT, (int)(48 * 1024 / (sizeof(double) * 3 * KS))));
+    const int per = std::max(1, std::min(kEdgeMaxT, (int)(22 * 1024 / (sizeof(double) * 3 * KS))));  // + 24 KB static
     for (int c0 = t0; c0 < std::min(n_t, t0 + kEdgeMaxT); c0 += per) {
       const int nc = std::min(per, std::min(n_t, t0 + kEdgeMaxT) - c0);
       CK(cudaStreamSynchronize(e->stream));  // hT staging
@@ -1421,15 +1421,23 @@ extern "C" int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, dou
       const int g = (int)std::min<int64_t>(e->nPart, (int64_t)e->sm_count * 4);
       {
         ProfScope prof(e, KC_EDGE);
-        if (e->mask_dev_bytes == 1)
-          edge_eval_kernel<uint8_t><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, e->pinvar,
-                                                              (const uint8_t *)e->dInv, e->dWeights, e->dEdgeT, nc, e->sym, e->S, e->K, e->N, e->dEdgePart);
-        else if (e->mask_dev_bytes == 4)
-          edge_eval_kernel<uint32_t><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, e->pinvar,
-                                                               (const uint32_t *)e->dInv, e->dWeights, e->dEdgeT, nc, e->sym, e->S, e->K, e->N, e->dEdgePart);
-        else
-          edge_eval_kernel<uint64_t><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, e->pinvar,
-                                                               (const uint64_t *)e->dInv, e->dWeights, e->dEdgeT, nc, e->sym, e->S, e->K, e->N, e->dEdgePart);
+#define EDGE_EVAL(MT, GV)                                                                                          \
+  edge_eval_kernel<MT, GV><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, \
+                                                         e->pinvar, (const MT *)e->dInv, e->dWeights, e->dEdgeT, nc, \
+                                                         e->sym, e->S, e->K, e->N, e->dEdgePart)
+#define EDGE_EVAL_G(MT)                                                      \
+  {                                                                          \
+    if (KS <= 4) EDGE_EVAL(MT, 1);                                           \
+    else if (KS <= 16) EDGE_EVAL(MT, 4);                                     \
+    else if (KS <= 32) EDGE_EVAL(MT, 8);                                     \
+    else if (KS <= 128) EDGE_EVAL(MT, 16);                                   \
+    else EDGE_EVAL(MT, 32);                                                  \
+  }
+        if (e->mask_dev_bytes == 1) EDGE_EVAL_G(uint8_t)
+        else if (e->mask_dev_bytes == 4) EDGE_EVAL_G(uint32_t)
+        else EDGE_EVAL_G(uint64_t)
+#undef EDGE_EVAL_G
+#undef EDGE_EVAL
         LAUNCH_CHECK();
         fold_rows_kernel<<<3 * nc, 256, 0, e->stream>>>(e->dEdgePart, e->nPart, e->dEdgeOut);
         LAUNCH_CHECK();

@@ -59,7 +59,10 @@ edge_sumtable_kernel(const void *__restrict__ asrc, const int32_t *__restrict__ 
 // exp(lam_m r_k t_ti) is built in shared memory by the CTA itself. Per 1024-pattern block and
 // per (ti, d) one canonical partial: part[((ti*3 + d) * nblocks) + blk] with
 //   d=0: sum w ln(site)   d=1: sum w site'/site   d=2: sum w (site''/site - (site'/site)^2).
-template <typename MaskT>
+// G lanes share a pattern (G = 4 for DNA+G4: each lane one 32-byte chunk; 16 for 20 states x 4
+// classes; 32 for codons): consecutive lanes read consecutive doubles of the sum table, so a
+// warp request is one contiguous run, and the three sums are combined by xor-shuffles.
+template <typename MaskT, int G>
 __global__ void __launch_bounds__(256)
 edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum_sc,
                  const double *__restrict__ lam, const double *__restrict__ rates,
@@ -83,29 +86,52 @@ edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum
     coef[(ti * 3 + 2) * KS + km] = e0 * g * g;
   }
   __syncthreads();
+  constexpr int PPB = 256 / G;  // patterns per pass of the CTA
+  const int sub_lane = threadIdx.x % G, grp = threadIdx.x / G;
   const int64_t nblocks = (N + kLnlBlock - 1) / kLnlBlock;
   for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     for (int ti = 0; ti < n_t; ++ti) {
       const double *c0 = coef + (ti * 3) * KS, *c1 = c0 + KS, *c2 = c1 + KS;
-      for (int sub = 0; sub < kLnlBlock / 256; ++sub) {
-        const int64_t p = blk * kLnlBlock + sub * 256 + threadIdx.x;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      // phase 1: the three sums of every pattern of the block, G lanes per pattern
+#pragma unroll 4
+      for (int sub = 0; sub < kLnlBlock / PPB; ++sub) {
+        const int64_t p = blk * kLnlBlock + sub * PPB + grp;
+        double l0 = 0.0, l1 = 0.0, l2 = 0.0;
         if (p < N) {
           const double *c = sum + p * KS;
-          double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-          for (int km = 0; km < KS; ++km) {
+          for (int km = sub_lane; km < KS; km += G) {
             const double x = __ldg(c + km);
             l0 += x * c0[km];
             l1 += x * c1[km];
             l2 += x * c2[km];
           }
+        }
+#pragma unroll
+        for (int off = G / 2; off >= 1; off >>= 1) {
+          l0 += __shfl_xor_sync(0xffffffffu, l0, off);
+          l1 += __shfl_xor_sync(0xffffffffu, l1, off);
+          l2 += __shfl_xor_sync(0xffffffffu, l2, off);
+        }
+        if (sub_lane == 0) {
+          vals[0][sub * PPB + grp] = l0;
+          vals[1][sub * PPB + grp] = l1;
+          vals[2][sub * PPB + grp] = l2;
+        }
+      }
+      __syncthreads();
+      // phase 2: one thread per pattern turns the sums into weighted ln / derivative terms
+      for (int i = threadIdx.x; i < kLnlBlock; i += 256) {
+        const int64_t p = blk * kLnlBlock + i;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (p < N) {
+          const double l0 = vals[0][i], l1 = vals[1][i], l2 = vals[2][i];
           const int sc = sum_sc[p];
           const double w = weights ? weights[p] : 1.0;
           if (pinvar >= 0.0) {
             const uint64_t mk = (uint64_t)inv[p];
             double pv = 0.0;
-            for (int i = 0; i < S; ++i)
-              if ((mk >> i) & 1) pv += pi[i];
+            for (int s = 0; s < S; ++s)
+              if ((mk >> s) & 1) pv += pi[s];
             const double f = (1.0 - pinvar) * ldexp(1.0, -kScaleExp * sc);
             const double site = f * l0 + pinvar * pv, r1 = f * l1 / site, r2 = f * l2 / site;
             v0 = w * log(site);
@@ -118,9 +144,9 @@ edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum
             v2 = w * (r2 - r1 * r1);
           }
         }
-        vals[0][sub * 256 + threadIdx.x] = v0;
-        vals[1][sub * 256 + threadIdx.x] = v1;
-        vals[2][sub * 256 + threadIdx.x] = v2;
+        vals[0][i] = v0;
+        vals[1][i] = v1;
+        vals[2][i] = v2;
       }
       __syncthreads();
       for (int d = 0; d < 3; ++d) {

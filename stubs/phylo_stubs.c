@@ -211,6 +211,44 @@ CAMLprim value likelihood_CAML_edge_lnl(value ve, value va, value vb, value ts, 
   CAMLreturn(Val_unit);
 }
 
+/* external optimize_branch : engine -> int -> int -> (float * float * float * float) -> float * float
+ * (t0, t_min, t_max, tol) -> (t_opt, lnL): Likelihood_c.adjust_3 (lib/nodeData.ml:25; TODO in
+ * lib/likelihood_c.ml:19) -- maximum-likelihood length of the edge between two directed CLVs */
+CAMLprim value likelihood_CAML_optimize_branch(value ve, value va, value vb, value par)
+{
+  CAMLparam4(ve, va, vb, par);
+  CAMLlocal1(res);
+  phylo_engine *e = Engine_val(ve);
+  int rc, iters = 0, a = Int_val(va), b = Int_val(vb);
+  double t0 = Double_val(Field(par, 0)), tmin = Double_val(Field(par, 1)), tmax = Double_val(Field(par, 2));
+  double tol = Double_val(Field(par, 3)), t = 0.0, lnl = 0.0;
+  caml_release_runtime_system();
+  rc = phylo_lk_optimize_branch(e, a, b, t0, tmin, tmax, tol, 50, &t, &lnl, &iters);
+  caml_acquire_runtime_system();
+  check(e, rc);
+  res = caml_alloc_tuple(2);
+  Store_field(res, 0, caml_copy_double(t));
+  Store_field(res, 1, caml_copy_double(lnl));
+  CAMLreturn(res);
+}
+
+/* external edge_eval : engine -> int -> int -> vector (lengths) -> matrix (3 x n: lnL, d1, d2) -> unit
+ * sum table of the edge, then lnL and its derivatives for a batch of lengths */
+CAMLprim value likelihood_CAML_edge_eval(value ve, value va, value vb, value ts, value out)
+{
+  CAMLparam5(ve, va, vb, ts, out);
+  phylo_engine *e = Engine_val(ve);
+  int rc, n = (int)Bigarray_val(ts)->dim[0], a = Int_val(va), b = Int_val(vb);
+  const double *t = (const double *)Data_bigarray_val(ts);
+  double *o = (double *)Data_bigarray_val(out);
+  caml_release_runtime_system();
+  rc = phylo_lk_edge_prepare(e, a, b);
+  if (rc == PHYLO_OK) rc = phylo_lk_edge_eval(e, t, n, o, o + n, o + 2 * n);
+  caml_acquire_runtime_system();
+  check(e, rc);
+  CAMLreturn(Val_unit);
+}
+
 /* external get_clv : engine -> int -> (float, float64_elt, c_layout) Array3.t -> unit */
 CAMLprim value likelihood_CAML_get_clv(value ve, value vnode, value out)
 {
