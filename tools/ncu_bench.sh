@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 W=${1:-dna}
 P=${2:-1000000}
 shift 2
-CMD="python bench.py --workload $W --patterns $P --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 1"
+CMD="python bench.py --workload $W --patterns $P --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 1 --no-other-modes"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$W.csv \
     $CMD > gpurun_out/ncu_bench_$W.log 2>&1
 for K in "$@"; do
