@@ -704,11 +704,19 @@ static bool launch_prune_mma(phylo_engine *e, const double *Pl, const double *Pr
   constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4;
   const size_t smem = sizeof(double) * 2 * (size_t)e->K * MT * KS * 32;
   if (smem > 200 * 1024) return false;
-  auto kern = prune_mma_kernel<S, MaskT>;
-  *st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (*st != cudaSuccess) return true;
-  const int g = resident_grid(e, kern, 256, smem, (e->N + 63) / 64);
-  kern<<<g, 256, smem, e->stream>>>(Pl, Pr, l.src, l.scale, l.tip, r.src, r.scale, r.tip, out, osc, e->N, e->K);
+#define MMA_LAUNCH(LT, RT)                                                                              \
+  {                                                                                                     \
+    auto kern = prune_mma_kernel<S, MaskT, LT, RT>;                                                     \
+    *st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    if (*st != cudaSuccess) return true;                                                                \
+    const int g = resident_grid(e, kern, 256, smem, (e->N + 63) / 64);                                  \
+    kern<<<g, 256, smem, e->stream>>>(Pl, Pr, l.src, l.scale, r.src, r.scale, out, osc, e->N, e->K);    \
+  }
+  if (l.tip && r.tip) MMA_LAUNCH(true, true)
+  else if (l.tip) MMA_LAUNCH(true, false)
+  else if (r.tip) MMA_LAUNCH(false, true)
+  else MMA_LAUNCH(false, false)
+#undef MMA_LAUNCH
   return true;
 }
 

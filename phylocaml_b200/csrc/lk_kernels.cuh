@@ -575,12 +575,15 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-template <int S, typename MaskT>
+// LT / RT: the side is a tip (compile-time, so the inner+inner instance carries none of the
+// tip code: with run-time flags its main loop lost 20 % to register pressure).
+template <int S, typename MaskT, bool LT, bool RT>
 __global__ void __launch_bounds__(256)
 prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
-                 const void *__restrict__ lsrc, const int32_t *__restrict__ lsc, bool ltip,
-                 const void *__restrict__ rsrc, const int32_t *__restrict__ rsc, bool rtip,
+                 const void *__restrict__ lsrc, const int32_t *__restrict__ lsc,
+                 const void *__restrict__ rsrc, const int32_t *__restrict__ rsc,
                  double *__restrict__ out, int32_t *__restrict__ osc, int64_t N, int K) {
+  constexpr bool ltip = LT, rtip = RT;
   constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4;
   extern __shared__ __align__(16) double frag[];  // [2][K][MT][KS][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -610,6 +613,24 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
     MaskT ml = 0, mr = 0;
     if (ltip && pb_ok) ml = lmask[pb];
     if (rtip && pb_ok) mr = rmask[pb];
+    // One-hot tips (the usual case: an observed state): P L is column j of P, taken straight
+    // from the A-fragment table -- no DMMA for that side. 0/1 products and additions of +0 are
+    // exact, so the values are those of the DMMA path bit for bit. Decided per warp.
+    const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
+    const bool lhot = ltip && __all_sync(0xffffffffu, !pb_ok || ((ml & keep) & ((ml & keep) - 1)) == 0);
+    const bool rhot = rtip && __all_sync(0xffffffffu, !pb_ok || ((mr & keep) & ((mr & keep) - 1)) == 0);
+    int jl0 = 0, jl1 = 0, jr0 = 0, jr1 = 0;  // state of the tip for this lane's two result patterns
+    if (lhot) {
+      jl0 = pa0_ok ? __ffsll((long long)(lmask[pa0] & keep)) - 1 : 0;
+      jl1 = pa1_ok ? __ffsll((long long)(lmask[pa0 + 1] & keep)) - 1 : 0;
+    }
+    if (rhot) {
+      jr0 = pa0_ok ? __ffsll((long long)(rmask[pa0] & keep)) - 1 : 0;
+      jr1 = pa1_ok ? __ffsll((long long)(rmask[pa0 + 1] & keep)) - 1 : 0;
+    }
+    // element (i, j) of a fragment table: [mt = i/8][ks = j/4][lane = (i%8)*4 + j%4]
+    const int col_l0 = (jl0 >> 2) * 32 + fr * 4 + (jl0 & 3), col_l1 = (jl1 >> 2) * 32 + fr * 4 + (jl1 & 3);
+    const int col_r0 = (jr0 >> 2) * 32 + fr * 4 + (jr0 & 3), col_r1 = (jr1 >> 2) * 32 + fr * 4 + (jr1 & 3);
     int h0 = (int)0x80000000, h1 = (int)0x80000000;
     for (int k = 0; k < K; ++k) {
       double bl[KS], br[KS];
@@ -622,14 +643,24 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
         if (rtip) br[ks] = (ok && ((mr >> j) & 1)) ? 1.0 : 0.0;
         else br[ks] = ok ? rclv[((size_t)pb * K + k) * S + j] : 0.0;
       }
-      const double *flk = fl + (size_t)k * MT * KS * 32 + lane, *frk = frg + (size_t)k * MT * KS * 32 + lane;
+      const double *flk0 = fl + (size_t)k * MT * KS * 32, *frk0 = frg + (size_t)k * MT * KS * 32;
+      const double *flk = flk0 + lane, *frk = frk0 + lane;
 #pragma unroll 2
       for (int mt = 0; mt < MT; ++mt) {
         double cx[2] = {0.0, 0.0}, cy[2] = {0.0, 0.0};
+        if (lhot) {
+          cx[0] = flk0[mt * KS * 32 + col_l0];
+          cx[1] = flk0[mt * KS * 32 + col_l1];
+        } else {
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          dmma_8x8x4(cx, flk[(mt * KS + ks) * 32], bl[ks]);
-          dmma_8x8x4(cy, frk[(mt * KS + ks) * 32], br[ks]);
+          for (int ks = 0; ks < KS; ++ks) dmma_8x8x4(cx, flk[(mt * KS + ks) * 32], bl[ks]);
+        }
+        if (rhot) {
+          cy[0] = frk0[mt * KS * 32 + col_r0];
+          cy[1] = frk0[mt * KS * 32 + col_r1];
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) dmma_8x8x4(cy, frk[(mt * KS + ks) * 32], br[ks]);
         }
         const int i = mt * 8 + fr;
         if (i < S) {
