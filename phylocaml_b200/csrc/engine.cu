@@ -100,7 +100,7 @@ struct phylo_engine {
   double *dP = nullptr;  // transition matrices [branch][K][S][S]
   size_t capP = 0;       // branches
   double *dT = nullptr, *hT = nullptr;  // branch lengths (device / pinned)
-  double *dSite = nullptr;
+  double *dSite = nullptr, *dWSite = nullptr;
   // branch-length loop (lk_edge_kernels.cuh): eigenvector matrices in the orientation the sum table needs,
   // the sum table of the prepared edge, per-(t, derivative) block partials
   double *dUL = nullptr, *dUR = nullptr, *dSum = nullptr, *dEdgePart = nullptr, *dEdgeOut = nullptr, *dEdgeT = nullptr;
@@ -271,6 +271,7 @@ static void lk_free_data(phylo_engine *e) {
   dfree(e->dInv);
   dfree(e->dWeights);
   dfree(e->dSite);
+  dfree(e->dWSite);
   dfree(e->dPart);
   dfree(e->dGroups);
   dfree(e->dPart2);
@@ -774,6 +775,35 @@ static cudaError_t launch_root_any(phylo_engine *e, const double *Pr, const Oper
   return cudaSuccess;
 }
 
+// fp64 tensor-core root join for S = 20 / 61 (root_mma_kernel): site values first, then the
+// canonical fold over them; returns false when the fragments do not fit in shared memory
+template <int S, typename MaskT>
+static bool launch_root_mma(phylo_engine *e, const double *Pr, const Operand &a, const Operand &b, cudaError_t *st) {
+  constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4;
+  const size_t smem = sizeof(double) * ((size_t)e->K * MT * KS * 32 + S);
+  if (smem > 200 * 1024) return false;
+  if (!e->dWSite) {
+    *st = cudaMalloc(&e->dWSite, sizeof(double) * (size_t)e->N);
+    if (*st != cudaSuccess) return true;
+  }
+#define ROOT_MMA(AT, BT)                                                                                        \
+  {                                                                                                             \
+    auto kern = root_mma_kernel<S, MaskT, AT, BT>;                                                              \
+    *st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
+    if (*st != cudaSuccess) return true;                                                                        \
+    const int g = resident_grid(e, kern, 256, smem, (e->N + 63) / 64);                                          \
+    kern<<<g, 256, smem, e->stream>>>(Pr, e->dPi, e->dProbs, e->pinvar, (const MaskT *)e->dInv, a.src, a.scale, \
+                                      b.src, b.scale, e->dWeights, e->dSite, e->dWSite, e->N, e->K);            \
+  }
+  if (a.tip && b.tip) ROOT_MMA(true, true)
+  else if (a.tip) ROOT_MMA(true, false)
+  else if (b.tip) ROOT_MMA(false, true)
+  else ROOT_MMA(false, false)
+#undef ROOT_MMA
+  *st = cudaSuccess;
+  return true;
+}
+
 // root-edge join with transition matrices Pr ([K][S][S] on device) -> *lnl_host (pinned slot)
 static int lk_root_eval(phylo_engine *e, const double *Pr, const Operand &a, const Operand &b, double *slot) {
   {
@@ -788,7 +818,16 @@ static int lk_root_eval(phylo_engine *e, const double *Pr, const Operand &a, con
     }
   } else {
     cudaError_t st;
-    if (e->S == 20) st = launch_root_any<20, uint32_t>(e, Pr, a, b);
+    bool mma = false;
+    if (e->S == 20) mma = launch_root_mma<20, uint32_t>(e, Pr, a, b, &st);
+    else if (e->S == 61) mma = launch_root_mma<61, uint64_t>(e, Pr, a, b, &st);
+    if (mma) {
+      if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "root_mma setup: %s", cudaGetErrorString(st));
+      LAUNCH_CHECK();
+      // level 1 of the canonical fold: the weighted site values -> per-1024-block partials
+      reduce1024_kernel<<<(int)e->nPart, 256, 0, e->stream>>>(e->dWSite, e->N, e->dPart);
+    }
+    else if (e->S == 20) st = launch_root_any<20, uint32_t>(e, Pr, a, b);
     else if (e->S == 61) st = launch_root_any<61, uint64_t>(e, Pr, a, b);
     else if (e->mask_dev_bytes == 1) st = launch_root_any<0, uint8_t>(e, Pr, a, b);
     else if (e->mask_dev_bytes == 4) st = launch_root_any<0, uint32_t>(e, Pr, a, b);

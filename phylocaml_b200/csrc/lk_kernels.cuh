@@ -694,6 +694,128 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
   }
 }
 
+// ------------------------------------------ 20/61-state root-edge join on fp64 tensor cores ----
+// Site values of the root edge with the fragment machinery of prune_mma_kernel: Y = P b by
+// DMMA (or a column lookup for a one-hot tip), l = sum_k p_k sum_i (pi_i a_ki) Y_ki with the
+// row sum folded across the 8 row groups by xor-shuffles. A warp owns 8 patterns, so the
+// grid is as wide as the alignment (root_any_kernel ties one CTA to each 1024-pattern block:
+// 196 CTAs of 128 threads for 200 k codon patterns). Weighted site ln-likelihoods go to
+// `wsite`; the canonical fold runs over that array afterwards (reduce1024_kernel).
+template <int S, typename MaskT, bool AT, bool BT>
+__global__ void __launch_bounds__(256)
+root_mma_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
+                const double *__restrict__ probs, double pinvar, const MaskT *__restrict__ inv,
+                const void *__restrict__ asrc, const int32_t *__restrict__ asc,
+                const void *__restrict__ bsrc, const int32_t *__restrict__ bsc,
+                const double *__restrict__ weights, double *__restrict__ site_lnl,
+                double *__restrict__ wsite, int64_t N, int K) {
+  constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4;
+  extern __shared__ __align__(16) double frag[];  // [K][MT][KS][32] + pi[S]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const size_t side = (size_t)K * MT * KS * 32;
+  double *spi = frag + side;
+  for (size_t idx = threadIdx.x; idx < side; idx += blockDim.x) {
+    const int l = (int)(idx & 31);
+    size_t rest = idx >> 5;
+    const int ks = (int)(rest % KS); rest /= KS;
+    const int mt = (int)(rest % MT); rest /= MT;
+    const int k = (int)rest;
+    const int i = mt * 8 + (l >> 2), j = ks * 4 + (l & 3);
+    frag[idx] = (i < S && j < S) ? Proot[((size_t)k * S + i) * S + j] : 0.0;
+  }
+  for (int i = threadIdx.x; i < S; i += blockDim.x) spi[i] = pi[i];
+  __syncthreads();
+  const double *aclv = (const double *)asrc, *bclv = (const double *)bsrc;
+  const MaskT *amask = (const MaskT *)asrc, *bmask = (const MaskT *)bsrc;
+  const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
+
+  const int64_t ngroups = (N + 7) / 8;
+  for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < ngroups; g += (int64_t)gridDim.x * nwarps) {
+    const int64_t pb = g * 8 + fr, pa0 = g * 8 + 2 * fc;
+    const bool pb_ok = pb < N, pa0_ok = pa0 < N, pa1_ok = pa0 + 1 < N;
+    MaskT mb = 0, ma0 = 0, ma1 = 0;
+    if (BT && pb_ok) mb = bmask[pb];
+    if (AT) {
+      if (pa0_ok) ma0 = amask[pa0];
+      if (pa1_ok) ma1 = amask[pa0 + 1];
+    }
+    const bool bhot = BT && __all_sync(0xffffffffu, !pb_ok || ((mb & keep) & ((mb & keep) - 1)) == 0);
+    int jb0 = 0, jb1 = 0;
+    if (bhot) {
+      jb0 = pa0_ok ? __ffsll((long long)(bmask[pa0] & keep)) - 1 : 0;
+      jb1 = pa1_ok ? __ffsll((long long)(bmask[pa0 + 1] & keep)) - 1 : 0;
+    }
+    const int col_b0 = (jb0 >> 2) * 32 + fr * 4 + (jb0 & 3), col_b1 = (jb1 >> 2) * 32 + fr * 4 + (jb1 & 3);
+    double l0 = 0.0, l1 = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double bb[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int j = ks * 4 + fc;
+        const bool ok = pb_ok && j < S;
+        if (BT) bb[ks] = (ok && ((mb >> j) & 1)) ? 1.0 : 0.0;
+        else bb[ks] = ok ? bclv[((size_t)pb * K + k) * S + j] : 0.0;
+      }
+      const double *fk0 = frag + (size_t)k * MT * KS * 32, *fk = fk0 + lane;
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 2
+      for (int mt = 0; mt < MT; ++mt) {
+        double cy[2] = {0.0, 0.0};
+        if (bhot) {
+          cy[0] = fk0[mt * KS * 32 + col_b0];
+          cy[1] = fk0[mt * KS * 32 + col_b1];
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) dmma_8x8x4(cy, fk[(mt * KS + ks) * 32], bb[ks]);
+        }
+        const int i = mt * 8 + fr;
+        if (i < S) {
+          double a0, a1;
+          if (AT) {
+            a0 = (double)((ma0 >> i) & 1);
+            a1 = (double)((ma1 >> i) & 1);
+          } else {
+            a0 = pa0_ok ? aclv[((size_t)pa0 * K + k) * S + i] : 0.0;
+            a1 = pa1_ok ? aclv[((size_t)(pa0 + 1) * K + k) * S + i] : 0.0;
+          }
+          acc0 += (spi[i] * a0) * cy[0];
+          acc1 += (spi[i] * a1) * cy[1];
+        }
+      }
+#pragma unroll
+      for (int off = 4; off <= 16; off <<= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+      }
+      l0 += probs[k] * acc0;
+      l1 += probs[k] * acc1;
+    }
+    if (fr == 0) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t p = pa0 + u;
+        if (p < N) {
+          const double l = u ? l1 : l0;
+          const int c = (AT ? 0 : asc[p]) + (BT ? 0 : bsc[p]);
+          double lnl;
+          if (pinvar >= 0.0) {
+            const MaskT m = inv[p];
+            double pv = 0.0;
+            for (int i = 0; i < S; ++i)
+              if ((m >> i) & 1) pv += spi[i];
+            lnl = log((1.0 - pinvar) * ldexp(l, -kScaleExp * c) + pinvar * pv);
+          } else {
+            lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
+          }
+          if (site_lnl) site_lnl[p] = lnl;
+          wsite[p] = (weights ? weights[p] : 1.0) * lnl;
+        }
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------- tip preparation ----
 // Converts raw tip masks of any element width to the device width (rows padded to
 // out_stride elements so bulk-TMA tile loads stay aligned and in bounds), masks off bits >= S,
