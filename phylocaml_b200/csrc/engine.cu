@@ -1859,10 +1859,10 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   std::vector<int> produced(e->fcap, -1), in_index(e->fcap, -1), inputs;
   struct Raw { int l, r, out_slot; };
   std::vector<Raw> raw(n_tot);
-  auto operand = [&](int slot) {
+  auto operand = [&](int slot) {  // every use of a resident set gets its own table row (results overwrite rows)
     if (produced[slot] >= 0) return -1 - produced[slot];
-    if (in_index[slot] < 0) { in_index[slot] = (int)inputs.size(); inputs.push_back(slot); }
-    return in_index[slot];
+    inputs.push_back(slot);
+    return (int)inputs.size() - 1;
   };
   std::vector<int> size(n_tot, 1), consumer(n_tot, -1);
   for (int o = 0; o < n_tot; ++o) {
@@ -1879,7 +1879,7 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   }
   const int n_in = (int)inputs.size();
   const bool weighted = e->dFW != nullptr;
-  const size_t smem = (size_t)(n_in + n_tot) * 512 + (size_t)(n_tot + 1) * (sizeof(FitchTileOp) + (weighted ? 256 : 128)) +
+  const size_t smem = (size_t)n_in * 512 + (size_t)(n_tot + 4) * (sizeof(FitchTileOp) + (weighted ? 256 : 64)) +
                       (size_t)n_in * 8;
   if (smem > 200 * 1024) return PHYLO_OK;
   // Cut the forest into whole subtrees of at most `cap` medians (phase 1, dealt to the warps,
@@ -1919,19 +1919,24 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     CK(cudaStreamSynchronize(e->stream));
     dfree(e->dAcc);
     e->capAcc = 0;
-    CK(cudaMalloc(&e->dAcc, sizeof(unsigned long long) * ((size_t)n_tot + 2) * 2));
-    CK(cudaMemset(e->dAcc, 0, sizeof(unsigned long long) * ((size_t)n_tot + 2) * 2));
-    e->capAcc = ((size_t)n_tot + 2) * 2;
+    const size_t cap = ((size_t)n_tot + 2) * 2;
+    CK(cudaMalloc(&e->dAcc, sizeof(unsigned long long) * cap * kFitchAccCopies));
+    CK(cudaMemset(e->dAcc, 0, sizeof(unsigned long long) * cap * kFitchAccCopies));
+    e->capAcc = cap;
   }
   CK(cudaStreamSynchronize(e->stream));  // pinned staging is about to be rewritten
   char *hb = (char *)e->hSched;
   FitchTileOp *hops = (FitchTileOp *)hb;
   const uint32_t **hin = (const uint32_t **)(hb + sizeof(FitchTileOp) * n_tot);
   int *hlev = (int *)(hb + sizeof(FitchTileOp) * n_tot + 8 * (size_t)n_in);
+  std::vector<int> res_row(n_tot, -1);  // table row holding op o's result (schedule order: producers first)
+  auto row_of = [&](int c) { return c >= 0 ? c : res_row[-1 - c]; };
+  for (int o = 0; o < n_tot; ++o) res_row[o] = row_of(raw[o].l);
   for (int i = 0; i < n_tot; ++i) {
     const Raw &rw = raw[order[i]];
-    hops[i].l_off = 512u * (uint32_t)(rw.l >= 0 ? rw.l : n_in + pos[-1 - rw.l]);
-    hops[i].r_off = 512u * (uint32_t)(rw.r >= 0 ? rw.r : n_in + pos[-1 - rw.r]);
+    // rows: an input use has its own row; a result lives in the row of its producer's left operand
+    hops[i].l_off = 512u * (uint32_t)row_of(rw.l);
+    hops[i].r_off = 512u * (uint32_t)row_of(rw.r);
     hops[i].out = rw.out_slot >= 0 ? e->fPre[rw.out_slot] : nullptr;
   }
   for (int i = 0; i < n_in; ++i) hin[i] = e->fPre[inputs[i]];
@@ -1948,7 +1953,7 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   CK(cudaHostGetDevicePointer((void **)&a.host_out, e->hCost, 0));
   {
     ProfScope prof(e, KC_FITCH_TREE);
-    auto kern = weighted ? fitch_tile_kernel<unsigned long long> : fitch_tile_kernel<uint32_t>;
+    auto kern = weighted ? fitch_tile_kernel<unsigned long long> : fitch_tile_kernel<uint16_t>;
     if (e->tileSmem != smem || e->tileWeighted != weighted) {  // attribute + occupancy are looked up once per program shape
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       int q = 1;
@@ -1961,6 +1966,7 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     const int64_t ntiles = (e->fWords + 31) / 32, maxg = (int64_t)e->sm_count * e->tileOcc;
     const int64_t waves = (ntiles + maxg - 1) / maxg;
     const int g = (int)((ntiles + waves - 1) / waves);
+    if (!weighted && waves > 2000) return PHYLO_OK;  // 16-bit per-lane counters: the other kernels take it
     kern<<<g, 256, smem, e->stream>>>(a);
     LAUNCH_CHECK();
   }

@@ -318,8 +318,9 @@ fitch_treep_kernel(const FitchInstr *__restrict__ prog, int n_steps, int depth, 
 // The last CTA to finish publishes the per-op costs and the length straight into mapped
 // host memory and re-zeroes the accumulators: one kernel launch is the whole call.
 constexpr int kFitchTileWarps = 8;
+constexpr int kFitchAccCopies = 16;  // CTAs spread their atomics over this many accumulator sets (L2 serialises same-address atomics)
 struct __align__(16) FitchTileOp {
-  uint32_t l_off, r_off;  // byte offsets of the operands' rows in the tile table (inputs first, then op results)
+  uint32_t l_off, r_off;  // byte offsets of the operands' rows in the tile table; the result replaces the left row
   uint32_t *out;          // parent set in HBM, or NULL (root-edge join)
 };
 struct FitchTileArgs {
@@ -329,21 +330,24 @@ struct FitchTileArgs {
   int n_in, n_ops;
   int64_t nwords, N;
   const uint32_t *wt;
-  unsigned long long *acc;         // [n_ops + 2]: per-op costs, total, CTA counter (all zero between calls)
+  unsigned long long *acc;         // [kFitchAccCopies][n_ops + 2]: per-op costs, total, CTA counter (all zero between calls)
   unsigned long long *host_out;    // mapped host memory [n_ops + 1]: per-op costs, total
 };
 
-// CNT = uint32_t (unweighted: <= 32 per tile and op) or unsigned long long (weighted)
+// Every operand is consumed exactly once (the host checks the schedule is a forest and gives
+// every use of an input its own row), so a median is written over its left operand: the table
+// holds only the n_in input rows (T x 512 bytes for a whole tree), 6 CTAs per SM for 64 taxa.
+// CNT = uint16_t (unweighted: <= 32 per tile and op, <= 2047 tiles per CTA) or unsigned long long (weighted)
 template <typename CNT>
 __global__ void __launch_bounds__(256)
 fitch_tile_kernel(const FitchTileArgs a) {
   extern __shared__ __align__(16) unsigned char tsm[];
-  unsigned char *table = tsm;                                                              // [n_in + n_ops][32] uint4
-  FitchTileOp *sops = reinterpret_cast<FitchTileOp *>(table + (size_t)(a.n_in + a.n_ops) * 512);  // [n_ops]
+  unsigned char *table = tsm;                                                              // [n_in][32] uint4
+  FitchTileOp *sops = reinterpret_cast<FitchTileOp *>(table + (size_t)a.n_in * 512);       // [n_ops]
   // per-lane cost counters [n_ops][32]: plain read-modify-write by the owning lane -- no warp
   // reduction and no atomics on the per-level critical path (an op always maps to one warp)
   CNT *sh_cnt = reinterpret_cast<CNT *>(sops + a.n_ops);
-  const uint32_t **sin = reinterpret_cast<const uint32_t **>(sh_cnt + (size_t)(a.n_ops + (a.n_ops & 1)) * 32);  // [n_in]
+  const uint32_t **sin = reinterpret_cast<const uint32_t **>(sh_cnt + (size_t)((a.n_ops + 3) & ~3) * 32);  // [n_in]
   __shared__ bool is_last;
   __shared__ int stask[kFitchTileWarps + 2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFitchTileWarps;
@@ -354,7 +358,6 @@ fitch_tile_kernel(const FitchTileArgs a) {
   __syncthreads();
   const int64_t ntiles = (a.nwords + 31) / 32;
   unsigned char *mine = table + lane * 16;                 // this lane's column inside any table row
-  unsigned char *res0 = mine + (size_t)a.n_in * 512;       // ... inside op 0's result row
   const int p1_lo = stask[warp], p1_hi = stask[warp + 1], p2_lo = stask[kFitchTileWarps], p2_hi = stask[kFitchTileWarps + 1];
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t w = tile * 32 + lane;  // buffers are padded to whole tiles: always in bounds
@@ -375,7 +378,7 @@ fitch_tile_kernel(const FitchTileArgs a) {
         pb.v[0] = ub.x; pb.v[1] = ub.y; pb.v[2] = ub.z; pb.v[3] = ub.w;
         const uint32_t chg = fitch_rule<4>(pa, pb, pc) & valid;
         const uint4 uc = make_uint4(pc.v[0], pc.v[1], pc.v[2], pc.v[3]);
-        *reinterpret_cast<uint4 *>(res0 + o * 512) = uc;
+        *reinterpret_cast<uint4 *>(mine + op.l_off) = uc;
         if (op.out != nullptr) *reinterpret_cast<uint4 *>(op.out + w * 4) = uc;
         if (sizeof(CNT) == 8) sh_cnt[o * 32 + lane] += (CNT)weighted_cost(chg, w, a.wt);
         else sh_cnt[o * 32 + lane] += (CNT)__popc(chg);
@@ -388,6 +391,7 @@ fitch_tile_kernel(const FitchTileArgs a) {
     __syncthreads();  // the table is rewritten by the next tile's inputs
   }
   // per-op totals: one warp per op folds its 32 lane counters
+  unsigned long long *acc = a.acc + (size_t)(blockIdx.x % kFitchAccCopies) * (a.n_ops + 2);
   unsigned long long t = 0;
   for (int o = warp; o < a.n_ops; o += nwarps) {
     unsigned long long c;
@@ -399,11 +403,11 @@ fitch_tile_kernel(const FitchTileArgs a) {
       c = __reduce_add_sync(0xffffffffu, (unsigned)sh_cnt[o * 32 + lane]);
     }
     if (lane == 0 && c) {
-      atomicAdd(&a.acc[o], c);
+      atomicAdd(&acc[o], c);
       t += c;
     }
   }
-  if (lane == 0 && t) atomicAdd(&a.acc[a.n_ops], t);
+  if (lane == 0 && t) atomicAdd(&acc[a.n_ops], t);
   // ---- last CTA publishes to mapped host memory and restores the all-zero invariant.
   // bar.sync orders the CTA's atomics before thread 0's fence + counter increment
   // (cumulativity), so only one thread pays for the fence.
@@ -416,8 +420,13 @@ fitch_tile_kernel(const FitchTileArgs a) {
   if (is_last) {
     __threadfence();
     for (int o = tid; o <= a.n_ops; o += blockDim.x) {
-      a.host_out[o] = __ldcg(&a.acc[o]);
-      a.acc[o] = 0;
+      unsigned long long v = 0;
+#pragma unroll
+      for (int c = 0; c < kFitchAccCopies; ++c) {
+        v += __ldcg(&a.acc[(size_t)c * (a.n_ops + 2) + o]);
+        a.acc[(size_t)c * (a.n_ops + 2) + o] = 0;
+      }
+      a.host_out[o] = v;
     }
     if (tid == 0) a.acc[a.n_ops + 1] = 0;
     __threadfence_system();
