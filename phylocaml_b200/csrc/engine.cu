@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -66,6 +68,7 @@ struct phylo_engine {
   int opt_fitch_walk = 1;  // Fitch tree kernel: 0 = L2 walk, 1 = auto, 2 = register walk, 3 = on-chip tiles
   unsigned long long *dAcc = nullptr;  // tile kernel accumulators (all zero between calls)
   size_t capAcc = 0, tileSmem = 0;
+  unsigned long long tileSeq = 0;
   int tileOcc = 1;
   bool tileWeighted = false;
   int opt_fused = 1;  // 0 = one kernel per node, 1 = tree-fused (warp-autonomous where eligible), 2 = tile kernel only
@@ -1914,7 +1917,7 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   int rc;
   const size_t blob = sizeof(FitchTileOp) * n_tot + 8 * (size_t)n_in + 4 * (size_t)(kFitchTileWarps + 2) + 64;
   if ((rc = fitch_sched_capacity(e, blob)) != PHYLO_OK) return rc;
-  if ((rc = fitch_cost_capacity(e, (size_t)n_tot + 4)) != PHYLO_OK) return rc;
+  if ((rc = fitch_cost_capacity(e, (size_t)n_tot + 8)) != PHYLO_OK) return rc;
   if ((size_t)n_tot + 2 > e->capAcc) {
     CK(cudaStreamSynchronize(e->stream));
     dfree(e->dAcc);
@@ -1924,8 +1927,10 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     CK(cudaMemset(e->dAcc, 0, sizeof(unsigned long long) * cap * kFitchAccCopies));
     e->capAcc = cap;
   }
-  CK(cudaStreamSynchronize(e->stream));  // pinned staging is about to be rewritten
-  char *hb = (char *)e->hSched;
+  const bool inl = blob - 64 <= (size_t)kFitchInlineProg;
+  FitchTileArgs a;
+  if (!inl) CK(cudaStreamSynchronize(e->stream));  // pinned staging is about to be rewritten
+  char *hb = inl ? (char *)a.prog : (char *)e->hSched;
   FitchTileOp *hops = (FitchTileOp *)hb;
   const uint32_t **hin = (const uint32_t **)(hb + sizeof(FitchTileOp) * n_tot);
   int *hlev = (int *)(hb + sizeof(FitchTileOp) * n_tot + 8 * (size_t)n_in);
@@ -1941,8 +1946,10 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   }
   for (int i = 0; i < n_in; ++i) hin[i] = e->fPre[inputs[i]];
   for (int w = 0; w < kFitchTileWarps + 2; ++w) hlev[w] = tstart[w];
-  CK(cudaMemcpyAsync(e->dSched, hb, blob - 64, cudaMemcpyHostToDevice, e->stream));
-  FitchTileArgs a;
+  if (!inl) CK(cudaMemcpyAsync(e->dSched, hb, blob - 64, cudaMemcpyHostToDevice, e->stream));
+  a.inline_prog = inl;
+  a.seq = ++e->tileSeq;
+  e->hCost[n_tot + 1] = ~0ull;  // the slot the last CTA overwrites with a.seq
   char *db = (char *)e->dSched;
   a.ops = (const FitchTileOp *)db;
   a.in_ptr = (const uint32_t *const *)(db + sizeof(FitchTileOp) * n_tot);
@@ -1970,7 +1977,24 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     kern<<<g, 256, smem, e->stream>>>(a);
     LAUNCH_CHECK();
   }
-  CK(cudaStreamSynchronize(e->stream));
+  // small alignments: spin on the sequence number the last CTA writes after the results (a
+  // blocking stream sync costs more than the kernel); otherwise, or after 2 ms, a stream sync
+  {
+    volatile unsigned long long *flag = (volatile unsigned long long *)&e->hCost[n_tot + 1];
+    bool seen = false;
+    if (e->fWords <= kFitchTileMaxWords) {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int spin = 0;; ++spin) {
+        if (*flag == a.seq) { seen = true; break; }
+        if ((spin & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+      }
+    }
+    if (!seen) {
+      CK(cudaStreamSynchronize(e->stream));
+      if (*flag != a.seq) return fail(e, PHYLO_ERR_CUDA, "fitch_score_tree: the tile kernel did not publish its result");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   *length_out = e->hCost[n_tot];
   for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[pos[o]];
   if (e->prof_on) prof_resolve_lazy(e);

@@ -318,6 +318,7 @@ fitch_treep_kernel(const FitchInstr *__restrict__ prog, int n_steps, int depth, 
 // The last CTA to finish publishes the per-op costs and the length straight into mapped
 // host memory and re-zeroes the accumulators: one kernel launch is the whole call.
 constexpr int kFitchTileWarps = 8;
+constexpr int kFitchInlineProg = 3200;  // bytes of program that fit into the kernel parameters
 constexpr int kFitchAccCopies = 16;  // CTAs spread their atomics over this many accumulator sets (L2 serialises same-address atomics)
 struct __align__(16) FitchTileOp {
   uint32_t l_off, r_off;  // byte offsets of the operands' rows in the tile table; the result replaces the left row
@@ -331,7 +332,10 @@ struct FitchTileArgs {
   int64_t nwords, N;
   const uint32_t *wt;
   unsigned long long *acc;         // [kFitchAccCopies][n_ops + 2]: per-op costs, total, CTA counter (all zero between calls)
-  unsigned long long *host_out;    // mapped host memory [n_ops + 1]: per-op costs, total
+  unsigned long long *host_out;    // mapped host memory [n_ops + 2]: per-op costs, total, then the call's sequence number
+  unsigned long long seq;          // written last: the host spins on it instead of a stream sync
+  int inline_prog;                 // 1: the program travels in `prog` (kernel parameter space), no H2D copy
+  __align__(16) unsigned char prog[kFitchInlineProg];  // ops | in_ptr | task_start
 };
 
 // Every operand is consumed exactly once (the host checks the schedule is a forest and gives
@@ -351,10 +355,15 @@ fitch_tile_kernel(const FitchTileArgs a) {
   __shared__ bool is_last;
   __shared__ int stask[kFitchTileWarps + 2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFitchTileWarps;
-  for (int i = tid; i < a.n_ops; i += blockDim.x) sops[i] = a.ops[i];
+  {
+    const FitchTileOp *gops = a.inline_prog ? reinterpret_cast<const FitchTileOp *>(a.prog) : a.ops;
+    const uint32_t *const *gin = a.inline_prog ? reinterpret_cast<const uint32_t *const *>(a.prog + sizeof(FitchTileOp) * a.n_ops) : a.in_ptr;
+    const int *gts = a.inline_prog ? reinterpret_cast<const int *>(a.prog + sizeof(FitchTileOp) * a.n_ops + 8 * (size_t)a.n_in) : a.task_start;
+    for (int i = tid; i < a.n_ops; i += blockDim.x) sops[i] = gops[i];
+    for (int i = tid; i < a.n_in; i += blockDim.x) sin[i] = gin[i];
+    if (tid < kFitchTileWarps + 2) stask[tid] = gts[tid];
+  }
   for (int i = tid; i < a.n_ops * 32; i += blockDim.x) sh_cnt[i] = 0;
-  for (int i = tid; i < a.n_in; i += blockDim.x) sin[i] = a.in_ptr[i];
-  if (tid < kFitchTileWarps + 2) stask[tid] = a.task_start[tid];
   __syncthreads();
   const int64_t ntiles = (a.nwords + 31) / 32;
   unsigned char *mine = table + lane * 16;                 // this lane's column inside any table row
@@ -430,6 +439,11 @@ fitch_tile_kernel(const FitchTileArgs a) {
     }
     if (tid == 0) a.acc[a.n_ops + 1] = 0;
     __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      *reinterpret_cast<volatile unsigned long long *>(&a.host_out[a.n_ops + 1]) = a.seq;
+      __threadfence_system();
+    }
   }
 }
 
