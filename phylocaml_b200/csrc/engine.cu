@@ -1029,48 +1029,56 @@ static cudaError_t launch_tree_k(phylo_engine *e, const TreeArgs &a, size_t smem
 struct TreeWGeom {
   int warps = 0;     // warps per CTA
   size_t smem = 0;   // dynamic shared memory per CTA
-  int slev = kTreeWSmemLevels, obufs = 1, interleave = 1;
+  int slev = kTreeWSmemLevels, R = 1, interleave = 1;
 };
-// experiment knob: PHYLO_TREEW_TUNE="slev,obufs,interleave" (defaults are the measured best)
-static void treew_tune(TreeWGeom &g) {
-  const char *t = getenv("PHYLO_TREEW_TUNE");
-  if (!t) return;
-  int a = g.slev, b = g.obufs, c = g.interleave;
-  if (sscanf(t, "%d,%d,%d", &a, &b, &c) >= 1) {
-    g.slev = std::max(1, a);
-    g.obufs = (b == 1) ? 1 : 2;
-    g.interleave = c != 0;
-  }
-}
+// R = 2 (two patterns per thread share every matrix read) pays when 8 warps of it fit: it needs
+// twice the per-warp shared memory, and 4 or 8 warps to keep the four SM sub-partitions even.
+// Otherwise R = 1 with as many warps as fit. PHYLO_TREEW_TUNE="slev,R,interleave" overrides
+// (experiments; R = 0: automatic).
 static TreeWGeom treew_geometry(const phylo_engine *e, int depth, int n_steps, bool retain) {
-  TreeWGeom g;
-  treew_tune(g);
   const size_t kMaxSmem = 227 * 1024, fixed = treew_prog_bytes(n_steps) + 1024;  // +1024: manual alignment
-  const size_t wb = treew_warp_bytes(e->K, e->T, depth, retain, g.slev, g.obufs);
-  if (fixed + wb > kMaxSmem) return g;
-  int w = (int)std::min<size_t>(kTreeWMaxWarps, (kMaxSmem - fixed) / wb);
-  // few groups (small alignments): spread them over the SMs instead of filling CTAs
   const int64_t ngroups = (e->N + 31) / 32;
-  w = (int)std::max<int64_t>(1, std::min<int64_t>(w, (ngroups + e->sm_count - 1) / e->sm_count));
-  g.warps = w;
-  g.smem = fixed + (size_t)w * wb;
-  return g;
+  int want_slev = 0, want_R = 0, want_il = 1;
+  if (const char *t = getenv("PHYLO_TREEW_TUNE")) sscanf(t, "%d,%d,%d", &want_slev, &want_R, &want_il);
+  auto fit = [&](int R, int slev, int max_warps) {
+    TreeWGeom g;
+    g.R = R; g.slev = slev; g.interleave = want_il != 0;
+    const size_t wb = treew_stage_bytes(e->K, retain, R) + treew_warp_bytes(e->K, e->T, depth, slev, R);
+    if (fixed + wb > kMaxSmem) return g;
+    int w = (int)std::min<size_t>(max_warps, (kMaxSmem - fixed) / wb);
+    // few units (small alignments): spread them over the SMs instead of filling CTAs
+    const int64_t units = (ngroups + R - 1) / R;
+    w = (int)std::max<int64_t>(1, std::min<int64_t>(w, (units + e->sm_count - 1) / e->sm_count));
+    g.warps = w;
+    g.smem = fixed + (size_t)w * wb;
+    return g;
+  };
+  if (want_R == 1 || want_R == 2) return fit(want_R, want_slev > 0 ? want_slev : kTreeWSmemLevels, want_R == 1 ? kTreeWMaxWarps : 8);
+  if (want_slev > 0) return fit(1, want_slev, kTreeWMaxWarps);
+  if (ngroups >= (int64_t)e->sm_count * 16) {  // enough work for 8 double-width warps per SM
+    for (int slev = kTreeWSmemLevels; slev >= 1; --slev) {
+      TreeWGeom g = fit(2, slev, 8);
+      if (g.warps == 8) return g;
+    }
+  }
+  return fit(1, kTreeWSmemLevels, kTreeWMaxWarps);
 }
 
-template <int K>
-static cudaError_t launch_treew(phylo_engine *e, TreeArgs args, const TreeWGeom &geo, bool retain, int64_t g_begin,
+template <int K, int R>
+static cudaError_t launch_treew(phylo_engine *e, const TreeWArgs &wargs, const TreeWGeom &geo, bool retain, int64_t g_begin,
                                 int64_t g_end, cudaStream_t cs) {
-  args.tile_begin = g_begin;
-  args.tile_end = g_end;
-  const int64_t ctas = (g_end - g_begin + geo.warps - 1) / geo.warps;
+  TreeWArgs args = wargs;
+  args.t.tile_begin = g_begin;
+  args.t.tile_end = g_end;
+  const int64_t units = (g_end - g_begin + R - 1) / R, ctas = (units + geo.warps - 1) / geo.warps;
   const int g = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, e->sm_count));
   cudaError_t st;
   if (retain) {
-    auto kern = lk_treew_kernel<K, true>;
+    auto kern = lk_treew_kernel<K, R, true>;
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem)) != cudaSuccess) return st;
     kern<<<g, geo.warps * 32, geo.smem, cs>>>(args);
   } else {
-    auto kern = lk_treew_kernel<K, false>;
+    auto kern = lk_treew_kernel<K, R, false>;
     if ((st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem)) != cudaSuccess) return st;
     kern<<<g, geo.warps * 32, geo.smem, cs>>>(args);
   }
@@ -1080,11 +1088,18 @@ static cudaError_t launch_treew(phylo_engine *e, TreeArgs args, const TreeWGeom 
 
 static cudaError_t launch_treew_k(phylo_engine *e, const TreeArgs &a, const TreeWGeom &geo, int64_t g_begin, int64_t g_end,
                                   cudaStream_t cs) {
+  TreeWArgs w;
+  w.t = a;
+  w.tmaps = (const char *)e->dTmaps;
+#define TREEW(KV)                                                                             \
+  (geo.R == 2 ? launch_treew<KV, 2>(e, w, geo, e->opt_retain, g_begin, g_end, cs)             \
+              : launch_treew<KV, 1>(e, w, geo, e->opt_retain, g_begin, g_end, cs))
   switch (e->K) {
-    case 1: return launch_treew<1>(e, a, geo, e->opt_retain, g_begin, g_end, cs);
-    case 2: return launch_treew<2>(e, a, geo, e->opt_retain, g_begin, g_end, cs);
-    default: return launch_treew<4>(e, a, geo, e->opt_retain, g_begin, g_end, cs);
+    case 1: return TREEW(1);
+    case 2: return TREEW(2);
+    default: return TREEW(4);
   }
+#undef TREEW
 }
 
 // (re)builds the TMA tensor maps of all allocated node CLVs: [N rows][4K doubles], box =
@@ -1157,18 +1172,22 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   if (useW && e->opt_retain && e->tmapDirty && (rc = lk_build_tmaps(e)) != PHYLO_OK) return rc;
   {
     TreeInstr *hp = (TreeInstr *)e->hProg;
+    TreeWInstr *hw = (TreeWInstr *)e->hProg;
     for (size_t i = 0; i < pl.steps.size(); ++i) {
       const PlanStep &st = pl.steps[i];
-      TreeInstr in{};
-      in.kinds = st.lkind | (st.rkind << 2) | (st.push_first << 4);
-      in.lidx = st.lidx;
-      in.ridx = st.ridx;
-      in.out_slot = st.out_slot;
-      in.out_clv = (e->opt_retain && st.out_slot >= 0)
-                       ? (useW ? reinterpret_cast<double *>(e->dTmaps + st.out_slot) : e->nodes[st.out_slot].clv)
-                       : nullptr;
-      in.out_sc = (e->opt_retain && st.out_slot >= 0) ? e->nodes[st.out_slot].scale : nullptr;
-      hp[i] = in;
+      if (useW) {
+        hw[i] = TreeWInstr{st.lkind | (st.rkind << 2) | (st.push_first << 4), st.lidx, st.ridx,
+                           e->opt_retain ? st.out_slot : -1};
+      } else {
+        TreeInstr in{};
+        in.kinds = st.lkind | (st.rkind << 2) | (st.push_first << 4);
+        in.lidx = st.lidx;
+        in.ridx = st.ridx;
+        in.out_slot = st.out_slot;
+        in.out_clv = (e->opt_retain && st.out_slot >= 0) ? e->nodes[st.out_slot].clv : nullptr;
+        in.out_sc = (e->opt_retain && st.out_slot >= 0) ? e->nodes[st.out_slot].scale : nullptr;
+        hp[i] = in;
+      }
       if (i + 1 < pl.steps.size()) { e->hT[2 * i] = st.t_left; e->hT[2 * i + 1] = st.t_right; }
       else e->hT[2 * i] = st.t_left;
     }
@@ -1196,9 +1215,9 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   a.spill = nullptr;
   if (useW) {
     // two regions: consecutive slabs of phylo_lk_score_alignment run on two streams
-    const size_t region = treew_spill_bytes(e->K, pl.depth, geo.slev) * kTreeWMaxWarps * (size_t)e->sm_count, need = 2 * region;
+    const size_t region = treew_spill_bytes(e->K, pl.depth, geo.slev, geo.R) * kTreeWMaxWarps * (size_t)e->sm_count, need = 2 * region;
     a.smem_levels = geo.slev;
-    a.obufs = geo.obufs;
+    a.obufs = 1;
     a.interleave = geo.interleave;
     if (need > e->capSpill) {
       CK(cudaStreamSynchronize(e->stream));

@@ -467,6 +467,34 @@ def test_fused_tree_equals_per_node_path_bitwise(eng, oracle, T, N, kind):
     assert rel_err(a, want) <= LNL_RTOL
 
 
+@pytest.mark.parametrize("tune", ["2,2,1", "1,2,0", "1,1,1", "3,1,0"])
+@pytest.mark.parametrize("K", [4, 2, 1])
+def test_fused_tree_kernel_variants_bitwise(eng, tune, K, monkeypatch):
+    """The warp-autonomous kernel in its geometry variants (shared-memory stack levels, R = 1 or
+    2 patterns per thread, group order; PHYLO_TREEW_TUNE) == the per-node path, bit for bit:
+    lnL, site lnL, every CLV and scale counter. N is not a multiple of 64 (odd group count)."""
+    sv = ("gamma", K, 0.6) if K > 1 else None
+    m = mlmodel.create(("GTR", [1.0, 2.5, 0.8, 1.2, 3.0]), 4, pi=[0.3, 0.2, 0.25, 0.25], site_var=sv)
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(40, 7000 + 33, m, seed=44, mean_bl=0.4)
+    monkeypatch.setenv("PHYLO_TREEW_TUNE", tune)
+    eng.profile(True)
+    try:
+        a, fa = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=1)
+        site_a = eng.lk_get_site_lnl()
+        clv_a = [eng.lk_get_clv(int(op["parent"])) for op in ops]
+        c, fc = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=0)
+        monkeypatch.delenv("PHYLO_TREEW_TUNE")
+        b, fb = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=0, retain=1)
+        site_b = eng.lk_get_site_lnl()
+        clv_b = [eng.lk_get_clv(int(op["parent"])) for op in ops]
+    finally:
+        eng.profile(False)
+    assert fa and fc and not fb and a == b == c
+    assert np.array_equal(site_a, site_b)
+    for (ca, sa), (cb, sb) in zip(clv_a, clv_b):
+        assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
+
+
 @pytest.mark.parametrize("K", [1, 2, 8])
 def test_fused_tree_other_rate_counts(eng, oracle, K):
     sv = ("gamma", K, 0.8) if K > 1 else None
