@@ -161,6 +161,19 @@ int phylo_lk_get_site_lnl(phylo_engine *e, double *out);
 int phylo_lk_get_block_partials(phylo_engine *e, double *out, int64_t *n_out);
 double phylo_reduce_partials(const double *partials, int64_t n);
 
+/* ------------------------------------------------ site-pattern compression (next to the path) ---- */
+/* The step before scoring: identical alignment columns are merged into one site pattern whose
+ * weight is the sum of the columns' weights (the `weights` of NonAdditive_c.t,
+ * lib/nonAdditive_c.ml:3, and of phylo_lk_set_tips). masks: T x N, tip-major, elements of
+ * mask_bytes; weights_in: N doubles or NULL (1 each). Outputs are HOST buffers sized for the
+ * worst case: patterns_out T x N elements (written compactly as T rows of *n_patterns),
+ * weights_out N doubles, site_to_pattern N int32 (may be NULL). Patterns come out in order of
+ * first occurrence, so the result is deterministic. Done on the device (hashing into an
+ * open-addressing table, full-column verification, prefix sum); no CPU fallback. */
+int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                            const double *weights_in, void *patterns_out, double *weights_out,
+                            int32_t *site_to_pattern, int64_t *n_patterns);
+
 /* -------------------------- NonAdditive node data / Bitvector (lib/nonAdditive_c.ml) ---- */
 /* T taxa x N characters, one character per element of elt_bytes (W/8, W in {8,16,32,64},
  * lib/bitvector/bv.h:29-55), n_states = number of usable low bits (vect.msize, bv.h:61).

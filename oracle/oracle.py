@@ -47,6 +47,25 @@ def make_ops(parent, left, right, t_left=None, t_right=None):
     return ops
 
 
+def compress_patterns(masks, weights=None):
+    """CPU statement of site-pattern compression (test oracle for phylo_compress_patterns):
+    identical columns of the tip-major alignment `masks` [T x N] are merged, patterns are
+    numbered by first occurrence, weights are summed. Returns (patterns [T x P], weights [P],
+    site_to_pattern [N]). The reference carries such weights (lib/nonAdditive_c.ml:3) but has no
+    code that produces them."""
+    masks = np.ascontiguousarray(masks)
+    cols = np.ascontiguousarray(masks.T)
+    view = cols.view(np.dtype((np.void, cols.dtype.itemsize * cols.shape[1]))).ravel()
+    _, first, inverse = np.unique(view, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    s2p = rank[np.asarray(inverse).ravel()].astype(np.int32)
+    w = np.bincount(s2p, weights=None if weights is None else np.asarray(weights, dtype=float),
+                    minlength=len(order)).astype(float)
+    return np.ascontiguousarray(masks[:, first[order]]), w, s2p
+
+
 class Oracle:
     def __init__(self):
         path = os.path.join(HERE, "liboracle.so")

@@ -21,6 +21,7 @@
 #include "lk_tree_kernel.cuh"
 #include "lk_treew_kernel.cuh"
 #include "lk_edge_kernels.cuh"
+#include "compress_kernels.cuh"
 #include "phylo_engine.h"
 
 using namespace phylo;
@@ -36,11 +37,11 @@ struct LkNode {
 // kernel classes for the CUDA-event profiler (phylo_engine_profile_*)
 enum KClass {
   KC_PT_BUILD = 0, KC_TREE_FUSED, KC_PRUNE_II, KC_PRUNE_TI, KC_PRUNE_TT, KC_ROOT, KC_REDUCE, KC_TIPS_PREPARE,
-  KC_FITCH_TREE, KC_FITCH_NODE, KC_FITCH_UPPASS, KC_FITCH_TRANSCODE, KC_BV, KC_EDGE, KC_COUNT
+  KC_FITCH_TREE, KC_FITCH_NODE, KC_FITCH_UPPASS, KC_FITCH_TRANSCODE, KC_BV, KC_EDGE, KC_COMPRESS, KC_COUNT
 };
 static const char *kClassNames[KC_COUNT] = {
     "pt_build", "tree_fused", "prune_inner_inner", "prune_tip_inner", "prune_tip_tip", "root_lnl", "reduce1024",
-    "tips_prepare", "fitch_tree", "fitch_median2", "fitch_uppass", "fitch_transcode", "bv_setops", "edge_loop"};
+    "tips_prepare", "fitch_tree", "fitch_median2", "fitch_uppass", "fitch_transcode", "bv_setops", "edge_loop", "compress"};
 
 struct phylo_engine {
   int device = 0;
@@ -1424,6 +1425,115 @@ extern "C" int phylo_lk_edge_lnl(phylo_engine *e, int a_slot, int b_slot, const 
     lnl_out[i] = e->hScalar[0];
   }
   e->lk_evaluated = true;
+  return PHYLO_OK;
+}
+
+// ---------------------------------------------------------- site-pattern compression ----
+template <int EB>
+static void launch_cmp_transpose(const uint8_t *in, uint8_t *rec, int T, int64_t N, int TP, cudaStream_t st) {
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)((T + 31) / 32));
+  cmp_transpose_kernel<EB><<<grid, 256, 0, st>>>(in, rec, T, N, TP);
+}
+template <int EB>
+static void launch_cmp_gather(const uint8_t *in, int T, int64_t N, const int *rep_site, int64_t P, uint8_t *out, int g,
+                              cudaStream_t st) {
+  cmp_gather_kernel<EB><<<g, 256, 0, st>>>(in, T, N, rep_site, P, out);
+}
+
+extern "C" int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                       const double *weights_in, void *patterns_out, double *weights_out,
+                                       int32_t *site_to_pattern, int64_t *n_patterns) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (T < 1 || N < 1 || N > 2000000000ll || !masks || !patterns_out || !weights_out || !n_patterns ||
+      !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
+    return fail(e, PHYLO_ERR_ARG, "compress_patterns: bad arguments (T=%d N=%lld mask_bytes=%d)", T, (long long)N, mask_bytes);
+  CK(cudaSetDevice(e->device));
+  const int EB = mask_bytes, TP = (int)(((size_t)T * EB + 15) / 16 * 16);
+  uint64_t M = 1;
+  while (M < 2 * (uint64_t)N) M <<= 1;
+  const int64_t nb = (N + 1023) / 1024;
+  // one arena for all temporaries (freed on return)
+  struct Part { size_t off, bytes; };
+  size_t total = 0;
+  auto reserve = [&](size_t bytes) { Part p{total, bytes}; total += (bytes + 255) & ~(size_t)255; return p; };
+  const Part pIn = reserve((size_t)T * N * EB), pRec = reserve((size_t)N * TP), pKey = reserve(8 * (size_t)N),
+             pTKey = reserve(8 * (size_t)M), pTRep = reserve(4 * (size_t)M), pSlot = reserve(4 * (size_t)N),
+             pFlag = reserve(4 * (size_t)N), pBsum = reserve(4 * (size_t)(nb + 1)), pPid = reserve(4 * (size_t)N),
+             pRepSite = reserve(4 * (size_t)N), pSitePat = reserve(4 * (size_t)N), pWout = reserve(8 * (size_t)N),
+             pWin = reserve(weights_in ? 8 * (size_t)N : 0), pScal = reserve(64), pOut = reserve((size_t)T * N * EB);
+  char *arena = nullptr;
+  if (cudaMalloc(&arena, total) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, PHYLO_ERR_CUDA, "compress_patterns: cannot allocate %zu bytes of device memory", total);
+  }
+  struct Free { char *p; ~Free() { cudaFree(p); } } guard{arena};
+  uint8_t *dIn = (uint8_t *)(arena + pIn.off), *dRec = (uint8_t *)(arena + pRec.off), *dOut = (uint8_t *)(arena + pOut.off);
+  uint64_t *dKey = (uint64_t *)(arena + pKey.off);
+  unsigned long long *dTKey = (unsigned long long *)(arena + pTKey.off), *dColl = (unsigned long long *)(arena + pScal.off);
+  long long *dTotal = (long long *)(arena + pScal.off + 8);
+  int *dTRep = (int *)(arena + pTRep.off), *dFlag = (int *)(arena + pFlag.off), *dBsum = (int *)(arena + pBsum.off),
+      *dPid = (int *)(arena + pPid.off), *dRepSite = (int *)(arena + pRepSite.off), *dSitePat = (int *)(arena + pSitePat.off);
+  uint32_t *dSlot = (uint32_t *)(arena + pSlot.off);
+  double *dWout = (double *)(arena + pWout.off), *dWin = weights_in ? (double *)(arena + pWin.off) : nullptr;
+  cudaStream_t st = e->stream;
+  CK(cudaMemcpyAsync(dIn, masks, (size_t)T * N * EB, cudaMemcpyHostToDevice, st));
+  if (weights_in) CK(cudaMemcpyAsync(dWin, weights_in, 8 * (size_t)N, cudaMemcpyHostToDevice, st));
+  const int g = grid_for(N, 256, e->sm_count * 16);
+  long long hTotal = 0;
+  unsigned long long hColl = 0;
+  {
+    ProfScope prof(e, KC_COMPRESS);
+    CK(cudaMemsetAsync(dRec, 0, (size_t)N * TP, st));  // record padding must compare equal
+    switch (EB) {
+      case 1: launch_cmp_transpose<1>(dIn, dRec, T, N, TP, st); break;
+      case 2: launch_cmp_transpose<2>(dIn, dRec, T, N, TP, st); break;
+      case 4: launch_cmp_transpose<4>(dIn, dRec, T, N, TP, st); break;
+      default: launch_cmp_transpose<8>(dIn, dRec, T, N, TP, st);
+    }
+    LAUNCH_CHECK();
+    for (int attempt = 0;; ++attempt) {
+      CK(cudaMemsetAsync(dTKey, 0, 8 * (size_t)M, st));
+      CK(cudaMemsetAsync(dTRep, 0x7f, 4 * (size_t)M, st));
+      CK(cudaMemsetAsync(dColl, 0, 16, st));
+      cmp_hash_kernel<<<g, 256, 0, st>>>(dRec, N, TP, 0x243f6a8885a308d3ull + 0x9e3779b97f4a7c15ull * (uint64_t)attempt, dKey);
+      LAUNCH_CHECK();
+      cmp_insert_kernel<<<g, 256, 0, st>>>(dKey, N, dTKey, dTRep, M - 1, dSlot);
+      LAUNCH_CHECK();
+      cmp_verify_kernel<<<g, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl);
+      LAUNCH_CHECK();
+      CK(cudaMemcpyAsync(&hColl, dColl, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (hColl == 0) break;
+      if (attempt == 3) return fail(e, PHYLO_ERR_NUMERIC, "compress_patterns: hash collisions persist after 4 seeds");
+    }
+    cmp_scan_block_sums<<<(int)nb, 256, 0, st>>>(dFlag, N, dBsum);
+    LAUNCH_CHECK();
+    cmp_scan_sums<<<1, 1024, 0, st>>>(dBsum, nb, dTotal);
+    LAUNCH_CHECK();
+    cmp_scan_apply<<<(int)nb, 256, 0, st>>>(dFlag, N, dBsum, dPid, dRepSite);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&hTotal, dTotal, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(dWout, 0, 8 * (size_t)N, st));
+    cmp_assign_kernel<<<g, 256, 0, st>>>(N, dTRep, dSlot, dPid, dWin, dSitePat, dWout);
+    LAUNCH_CHECK();
+    CK(cudaStreamSynchronize(st));
+    const int64_t P = hTotal;
+    const int gg = grid_for((int64_t)T * P, 256, e->sm_count * 16);
+    switch (EB) {
+      case 1: launch_cmp_gather<1>(dIn, T, N, dRepSite, P, dOut, gg, st); break;
+      case 2: launch_cmp_gather<2>(dIn, T, N, dRepSite, P, dOut, gg, st); break;
+      case 4: launch_cmp_gather<4>(dIn, T, N, dRepSite, P, dOut, gg, st); break;
+      default: launch_cmp_gather<8>(dIn, T, N, dRepSite, P, dOut, gg, st);
+    }
+    LAUNCH_CHECK();
+  }
+  const int64_t P = hTotal;
+  CK(cudaMemcpyAsync(patterns_out, dOut, (size_t)T * P * EB, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(weights_out, dWout, 8 * (size_t)P, cudaMemcpyDeviceToHost, st));
+  if (site_to_pattern) CK(cudaMemcpyAsync(site_to_pattern, dSitePat, 4 * (size_t)N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_patterns = P;
+  if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }
 

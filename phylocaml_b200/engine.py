@@ -55,6 +55,7 @@ SIGNATURES = {
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
                                            C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
+    "phylo_compress_patterns": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, _vp, _dp, _vp, C.POINTER(_i64)]),
     "phylo_lk_edge_prepare": (C.c_int, [_vp, C.c_int, C.c_int]),
     "phylo_lk_edge_eval": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp]),
     "phylo_lk_optimize_branch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -286,6 +287,21 @@ class Engine:
                                                    _p(ops), len(ops), root_a, root_b, float(root_t), C.byref(out)))
         self.lk_shape = (T, N, capacity)
         return out.value
+
+    def compress_patterns(self, masks, weights=None):
+        """Merge identical alignment columns: (patterns [T x P], weights [P], site_to_pattern [N])."""
+        masks = np.ascontiguousarray(masks)
+        T, N = masks.shape
+        out = np.empty((T, N), dtype=masks.dtype)
+        w_out = np.empty(N)
+        s2p = np.empty(N, dtype=np.int32)
+        n = _i64()
+        w_in = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_compress_patterns(self.h, T, N, _p(masks), masks.dtype.itemsize,
+                                                  None if w_in is None else _p(w_in, _dp), _p(out), _p(w_out, _dp),
+                                                  _p(s2p), C.byref(n)))
+        P = n.value
+        return np.ascontiguousarray(out.reshape(-1)[:T * P].reshape(T, P)), w_out[:P].copy(), s2p
 
     def lk_edge_prepare(self, a, b):
         """Sum table of edge (a, b) for the branch-length loop (Likelihood.adjust_3)."""

@@ -276,6 +276,55 @@ def test_lk_optimize_branch_matches_scalar_minimiser(eng, oracle):
         assert abs(d1[0]) <= 1e-5 * abs(d2[0]) * max(t_opt, 1e-3) + 1e-6
 
 
+# ------------------------------------------------------ site-pattern compression ----
+@pytest.mark.parametrize("dtype,T,N", [(np.uint8, 12, 50000), (np.uint8, 7, 1), (np.uint16, 5, 3001),
+                                       (np.uint32, 33, 4097), (np.uint64, 3, 70000), (np.uint8, 256, 20000)])
+def test_compress_patterns_equals_oracle(eng, dtype, T, N):
+    """phylo_compress_patterns == the numpy oracle exactly: patterns in order of first occurrence,
+    summed weights, site -> pattern map; element widths 1/2/4/8 bytes, record padding."""
+    from oracle.oracle import compress_patterns
+
+    rng = np.random.default_rng(N + T)
+    base = rng.integers(1, 16, size=(T, max(1, N // 7))).astype(dtype)  # ~7 copies of every column
+    masks = np.ascontiguousarray(base[:, rng.integers(0, base.shape[1], N)])
+    w = rng.integers(1, 6, N).astype(float)
+    for weights in (None, w):
+        pats, wt, s2p = eng.compress_patterns(masks, weights)
+        opats, owt, os2p = compress_patterns(masks, weights)
+        assert pats.shape == opats.shape
+        assert np.array_equal(pats, opats) and np.array_equal(wt, owt) and np.array_equal(s2p, os2p)
+
+
+def test_compress_patterns_extremes(eng):
+    from oracle.oracle import compress_patterns
+
+    same = np.full((9, 5000), 4, dtype=np.uint8)
+    pats, wt, s2p = eng.compress_patterns(same)
+    assert pats.shape == (9, 1) and wt[0] == 5000 and not s2p.any()
+    distinct = np.arange(1, 40001, dtype=np.uint64).reshape(1, -1).repeat(3, axis=0)
+    pats, wt, s2p = eng.compress_patterns(distinct)
+    assert pats.shape == (3, 40000) and np.array_equal(pats, distinct) and np.all(wt == 1)
+    assert np.array_equal(s2p, np.arange(40000))
+
+
+def test_compressed_alignment_scores_like_the_raw_one(eng, oracle):
+    """lnL and Fitch length of (patterns, weights) == those of the raw alignment."""
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(10, 30000, model, seed=9, mean_bl=0.05)
+    pats, wt, _ = eng.compress_patterns(tips)
+    assert pats.shape[1] < tips.shape[1] // 2
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=n_nodes)
+    raw = eng.lk_score_tree(ops, ra, rb, rt)
+    eng.lk_set_tips(pats, weights=wt, capacity=n_nodes)
+    assert rel_err(eng.lk_score_tree(ops, ra, rb, rt), raw) <= LNL_RTOL
+    chars = np.where(tips == 15, 15, tips).astype(np.uint8)
+    eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+    raw_len = eng.fitch_score_tree(ops, ra, rb)
+    eng.fitch_set_tips(pats, 4, weights=wt, capacity=n_nodes)
+    assert eng.fitch_score_tree(ops, ra, rb) == raw_len
+
+
 # ------------------------------------------------------------------------ Fitch ----
 def _fitch_setup(T, N, n_states, dtype, seed=1):
     tr = tree.random_tree(T, seed)
