@@ -39,6 +39,8 @@ WORKLOADS = {
                   name="Codon 61-state pruning, 64 taxa x 200k patterns"),
     "fitch": dict(T=64, N=1_000_000, S=4, K=1, cpu_sample=1_000_000,
                   name="Fitch/non-additive parsimony length, 64 taxa x 1M bit-packed DNA characters"),
+    "compress": dict(T=256, N=4_000_000, S=4, K=4, cpu_sample=500_000,
+                     name="site-pattern compression (the step before the path), 256 taxa x 4M raw DNA sites"),
 }
 
 
@@ -227,6 +229,80 @@ def cpu_baseline(wl, workload, tr, ops, ra, rb, rt, n_nodes, model, tips_sample,
     return out, check, res
 
 
+def run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src):
+    """raw alignment (host) -> unique site patterns + weights (host), through
+    phylo_compress_patterns. A step = one whole alignment; single GPU (sites could be sharded, but
+    the merge of per-shard tables is not built)."""
+    T, N = wl["T"], args.patterns or wl["N"]
+    if args.taxa:
+        T = args.taxa
+    tr = tree_mod.random_tree(T, seed=1)
+    model = make_model(WORKLOADS["dna"])
+    base = tree_mod.evolve_tips(tr, model, BASE_PATTERNS, seed=3)
+    rng = np.random.default_rng(11)
+    raw = engine.pinned_empty((T, N), np.uint8)  # page-locked, like the Bigarray staging buffers (phylo_host_alloc)
+    raw[:] = base[:, rng.integers(0, base.shape[1], N)]  # every column ~61 times, shuffled
+    eng = engine.Engine(local)
+    for _ in range(args.warmup):
+        pats, wt, s2p = eng.compress_patterns(raw)
+    eng.profile(True, reset=True)
+    sampler = ClockSampler(local)
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    steps = max(1, args.steps // 4)
+    for _ in range(steps):
+        pats, wt, s2p = eng.compress_patterns(raw)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    clocks = sampler.stop()
+    prof = eng.profile_get()
+    eng.profile(False)
+    kms, kn = prof.get("compress", (0.0, 0))
+    kms_step = kms / max(1, steps)
+    P = pats.shape[1]
+    comp_bytes = T * N + T * P + 8 * P + 4 * N  # read the alignment, write patterns + weights + site map
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle.oracle import compress_patterns as cpu_compress
+
+        ns = min(N, wl["cpu_sample"])
+        t0 = time.perf_counter()
+        opats, owt, os2p = cpu_compress(raw[:, :ns])
+        dt = time.perf_counter() - t0
+        cpu = {"value": ns / dt, "unit": "sites/s", "cores": 1, "kind": "port",
+               "sample": "first %d sites, numpy void-view unique (oracle/oracle.py)" % ns}
+    full_ok = None
+    if N <= 2_000_000 or args.no_cpu_baseline is False:
+        from oracle.oracle import compress_patterns as cpu_compress
+
+        ns = min(N, 1_000_000)
+        a, b, c = eng.compress_patterns(raw[:, :ns])
+        oa, ob, oc = cpu_compress(raw[:, :ns])
+        full_ok = bool(np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(c, oc))
+    line = {
+        "metric": "compress_sites_per_s", "value": N / (kms_step * 1e-3) if kms_step else None, "unit": "sites/s",
+        "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": kms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": wl["name"], "taxa": T, "sites": N, "patterns_found": int(P),
+                   "l2": "inputs exceed L2 (%.2f GB alignment)" % (T * N / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": "compress (transpose + hash + insert + verify + scan + gather)",
+                     "achieved": comp_bytes / (kms_step * 1e-3) / 1e9 if kms_step else None, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": comp_bytes / (kms_step * 1e-3) / 1e9 / hbm_peak if kms_step else None,
+                     "traffic": None, "peak_source": peak_src,
+                     "bytes_model": "compulsory: alignment read once, patterns + weights + site map written once"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": N / (ms * 1e-3), "unit": "sites/s", "h2d_bytes_per_step": int(raw.nbytes),
+                "d2h_bytes_per_step": int(T * P + 8 * P + 4 * N), "ms_per_step": ms, "steps": steps},
+        "gpu_launches": int(eng.launch_count - l0), "clocks": clocks,
+        "check": {"patterns": int(P), "weights_sum": float(wt.sum()), "equals_oracle_on_first_1M_sites": full_ok},
+    }
+    print(json.dumps(line))
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,6 +348,10 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, peak_src = peaks()
+
+    if args.workload == "compress":
+        run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src)
+        return
 
     T, S, K = wl["T"], wl["S"], wl["K"]
     n_total = wl["N"] * (world if args.scaling == "weak" else 1)

@@ -53,19 +53,107 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
   x ^= x >> 31;
   return x;
 }
+// Record hash = finalise(seed ^ sum over 32-bit words w of term(w, position)): the sum is
+// commutative, so lanes can each take some words and combine by shuffles.
+// A term is a 32-bit avalanche (murmur3 finaliser) of the position-salted word, widened by a
+// position-dependent odd multiplier: ~10 integer instructions per 4 bytes (a splitmix64 per
+// word cost three times that and made the transpose ALU-bound; a plain multiply-add term
+// collided persistently on real alignments -- the verification caught it).
+__device__ __forceinline__ uint64_t hash_term(uint32_t word, int pos) {
+  const uint32_t salt = (uint32_t)(pos + 1) * 0x9e3779b1u;
+  uint32_t x = word ^ salt;
+  x ^= x >> 16; x *= 0x85ebca6bu;
+  x ^= x >> 13; x *= 0xc2b2ae35u;
+  x ^= x >> 16;
+  return (uint64_t)x * (salt | 1u) + ((uint64_t)x << 32);
+}
+__device__ __forceinline__ uint64_t hash_final(uint64_t seed, uint64_t sum) {
+  const uint64_t h = mix64(seed ^ sum);
+  return h ? h : 1;
+}
 
-// one thread per site: 64-bit hash of its TP-byte record (TP multiple of 16), never 0
+// Fast path for 1-byte elements and N % 4 == 0: a thread turns a 4-taxa x 4-sites micro-tile
+// (four aligned 32-bit loads, lanes along the sites: 128 contiguous bytes per row and warp)
+// into four words "4 taxa of one site" with byte permutes, parks them in a site-major
+// shared-memory tile, and the CTA copies whole records out (256 contiguous bytes per site).
+constexpr int kCmpTileSites = 128, kCmpTileTaxa = 256, kCmpPitch = kCmpTileTaxa + 4;
+__global__ void __launch_bounds__(256)
+cmp_transpose4_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ rec, int T, int64_t N, int TP,
+                      uint64_t seed, uint64_t *__restrict__ key) {  // key != NULL (one taxa tile): hash on the way out
+  extern __shared__ __align__(16) uint8_t ttile[];  // [128 sites][kCmpPitch]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s0 = (int64_t)blockIdx.x * kCmpTileSites;
+  const int t0 = blockIdx.y * kCmpTileTaxa;
+  const int tt = min(kCmpTileTaxa, T - t0);              // taxa in this tile
+  const int tq_n = (tt + 3) / 4;
+  const int64_t s = s0 + 4 * lane;                       // this lane's four sites
+  constexpr int U = 4;  // micro-tiles in flight per thread: 16 independent 128-byte row requests per warp
+  for (int tq0 = warp; tq0 < tq_n; tq0 += 8 * U) {
+    uint32_t r[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = t0 + 4 * (tq0 + 8 * u) + j;
+        r[u][j] = (tq0 + 8 * u < tq_n && t < T && s < N) ? __ldg(reinterpret_cast<const uint32_t *>(in + (int64_t)t * N + s)) : 0u;
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int tq = tq0 + 8 * u;
+      if (tq < tq_n) {
+        const uint32_t a = __byte_perm(r[u][0], r[u][1], 0x5140), b = __byte_perm(r[u][2], r[u][3], 0x5140);
+        const uint32_t c = __byte_perm(r[u][0], r[u][1], 0x7362), d = __byte_perm(r[u][2], r[u][3], 0x7362);
+        uint32_t *row = reinterpret_cast<uint32_t *>(ttile + (size_t)(4 * lane) * kCmpPitch + 4 * tq);
+        row[0] = __byte_perm(a, b, 0x5410);
+        row[kCmpPitch / 4] = __byte_perm(a, b, 0x7632);
+        row[2 * (kCmpPitch / 4)] = __byte_perm(c, d, 0x5410);
+        row[3 * (kCmpPitch / 4)] = __byte_perm(c, d, 0x7632);
+      }
+    }
+  }
+  __syncthreads();
+  const int words = tq_n;  // 32-bit words per record piece (padding taxa are zero)
+  for (int i = warp; i < kCmpTileSites; i += 8) {
+    const int64_t si = s0 + i;
+    if (si >= N) break;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(ttile + (size_t)i * kCmpPitch);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(rec + si * TP + t0);
+    uint64_t part = 0;
+    for (int wd = lane; wd < words; wd += 32) {
+      const uint32_t v = src[wd];
+      dst[wd] = v;
+      part += hash_term(v, wd);
+    }
+    if (key) {
+      // the zero padding words of the record (positions words .. TP/4-1) belong to the hash too
+      for (int wd = words + lane; wd < TP / 4; wd += 32) part += hash_term(0u, wd);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if (lane == 0) key[si] = hash_final(seed, part);
+    }
+  }
+}
+
+// G lanes per site (G = power of two <= 32, about one lane per 16-byte chunk): 64-bit hash of the
+// TP-byte record (TP multiple of 16), never 0. Lanes of a group read consecutive chunks.
+template <int G>
 __global__ void __launch_bounds__(256)
 cmp_hash_kernel(const uint8_t *__restrict__ rec, int64_t N, int TP, uint64_t seed, uint64_t *__restrict__ key) {
-  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(rec + s * TP);
-    uint64_t h = seed;
-    for (int i = 0; i < TP / 16; ++i) {
-      const uint4 v = __ldg(p + i);
-      h = mix64(h ^ (((uint64_t)v.y << 32) | v.x)) + 0x9e3779b97f4a7c15ull;
-      h = mix64(h ^ (((uint64_t)v.w << 32) | v.z)) + 0x9e3779b97f4a7c15ull;
+  const int sub = threadIdx.x % G;
+  const int64_t stride = (int64_t)gridDim.x * (256 / G);
+  for (int64_t s0 = (int64_t)blockIdx.x * (256 / G); s0 < N; s0 += stride) {  // all lanes of a warp stay in the loop
+    const int64_t s = s0 + threadIdx.x / G;
+    uint64_t part = 0;
+    if (s < N) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(rec + s * TP);
+      for (int i = sub; i < TP / 16; i += G) {
+        const uint4 v = __ldg(p + i);
+        part += hash_term(v.x, 4 * i) + hash_term(v.y, 4 * i + 1) + hash_term(v.z, 4 * i + 2) + hash_term(v.w, 4 * i + 3);
+      }
     }
-    key[s] = h ? h : 1;
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (s < N && sub == 0) key[s] = hash_final(seed, part);
   }
 }
 
@@ -86,24 +174,33 @@ cmp_insert_kernel(const uint64_t *__restrict__ key, int64_t N, unsigned long lon
   }
 }
 
-// every site against its representative; counts differing records (hash collisions)
+// every site against its representative, G lanes per site (consecutive 16-byte chunks); counts
+// differing records (hash collisions)
+template <int G>
 __global__ void __launch_bounds__(256)
 cmp_verify_kernel(const uint8_t *__restrict__ rec, int64_t N, int TP, const int *__restrict__ trep,
                   const uint32_t *__restrict__ slot_of, int *__restrict__ is_rep,
                   unsigned long long *__restrict__ n_collide) {
+  const int sub = threadIdx.x % G;
+  const int64_t stride = (int64_t)gridDim.x * (256 / G);
   unsigned long long bad = 0;
-  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
-    const int r = trep[slot_of[s]];
-    is_rep[s] = (r == (int)s);
-    if (r != (int)s) {
-      const uint4 *a = reinterpret_cast<const uint4 *>(rec + s * TP), *b = reinterpret_cast<const uint4 *>(rec + (int64_t)r * TP);
-      bool same = true;
-      for (int i = 0; i < TP / 16; ++i) {
-        const uint4 x = __ldg(a + i), y = __ldg(b + i);
-        same = same && x.x == y.x && x.y == y.y && x.z == y.z && x.w == y.w;
+  for (int64_t s0 = (int64_t)blockIdx.x * (256 / G); s0 < N; s0 += stride) {
+    const int64_t s = s0 + threadIdx.x / G;
+    int diff = 0;
+    if (s < N) {
+      const int r = trep[slot_of[s]];
+      if (sub == 0) is_rep[s] = (r == (int)s);
+      if (r != (int)s) {
+        const uint4 *a = reinterpret_cast<const uint4 *>(rec + s * TP), *b = reinterpret_cast<const uint4 *>(rec + (int64_t)r * TP);
+        for (int i = sub; i < TP / 16; i += G) {
+          const uint4 x = __ldg(a + i), y = __ldg(b + i);
+          diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+        }
       }
-      if (!same) ++bad;
     }
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, off);
+    if (s < N && sub == 0 && diff) ++bad;
   }
   if (bad) atomicAdd(n_collide, bad);
 }

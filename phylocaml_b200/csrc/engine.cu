@@ -1483,9 +1483,23 @@ extern "C" int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const 
   unsigned long long hColl = 0;
   {
     ProfScope prof(e, KC_COMPRESS);
+    const uint64_t kCmpSeed0 = 0x243f6a8885a308d3ull;
+    bool fused_hash = false;
+    const int chunks = TP / 16;
+    const int G = chunks >= 32 ? 32 : (chunks >= 16 ? 16 : (chunks >= 8 ? 8 : (chunks >= 4 ? 4 : (chunks >= 2 ? 2 : 1))));
+    const int gG = grid_for(N, 256 / G, e->sm_count * 16);
     CK(cudaMemsetAsync(dRec, 0, (size_t)N * TP, st));  // record padding must compare equal
     switch (EB) {
-      case 1: launch_cmp_transpose<1>(dIn, dRec, T, N, TP, st); break;
+      case 1:
+        if (N % 4 == 0) {
+          dim3 grid((unsigned)((N + kCmpTileSites - 1) / kCmpTileSites), (unsigned)((T + kCmpTileTaxa - 1) / kCmpTileTaxa));
+          fused_hash = grid.y == 1;  // whole records pass through shared memory: hash them on the way out
+          cmp_transpose4_kernel<<<grid, 256, kCmpTileSites * kCmpPitch, st>>>(dIn, dRec, T, N, TP, kCmpSeed0,
+                                                                             fused_hash ? dKey : nullptr);
+        } else {
+          launch_cmp_transpose<1>(dIn, dRec, T, N, TP, st);
+        }
+        break;
       case 2: launch_cmp_transpose<2>(dIn, dRec, T, N, TP, st); break;
       case 4: launch_cmp_transpose<4>(dIn, dRec, T, N, TP, st); break;
       default: launch_cmp_transpose<8>(dIn, dRec, T, N, TP, st);
@@ -1495,11 +1509,28 @@ extern "C" int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const 
       CK(cudaMemsetAsync(dTKey, 0, 8 * (size_t)M, st));
       CK(cudaMemsetAsync(dTRep, 0x7f, 4 * (size_t)M, st));
       CK(cudaMemsetAsync(dColl, 0, 16, st));
-      cmp_hash_kernel<<<g, 256, 0, st>>>(dRec, N, TP, 0x243f6a8885a308d3ull + 0x9e3779b97f4a7c15ull * (uint64_t)attempt, dKey);
-      LAUNCH_CHECK();
+      if (!(fused_hash && attempt == 0)) {
+        const uint64_t seed = kCmpSeed0 + 0x9e3779b97f4a7c15ull * (uint64_t)attempt;
+        switch (G) {
+          case 32: cmp_hash_kernel<32><<<gG, 256, 0, st>>>(dRec, N, TP, seed, dKey); break;
+          case 16: cmp_hash_kernel<16><<<gG, 256, 0, st>>>(dRec, N, TP, seed, dKey); break;
+          case 8: cmp_hash_kernel<8><<<gG, 256, 0, st>>>(dRec, N, TP, seed, dKey); break;
+          case 4: cmp_hash_kernel<4><<<gG, 256, 0, st>>>(dRec, N, TP, seed, dKey); break;
+          case 2: cmp_hash_kernel<2><<<gG, 256, 0, st>>>(dRec, N, TP, seed, dKey); break;
+          default: cmp_hash_kernel<1><<<gG, 256, 0, st>>>(dRec, N, TP, seed, dKey);
+        }
+        LAUNCH_CHECK();
+      }
       cmp_insert_kernel<<<g, 256, 0, st>>>(dKey, N, dTKey, dTRep, M - 1, dSlot);
       LAUNCH_CHECK();
-      cmp_verify_kernel<<<g, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl);
+      switch (G) {
+        case 32: cmp_verify_kernel<32><<<gG, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl); break;
+        case 16: cmp_verify_kernel<16><<<gG, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl); break;
+        case 8: cmp_verify_kernel<8><<<gG, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl); break;
+        case 4: cmp_verify_kernel<4><<<gG, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl); break;
+        case 2: cmp_verify_kernel<2><<<gG, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl); break;
+        default: cmp_verify_kernel<1><<<gG, 256, 0, st>>>(dRec, N, TP, dTRep, dSlot, dFlag, dColl);
+      }
       LAUNCH_CHECK();
       CK(cudaMemcpyAsync(&hColl, dColl, 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
