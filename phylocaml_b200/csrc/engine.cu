@@ -69,7 +69,9 @@ struct phylo_engine {
   int opt_fitch_walk = 1;  // Fitch tree kernel: 0 = L2 walk, 1 = auto, 2 = register walk, 3 = on-chip tiles
   unsigned long long *dAcc = nullptr;  // tile kernel accumulators (all zero between calls)
   size_t capAcc = 0, tileSmem = 0;
-  unsigned long long tileSeq = 0;
+  unsigned long long tileSeq = 0, treeSeq = 0;
+  unsigned int *dTreeDone = nullptr;  // CTA counter of the fused final fold (zero between calls)
+  bool fused_result_ready = false;    // the last fused evaluation already left lnL in hScalar[0]
   int tileOcc = 1;
   bool tileWeighted = false;
   int opt_fused = 1;  // 0 = one kernel per node, 1 = tree-fused (warp-autonomous where eligible), 2 = tile kernel only
@@ -301,7 +303,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
+  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -1051,7 +1053,7 @@ static TreeWGeom treew_geometry(const phylo_engine *e, int depth, int n_steps, b
     const int64_t units = (ngroups + R - 1) / R;
     w = (int)std::max<int64_t>(1, std::min<int64_t>(w, (units + e->sm_count - 1) / e->sm_count));
     g.warps = w;
-    g.smem = fixed + (size_t)w * wb;
+    g.smem = std::max(fixed + (size_t)w * wb, (size_t)kTreeWFuseBytes + 1024);  // the fused final fold reuses it
     return g;
   };
   if (want_R == 1 || want_R == 2) return fit(want_R, want_slev > 0 ? want_slev : kTreeWSmemLevels, want_R == 1 ? kTreeWMaxWarps : 8);
@@ -1088,8 +1090,10 @@ static cudaError_t launch_treew(phylo_engine *e, const TreeWArgs &wargs, const T
 }
 
 static cudaError_t launch_treew_k(phylo_engine *e, const TreeArgs &a, const TreeWGeom &geo, int64_t g_begin, int64_t g_end,
-                                  cudaStream_t cs) {
+                                  cudaStream_t cs, const TreeWArgs *fuse = nullptr) {
   TreeWArgs w;
+  if (fuse) w = *fuse;
+  else { w.fuse_reduce = 0; w.inline_prog = 0; }
   w.t = a;
   w.tmaps = (const char *)e->dTmaps;
 #define TREEW(KV)                                                                             \
@@ -1193,7 +1197,32 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
       else e->hT[2 * i] = st.t_left;
     }
   }
-  CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
+  // small alignments on the warp-autonomous kernel: program in the kernel parameters, final
+  // reduction and result publication inside the kernel (see TreeWArgs)
+  const bool fuse = useW && !host_masks && e->nPart <= kLnlBlock;
+  TreeWArgs fargs;
+  fargs.fuse_reduce = 0;
+  fargs.inline_prog = 0;
+  if (fuse) {
+    if (!e->dTreeDone) {
+      CK(cudaMalloc(&e->dTreeDone, sizeof(unsigned int)));
+      CK(cudaMemset(e->dTreeDone, 0, sizeof(unsigned int)));
+    }
+    fargs.fuse_reduce = 1;
+    fargs.n_part = e->nPart;
+    fargs.partials = e->dPart;
+    fargs.done_counter = e->dTreeDone;
+    double *dev_out = nullptr;
+    CK(cudaHostGetDevicePointer((void **)&dev_out, e->hScalar + 16, 0));
+    fargs.host_out = dev_out;
+    fargs.seq = ++e->treeSeq;
+    const size_t wbytes = sizeof(TreeWInstr) * pl.steps.size();
+    if (wbytes <= (size_t)kTreeWInlineProg) {
+      std::memcpy(fargs.prog_inline, e->hProg, wbytes);
+      fargs.inline_prog = 1;
+    }
+  }
+  if (!fargs.inline_prog) CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
   if ((rc = build_pt(e, nb, useW ? 0 : 1)) != PHYLO_OK) return rc;
   TreeArgs a;
   a.prog = (const TreeInstr *)e->dProg;
@@ -1232,7 +1261,12 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   const int64_t tile = useW ? 32 : (int64_t)kTreeR * kTreeThreads / e->K, ntiles = (e->N + tile - 1) / tile;
   if (!host_masks) {
     ProfScope prof(e, KC_TREE_FUSED);
-    cudaError_t st = useW ? launch_treew_k(e, a, geo, 0, ntiles, e->stream) : launch_tree_k(e, a, smem, 0, ntiles, e->stream);
+    if (fuse) {
+      volatile double *flag = e->hScalar + 17;
+      *flag = -1.0;  // sequence numbers are positive integers' bit patterns: never this value
+    }
+    cudaError_t st = useW ? launch_treew_k(e, a, geo, 0, ntiles, e->stream, fuse ? &fargs : nullptr)
+                          : launch_tree_k(e, a, smem, 0, ntiles, e->stream);
     if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused launch: %s", cudaGetErrorString(st));
   } else {
     // slabs of whole 1024-pattern blocks: >= ~2 waves of tiles each, at most 16 slabs
@@ -1267,15 +1301,39 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     CK(cudaEventRecord(e->auxDone, e->auxStream));
     CK(cudaStreamWaitEvent(e->stream, e->auxDone, 0));
   }
+  if (e->opt_retain)
+    for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = true;
+  else
+    for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = false;
+  e->fused_result_ready = false;
+  if (fuse) {
+    // spin on the sequence number the last CTA writes after lnL (mapped host memory); a
+    // blocking stream sync would cost more than these kernels. Fallback after 2 ms.
+    const double want = [&] { double d; const long long q = (long long)fargs.seq; std::memcpy(&d, &q, 8); return d; }();
+    volatile double *out = e->hScalar + 16;
+    bool seen = false;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int spin = 0;; ++spin) {
+      double f = out[1];
+      if (std::memcmp(&f, &want, 8) == 0) { seen = true; break; }
+      if ((spin & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+    }
+    if (!seen) {
+      CK(cudaStreamSynchronize(e->stream));
+      double f = out[1];
+      if (std::memcmp(&f, &want, 8) != 0) return fail(e, PHYLO_ERR_CUDA, "lk_score_tree: the tree kernel did not publish its result");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    e->hScalar[0] = out[0];
+    e->fused_result_ready = true;
+    *done = true;
+    return PHYLO_OK;
+  }
   {
     ProfScope prof(e, KC_REDUCE);
     fold_groups_kernel<<<(int)e->nPart, 32, 0, e->stream>>>(e->dGroups, (e->N + 31) / 32, e->dPart);
     LAUNCH_CHECK();
   }
-  if (e->opt_retain)
-    for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = true;
-  else
-    for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = false;
   if ((rc = lk_finish_reduce(e, e->hScalar)) != PHYLO_OK) return rc;
   *done = true;
   return PHYLO_OK;
@@ -1339,7 +1397,7 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
     bool done = false;
     if ((rc = lk_score_tree_fused(e, ops, n_ops, root_a, root_b, root_t, &done)) != PHYLO_OK) return rc;
     if (done) {
-      CK(cudaStreamSynchronize(e->stream));
+      if (!e->fused_result_ready) CK(cudaStreamSynchronize(e->stream));
       *lnl_out = e->hScalar[0];
       e->lk_evaluated = true;
       if (e->prof_on) prof_resolve_lazy(e);

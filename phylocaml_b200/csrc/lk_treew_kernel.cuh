@@ -88,9 +88,22 @@ __device__ __forceinline__ void matvec_u(const double2 *pm, const d4 (&v)[R], do
   }
 }
 
+constexpr int kTreeWFuseBytes = (kLnlBlock + 32) * 8;  // dynamic shared memory the fused final fold needs
+constexpr int kTreeWInlineProg = 3072;  // bytes of program that can travel in the kernel parameters
 struct TreeWArgs {
   TreeArgs t;              // shared fields (prog is a TreeWInstr array here)
   const char *tmaps;       // RETAIN: CUtensorMap per node slot (128 bytes each)
+  // Small alignments (<= 1024 level-1 blocks): the last CTA to finish folds the groups into
+  // the block partials and the final sum (the same canonical tree as fold_groups_kernel +
+  // reduce1024_kernel) and publishes lnL + a sequence number into mapped host memory -- the
+  // call is then pt_build + this kernel, and the host spins on the flag instead of a sync.
+  int fuse_reduce, inline_prog;
+  int64_t n_part;
+  double *partials;                 // [n_part] level-1 block partials (kept for get_block_partials)
+  unsigned int *done_counter;       // zero between calls
+  volatile double *host_out;        // mapped: [0] = lnL, [1] = sequence number (as a double bit pattern)
+  unsigned long long seq;
+  __align__(16) unsigned char prog_inline[kTreeWInlineProg];
 };
 
 template <int K, int R, bool RETAIN>
@@ -120,7 +133,10 @@ __global__ void __launch_bounds__(R == 1 ? kTreeWMaxWarps * 32 : 256, 1) lk_tree
   constexpr int SPILL_LEVEL = CH * 32 + 8;  // in double2 units
   double2 *spill = a.spill + ((size_t)blockIdx.x * kTreeWMaxWarps + warp) * (treew_spill_bytes(K, a.stack_depth, a.smem_levels, R) / 16);
 
-  for (int i = threadIdx.x; i < n_steps; i += blockDim.x) sprog[i] = __ldg(reinterpret_cast<const int4 *>(a.prog) + i);
+  {
+    const int4 *gprog = wa.inline_prog ? reinterpret_cast<const int4 *>(wa.prog_inline) : reinterpret_cast<const int4 *>(a.prog);
+    for (int i = threadIdx.x; i < n_steps; i += blockDim.x) sprog[i] = gprog[i];
+  }
   if (threadIdx.x == 0) sprog[n_steps] = make_int4(0, 0, 0, -1);  // harmless word past the end
   if (lane == 0) {
     mbar_init(&bar[0], 1);
@@ -147,7 +163,9 @@ __global__ void __launch_bounds__(R == 1 ? kTreeWMaxWarps * 32 : 256, 1) lk_tree
     u_hi = min(u_end, u_lo + per);
     u_step = 1;
   }
-  if (u_lo >= u_hi) return;
+  const bool has_work = u_lo < u_hi;
+  if (!has_work && !wa.fuse_reduce) return;
+  if (has_work) {
 
   double pi[4], prob[K];
 #pragma unroll
@@ -448,6 +466,43 @@ __global__ void __launch_bounds__(R == 1 ? kTreeWMaxWarps * 32 : 256, 1) lk_tree
   if (RETAIN) {
     if (lane == 0) bulk_wait0();  // staged tiles must be read out before the CTA may exit
     __syncwarp();
+  }
+  }  // has_work
+  if (wa.fuse_reduce) {
+    // ---- last CTA: canonical fold of all group sums -> block partials -> lnL, straight to the host
+    // (the warps' working storage is dead by now: the fold reuses the dynamic shared memory; the
+    // host sizes it to at least kTreeWFuseBytes)
+    __shared__ bool is_last;
+    double *fvals = reinterpret_cast<double *>(base), *fwsum = fvals + kLnlBlock;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      is_last = atomicAdd(wa.done_counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const int64_t n_groups = (a.N + 31) / 32;
+      for (int b = threadIdx.x; b < kLnlBlock; b += blockDim.x) fvals[b] = 0.0;
+      __syncthreads();
+      for (int64_t b = warp; b < wa.n_part; b += nwarps) {
+        const int64_t gi = b * 32 + lane;
+        const double v = warp_fold(gi < n_groups ? __ldcg(a.groups + gi) : 0.0);
+        if (lane == 0) {
+          fvals[b] = v;
+          wa.partials[b] = v;
+        }
+      }
+      __syncthreads();
+      const double r = block_fold_1024(fvals, fwsum);
+      if (threadIdx.x == 0) {
+        wa.host_out[0] = r;
+        __threadfence_system();
+        wa.host_out[1] = __longlong_as_double((long long)wa.seq);
+        *wa.done_counter = 0;
+        __threadfence_system();
+      }
+    }
   }
 }
 
