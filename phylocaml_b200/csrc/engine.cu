@@ -1,7 +1,10 @@
 // C ABI implementation (include/phylo_engine.h) of the B200 tree-scoring engine.
 // Host-side handle, device arenas and kernel dispatch; all arithmetic lives in the kernels
-// (lk_kernels.cuh, fitch_kernels.cuh). No CPU fallback anywhere: every entry point that
-// computes launches CUDA kernels on the handle's device.
+// (lk_kernels.cuh: P(t), per-node pruning, DMMA kernels, root joins; lk_treew_kernel.cuh /
+// lk_tree_kernel.cuh: single-launch tree-fused pruning; lk_edge_kernels.cuh: branch-length
+// loop; fitch_kernels.cuh: Fitch / bitvector; compress_kernels.cuh: site-pattern compression).
+// No CPU fallback anywhere: every entry point that computes launches CUDA kernels on the
+// handle's device.
 #include <cuda.h>  // CUtensorMap types only; the driver entry point is resolved at run time
 #include <cuda_runtime.h>
 
@@ -1247,7 +1250,6 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     // two regions: consecutive slabs of phylo_lk_score_alignment run on two streams
     const size_t region = treew_spill_bytes(e->K, pl.depth, geo.slev, geo.R) * kTreeWMaxWarps * (size_t)e->sm_count, need = 2 * region;
     a.smem_levels = geo.slev;
-    a.obufs = 1;
     a.interleave = geo.interleave;
     if (need > e->capSpill) {
       CK(cudaStreamSynchronize(e->stream));

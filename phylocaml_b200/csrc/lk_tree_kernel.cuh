@@ -102,7 +102,7 @@ struct TreeArgs {
   double *groups;          // [ceil(N/32)] sums of 32 consecutive weighted site lnL (canonical level 0)
   int stack_depth;
   double2 *spill;          // warp-autonomous kernel: global scratch for deep stack levels
-  int smem_levels, obufs, interleave;  // warp-autonomous kernel: stack levels in smem, staging tiles (1|2), group order
+  int smem_levels, interleave;  // warp-autonomous kernel: stack levels in shared memory, group order
   int64_t tile_begin, tile_end;  // tiles this launch covers (a slab of the alignment)
 };
 

@@ -482,7 +482,8 @@ def _score(eng, model, tips, ops, ra, rb, rt, n_nodes, fused, retain, weights=No
 
 
 @pytest.mark.parametrize("T,N,kind", [(16, 10000, "random"), (64, 3000, "random"), (200, 700, "caterpillar"),
-                                      (3, 50, "random"), (2, 33, "random"), (40, 1, "random")])
+                                      (3, 50, "random"), (2, 33, "random"), (40, 1, "random"),
+                                      (600, 257, "random"), (24, 90000, "random")])
 def test_fused_tree_equals_per_node_path_bitwise(eng, oracle, T, N, kind):
     """The single-launch tree-fused kernel and the one-kernel-per-node path run the same
     arithmetic in the same order: lnL, site lnL, CLVs and scale counters are bit-identical;
