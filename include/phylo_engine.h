@@ -201,6 +201,19 @@ int phylo_fitch_get_states(phylo_engine *e, int node, int which, void *out);
 /* upload one node's preliminary sets (Bitvector.of_array, lib/bitvector/bv.c:305-327) */
 int phylo_fitch_set_states(phylo_engine *e, int node, const void *codes);
 
+/* General-TCM parsimony median on state sets -- CostMatrix.find_median_general / _metric
+ * (lib/costMatrix.ml:68-86, :107-124): for two sets a, b the cost is the minimum over i in a,
+ * j in b and a candidate median state k of M[i][k] + M[j][k], the median is the set of all k
+ * that reach it (candidates: every state; metric != 0: only the states of a | b). M is
+ * n_states x n_states, row-major, 0 <= M <= 30000, n_states <= 6 and equal to the n_states of
+ * phylo_fitch_set_tips; the medians live in the same node slots as the Fitch sets. With the
+ * 0/1 matrix both variants are the Fitch rule (the reference tests exactly that,
+ * test/costMatrixTest.ml:110-125). parent < 0 in phylo_tcm_median_2: cost only. */
+int phylo_tcm_set_matrix(phylo_engine *e, int n_states, const int32_t *M, int metric);
+int phylo_tcm_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *cost_out);
+int phylo_tcm_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                         uint64_t *length_out);
+
 /* Bitvector set algebra over node slots (lib/bitvector/bv.c:59-144; stubs :405-453) */
 int phylo_bv_union(phylo_engine *e, int dst, int a, int b);
 int phylo_bv_inter(phylo_engine *e, int dst, int a, int b);

@@ -66,6 +66,36 @@ def compress_patterns(masks, weights=None):
     return np.ascontiguousarray(masks[:, first[order]]), w, s2p
 
 
+def tcm_median_table(M, metric=False):
+    """CPU restatement of CostMatrix.find_median_general (lib/costMatrix.ml:68-86) and
+    find_median_metric (:107-124) for every pair of state sets: the literal fold over
+    (istate in a, jstate in b, k in candidates) with find_median_pair (:55-66) collecting every
+    k that reaches the minimum. Returns (cost[a][b], median[a][b]) indexed by bit masks."""
+    M = np.asarray(M)
+    S = M.shape[0]
+    sets = 1 << S
+    cost = np.zeros((sets, sets), dtype=np.int64)
+    med = np.zeros((sets, sets), dtype=np.int64)
+    for a in range(1, sets):
+        for b in range(1, sets):
+            cand = [k for k in range(S) if (not metric) or ((a | b) >> k) & 1]
+            best, assign = None, 0
+            for i in range(S):
+                if not (a >> i) & 1:
+                    continue
+                for j in range(S):
+                    if not (b >> j) & 1:
+                        continue
+                    for k in cand:  # find_median_pair
+                        c = int(M[i][k]) + int(M[j][k])
+                        if best is None or c < best:
+                            best, assign = c, 1 << k
+                        elif c == best:
+                            assign |= 1 << k
+            cost[a][b], med[a][b] = best, assign
+    return cost, med
+
+
 class Oracle:
     def __init__(self):
         path = os.path.join(HERE, "liboracle.so")

@@ -71,6 +71,8 @@ struct phylo_engine {
   int64_t N = 0;
   int opt_fitch_walk = 1;  // Fitch tree kernel: 0 = L2 walk, 1 = auto, 2 = register walk, 3 = on-chip tiles
   unsigned long long *dAcc = nullptr;  // tile kernel accumulators (all zero between calls)
+  uint32_t *dTcm = nullptr;            // general-TCM median table: 2^S x 2^S entries (cost | median << 16)
+  int tcmS = 0;
   size_t capAcc = 0, tileSmem = 0;
   unsigned long long tileSeq = 0, treeSeq = 0;
   unsigned int *dTreeDone = nullptr;  // CTA counter of the fused final fold (zero between calls)
@@ -306,7 +308,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
+  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -2318,6 +2320,112 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
   CK(cudaStreamSynchronize(e->stream));
   *length_out = e->hCost[n_ops + 1];
   for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[o];
+  if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
+}
+
+// ------------------------------------------- general-TCM median (CostMatrix, lib/costMatrix.ml) ----
+extern "C" int phylo_tcm_set_matrix(phylo_engine *e, int n_states, const int32_t *M, int metric) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (n_states < 2 || n_states > 6 || !M) return fail(e, PHYLO_ERR_ARG, "tcm_set_matrix: 2 <= n_states <= 6 and a matrix are required");
+  const int S = n_states, sets = 1 << S;
+  for (int i = 0; i < S * S; ++i)
+    if (M[i] < 0 || M[i] > 30000) return fail(e, PHYLO_ERR_ARG, "tcm_set_matrix: costs must be in [0, 30000]");
+  std::vector<uint32_t> tab((size_t)sets * sets, 0);
+  for (int a = 1; a < sets; ++a)
+    for (int b = 1; b < sets; ++b) {
+      // find_median_general (lib/costMatrix.ml:68-86) / find_median_metric (:107-124): the best k over
+      // all (istate, jstate) pairs is the best k for the cheapest istate and the cheapest jstate
+      int best = INT32_MAX;
+      uint32_t med = 0;
+      for (int k = 0; k < S; ++k) {
+        if (metric && !(((a | b) >> k) & 1)) continue;
+        int ca = INT32_MAX, cb = INT32_MAX;
+        for (int i = 0; i < S; ++i) {
+          if ((a >> i) & 1) ca = std::min(ca, M[i * S + k]);
+          if ((b >> i) & 1) cb = std::min(cb, M[i * S + k]);
+        }
+        const int c = ca + cb;
+        if (c < best) { best = c; med = 1u << k; }
+        else if (c == best) med |= 1u << k;
+      }
+      tab[(size_t)a * sets + b] = (uint32_t)best | (med << 16);
+    }
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  dfree(e->dTcm);
+  CK(cudaMalloc(&e->dTcm, sizeof(uint32_t) * tab.size()));
+  CK(cudaMemcpy(e->dTcm, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice));
+  e->tcmS = S;
+  return PHYLO_OK;
+}
+
+// one median (store) or the cost only (parent < 0) on the engine's stream; adds into dCost[idx]
+static int tcm_launch(phylo_engine *e, int parent, int left, int right, size_t idx) {
+  const int g = grid_for(e->fWords, 256, e->sm_count * 8);
+  const size_t smem = sizeof(uint32_t) << (2 * e->tcmS);
+  uint32_t *c = parent >= 0 ? e->fPre[parent] : nullptr;
+  const uint32_t *a = e->fPre[left], *b = e->fPre[right];
+  ProfScope prof(e, KC_FITCH_NODE);
+  if (parent >= 0) {
+    NP_DISPATCH(e->fNPdev, (tcm_median2_kernel<NP, true><<<g, 256, smem, e->stream>>>(a, b, c, e->fWords, e->fN, e->tcmS, e->dTcm, e->dFW, e->dCost + idx)));
+  } else {
+    NP_DISPATCH(e->fNPdev, (tcm_median2_kernel<NP, false><<<g, 256, smem, e->stream>>>(a, b, c, e->fWords, e->fN, e->tcmS, e->dTcm, e->dFW, e->dCost + idx)));
+  }
+  LAUNCH_CHECK();
+  return PHYLO_OK;
+}
+
+static int tcm_ready(phylo_engine *e, const char *who) {
+  if (e->fT == 0) return fail(e, PHYLO_ERR_STATE, "%s: no Fitch data loaded", who);
+  if (!e->dTcm) return fail(e, PHYLO_ERR_STATE, "%s: call phylo_tcm_set_matrix first", who);
+  if (e->tcmS != e->fNP) return fail(e, PHYLO_ERR_STATE, "%s: the cost matrix has %d states, the characters %d", who, e->tcmS, e->fNP);
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_tcm_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *cost_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = tcm_ready(e, "tcm_median_2")) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, left, true, "tcm_median_2")) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, right, true, "tcm_median_2")) != PHYLO_OK) return rc;
+  if (parent >= 0) {
+    if ((rc = fitch_slot_ok(e, parent, false, "tcm_median_2")) != PHYLO_OK) return rc;
+    if (parent < e->fT) return fail(e, PHYLO_ERR_ARG, "tcm_median_2: parent slot %d is a tip", parent);
+    if ((rc = fitch_ensure(e, parent, false)) != PHYLO_OK) return rc;
+  }
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
+  if ((rc = tcm_launch(e, parent, left, right, 0)) != PHYLO_OK) return rc;
+  CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (cost_out) *cost_out = e->hCost[0];
+  if (parent >= 0) e->nodeCost[parent] = e->hCost[0];
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_tcm_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                    uint64_t *length_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = tcm_ready(e, "tcm_score_tree")) != PHYLO_OK) return rc;
+  if ((rc = fitch_check_schedule(e, ops, n_ops, root_a, root_b, "tcm_score_tree")) != PHYLO_OK) return rc;
+  if (!length_out) return fail(e, PHYLO_ERR_ARG, "tcm_score_tree: length_out is NULL");
+  CK(cudaSetDevice(e->device));
+  for (int o = 0; o < n_ops; ++o)
+    if ((rc = fitch_ensure(e, ops[o].parent, false)) != PHYLO_OK) return rc;
+  if ((rc = fitch_cost_capacity(e, (size_t)n_ops + 8)) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long) * (size_t)(n_ops + 2), e->stream));
+  for (int o = 0; o < n_ops; ++o)
+    if ((rc = tcm_launch(e, ops[o].parent, ops[o].left, ops[o].right, (size_t)o)) != PHYLO_OK) return rc;
+  if ((rc = tcm_launch(e, -1, root_a, root_b, (size_t)n_ops)) != PHYLO_OK) return rc;
+  CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long) * (size_t)(n_ops + 1), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  uint64_t total = 0;
+  for (int o = 0; o <= n_ops; ++o) total += e->hCost[o];
+  for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[o];
+  *length_out = total;
   if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }

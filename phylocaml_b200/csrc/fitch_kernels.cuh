@@ -493,6 +493,52 @@ fitch_uppass_kernel(uint32_t *const *__restrict__ prelim, uint32_t *const *__res
   }
 }
 
+// -------------------------------------------- general-TCM median on state sets (Sankoff side) ----
+// CostMatrix.find_median_general / find_median_metric (lib/costMatrix.ml:68-86, :107-124): for
+// two state SETS a and b,  cost = min over i in a, j in b, k in candidates of M[i][k] + M[j][k]
+// and the median is the set of all k that reach the minimum (candidates: every state, or the
+// states of a | b in the metric variant). With <= 6 states the whole function is a table of
+// 2^S x 2^S entries (cost | median << 16) built on the host from M; the kernel gathers each
+// character's two masks out of the bit-sliced planes, looks the pair up in shared memory, and
+// scatters the median back into planes. One thread per 32-character word.
+template <int NP, bool STORE>
+__global__ void __launch_bounds__(256)
+tcm_median2_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint32_t *__restrict__ c,
+                   int64_t nwords, int64_t N, int S, const uint32_t *__restrict__ table,
+                   const uint32_t *__restrict__ wt, unsigned long long *__restrict__ cost) {
+  extern __shared__ uint32_t stab[];
+  const int entries = 1 << (2 * S);
+  for (int i = threadIdx.x; i < entries; i += blockDim.x) stab[i] = table[i];
+  __syncthreads();
+  const uint32_t smask = (1u << S) - 1u;
+  unsigned long long local = 0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+    const Planes<NP> pa = ld_planes<NP>(a, w), pb = ld_planes<NP>(b, w);
+    Planes<NP> pc;
+#pragma unroll
+    for (int s = 0; s < NP; ++s) pc.v[s] = 0;
+    const uint32_t valid = valid_mask(w, N);
+    for (int ch = 0; ch < 32; ++ch) {
+      if (!((valid >> ch) & 1)) break;  // valid characters are the low bits
+      uint32_t ma = 0, mb = 0;
+#pragma unroll
+      for (int s = 0; s < NP; ++s) {
+        ma |= ((pa.v[s] >> ch) & 1u) << s;
+        mb |= ((pb.v[s] >> ch) & 1u) << s;
+      }
+      const uint32_t e = stab[((ma & smask) << S) | (mb & smask)];
+      local += (unsigned long long)(e & 0xffffu) * (wt ? wt[w * 32 + ch] : 1u);
+      if (STORE) {
+        const uint32_t med = e >> 16;
+#pragma unroll
+        for (int s = 0; s < NP; ++s) pc.v[s] |= ((med >> s) & 1u) << ch;
+      }
+    }
+    if (STORE) st_planes<NP>(c, w, pc);
+  }
+  block_add_u64(local, cost);
+}
+
 // ---------------------------------------------------------------- layout transcoding ----
 // reference layout (one character per W-bit element, lib/bitvector/bv.h:29-55) <-> planes.
 // A warp turns 32 consecutive elements into NP plane words with NP ballots.

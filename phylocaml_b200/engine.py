@@ -55,6 +55,9 @@ SIGNATURES = {
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
                                            C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
+    "phylo_tcm_set_matrix": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
+    "phylo_tcm_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "phylo_tcm_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_compress_patterns": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, _vp, _dp, _vp, C.POINTER(_i64)]),
     "phylo_lk_edge_prepare": (C.c_int, [_vp, C.c_int, C.c_int]),
     "phylo_lk_edge_eval": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp]),
@@ -286,6 +289,22 @@ class Engine:
         self._ck(self.lib.phylo_lk_score_alignment(self.h, T, N, _p(tips), tips.dtype.itemsize, _p(w, _dp), capacity,
                                                    _p(ops), len(ops), root_a, root_b, float(root_t), C.byref(out)))
         self.lk_shape = (T, N, capacity)
+        return out.value
+
+    def tcm_set_matrix(self, M, metric=False):
+        """General-TCM median table from an S x S integer cost matrix (CostMatrix, lib/costMatrix.ml)."""
+        M = np.ascontiguousarray(M, dtype=np.int32)
+        self._ck(self.lib.phylo_tcm_set_matrix(self.h, M.shape[0], _p(M), 1 if metric else 0))
+
+    def tcm_median_2(self, parent, left, right):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_tcm_median_2(self.h, parent, left, right, C.byref(out)))
+        return out.value
+
+    def tcm_score_tree(self, ops, root_a, root_b):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_tcm_score_tree(self.h, _p(ops), len(ops), root_a, root_b, C.byref(out)))
         return out.value
 
     def compress_patterns(self, masks, weights=None):

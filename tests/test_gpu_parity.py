@@ -276,6 +276,65 @@ def test_lk_optimize_branch_matches_scalar_minimiser(eng, oracle):
         assert abs(d1[0]) <= 1e-5 * abs(d2[0]) * max(t_opt, 1e-3) + 1e-6
 
 
+# ------------------------------------------------- general-TCM median (CostMatrix) ----
+@pytest.mark.parametrize("S,metric", [(4, False), (4, True), (5, False), (6, True)])
+def test_tcm_median_equals_costmatrix_restatement(eng, S, metric):
+    """phylo_tcm_median_2 == the literal restatement of CostMatrix.find_median_general / _metric
+    (lib/costMatrix.ml:68-124) for every character: median set and cost; weighted too."""
+    from oracle.oracle import tcm_median_table
+
+    rng = np.random.default_rng(S * 7 + metric)
+    M = rng.integers(0, 9, size=(S, S)).astype(np.int32)
+    M = (M + M.T) // 2
+    np.fill_diagonal(M, 0)
+    cost, med = tcm_median_table(M, metric)
+    N = 5003
+    chars = rng.integers(1, 1 << S, size=(2, N)).astype(np.uint8)
+    w = rng.integers(0, 5, N).astype(float)
+    for weights in (None, w):
+        eng.fitch_set_tips(chars, S, weights=weights, capacity=4)
+        eng.tcm_set_matrix(M, metric)
+        got = eng.tcm_median_2(2, 0, 1)
+        per_char = cost[chars[0], chars[1]]
+        assert got == int((per_char * (1 if weights is None else w)).sum())
+        assert np.array_equal(eng.fitch_get_states(2), med[chars[0], chars[1]].astype(np.uint8))
+        assert eng.tcm_median_2(-1, 0, 1) == got  # cost only
+
+
+def test_tcm_unit_costs_are_the_fitch_rule_on_a_tree(eng, oracle):
+    """With the 0/1 matrix the TCM down-pass is the Fitch down-pass (test/costMatrixTest.ml:110-125):
+    same sets at every node, same length."""
+    ops, ra, rb, n_nodes, chars = _fitch_setup(20, 4097, 4, np.uint8, seed=12)
+    eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+    want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, want_sets=True)
+    for metric in (False, True):
+        eng.tcm_set_matrix(1 - np.eye(4, dtype=np.int32), metric)
+        assert eng.tcm_score_tree(ops, ra, rb) == want["length"]
+        for op in ops:
+            p = int(op["parent"])
+            assert np.array_equal(eng.fitch_get_states(p), want["prelim"][p])
+
+
+def test_tcm_tree_length_with_transversion_costs(eng):
+    """Transition/transversion matrix (1/2) on a tree: node by node against the table oracle."""
+    from oracle.oracle import tcm_median_table
+
+    M = np.array([[0, 2, 1, 2], [2, 0, 2, 1], [1, 2, 0, 2], [2, 1, 2, 0]], dtype=np.int32)
+    cost, med = tcm_median_table(M, False)
+    ops, ra, rb, n_nodes, chars = _fitch_setup(14, 3000, 4, np.uint8, seed=21)
+    eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+    eng.tcm_set_matrix(M)
+    sets = {t: chars[t] for t in range(14)}
+    total = 0
+    for op in ops:
+        p, l, r = int(op["parent"]), int(op["left"]), int(op["right"])
+        total += int(cost[sets[l], sets[r]].sum())
+        sets[p] = med[sets[l], sets[r]].astype(np.uint8)
+    total += int(cost[sets[ra], sets[rb]].sum())
+    assert eng.tcm_score_tree(ops, ra, rb) == total
+    assert np.array_equal(eng.fitch_get_states(int(ops[-1]["parent"])), sets[int(ops[-1]["parent"])])
+
+
 # ------------------------------------------------------ site-pattern compression ----
 @pytest.mark.parametrize("dtype,T,N", [(np.uint8, 12, 50000), (np.uint8, 7, 1), (np.uint16, 5, 3001),
                                        (np.uint32, 33, 4097), (np.uint64, 3, 70000), (np.uint8, 256, 20000)])
