@@ -17,3 +17,4 @@ try:
 except Exception as ex: print("  parse failed", ex)
 PY
 done
+python bench.py --workload compress --steps 8 --warmup 1 > gpurun_out/bench_compress.json 2>> gpurun_out/bench_dna.err
