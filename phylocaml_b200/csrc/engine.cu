@@ -1975,15 +1975,43 @@ extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_b
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, ((size_t)256 << 20) / row));
   if ((rc = fitch_stage(e, row * chunk)) != PHYLO_OK) return rc;
   CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
+  // Within a chunk the H2D copy runs in pieces of ~8 MB on the copy stream while the pieces
+  // that have landed are already being transcoded on the engine's stream.
+  if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+  const int piece = (int)std::max<size_t>(1, ((size_t)8 << 20) / row);
+  for (int t = 0; t < T; ++t)
+    if ((rc = fitch_ensure(e, t, false)) != PHYLO_OK) return rc;  // allocations (and their memsets) up front
+  {
+    // the copy stream must not overtake work already queued on the engine's stream (memsets above)
+    while (e->slabEvents.empty()) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->slabEvents.push_back(ev);
+    }
+    CK(cudaEventRecord(e->slabEvents[0], e->stream));
+    CK(cudaStreamWaitEvent(e->copyStream, e->slabEvents[0], 0));
+  }
   for (int t0 = 0; t0 < T; t0 += chunk) {
     const int nt = std::min(chunk, T - t0);
-    CK(cudaMemcpyAsync(e->dStage, (const char *)codes + (size_t)t0 * row, row * nt, cudaMemcpyHostToDevice, e->stream));
-    for (int t = 0; t < nt; ++t) {
-      if ((rc = fitch_ensure(e, t0 + t, false)) != PHYLO_OK) return rc;
-      if ((rc = fitch_encode(e, (const char *)e->dStage + (size_t)t * row, e->fPre[t0 + t], e->dCost)) != PHYLO_OK)
-        return rc;
+    const int npieces = (nt + piece - 1) / piece;
+    while ((int)e->slabEvents.size() < npieces) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->slabEvents.push_back(ev);
     }
-    if (t0 + chunk < T) CK(cudaStreamSynchronize(e->stream));  // staging buffer is reused by the next chunk
+    for (int pc = 0; pc < npieces; ++pc) {
+      const int a0 = pc * piece, a1 = std::min(nt, a0 + piece);
+      CK(cudaMemcpyAsync((char *)e->dStage + (size_t)a0 * row, (const char *)codes + (size_t)(t0 + a0) * row,
+                         row * (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copyStream));
+      CK(cudaEventRecord(e->slabEvents[pc], e->copyStream));
+      CK(cudaStreamWaitEvent(e->stream, e->slabEvents[pc], 0));
+      for (int t = a0; t < a1; ++t)
+        if ((rc = fitch_encode(e, (const char *)e->dStage + (size_t)t * row, e->fPre[t0 + t], e->dCost)) != PHYLO_OK)
+          return rc;
+    }
+    if (t0 + chunk < T) {  // staging buffer is reused by the next chunk
+      CK(cudaStreamSynchronize(e->stream));
+    }
   }
   CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
