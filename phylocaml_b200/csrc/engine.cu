@@ -1693,17 +1693,21 @@ extern "C" int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, dou
       const int g = (int)std::min<int64_t>(e->nPart, (int64_t)e->sm_count * 4);
       {
         ProfScope prof(e, KC_EDGE);
-#define EDGE_EVAL(MT, GV)                                                                                          \
-  edge_eval_kernel<MT, GV><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, \
-                                                         e->pinvar, (const MT *)e->dInv, e->dWeights, e->dEdgeT, nc, \
-                                                         e->sym, e->S, e->K, e->N, e->dEdgePart)
+#define EDGE_EVAL(MT, GV, PV)                                                                                      \
+  edge_eval_kernel<MT, GV, PV><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, \
+                                                             e->pinvar, (const MT *)e->dInv, e->dWeights, e->dEdgeT, nc, \
+                                                             e->sym, e->S, e->K, e->N, e->dEdgePart)
 #define EDGE_EVAL_G(MT)                                                      \
   {                                                                          \
-    if (KS <= 4) EDGE_EVAL(MT, 1);                                           \
-    else if (KS <= 16) EDGE_EVAL(MT, 4);                                     \
-    else if (KS <= 32) EDGE_EVAL(MT, 8);                                     \
-    else if (KS <= 128) EDGE_EVAL(MT, 16);                                   \
-    else EDGE_EVAL(MT, 32);                                                  \
+    if (KS == 4) EDGE_EVAL(MT, 1, 4);                                        \
+    else if (KS < 4) EDGE_EVAL(MT, 1, 0);                                    \
+    else if (KS == 16) EDGE_EVAL(MT, 4, 4);                                  \
+    else if (KS <= 16) EDGE_EVAL(MT, 4, 0);                                  \
+    else if (KS <= 32) EDGE_EVAL(MT, 8, 0);                                  \
+    else if (KS <= 64) EDGE_EVAL(MT, 32, 2);                                 \
+    else if (KS <= 80) EDGE_EVAL(MT, 16, 5);                                 \
+    else if (KS <= 128) EDGE_EVAL(MT, 16, 0);                                \
+    else EDGE_EVAL(MT, 32, 0);                                               \
   }
         if (e->mask_dev_bytes == 1) EDGE_EVAL_G(uint8_t)
         else if (e->mask_dev_bytes == 4) EDGE_EVAL_G(uint32_t)

@@ -62,7 +62,11 @@ edge_sumtable_kernel(const void *__restrict__ asrc, const int32_t *__restrict__ 
 // G lanes share a pattern (G = 4 for DNA+G4: each lane one 32-byte chunk; 16 for 20 states x 4
 // classes; 32 for codons): consecutive lanes read consecutive doubles of the sum table, so a
 // warp request is one contiguous run, and the three sums are combined by xor-shuffles.
-template <typename MaskT, int G>
+// PER > 0: lane `sub` of a group owns the PER consecutive table entries sub*PER .. sub*PER+PER-1
+// and keeps their 3*PER coefficients in registers for the whole block (DNA+G4: G = 4, PER = 4:
+// one 256-bit load and 12 FMAs per pattern and lane). PER = 0: entries strided by G, coefficients
+// read from shared memory (any shape).
+template <typename MaskT, int G, int PER>
 __global__ void __launch_bounds__(256)
 edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum_sc,
                  const double *__restrict__ lam, const double *__restrict__ rates,
@@ -93,17 +97,43 @@ edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum
     for (int ti = 0; ti < n_t; ++ti) {
       const double *c0 = coef + (ti * 3) * KS, *c1 = c0 + KS, *c2 = c1 + KS;
       // phase 1: the three sums of every pattern of the block, G lanes per pattern
+      double cc[3][PER > 0 ? PER : 1];
+      if (PER > 0) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int km = sub_lane * PER + j;
+          cc[0][j] = km < KS ? c0[km] : 0.0;
+          cc[1][j] = km < KS ? c1[km] : 0.0;
+          cc[2][j] = km < KS ? c2[km] : 0.0;
+        }
+      }
 #pragma unroll 4
       for (int sub = 0; sub < kLnlBlock / PPB; ++sub) {
         const int64_t p = blk * kLnlBlock + sub * PPB + grp;
         double l0 = 0.0, l1 = 0.0, l2 = 0.0;
         if (p < N) {
           const double *c = sum + p * KS;
-          for (int km = sub_lane; km < KS; km += G) {
-            const double x = __ldg(c + km);
-            l0 += x * c0[km];
-            l1 += x * c1[km];
-            l2 += x * c2[km];
+          if (PER == 4) {  // 32-byte aligned when KS % 4 == 0 (the host only picks PER = 4 then)
+            const d4 x = ld256_stream(c + 4 * sub_lane);
+            l0 = ((x.x * cc[0][0] + x.y * cc[0][1]) + x.z * cc[0][2]) + x.w * cc[0][3];
+            l1 = ((x.x * cc[1][0] + x.y * cc[1][1]) + x.z * cc[1][2]) + x.w * cc[1][3];
+            l2 = ((x.x * cc[2][0] + x.y * cc[2][1]) + x.z * cc[2][2]) + x.w * cc[2][3];
+          } else if (PER > 0) {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+              const int km = sub_lane * PER + j;
+              const double x = km < KS ? __ldg(c + km) : 0.0;
+              l0 += x * cc[0][j];
+              l1 += x * cc[1][j];
+              l2 += x * cc[2][j];
+            }
+          } else {
+            for (int km = sub_lane; km < KS; km += G) {
+              const double x = __ldg(c + km);
+              l0 += x * c0[km];
+              l1 += x * c1[km];
+              l2 += x * c2[km];
+            }
           }
         }
 #pragma unroll
