@@ -1686,16 +1686,15 @@ extern "C" int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, dou
     const int per = std::max(1, std::min(kEdgeMaxT, (int)(22 * 1024 / (sizeof(double) * 3 * KS))));  // + 24 KB static
     for (int c0 = t0; c0 < std::min(n_t, t0 + kEdgeMaxT); c0 += per) {
       const int nc = std::min(per, std::min(n_t, t0 + kEdgeMaxT) - c0);
-      CK(cudaStreamSynchronize(e->stream));  // hT staging
-      for (int i = 0; i < nc; ++i) e->hT[i] = t[c0 + i];
-      CK(cudaMemcpyAsync(e->dEdgeT, e->hT, sizeof(double) * nc, cudaMemcpyHostToDevice, e->stream));
+      EdgeLengths tl;
+      for (int i = 0; i < 16; ++i) tl.t[i] = i < nc ? t[c0 + i] : 0.0;
       const size_t smem = sizeof(double) * 3 * (size_t)KS * nc;
       const int g = (int)std::min<int64_t>(e->nPart, (int64_t)e->sm_count * 4);
       {
         ProfScope prof(e, KC_EDGE);
 #define EDGE_EVAL(MT, GV, PV)                                                                                      \
   edge_eval_kernel<MT, GV, PV><<<g, 256, smem, e->stream>>>(e->dSum, e->dSumSc, e->dLam, e->dRates, e->dProbs, e->dPi, \
-                                                             e->pinvar, (const MT *)e->dInv, e->dWeights, e->dEdgeT, nc, \
+                                                             e->pinvar, (const MT *)e->dInv, e->dWeights, tl, nc, \
                                                              e->sym, e->S, e->K, e->N, e->dEdgePart)
 #define EDGE_EVAL_G(MT)                                                      \
   {                                                                          \
@@ -1715,15 +1714,17 @@ extern "C" int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, dou
 #undef EDGE_EVAL_G
 #undef EDGE_EVAL
         LAUNCH_CHECK();
-        fold_rows_kernel<<<3 * nc, 256, 0, e->stream>>>(e->dEdgePart, e->nPart, e->dEdgeOut);
+        // the folded sums go straight into mapped host memory: no D2H copy
+        double *host_out = nullptr;
+        CK(cudaHostGetDevicePointer((void **)&host_out, e->hScalar + 24, 0));
+        fold_rows_kernel<<<3 * nc, 256, 0, e->stream>>>(e->dEdgePart, e->nPart, host_out);
         LAUNCH_CHECK();
       }
-      CK(cudaMemcpyAsync(e->hScalar + 8, e->dEdgeOut, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost, e->stream));
       CK(cudaStreamSynchronize(e->stream));
       for (int i = 0; i < nc; ++i) {
-        lnl_out[c0 + i] = e->hScalar[8 + 3 * i];
-        if (d1_out) d1_out[c0 + i] = e->hScalar[8 + 3 * i + 1];
-        if (d2_out) d2_out[c0 + i] = e->hScalar[8 + 3 * i + 2];
+        lnl_out[c0 + i] = e->hScalar[24 + 3 * i];
+        if (d1_out) d1_out[c0 + i] = e->hScalar[24 + 3 * i + 1];
+        if (d2_out) d2_out[c0 + i] = e->hScalar[24 + 3 * i + 2];
       }
     }
   }

@@ -62,6 +62,10 @@ edge_sumtable_kernel(const void *__restrict__ asrc, const int32_t *__restrict__ 
 // G lanes share a pattern (G = 4 for DNA+G4: each lane one 32-byte chunk; 16 for 20 states x 4
 // classes; 32 for codons): consecutive lanes read consecutive doubles of the sum table, so a
 // warp request is one contiguous run, and the three sums are combined by xor-shuffles.
+struct EdgeLengths {  // the branch lengths of one pass travel in the kernel parameters
+  double t[16];
+};
+
 // PER > 0: lane `sub` of a group owns the PER consecutive table entries sub*PER .. sub*PER+PER-1
 // and keeps their 3*PER coefficients in registers for the whole block (DNA+G4: G = 4, PER = 4:
 // one 256-bit load and 12 FMAs per pattern and lane). PER = 0: entries strided by G, coefficients
@@ -72,7 +76,7 @@ edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum
                  const double *__restrict__ lam, const double *__restrict__ rates,
                  const double *__restrict__ probs, const double *__restrict__ pi, double pinvar,
                  const MaskT *__restrict__ inv, const double *__restrict__ weights,
-                 const double *__restrict__ tlen, int n_t, int sym, int S, int K, int64_t N,
+                 const EdgeLengths tl, int n_t, int sym, int S, int K, int64_t N,
                  double *__restrict__ part) {
   extern __shared__ __align__(16) double esm[];
   __shared__ double vals[3][kLnlBlock];
@@ -81,7 +85,7 @@ edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum
   const int KS = K * S;
   for (int i = threadIdx.x; i < n_t * KS; i += blockDim.x) {
     const int ti = i / KS, km = i - ti * KS, k = km / S, m = km - k * S;
-    double tau = tlen[ti] * rates[k];
+    double tau = tl.t[ti] * rates[k];
     if (sym) tau = (double)(float)tau;  // compose_sym's `const float t` (lib/mlmodel.c:280)
     const double g = lam[m] * rates[k];
     const double e0 = probs[k] * (tau >= 1e-10 ? exp(lam[m] * tau) : 1.0);  // t < 1e-10 -> identity (:339-341)
