@@ -31,6 +31,15 @@ using namespace phylo;
 
 static std::string g_create_error;
 
+// layout of the pinned (and device-mapped) scalar block phylo_engine::hScalar (128 doubles)
+enum : int {
+  HS_LNL = 0,        // lnL of the last evaluation (D2H copy target)
+  HS_BAD = 1,        // invalid-mask counter read-back
+  HS_TREE_OUT = 16,  // [0] lnL, [1] sequence number written by the tree kernel's last CTA (mapped)
+  HS_EDGE_OUT = 24,  // 3 x kEdgeMaxT folded sums of phylo_lk_edge_eval (mapped)
+  HS_DOUBLES = 128
+};
+
 struct LkNode {
   double *clv = nullptr;
   int32_t *scale = nullptr;
@@ -256,7 +265,7 @@ extern "C" int phylo_engine_create(int device, phylo_engine **out) {
       e->encodeTiled = (phylo_engine::EncodeTiledFn)fn;
     cudaGetLastError();
   }
-  if (cudaMallocHost(&e->hScalar, 1024) != cudaSuccess) {
+  if (cudaMallocHost(&e->hScalar, sizeof(double) * HS_DOUBLES) != cudaSuccess) {
     delete e;
     return fail(nullptr, PHYLO_ERR_CUDA, "phylo_engine_create: cudaMallocHost failed");
   }
@@ -612,9 +621,9 @@ static int lk_upload_slab(phylo_engine *e, const void *masks, int mask_bytes, in
 
 // reads back the invalid-mask counter (call after a stream sync)
 static int lk_check_bad(phylo_engine *e, const char *who) {
-  CK(cudaMemcpyAsync(e->hScalar + 1, e->dBad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->hScalar + HS_BAD, e->dBad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  const unsigned long long bad = *(unsigned long long *)(e->hScalar + 1);
+  const unsigned long long bad = *(unsigned long long *)(e->hScalar + HS_BAD);
   if (bad) {
     lk_free_data(e);
     return fail(e, PHYLO_ERR_DATA, "%s: %llu tip cells have none of the %d state bits set", who, bad, e->S);
@@ -1218,7 +1227,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     fargs.partials = e->dPart;
     fargs.done_counter = e->dTreeDone;
     double *dev_out = nullptr;
-    CK(cudaHostGetDevicePointer((void **)&dev_out, e->hScalar + 16, 0));
+    CK(cudaHostGetDevicePointer((void **)&dev_out, e->hScalar + HS_TREE_OUT, 0));
     fargs.host_out = dev_out;
     fargs.seq = ++e->treeSeq;
     const size_t wbytes = sizeof(TreeWInstr) * pl.steps.size();
@@ -1266,7 +1275,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   if (!host_masks) {
     ProfScope prof(e, KC_TREE_FUSED);
     if (fuse) {
-      volatile double *flag = e->hScalar + 17;
+      volatile double *flag = e->hScalar + HS_TREE_OUT + 1;
       *flag = -1.0;  // sequence numbers are positive integers' bit patterns: never this value
     }
     cudaError_t st = useW ? launch_treew_k(e, a, geo, 0, ntiles, e->stream, fuse ? &fargs : nullptr)
@@ -1314,7 +1323,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     // spin on the sequence number the last CTA writes after lnL (mapped host memory); a
     // blocking stream sync would cost more than these kernels. Fallback after 2 ms.
     const double want = [&] { double d; const long long q = (long long)fargs.seq; std::memcpy(&d, &q, 8); return d; }();
-    volatile double *out = e->hScalar + 16;
+    volatile double *out = e->hScalar + HS_TREE_OUT;
     bool seen = false;
     const auto t0 = std::chrono::steady_clock::now();
     for (int spin = 0;; ++spin) {
@@ -1716,15 +1725,15 @@ extern "C" int phylo_lk_edge_eval(phylo_engine *e, const double *t, int n_t, dou
         LAUNCH_CHECK();
         // the folded sums go straight into mapped host memory: no D2H copy
         double *host_out = nullptr;
-        CK(cudaHostGetDevicePointer((void **)&host_out, e->hScalar + 24, 0));
+        CK(cudaHostGetDevicePointer((void **)&host_out, e->hScalar + HS_EDGE_OUT, 0));
         fold_rows_kernel<<<3 * nc, 256, 0, e->stream>>>(e->dEdgePart, e->nPart, host_out);
         LAUNCH_CHECK();
       }
       CK(cudaStreamSynchronize(e->stream));
       for (int i = 0; i < nc; ++i) {
-        lnl_out[c0 + i] = e->hScalar[24 + 3 * i];
-        if (d1_out) d1_out[c0 + i] = e->hScalar[24 + 3 * i + 1];
-        if (d2_out) d2_out[c0 + i] = e->hScalar[24 + 3 * i + 2];
+        lnl_out[c0 + i] = e->hScalar[HS_EDGE_OUT + 3 * i];
+        if (d1_out) d1_out[c0 + i] = e->hScalar[HS_EDGE_OUT + 3 * i + 1];
+        if (d2_out) d2_out[c0 + i] = e->hScalar[HS_EDGE_OUT + 3 * i + 2];
       }
     }
   }
