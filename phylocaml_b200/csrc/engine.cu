@@ -497,11 +497,21 @@ extern "C" int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U
         ul[(size_t)i * S + m] = Ui ? U[(size_t)i * S + m] : U[(size_t)m * S + i];
         ur[(size_t)m * S + i] = Ui ? Ui[(size_t)m * S + i] : U[(size_t)m * S + i];
       }
+    // The edge sum table c_km = (sum_i pi_i a_ki UL[i][m]) (sum_j UR[m][j] b_kj) is a pruning update
+    // with the "transition matrices" M1[m][i] = pi_i UL[i][m] and M2[m][j] = UR[m][j] for every
+    // rate class: phylo_lk_edge_prepare runs the ordinary pruning kernels on them.
+    std::vector<double> m1((size_t)K * ss), m2((size_t)K * ss);
+    for (int k = 0; k < K; ++k)
+      for (int m = 0; m < S; ++m)
+        for (int i = 0; i < S; ++i) {
+          m1[(size_t)k * ss + (size_t)m * S + i] = priors[i] * ul[(size_t)i * S + m];
+          m2[(size_t)k * ss + (size_t)m * S + i] = ur[(size_t)m * S + i];
+        }
     dfree(e->dUL); dfree(e->dUR);
-    CK(cudaMalloc(&e->dUL, sizeof(double) * ss));
-    CK(cudaMalloc(&e->dUR, sizeof(double) * ss));
-    CK(cudaMemcpy(e->dUL, ul.data(), sizeof(double) * ss, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->dUR, ur.data(), sizeof(double) * ss, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&e->dUL, sizeof(double) * K * ss));
+    CK(cudaMalloc(&e->dUR, sizeof(double) * K * ss));
+    CK(cudaMemcpy(e->dUL, m1.data(), sizeof(double) * K * ss, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->dUR, m2.data(), sizeof(double) * K * ss, cudaMemcpyHostToDevice));
   }
   dfree(e->dSum); dfree(e->dSumSc);
   e->edge_ready = false;
@@ -1658,24 +1668,10 @@ extern "C" int phylo_lk_edge_prepare(phylo_engine *e, int a_slot, int b_slot) {
   if (!e->dEdgePart) CK(cudaMalloc(&e->dEdgePart, sizeof(double) * (size_t)e->nPart * 3 * kEdgeMaxT));
   if (!e->dEdgeOut) CK(cudaMalloc(&e->dEdgeOut, sizeof(double) * 3 * kEdgeMaxT));
   if (!e->dEdgeT) CK(cudaMalloc(&e->dEdgeT, sizeof(double) * kEdgeMaxT));
-  const size_t mat = 2 * sizeof(double) * (size_t)e->S * e->S;
-  const int stage = mat <= 96 * 1024;
-  const int g = grid_for(e->N * e->K, 128, e->sm_count * 16);
-  {
-    ProfScope prof(e, KC_EDGE);
-#define EDGE_SUM(MT)                                                                                              \
-  {                                                                                                               \
-    auto kern = edge_sumtable_kernel<MT>;                                                                         \
-    if (stage && mat > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mat)); \
-    kern<<<g, 128, stage ? mat : 0, e->stream>>>(a.src, a.scale, a.tip, b.src, b.scale, b.tip, e->dUL, e->dUR, e->dPi, \
-                                                 e->S, e->K, e->N, stage, e->dSum, e->dSumSc);                    \
-  }
-    if (e->mask_dev_bytes == 1) EDGE_SUM(uint8_t)
-    else if (e->mask_dev_bytes == 4) EDGE_SUM(uint32_t)
-    else EDGE_SUM(uint64_t)
-#undef EDGE_SUM
-    LAUNCH_CHECK();
-  }
+  // one pruning update with M1 / M2 in place of P_left / P_right (see phylo_lk_set_model): the
+  // DNA, DMMA (20 / 61 states) and any-S kernels, their tip paths and their rescaling all apply;
+  // the "scale counters" that come out are exactly the summed counters the evaluation needs
+  if ((rc = lk_launch_prune(e, e->dUL, e->dUR, a, b, e->dSum, e->dSumSc)) != PHYLO_OK) return rc;
   e->edge_ready = true;
   e->edge_a = a_slot;
   e->edge_b = b_slot;

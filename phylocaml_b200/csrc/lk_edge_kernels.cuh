@@ -6,7 +6,9 @@
 // symmetric path, lib/mlmodel.c:280-302) the site likelihood on the edge is
 //     l(t) = sum_k p_k sum_m c_km exp(lam_m r_k t),
 //     c_km = (sum_i pi_i a_ki UL[i][m]) * (sum_j UR[m][j] b_kj),
-// so ONE pass over the two CLVs builds the "sum table" c (one CLV-sized array) and every
+// so ONE pass over the two CLVs builds the "sum table" c (one CLV-sized array; it is an ordinary
+// pruning update with M1[m][i] = pi_i UL[i][m] and M2[m][j] = UR[m][j] as the two "transition
+// matrices", so phylo_lk_edge_prepare runs the pruning kernels of lk_kernels.cuh) and every
 // further evaluation of lnL(t), dlnL/dt and d2lnL/dt2 -- for several t at once -- streams
 // that single array: K*S*8 bytes per pattern instead of two CLVs and an S x S product.
 //
@@ -17,51 +19,6 @@
 
 namespace phylo {
 
-// c[p][k][m]; thread = (pattern, rate class). UL, UR staged in shared memory when they fit.
-template <typename MaskT>
-__global__ void __launch_bounds__(128)
-edge_sumtable_kernel(const void *__restrict__ asrc, const int32_t *__restrict__ asc, bool atip,
-                     const void *__restrict__ bsrc, const int32_t *__restrict__ bsc, bool btip,
-                     const double *__restrict__ UL, const double *__restrict__ UR,
-                     const double *__restrict__ pi, int S, int K, int64_t N, int stage,
-                     double *__restrict__ sum, int32_t *__restrict__ sum_sc) {
-  extern __shared__ __align__(16) double esm[];
-  const double *ul = UL, *ur = UR;
-  if (stage) {
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) { esm[i] = UL[i]; esm[S * S + i] = UR[i]; }
-    __syncthreads();
-    ul = esm;
-    ur = esm + S * S;
-  }
-  const int64_t items = N * K;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < items; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = q / K;
-    const int k = (int)(q - p * K);
-    const double *av = atip ? nullptr : (const double *)asrc + q * S;
-    const double *bv = btip ? nullptr : (const double *)bsrc + q * S;
-    const uint64_t am = atip ? (uint64_t)((const MaskT *)asrc)[p] : 0, bm = btip ? (uint64_t)((const MaskT *)bsrc)[p] : 0;
-    double *out = sum + q * S;
-    for (int m = 0; m < S; ++m) {
-      double A = 0.0, B = 0.0;
-      for (int i = 0; i < S; ++i) {
-        const double ai = atip ? (double)((am >> i) & 1) : __ldg(av + i);
-        const double bi = btip ? (double)((bm >> i) & 1) : __ldg(bv + i);
-        A += (pi[i] * ai) * ul[i * S + m];
-        B += ur[m * S + i] * bi;
-      }
-      out[m] = A * B;
-    }
-    if (k == 0) sum_sc[p] = (atip ? 0 : asc[p]) + (btip ? 0 : bsc[p]);
-  }
-}
-
-// Evaluates n_t branch lengths in one launch. coef[(ti*3 + d)*K*S + k*S + m] = p_k (lam_m r_k)^d
-// exp(lam_m r_k t_ti) is built in shared memory by the CTA itself. Per 1024-pattern block and
-// per (ti, d) one canonical partial: part[((ti*3 + d) * nblocks) + blk] with
-//   d=0: sum w ln(site)   d=1: sum w site'/site   d=2: sum w (site''/site - (site'/site)^2).
-// G lanes share a pattern (G = 4 for DNA+G4: each lane one 32-byte chunk; 16 for 20 states x 4
-// classes; 32 for codons): consecutive lanes read consecutive doubles of the sum table, so a
-// warp request is one contiguous run, and the three sums are combined by xor-shuffles.
 struct EdgeLengths {  // the branch lengths of one pass travel in the kernel parameters
   double t[16];
 };
