@@ -11,6 +11,10 @@ A "step" is one full evaluation of the hot path on one batch of synthetic input:
   fitch (BASELINE config 2) Fitch down-pass length, 64 taxa x 1M characters (and x64M).
   aa / codon (BASELINE configs 4 / 5) 20-state +G4 and 61-state pruning.
 One JSON line on stdout (rank 0). PyTorch is used for events, NCCL and nothing else.
+
+L2 rule: a working set below 4 x the 126 MB L2 (config 1, config 2, lnL-only mode on small shards)
+gets 512 MB written between timed iterations, outside each iteration's own event pair; larger ones
+are timed with one event pair around all K steps. `config.l2` says which applied.
 """
 import argparse
 import json
@@ -89,6 +93,20 @@ def lk_bytes(T, S, K, tip_bytes, mode="pernode"):
     return d
 
 
+L2_BYTES = 126 << 20      # B200 L2
+FLUSH_BYTES = 512 << 20   # written between timed iterations when a working set could stay in L2
+
+
+def device_footprint(workload, T, S, K, tip_bytes, mode, n_local):
+    """Bytes one evaluation touches in HBM on this rank (decides the L2 rule): Fitch = every node's
+    bit-sliced set (0.5 B per character for DNA); likelihood = tips (nibble-packed for 4 states) plus
+    every interior CLV + scale counter when they are kept."""
+    if workload == "fitch":
+        return (2 * T - 1) * 0.5 * n_local
+    tips = T * (0.5 if S == 4 else tip_bytes) * n_local
+    return tips if mode == "fused-lnl" else tips + (T - 2) * (S * K * 8 + 4) * n_local
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -157,7 +175,7 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import Oracle
+    from oracle.oracle import Oracle, Ref
     from phylocaml_b200 import tree as tree_mod
 
     cores = os.cpu_count() or 1
@@ -169,9 +187,17 @@ def run_reference(args, wl):
     times = []
     if args.workload == "fitch":
         chars = tree_mod.random_fitch_chars(T, ns, 4, seed=5)
-        fn = lambda: orc.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, nthreads=cores)["length"]
-        units, metric, unit, kind = (T - 1) * ns, "fitch_char_ops_per_s", "char-ops/s", "port"
-        sample = "64 taxa x %d chars, W=8 one char per byte (bv.c layout), %d pthreads" % (ns, cores)
+        if Ref.available():  # the reference's own bv_fitch / bv_distance, compiled unmodified
+            ref = Ref()
+            fn = lambda: ref.fitch_score_tree(chars, ops, n_nodes, ra, rb, nthreads=cores)
+            kind = "reference"
+            sample = ("64 taxa x %d chars, W=8 one char per byte; reference bv_fitch per node + bv_distance "
+                      "(lib/bitvector/bv.c, -O2), characters in %d slabs on %d host threads" % (ns, cores, cores))
+        else:
+            fn = lambda: orc.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, nthreads=cores)["length"]
+            kind = "port"
+            sample = "64 taxa x %d chars, W=8 one char per byte (bv.c layout), %d pthreads" % (ns, cores)
+        units, metric, unit = (T - 1) * ns, "fitch_char_ops_per_s", "char-ops/s"
     else:
         model = make_model(wl)
         tips = tree_mod.evolve_tips(tr, model, min(ns, BASE_PATTERNS), seed=3, dtype=mask_dtype(S))
@@ -200,17 +226,20 @@ def run_reference(args, wl):
 
 
 def cpu_baseline(wl, workload, tr, ops, ra, rb, rt, n_nodes, model, tips_sample, site_gpu):
-    from oracle.oracle import Oracle
+    from oracle.oracle import Oracle, Ref
 
     cores = os.cpu_count() or 1
     orc = Oracle()
+    ref = Ref() if workload == "fitch" and Ref.available() else None
     T = wl["T"]
     ns = tips_sample.shape[1]
     best, res = None, None
     t_all = time.perf_counter()
     for _ in range(3):
         t0 = time.perf_counter()
-        if workload == "fitch":
+        if ref is not None:
+            res = {"length": ref.fitch_score_tree(tips_sample, ops, n_nodes, ra, rb, nthreads=cores)}
+        elif workload == "fitch":
             res = orc.fitch_score_tree(tips_sample, None, ops, n_nodes, ra, rb, nthreads=cores)
         else:
             res = orc.lk_score_tree(model, tips_sample, None, ops, n_nodes, ra, rb, rt, nthreads=cores)
@@ -219,9 +248,11 @@ def cpu_baseline(wl, workload, tr, ops, ra, rb, rt, n_nodes, model, tips_sample,
         if time.perf_counter() - t_all > 25:
             break
     unit = "char-ops/s" if workload == "fitch" else "site-updates/s"
-    out = {"value": (T - 1) * ns / best, "unit": unit, "cores": cores, "kind": "port",
-           "sample": "first %d of this rank's patterns, best of <=3 passes, oracle C port with %d pthreads"
-                     % (ns, cores)}
+    out = {"value": (T - 1) * ns / best, "unit": unit, "cores": cores, "kind": "reference" if ref else "port",
+           "sample": ("first %d of this rank's characters, best of <=3 passes, reference bv_fitch/bv_distance "
+                      "(oracle/_ref) on %d host threads" % (ns, cores)) if ref else
+                     ("first %d of this rank's patterns, best of <=3 passes, oracle C port with %d pthreads"
+                      % (ns, cores))}
     check = None
     if workload != "fitch" and site_gpu is not None:
         ref = res["site_lnl"]
@@ -367,6 +398,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    flush_buf = [None]
+
+    def needs_flush(mode):
+        return device_footprint(args.workload, T, S, K, mask_dtype(S)().itemsize, mode, n_local) < 4 * L2_BYTES
+
+    def timed_steps(fn, n, flush):
+        """Device time of exactly n calls of fn (ms, max over ranks) and the last result. Large
+        working sets: one event pair around all n, barrier + synchronize on both sides. Working sets
+        that could survive in the 126 MB L2: 512 MB are written before every iteration and each
+        iteration has its own event pair (the flush is outside the timed region); the pairs are summed."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out, total = None, 0.0
+        if not flush:
+            barrier()
+            a.record()
+            for _ in range(n):
+                out = fn()
+            b.record()
+            barrier()
+            total = a.elapsed_time(b)
+        else:
+            if flush_buf[0] is None:
+                flush_buf[0] = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+            barrier()
+            for i in range(n):
+                flush_buf[0].fill_(i & 0xFF)
+                a.record()
+                out = fn()
+                b.record()
+                b.synchronize()
+                total += a.elapsed_time(b)
+            barrier()
+        tms = torch.tensor([total], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        return float(tms.item()), out
+
     if args.workload == "fitch":
         model = None
         tips = engine.pinned_empty((T, n_local), np.uint8)
@@ -434,23 +502,13 @@ def main():
         result = step()
     eng.profile(True, reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        result = step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    flush = needs_flush(args.mode)
+    ms, result = timed_steps(step, args.steps, flush)
     clocks = sampler.stop() if sampler else None
     prof = eng.profile_get()
     eng.profile(False)
     launches = eng.launch_count - launches0
     step_launches = (eng.launch_count - launches0) // (args.steps + args.warmup)
-    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
     value = units_per_step * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel class (CUDA events on the launching stream)
@@ -491,20 +549,11 @@ def main():
         roof_step = None
 
     # ---- e2e: host buffers in, scalar out, through the C ABI, every step
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_step()
-    barrier()
-    e0.record()
-    for _ in range(args.e2e_steps):
-        result_e2e = e2e_step()
-    e1.record()
-    barrier()
-    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    e2e_val = units_per_step * args.e2e_steps / (float(tms.item()) * 1e-3)
+    e2e_ms, result_e2e = timed_steps(e2e_step, args.e2e_steps, flush)
+    e2e_val = units_per_step * args.e2e_steps / (e2e_ms * 1e-3)
     e2e = {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-           "ms_per_step": float(tms.item()) / args.e2e_steps, "steps": args.e2e_steps}
+           "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps}
 
     # ---- the other likelihood modes, briefly (same inputs, same timing method)
     modes = None
@@ -516,19 +565,10 @@ def main():
             set_mode(m)
             for _ in range(2):
                 r_m = step()
-            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             nm = max(3, args.steps // 4)
-            barrier()
-            m0.record()
-            for _ in range(nm):
-                r_m = step()
-            m1.record()
-            barrier()
-            tm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            modes[m] = {"value": units_per_step * nm / (float(tm.item()) * 1e-3),
-                        "ms_per_step": float(tm.item()) / nm, "lnl": r_m}
+            tm, r_m = timed_steps(step, nm, needs_flush(m))
+            modes[m] = {"value": units_per_step * nm / (tm * 1e-3), "ms_per_step": tm / nm, "lnl": r_m,
+                        "l2_flushed_between_steps": needs_flush(m)}
         set_mode(args.mode)
         step()  # leave the engine's site lnL / CLVs in the primary mode's state
 
@@ -578,7 +618,9 @@ def main():
             "newton_optimize_ms": opt_ms, "newton_iters": opt[2], "t_opt": opt[0],
             "reprune_path_ops": len(path), "reprune_ms": rep_ms, "reprunes": 10,
             "loop_total_ms": prep_ms + 50 * eval_ms + 10 * rep_ms,
-            "note": "per-rank times (no allreduce); sum table = one CLV-sized pass per evaluation",
+            "note": "per-rank times (no allreduce); sum table = one CLV-sized pass per evaluation; no L2 flush "
+                    "inside this loop: consecutive evaluations re-read the same %.0f MB table, as the "
+                    "optimiser's loop does" % (n_local * S * K * 8 / 1e6),
         }
         eng.lk_set_tips(tips, capacity=n_nodes)
         step()  # restore the unmodified tree's state
@@ -597,6 +639,10 @@ def main():
         else:
             check["site_lnl_max_rel_err_vs_oracle_on_sample"] = err
 
+    foot = device_footprint(args.workload, T, S, K, mask_dtype(S)().itemsize, args.mode, n_local)
+    l2_note = ("L2 flushed between timed iterations (%d MB written before each, outside its event pair; "
+               "working set %.3f GB per GPU could stay in the 126 MB L2)" % (FLUSH_BYTES >> 20, foot / 1e9)
+               if flush else "inputs exceed L2 (working set %.1f GB per GPU, 126 MB L2); no flush" % (foot / 1e9))
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
@@ -607,8 +653,7 @@ def main():
                        "tree": "random topology seed 1, Exp(0.1) branch lengths",
                        "tips": "evolved under the model (65536 patterns, tiled), 1% missing"
                        if args.workload != "fitch" else "random DNA singletons + 2% two-state ambiguity",
-                       "l2": "inputs exceed L2 (working set %.1f GB per GPU)" %
-                             ((kbytes.get("tree", 64) * n_local) / 1e9),
+                       "l2": l2_note,
                        "sharding": "contiguous 1024-aligned pattern slabs, one process per GPU",
                        "collective": "allreduce of one scalar per step" if world > 1 else "none"},
             "mode": args.mode if args.workload != "fitch" else None, "modes": modes,

@@ -327,6 +327,38 @@ class Ref:
         va, vb = self._vect(a), self._vect(b)
         return int(self.bv[a.dtype.itemsize * 8].bv_distance(C.byref(va), C.byref(vb)))
 
+    def fitch_score_tree(self, chars, ops, n_nodes, root_a, root_b, nthreads=1):
+        """Whole-tree Fitch length out of the reference's own kernels: one bv_fitch per schedule
+        entry (lib/bitvector/bv.c:148-160, the call Node.median_2 makes per node, lib/node.ml:183-198)
+        plus bv_distance across the root edge (bv.c:46-55), the characters cut into `nthreads`
+        contiguous slabs walked by one host thread each (ctypes releases the GIL during the calls).
+        This is bench.py's `--impl reference` arm for the Fitch workload."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        chars = np.ascontiguousarray(chars)
+        T, N = chars.shape
+        lib = self.bv[chars.dtype.itemsize * 8]
+        cuts = [(N * i) // nthreads for i in range(nthreads + 1)]
+
+        def walk(lo, hi):
+            if hi <= lo:
+                return 0
+            sets = {t: chars[t, lo:hi] for t in range(T)}
+            cost = 0
+            for op in ops:
+                a, b = sets[int(op["left"])], sets[int(op["right"])]
+                c = np.empty(hi - lo, dtype=chars.dtype)
+                va, vb, vc = self._vect(a), self._vect(b), self._vect(c)
+                cost += int(lib.bv_fitch(C.byref(vc), C.byref(va), C.byref(vb)))
+                sets[int(op["parent"])] = c
+            va, vb = self._vect(sets[root_a]), self._vect(sets[root_b])
+            return cost + int(lib.bv_distance(C.byref(va), C.byref(vb)))
+
+        if nthreads <= 1:
+            return walk(0, N)
+        with ThreadPoolExecutor(nthreads) as ex:
+            return sum(ex.map(lambda i: walk(cuts[i], cuts[i + 1]), range(nthreads)))
+
     def bv_binop(self, name, a, b):
         a = np.ascontiguousarray(a)
         b = np.ascontiguousarray(b, dtype=a.dtype)
