@@ -12,7 +12,8 @@
  *     (lib/mlmodel.c:109-121: failwith).
  *   - An engine handle is bound to ONE CUDA device and is not thread-safe (the reference is
  *     single-threaded: no caml_enter_blocking_section anywhere). Multi-GPU = one process
- *     (one handle) per GPU, patterns sharded contiguously, see DESIGN.md.
+ *     (one handle) per GPU, patterns sharded contiguously (bench.py), or one
+ *     phylo_group handle that owns an engine per GPU inside a single process (last section).
  *   - There is no CPU fallback: phylo_engine_create fails when no CUDA device is usable.
  *   - Matrices are row-major float64, exactly as OCaml Bigarray c_layout holds them
  *     (lib/mlModel.ml:50-51).
@@ -120,6 +121,11 @@ int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U, const dou
  * capacity >= T: number of node slots. A mask with none of the low S bits set is rejected. */
 int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
                       const double *weights, int capacity);
+/* Same, for a column slab of a wider host matrix: consecutive taxon rows are host_pitch_bytes
+ * apart (0 = N * mask_bytes). This is how phylo_group hands each device its shard without
+ * repacking the alignment on the host. */
+int phylo_lk_set_tips_pitched(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                              uint64_t host_pitch_bytes, const double *weights, int capacity);
 /* Likelihood.median_2 (lib/nodeData.ml:21, lib/likelihood_c.ml:15): CLV of `parent` from its
  * two children with per-site rescaling. */
 int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int right,
@@ -182,6 +188,10 @@ int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const void *masks
  * plane per 32 characters). An all-zero element is rejected. */
 int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
                          const void *codes, const double *weights, int capacity);
+/* column slab of a wider host matrix, rows host_pitch_bytes apart (0 = N * elt_bytes) */
+int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
+                                 const void *codes, uint64_t host_pitch_bytes, const double *weights,
+                                 int capacity);
 /* NonAdditive.median_2 (lib/nonAdditive_c.ml:19-35) == bv_fitch (lib/bitvector/bv.c:148-160;
  * stub bv_CAML_fitch_median2 :463-480): parent set + cost of this node alone. */
 int phylo_fitch_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *cost_out);
@@ -221,6 +231,52 @@ int phylo_bv_popcount(phylo_engine *e, int a, uint64_t *out);
 int phylo_bv_saturation(phylo_engine *e, int a, uint64_t state_mask, uint64_t *out);
 int phylo_bv_poly_saturation(phylo_engine *e, int a, int n, uint64_t *out);
 int phylo_bv_compare(phylo_engine *e, int a, int b, int *out);
+
+/* --------------------------------------- several GPUs behind one handle (one process) ---- */
+/* The reference is a single OCaml process (no threads: no caml_enter_blocking_section anywhere under lib/),
+ * so a drop-in that wants all GPUs of a box cannot rely on one-process-per-GPU launchers. A
+ * phylo_group owns one engine per listed device (a device may be listed more than once) and one
+ * host worker thread per engine; every call below fans out to the workers and returns when all
+ * are done. Site patterns / characters are cut into contiguous shards whose boundaries are
+ * multiples of PHYLO_LNL_BLOCK; the model, the schedule and P(t) are replicated.
+ * The path's only exchange is the final scalar: the level-1 block partials of every shard are
+ * concatenated in shard order and folded by phylo_reduce_partials, so lnL is BIT-IDENTICAL to the
+ * single-engine value for any device count; Fitch / TCM lengths are exact integer sums. No
+ * device-to-device traffic is needed (the scalars come back through each engine's mapped host
+ * block), hence no NCCL dependency in the library; bench.py's one-process-per-GPU arm does the same
+ * sum with an NCCL allreduce. Errors: the first failing shard's message, phylo_group_last_error. */
+typedef struct phylo_group phylo_group;
+int phylo_group_create(const int *devices, int n_devices, phylo_group **out);
+void phylo_group_destroy(phylo_group *g);
+const char *phylo_group_last_error(const phylo_group *g);
+int phylo_group_size(const phylo_group *g);
+/* engine of shard i (options, profiler, per-shard read-back); NULL when out of range */
+phylo_engine *phylo_group_engine(phylo_group *g, int i);
+/* patterns [*lo, *hi) of the loaded likelihood alignment (which = 0) or Fitch characters
+ * (which = 1) that shard i holds; lo == hi for a shard left empty by a short alignment */
+int phylo_group_shard(const phylo_group *g, int which, int i, int64_t *lo, int64_t *hi);
+int phylo_group_set_option(phylo_group *g, int option, int64_t value);
+int phylo_group_lk_set_model(phylo_group *g, int S, int K, const double *U, const double *D,
+                             const double *Ui, const double *priors, const double *rates,
+                             const double *probs, double pinvar);
+int phylo_group_lk_set_tips(phylo_group *g, int T, int64_t N, const void *masks, int mask_bytes,
+                            const double *weights, int capacity);
+int phylo_group_lk_score_tree(phylo_group *g, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                              double root_t, double *lnl_out);
+/* sums over shards in shard order (deterministic; not the blocked reduction) */
+int phylo_group_lk_edge_lnl(phylo_group *g, int a, int b, const double *t, int n_t, double *lnl_out);
+/* safeguarded Newton of phylo_lk_optimize_branch on the summed lnL, d1, d2 of all shards */
+int phylo_group_lk_optimize_branch(phylo_group *g, int a, int b, double t0, double t_min, double t_max,
+                                   double tol, int max_iter, double *t_opt, double *lnl_opt,
+                                   int *iters_out);
+int phylo_group_lk_get_site_lnl(phylo_group *g, double *out);
+int phylo_group_lk_get_clv(phylo_group *g, int node, double *clv_out, int32_t *scale_out);
+int phylo_group_fitch_set_tips(phylo_group *g, int T, int64_t N, int elt_bytes, int n_states,
+                               const void *codes, const double *weights, int capacity);
+int phylo_group_fitch_score_tree(phylo_group *g, const phylo_op *ops, int n_ops, int root_a,
+                                 int root_b, uint64_t *length_out);
+int phylo_group_fitch_uppass(phylo_group *g, const phylo_op *ops, int n_ops, int root_a, int root_b);
+int phylo_group_fitch_get_states(phylo_group *g, int node, int which, void *out);
 
 #ifdef __cplusplus
 }

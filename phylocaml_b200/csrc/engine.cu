@@ -100,6 +100,7 @@ struct phylo_engine {
   size_t capSpill = 0;
   bool tmapDirty = true;
   int64_t tipStride = 0;  // elements per tip row (N rounded up to 1024)
+  size_t hostPitch = 0;   // bytes between taxon rows of the host alignment being uploaded (0: N * mask_bytes)
   double **dNodeClv = nullptr;   // device tables of node buffers (tree-fused kernel)
   int32_t **dNodeSc = nullptr;
   bool nodeTabDirty = true;
@@ -605,8 +606,9 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
 static int lk_upload_slab(phylo_engine *e, const void *masks, int mask_bytes, int64_t p_lo, int64_t p_hi,
                           cudaStream_t copy, cudaEvent_t ready, cudaStream_t cs) {
   const size_t pitch = (size_t)e->N * mask_bytes;
+  const size_t host_pitch = e->hostPitch ? e->hostPitch : pitch;
   CK(cudaMemcpy2DAsync((char *)e->dRaw + (size_t)p_lo * mask_bytes, pitch, (const char *)masks + (size_t)p_lo * mask_bytes,
-                       pitch, (size_t)(p_hi - p_lo) * mask_bytes, e->T, cudaMemcpyHostToDevice, copy ? copy : cs));
+                       host_pitch, (size_t)(p_hi - p_lo) * mask_bytes, e->T, cudaMemcpyHostToDevice, copy ? copy : cs));
   if (copy) {
     CK(cudaEventRecord(ready, copy));
     CK(cudaStreamWaitEvent(cs, ready, 0));
@@ -641,13 +643,24 @@ static int lk_check_bad(phylo_engine *e, const char *who) {
   return PHYLO_OK;
 }
 
-extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
-                                 const double *weights, int capacity) {
+extern "C" int phylo_lk_set_tips_pitched(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                         uint64_t host_pitch_bytes, const double *weights, int capacity) {
   if (!e) return PHYLO_ERR_ARG;
+  if (host_pitch_bytes != 0 && N > 0 && host_pitch_bytes < (uint64_t)N * (uint64_t)std::max(mask_bytes, 1))
+    return fail(e, PHYLO_ERR_ARG, "lk_set_tips: host pitch %llu is shorter than a row of %lld masks",
+                (unsigned long long)host_pitch_bytes, (long long)N);
   int rc;
   if ((rc = lk_prepare_shape(e, T, N, masks, mask_bytes, weights, capacity, "lk_set_tips")) != PHYLO_OK) return rc;
-  if ((rc = lk_upload_slab(e, masks, mask_bytes, 0, N, nullptr, nullptr, e->stream)) != PHYLO_OK) { lk_free_data(e); return rc; }
+  e->hostPitch = (size_t)host_pitch_bytes;
+  rc = lk_upload_slab(e, masks, mask_bytes, 0, N, nullptr, nullptr, e->stream);
+  e->hostPitch = 0;
+  if (rc != PHYLO_OK) { lk_free_data(e); return rc; }
   return lk_check_bad(e, "lk_set_tips");
+}
+
+extern "C" int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                 const double *weights, int capacity) {
+  return phylo_lk_set_tips_pitched(e, T, N, masks, mask_bytes, 0, weights, capacity);
 }
 
 static int lk_ensure_node(phylo_engine *e, int slot) {
@@ -1941,7 +1954,16 @@ static int fitch_encode(phylo_engine *e, const void *dcodes, uint32_t *dst, unsi
 
 extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
                                     const void *codes, const double *weights, int capacity) {
+  return phylo_fitch_set_tips_pitched(e, T, N, elt_bytes, n_states, codes, 0, weights, capacity);
+}
+
+extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
+                                            const void *codes, uint64_t host_pitch_bytes, const double *weights,
+                                            int capacity) {
   if (!e) return PHYLO_ERR_ARG;
+  if (host_pitch_bytes != 0 && N > 0 && host_pitch_bytes < (uint64_t)N * (uint64_t)std::max(elt_bytes, 1))
+    return fail(e, PHYLO_ERR_ARG, "fitch_set_tips: host pitch %llu is shorter than a row of %lld codes",
+                (unsigned long long)host_pitch_bytes, (long long)N);
   if (T < 1 || N < 1 || !codes || capacity < T ||
       !(elt_bytes == 1 || elt_bytes == 2 || elt_bytes == 4 || elt_bytes == 8) || n_states < 1 ||
       n_states > elt_bytes * 8)
@@ -1982,6 +2004,7 @@ extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_b
   if ((rc = fitch_cost_capacity(e, (size_t)capacity + 4)) != PHYLO_OK) return rc;
   // upload in chunks of whole taxa through the staging buffer, transcoding on device
   const size_t row = (size_t)N * elt_bytes;
+  const size_t host_row = host_pitch_bytes ? (size_t)host_pitch_bytes : row;
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, ((size_t)256 << 20) / row));
   if ((rc = fitch_stage(e, row * chunk)) != PHYLO_OK) return rc;
   CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
@@ -2011,8 +2034,12 @@ extern "C" int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_b
     }
     for (int pc = 0; pc < npieces; ++pc) {
       const int a0 = pc * piece, a1 = std::min(nt, a0 + piece);
-      CK(cudaMemcpyAsync((char *)e->dStage + (size_t)a0 * row, (const char *)codes + (size_t)(t0 + a0) * row,
-                         row * (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copyStream));
+      if (host_row == row)
+        CK(cudaMemcpyAsync((char *)e->dStage + (size_t)a0 * row, (const char *)codes + (size_t)(t0 + a0) * row,
+                           row * (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copyStream));
+      else  // a column slab of a wider host matrix (phylo_group shards)
+        CK(cudaMemcpy2DAsync((char *)e->dStage + (size_t)a0 * row, row, (const char *)codes + (size_t)(t0 + a0) * host_row,
+                             host_row, row, (size_t)(a1 - a0), cudaMemcpyHostToDevice, e->copyStream));
       CK(cudaEventRecord(e->slabEvents[pc], e->copyStream));
       CK(cudaStreamWaitEvent(e->stream, e->slabEvents[pc], 0));
       for (int t = a0; t < a1; ++t)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "phylo_compose_gtr": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
     "phylo_lk_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
     "phylo_lk_set_tips": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int]),
+    "phylo_lk_set_tips_pitched": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_uint64, _dp, C.c_int]),
     "phylo_lk_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]),
     "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
@@ -68,6 +69,7 @@ SIGNATURES = {
     "phylo_lk_get_block_partials": (C.c_int, [_vp, _dp, C.POINTER(_i64)]),
     "phylo_reduce_partials": (C.c_double, [_dp, _i64]),
     "phylo_fitch_set_tips": (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, _vp, _dp, C.c_int]),
+    "phylo_fitch_set_tips_pitched": (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, _vp, C.c_uint64, _dp, C.c_int]),
     "phylo_fitch_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _u64p]),
     "phylo_fitch_distance": (C.c_int, [_vp, C.c_int, C.c_int, _u64p]),
     "phylo_fitch_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _u64p]),
@@ -81,6 +83,26 @@ SIGNATURES = {
     "phylo_bv_saturation": (C.c_int, [_vp, C.c_int, C.c_uint64, _u64p]),
     "phylo_bv_poly_saturation": (C.c_int, [_vp, C.c_int, C.c_int, _u64p]),
     "phylo_bv_compare": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    # several GPUs behind one handle
+    "phylo_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "phylo_group_destroy": (None, [_vp]),
+    "phylo_group_last_error": (C.c_char_p, [_vp]),
+    "phylo_group_size": (C.c_int, [_vp]),
+    "phylo_group_engine": (_vp, [_vp, C.c_int]),
+    "phylo_group_shard": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64)]),
+    "phylo_group_set_option": (C.c_int, [_vp, C.c_int, _i64]),
+    "phylo_group_lk_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
+    "phylo_group_lk_set_tips": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int]),
+    "phylo_group_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
+    "phylo_group_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
+    "phylo_group_lk_optimize_branch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                                 C.c_double, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
+    "phylo_group_lk_get_site_lnl": (C.c_int, [_vp, _dp]),
+    "phylo_group_lk_get_clv": (C.c_int, [_vp, C.c_int, _dp, _vp]),
+    "phylo_group_fitch_set_tips": (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, _vp, _dp, C.c_int]),
+    "phylo_group_fitch_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _u64p]),
+    "phylo_group_fitch_uppass": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "phylo_group_fitch_get_states": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
 }
 
 _lib = None
@@ -441,3 +463,127 @@ class Engine:
         out = C.c_int()
         self._ck(self.lib.phylo_bv_compare(self.h, a, b, C.byref(out)))
         return out.value
+
+
+class Group:
+    """Several GPUs behind one handle, in one process (phylo_group_*): one engine + one host
+    worker thread per listed device, patterns / characters in contiguous 1024-aligned shards,
+    lnL bit-identical to a single engine. `devices` may repeat a device id."""
+
+    OPT_FUSED_TREE, OPT_RETAIN_CLV, OPT_FITCH_WALK = 1, 2, 3
+
+    def __init__(self, devices):
+        self.lib = load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = _vp()
+        rc = self.lib.phylo_group_create(devs, len(devices), C.byref(h))
+        if rc != PHYLO_OK:
+            raise PhyloError(rc, self.lib.phylo_group_last_error(None).decode())
+        self.h = h
+        self.size = self.lib.phylo_group_size(h)
+        self.lk_shape = self.fitch_shape = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phylo_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != PHYLO_OK:
+            raise PhyloError(rc, self.lib.phylo_group_last_error(self.h).decode())
+
+    def shard(self, i, fitch=False):
+        lo, hi = _i64(), _i64()
+        self._ck(self.lib.phylo_group_shard(self.h, 1 if fitch else 0, i, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    @property
+    def launch_count(self):
+        return sum(self.lib.phylo_engine_launch_count(self.lib.phylo_group_engine(self.h, i)) for i in range(self.size))
+
+    def set_option(self, option, value):
+        self._ck(self.lib.phylo_group_set_option(self.h, option, int(value)))
+
+    def lk_set_model(self, model):
+        S, K = int(model["S"]), int(model["K"])
+        U, D = _f64(model["U"]), _f64(model["D"])
+        if D.ndim == 1:
+            D = _f64(np.diag(D))
+        Ui = model.get("Ui")
+        Ui = None if Ui is None else _f64(Ui)
+        pi, rates, probs = _f64(model["pi"]), _f64(model["rates"]), _f64(model["probs"])
+        pinvar = model.get("pinvar")
+        pinvar = -1.0 if pinvar is None else float(pinvar)
+        self._ck(self.lib.phylo_group_lk_set_model(self.h, S, K, _p(U, _dp), _p(D, _dp), _p(Ui, _dp), _p(pi, _dp),
+                                                   _p(rates, _dp), _p(probs, _dp), pinvar))
+        self.S, self.K = S, K
+
+    def lk_set_tips(self, tips, weights=None, capacity=None):
+        tips = np.ascontiguousarray(tips)
+        T, N = tips.shape
+        capacity = 2 * T if capacity is None else capacity
+        w = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_group_lk_set_tips(self.h, T, N, _p(tips), tips.dtype.itemsize, _p(w, _dp), capacity))
+        self.lk_shape = (T, N, capacity)
+
+    def lk_score_tree(self, ops, root_a, root_b, root_t):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        out = C.c_double()
+        self._ck(self.lib.phylo_group_lk_score_tree(self.h, _p(ops), len(ops), root_a, root_b, float(root_t),
+                                                    C.byref(out)))
+        return out.value
+
+    def lk_edge_lnl(self, a, b, ts):
+        ts = _f64(np.atleast_1d(ts))
+        out = np.empty(ts.size)
+        self._ck(self.lib.phylo_group_lk_edge_lnl(self.h, a, b, _p(ts, _dp), ts.size, _p(out, _dp)))
+        return out
+
+    def lk_optimize_branch(self, a, b, t0=0.1, t_min=1e-8, t_max=100.0, tol=1e-9, max_iter=50):
+        t, l, it = C.c_double(), C.c_double(), C.c_int()
+        self._ck(self.lib.phylo_group_lk_optimize_branch(self.h, a, b, t0, t_min, t_max, tol, max_iter, C.byref(t),
+                                                         C.byref(l), C.byref(it)))
+        return t.value, l.value, it.value
+
+    def lk_get_site_lnl(self):
+        out = np.empty(self.lk_shape[1])
+        self._ck(self.lib.phylo_group_lk_get_site_lnl(self.h, _p(out, _dp)))
+        return out
+
+    def lk_get_clv(self, node):
+        N = self.lk_shape[1]
+        clv = np.empty((N, self.K, self.S))
+        sc = np.empty(N, dtype=np.int32)
+        self._ck(self.lib.phylo_group_lk_get_clv(self.h, node, _p(clv, _dp), _p(sc)))
+        return clv, sc
+
+    def fitch_set_tips(self, codes, n_states, weights=None, capacity=None):
+        codes = np.ascontiguousarray(codes)
+        T, N = codes.shape
+        capacity = 2 * T if capacity is None else capacity
+        w = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_group_fitch_set_tips(self.h, T, N, codes.dtype.itemsize, n_states, _p(codes),
+                                                     _p(w, _dp), capacity))
+        self.fitch_shape = (T, N, capacity)
+        self.fitch_dtype = codes.dtype
+
+    def fitch_score_tree(self, ops, root_a, root_b):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_group_fitch_score_tree(self.h, _p(ops), len(ops), root_a, root_b, C.byref(out)))
+        return out.value
+
+    def fitch_uppass(self, ops, root_a, root_b):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        self._ck(self.lib.phylo_group_fitch_uppass(self.h, _p(ops), len(ops), root_a, root_b))
+
+    def fitch_get_states(self, node, final=False):
+        out = np.empty(self.fitch_shape[1], dtype=self.fitch_dtype)
+        self._ck(self.lib.phylo_group_fitch_get_states(self.h, node, 1 if final else 0, _p(out)))
+        return out

@@ -401,3 +401,152 @@ CAMLprim value nonadd_CAML_compare(value ve, value va, value vb)
   check(e, phylo_bv_compare(e, Int_val(va), Int_val(vb), &r));
   CAMLreturn(Val_int(r));
 }
+
+/* ------------------------------------- several GPUs behind one handle (phylo_group_*) ---- */
+/* The OCaml runtime is one process, so the whole-tree entry points also exist over a group
+ * handle that owns one engine per GPU (include/phylo_engine.h, last section). Same argument
+ * shapes as the single-engine stubs above; `group` is a second custom block. */
+#define Group_val(v) (*((phylo_group **)Data_custom_val(v)))
+
+static void group_finalize(value v)
+{
+  if (Group_val(v)) phylo_group_destroy(Group_val(v));
+  Group_val(v) = NULL;
+}
+
+static struct custom_operations group_ops = {
+    "AMNH/phylo_b200/group/0.1", group_finalize, custom_compare_default, custom_hash_default,
+    custom_serialize_default, custom_deserialize_default, custom_compare_ext_default};
+
+static void gcheck(phylo_group *g, int rc)
+{
+  if (rc != PHYLO_OK) caml_failwith(phylo_group_last_error(g));
+}
+
+/* external group_create : int array -> group = "phylo_CAML_group_create"   (device ids) */
+CAMLprim value phylo_CAML_group_create(value vdevs)
+{
+  CAMLparam1(vdevs);
+  CAMLlocal1(res);
+  int n = (int)Wosize_val(vdevs), i, rc;
+  int devs[64];
+  phylo_group *g = NULL;
+  if (n < 1 || n > 64) caml_failwith("group_create: need 1..64 device ids");
+  for (i = 0; i < n; ++i) devs[i] = Int_val(Field(vdevs, i));
+  rc = phylo_group_create(devs, n, &g);
+  if (rc != PHYLO_OK) caml_failwith(phylo_group_last_error(NULL));
+  res = caml_alloc_custom(&group_ops, sizeof(phylo_group *), 0, 1);
+  Group_val(res) = g;
+  CAMLreturn(res);
+}
+
+/* external group_set_model : group -> matrix -> matrix -> matrix option -> (vector * vector * vector * float option) -> unit */
+CAMLprim value likelihood_CAML_group_set_model(value vg, value U, value D, value Uio, value rest)
+{
+  CAMLparam5(vg, U, D, Uio, rest);
+  phylo_group *g = Group_val(vg);
+  value pri = Field(rest, 0), rates = Field(rest, 1), probs = Field(rest, 2), pinv = Field(rest, 3);
+  const double *ui = (Uio == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(Uio, 0));
+  double pv = (pinv == Val_int(0)) ? -1.0 : Double_val(Field(pinv, 0));
+  gcheck(g, phylo_group_lk_set_model(g, (int)Bigarray_val(U)->dim[0], (int)Bigarray_val(rates)->dim[0],
+                                     (double *)Data_bigarray_val(U), (double *)Data_bigarray_val(D), ui,
+                                     (double *)Data_bigarray_val(pri), (double *)Data_bigarray_val(rates),
+                                     (double *)Data_bigarray_val(probs), pv));
+  CAMLreturn(Val_unit);
+}
+
+/* external group_set_tips : group -> masks -> vector option -> int -> unit */
+CAMLprim value likelihood_CAML_group_set_tips(value vg, value masks, value wo, value vcap)
+{
+  CAMLparam4(vg, masks, wo, vcap);
+  phylo_group *g = Group_val(vg);
+  struct caml_ba_array *b = Bigarray_val(masks);
+  int kind = (int)(b->flags & 0xff), bytes = 1, rc;
+  const double *w = (wo == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(wo, 0));
+  if (kind == CAML_BA_INT32) bytes = 4;
+  else if (kind == CAML_BA_INT64) bytes = 8;
+  else if (kind != CAML_BA_UINT8) caml_failwith("likelihood group_set_tips: masks must be uint8, int32 or int64");
+  caml_release_runtime_system();
+  rc = phylo_group_lk_set_tips(g, (int)b->dim[0], (int64_t)b->dim[1], b->data, bytes, w, Int_val(vcap));
+  caml_acquire_runtime_system();
+  gcheck(g, rc);
+  CAMLreturn(Val_unit);
+}
+
+/* external group_score_tree : group -> ids -> lens -> (int * int * float) -> float */
+CAMLprim value likelihood_CAML_group_score_tree(value vg, value ids, value lens, value root)
+{
+  CAMLparam4(vg, ids, lens, root);
+  phylo_group *g = Group_val(vg);
+  int n = (int)Bigarray_val(ids)->dim[0], i, rc;
+  const int32_t *id = (const int32_t *)Data_bigarray_val(ids);
+  const double *tl = (const double *)Data_bigarray_val(lens);
+  phylo_op *ops = (phylo_op *)malloc(sizeof(phylo_op) * (n > 0 ? n : 1));
+  double lnl = 0.0;
+  int ra = Int_val(Field(root, 0)), rb = Int_val(Field(root, 1));
+  double rt = Double_val(Field(root, 2));
+  for (i = 0; i < n; ++i) {
+    ops[i].parent = id[3 * i]; ops[i].left = id[3 * i + 1]; ops[i].right = id[3 * i + 2];
+    ops[i].pad_ = 0; ops[i].t_left = tl[2 * i]; ops[i].t_right = tl[2 * i + 1];
+  }
+  caml_release_runtime_system();
+  rc = phylo_group_lk_score_tree(g, ops, n, ra, rb, rt, &lnl);
+  caml_acquire_runtime_system();
+  free(ops);
+  gcheck(g, rc);
+  CAMLreturn(caml_copy_double(lnl));
+}
+
+/* external group_optimize_branch : group -> int -> int -> (float * float * float * float) -> float * float */
+CAMLprim value likelihood_CAML_group_optimize_branch(value vg, value va, value vb, value par)
+{
+  CAMLparam4(vg, va, vb, par);
+  CAMLlocal1(res);
+  phylo_group *g = Group_val(vg);
+  int rc, a = Int_val(va), b = Int_val(vb), iters = 0;
+  double t0 = Double_val(Field(par, 0)), tmin = Double_val(Field(par, 1)), tmax = Double_val(Field(par, 2)),
+         tol = Double_val(Field(par, 3)), t = 0.0, l = 0.0;
+  caml_release_runtime_system();
+  rc = phylo_group_lk_optimize_branch(g, a, b, t0, tmin, tmax, tol, 50, &t, &l, &iters);
+  caml_acquire_runtime_system();
+  gcheck(g, rc);
+  res = caml_alloc_tuple(2);
+  Store_field(res, 0, caml_copy_double(t));
+  Store_field(res, 1, caml_copy_double(l));
+  CAMLreturn(res);
+}
+
+/* external group_set_tips : group -> codes -> n_states:int -> vector option -> capacity:int -> unit */
+CAMLprim value nonadd_CAML_group_set_tips(value vg, value codes, value vns, value wo, value vcap)
+{
+  CAMLparam5(vg, codes, vns, wo, vcap);
+  phylo_group *g = Group_val(vg);
+  struct caml_ba_array *b = Bigarray_val(codes);
+  int kind = (int)(b->flags & 0xff), bytes = 1, rc;
+  const double *w = (wo == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(wo, 0));
+  if (kind == CAML_BA_INT32) bytes = 4;
+  else if (kind == CAML_BA_INT64) bytes = 8;
+  else if (kind != CAML_BA_UINT8) caml_failwith("nonadd group_set_tips: codes must be uint8, int32 or int64");
+  caml_release_runtime_system();
+  rc = phylo_group_fitch_set_tips(g, (int)b->dim[0], (int64_t)b->dim[1], bytes, Int_val(vns), b->data, w,
+                                  Int_val(vcap));
+  caml_acquire_runtime_system();
+  gcheck(g, rc);
+  CAMLreturn(Val_unit);
+}
+
+/* external group_score_tree : group -> ids -> root_a:int -> root_b:int -> int   (* tree length *) */
+CAMLprim value nonadd_CAML_group_score_tree(value vg, value ids, value va, value vb)
+{
+  CAMLparam4(vg, ids, va, vb);
+  phylo_group *g = Group_val(vg);
+  int n, rc, a = Int_val(va), b = Int_val(vb);
+  phylo_op *ops = ops_of_ids(ids, &n);
+  uint64_t len = 0;
+  caml_release_runtime_system();
+  rc = phylo_group_fitch_score_tree(g, ops, n, a, b, &len);
+  caml_acquire_runtime_system();
+  free(ops);
+  gcheck(g, rc);
+  CAMLreturn(Val_long((intptr_t)len));
+}

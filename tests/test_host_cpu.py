@@ -63,6 +63,21 @@ def test_engine_create_fails_loudly_without_gpu(built):
         engine.Engine(0)
 
 
+def test_group_create_fails_loudly_without_gpu(built):
+    lib = engine.load()
+    h = ctypes.c_void_p()
+    devs = (ctypes.c_int * 2)(0, 0)
+    rc = lib.phylo_group_create(devs, 2, ctypes.byref(h))
+    if rc == 0:
+        lib.phylo_group_destroy(h)
+        pytest.skip("a GPU is present")
+    assert rc == -1 and h.value is None
+    assert b"no CPU fallback" in lib.phylo_group_last_error(None)
+    with pytest.raises(engine.PhyloError):
+        engine.Group([0])
+    assert lib.phylo_group_create(devs, 0, ctypes.byref(h)) == -2  # PHYLO_ERR_ARG
+
+
 # ------------------------------------------------------------- eigen-decomposition ----
 @pytest.mark.parametrize("case", ["dna_gtr", "dna_f81", "aa20", "codon61"])
 def test_diagonalize_gtr_reproduces_reference_P(built, oracle, case):
