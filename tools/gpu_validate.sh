@@ -3,7 +3,7 @@
 # Everything lands in gpurun_out/; each leg has its own timeout so one hang cannot eat the box.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt 2>&1
-( time timeout 600 python -m pytest tests -m gpu -q --maxfail=12 -x --durations=15 ) > gpurun_out/pytest_gpu.log 2>&1
+( time timeout 600 python -m pytest tests -m gpu -q --maxfail=12 --durations=15 ) > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit: $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit: $?" >> gpurun_out/smoke.log
