@@ -93,6 +93,10 @@ def lk_bytes(T, S, K, tip_bytes, mode="pernode"):
     return d
 
 
+# fp64 tensor-core (mma.sync.m8n8k4.f64) peak of this pool's B200s measured by tools/peaks.cu
+# (k_dmma; profiles/README.md): the denominator for the 20/61-state contraction kernels.
+# MEASURED_PEAKS.json only carries the bf16 figure, which no fp64 kernel can be held against.
+FP64_DMMA_TFLOPS = 37.1
 L2_BYTES = 126 << 20      # B200 L2
 FLUSH_BYTES = 512 << 20   # written between timed iterations when a working set could stay in L2
 
@@ -120,6 +124,16 @@ class ClockSampler:
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+
+    def count(self):
+        """samples written so far"""
+        if self.p is None:
+            return 1 << 30
+        try:
+            with open(self.f.name) as g:
+                return sum(1 for _ in g)
+        except OSError:
+            return 0
 
     def stop(self):
         if self.p is None:
@@ -504,11 +518,19 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     flush = needs_flush(args.mode)
     ms, result = timed_steps(step, args.steps, flush)
-    clocks = sampler.stop() if sampler else None
     prof = eng.profile_get()
     eng.profile(False)
     launches = eng.launch_count - launches0
     step_launches = (eng.launch_count - launches0) // (args.steps + args.warmup)
+    # a timed region shorter than a few nvidia-smi samples (50 ms apart): keep the same load running,
+    # untimed, for ~0.6 s so that the clocks / throttle reasons are sampled under it (the count is
+    # derived from the all-reduced time, so every rank runs the same number of steps)
+    extra_steps = 0 if ms >= 600.0 else min(5000, int(np.ceil((600.0 - ms) / max(ms / args.steps, 1e-3))))
+    for _ in range(extra_steps):
+        step()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["untimed_steps_run_for_sampling"] = extra_steps
     value = units_per_step * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel class (CUDA events on the launching stream)
@@ -530,7 +552,7 @@ def main():
                     with open(tpath) as f:
                         tj = json.load(f)
                     t = tj.get(name)
-                    if t and t.get("patterns"):
+                    if t and t.get("patterns") and t.get("workload", "dna") == args.workload:
                         traffic = t["dram_bytes_per_launch"] * n_local / t["patterns"]
                 roof = {"bound": "hbm", "kernel": name, "achieved": entry["achieved_gbs"], "peak": hbm_peak,
                         "unit": "GB/s", "frac": entry["frac"], "traffic": traffic, "peak_source": peak_src,
@@ -539,6 +561,24 @@ def main():
                                         "SURVEY 8(d) per-node streaming") if args.workload != "fitch"
                         else "compulsory (tree-fused: every node set moved once)"}
         kernels[name] = entry
+    # 20 / 61 states: the update is a dense contraction (K S (2 (2S - 1) + 1) flops per
+    # update); the inner+inner kernel is held against the measured fp64 DMMA peak as well. For 61
+    # states that is the governing roofline (15 flop/B), for 20 states the two rooflines meet.
+    roof_tensor = None
+    if args.workload != "fitch" and S >= 20 and "prune_inner_inner" in kernels:
+        fl = K * S * (2 * (2 * S - 1) + 1) * n_local
+        ent = kernels["prune_inner_inner"]
+        tf = fl / (ent["avg_us"] * 1e-6) / 1e12
+        ent["algorithmic_flops_per_launch"] = fl
+        ent["achieved_tflops"] = tf
+        roof_tensor = {"bound": "tensor", "kernel": "prune_inner_inner", "achieved": tf, "peak": FP64_DMMA_TFLOPS,
+                       "unit": "TFLOP/s", "frac": tf / FP64_DMMA_TFLOPS, "traffic": None,
+                       "peak_source": "fp64 DMMA (mma.sync.m8n8k4.f64) measured by tools/peaks.cu on this pool",
+                       "step_level": {"algorithmic_flops_per_step": fl * (T - 1),
+                                      "achieved_tflops": fl * (T - 1) / (ms * 1e-3 / args.steps) / 1e12,
+                                      "note": "SURVEY's dense count for every update; tip sides are table "
+                                              "lookups in the engine, so this exceeds the executed flops"}}
+        roof_tensor["step_level"]["frac"] = roof_tensor["step_level"]["achieved_tflops"] / FP64_DMMA_TFLOPS
     if args.workload != "fitch":
         step_bytes = kbytes["tree"] * n_local
         roof_step = {"bytes_model": "SURVEY 8(d) per-node streaming (what a kernel-per-node engine must move)",
@@ -657,7 +697,10 @@ def main():
                        "sharding": "contiguous 1024-aligned pattern slabs, one process per GPU",
                        "collective": "allreduce of one scalar per step" if world > 1 else "none"},
             "mode": args.mode if args.workload != "fitch" else None, "modes": modes,
-            "roofline": roof, "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": (roof_tensor if roof_tensor and S > 32 else roof),
+            "roofline_hbm": roof if roof_tensor and S > 32 else None,
+            "roofline_tensor": roof_tensor if roof_tensor and S <= 32 else None,
+            "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
             "e2e": e2e, "branch_loop": branch_loop, "gpu_launches": int(step_launches * args.steps),
             "gpu_launches_total_incl_warmup": int(launches), "clocks": clocks, "check": check,
         }

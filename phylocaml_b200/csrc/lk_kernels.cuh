@@ -577,7 +577,11 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
 
 // LT / RT: the side is a tip (compile-time, so the inner+inner instance carries none of the
 // tip code: with run-time flags its main loop lost 20 % to register pressure).
-template <int S, typename MaskT, bool LT, bool RT>
+// R: pattern groups (of 8) a warp works on at once. Every A fragment read from shared memory
+// feeds R DMMAs (one per group, the groups' B fragments live in registers): the R = 1 kernel was
+// bound by exactly those reads (ncu: L1/LSU 87 % busy, tensor pipe 56 %, profiles/r01_ncu_prune_mma_*).
+// The arithmetic per pattern is unchanged, so every R gives bit-identical CLVs.
+template <int S, typename MaskT, bool LT, bool RT, int R>
 __global__ void __launch_bounds__(256)
 prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
                  const void *__restrict__ lsrc, const int32_t *__restrict__ lsc,
@@ -604,92 +608,134 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
   const double *fl = frag, *frg = frag + side;
   const double *lclv = (const double *)lsrc, *rclv = (const double *)rsrc;
   const MaskT *lmask = (const MaskT *)lsrc, *rmask = (const MaskT *)rsrc;
+  const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
 
-  const int64_t ngroups = (N + 7) / 8;
-  for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < ngroups; g += (int64_t)gridDim.x * nwarps) {
-    const int64_t pb = g * 8 + fr;            // pattern whose CLV row this lane loads (B fragment)
-    const int64_t pa0 = g * 8 + 2 * fc;       // patterns whose results this lane holds (C fragment)
-    const bool pb_ok = pb < N, pa0_ok = pa0 < N, pa1_ok = pa0 + 1 < N;
-    MaskT ml = 0, mr = 0;
-    if (ltip && pb_ok) ml = lmask[pb];
-    if (rtip && pb_ok) mr = rmask[pb];
+  const int64_t ngroups = (N + 7) / 8, nsuper = (ngroups + R - 1) / R;
+  for (int64_t sg = (int64_t)blockIdx.x * nwarps + warp; sg < nsuper; sg += (int64_t)gridDim.x * nwarps) {
+    int64_t pb[R], pa0[R];  // pb: pattern whose CLV row this lane loads (B fragment); pa0, pa0 + 1: patterns
+    bool pb_ok[R], pa0_ok[R], pa1_ok[R];  // whose results this lane holds (C fragment)
+    MaskT ml[R], mr[R];
+    bool l1hot = true, r1hot = true;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t g = sg * R + r;
+      pb[r] = g * 8 + fr;
+      pa0[r] = g * 8 + 2 * fc;
+      pb_ok[r] = pb[r] < N; pa0_ok[r] = pa0[r] < N; pa1_ok[r] = pa0[r] + 1 < N;
+      ml[r] = 0; mr[r] = 0;
+      if (ltip && pb_ok[r]) ml[r] = lmask[pb[r]];
+      if (rtip && pb_ok[r]) mr[r] = rmask[pb[r]];
+      l1hot = l1hot && (!pb_ok[r] || ((ml[r] & keep) & ((ml[r] & keep) - 1)) == 0);
+      r1hot = r1hot && (!pb_ok[r] || ((mr[r] & keep) & ((mr[r] & keep) - 1)) == 0);
+    }
     // One-hot tips (the usual case: an observed state): P L is column j of P, taken straight
     // from the A-fragment table -- no DMMA for that side. 0/1 products and additions of +0 are
     // exact, so the values are those of the DMMA path bit for bit. Decided per warp.
-    const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
-    const bool lhot = ltip && __all_sync(0xffffffffu, !pb_ok || ((ml & keep) & ((ml & keep) - 1)) == 0);
-    const bool rhot = rtip && __all_sync(0xffffffffu, !pb_ok || ((mr & keep) & ((mr & keep) - 1)) == 0);
-    int jl0 = 0, jl1 = 0, jr0 = 0, jr1 = 0;  // state of the tip for this lane's two result patterns
-    if (lhot) {
-      jl0 = pa0_ok ? __ffsll((long long)(lmask[pa0] & keep)) - 1 : 0;
-      jl1 = pa1_ok ? __ffsll((long long)(lmask[pa0 + 1] & keep)) - 1 : 0;
-    }
-    if (rhot) {
-      jr0 = pa0_ok ? __ffsll((long long)(rmask[pa0] & keep)) - 1 : 0;
-      jr1 = pa1_ok ? __ffsll((long long)(rmask[pa0 + 1] & keep)) - 1 : 0;
-    }
+    const bool lhot = ltip && __all_sync(0xffffffffu, l1hot);
+    const bool rhot = rtip && __all_sync(0xffffffffu, r1hot);
     // element (i, j) of a fragment table: [mt = i/8][ks = j/4][lane = (i%8)*4 + j%4]
-    const int col_l0 = (jl0 >> 2) * 32 + fr * 4 + (jl0 & 3), col_l1 = (jl1 >> 2) * 32 + fr * 4 + (jl1 & 3);
-    const int col_r0 = (jr0 >> 2) * 32 + fr * 4 + (jr0 & 3), col_r1 = (jr1 >> 2) * 32 + fr * 4 + (jr1 & 3);
-    int h0 = (int)0x80000000, h1 = (int)0x80000000;
-    for (int k = 0; k < K; ++k) {
-      double bl[KS], br[KS];
+    int col_l0[R], col_l1[R], col_r0[R], col_r1[R];
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int j = ks * 4 + fc;
-        const bool ok = pb_ok && j < S;
-        if (ltip) bl[ks] = (ok && ((ml >> j) & 1)) ? 1.0 : 0.0;
-        else bl[ks] = ok ? lclv[((size_t)pb * K + k) * S + j] : 0.0;
-        if (rtip) br[ks] = (ok && ((mr >> j) & 1)) ? 1.0 : 0.0;
-        else br[ks] = ok ? rclv[((size_t)pb * K + k) * S + j] : 0.0;
+    for (int r = 0; r < R; ++r) {
+      int jl0 = 0, jl1 = 0, jr0 = 0, jr1 = 0;  // state of the tip for this lane's two result patterns
+      if (lhot) {
+        jl0 = pa0_ok[r] ? __ffsll((long long)(lmask[pa0[r]] & keep)) - 1 : 0;
+        jl1 = pa1_ok[r] ? __ffsll((long long)(lmask[pa0[r] + 1] & keep)) - 1 : 0;
+      }
+      if (rhot) {
+        jr0 = pa0_ok[r] ? __ffsll((long long)(rmask[pa0[r]] & keep)) - 1 : 0;
+        jr1 = pa1_ok[r] ? __ffsll((long long)(rmask[pa0[r] + 1] & keep)) - 1 : 0;
+      }
+      col_l0[r] = (jl0 >> 2) * 32 + fr * 4 + (jl0 & 3); col_l1[r] = (jl1 >> 2) * 32 + fr * 4 + (jl1 & 3);
+      col_r0[r] = (jr0 >> 2) * 32 + fr * 4 + (jr0 & 3); col_r1[r] = (jr1 >> 2) * 32 + fr * 4 + (jr1 & 3);
+    }
+    int h0[R], h1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { h0[r] = (int)0x80000000; h1[r] = (int)0x80000000; }
+    for (int k = 0; k < K; ++k) {
+      double bl[R][KS], br[R][KS];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const int j = ks * 4 + fc;
+          const bool ok = pb_ok[r] && j < S;
+          if (ltip) bl[r][ks] = (ok && ((ml[r] >> j) & 1)) ? 1.0 : 0.0;
+          else bl[r][ks] = ok ? lclv[((size_t)pb[r] * K + k) * S + j] : 0.0;
+          if (rtip) br[r][ks] = (ok && ((mr[r] >> j) & 1)) ? 1.0 : 0.0;
+          else br[r][ks] = ok ? rclv[((size_t)pb[r] * K + k) * S + j] : 0.0;
+        }
       }
       const double *flk0 = fl + (size_t)k * MT * KS * 32, *frk0 = frg + (size_t)k * MT * KS * 32;
       const double *flk = flk0 + lane, *frk = frk0 + lane;
 #pragma unroll 2
       for (int mt = 0; mt < MT; ++mt) {
-        double cx[2] = {0.0, 0.0}, cy[2] = {0.0, 0.0};
+        double cx[R][2], cy[R][2];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { cx[r][0] = cx[r][1] = 0.0; cy[r][0] = cy[r][1] = 0.0; }
         if (lhot) {
-          cx[0] = flk0[mt * KS * 32 + col_l0];
-          cx[1] = flk0[mt * KS * 32 + col_l1];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            cx[r][0] = flk0[mt * KS * 32 + col_l0[r]];
+            cx[r][1] = flk0[mt * KS * 32 + col_l1[r]];
+          }
         } else {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) dmma_8x8x4(cx, flk[(mt * KS + ks) * 32], bl[ks]);
+          for (int ks = 0; ks < KS; ++ks) {
+            const double a = flk[(mt * KS + ks) * 32];
+#pragma unroll
+            for (int r = 0; r < R; ++r) dmma_8x8x4(cx[r], a, bl[r][ks]);
+          }
         }
         if (rhot) {
-          cy[0] = frk0[mt * KS * 32 + col_r0];
-          cy[1] = frk0[mt * KS * 32 + col_r1];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            cy[r][0] = frk0[mt * KS * 32 + col_r0[r]];
+            cy[r][1] = frk0[mt * KS * 32 + col_r1[r]];
+          }
         } else {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) dmma_8x8x4(cy, frk[(mt * KS + ks) * 32], br[ks]);
+          for (int ks = 0; ks < KS; ++ks) {
+            const double a = frk[(mt * KS + ks) * 32];
+#pragma unroll
+            for (int r = 0; r < R; ++r) dmma_8x8x4(cy[r], a, br[r][ks]);
+          }
         }
         const int i = mt * 8 + fr;
         if (i < S) {
-          const double v0 = cx[0] * cy[0], v1 = cx[1] * cy[1];
-          if (pa0_ok) { out[((size_t)pa0 * K + k) * S + i] = v0; h0 = max(h0, hi32(v0)); }
-          if (pa1_ok) { out[((size_t)(pa0 + 1) * K + k) * S + i] = v1; h1 = max(h1, hi32(v1)); }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const double v0 = cx[r][0] * cy[r][0], v1 = cx[r][1] * cy[r][1];
+            if (pa0_ok[r]) { out[((size_t)pa0[r] * K + k) * S + i] = v0; h0[r] = max(h0[r], hi32(v0)); }
+            if (pa1_ok[r]) { out[((size_t)(pa0[r] + 1) * K + k) * S + i] = v1; h1[r] = max(h1[r], hi32(v1)); }
+          }
         }
       }
     }
-    // site maximum over all rows: combine the 8 row groups (lanes with equal lane%4)
 #pragma unroll
-    for (int off = 4; off <= 16; off <<= 1) {
-      h0 = max(h0, __shfl_xor_sync(0xffffffffu, h0, off));
-      h1 = max(h1, __shfl_xor_sync(0xffffffffu, h1, off));
-    }
-    const bool r0 = pa0_ok && h0 < kScaleHiThresh, r1 = pa1_ok && h1 < kScaleHiThresh;
-    if (r0 || r1) {  // rare: rescale in place what this lane stored
-      for (int k = 0; k < K; ++k)
-        for (int mt = 0; mt < MT; ++mt) {
-          const int i = mt * 8 + fr;
-          if (i < S) {
-            if (r0) out[((size_t)pa0 * K + k) * S + i] *= 0x1p+256;
-            if (r1) out[((size_t)(pa0 + 1) * K + k) * S + i] *= 0x1p+256;
+    for (int r = 0; r < R; ++r) {
+      // site maximum over all rows: combine the 8 row groups (lanes with equal lane%4)
+      int a0 = h0[r], a1 = h1[r];
+#pragma unroll
+      for (int off = 4; off <= 16; off <<= 1) {
+        a0 = max(a0, __shfl_xor_sync(0xffffffffu, a0, off));
+        a1 = max(a1, __shfl_xor_sync(0xffffffffu, a1, off));
+      }
+      const bool r0 = pa0_ok[r] && a0 < kScaleHiThresh, r1 = pa1_ok[r] && a1 < kScaleHiThresh;
+      if (r0 || r1) {  // rare: rescale in place what this lane stored
+        for (int k = 0; k < K; ++k)
+          for (int mt = 0; mt < MT; ++mt) {
+            const int i = mt * 8 + fr;
+            if (i < S) {
+              if (r0) out[((size_t)pa0[r] * K + k) * S + i] *= 0x1p+256;
+              if (r1) out[((size_t)(pa0[r] + 1) * K + k) * S + i] *= 0x1p+256;
+            }
           }
-        }
-    }
-    if (fr == 0) {
-      if (pa0_ok) osc[pa0] = (ltip ? 0 : lsc[pa0]) + (rtip ? 0 : rsc[pa0]) + (r0 ? 1 : 0);
-      if (pa1_ok) osc[pa0 + 1] = (ltip ? 0 : lsc[pa0 + 1]) + (rtip ? 0 : rsc[pa0 + 1]) + (r1 ? 1 : 0);
+      }
+      if (fr == 0) {
+        if (pa0_ok[r]) osc[pa0[r]] = (ltip ? 0 : lsc[pa0[r]]) + (rtip ? 0 : rsc[pa0[r]]) + (r0 ? 1 : 0);
+        if (pa1_ok[r]) osc[pa0[r] + 1] = (ltip ? 0 : lsc[pa0[r] + 1]) + (rtip ? 0 : rsc[pa0[r] + 1]) + (r1 ? 1 : 0);
+      }
     }
   }
 }
