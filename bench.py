@@ -551,9 +551,10 @@ def main():
                 if os.path.exists(tpath):
                     with open(tpath) as f:
                         tj = json.load(f)
-                    t = tj.get(name)
-                    if t and t.get("patterns") and t.get("workload", "dna") == args.workload:
-                        traffic = t["dram_bytes_per_launch"] * n_local / t["patterns"]
+                    for t in (tj.get(name), tj.get(name + "_small")):
+                        if (t and t.get("patterns") and t.get("workload", "dna") == args.workload and
+                                t.get("min_patterns", 0) <= n_local <= t.get("max_patterns", 1 << 62)):
+                            traffic = t["dram_bytes_per_launch"] * n_local / t["patterns"]
                 roof = {"bound": "hbm", "kernel": name, "achieved": entry["achieved_gbs"], "peak": hbm_peak,
                         "unit": "GB/s", "frac": entry["frac"], "traffic": traffic, "peak_source": peak_src,
                         "bytes_model": ("compulsory (tree-fused: each interior CLV + scale counter written once, "

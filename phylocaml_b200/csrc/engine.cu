@@ -740,17 +740,6 @@ static cudaError_t launch_prune_any(phylo_engine *e, const double *Pl, const dou
   return cudaSuccess;
 }
 
-// pattern groups per warp of prune_mma_kernel (its template parameter R); PHYLO_MMA_R overrides
-static int mma_groups_per_warp(int S) {
-  static int env = -1;
-  if (env < 0) {
-    const char *v = std::getenv("PHYLO_MMA_R");
-    env = v ? std::atoi(v) : 0;
-  }
-  if (env > 0) return env;
-  return S <= 32 ? 2 : 2;
-}
-
 // fp64 tensor-core path for S = 20 / 61; returns false when the A fragments of all K rate
 // classes do not fit in shared memory (then the FMA kernel above is used)
 template <int S, typename MaskT>
@@ -759,31 +748,18 @@ static bool launch_prune_mma(phylo_engine *e, const double *Pl, const double *Pr
   constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4;
   const size_t smem = sizeof(double) * 2 * (size_t)e->K * MT * KS * 32;
   if (smem > 200 * 1024) return false;
-#define MMA_LAUNCH_R(LT, RT, RR)                                                                        \
-  {                                                                                                     \
-    auto kern = prune_mma_kernel<S, MaskT, LT, RT, RR>;                                                 \
-    *st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    if (*st != cudaSuccess) return true;                                                                \
-    const int g = resident_grid(e, kern, 256, smem, (e->N + 64 * RR - 1) / (64 * RR));                  \
-    kern<<<g, 256, smem, e->stream>>>(Pl, Pr, l.src, l.scale, r.src, r.scale, out, osc, e->N, e->K);    \
-  }
 #define MMA_LAUNCH(LT, RT)                                                                              \
   {                                                                                                     \
-    bool launched = false;                                                                              \
-    if constexpr (S <= 32) {                                                                            \
-      if (rr >= 4) { MMA_LAUNCH_R(LT, RT, 4) launched = true; }                                         \
-    }                                                                                                   \
-    if (!launched) {                                                                                    \
-      if (rr >= 2) MMA_LAUNCH_R(LT, RT, 2)                                                              \
-      else MMA_LAUNCH_R(LT, RT, 1)                                                                      \
-    }                                                                                                   \
+    auto kern = prune_mma_kernel<S, MaskT, LT, RT>;                                                     \
+    *st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    if (*st != cudaSuccess) return true;                                                                \
+    const int g = resident_grid(e, kern, 256, smem, (e->N + 63) / 64);                                  \
+    kern<<<g, 256, smem, e->stream>>>(Pl, Pr, l.src, l.scale, r.src, r.scale, out, osc, e->N, e->K);    \
   }
-  const int rr = mma_groups_per_warp(S);
   if (l.tip && r.tip) MMA_LAUNCH(true, true)
   else if (l.tip) MMA_LAUNCH(true, false)
   else if (r.tip) MMA_LAUNCH(false, true)
   else MMA_LAUNCH(false, false)
-#undef MMA_LAUNCH_R
 #undef MMA_LAUNCH
   return true;
 }

@@ -575,18 +575,45 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// Which contraction index j sits in k-slot (ks, fc) of a fragment, and which output state i in
+// row slot (mt, fr), is free as long as the A table and the B / C fragments agree. The identity
+// (j = 4 ks + fc, i = 8 mt + fr) makes every lane touch 8 bytes per access: a warp-wide load is
+// 8 rows x 32 bytes, a store 4 rows x 64 bytes, and ncu shows the LSU 87 % busy with those
+// (profiles/r01_ncu_prune_mma_*). For 20 states (160-byte rows, 32-byte aligned) the map below
+// lets a lane load j = 4 fc .. 4 fc + 3 with one 256-bit access (k-steps 0-3; k-step 4 takes
+// j = 16 + fc) and store i = 2 fr, 2 fr + 1 with one 128-bit access (row tiles 0, 1; tile 2 takes
+// i = 16 + fr). 61-state rows are only 8-byte aligned (488 bytes), so codons keep the identity.
+template <int S>
+struct MmaMap {
+  static constexpr bool kVec = false;
+  __device__ static __forceinline__ int j_of(int ks, int fc) { return ks * 4 + fc; }
+  __device__ static __forceinline__ int i_of(int mt, int fr) { return mt * 8 + fr; }
+  // offset of column j inside one row tile of the A table ([ks][lane]), without the fr * 4 term
+  __device__ static __forceinline__ int col_slot(int j) { return (j >> 2) * 32 + (j & 3); }
+};
+template <>
+struct MmaMap<20> {
+  static constexpr bool kVec = true;
+  __device__ static __forceinline__ int j_of(int ks, int fc) { return ks < 4 ? 4 * fc + ks : 16 + fc; }
+  __device__ static __forceinline__ int i_of(int mt, int fr) { return mt < 2 ? 2 * fr + mt : 16 + fr; }
+  __device__ static __forceinline__ int col_slot(int j) { return j < 16 ? (j & 3) * 32 + (j >> 2) : 4 * 32 + (j - 16); }
+};
+
+__device__ __forceinline__ void st128(double *p, double a, double b) {
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
 // LT / RT: the side is a tip (compile-time, so the inner+inner instance carries none of the
 // tip code: with run-time flags its main loop lost 20 % to register pressure).
-// R: pattern groups (of 8) a warp works on at once. Every A fragment read from shared memory
-// feeds R DMMAs (one per group, the groups' B fragments live in registers): the R = 1 kernel was
-// bound by exactly those reads (ncu: L1/LSU 87 % busy, tensor pipe 56 %, profiles/r01_ncu_prune_mma_*).
-// The arithmetic per pattern is unchanged, so every R gives bit-identical CLVs.
-template <int S, typename MaskT, bool LT, bool RT, int R>
+// Measured and not kept: several pattern groups per warp sharing each A-fragment read (R = 2:
+// +0.5 %, R = 4: 55 % slower for 20 states; R = 2: 19 % slower for 61 states).
+template <int S, typename MaskT, bool LT, bool RT>
 __global__ void __launch_bounds__(256)
 prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
                  const void *__restrict__ lsrc, const int32_t *__restrict__ lsc,
                  const void *__restrict__ rsrc, const int32_t *__restrict__ rsc,
                  double *__restrict__ out, int32_t *__restrict__ osc, int64_t N, int K) {
+  using Map = MmaMap<S>;
   constexpr bool ltip = LT, rtip = RT;
   constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4;
   extern __shared__ __align__(16) double frag[];  // [2][K][MT][KS][32]
@@ -600,7 +627,7 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
     const int mt = (int)(rest % MT); rest /= MT;
     const int k = (int)(rest % K);
     const int which = (int)(rest / K);
-    const int i = mt * 8 + (l >> 2), j = ks * 4 + (l & 3);
+    const int i = Map::i_of(mt, l >> 2), j = Map::j_of(ks, l & 3);
     const double *P = which ? Pr : Pl;
     frag[idx] = (i < S && j < S) ? P[((size_t)k * S + i) * S + j] : 0.0;
   }
@@ -610,132 +637,140 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
   const MaskT *lmask = (const MaskT *)lsrc, *rmask = (const MaskT *)rsrc;
   const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
 
-  const int64_t ngroups = (N + 7) / 8, nsuper = (ngroups + R - 1) / R;
-  for (int64_t sg = (int64_t)blockIdx.x * nwarps + warp; sg < nsuper; sg += (int64_t)gridDim.x * nwarps) {
-    int64_t pb[R], pa0[R];  // pb: pattern whose CLV row this lane loads (B fragment); pa0, pa0 + 1: patterns
-    bool pb_ok[R], pa0_ok[R], pa1_ok[R];  // whose results this lane holds (C fragment)
-    MaskT ml[R], mr[R];
-    bool l1hot = true, r1hot = true;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t g = sg * R + r;
-      pb[r] = g * 8 + fr;
-      pa0[r] = g * 8 + 2 * fc;
-      pb_ok[r] = pb[r] < N; pa0_ok[r] = pa0[r] < N; pa1_ok[r] = pa0[r] + 1 < N;
-      ml[r] = 0; mr[r] = 0;
-      if (ltip && pb_ok[r]) ml[r] = lmask[pb[r]];
-      if (rtip && pb_ok[r]) mr[r] = rmask[pb[r]];
-      l1hot = l1hot && (!pb_ok[r] || ((ml[r] & keep) & ((ml[r] & keep) - 1)) == 0);
-      r1hot = r1hot && (!pb_ok[r] || ((mr[r] & keep) & ((mr[r] & keep) - 1)) == 0);
-    }
+  const int64_t ngroups = (N + 7) / 8;
+  for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < ngroups; g += (int64_t)gridDim.x * nwarps) {
+    const int64_t pb = g * 8 + fr;            // pattern whose CLV row this lane loads (B fragment)
+    const int64_t pa0 = g * 8 + 2 * fc;       // patterns whose results this lane holds (C fragment)
+    const bool pb_ok = pb < N, pa0_ok = pa0 < N, pa1_ok = pa0 + 1 < N;
+    MaskT ml = 0, mr = 0;
+    if (ltip && pb_ok) ml = lmask[pb];
+    if (rtip && pb_ok) mr = rmask[pb];
     // One-hot tips (the usual case: an observed state): P L is column j of P, taken straight
     // from the A-fragment table -- no DMMA for that side. 0/1 products and additions of +0 are
     // exact, so the values are those of the DMMA path bit for bit. Decided per warp.
-    const bool lhot = ltip && __all_sync(0xffffffffu, l1hot);
-    const bool rhot = rtip && __all_sync(0xffffffffu, r1hot);
-    // element (i, j) of a fragment table: [mt = i/8][ks = j/4][lane = (i%8)*4 + j%4]
-    int col_l0[R], col_l1[R], col_r0[R], col_r1[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int jl0 = 0, jl1 = 0, jr0 = 0, jr1 = 0;  // state of the tip for this lane's two result patterns
-      if (lhot) {
-        jl0 = pa0_ok[r] ? __ffsll((long long)(lmask[pa0[r]] & keep)) - 1 : 0;
-        jl1 = pa1_ok[r] ? __ffsll((long long)(lmask[pa0[r] + 1] & keep)) - 1 : 0;
-      }
-      if (rhot) {
-        jr0 = pa0_ok[r] ? __ffsll((long long)(rmask[pa0[r]] & keep)) - 1 : 0;
-        jr1 = pa1_ok[r] ? __ffsll((long long)(rmask[pa0[r] + 1] & keep)) - 1 : 0;
-      }
-      col_l0[r] = (jl0 >> 2) * 32 + fr * 4 + (jl0 & 3); col_l1[r] = (jl1 >> 2) * 32 + fr * 4 + (jl1 & 3);
-      col_r0[r] = (jr0 >> 2) * 32 + fr * 4 + (jr0 & 3); col_r1[r] = (jr1 >> 2) * 32 + fr * 4 + (jr1 & 3);
+    const bool lhot = ltip && __all_sync(0xffffffffu, !pb_ok || ((ml & keep) & ((ml & keep) - 1)) == 0);
+    const bool rhot = rtip && __all_sync(0xffffffffu, !pb_ok || ((mr & keep) & ((mr & keep) - 1)) == 0);
+    int jl0 = 0, jl1 = 0, jr0 = 0, jr1 = 0;  // state of the tip for this lane's two result patterns
+    if (lhot) {
+      jl0 = pa0_ok ? __ffsll((long long)(lmask[pa0] & keep)) - 1 : 0;
+      jl1 = pa1_ok ? __ffsll((long long)(lmask[pa0 + 1] & keep)) - 1 : 0;
     }
-    int h0[R], h1[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) { h0[r] = (int)0x80000000; h1[r] = (int)0x80000000; }
+    if (rhot) {
+      jr0 = pa0_ok ? __ffsll((long long)(rmask[pa0] & keep)) - 1 : 0;
+      jr1 = pa1_ok ? __ffsll((long long)(rmask[pa0 + 1] & keep)) - 1 : 0;
+    }
+    // element (i, j) of a fragment table: [row tile of i][k-step of j][lane = row slot * 4 + k slot]
+    const int col_l0 = Map::col_slot(jl0) + fr * 4, col_l1 = Map::col_slot(jl1) + fr * 4;
+    const int col_r0 = Map::col_slot(jr0) + fr * 4, col_r1 = Map::col_slot(jr1) + fr * 4;
+    int h0 = (int)0x80000000, h1 = (int)0x80000000;
     for (int k = 0; k < K; ++k) {
-      double bl[R][KS], br[R][KS];
+      double bl[KS], br[KS];
+      if constexpr (Map::kVec) {
+        // 20 states: j = 4 fc .. 4 fc + 3 in one 256-bit load (k-steps 0-3), j = 16 + fc for k-step 4
+        if (ltip) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
+          for (int ks = 0; ks < KS; ++ks) bl[ks] = (pb_ok && ((ml >> Map::j_of(ks, fc)) & 1)) ? 1.0 : 0.0;
+        } else if (pb_ok) {
+          const double *row = lclv + ((size_t)pb * K + k) * S;
+          const d4 v = ld256_stream(row + 4 * fc);
+          bl[0] = v.x; bl[1] = v.y; bl[2] = v.z; bl[3] = v.w; bl[4] = row[16 + fc];
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) bl[ks] = 0.0;
+        }
+        if (rtip) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) br[ks] = (pb_ok && ((mr >> Map::j_of(ks, fc)) & 1)) ? 1.0 : 0.0;
+        } else if (pb_ok) {
+          const double *row = rclv + ((size_t)pb * K + k) * S;
+          const d4 v = ld256_stream(row + 4 * fc);
+          br[0] = v.x; br[1] = v.y; br[2] = v.z; br[3] = v.w; br[4] = row[16 + fc];
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) br[ks] = 0.0;
+        }
+      } else {
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          const int j = ks * 4 + fc;
-          const bool ok = pb_ok[r] && j < S;
-          if (ltip) bl[r][ks] = (ok && ((ml[r] >> j) & 1)) ? 1.0 : 0.0;
-          else bl[r][ks] = ok ? lclv[((size_t)pb[r] * K + k) * S + j] : 0.0;
-          if (rtip) br[r][ks] = (ok && ((mr[r] >> j) & 1)) ? 1.0 : 0.0;
-          else br[r][ks] = ok ? rclv[((size_t)pb[r] * K + k) * S + j] : 0.0;
+          const int j = Map::j_of(ks, fc);
+          const bool ok = pb_ok && j < S;
+          if (ltip) bl[ks] = (ok && ((ml >> j) & 1)) ? 1.0 : 0.0;
+          else bl[ks] = ok ? lclv[((size_t)pb * K + k) * S + j] : 0.0;
+          if (rtip) br[ks] = (ok && ((mr >> j) & 1)) ? 1.0 : 0.0;
+          else br[ks] = ok ? rclv[((size_t)pb * K + k) * S + j] : 0.0;
         }
       }
       const double *flk0 = fl + (size_t)k * MT * KS * 32, *frk0 = frg + (size_t)k * MT * KS * 32;
       const double *flk = flk0 + lane, *frk = frk0 + lane;
-#pragma unroll 2
-      for (int mt = 0; mt < MT; ++mt) {
-        double cx[R][2], cy[R][2];
-#pragma unroll
-        for (int r = 0; r < R; ++r) { cx[r][0] = cx[r][1] = 0.0; cy[r][0] = cy[r][1] = 0.0; }
+      auto tile = [&](int mt, double &v0, double &v1) {  // both patterns' results for row slot (mt, fr)
+        double cx[2] = {0.0, 0.0}, cy[2] = {0.0, 0.0};
         if (lhot) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            cx[r][0] = flk0[mt * KS * 32 + col_l0[r]];
-            cx[r][1] = flk0[mt * KS * 32 + col_l1[r]];
-          }
+          cx[0] = flk0[mt * KS * 32 + col_l0];
+          cx[1] = flk0[mt * KS * 32 + col_l1];
         } else {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const double a = flk[(mt * KS + ks) * 32];
-#pragma unroll
-            for (int r = 0; r < R; ++r) dmma_8x8x4(cx[r], a, bl[r][ks]);
-          }
+          for (int ks = 0; ks < KS; ++ks) dmma_8x8x4(cx, flk[(mt * KS + ks) * 32], bl[ks]);
         }
         if (rhot) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            cy[r][0] = frk0[mt * KS * 32 + col_r0[r]];
-            cy[r][1] = frk0[mt * KS * 32 + col_r1[r]];
-          }
+          cy[0] = frk0[mt * KS * 32 + col_r0];
+          cy[1] = frk0[mt * KS * 32 + col_r1];
         } else {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const double a = frk[(mt * KS + ks) * 32];
-#pragma unroll
-            for (int r = 0; r < R; ++r) dmma_8x8x4(cy[r], a, br[r][ks]);
-          }
+          for (int ks = 0; ks < KS; ++ks) dmma_8x8x4(cy, frk[(mt * KS + ks) * 32], br[ks]);
         }
-        const int i = mt * 8 + fr;
-        if (i < S) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const double v0 = cx[r][0] * cy[r][0], v1 = cx[r][1] * cy[r][1];
-            if (pa0_ok[r]) { out[((size_t)pa0[r] * K + k) * S + i] = v0; h0[r] = max(h0[r], hi32(v0)); }
-            if (pa1_ok[r]) { out[((size_t)(pa0[r] + 1) * K + k) * S + i] = v1; h1[r] = max(h1[r], hi32(v1)); }
+        v0 = cx[0] * cy[0];
+        v1 = cx[1] * cy[1];
+      };
+      if constexpr (Map::kVec) {
+        // row tiles 0 and 1 hold i = 2 fr and 2 fr + 1: one 128-bit store per pattern; tile 2: i = 16 + fr
+        double a0, a1, b0, b1, c0, c1;
+        tile(0, a0, a1);
+        tile(1, b0, b1);
+        tile(2, c0, c1);
+        double *o0 = out + ((size_t)pa0 * K + k) * S, *o1 = o0 + (size_t)K * S;
+        if (pa0_ok) {
+          st128(o0 + 2 * fr, a0, b0);
+          h0 = max(h0, max(hi32(a0), hi32(b0)));
+          if (fr < 4) { o0[16 + fr] = c0; h0 = max(h0, hi32(c0)); }
+        }
+        if (pa1_ok) {
+          st128(o1 + 2 * fr, a1, b1);
+          h1 = max(h1, max(hi32(a1), hi32(b1)));
+          if (fr < 4) { o1[16 + fr] = c1; h1 = max(h1, hi32(c1)); }
+        }
+      } else {
+#pragma unroll 2
+        for (int mt = 0; mt < MT; ++mt) {
+          double v0, v1;
+          tile(mt, v0, v1);
+          const int i = Map::i_of(mt, fr);
+          if (i < S) {
+            if (pa0_ok) { out[((size_t)pa0 * K + k) * S + i] = v0; h0 = max(h0, hi32(v0)); }
+            if (pa1_ok) { out[((size_t)(pa0 + 1) * K + k) * S + i] = v1; h1 = max(h1, hi32(v1)); }
           }
         }
       }
     }
+    // site maximum over all rows: combine the 8 row groups (lanes with equal lane%4)
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      // site maximum over all rows: combine the 8 row groups (lanes with equal lane%4)
-      int a0 = h0[r], a1 = h1[r];
-#pragma unroll
-      for (int off = 4; off <= 16; off <<= 1) {
-        a0 = max(a0, __shfl_xor_sync(0xffffffffu, a0, off));
-        a1 = max(a1, __shfl_xor_sync(0xffffffffu, a1, off));
-      }
-      const bool r0 = pa0_ok[r] && a0 < kScaleHiThresh, r1 = pa1_ok[r] && a1 < kScaleHiThresh;
-      if (r0 || r1) {  // rare: rescale in place what this lane stored
-        for (int k = 0; k < K; ++k)
-          for (int mt = 0; mt < MT; ++mt) {
-            const int i = mt * 8 + fr;
-            if (i < S) {
-              if (r0) out[((size_t)pa0[r] * K + k) * S + i] *= 0x1p+256;
-              if (r1) out[((size_t)(pa0[r] + 1) * K + k) * S + i] *= 0x1p+256;
-            }
+    for (int off = 4; off <= 16; off <<= 1) {
+      h0 = max(h0, __shfl_xor_sync(0xffffffffu, h0, off));
+      h1 = max(h1, __shfl_xor_sync(0xffffffffu, h1, off));
+    }
+    const bool r0 = pa0_ok && h0 < kScaleHiThresh, r1 = pa1_ok && h1 < kScaleHiThresh;
+    if (r0 || r1) {  // rare: rescale in place what this lane stored
+      for (int k = 0; k < K; ++k)
+        for (int mt = 0; mt < MT; ++mt) {
+          const int i = Map::i_of(mt, fr);
+          if (i < S) {
+            if (r0) out[((size_t)pa0 * K + k) * S + i] *= 0x1p+256;
+            if (r1) out[((size_t)(pa0 + 1) * K + k) * S + i] *= 0x1p+256;
           }
-      }
-      if (fr == 0) {
-        if (pa0_ok[r]) osc[pa0[r]] = (ltip ? 0 : lsc[pa0[r]]) + (rtip ? 0 : rsc[pa0[r]]) + (r0 ? 1 : 0);
-        if (pa1_ok[r]) osc[pa0[r] + 1] = (ltip ? 0 : lsc[pa0[r] + 1]) + (rtip ? 0 : rsc[pa0[r] + 1]) + (r1 ? 1 : 0);
-      }
+        }
+    }
+    if (fr == 0) {
+      if (pa0_ok) osc[pa0] = (ltip ? 0 : lsc[pa0]) + (rtip ? 0 : rsc[pa0]) + (r0 ? 1 : 0);
+      if (pa1_ok) osc[pa0 + 1] = (ltip ? 0 : lsc[pa0 + 1]) + (rtip ? 0 : rsc[pa0 + 1]) + (r1 ? 1 : 0);
     }
   }
 }

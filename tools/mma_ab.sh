@@ -1,19 +1,12 @@
 #!/bin/bash
-# Run under gpurun: A/B of prune_mma_kernel's R (pattern groups per warp) on configs 4 and 5,
-# plus the tests that exercise the DMMA kernels under each R.
+# Run under gpurun: the DMMA pruning kernel on configs 4 and 5 (bench) + the tests that exercise it.
 mkdir -p gpurun_out
-for R in 1 2 4; do
-  PHYLO_MMA_R=$R timeout 200 python bench.py --workload aa --steps 5 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-other-modes > gpurun_out/mma_aa_R$R.json 2>> gpurun_out/mma.err
-done
-for R in 1 2; do
-  PHYLO_MMA_R=$R timeout 200 python bench.py --workload codon --steps 5 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-other-modes > gpurun_out/mma_codon_R$R.json 2>> gpurun_out/mma.err
-done
-for R in 2 4; do
-  PHYLO_MMA_R=$R timeout 300 python -m pytest tests -m gpu -q -x -k "aa or codon or cfg4 or cfg5 or edge or group or large_alphabets" > gpurun_out/mma_pytest_R$R.log 2>&1
-  tail -3 gpurun_out/mma_pytest_R$R.log
-done
+timeout 300 python -m pytest tests -m gpu -q -x -k "aa or codon or cfg4 or cfg5 or edge or group or large_alphabets" > gpurun_out/mma_pytest.log 2>&1
+tail -5 gpurun_out/mma_pytest.log
+timeout 200 python bench.py --workload aa --steps 5 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-other-modes > gpurun_out/mma_aa.json 2>> gpurun_out/mma.err
+timeout 200 python bench.py --workload codon --steps 5 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-other-modes > gpurun_out/mma_codon.json 2>> gpurun_out/mma.err
 tail -c 400 gpurun_out/mma.err
-for f in gpurun_out/mma_*.json; do python - "$f" <<'PY'
+for f in gpurun_out/mma_aa.json gpurun_out/mma_codon.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
@@ -21,3 +14,8 @@ try:
 except Exception as ex: print(sys.argv[1], "parse failed", ex)
 PY
 done
+if [ -n "$NCU_MMA" ]; then
+  bash tools/ncu_bench.sh aa 500000 'prune_mma_kernelILi20EjLb0ELb0' 'prune_mma_kernelILi20EjLb1ELb0' > /dev/null 2>&1
+  for f in gpurun_out/prof_aa_*.ncu-rep; do python tools/ncu_summary.py rep $f > ${f%.ncu-rep}.txt 2>&1; done
+  head -30 gpurun_out/prof_aa_*Lb0ELb0*.txt
+fi
