@@ -605,8 +605,10 @@ __device__ __forceinline__ void st128(double *p, double a, double b) {
 
 // LT / RT: the side is a tip (compile-time, so the inner+inner instance carries none of the
 // tip code: with run-time flags its main loop lost 20 % to register pressure).
-// Measured and not kept: several pattern groups per warp sharing each A-fragment read (R = 2:
-// +0.5 %, R = 4: 55 % slower for 20 states; R = 2: 19 % slower for 61 states).
+// Measured and not kept (tools/mma_ab.sh, profiles/README.md): several pattern groups per warp
+// sharing each A-fragment read (R = 2: +0.5 %, R = 4: 55 % slower for 20 states; R = 2: 19 % slower
+// for 61 states); prefetching the next group's rows into L2 (inner+inner 193 -> 250 us); loading
+// the B fragments of rate class k + 1 before the DMMAs of class k (80 registers, 193 -> 203 us).
 template <int S, typename MaskT, bool LT, bool RT>
 __global__ void __launch_bounds__(256)
 prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
