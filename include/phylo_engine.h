@@ -61,6 +61,20 @@ int phylo_engine_set_stream(phylo_engine *e, void *cuda_stream);
 int phylo_engine_sync(phylo_engine *e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches evidence) */
 uint64_t phylo_engine_launch_count(const phylo_engine *e);
+/* Alphabet symbols instead of state masks (the data format one step before the path). With a
+ * table set, every alignment handed to phylo_lk_set_tips(_pitched), phylo_lk_score_alignment,
+ * phylo_fitch_set_tips(_pitched) and phylo_compress_patterns must be 1 byte per cell and is read
+ * as symbols: cell c stands for the state set table256[c], translated on the device by the
+ * kernels that already convert the upload (no extra pass, no host loop). The table is what
+ * Alphabet's name -> code map holds for single-character names, e.g. Alphabet.nucleotides
+ * (lib/alphabet.ml:309-326: A,C,G,T,- = 1,2,4,8,16, IUPAC and indel-polymorphism letters = the OR
+ * of their states, ? = 31) or Alphabet.dna (:301-307); `case:false` alphabets list both cases.
+ * A symbol whose entry is 0 is unknown: the call fails with PHYLO_ERR_DATA, like the reference's
+ * `Illegal_Character` (lib/alphabet.ml:186). For likelihood the caller folds gap / missing into
+ * "all states" in the table (lib/mlModel.mli:75-76). Fitch needs every entry < 256 (sets come
+ * back one byte per character); phylo_compress_patterns likewise, and returns state masks.
+ * table256 == NULL restores plain state-mask input. phylo_fitch_set_states always takes codes. */
+int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256);
 /* Engine options. PHYLO_OPT_FUSED_TREE (default 1): phylo_lk_score_tree evaluates eligible
  * schedules (4 states, K in {1,2,4,8}, plain tree) with a single-launch tree-fused kernel
  * (warp-autonomous kernel for K <= 4, tile kernel otherwise); 2 = tile kernel only;
@@ -256,6 +270,7 @@ phylo_engine *phylo_group_engine(phylo_group *g, int i);
  * (which = 1) that shard i holds; lo == hi for a shard left empty by a short alignment */
 int phylo_group_shard(const phylo_group *g, int which, int i, int64_t *lo, int64_t *hi);
 int phylo_group_set_option(phylo_group *g, int option, int64_t value);
+int phylo_group_set_symbol_table(phylo_group *g, const uint64_t *table256);
 int phylo_group_lk_set_model(phylo_group *g, int S, int K, const double *U, const double *D,
                              const double *Ui, const double *priors, const double *rates,
                              const double *probs, double pinvar);

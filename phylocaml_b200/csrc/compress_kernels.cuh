@@ -23,6 +23,41 @@
 namespace phylo {
 
 // [T][N] elements of EB bytes  ->  [N][TP] bytes (row t of a record at byte t*EB), 32x32 tiles
+// In-place symbol -> state-mask translation of a 1-byte alignment (phylo_engine_set_symbol_table;
+// every table entry fits a byte here). 16 bytes per thread; unknown symbols (entry 0) are counted.
+__global__ void __launch_bounds__(256)
+cmp_symbols_kernel(uint8_t *__restrict__ buf, size_t n, const uint64_t *__restrict__ lut,
+                   unsigned long long *__restrict__ n_bad) {
+  __shared__ uint8_t tab[256];
+  tab[threadIdx.x] = (uint8_t)lut[threadIdx.x];
+  __syncthreads();
+  unsigned long long bad = 0;
+  const size_t nvec = n / 16;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+    uint4 w = reinterpret_cast<uint4 *>(buf)[v];
+    uint32_t *x = reinterpret_cast<uint32_t *>(&w);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t m = tab[(x[q] >> (8 * b)) & 0xff];
+        bad += (m == 0);
+        o |= m << (8 * b);
+      }
+      x[q] = o;
+    }
+    reinterpret_cast<uint4 *>(buf)[v] = w;
+  }
+  if (blockIdx.x == 0)  // ragged tail
+    for (size_t i = nvec * 16 + threadIdx.x; i < n; i += blockDim.x) {
+      const uint8_t m = tab[buf[i]];
+      bad += (m == 0);
+      buf[i] = m;
+    }
+  if (bad) atomicAdd(n_bad, bad);
+}
+
 template <int EB>
 __global__ void __launch_bounds__(256)
 cmp_transpose_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ rec, int T, int64_t N, int TP) {

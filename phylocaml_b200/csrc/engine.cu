@@ -100,6 +100,8 @@ struct phylo_engine {
   size_t capSpill = 0;
   bool tmapDirty = true;
   int64_t tipStride = 0;  // elements per tip row (N rounded up to 1024)
+  uint64_t *dSymTab = nullptr;  // 256 state masks by symbol byte (phylo_engine_set_symbol_table) or NULL
+  bool symtab_fits_byte = false;
   size_t hostPitch = 0;   // bytes between taxon rows of the host alignment being uploaded (0: N * mask_bytes)
   double **dNodeClv = nullptr;   // device tables of node buffers (tree-fused kernel)
   int32_t **dNodeSc = nullptr;
@@ -318,7 +320,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
+  dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -350,6 +352,22 @@ extern "C" int phylo_engine_sync(phylo_engine *e) {
 }
 
 extern "C" uint64_t phylo_engine_launch_count(const phylo_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256) {
+  if (!e) return PHYLO_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  if (!table256) {
+    dfree(e->dSymTab);
+    return PHYLO_OK;
+  }
+  if (!e->dSymTab) CK(cudaMalloc(&e->dSymTab, sizeof(uint64_t) * 256));
+  CK(cudaMemcpy(e->dSymTab, table256, sizeof(uint64_t) * 256, cudaMemcpyHostToDevice));
+  e->symtab_fits_byte = true;
+  for (int i = 0; i < 256; ++i)
+    if (table256[i] > 0xff) e->symtab_fits_byte = false;
+  return PHYLO_OK;
+}
 
 extern "C" int phylo_engine_profile(phylo_engine *e, int enable) {
   if (!e) return PHYLO_ERR_ARG;
@@ -527,19 +545,20 @@ template <typename InT>
 static int launch_tips_prepare(phylo_engine *e, const void *raw, unsigned long long *dBad, int64_t p_lo, int64_t p_hi,
                                cudaStream_t cs) {
   const int g = grid_for(p_hi - p_lo, 256, e->sm_count * 8);
+  const uint64_t *lut = sizeof(InT) == 1 ? e->dSymTab : nullptr;  // symbols are bytes (checked in lk_prepare_shape)
   ProfScope prof(e, KC_TIPS_PREPARE);
   switch (e->mask_dev_bytes) {
     case 1:
       tips_prepare_kernel<InT, uint8_t><<<g, 256, 0, cs>>>((const InT *)raw, (uint8_t *)e->dTips, e->tipStride,
-                                                                 (uint8_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi);
+                                                                 (uint8_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi, lut);
       break;
     case 4:
       tips_prepare_kernel<InT, uint32_t><<<g, 256, 0, cs>>>((const InT *)raw, (uint32_t *)e->dTips, e->tipStride,
-                                                                  (uint32_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi);
+                                                                  (uint32_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi, lut);
       break;
     default:
       tips_prepare_kernel<InT, uint64_t><<<g, 256, 0, cs>>>((const InT *)raw, (uint64_t *)e->dTips, e->tipStride,
-                                                                  (uint64_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi);
+                                                                  (uint64_t *)e->dInv, e->T, e->N, e->S, dBad, p_lo, p_hi, lut);
   }
   LAUNCH_CHECK();
   return PHYLO_OK;
@@ -554,7 +573,9 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
       !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
     return fail(e, PHYLO_ERR_ARG, "%s: bad arguments (T=%d N=%lld mask_bytes=%d capacity=%d)", who, T,
                 (long long)N, mask_bytes, capacity);
-  if (mask_bytes * 8 < e->S)
+  if (e->dSymTab && mask_bytes != 1)
+    return fail(e, PHYLO_ERR_ARG, "%s: a symbol table is set, the alignment must be 1 byte per cell (got %d)", who, mask_bytes);
+  if (!e->dSymTab && mask_bytes * 8 < e->S)
     return fail(e, PHYLO_ERR_ARG, "%s: %d-bit masks cannot hold %d states", who, mask_bytes * 8, e->S);
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
@@ -1541,6 +1562,9 @@ extern "C" int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const 
   if (T < 1 || N < 1 || N > 2000000000ll || !masks || !patterns_out || !weights_out || !n_patterns ||
       !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
     return fail(e, PHYLO_ERR_ARG, "compress_patterns: bad arguments (T=%d N=%lld mask_bytes=%d)", T, (long long)N, mask_bytes);
+  if (e->dSymTab && (mask_bytes != 1 || !e->symtab_fits_byte))
+    return fail(e, PHYLO_ERR_UNSUPPORTED,
+                "compress_patterns: with a symbol table the alignment must be 1 byte per cell and every table entry < 256");
   CK(cudaSetDevice(e->device));
   const int EB = mask_bytes, TP = (int)(((size_t)T * EB + 15) / 16 * 16);
   uint64_t M = 1;
@@ -1572,6 +1596,18 @@ extern "C" int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const 
   cudaStream_t st = e->stream;
   CK(cudaMemcpyAsync(dIn, masks, (size_t)T * N * EB, cudaMemcpyHostToDevice, st));
   if (weights_in) CK(cudaMemcpyAsync(dWin, weights_in, 8 * (size_t)N, cudaMemcpyHostToDevice, st));
+  if (e->dSymTab) {  // the cells are alphabet symbols: translate in place, patterns come out as state masks
+    ProfScope prof(e, KC_COMPRESS);
+    CK(cudaMemsetAsync(dColl, 0, 8, st));
+    cmp_symbols_kernel<<<grid_for((int64_t)(((size_t)T * N + 15) / 16), 256, e->sm_count * 16), 256, 0, st>>>(
+        dIn, (size_t)T * N, e->dSymTab, dColl);
+    LAUNCH_CHECK();
+    unsigned long long unknown = 0;
+    CK(cudaMemcpyAsync(&unknown, dColl, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (unknown)
+      return fail(e, PHYLO_ERR_DATA, "compress_patterns: %llu cells hold a symbol the table does not know", unknown);
+  }
   const int g = grid_for(N, 256, e->sm_count * 16);
   long long hTotal = 0;
   unsigned long long hColl = 0;
@@ -1939,14 +1975,16 @@ static int fitch_sched_capacity(phylo_engine *e, size_t bytes) {
 
 // encode `count` nodes worth of reference-layout codes (already on device in dStage) into
 // plane buffers; returns the number of empty elements through *bad
-static int fitch_encode(phylo_engine *e, const void *dcodes, uint32_t *dst, unsigned long long *dBad) {
+static int fitch_encode(phylo_engine *e, const void *dcodes, uint32_t *dst, unsigned long long *dBad,
+                        bool symbols = true) {
   const int g = grid_for(e->fWords * 32, 256, e->sm_count * 8);
+  const uint64_t *lut = symbols ? e->dSymTab : nullptr;
   ProfScope prof(e, KC_FITCH_TRANSCODE);
   switch (e->felt) {
-    case 1: fitch_encode_kernel<uint8_t><<<g, 256, 0, e->stream>>>((const uint8_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
-    case 2: fitch_encode_kernel<uint16_t><<<g, 256, 0, e->stream>>>((const uint16_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
-    case 4: fitch_encode_kernel<uint32_t><<<g, 256, 0, e->stream>>>((const uint32_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad); break;
-    default: fitch_encode_kernel<uint64_t><<<g, 256, 0, e->stream>>>((const uint64_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad);
+    case 1: fitch_encode_kernel<uint8_t><<<g, 256, 0, e->stream>>>((const uint8_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad, lut); break;
+    case 2: fitch_encode_kernel<uint16_t><<<g, 256, 0, e->stream>>>((const uint16_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad, nullptr); break;
+    case 4: fitch_encode_kernel<uint32_t><<<g, 256, 0, e->stream>>>((const uint32_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad, nullptr); break;
+    default: fitch_encode_kernel<uint64_t><<<g, 256, 0, e->stream>>>((const uint64_t *)dcodes, dst, e->fN, e->fWords, e->fNPdev, dBad, nullptr);
   }
   LAUNCH_CHECK();
   return PHYLO_OK;
@@ -1964,6 +2002,8 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
   if (host_pitch_bytes != 0 && N > 0 && host_pitch_bytes < (uint64_t)N * (uint64_t)std::max(elt_bytes, 1))
     return fail(e, PHYLO_ERR_ARG, "fitch_set_tips: host pitch %llu is shorter than a row of %lld codes",
                 (unsigned long long)host_pitch_bytes, (long long)N);
+  if (e->dSymTab && elt_bytes != 1)
+    return fail(e, PHYLO_ERR_ARG, "fitch_set_tips: a symbol table is set, the characters must be 1 byte each (got %d)", elt_bytes);
   if (T < 1 || N < 1 || !codes || capacity < T ||
       !(elt_bytes == 1 || elt_bytes == 2 || elt_bytes == 4 || elt_bytes == 8) || n_states < 1 ||
       n_states > elt_bytes * 8)
@@ -2584,7 +2624,7 @@ extern "C" int phylo_fitch_set_states(phylo_engine *e, int node, const void *cod
   if ((rc = fitch_cost_capacity(e, 4)) != PHYLO_OK) return rc;
   CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
   CK(cudaMemcpyAsync(e->dStage, codes, row, cudaMemcpyHostToDevice, e->stream));
-  if ((rc = fitch_encode(e, e->dStage, e->fPre[node], e->dCost)) != PHYLO_OK) return rc;
+  if ((rc = fitch_encode(e, e->dStage, e->fPre[node], e->dCost, false)) != PHYLO_OK) return rc;  // codes, never symbols
   CK(cudaStreamSynchronize(e->stream));
   return PHYLO_OK;
 }

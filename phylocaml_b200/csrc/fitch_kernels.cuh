@@ -545,14 +545,16 @@ tcm_median2_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ 
 template <typename Elt>
 __global__ void __launch_bounds__(256)
 fitch_encode_kernel(const Elt *__restrict__ codes, uint32_t *__restrict__ buf, int64_t N,
-                    int64_t nwords, int NP, unsigned long long *__restrict__ n_bad) {
+                    int64_t nwords, int NP, unsigned long long *__restrict__ n_bad,
+                    const uint64_t *__restrict__ lut) {  // lut != NULL: 1-byte symbols -> state sets
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long bad = 0;
   for (int64_t w = warp0; w < nwords; w += nwarps) {
     const int64_t c = w * 32 + lane;
-    const uint64_t e = c < N ? (uint64_t)codes[c] : 0;
+    uint64_t e = c < N ? (uint64_t)codes[c] : 0;
+    if (lut && c < N) e = lut[e & 0xff];
     const uint64_t keep = NP >= 64 ? ~0ull : ((1ull << NP) - 1);
     if (c < N && (e & keep) == 0) ++bad;
     uint32_t mine = 0, mine2 = 0;

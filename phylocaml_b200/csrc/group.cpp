@@ -181,6 +181,15 @@ extern "C" int phylo_group_set_option(phylo_group *g, int option, int64_t value)
   return PHYLO_OK;
 }
 
+extern "C" int phylo_group_set_symbol_table(phylo_group *g, const uint64_t *table256) {
+  if (!g) return PHYLO_ERR_ARG;
+  for (size_t i = 0; i < g->eng.size(); ++i) {
+    const int rc = phylo_engine_set_symbol_table(g->eng[i], table256);
+    if (rc != PHYLO_OK) return gfail(g, rc, std::string("group_set_symbol_table: ") + phylo_last_error(g->eng[i]));
+  }
+  return PHYLO_OK;
+}
+
 // ------------------------------------------------------------------- likelihood ----
 extern "C" int phylo_group_lk_set_model(phylo_group *g, int S, int K, const double *U, const double *D,
                                         const double *Ui, const double *priors, const double *rates,

@@ -908,7 +908,10 @@ template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, int64_t out_stride,
                     OutT *__restrict__ inv, int T, int64_t N, int S,
-                    unsigned long long *__restrict__ n_bad, int64_t p_lo, int64_t p_hi) {
+                    unsigned long long *__restrict__ n_bad, int64_t p_lo, int64_t p_hi,
+                    const uint64_t *__restrict__ lut) {
+  // lut != NULL (1-byte input only): the cells are alphabet symbols, lut[byte] is the state mask
+  // (phylo_engine_set_symbol_table); a symbol the table does not know maps to 0 and is counted bad
   // patterns [p_lo, p_hi): a slab of the alignment (the whole of it for a plain set_tips)
   const uint64_t keep = (S >= 64) ? ~0ull : ((1ull << S) - 1);
   unsigned long long bad = 0;
@@ -916,7 +919,8 @@ tips_prepare_kernel(const InT *__restrict__ in, OutT *__restrict__ out, int64_t 
        p += (int64_t)gridDim.x * blockDim.x) {
     uint64_t all = keep;
     for (int t = 0; t < T; ++t) {
-      const uint64_t m = (uint64_t)in[(int64_t)t * N + p] & keep;
+      const uint64_t raw = (uint64_t)in[(int64_t)t * N + p];
+      const uint64_t m = (lut ? lut[raw & 0xff] : raw) & keep;
       out[(int64_t)t * out_stride + p] = (OutT)m;
       if (m == 0) ++bad;
       all &= m;

@@ -35,6 +35,7 @@ SIGNATURES = {
     "phylo_engine_set_stream": (C.c_int, [_vp, _vp]),
     "phylo_engine_sync": (C.c_int, [_vp]),
     "phylo_engine_launch_count": (C.c_uint64, [_vp]),
+    "phylo_engine_set_symbol_table": (C.c_int, [_vp, _u64p]),
     "phylo_engine_set_option": (C.c_int, [_vp, C.c_int, _i64]),
     "phylo_engine_get_option": (C.c_int, [_vp, C.c_int, C.POINTER(_i64)]),
     "phylo_engine_profile": (C.c_int, [_vp, C.c_int]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "phylo_group_engine": (_vp, [_vp, C.c_int]),
     "phylo_group_shard": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64)]),
     "phylo_group_set_option": (C.c_int, [_vp, C.c_int, _i64]),
+    "phylo_group_set_symbol_table": (C.c_int, [_vp, _u64p]),
     "phylo_group_lk_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
     "phylo_group_lk_set_tips": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int]),
     "phylo_group_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
@@ -230,6 +232,15 @@ class Engine:
         return int(self.lib.phylo_engine_launch_count(self.h))
 
     OPT_FUSED_TREE, OPT_RETAIN_CLV, OPT_FITCH_WALK = 1, 2, 3
+
+    def set_symbol_table(self, table):
+        """256 state masks by symbol byte (phylocaml_b200.alphabet), or None for plain masks."""
+        if table is None:
+            self._ck(self.lib.phylo_engine_set_symbol_table(self.h, None))
+            return
+        t = np.ascontiguousarray(table, dtype=np.uint64)
+        assert t.shape == (256,)
+        self._ck(self.lib.phylo_engine_set_symbol_table(self.h, _p(t, _u64p)))
 
     def set_option(self, option, value):
         self._ck(self.lib.phylo_engine_set_option(self.h, option, int(value)))
@@ -506,6 +517,10 @@ class Group:
     @property
     def launch_count(self):
         return sum(self.lib.phylo_engine_launch_count(self.lib.phylo_group_engine(self.h, i)) for i in range(self.size))
+
+    def set_symbol_table(self, table):
+        t = None if table is None else np.ascontiguousarray(table, dtype=np.uint64)
+        self._ck(self.lib.phylo_group_set_symbol_table(self.h, None if t is None else _p(t, _u64p)))
 
     def set_option(self, option, value):
         self._ck(self.lib.phylo_group_set_option(self.h, option, int(value)))

@@ -550,3 +550,19 @@ CAMLprim value nonadd_CAML_group_score_tree(value vg, value ids, value va, value
   gcheck(g, rc);
   CAMLreturn(Val_long((intptr_t)len));
 }
+
+/* external set_symbol_table : engine -> (int64, int64_elt, c_layout) Array1.t option -> unit
+ * 256 state masks indexed by symbol byte, read off Alphabet.t's name_code map for the
+ * single-character names (lib/alphabet.ml:180-199); None restores state-mask input. */
+CAMLprim value phylo_CAML_set_symbol_table(value ve, value vtab)
+{
+  CAMLparam2(ve, vtab);
+  phylo_engine *e = Engine_val(ve);
+  const uint64_t *t = NULL;
+  if (vtab != Val_int(0)) {
+    if (Bigarray_val(Field(vtab, 0))->dim[0] != 256) caml_failwith("set_symbol_table: need 256 entries");
+    t = (const uint64_t *)Data_bigarray_val(Field(vtab, 0));
+  }
+  check(e, phylo_engine_set_symbol_table(e, t));
+  CAMLreturn(Val_unit);
+}

@@ -78,6 +78,27 @@ def test_group_create_fails_loudly_without_gpu(built):
     assert lib.phylo_group_create(devs, 0, ctypes.byref(h)) == -2  # PHYLO_ERR_ARG
 
 
+def test_alphabet_tables_follow_the_reference():
+    """phylocaml_b200/alphabet.py against what the reference pins: test/alphabetTest.ml:12-18
+    (1,2,4,8,16 <-> A,C,G,T,- in Alphabet.dna) and the equates of lib/alphabet.ml:301-326."""
+    from phylocaml_b200 import alphabet
+
+    d = alphabet.dna_codes()
+    assert [d[c] for c in "ACGT-X"] == [1, 2, 4, 8, 16, 32]
+    assert [d[c] for c in "01234"] == [1, 2, 4, 8, 16]
+    n = alphabet.nucleotides_codes()
+    assert [n[c] for c in "ACGT-"] == [1, 2, 4, 8, 16]
+    assert n["R"] == 1 | 4 and n["Y"] == 8 | 2 and n["N"] == 15 and n["X"] == 15 and n["?"] == 31
+    assert n["1"] == 8 | 16 and n["P"] == 31 and n["E"] == 4 | 8 | 1 | 16
+    t = alphabet.nucleotides_table()
+    assert t[ord("a")] == t[ord("A")] == 1 and t[ord("Z")] == 0 and t[ord("?")] == 31
+    lk = alphabet.nucleotides_table_likelihood()
+    assert lk[ord("-")] == 15 and lk[ord("?")] == 15 and lk[ord("8")] == 1 and lk[ord("Z")] == 0
+    aa = alphabet.aminoacids_table_likelihood()
+    assert aa[ord("A")] == 1 and aa[ord("V")] == 1 << 19 and aa[ord("X")] == (1 << 20) - 1
+    assert np.array_equal(alphabet.translate(t, np.frombuffer(b"ACgt-", dtype=np.uint8)), [1, 2, 4, 8, 16])
+
+
 # ------------------------------------------------------------- eigen-decomposition ----
 @pytest.mark.parametrize("case", ["dna_gtr", "dna_f81", "aa20", "codon61"])
 def test_diagonalize_gtr_reproduces_reference_P(built, oracle, case):
