@@ -553,6 +553,7 @@ def main():
                         tj = json.load(f)
                     for t in (tj.get(name), tj.get(name + "_small")):
                         if (t and t.get("patterns") and t.get("workload", "dna") == args.workload and
+                                t.get("taxa") in (None, T) and
                                 t.get("min_patterns", 0) <= n_local <= t.get("max_patterns", 1 << 62)):
                             traffic = t["dram_bytes_per_launch"] * n_local / t["patterns"]
                 roof = {"bound": "hbm", "kernel": name, "achieved": entry["achieved_gbs"], "peak": hbm_peak,
