@@ -167,18 +167,22 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def build_tips(tree_mod, tr, model, T, n_local, S, rank):
-    """Evolve BASE_PATTERNS realistic patterns down the tree once, tile to the shard size, into
-    page-locked host memory (the e2e leg uploads from there)."""
+def build_tips(tree_mod, tr, model, T, n_local, S, lo=0):
+    """Evolve BASE_PATTERNS realistic patterns down the tree once; the global alignment is that
+    block tiled to the workload size, and a rank holds columns [lo, lo + n_local) of it (so every
+    rank count scores the same alignment), in page-locked host memory (the e2e leg uploads from
+    there)."""
     from phylocaml_b200 import engine
 
-    base_n = min(BASE_PATTERNS, max(n_local, 1))
+    base_n = BASE_PATTERNS
     base = tree_mod.evolve_tips(tr, model, base_n, seed=3, dtype=mask_dtype(S))
-    base = np.roll(base, 997 * rank, axis=1)
     tips = engine.pinned_empty((T, n_local), mask_dtype(S))
-    for lo in range(0, n_local, base_n):
-        hi = min(n_local, lo + base_n)
-        tips[:, lo:hi] = base[:, :hi - lo]
+    pos = 0
+    while pos < n_local:
+        off = (lo + pos) % base_n
+        n = min(base_n - off, n_local - pos)
+        tips[:, pos:pos + n] = base[:, off:off + n]
+        pos += n
     return tips
 
 
@@ -452,10 +456,14 @@ def main():
     if args.workload == "fitch":
         model = None
         tips = engine.pinned_empty((T, n_local), np.uint8)
-        base = tree_mod.random_fitch_chars(T, min(n_local, 1 << 20), 4, seed=5 + rank)
-        for a in range(0, n_local, base.shape[1]):
-            b = min(n_local, a + base.shape[1])
-            tips[:, a:b] = base[:, :b - a]
+        # the global alignment is one random block tiled to n_total; this rank holds columns [lo, hi)
+        base = tree_mod.random_fitch_chars(T, min(n_total, 1 << 20), 4, seed=5)
+        pos = 0
+        while pos < n_local:
+            off = (lo + pos) % base.shape[1]
+            n = min(base.shape[1] - off, n_local - pos)
+            tips[:, pos:pos + n] = base[:, off:off + n]
+            pos += n
         eng.set_option(eng.OPT_FITCH_WALK, {"auto": 1, "tile": 3, "regwalk": 2, "l2": 0}[args.fitch_kernel])
         eng.fitch_set_tips(tips, 4, capacity=n_nodes)
         acc = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -478,7 +486,7 @@ def main():
         h2d = tips.nbytes
     else:
         model = make_model(wl)
-        tips = build_tips(tree_mod, tr, model, T, n_local, S, rank)
+        tips = build_tips(tree_mod, tr, model, T, n_local, S, lo)
         eng.lk_set_model(model)
 
         def set_mode(mode):
