@@ -99,6 +99,31 @@ def test_alphabet_tables_follow_the_reference():
     assert np.array_equal(alphabet.translate(t, np.frombuffer(b"ACgt-", dtype=np.uint8)), [1, 2, 4, 8, 16])
 
 
+def test_bench_ranks_hold_slices_of_one_global_alignment(monkeypatch):
+    """bench.py: for every rank count the shards are contiguous, 1024-aligned, cover [0, N) and
+    concatenate to the alignment a single rank scores; the L2 rule flags the small configurations."""
+    import bench
+
+    monkeypatch.setattr(engine, "pinned_empty", lambda shape, dtype: np.empty(shape, dtype))
+    monkeypatch.setattr(bench, "BASE_PATTERNS", 3000)
+    model = mlmodel.create(("JC69",), 4)
+    tr = tree.random_tree(6, 2)
+    N = 10_000
+    whole = bench.build_tips(tree, tr, model, 6, N, 4, 0)
+    assert np.array_equal(whole[:, :3000], whole[:, 3000:6000])
+    for world in (1, 2, 3, 8):
+        bounds = [bench.shard_bounds(N, world, r) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == N
+        assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+        assert all(lo % 1024 == 0 for lo, hi in bounds if hi > lo)
+        parts = [bench.build_tips(tree, tr, model, 6, hi - lo, 4, lo) for lo, hi in bounds if hi > lo]
+        assert np.array_equal(np.concatenate(parts, axis=1), whole)
+    foot = bench.device_footprint
+    assert foot("fitch", 64, 4, 1, 1, None, 1_000_000) == 127 * 0.5 * 1_000_000 < 4 * bench.L2_BYTES
+    assert foot("dna", 256, 4, 4, 1, "fused", 4_000_000) > 100e9
+    assert foot("dna", 256, 4, 4, 1, "fused-lnl", 500_000) < 4 * bench.L2_BYTES
+
+
 # ------------------------------------------------------------- eigen-decomposition ----
 @pytest.mark.parametrize("case", ["dna_gtr", "dna_f81", "aa20", "codon61"])
 def test_diagonalize_gtr_reproduces_reference_P(built, oracle, case):
