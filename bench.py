@@ -533,7 +533,7 @@ def main():
     # a timed region shorter than a few nvidia-smi samples (50 ms apart): keep the same load running,
     # untimed, for ~0.6 s so that the clocks / throttle reasons are sampled under it (the count is
     # derived from the all-reduced time, so every rank runs the same number of steps)
-    extra_steps = 0 if ms >= 600.0 else min(5000, int(np.ceil((600.0 - ms) / max(ms / args.steps, 1e-3))))
+    extra_steps = 0 if ms >= 600.0 else min(20000, int(np.ceil((600.0 - ms) / max(ms / args.steps, 1e-3))))
     for _ in range(extra_steps):
         step()
     clocks = sampler.stop() if sampler else None
