@@ -100,6 +100,10 @@ struct phylo_engine {
   size_t capSpill = 0;
   bool tmapDirty = true;
   int64_t tipStride = 0;  // elements per tip row (N rounded up to 1024)
+  double *dTT = nullptr;        // tip+tip table of finished vectors (20 / 61 states), S*S rows of K*S doubles
+  int32_t *dTTsc = nullptr;     // their scale counters
+  size_t capTT = 0;
+  int opt_tt_table = 1;         // PHYLO_TT_TABLE=0 keeps the DMMA kernel for tip+tip (A/B switch)
   uint64_t *dSymTab = nullptr;  // 256 state masks by symbol byte (phylo_engine_set_symbol_table) or NULL
   bool symtab_fits_byte = false;
   size_t hostPitch = 0;   // bytes between taxon rows of the host alignment being uploaded (0: N * mask_bytes)
@@ -259,6 +263,7 @@ extern "C" int phylo_engine_create(int device, phylo_engine **out) {
                 device, prop.major, prop.minor);
   e = new phylo_engine();
   e->device = device;
+  if (const char *v = std::getenv("PHYLO_TT_TABLE")) e->opt_tt_table = std::atoi(v);
   e->sm_count = prop.multiProcessorCount;
   {
     void *fn = nullptr;
@@ -320,7 +325,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
+  dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -785,6 +790,34 @@ static bool launch_prune_mma(phylo_engine *e, const double *Pl, const double *Pr
   return true;
 }
 
+// tip+tip for 20 / 61 states: table of the S*S finished vectors + a copy kernel (lk_kernels.cuh);
+// returns false when the table cannot be allocated (the DMMA kernel is used then)
+template <int S, typename MaskT>
+static bool launch_prune_tt_table(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
+                                  const Operand &r, double *out, int32_t *osc, cudaError_t *st) {
+  const size_t rows = (size_t)S * S, need = rows * e->K * S;
+  if (need > e->capTT) {
+    cudaStreamSynchronize(e->stream);
+    dfree(e->dTT); dfree(e->dTTsc);
+    e->capTT = 0;
+    if (cudaMalloc(&e->dTT, sizeof(double) * need) != cudaSuccess ||
+        cudaMalloc(&e->dTTsc, sizeof(int32_t) * rows) != cudaSuccess) {
+      cudaGetLastError();
+      dfree(e->dTT); dfree(e->dTTsc);
+      return false;
+    }
+    e->capTT = need;
+  }
+  tt_table_kernel<S><<<(unsigned)rows, 128, 0, e->stream>>>(Pl, Pr, e->K, e->dTT, e->dTTsc);
+  ++e->launches;
+  auto kern = prune_tt_copy_kernel<S, MaskT>;
+  const int g = resident_grid(e, kern, 256, 0, (e->N + 63) / 64);
+  kern<<<g, 256, 0, e->stream>>>(Pl, Pr, e->dTT, e->dTTsc, (const MaskT *)l.src, (const MaskT *)r.src, out, osc,
+                                 e->N, e->K);
+  *st = cudaSuccess;
+  return true;
+}
+
 static int lk_launch_prune(phylo_engine *e, const double *Pl, const double *Pr, const Operand &l,
                            const Operand &r, double *out, int32_t *osc) {
   ProfScope prof(e, (l.tip && r.tip) ? KC_PRUNE_TT : ((l.tip || r.tip) ? KC_PRUNE_TI : KC_PRUNE_II));
@@ -797,8 +830,14 @@ static int lk_launch_prune(phylo_engine *e, const double *Pl, const double *Pr, 
       default: launch_prune4<16>(e, Pl, Pr, l, r, out, osc);
     }
   } else {
-    cudaError_t st;
-    if (e->S == 20 && launch_prune_mma<20, uint32_t>(e, Pl, Pr, l, r, out, osc, &st)) {}
+    cudaError_t st = cudaSuccess;
+    bool tt_done = false;
+    if (l.tip && r.tip && e->opt_tt_table) {
+      if (e->S == 20) tt_done = launch_prune_tt_table<20, uint32_t>(e, Pl, Pr, l, r, out, osc, &st);
+      else if (e->S == 61) tt_done = launch_prune_tt_table<61, uint64_t>(e, Pl, Pr, l, r, out, osc, &st);
+    }
+    if (tt_done) {}
+    else if (e->S == 20 && launch_prune_mma<20, uint32_t>(e, Pl, Pr, l, r, out, osc, &st)) {}
     else if (e->S == 61 && launch_prune_mma<61, uint64_t>(e, Pl, Pr, l, r, out, osc, &st)) {}
     else if (e->S == 20) st = launch_prune_any<20, uint32_t>(e, Pl, Pr, l, r, out, osc);
     else if (e->S == 61) st = launch_prune_any<61, uint64_t>(e, Pl, Pr, l, r, out, osc);
