@@ -102,8 +102,7 @@ struct phylo_engine {
   int64_t tipStride = 0;  // elements per tip row (N rounded up to 1024)
   double *dTT = nullptr;        // tip+tip table of finished vectors (20 / 61 states), S*S rows of K*S doubles
   int32_t *dTTsc = nullptr;     // their scale counters
-  int *dTTlist = nullptr;       // [0] = count, [1..] = patterns with an ambiguous tip (tip+tip table path)
-  size_t capTT = 0, capTTlist = 0;
+  size_t capTT = 0;
   int opt_tt_table = 1;         // PHYLO_TT_TABLE=0 keeps the DMMA kernel for tip+tip (A/B switch)
   uint64_t *dSymTab = nullptr;  // 256 state masks by symbol byte (phylo_engine_set_symbol_table) or NULL
   bool symtab_fits_byte = false;
@@ -326,7 +325,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dT);
-  dfree(e->dTT); dfree(e->dTTsc); dfree(e->dTTlist); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
+  dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -809,29 +808,12 @@ static bool launch_prune_tt_table(phylo_engine *e, const double *Pl, const doubl
     }
     e->capTT = need;
   }
-  if ((size_t)e->N + 1 > e->capTTlist) {
-    cudaStreamSynchronize(e->stream);
-    dfree(e->dTTlist);
-    e->capTTlist = 0;
-    if (cudaMalloc(&e->dTTlist, sizeof(int) * ((size_t)e->N + 1)) != cudaSuccess) { cudaGetLastError(); return false; }
-    e->capTTlist = (size_t)e->N + 1;
-  }
-  const int KS = e->K * S, VEC = (KS % 4 == 0) ? 4 : 1, CH = KS / VEC;
-  if (CH > 256 || e->N > 2000000000ll) return false;
-  cudaMemsetAsync(e->dTTlist, 0, sizeof(int), e->stream);
   tt_table_kernel<S><<<(unsigned)rows, 128, 0, e->stream>>>(Pl, Pr, e->K, e->dTT, e->dTTsc);
   ++e->launches;
-  const int threads = (256 / CH) * CH, ppb = threads / CH;
-  const int g = (int)std::max<int64_t>(1, std::min<int64_t>((e->N + (int64_t)ppb * 4 - 1) / ((int64_t)ppb * 4), (int64_t)e->sm_count * 8));
-  if (VEC == 4)
-    prune_tt_copy_kernel<S, MaskT, 4><<<g, threads, 0, e->stream>>>(e->dTT, e->dTTsc, (const MaskT *)l.src, (const MaskT *)r.src,
-                                                                    out, osc, e->N, e->K, e->dTTlist + 1, e->dTTlist);
-  else
-    prune_tt_copy_kernel<S, MaskT, 1><<<g, threads, 0, e->stream>>>(e->dTT, e->dTTsc, (const MaskT *)l.src, (const MaskT *)r.src,
-                                                                    out, osc, e->N, e->K, e->dTTlist + 1, e->dTTlist);
-  ++e->launches;
-  prune_tt_amb_kernel<S, MaskT><<<e->sm_count * 2, 256, 0, e->stream>>>(Pl, Pr, (const MaskT *)l.src, (const MaskT *)r.src, out, osc,
-                                                                        e->K, e->dTTlist + 1, e->dTTlist);
+  auto kern = prune_tt_copy_kernel<S, MaskT>;
+  const int g = resident_grid(e, kern, 256, 0, (e->N + 63) / 64);
+  kern<<<g, 256, 0, e->stream>>>(Pl, Pr, e->dTT, e->dTTsc, (const MaskT *)l.src, (const MaskT *)r.src, out, osc,
+                                 e->N, e->K);
   *st = cudaSuccess;
   return true;
 }
@@ -851,8 +833,11 @@ static int lk_launch_prune(phylo_engine *e, const double *Pl, const double *Pr, 
     cudaError_t st = cudaSuccess;
     bool tt_done = false;
     if (l.tip && r.tip && e->opt_tt_table) {
+      // 20 states only: measured 99.7 -> 83.1 us per tip+tip update (config 4); for 61 states the
+      // table path was slower than the DMMA kernel's one-hot lookups (63.5 -> 74.5 us) and is not used.
+      // A chunk-per-thread copy kernel + a second kernel for the ambiguous patterns was slower for both
+      // (105 / 104 us) and was removed.
       if (e->S == 20) tt_done = launch_prune_tt_table<20, uint32_t>(e, Pl, Pr, l, r, out, osc, &st);
-      else if (e->S == 61) tt_done = launch_prune_tt_table<61, uint64_t>(e, Pl, Pr, l, r, out, osc, &st);
     }
     if (tt_done) {}
     else if (e->S == 20 && launch_prune_mma<20, uint32_t>(e, Pl, Pr, l, r, out, osc, &st)) {}

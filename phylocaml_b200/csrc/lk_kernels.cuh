@@ -777,14 +777,15 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
   }
 }
 
-// ------------------------------------------------- 20/61-state tip+tip update as a table copy ----
+// ---------------------------------------------------- 20-state tip+tip update as a table copy ----
 // Both children are tips. For observed states (one-hot masks, the usual case) the result is
 // out[k][i] = Pl[k][i][jl] * Pr[k][i][jr]: one of S*S finished vectors. tt_table_kernel builds all
 // of them (256 KB for 20 states x 4 classes, 1.8 MB for 61 states: L2-resident), already rescaled
 // where the rule asks for it, and prune_tt_copy_kernel turns the update into a table-row copy per
 // pattern -- a pure write stream instead of 12 scattered shared-memory lookups per DMMA row tile
-// (tip+tip was at 50 % of HBM for 20 states, 25 % for 61). A pattern with an ambiguous tip (more
-// than one state bit) is listed and computed by a second, small kernel. The products are the ones the
+// (tip+tip was at 50 % of HBM for 20 states; 61 % with this path. For 61 states it measured slower
+// than the DMMA kernel and is not dispatched). A pattern with an ambiguous tip (more
+// than one state bit) is computed in place by the warp that meets it. The products are the ones the
 // DMMA kernel's one-hot path forms (same two operands), so the CLVs are bit-identical to it.
 template <int S>
 __global__ void __launch_bounds__(128)
@@ -810,69 +811,58 @@ tt_table_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr, in
   if (threadIdx.x == 0) tabsc[blockIdx.x] = rescale ? 1 : 0;
 }
 
-// Copy kernel: thread = one chunk (VEC doubles) of one pattern's row; a CTA covers blockDim / CH
-// whole patterns per iteration (CH = K S / VEC chunks per pattern, blockDim a multiple of CH), so
-// consecutive threads write consecutive chunks of consecutive patterns: a linear store stream, the
-// table rows come from L2. Patterns with an ambiguous tip are appended to `list` and left to
-// prune_tt_amb_kernel.
-template <int S, typename MaskT, int VEC>
-__global__ void __launch_bounds__(256)
-prune_tt_copy_kernel(const double *__restrict__ tab, const int32_t *__restrict__ tabsc,
-                     const MaskT *__restrict__ lmask, const MaskT *__restrict__ rmask,
-                     double *__restrict__ out, int32_t *__restrict__ osc, int64_t N, int K,
-                     int *__restrict__ list, int *__restrict__ nlist) {
-  const int KS = K * S, CH = KS / VEC, ppb = blockDim.x / CH;
-  const int c = threadIdx.x % CH, pl = threadIdx.x / CH;
-  const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
-  if (pl >= ppb) return;
-#pragma unroll 4
-  for (int64_t p = (int64_t)blockIdx.x * ppb + pl; p < N; p += (int64_t)gridDim.x * ppb) {
-    const MaskT a = lmask[p] & keep, b = rmask[p] & keep;
-    if ((a & (a - 1)) == 0 && (b & (b - 1)) == 0) {
-      const int combo = (__ffsll((long long)a) - 1) * S + (__ffsll((long long)b) - 1);
-      const double *row = tab + (size_t)combo * KS;
-      double *o = out + (size_t)p * KS;
-      if (VEC == 4) st256(o + 4 * c, ld256_stream(row + 4 * c));
-      else o[c] = row[c];
-      if (c == 0) osc[p] = tabsc[combo];
-    } else if (c == 0) {
-      list[atomicAdd(nlist, 1)] = (int)p;
-    }
-  }
-}
-
-// The listed patterns (ambiguous tips): a warp per pattern sums the allowed columns (ascending j)
-// and applies the rescaling rule.
 template <int S, typename MaskT>
 __global__ void __launch_bounds__(256)
-prune_tt_amb_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr, const MaskT *__restrict__ lmask,
-                    const MaskT *__restrict__ rmask, double *__restrict__ out, int32_t *__restrict__ osc, int K,
-                    const int *__restrict__ list, const int *__restrict__ nlist) {
-  const int lane = threadIdx.x & 31, KS = K * S, n = *nlist;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+prune_tt_copy_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr, const double *__restrict__ tab,
+                     const int32_t *__restrict__ tabsc, const MaskT *__restrict__ lmask,
+                     const MaskT *__restrict__ rmask, double *__restrict__ out, int32_t *__restrict__ osc,
+                     int64_t N, int K) {
+  const int lane = threadIdx.x & 31, KS = K * S;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
-  for (int idx = warp; idx < n; idx += nwarps) {
-    const int64_t p = list[idx];
-    const MaskT a = lmask[p] & keep, b = rmask[p] & keep;
-    double *o = out + (size_t)p * KS;
-    int h = (int)0x80000000;
-    for (int e = lane; e < KS; e += 32) {
-      const double *pl = Pl + (size_t)e * S, *pr = Pr + (size_t)e * S;
-      double sl = 0.0, sr = 0.0;
-      for (int j = 0; j < S; ++j) {
-        if ((a >> j) & 1) sl += pl[j];
-        if ((b >> j) & 1) sr += pr[j];
-      }
-      const double v = sl * sr;
-      o[e] = v;
-      h = max(h, hi32(v));
-    }
+  const bool vec = (KS % 4) == 0;  // rows are whole 32-byte units (20 states): 256-bit copies
+  const int64_t ngroups = (N + 7) / 8;
+  for (int64_t g = warp; g < ngroups; g += nwarps) {
+    const int64_t pmine = g * 8 + (lane & 7);
+    MaskT ml = keep, mr = keep;
+    if (pmine < N) { ml = lmask[pmine] & keep; mr = rmask[pmine] & keep; }
+#pragma unroll 2
+    for (int r = 0; r < 8; ++r) {
+      const int64_t p = g * 8 + r;
+      if (p >= N) break;  // warp-uniform
+      const MaskT a = __shfl_sync(0xffffffffu, ml, r), b = __shfl_sync(0xffffffffu, mr, r);
+      double *o = out + (size_t)p * KS;
+      if ((a & (a - 1)) == 0 && (b & (b - 1)) == 0) {  // both observed: copy the finished vector
+        const int combo = (__ffsll((long long)a) - 1) * S + (__ffsll((long long)b) - 1);
+        const double *row = tab + (size_t)combo * KS;
+        if (vec) {
+          for (int q = lane; q < KS / 4; q += 32) st256(o + 4 * q, ld256_stream(row + 4 * q));
+        } else {
+          for (int e = lane; e < KS; e += 32) o[e] = row[e];
+        }
+        if (lane == 0) osc[p] = tabsc[combo];
+      } else {  // ambiguous tip(s): sum the allowed columns (ascending j), rescale by the same rule
+        int h = (int)0x80000000;
+        for (int e = lane; e < KS; e += 32) {
+          const double *pl = Pl + (size_t)e * S, *pr = Pr + (size_t)e * S;
+          double sl = 0.0, sr = 0.0;
+          for (int j = 0; j < S; ++j) {
+            if ((a >> j) & 1) sl += pl[j];
+            if ((b >> j) & 1) sr += pr[j];
+          }
+          const double v = sl * sr;
+          o[e] = v;
+          h = max(h, hi32(v));
+        }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, off));
-    const bool rescale = h < kScaleHiThresh;
-    if (rescale)
-      for (int e = lane; e < KS; e += 32) o[e] *= 0x1p+256;
-    if (lane == 0) osc[p] = rescale ? 1 : 0;
+        for (int off = 16; off >= 1; off >>= 1) h = max(h, __shfl_xor_sync(0xffffffffu, h, off));
+        const bool rescale = h < kScaleHiThresh;
+        if (rescale)
+          for (int e = lane; e < KS; e += 32) o[e] *= 0x1p+256;
+        if (lane == 0) osc[p] = rescale ? 1 : 0;
+      }
+    }
   }
 }
 
