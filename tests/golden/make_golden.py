@@ -58,6 +58,54 @@ def golden_compose(ref):
     return sorted(cases)
 
 
+def nonreversible_cases():
+    """Generators that are NOT time-reversible but have a real spectrum (what Const / m_file /
+    m_custom can hand to diagonalize_gtr, lib/mlModel.ml:473-520), and cyclic ones whose spectrum
+    is complex (the reference raises "Imaginary eigenvalues", lib/mlmodel.c:248-250)."""
+    rng = np.random.default_rng(7)
+
+    def gen(R):
+        R = np.array(R, dtype=float)
+        np.fill_diagonal(R, 0.0)
+        Q = R.copy()
+        np.fill_diagonal(Q, -R.sum(1))
+        return Q
+
+    cases = {"irrev4": gen(np.triu(rng.uniform(0.1, 2, (4, 4)), 1)),
+             "irrev20": gen(np.triu(rng.uniform(0.1, 2, (20, 20)), 1))}
+    for n in (4, 20, 61):
+        R, pi = mlmodel.synthetic_reversible(n, 3)
+        cases["pert%d" % n] = gen(np.array(R) * np.asarray(pi)[None, :] * (1 + 0.02 * rng.uniform(-1, 1, (n, n))))
+    complex_cases = {}
+    for n in (3, 4, 7):
+        R = np.zeros((n, n))
+        for i in range(n):
+            R[i, (i + 1) % n] = 1.0
+        complex_cases["cyc%d" % n] = gen(R)
+    return cases, complex_cases
+
+
+def golden_compose_nonreversible(ref):
+    cases, complex_cases = nonreversible_cases()
+    out = {}
+    ts = [0.01, 0.3, 2.0]
+    for name, Q in cases.items():
+        U, D, Ui = ref.diagonalize(Q, False)
+        out[name + "_Q"] = Q
+        out[name + "_t"] = np.array(ts)
+        out[name + "_P"] = np.stack([ref.compose(U, D, Ui, t) for t in ts])
+        assert max(np.abs(P - sl.expm(Q * t)).max() for P, t in zip(out[name + "_P"], ts)) < 1e-10
+    for name, Q in complex_cases.items():
+        try:
+            ref.diagonalize(Q, False)
+            raise AssertionError("the reference accepted a complex spectrum: " + name)
+        except RuntimeError as ex:
+            assert "Imaginary" in str(ex)
+        out[name + "_Q"] = Q
+    np.savez_compressed(os.path.join(HERE, "compose_nonrev_ref.npz"), **out)
+    return sorted(cases), sorted(complex_cases)
+
+
 def golden_bv(ref):
     out = {}
     rng = np.random.default_rng(20261017)
@@ -233,6 +281,7 @@ def golden_fitch():
 if __name__ == "__main__":
     ref = Ref()
     print("compose:", golden_compose(ref))
+    print("compose, non-reversible:", golden_compose_nonreversible(ref))
     golden_bv(ref)
     golden_lnl()
     golden_fitch()

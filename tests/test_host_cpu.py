@@ -125,6 +125,34 @@ def test_bench_ranks_hold_slices_of_one_global_alignment(monkeypatch):
 
 
 # ------------------------------------------------------------- eigen-decomposition ----
+@pytest.mark.parametrize("case", ["irrev4", "irrev20", "pert4", "pert20", "pert61"])
+def test_diagonalize_gtr_non_reversible_generators(built, oracle, case):
+    """Generators that are not time-reversible but have a real spectrum (Const / m_file / m_custom,
+    lib/mlModel.ml:473-520): the general solver (Hessenberg + shifted QR + back-substitution) must
+    reproduce the P(t) of the reference's dgeev path (golden vectors made by oracle/_ref)."""
+    from scipy.linalg import expm
+
+    g = np.load(os.path.join(GOLD, "compose_nonrev_ref.npz"))
+    Q = g[case + "_Q"]
+    U, D, Ui = engine.diagonalize(Q, False)
+    assert np.abs(U @ Ui - np.eye(Q.shape[0])).max() <= 1e-9
+    for t, P in zip(g[case + "_t"], g[case + "_P"]):
+        got = oracle.compose(U, D, Ui, t)
+        # the triangular generators have an ill-conditioned eigenbasis (cond ~ 7e3 for irrev20): the
+        # reference itself is 1.3e-11 away from expm there, ours 2.6e-12
+        assert np.abs(got - P).max() <= 1e-10, (case, t)
+        assert np.abs(got - expm(Q * t)).max() <= 1e-11, (case, t)
+
+
+@pytest.mark.parametrize("case", ["cyc3", "cyc4", "cyc7"])
+def test_diagonalize_gtr_rejects_complex_spectra_like_the_reference(built, case):
+    """lib/mlmodel.c:248-250 raises "Imaginary eigenvalues"; ours returns PHYLO_ERR_NUMERIC."""
+    g = np.load(os.path.join(GOLD, "compose_nonrev_ref.npz"))
+    with pytest.raises(engine.PhyloError) as ei:
+        engine.diagonalize(g[case + "_Q"], False)
+    assert ei.value.code == -5
+
+
 @pytest.mark.parametrize("case", ["dna_gtr", "dna_f81", "aa20", "codon61"])
 def test_diagonalize_gtr_reproduces_reference_P(built, oracle, case):
     """phylo_diagonalize_gtr (Jacobi on the symmetrised generator) vs the reference's LAPACK
