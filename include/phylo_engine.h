@@ -117,6 +117,12 @@ int phylo_diagonalize_gtr(double *Q_inout_U, double *D, double *Ui, int n);
  * P = exp(Q t) from the eigensystem, computed by the pt_build kernel. Same special cases:
  * t == -1.0 -> Q; t < 1e-10 -> I; compose_sym rounds t to float first (mlmodel.c:280).
  * D is the full n*n matrix. P_out: n*n host buffer. */
+/* Discrete-Gamma rate classes (lib/mlModel.ml:93-99, :676-694; the reference computes them with
+ * Pareto/GSL, which is neither vendored nor pinned). mode 0 = what the reference's code does:
+ * rates[i] = quantile at p = i/k of Gamma(shape = alpha, scale = alpha), so rates[0] = 0;
+ * mode 1 = what lib/mlModel.mli:12 documents: Yang's (1994) class means of Gamma(alpha, rate alpha),
+ * average 1. probs (may be NULL) = 1/k each. Host-side, self-contained incomplete-gamma code. */
+int phylo_gamma_rates(double alpha, int k, int mode, double *rates, double *probs);
 int phylo_compose_sym(phylo_engine *e, const double *U, const double *D, double t, int n,
                       double *P_out);
 int phylo_compose_gtr(phylo_engine *e, const double *U, const double *D, const double *Ui,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "phylo_host_free": (C.c_int, [_vp]),
     "phylo_diagonalize_sym": (C.c_int, [_dp, _dp, C.c_int]),
     "phylo_diagonalize_gtr": (C.c_int, [_dp, _dp, _dp, C.c_int]),
+    "phylo_gamma_rates": (C.c_int, [C.c_double, C.c_int, C.c_int, _dp, _dp]),
     "phylo_compose_sym": (C.c_int, [_vp, _dp, _dp, C.c_double, C.c_int, _dp]),
     "phylo_compose_gtr": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
     "phylo_lk_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
@@ -167,6 +168,15 @@ def diagonalize(Q, sym):
     if rc != PHYLO_OK:
         raise PhyloError(rc, "diagonalize failed (complex eigenvalues / not convergent / NaN)")
     return U, D, Ui
+
+
+def gamma_rates(alpha, k, mode="yang_mean"):
+    """(rates, probs) of the discrete Gamma: mode "ref_literal" (lib/mlModel.ml:93-99) or "yang_mean"."""
+    rates, probs = np.empty(k), np.empty(k)
+    rc = load().phylo_gamma_rates(float(alpha), int(k), 0 if mode == "ref_literal" else 1, _p(rates, _dp), _p(probs, _dp))
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "phylo_gamma_rates(alpha=%r, k=%r) failed" % (alpha, k))
+    return rates, probs
 
 
 def pinned_empty(shape, dtype):

@@ -566,3 +566,19 @@ CAMLprim value phylo_CAML_set_symbol_table(value ve, value vtab)
   check(e, phylo_engine_set_symbol_table(e, t));
   CAMLreturn(Val_unit);
 }
+
+/* external gamma_rates : float -> int -> int -> vector   (alpha, classes, mode) -> rates
+ * replaces MlModel.gamma_rates (lib/mlModel.ml:93-99; Pareto/GSL there). mode 0 = the reference's
+ * literal quantiles, 1 = Yang (1994) class means. */
+CAMLprim value likelihood_CAML_gamma_rates(value valpha, value vk, value vmode)
+{
+  CAMLparam3(valpha, vk, vmode);
+  CAMLlocal1(res);
+  intptr_t dims[1];
+  dims[0] = Int_val(vk);
+  if (dims[0] < 1) caml_failwith("gamma_rates: need at least one class");
+  res = caml_ba_alloc(CAML_BA_FLOAT64 | CAML_BA_C_LAYOUT, 1, NULL, dims);
+  if (phylo_gamma_rates(Double_val(valpha), Int_val(vk), Int_val(vmode), (double *)Data_bigarray_val(res), NULL) != PHYLO_OK)
+    caml_failwith("gamma_rates: alpha must be positive and finite");
+  CAMLreturn(res);
+}

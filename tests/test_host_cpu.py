@@ -144,6 +144,24 @@ def test_diagonalize_gtr_non_reversible_generators(built, oracle, case):
         assert np.abs(got - expm(Q * t)).max() <= 1e-11, (case, t)
 
 
+@pytest.mark.parametrize("alpha", [0.02, 0.3, 0.5, 1.0, 2.5, 10.0, 300.0])
+def test_gamma_rates_against_scipy(built, alpha):
+    """phylo_gamma_rates (self-contained incomplete gamma + inverse) against SciPy, for the two
+    definitions: the reference's literal quantiles (lib/mlModel.ml:93-99, r_0 = 0; Pareto/GSL
+    there -- parity unpinned by the reference, pinned here to SciPy) and Yang's class means."""
+    for k in (1, 2, 4, 8, 16):
+        r0, p0 = engine.gamma_rates(alpha, k, "ref_literal")
+        w0 = mlmodel.gamma_rates_ref_literal(alpha, k)
+        assert r0[0] == 0.0 and np.allclose(p0, 1.0 / k)
+        assert np.all(np.abs(r0 - w0) <= 1e-11 * np.abs(w0))
+        r1, _ = engine.gamma_rates(alpha, k, "yang_mean")
+        w1 = mlmodel.gamma_rates_yang_mean(alpha, k)
+        assert np.all(np.abs(r1 - w1) <= 1e-11 * np.abs(w1))
+        assert abs(r1.mean() - 1.0) <= 1e-12 and np.all(np.diff(r1) >= 0)
+    lib = engine.load()
+    assert lib.phylo_gamma_rates(-1.0, 4, 0, None, None) == -2
+
+
 def test_non_reversible_model_through_the_pruning_oracle(built, oracle):
     """End to end on the CPU side: a non-reversible 4-state generator, decomposed by the product's
     general solver, scored by the pruning oracle, against brute-force summation over all interior
