@@ -111,3 +111,37 @@ let create_spec (model : m) (tips : masks) (weights : vector option) =
   set_tips_ e tips weights capacity;
   let s = { engine = e; n_taxa; capacity; next = n_taxa } in
   the_spec := Some s; s
+
+(* ---- alignments as text, and all GPUs of the box ------------------------------------------
+   [symbol_table] turns an Alphabet.t into the 256-entry table of state sets the engine applies on
+   the device (single-character names only; gap and missing fold into "all states" for likelihood,
+   lib/mlModel.mli:75-76). [create_spec_text] is create_spec for an alignment that is still the
+   characters of the input file. *)
+external set_symbol_table_ :
+  engine -> (int64, Bigarray.int64_elt, Bigarray.c_layout) Bigarray.Array1.t option -> unit
+  = "phylo_CAML_set_symbol_table"
+
+let symbol_table (alph : Alphabet.t) (n_states : int) =
+  let all = Int64.pred (Int64.shift_left 1L n_states) in
+  let t = Bigarray.Array1.create Bigarray.int64 Bigarray.c_layout 256 in
+  Bigarray.Array1.fill t 0L;
+  StringMap.iter
+    (fun name code ->
+      if String.length name = 1 then begin
+        let m = Int64.logand (Int64.of_int code) all in
+        let m = if m = 0L then all else m in          (* gap-only / missing: every state *)
+        t.{Char.code (Char.uppercase name.[0])} <- m;
+        t.{Char.code (Char.lowercase name.[0])} <- m
+      end)
+    alph.Alphabet.name_code;
+  t
+
+let create_spec_text (model : m) (alph : Alphabet.t) (text : masks) (weights : vector option) =
+  let e = engine_create 0 in
+  let n_taxa = Bigarray.Array2.dim1 text in
+  let capacity = 2 * n_taxa in
+  load_model e model;
+  set_symbol_table_ e (Some (symbol_table alph (Bigarray.Array2.dim1 model.MlModel.u)));
+  set_tips_ e text weights capacity;
+  let s = { engine = e; n_taxa; capacity; next = n_taxa } in
+  the_spec := Some s; s
