@@ -90,6 +90,10 @@ int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256);
  * 2 = register walk (compiled depth-first plan, tips prefetched several medians ahead, up to
  * 8 planes); 0 = L2 walk (re-reads its own earlier writes through L2, any plane count). */
 #define PHYLO_OPT_FITCH_WALK 3
+/* Two environment variables exist for measurements only (tools/tune_treew.sh, tools/mma_ab.sh):
+ * PHYLO_TREEW_TUNE="slev,R,il" overrides the geometry the warp-autonomous tree kernel picks, and
+ * PHYLO_TT_TABLE=0 sends 20-state tip+tip updates through the DMMA kernel instead of the table
+ * copy. Results are bit-identical under every setting. */
 int phylo_engine_set_option(phylo_engine *e, int option, int64_t value);
 int phylo_engine_get_option(phylo_engine *e, int option, int64_t *value);
 /* CUDA-event profiler: while enabled, every kernel launch is bracketed by an event pair on
