@@ -93,7 +93,8 @@ int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256);
 /* Two environment variables exist for measurements only (tools/tune_treew.sh, tools/mma_ab.sh):
  * PHYLO_TREEW_TUNE="slev,R,il" overrides the geometry the warp-autonomous tree kernel picks, and
  * PHYLO_TT_TABLE=0 sends 20-state tip+tip updates through the DMMA kernel instead of the table
- * copy. Results are bit-identical under every setting. */
+ * copy. PHYLO_TREEW_TUNE never changes a bit of the result; the two tip+tip paths give identical
+ * CLVs for observed tips and agree to rounding (1e-16 relative) where a tip is ambiguous. */
 int phylo_engine_set_option(phylo_engine *e, int option, int64_t value);
 int phylo_engine_get_option(phylo_engine *e, int option, int64_t *value);
 /* CUDA-event profiler: while enabled, every kernel launch is bracketed by an event pair on

@@ -786,7 +786,9 @@ prune_mma_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
 // (tip+tip was at 50 % of HBM for 20 states; 61 % with this path. For 61 states it measured slower
 // than the DMMA kernel and is not dispatched). A pattern with an ambiguous tip (more
 // than one state bit) is computed in place by the warp that meets it. The products are the ones the
-// DMMA kernel's one-hot path forms (same two operands), so the CLVs are bit-identical to it.
+// DMMA kernel's one-hot path forms (same two operands), so for observed tips the CLVs are
+// bit-identical to it; an ambiguous tip is summed in ascending state order here, in fragment order
+// there (agreement to rounding).
 template <int S>
 __global__ void __launch_bounds__(128)
 tt_table_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr, int K, double *__restrict__ tab,
