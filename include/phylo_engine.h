@@ -245,6 +245,13 @@ int phylo_fitch_set_states(phylo_engine *e, int node, const void *codes);
  * 0/1 matrix both variants are the Fitch rule (the reference tests exactly that,
  * test/costMatrixTest.ml:110-125). parent < 0 in phylo_tcm_median_2: cost only. */
 int phylo_tcm_set_matrix(phylo_engine *e, int n_states, const int32_t *M, int metric);
+/* MlModel.integerized_model (lib/mlModel.ml:639-660), the bridge from a likelihood model to such
+ * a cost matrix: cost[i][j] = -trunc(10^sigma * ln(priors[i] * P[i][j])) for P = P(t) from
+ * phylo_compose_* (priors == NULL for JC69 / K2P, which the reference leaves out there). Host
+ * side. PHYLO_ERR_NUMERIC when an entry of P is not positive. Mind phylo_tcm_set_matrix's range
+ * (costs <= 30000): sigma = 3 is the largest that fits for usual branch lengths (the reference's
+ * default sigma = 4 gives costs up to ~10^5). */
+int phylo_integerize_matrix(const double *P, const double *priors, int n, int sigma, int32_t *cost_out);
 int phylo_tcm_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *cost_out);
 int phylo_tcm_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                          uint64_t *length_out);

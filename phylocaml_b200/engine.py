@@ -59,6 +59,7 @@ SIGNATURES = {
                                            C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "phylo_tcm_set_matrix": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),
+    "phylo_integerize_matrix": (C.c_int, [_dp, _dp, C.c_int, C.c_int, _vp]),
     "phylo_tcm_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_tcm_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_compress_patterns": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, _vp, _dp, _vp, C.POINTER(_i64)]),
@@ -177,6 +178,18 @@ def gamma_rates(alpha, k, mode="yang_mean"):
     if rc != PHYLO_OK:
         raise PhyloError(rc, "phylo_gamma_rates(alpha=%r, k=%r) failed" % (alpha, k))
     return rates, probs
+
+
+def integerize_matrix(P, priors=None, sigma=4):
+    """MlModel.integerized_model's conversion (lib/mlModel.ml:639-660) of P(t) to integer costs."""
+    P = _f64(P)
+    n = P.shape[0]
+    pri = None if priors is None else _f64(priors)
+    out = np.empty((n, n), dtype=np.int32)
+    rc = load().phylo_integerize_matrix(_p(P, _dp), _p(pri, _dp), n, int(sigma), _p(out))
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "phylo_integerize_matrix failed (non-positive entry of P, or bad arguments)")
+    return out
 
 
 def pinned_empty(shape, dtype):

@@ -582,3 +582,21 @@ CAMLprim value likelihood_CAML_gamma_rates(value valpha, value vk, value vmode)
     caml_failwith("gamma_rates: alpha must be positive and finite");
   CAMLreturn(res);
 }
+
+/* external integerize : matrix -> vector option -> int -> (int32, int32_elt, c_layout) Array2.t
+ * MlModel.integerized_model's conversion (lib/mlModel.ml:639-660) of P(t) into integer costs. */
+CAMLprim value likelihood_CAML_integerize(value P, value prio, value vsigma)
+{
+  CAMLparam3(P, prio, vsigma);
+  CAMLlocal1(res);
+  intptr_t dims[2];
+  int n = (int)Bigarray_val(P)->dim[0];
+  const double *pri = (prio == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(prio, 0));
+  dims[0] = n;
+  dims[1] = n;
+  res = caml_ba_alloc(CAML_BA_INT32 | CAML_BA_C_LAYOUT, 2, NULL, dims);
+  if (phylo_integerize_matrix((const double *)Data_bigarray_val(P), pri, n, Int_val(vsigma),
+                              (int32_t *)Data_bigarray_val(res)) != PHYLO_OK)
+    caml_failwith("integerize: an entry of P is not positive");
+  CAMLreturn(res);
+}

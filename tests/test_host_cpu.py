@@ -162,6 +162,31 @@ def test_gamma_rates_against_scipy(built, alpha):
     assert lib.phylo_gamma_rates(-1.0, 4, 0, None, None) == -2
 
 
+def test_integerize_matrix_is_the_reference_formula(built, oracle):
+    """lib/mlModel.ml:639-660 restated with Python ints (int_of_float truncates toward zero), on
+    P(t) from the oracle's compose (pinned to the reference's compose_gtr)."""
+    import math
+
+    g = np.load(os.path.join(GOLD, "compose_ref.npz"))
+    for case, with_priors in (("dna_gtr", True), ("dna_jc69", False), ("aa20", True)):
+        Q = g[case + "_Q"]
+        n = Q.shape[0]
+        U, D = g[case + "_U"], g[case + "_D"]
+        Ui = g[case + "_Ui"] if case + "_Ui" in g else None
+        pri = np.full(n, 1.0 / n) if not with_priors else np.abs(np.linalg.svd(Q.T)[2][-1]) / np.abs(np.linalg.svd(Q.T)[2][-1]).sum()
+        for t in (0.05, 0.5):
+            P = oracle.compose(U, D, Ui, t)
+            for sigma in (2, 3, 4):
+                want = [[-int(10.0 ** sigma * math.log((pri[i] if with_priors else 1.0) * P[i, j])) for j in range(n)]
+                        for i in range(n)]
+                got = engine.integerize_matrix(P, pri if with_priors else None, sigma)
+                assert got.tolist() == want, (case, t, sigma)
+    bad = np.eye(4)
+    with pytest.raises(engine.PhyloError) as ei:
+        engine.integerize_matrix(bad, None, 3)  # ln 0
+    assert ei.value.code == -5
+
+
 def test_non_reversible_model_through_the_pruning_oracle(built, oracle):
     """End to end on the CPU side: a non-reversible 4-state generator, decomposed by the product's
     general solver, scored by the pruning oracle, against brute-force summation over all interior
