@@ -160,6 +160,17 @@ int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int 
  * phylo_lk_edge_lnl / phylo_lk_get_clv / incremental re-scoring. */
 int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                         double root_t, double *lnl_out);
+/* Host-only (no GPU needed), for tests and tooling: the compiled form of a schedule as the
+ * tree-fused likelihood kernels and the Fitch register walk execute it. One row of 6 int32 per
+ * step (n_ops medians in depth-first order + the root-edge join, whose out_slot is -1):
+ * left kind, left slot, right kind, right slot, push_first, out_slot. Kinds: 0 = tip, 1 = the value
+ * the previous step produced (in registers), 2 = popped from the on-chip stack, 3 = a CLV / set
+ * already resident in its node slot from an earlier call. push_first = 1: the live value is
+ * pushed before this step. *depth_out = stack levels needed (the subtree with the larger need is
+ * evaluated first). PHYLO_ERR_UNSUPPORTED: not a plain tree -- the per-node path runs such
+ * schedules. */
+int phylo_plan_compile(const phylo_op *ops, int n_ops, int T, int capacity, int root_a, int root_b,
+                       int32_t *steps_out, int *depth_out);
 /* phylo_lk_set_tips + phylo_lk_score_tree in one call for an alignment that is still in host
  * memory: the upload is cut into pattern slabs on a second stream and each slab is scored
  * (tree-fused kernel) while the next one is still crossing PCIe. Same result, bit for bit. */

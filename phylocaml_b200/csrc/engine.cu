@@ -1086,6 +1086,27 @@ static bool build_fused_plan(int cap, int T, const phylo_op *ops, int n_ops, int
   return (int)pl.steps.size() == n_ops + 1;
 }
 
+// Host-only view of the plan compiler for tests (no CUDA call): the steps the tree-fused
+// likelihood kernels and the Fitch register walk would execute for this schedule.
+extern "C" int phylo_plan_compile(const phylo_op *ops, int n_ops, int T, int capacity, int root_a, int root_b,
+                                  int32_t *steps_out, int *depth_out) {
+  if (n_ops < 0 || (n_ops > 0 && !ops) || T < 1 || capacity < T || !steps_out) return PHYLO_ERR_ARG;
+  if (root_a < 0 || root_a >= capacity || root_b < 0 || root_b >= capacity) return PHYLO_ERR_ARG;
+  for (int o = 0; o < n_ops; ++o)
+    if (ops[o].parent < T || ops[o].parent >= capacity || ops[o].left < 0 || ops[o].left >= capacity ||
+        ops[o].right < 0 || ops[o].right >= capacity)
+      return PHYLO_ERR_ARG;
+  FusedPlan pl;
+  if (!build_fused_plan(capacity, T, ops, n_ops, root_a, root_b, 0.0, pl)) return PHYLO_ERR_UNSUPPORTED;
+  for (size_t i = 0; i < pl.steps.size(); ++i) {
+    const PlanStep &st = pl.steps[i];
+    int32_t *row = steps_out + 6 * i;
+    row[0] = st.lkind; row[1] = st.lidx; row[2] = st.rkind; row[3] = st.ridx; row[4] = st.push_first; row[5] = st.out_slot;
+  }
+  if (depth_out) *depth_out = pl.depth;
+  return PHYLO_OK;
+}
+
 static size_t tree_smem_bytes(int K, int T, int depth, int n_steps) {
   const size_t tile = (size_t)kTreeR * kTreeThreads / K;
   return 2 * tile * 8 + 4 * 8 + (size_t)depth * kTreeR * kTreeThreads * (sizeof(d4) + sizeof(int)) +

@@ -55,6 +55,7 @@ SIGNATURES = {
     "phylo_lk_set_tips_pitched": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_uint64, _dp, C.c_int]),
     "phylo_lk_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]),
     "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
+    "phylo_plan_compile": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
                                            C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
@@ -190,6 +191,20 @@ def integerize_matrix(P, priors=None, sigma=4):
     if rc != PHYLO_OK:
         raise PhyloError(rc, "phylo_integerize_matrix failed (non-positive entry of P, or bad arguments)")
     return out
+
+
+def plan_compile(ops, T, capacity, root_a, root_b):
+    """(steps [n_ops + 1, 6] int32, stack depth) of the compiled schedule, or None when the schedule is
+    not a plain tree (host-only; see phylo_plan_compile)."""
+    ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+    steps = np.zeros((len(ops) + 1, 6), dtype=np.int32)
+    depth = C.c_int()
+    rc = load().phylo_plan_compile(_p(ops), len(ops), T, capacity, root_a, root_b, _p(steps), C.byref(depth))
+    if rc == -6:
+        return None
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "phylo_plan_compile: bad arguments")
+    return steps, depth.value
 
 
 def pinned_empty(shape, dtype):

@@ -162,6 +162,113 @@ def test_gamma_rates_against_scipy(built, alpha):
     assert lib.phylo_gamma_rates(-1.0, 4, 0, None, None) == -2
 
 
+def _interpret_plan(steps, T):
+    """Run a compiled plan on symbolic values: a value is the nested tuple of what it was computed
+    from. Returns (root expression, {slot: expression} of every median, deepest stack)."""
+    cur, stack, out, deepest = None, [], {}, 0
+
+    def operand(kind, idx):
+        nonlocal cur
+        if kind == 0:
+            assert idx < T
+            return ("tip", int(idx))
+        if kind == 3:
+            assert idx >= T
+            return ("stored", int(idx))
+        if kind == 1:
+            assert cur is not None
+            v, cur = cur, None
+            return v
+        assert kind == 2 and stack
+        return stack.pop()
+
+    for lk, li, rk, ri, push, slot in steps.tolist():
+        if push:
+            assert cur is not None
+            stack.append(cur)
+            cur = None
+            deepest = max(deepest, len(stack))
+        # a popped operand is taken before the in-register one is consumed, whichever side it is on
+        if lk == 2:
+            left = operand(lk, li)
+            right = operand(rk, ri)
+        else:
+            right = operand(rk, ri) if rk == 2 else None
+            left = operand(lk, li)
+            right = operand(rk, ri) if right is None else right
+        assert cur is None, "a live value would be overwritten"
+        cur = ("median", left, right)
+        if slot >= 0:
+            out[int(slot)] = cur
+    assert not stack
+    return cur, out, deepest
+
+
+def _meaning(ops, T, ra, rb):
+    val = {}
+    produced = {int(o["parent"]) for o in ops}
+
+    def get(s):
+        s = int(s)
+        if s < T:
+            return ("tip", s)
+        return val[s] if s in val else ("stored", s)
+
+    for o in ops:
+        val[int(o["parent"])] = ("median", get(o["left"]), get(o["right"]))
+    assert produced == set(val)
+    return ("median", get(ra), get(rb)), val
+
+
+@pytest.mark.parametrize("kind,T,seed", [("random", 5, 1), ("random", 64, 2), ("random", 257, 3), ("caterpillar", 300, 0),
+                                         ("random", 2, 4), ("random", 3, 5)])
+def test_plan_compiler_preserves_the_schedule(built, kind, T, seed):
+    """phylo_plan_compile (the program the tree-fused kernels and the Fitch register walk execute):
+    interpreting it on symbolic values reproduces exactly the expression the post-order schedule
+    denotes, for every root edge; the stack never exceeds the reported depth, which is
+    logarithmic for random trees and 1 for a caterpillar."""
+    tr = tree.random_tree(T, seed) if kind == "random" else tree.caterpillar_tree(T)
+    edges = tr.edges()
+    for e in edges[:: max(1, len(edges) // 7)]:
+        ops, ra, rb, rt, n_nodes = tree.schedule(tr, root_edge=e)
+        got = engine.plan_compile(ops, T, n_nodes, ra, rb)
+        assert got is not None
+        steps, depth = got
+        root, out, deepest = _interpret_plan(steps, T)
+        want_root, want = _meaning(ops, T, ra, rb)
+        assert root == want_root
+        assert out == want
+        assert deepest <= depth <= max(1, int(np.ceil(np.log2(max(T, 2)))) + 1)
+        if kind == "caterpillar":
+            assert depth == 1
+
+
+def test_plan_compiler_partial_schedules_and_rejections(built):
+    """Incremental re-scoring: a path-to-root schedule whose other operands are resident CLVs
+    (kind 3). Non-trees (a result used twice, a slot written twice) are refused -> per-node path."""
+    T = 24
+    tr = tree.random_tree(T, 12)
+    ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+    parent_of = {int(o["left"]): j for j, o in enumerate(ops)}
+    parent_of.update({int(o["right"]): j for j, o in enumerate(ops)})
+    path, j = [4], 4
+    while int(ops[j]["parent"]) in parent_of:
+        j = parent_of[int(ops[j]["parent"])]
+        path.append(j)
+    sub = ops[sorted(path)]
+    steps, depth = engine.plan_compile(sub, T, n_nodes, ra, rb)
+    root, out, deepest = _interpret_plan(steps, T)
+    want_root, want = _meaning(sub, T, ra, rb)
+    assert root == want_root and out == want and depth == 1
+    assert (steps[:, [0, 2]] == 3).any()
+    twice = ops.copy()
+    twice[-1]["left"] = twice[-2]["left"]  # some result feeds two medians
+    assert engine.plan_compile(twice, T, n_nodes, ra, rb) is None
+    dup = ops.copy()
+    dup[1]["parent"] = dup[0]["parent"]
+    assert engine.plan_compile(dup, T, n_nodes, ra, rb) is None
+
+
 def test_integerize_matrix_is_the_reference_formula(built, oracle):
     """lib/mlModel.ml:639-660 restated with Python ints (int_of_float truncates toward zero), on
     P(t) from the oracle's compose (pinned to the reference's compose_gtr)."""
