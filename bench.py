@@ -111,6 +111,45 @@ def device_footprint(workload, T, S, K, tip_bytes, mode, n_local):
     return tips if mode == "fused-lnl" else tips + (T - 2) * (S * K * 8 + 4) * n_local
 
 
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (sysfs local_cpulist format)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_local_cpus(torch, local, sysfs="/sys/bus/pci/devices", min_cpus=8):
+    """Multi-rank runs only: keep this rank's main thread (which allocates and first-touches the
+    pinned tip buffer of the end-to-end leg) on the CPUs the kernel lists as local to its GPU, so
+    that 8 ranks do not all upload across the socket interconnect. Best effort: returns a short
+    description for the JSON line, or None when anything needed is missing."""
+    try:
+        prop = torch.cuda.get_device_properties(local)
+        dom, bus, dev = getattr(prop, "pci_domain_id", 0), getattr(prop, "pci_bus_id", None), getattr(prop, "pci_device_id", None)
+        if bus is None or dev is None:
+            return None
+        path = os.path.join(sysfs, "%04x:%02x:%02x.0" % (dom, bus, dev))
+        with open(os.path.join(path, "local_cpulist")) as f:
+            cpus = set(parse_cpulist(f.read()))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if len(allowed) < min_cpus or allowed == set(os.sched_getaffinity(0)):
+            return None  # nothing to gain, or too few CPUs for this rank's helper threads
+        os.sched_setaffinity(0, allowed)
+        node = "?"
+        try:
+            with open(os.path.join(path, "numa_node")) as f:
+                node = f.read().strip()
+        except OSError:
+            pass
+        return "main thread bound to the %d CPUs local to the GPU (NUMA node %s)" % (len(allowed), node)
+    except Exception:  # noqa: BLE001 -- never let placement tuning break a measurement
+        return None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -392,6 +431,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_local_cpus(torch, local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
 
@@ -705,7 +745,8 @@ def main():
                        if args.workload != "fitch" else "random DNA singletons + 2% two-state ambiguity",
                        "l2": l2_note,
                        "sharding": "contiguous 1024-aligned pattern slabs, one process per GPU",
-                       "collective": "allreduce of one scalar per step" if world > 1 else "none"},
+                       "collective": "allreduce of one scalar per step" if world > 1 else "none",
+                       "host_placement": numa_note},
             "mode": args.mode if args.workload != "fitch" else None, "modes": modes,
             "roofline": (roof_tensor if roof_tensor and S > 32 else roof),
             "roofline_hbm": roof if roof_tensor and S > 32 else None,

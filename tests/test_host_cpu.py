@@ -99,6 +99,54 @@ def test_alphabet_tables_follow_the_reference():
     assert np.array_equal(alphabet.translate(t, np.frombuffer(b"ACgt-", dtype=np.uint8)), [1, 2, 4, 8, 16])
 
 
+def test_bench_gpu_local_cpu_binding_is_best_effort(tmp_path):
+    """bench.bind_to_gpu_local_cpus: parses sysfs' cpulist, binds only to a proper subset of the
+    allowed CPUs, and returns None (without raising) whenever something is missing."""
+    import bench
+
+    assert bench.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert bench.parse_cpulist("") == []
+
+    class Prop:
+        pci_domain_id, pci_bus_id, pci_device_id = 0, 0x1b, 0
+
+    class Cuda:
+        @staticmethod
+        def get_device_properties(i):
+            return Prop()
+
+    class Torch:
+        cuda = Cuda()
+
+    before = os.sched_getaffinity(0)
+    assert bench.bind_to_gpu_local_cpus(Torch(), 0, sysfs=str(tmp_path)) is None  # no such device directory
+    d = tmp_path / "0000:1b:00.0"
+    d.mkdir()
+    (d / "local_cpulist").write_text(",".join(str(c) for c in sorted(before)))
+    assert bench.bind_to_gpu_local_cpus(Torch(), 0, sysfs=str(tmp_path)) is None  # not a proper subset: nothing to do
+    (d / "local_cpulist").write_text("100000-100003")
+    assert bench.bind_to_gpu_local_cpus(Torch(), 0, sysfs=str(tmp_path)) is None  # no allowed CPU among them
+    assert os.sched_getaffinity(0) == before
+    if len(before) >= 2:
+        one = sorted(before)[0]
+        (d / "local_cpulist").write_text(str(one))
+        (d / "numa_node").write_text("1\n")
+        try:
+            assert bench.bind_to_gpu_local_cpus(Torch(), 0, sysfs=str(tmp_path)) is None  # fewer than min_cpus
+            note = bench.bind_to_gpu_local_cpus(Torch(), 0, sysfs=str(tmp_path), min_cpus=1)
+            assert note is not None and "NUMA node 1" in note and os.sched_getaffinity(0) == {one}
+        finally:
+            os.sched_setaffinity(0, before)
+
+    class Broken:
+        class cuda:
+            @staticmethod
+            def get_device_properties(i):
+                raise RuntimeError("no CUDA")
+
+    assert bench.bind_to_gpu_local_cpus(Broken(), 0) is None
+
+
 def test_bench_ranks_hold_slices_of_one_global_alignment(monkeypatch):
     """bench.py: for every rank count the shards are contiguous, 1024-aligned, cover [0, N) and
     concatenate to the alignment a single rank scores; the L2 rule flags the small configurations."""
