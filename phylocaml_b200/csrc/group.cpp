@@ -36,7 +36,12 @@ struct Worker {
         std::function<int()> j = std::move(job);
         has_job = false;
         lk.unlock();
-        const int r = j();
+        int r;
+        try {
+          r = j();
+        } catch (...) {  // e.g. std::bad_alloc in a host-side vector: report, never unwind out of the thread
+          r = PHYLO_ERR_STATE;
+        }
         lk.lock();
         rc = r;
         done = true;
