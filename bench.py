@@ -1,18 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 tree-scoring engine (see DESIGN.md "Measurement").
+"""bench.py -- benchmark of the B200 tree-scoring engine (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dna|fitch|aa|codon]
+    python bench.py [--gpus N] [--steps K] [--warmup W]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # CPU arm: oracle/_ref + oracle port, all cores
 
-A "step" is one full evaluation of the hot path on one batch of synthetic input:
-  dna   (default; BASELINE config 3) DNA GTR+G4 full-tree pruning + root lnL, 256 taxa x 4M
-        site patterns, sharded contiguously over the ranks (total fixed => "strong").
-  fitch (BASELINE config 2) Fitch down-pass length, 64 taxa x 1M characters (and x64M).
-  aa / codon (BASELINE configs 4 / 5) 20-state +G4 and 61-state pruning.
-One JSON line on stdout (rank 0). PyTorch is used for events, NCCL and nothing else.
+A "step" is one full evaluation of the hot path on one batch of synthetic input. The ONE JSON line
+rank 0 prints carries the headline workload at the top level and every other BASELINE
+configuration under "workloads" (each with value / ms_per_step / roofline / cpu_baseline / e2e /
+check), all measured in the same process, one after the other:
+  dna     (headline; BASELINE config 3) DNA GTR+G4 full-tree pruning + root lnL, 256 taxa x 4M
+          site patterns, sharded contiguously over the ranks (total fixed => "strong").
+  fitch   (BASELINE config 2) Fitch down-pass length, 64 taxa x 1M bit-packed DNA characters.
+  fitch64 the same tree over 64 Mi characters (the bandwidth regime).
+  aa / codon (BASELINE configs 4 / 5) 20-state +G4 and 61-state pruning (fp64 tensor cores); codon
+          also runs config 5's branch-length re-evaluation loop.
+  cfg1    (BASELINE config 1) DNA GTR+G4, 16 taxa x 10k sites: the latency regime.
+`--workload X` makes X the headline; `--workloads a,b|all|none` picks the secondary set (default: all
+when the headline is dna, none otherwise). PyTorch is used for events, NCCL and nothing else.
 
-L2 rule: a working set below 4 x the 126 MB L2 (config 1, config 2, lnL-only mode on small shards)
+L2 rule: a working set below 4 x the 126 MB L2 (configs 1 and 2, lnL-only mode on small shards)
 gets 512 MB written between timed iterations, outside each iteration's own event pair; larger ones
 are timed with one event pair around all K steps. `config.l2` says which applied.
 """
@@ -32,20 +39,26 @@ sys.path.insert(0, ROOT)
 GTR_CO = [1.0, 2.5, 0.8, 1.2, 3.0]
 GTR_PI = [0.30, 0.20, 0.25, 0.25]
 BASE_PATTERNS = 65536  # evolved once, tiled to the workload size
+FITCH_BASE = 1 << 20   # random characters generated once, tiled to the workload size
 
 WORKLOADS = {
-    # name: (T, N_total, S, K, cpu_sample_patterns)
-    "dna": dict(T=256, N=4_000_000, S=4, K=4, cpu_sample=131072,
+    # kind: "lk" (pruning) | "fitch" | "compress"; cpu_sample = patterns / characters of the CPU leg
+    "dna": dict(kind="lk", T=256, N=4_000_000, S=4, K=4, cpu_sample=409_600, cpu_sample_1core=32_768,
                 name="DNA GTR+G4 full-tree pruning, 256 taxa x 4M site patterns"),
-    "aa": dict(T=128, N=500_000, S=20, K=4, cpu_sample=8192,
+    "aa": dict(kind="lk", T=128, N=500_000, S=20, K=4, cpu_sample=16_384, cpu_sample_1core=2_048,
                name="AA 20-state +G4 pruning, 128 taxa x 500k patterns"),
-    "codon": dict(T=64, N=200_000, S=61, K=1, cpu_sample=4096,
+    "codon": dict(kind="lk", T=64, N=200_000, S=61, K=1, cpu_sample=8_192, cpu_sample_1core=1_024,
                   name="Codon 61-state pruning, 64 taxa x 200k patterns"),
-    "fitch": dict(T=64, N=1_000_000, S=4, K=1, cpu_sample=1_000_000,
+    "cfg1": dict(kind="lk", T=16, N=10_000, S=4, K=4, cpu_sample=10_000, cpu_sample_1core=10_000,
+                 name="DNA GTR+G4 log-likelihood, 16 taxa x 10k sites"),
+    "fitch": dict(kind="fitch", T=64, N=1_000_000, S=4, K=1, cpu_sample=1_000_000, cpu_sample_1core=1_000_000,
                   name="Fitch/non-additive parsimony length, 64 taxa x 1M bit-packed DNA characters"),
-    "compress": dict(T=256, N=4_000_000, S=4, K=4, cpu_sample=500_000,
+    "fitch64": dict(kind="fitch", T=64, N=64 * FITCH_BASE, S=4, K=1, cpu_sample=FITCH_BASE, cpu_sample_1core=FITCH_BASE,
+                    name="Fitch/non-additive parsimony length, 64 taxa x 64Mi bit-packed DNA characters"),
+    "compress": dict(kind="compress", T=256, N=4_000_000, S=4, K=4, cpu_sample=500_000,
                      name="site-pattern compression (the step before the path), 256 taxa x 4M raw DNA sites"),
 }
+SECONDARY = ["fitch", "fitch64", "aa", "codon", "cfg1"]
 
 
 def peaks():
@@ -57,16 +70,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_model(wl):
+def make_model(wl, diagonalize=None):
+    """The workload's MlModel.t record. diagonalize: the eigen-solver (default: the product's own
+    phylo_diagonalize_*; the CPU arm passes the reference's, so that it never loads the product)."""
     from phylocaml_b200 import mlmodel
 
     if wl["S"] == 4:
-        return mlmodel.create(("GTR", GTR_CO), 4, pi=GTR_PI, site_var=("gamma", wl["K"], 0.5))
+        return mlmodel.create(("GTR", GTR_CO), 4, pi=GTR_PI, site_var=("gamma", wl["K"], 0.5), diagonalize=diagonalize)
     if wl["S"] == 20:
         R, pi = mlmodel.synthetic_reversible(20, 4)
-        return mlmodel.create(("Const", R), 20, pi=pi, site_var=("gamma", wl["K"], 0.5))
+        return mlmodel.create(("Const", R), 20, pi=pi, site_var=("gamma", wl["K"], 0.5), diagonalize=diagonalize)
     R, pi = mlmodel.gy94(2.0, 0.5, 5)
-    return mlmodel.create(("Const", R), 61, pi=pi)
+    return mlmodel.create(("Const", R), 61, pi=pi, diagonalize=diagonalize)
 
 
 def mask_dtype(S):
@@ -150,6 +165,30 @@ def bind_to_gpu_local_cpus(torch, local, sysfs="/sys/bus/pci/devices", min_cpus=
         return None
 
 
+def host_placement(torch, local, world, sysfs="/sys/bus/pci/devices"):
+    """What is true about where this rank's host side runs, for the JSON line: the CPUs and NUMA
+    node the kernel lists as local to the GPU, whether the main thread was bound to them
+    (bind_to_gpu_local_cpus: multi-rank runs only, and only when that is a proper subset of the
+    CPUs this process may use), and the CPU count the ranks share."""
+    info = {"cpus_visible": len(os.sched_getaffinity(0)), "ranks_sharing_them": world, "bound": False}
+    try:
+        prop = torch.cuda.get_device_properties(local)
+        path = os.path.join(sysfs, "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id))
+        with open(os.path.join(path, "local_cpulist")) as f:
+            info["gpu_local_cpulist"] = f.read().strip()
+        with open(os.path.join(path, "numa_node")) as f:
+            info["gpu_numa_node"] = int(f.read().strip())
+    except Exception:  # noqa: BLE001
+        info["gpu_local_cpulist"] = None
+    note = bind_to_gpu_local_cpus(torch, local, sysfs) if world > 1 else None
+    if note:
+        info["bound"], info["note"] = True, note
+    elif world > 1:
+        info["note"] = ("not bound: the GPU-local CPU list is every CPU this process may use (all GPUs of the box hang "
+                        "off one NUMA node), so %d ranks share %d CPUs for their upload threads" % (world, info["cpus_visible"]))
+    return info
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -225,96 +264,235 @@ def build_tips(tree_mod, tr, model, T, n_local, S, lo=0):
     return tips
 
 
-def run_reference(args, wl):
-    """CPU arm: the reference's own C where it exists (bv_fitch / bv_distance from oracle/_ref
-    for Fitch), otherwise the oracle port of the path (pruning: the reference has no pruning
-    loop, lib/likelihood_c.ml:1-33), with all host threads, on a bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def fitch_tips(tree_mod, T, n_total, lo, n_local, pinned=True):
+    """The global Fitch alignment is one random block of FITCH_BASE characters tiled to n_total; a
+    rank holds columns [lo, lo + n_local) of it (one character per byte, the reference's W = 8
+    layout, lib/bitvector/bv.h:29-55)."""
+    from phylocaml_b200 import engine
+
+    base = tree_mod.random_fitch_chars(T, min(n_total, FITCH_BASE), 4, seed=5)
+    tips = engine.pinned_empty((T, n_local), np.uint8) if pinned else np.empty((T, n_local), np.uint8)
+    pos = 0
+    while pos < n_local:
+        off = (lo + pos) % base.shape[1]
+        n = min(base.shape[1] - off, n_local - pos)
+        tips[:, pos:pos + n] = base[:, off:off + n]
+        pos += n
+    return tips, base
+
+
+def cpu_legs(wl, kind, ops, ra, rb, rt, n_nodes, model, sample, budget_s=8.0):
+    """CPU baseline legs on `sample` (the first patterns / characters of rank 0's shard), timed on
+    this box's host cores: the reference's own C where it exists (Fitch: bv_fitch + bv_distance of
+    lib/bitvector/bv.c:46-55,148-160 out of oracle/_ref, kind "reference"), otherwise the oracle
+    port (pruning: the reference has no pruning loop, lib/likelihood_c.ml:1-33; kind "port").
+    Returns (headline leg = all threads at the reference's -O2, variants, last result)."""
+    from oracle.oracle import Oracle, Ref
+
+    cores = os.cpu_count() or 1
+    T = wl["T"]
+    unit = "char-ops/s" if kind == "fitch" else "site-updates/s"
+    use_ref = kind == "fitch" and Ref.available()
+
+    def runner(variant, nthreads, smp):
+        if use_ref:
+            ref = Ref(variant)
+            return lambda: {"length": ref.fitch_score_tree(smp, ops, n_nodes, ra, rb, nthreads=nthreads)}
+        orc = Oracle(variant)
+        if kind == "fitch":
+            return lambda: orc.fitch_score_tree(smp, None, ops, n_nodes, ra, rb, nthreads=nthreads)
+        return lambda: orc.lk_score_tree(model, smp, None, ops, n_nodes, ra, rb, rt, nthreads=nthreads)
+
+    def best_of(fn, budget):
+        best, res, t_all = None, None, time.perf_counter()
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = fn()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            if time.perf_counter() - t_all > budget:
+                break
+        return best, res
+
+    ns = sample.shape[1]
+    what = "characters" if kind == "fitch" else "patterns"
+    code = ("reference bv_fitch per node + bv_distance (lib/bitvector/bv.c via oracle/_ref, W=8)" if use_ref
+            else "oracle C port (oracle/phylo_oracle.c)")
+    best, res = best_of(runner("o2", cores, sample), budget_s)
+    main = {"value": (T - 1) * ns / best, "unit": unit, "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": "first %d of this rank's %s, best of <=3 passes, %s, gcc -O2 (the reference's flag, "
+                      "myocamlbuild.ml:6)%s, %d host threads" % (ns, what, code, "" if use_ref else " -ffp-contract=off", cores)}
+    variants = {}
+    n1 = min(ns, wl.get("cpu_sample_1core", ns))
+    s1 = np.ascontiguousarray(sample[:, :n1])
+    b1, _ = best_of(runner("o2", 1, s1), budget_s / 2)
+    variants["O2_1_thread"] = {"value": (T - 1) * n1 / b1, "unit": unit, "cores": 1, "sample": "first %d %s" % (n1, what)}
+    fast_ok = (Ref.available("o3") if use_ref else Oracle.available("o3"))
+    if fast_ok:
+        b3, _ = best_of(runner("o3", cores, sample), budget_s / 2)
+        variants["O3_x86-64-v3_all_threads"] = {"value": (T - 1) * ns / b3, "unit": unit, "cores": cores,
+                                               "sample": "first %d %s; gcc -O3 -march=x86-64-v3 (AVX2 + FMA; "
+                                                         "-march=native of the build container would not be "
+                                                         "portable to this box)" % (ns, what)}
+        b31, _ = best_of(runner("o3", 1, s1), budget_s / 2)
+        variants["O3_x86-64-v3_1_thread"] = {"value": (T - 1) * n1 / b31, "unit": unit, "cores": 1,
+                                            "sample": "first %d %s" % (n1, what)}
+    main["variants"] = variants
+    return main, res
+
+
+def reference_model(wl):
+    """Model record for the CPU arm built WITHOUT the product library: the eigensystem comes from the
+    reference's own diagonalize_* (lib/mlmodel.c:163-262, oracle/_ref) or, where that is not built,
+    from numpy.linalg."""
+    from oracle.oracle import Ref, numpy_diagonalize
+
+    diag = Ref().diagonalize if Ref.available() else numpy_diagonalize
+    return make_model(wl, diagonalize=diag), ("reference diagonalize_* (oracle/_ref, LAPACK)" if Ref.available()
+                                              else "numpy.linalg")
+
+
+def reference_leg(key, wl, steps, warmup):
+    """One workload of the CPU arm: `steps` timed passes over a bounded sample, all host threads."""
     from oracle.oracle import Oracle, Ref
     from phylocaml_b200 import tree as tree_mod
 
     cores = os.cpu_count() or 1
-    orc = Oracle()
     T, S, K = wl["T"], wl["S"], wl["K"]
     tr = tree_mod.random_tree(T, seed=1)
     ops, ra, rb, rt, n_nodes = tree_mod.schedule(tr)
-    ns = wl["cpu_sample"]
-    times = []
-    if args.workload == "fitch":
-        chars = tree_mod.random_fitch_chars(T, ns, 4, seed=5)
+    ns = min(wl["cpu_sample"], wl["N"])
+    if wl["kind"] == "fitch":
+        chars, _ = fitch_tips(tree_mod, T, wl["N"], 0, ns, pinned=False)
         if Ref.available():  # the reference's own bv_fitch / bv_distance, compiled unmodified
             ref = Ref()
             fn = lambda: ref.fitch_score_tree(chars, ops, n_nodes, ra, rb, nthreads=cores)
             kind = "reference"
-            sample = ("64 taxa x %d chars, W=8 one char per byte; reference bv_fitch per node + bv_distance "
-                      "(lib/bitvector/bv.c, -O2), characters in %d slabs on %d host threads" % (ns, cores, cores))
+            sample = ("%d taxa x %d chars (of %d), W=8 one char per byte; reference bv_fitch per node + bv_distance "
+                      "(lib/bitvector/bv.c, -O2), characters in %d slabs on %d host threads" % (T, ns, wl["N"], cores, cores))
         else:
+            orc = Oracle()
             fn = lambda: orc.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, nthreads=cores)["length"]
             kind = "port"
-            sample = "64 taxa x %d chars, W=8 one char per byte (bv.c layout), %d pthreads" % (ns, cores)
-        units, metric, unit = (T - 1) * ns, "fitch_char_ops_per_s", "char-ops/s"
+            sample = "%d taxa x %d chars (of %d), W=8 one char per byte (bv.c layout), %d pthreads" % (T, ns, wl["N"], cores)
+        metric, unit, dtype, extra = "fitch_char_ops_per_s", "char-ops/s", "u8", {}
     else:
-        model = make_model(wl)
+        orc = Oracle()
+        model, diag_src = reference_model(wl)
         tips = tree_mod.evolve_tips(tr, model, min(ns, BASE_PATTERNS), seed=3, dtype=mask_dtype(S))
         tips = np.tile(tips, (1, (ns + tips.shape[1] - 1) // tips.shape[1]))[:, :ns].copy()
         fn = lambda: orc.lk_score_tree(model, tips, None, ops, n_nodes, ra, rb, rt, nthreads=cores)["lnl"]
-        units, metric, unit, kind = (T - 1) * ns, "clv_site_updates_per_s", "site-updates/s", "port"
-        sample = "%d taxa x %d patterns (of %d), oracle C port -O2 no-FMA, %d pthreads" % (T, ns, wl["N"], cores)
-    for _ in range(args.warmup):
-        fn()
-    for _ in range(args.steps):
+        metric, unit, dtype, kind = "clv_site_updates_per_s", "site-updates/s", "f64", "port"
+        sample = ("%d taxa x %d patterns (of %d), oracle C port -O2 -ffp-contract=off (the reference has no pruning "
+                  "loop, lib/likelihood_c.ml:1-33), %d pthreads; eigensystem: %s" % (T, ns, wl["N"], cores, diag_src))
+        extra = {}
+    times, out = [], None
+    for _ in range(warmup):
+        out = fn()
+    for _ in range(steps):
         t0 = time.perf_counter()
-        fn()
+        out = fn()
         times.append(time.perf_counter() - t0)
     total = sum(times)
-    value = units * args.steps / total
-    line = {
-        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.workload != "fitch" else "u8",
-        "data": "synthetic", "config": {"workload": wl["name"], "cpu_sample": sample},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    value = (T - 1) * ns * steps / total
+    rec = {"metric": metric, "value": value, "unit": unit, "steps": steps, "warmup": warmup,
+           "ms_per_step": 1e3 * total / steps, "dtype": dtype,
+           "config": workload_config(key, wl, wl["N"], wl["N"], 1, None, None),
+           "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "check": {"result_on_sample": out}}
+    rec.update(extra)
+    return rec
+
+
+def run_reference(args, wl):
+    """CPU arm (`--impl reference`): the reference's own C where it exists (bv_fitch / bv_distance
+    from oracle/_ref for Fitch), otherwise the oracle port of the path, with all host threads, each
+    step a bounded sample of the workload. Nothing of the product library is loaded here: the model
+    record comes from the reference's diagonalize_* (or numpy)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rec = reference_leg(args.workload, wl, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": rec["metric"], "value": rec["value"], "unit": rec["unit"],
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": rec["dtype"],
+            "data": "synthetic", "config": rec["config"], "cpu_baseline": rec["cpu_baseline"], "e2e": rec["e2e"],
+            "gpu_launches": 0, "check": rec["check"]}
+    others = secondary_list(args)
+    if others:
+        line["workloads"] = {}
+        for key in others:
+            line["workloads"][key] = reference_leg(key, dict(WORKLOADS[key]), 3, 1)
     print(json.dumps(line))
 
 
-def cpu_baseline(wl, workload, tr, ops, ra, rb, rt, n_nodes, model, tips_sample, site_gpu):
-    from oracle.oracle import Oracle, Ref
+def secondary_list(args):
+    if args.workloads == "none" or (args.workloads == "default" and args.workload != "dna"):
+        return []
+    if args.workloads in ("all", "default"):
+        return [k for k in SECONDARY if k != args.workload]
+    return [k for k in args.workloads.split(",") if k and k != args.workload]
 
-    cores = os.cpu_count() or 1
-    orc = Oracle()
-    ref = Ref() if workload == "fitch" and Ref.available() else None
-    T = wl["T"]
-    ns = tips_sample.shape[1]
-    best, res = None, None
-    t_all = time.perf_counter()
-    for _ in range(3):
-        t0 = time.perf_counter()
-        if ref is not None:
-            res = {"length": ref.fitch_score_tree(tips_sample, ops, n_nodes, ra, rb, nthreads=cores)}
-        elif workload == "fitch":
-            res = orc.fitch_score_tree(tips_sample, None, ops, n_nodes, ra, rb, nthreads=cores)
+
+def workload_config(key, wl, n_total, n_local, world, l2_note, numa_note):
+    cfg = {"workload": wl["name"], "taxa": wl["T"], "patterns_total": n_total, "states": wl["S"],
+           "rate_classes": wl["K"], "tree": "random topology seed 1, Exp(0.1) branch lengths",
+           "tips": "random DNA singletons + 2% two-state ambiguity (2^20 characters, tiled)" if wl["kind"] == "fitch"
+           else "evolved under the model (65536 patterns, tiled), 1% missing"}
+    if l2_note is not None:
+        cfg.update({"patterns_per_gpu": n_local, "l2": l2_note,
+                    "sharding": "contiguous 1024-aligned pattern slabs, one process per GPU",
+                    "collective": "allreduce of one scalar per step" if world > 1 else "none",
+                    "host_placement": numa_note})
+    return cfg
+
+
+class Ctx:
+    """What every workload of one bench.py process shares: torch, the process group, the peaks."""
+
+    def __init__(self, torch, dist, world, rank, local, numa_note):
+        self.torch, self.dist, self.world, self.rank, self.local, self.numa_note = torch, dist, world, rank, local, numa_note
+        self.hbm_peak, self.peak_src = peaks()
+        self.flush_buf = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed_steps(self, fn, n, flush):
+        """Device time of exactly n calls of fn (ms, max over ranks) and the last result. Large
+        working sets: one event pair around all n, barrier + synchronize on both sides. Working sets
+        that could survive in the 126 MB L2: 512 MB are written before every iteration and each
+        iteration has its own event pair (the flush is outside the timed region); the pairs are summed."""
+        torch = self.torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out, total = None, 0.0
+        if not flush:
+            self.barrier()
+            a.record()
+            for _ in range(n):
+                out = fn()
+            b.record()
+            self.barrier()
+            total = a.elapsed_time(b)
         else:
-            res = orc.lk_score_tree(model, tips_sample, None, ops, n_nodes, ra, rb, rt, nthreads=cores)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        if time.perf_counter() - t_all > 25:
-            break
-    unit = "char-ops/s" if workload == "fitch" else "site-updates/s"
-    out = {"value": (T - 1) * ns / best, "unit": unit, "cores": cores, "kind": "reference" if ref else "port",
-           "sample": ("first %d of this rank's characters, best of <=3 passes, reference bv_fitch/bv_distance "
-                      "(oracle/_ref) on %d host threads" % (ns, cores)) if ref else
-                     ("first %d of this rank's patterns, best of <=3 passes, oracle C port with %d pthreads"
-                      % (ns, cores))}
-    check = None
-    if workload != "fitch" and site_gpu is not None:
-        ref = res["site_lnl"]
-        check = float(np.max(np.abs(site_gpu[:ns] - ref)) / np.max(np.abs(ref)))
-    return out, check, res
+            if self.flush_buf is None:
+                self.flush_buf = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+            self.barrier()
+            for i in range(n):
+                self.flush_buf.fill_(i & 0xFF)
+                a.record()
+                out = fn()
+                b.record()
+                b.synchronize()
+                total += a.elapsed_time(b)
+            self.barrier()
+        tms = torch.tensor([total], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(tms, op=self.dist.ReduceOp.MAX)
+        return float(tms.item()), out
 
 
 def run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src):
@@ -391,57 +569,22 @@ def run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src):
     eng.close()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dna", choices=sorted(WORKLOADS))
-    ap.add_argument("--patterns", type=int, default=0, help="override the total pattern count")
-    ap.add_argument("--taxa", type=int, default=0, help="override the number of taxa")
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="fused", choices=["fused", "fused-lnl", "pernode"],
-                    help="likelihood path: tree-fused kernel keeping every CLV (default), tree-fused "
-                         "lnL-only (no CLV written), or one streaming kernel per node")
-    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other modes")
-    ap.add_argument("--fitch-kernel", default="auto", choices=["auto", "tile", "regwalk", "l2"],
-                    help="whole-tree Fitch kernel (PHYLO_OPT_FITCH_WALK)")
-    args = ap.parse_args()
-    assert args.warmup >= 0 and args.steps >= 1
-    wl = dict(WORKLOADS[args.workload])
-    if args.patterns:
-        wl["N"] = args.patterns
-    if args.taxa:
-        wl["T"] = args.taxa
-    if args.patterns or args.taxa:
-        wl["name"] += " [overridden: %d taxa x %d patterns]" % (wl["T"], wl["N"])
-
-    if args.impl == "reference":
-        run_reference(args, wl)
-        return
-
-    import torch
-
+def run_workload(ctx, args, key, wl, primary):
+    """One workload on this process's GPU (all ranks call it together). Returns the JSON record on
+    rank 0 (None elsewhere). `primary`: the headline -- full step counts, the other likelihood modes,
+    the branch-length loop; secondary workloads run fewer steps and skip the mode comparison (codon
+    keeps the branch-length loop: it is half of BASELINE config 5)."""
     from phylocaml_b200 import engine, tree as tree_mod
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    numa_note = bind_to_gpu_local_cpus(torch, local) if world > 1 else None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    hbm_peak, peak_src = peaks()
-
-    if args.workload == "compress":
-        run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src)
-        return
-
+    torch, dist, world, rank, local = ctx.torch, ctx.dist, ctx.world, ctx.rank, ctx.local
+    hbm_peak, peak_src = ctx.hbm_peak, ctx.peak_src
+    kind = wl["kind"]
+    steps = args.steps if primary else max(5, min(args.steps, 10))
+    warmup = args.warmup if primary else max(3, min(args.warmup, 3))
+    e2e_steps = args.e2e_steps if primary else 3
+    other_modes = primary and not args.no_other_modes
+    want_branch_loop = (primary and not args.no_other_modes) or key == "codon"
+    mode = args.mode if kind == "lk" else None
     T, S, K = wl["T"], wl["S"], wl["K"]
     n_total = wl["N"] * (world if args.scaling == "weak" else 1)
     lo, hi = shard_bounds(n_total, world, rank)
@@ -451,59 +594,13 @@ def main():
     eng = engine.Engine(local)
     launches0 = eng.launch_count
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def needs_flush(m):
+        return device_footprint("fitch" if kind == "fitch" else key, T, S, K, mask_dtype(S)().itemsize, m, n_local) < 4 * L2_BYTES
 
-    flush_buf = [None]
-
-    def needs_flush(mode):
-        return device_footprint(args.workload, T, S, K, mask_dtype(S)().itemsize, mode, n_local) < 4 * L2_BYTES
-
-    def timed_steps(fn, n, flush):
-        """Device time of exactly n calls of fn (ms, max over ranks) and the last result. Large
-        working sets: one event pair around all n, barrier + synchronize on both sides. Working sets
-        that could survive in the 126 MB L2: 512 MB are written before every iteration and each
-        iteration has its own event pair (the flush is outside the timed region); the pairs are summed."""
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        out, total = None, 0.0
-        if not flush:
-            barrier()
-            a.record()
-            for _ in range(n):
-                out = fn()
-            b.record()
-            barrier()
-            total = a.elapsed_time(b)
-        else:
-            if flush_buf[0] is None:
-                flush_buf[0] = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-            barrier()
-            for i in range(n):
-                flush_buf[0].fill_(i & 0xFF)
-                a.record()
-                out = fn()
-                b.record()
-                b.synchronize()
-                total += a.elapsed_time(b)
-            barrier()
-        tms = torch.tensor([total], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        return float(tms.item()), out
-
-    if args.workload == "fitch":
+    base = None
+    if kind == "fitch":
         model = None
-        tips = engine.pinned_empty((T, n_local), np.uint8)
-        # the global alignment is one random block tiled to n_total; this rank holds columns [lo, hi)
-        base = tree_mod.random_fitch_chars(T, min(n_total, 1 << 20), 4, seed=5)
-        pos = 0
-        while pos < n_local:
-            off = (lo + pos) % base.shape[1]
-            n = min(base.shape[1] - off, n_local - pos)
-            tips[:, pos:pos + n] = base[:, off:off + n]
-            pos += n
+        tips, base = fitch_tips(tree_mod, T, n_total, lo, n_local)
         eng.set_option(eng.OPT_FITCH_WALK, {"auto": 1, "tile": 3, "regwalk": 2, "l2": 0}[args.fitch_kernel])
         eng.fitch_set_tips(tips, 4, capacity=n_nodes)
         acc = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -512,7 +609,7 @@ def main():
             v = eng.fitch_score_tree(ops, ra, rb)
             if world > 1:
                 acc[0] = v
-                dist.all_reduce(acc)
+                dist.all_reduce(acc)  # the path's only exchange: one exact integer
                 return int(acc.item())
             return v
 
@@ -521,7 +618,6 @@ def main():
             return step()
 
         metric, unit, dtype = "fitch_char_ops_per_s", "char-ops/s", "u32 (bit-sliced state planes)"
-        units_per_step = (T - 1) * n_total
         kbytes = {"fitch_tree": (2 * T - 1) * 0.5}  # compulsory: every node set moved once
         h2d = tips.nbytes
     else:
@@ -529,11 +625,11 @@ def main():
         tips = build_tips(tree_mod, tr, model, T, n_local, S, lo)
         eng.lk_set_model(model)
 
-        def set_mode(mode):
-            eng.set_option(eng.OPT_FUSED_TREE, 0 if mode == "pernode" else 1)
-            eng.set_option(eng.OPT_RETAIN_CLV, 0 if mode == "fused-lnl" else 1)
+        def set_mode(m):
+            eng.set_option(eng.OPT_FUSED_TREE, 0 if m == "pernode" else 1)
+            eng.set_option(eng.OPT_RETAIN_CLV, 0 if m == "fused-lnl" else 1)
 
-        set_mode(args.mode)
+        set_mode(mode)
         eng.lk_set_tips(tips, capacity=n_nodes)
         acc = torch.zeros(1, dtype=torch.float64, device="cuda")
 
@@ -556,37 +652,38 @@ def main():
             return v
 
         metric, unit, dtype = "clv_site_updates_per_s", "site-updates/s", "f64"
-        units_per_step = (T - 1) * n_total
-        kbytes = lk_bytes(T, S, K, tips.dtype.itemsize, args.mode)
+        kbytes = lk_bytes(T, S, K, tips.dtype.itemsize, mode)
         h2d = tips.nbytes + ops.nbytes
+    units_per_step = (T - 1) * n_total
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         result = step()
     eng.profile(True, reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
-    flush = needs_flush(args.mode)
-    ms, result = timed_steps(step, args.steps, flush)
+    flush = needs_flush(mode)
+    ms, result = ctx.timed_steps(step, steps, flush)
     prof = eng.profile_get()
     eng.profile(False)
     launches = eng.launch_count - launches0
-    step_launches = (eng.launch_count - launches0) // (args.steps + args.warmup)
+    step_launches = (eng.launch_count - launches0) // (steps + warmup)
     # a timed region shorter than a few nvidia-smi samples (50 ms apart): keep the same load running,
-    # untimed, for ~0.6 s so that the clocks / throttle reasons are sampled under it (the count is
-    # derived from the all-reduced time, so every rank runs the same number of steps)
-    extra_steps = 0 if ms >= 600.0 else min(20000, int(np.ceil((600.0 - ms) / max(ms / args.steps, 1e-3))))
+    # untimed, so that the clocks / throttle reasons are sampled under it (the count is derived from
+    # the all-reduced time, so every rank runs the same number of steps)
+    want_ms = 600.0 if primary else 300.0
+    extra_steps = 0 if ms >= want_ms else min(20000, int(np.ceil((want_ms - ms) / max(ms / steps, 1e-3))))
     for _ in range(extra_steps):
         step()
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
         clocks["untimed_steps_run_for_sampling"] = extra_steps
-    value = units_per_step * args.steps / (ms * 1e-3)
+    value = units_per_step * steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel class (CUDA events on the launching stream)
     roof, kernels = None, {}
     tot_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
     for name, (kms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         per_launch_ms = kms / n
-        entry = {"launches_per_step": n / args.steps, "avg_us": 1e3 * per_launch_ms,
+        entry = {"launches_per_step": n / steps, "avg_us": 1e3 * per_launch_ms,
                  "share_of_kernel_time": kms / tot_kernel_ms}
         if name in kbytes:
             by = kbytes[name] * n_local
@@ -599,8 +696,9 @@ def main():
                 if os.path.exists(tpath):
                     with open(tpath) as f:
                         tj = json.load(f)
-                    for t in (tj.get(name), tj.get(name + "_small")):
-                        if (t and t.get("patterns") and t.get("workload", "dna") == args.workload and
+                    tkey = "fitch" if kind == "fitch" else key
+                    for t in (tj.get(name), tj.get(name + "_small"), tj.get(name + "_" + key)):
+                        if (t and t.get("patterns") and t.get("workload", "dna") in (tkey, key) and
                                 t.get("taxa") in (None, T) and
                                 t.get("min_patterns", 0) <= n_local <= t.get("max_patterns", 1 << 62)):
                             traffic = t["dram_bytes_per_launch"] * n_local / t["patterns"]
@@ -608,14 +706,14 @@ def main():
                         "unit": "GB/s", "frac": entry["frac"], "traffic": traffic, "peak_source": peak_src,
                         "bytes_model": ("compulsory (tree-fused: each interior CLV + scale counter written once, "
                                         "tips read once)" if name == "tree_fused" else
-                                        "SURVEY 8(d) per-node streaming") if args.workload != "fitch"
+                                        "SURVEY 8(d) per-node streaming") if kind != "fitch"
                         else "compulsory (tree-fused: every node set moved once)"}
         kernels[name] = entry
     # 20 / 61 states: the update is a dense contraction (K S (2 (2S - 1) + 1) flops per
     # update); the inner+inner kernel is held against the measured fp64 DMMA peak as well. For 61
     # states that is the governing roofline (15 flop/B), for 20 states the two rooflines meet.
     roof_tensor = None
-    if args.workload != "fitch" and S >= 20 and "prune_inner_inner" in kernels:
+    if kind == "lk" and S >= 20 and "prune_inner_inner" in kernels:
         fl = K * S * (2 * (2 * S - 1) + 1) * n_local
         ent = kernels["prune_inner_inner"]
         tf = fl / (ent["avg_us"] * 1e-6) / 1e12
@@ -625,41 +723,46 @@ def main():
                        "unit": "TFLOP/s", "frac": tf / FP64_DMMA_TFLOPS, "traffic": None,
                        "peak_source": "fp64 DMMA (mma.sync.m8n8k4.f64) measured by tools/peaks.cu on this pool",
                        "step_level": {"algorithmic_flops_per_step": fl * (T - 1),
-                                      "achieved_tflops": fl * (T - 1) / (ms * 1e-3 / args.steps) / 1e12,
+                                      "achieved_tflops": fl * (T - 1) / (ms * 1e-3 / steps) / 1e12,
                                       "note": "SURVEY's dense count for every update; tip sides are table "
                                               "lookups in the engine, so this exceeds the executed flops"}}
         roof_tensor["step_level"]["frac"] = roof_tensor["step_level"]["achieved_tflops"] / FP64_DMMA_TFLOPS
-    if args.workload != "fitch":
+    if kind == "lk":
         step_bytes = kbytes["tree"] * n_local
         roof_step = {"bytes_model": "SURVEY 8(d) per-node streaming (what a kernel-per-node engine must move)",
                      "algorithmic_bytes_per_step": step_bytes,
-                     "achieved_gbs": step_bytes / (ms * 1e-3 / args.steps) / 1e9}
+                     "achieved_gbs": step_bytes / (ms * 1e-3 / steps) / 1e9}
         roof_step["frac"] = roof_step["achieved_gbs"] / hbm_peak
     else:
-        roof_step = None
+        step_bytes = kbytes["fitch_tree"] * n_local
+        roof_step = {"bytes_model": "compulsory, against the whole step (host schedule work + launch + result read-back "
+                                    "included), not the kernel alone",
+                     "algorithmic_bytes_per_step": step_bytes,
+                     "achieved_gbs": step_bytes / (ms * 1e-3 / steps) / 1e9}
+        roof_step["frac"] = roof_step["achieved_gbs"] / hbm_peak
 
     # ---- e2e: host buffers in, scalar out, through the C ABI, every step
     e2e_step()
-    e2e_ms, result_e2e = timed_steps(e2e_step, args.e2e_steps, flush)
-    e2e_val = units_per_step * args.e2e_steps / (e2e_ms * 1e-3)
+    e2e_ms, result_e2e = ctx.timed_steps(e2e_step, e2e_steps, flush)
+    e2e_val = units_per_step * e2e_steps / (e2e_ms * 1e-3)
     e2e = {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-           "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps}
+           "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps}
 
     # ---- the other likelihood modes, briefly (same inputs, same timing method)
     modes = None
-    if args.workload != "fitch" and not args.no_other_modes:
-        modes = {args.mode: {"value": value, "ms_per_step": ms / args.steps, "lnl": result}}
+    if kind == "lk" and other_modes:
+        modes = {mode: {"value": value, "ms_per_step": ms / steps, "lnl": result}}
         for m in ("fused", "fused-lnl", "pernode"):
-            if m == args.mode:
+            if m == mode:
                 continue
             set_mode(m)
             for _ in range(2):
                 r_m = step()
-            nm = max(3, args.steps // 4)
-            tm, r_m = timed_steps(step, nm, needs_flush(m))
+            nm = max(3, steps // 4)
+            tm, r_m = ctx.timed_steps(step, nm, needs_flush(m))
             modes[m] = {"value": units_per_step * nm / (tm * 1e-3), "ms_per_step": tm / nm, "lnl": r_m,
                         "l2_flushed_between_steps": needs_flush(m)}
-        set_mode(args.mode)
+        set_mode(mode)
         step()  # leave the engine's site lnL / CLVs in the primary mode's state
 
     # ---- branch-length re-evaluation loop (BASELINE config 5's second half):
@@ -667,7 +770,7 @@ def main():
     # length per call: each depends on the previous result), then 10 re-prunes of the path to
     # the root after one branch changed, all other CLVs staying resident.
     branch_loop = None
-    if args.workload != "fitch" and args.mode == "fused" and not args.no_other_modes:
+    if kind == "lk" and mode == "fused" and want_branch_loop:
         def timed(fn, reps):
             torch.cuda.synchronize()
             b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -715,50 +818,127 @@ def main():
         eng.lk_set_tips(tips, capacity=n_nodes)
         step()  # restore the unmodified tree's state
 
-    # ---- CPU baseline + correctness spot check (rank 0, N=1 only)
+    # ---- CPU baseline + correctness check against the oracle (rank 0, N=1 only)
     cpu, check = None, {"result": result, "result_e2e": result_e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(wl["cpu_sample"], n_local)
         sample = np.ascontiguousarray(tips[:, :ns])
-        site = eng.lk_get_site_lnl() if args.workload != "fitch" else None
-        cpu, err, res = cpu_baseline(wl, args.workload, tr, ops, ra, rb, rt, n_nodes, model, sample, site)
-        if args.workload == "fitch":
+        cpu, res = cpu_legs(wl, kind, ops, ra, rb, rt, n_nodes, model, sample, budget_s=8.0 if primary else 4.0)
+        if kind == "fitch":
+            check["oracle_length_of_sample"] = int(res["length"])
             if ns == n_local:
-                check["oracle_length"] = res["length"]
-                check["bit_exact"] = bool(res["length"] == result)
+                check["bit_exact"] = bool(res["length"] == result == result_e2e)
+            elif ns == FITCH_BASE and n_local % FITCH_BASE == 0:
+                # the alignment is the sample tiled: the length of the whole is an exact multiple
+                want = int(res["length"]) * (n_local // FITCH_BASE)
+                check["expected_from_tiling"] = want
+                check["bit_exact"] = bool(want == result == result_e2e)
         else:
-            check["site_lnl_max_rel_err_vs_oracle_on_sample"] = err
+            site = eng.lk_get_site_lnl()
+            ref_site = res["site_lnl"]
+            check["site_lnl_max_rel_err_vs_oracle_on_sample"] = float(np.max(np.abs(site[:ns] - ref_site)) / np.max(np.abs(ref_site)))
+            check["tolerance"] = 1e-9
+            if ns == n_local:
+                check["lnl_rel_err_vs_oracle"] = float(abs(result - res["lnl"]) / abs(res["lnl"]))
+            check["e2e_equals_resident"] = bool(result == result_e2e)
 
-    foot = device_footprint(args.workload, T, S, K, mask_dtype(S)().itemsize, args.mode, n_local)
+    foot = device_footprint("fitch" if kind == "fitch" else key, T, S, K, mask_dtype(S)().itemsize, mode, n_local)
     l2_note = ("L2 flushed between timed iterations (%d MB written before each, outside its event pair; "
                "working set %.3f GB per GPU could stay in the 126 MB L2)" % (FLUSH_BYTES >> 20, foot / 1e9)
                if flush else "inputs exceed L2 (working set %.1f GB per GPU, 126 MB L2); no flush" % (foot / 1e9))
+    line = None
     if rank == 0:
         line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": {"workload": wl["name"], "taxa": T, "patterns_total": n_total,
-                       "patterns_per_gpu": n_local, "states": S, "rate_classes": K,
-                       "tree": "random topology seed 1, Exp(0.1) branch lengths",
-                       "tips": "evolved under the model (65536 patterns, tiled), 1% missing"
-                       if args.workload != "fitch" else "random DNA singletons + 2% two-state ambiguity",
-                       "l2": l2_note,
-                       "sharding": "contiguous 1024-aligned pattern slabs, one process per GPU",
-                       "collective": "allreduce of one scalar per step" if world > 1 else "none",
-                       "host_placement": numa_note},
-            "mode": args.mode if args.workload != "fitch" else None, "modes": modes,
+            "config": workload_config(key, wl, n_total, n_local, world, l2_note, ctx.numa_note),
+            "mode": mode, "modes": modes,
             "roofline": (roof_tensor if roof_tensor and S > 32 else roof),
             "roofline_hbm": roof if roof_tensor and S > 32 else None,
             "roofline_tensor": roof_tensor if roof_tensor and S <= 32 else None,
             "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": e2e, "branch_loop": branch_loop, "gpu_launches": int(step_launches * args.steps),
+            "e2e": e2e, "branch_loop": branch_loop, "gpu_launches": int(step_launches * steps),
             "gpu_launches_total_incl_warmup": int(launches), "clocks": clocks, "check": check,
         }
+    eng.close()
+    engine.pinned_free(tips)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dna", choices=sorted(WORKLOADS), help="the headline workload")
+    ap.add_argument("--workloads", default="default",
+                    help="secondary workloads reported under \"workloads\": all | none | comma list "
+                         "(default: all when the headline is dna)")
+    ap.add_argument("--patterns", type=int, default=0, help="override the headline's total pattern count")
+    ap.add_argument("--taxa", type=int, default=0, help="override the headline's number of taxa")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fused", choices=["fused", "fused-lnl", "pernode"],
+                    help="likelihood path: tree-fused kernel keeping every CLV (default), tree-fused "
+                         "lnL-only (no CLV written), or one streaming kernel per node")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other modes")
+    ap.add_argument("--fitch-kernel", default="auto", choices=["auto", "tile", "regwalk", "l2"],
+                    help="whole-tree Fitch kernel (PHYLO_OPT_FITCH_WALK)")
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    wl = dict(WORKLOADS[args.workload])
+    if args.patterns:
+        wl["N"] = args.patterns
+    if args.taxa:
+        wl["T"] = args.taxa
+    if args.patterns or args.taxa:
+        wl["name"] += " [overridden: %d taxa x %d patterns]" % (wl["T"], wl["N"])
+
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+
+    from phylocaml_b200 import engine, tree as tree_mod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    numa_note = host_placement(torch, local, world)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Ctx(torch, dist, world, rank, local, numa_note)
+
+    if args.workload == "compress":
+        run_compress(args, wl, torch, engine, tree_mod, local, ctx.hbm_peak, ctx.peak_src)
+        return
+
+    t_all = time.perf_counter()
+    line = run_workload(ctx, args, args.workload, wl, primary=True)
+    others = secondary_list(args)
+    if others:
+        recs = {}
+        for key in others:
+            t0 = time.perf_counter()
+            rec = run_workload(ctx, args, key, dict(WORKLOADS[key]), primary=False)
+            if rec is not None:
+                rec["bench_wall_s"] = time.perf_counter() - t0
+                recs[key] = rec
+        if line is not None:
+            line["workloads"] = recs
+    if line is not None:
+        line["bench_wall_s"] = time.perf_counter() - t_all
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":

@@ -96,9 +96,32 @@ def tcm_median_table(M, metric=False):
     return cost, med
 
 
+def numpy_diagonalize(Q, sym):
+    """(U, D, Ui) in the reference's conventions (lib/mlmodel.c:155-158,208-262) from numpy.linalg:
+    gtr: Q = U D Ui; sym: the ROWS of U are the eigenvectors, Ui = None. For harness legs that must
+    not touch the product library and run where oracle/_ref is not built."""
+    Q = np.asarray(Q, dtype=np.float64)
+    if sym:
+        w, V = np.linalg.eigh(Q)
+        return np.ascontiguousarray(V.T), np.diag(w), None
+    w, V = np.linalg.eig(Q)
+    if np.abs(np.imag(w)).max() > 0:
+        raise RuntimeError("Imaginary eigenvalues")
+    V = np.real(V)
+    return np.ascontiguousarray(V), np.diag(np.real(w)), np.ascontiguousarray(np.linalg.inv(V))
+
+
 class Oracle:
-    def __init__(self):
-        path = os.path.join(HERE, "liboracle.so")
+    # variant "o2" = liboracle.so (-O2 -ffp-contract=off: the parity oracle); "o3" = liboracle_o3.so
+    # (-O3 -march=x86-64-v3, FMA contraction allowed: a faster CPU baseline for bench.py, never a checker)
+    FILES = {"o2": "liboracle.so", "o3": "liboracle_o3.so"}
+
+    @classmethod
+    def available(cls, variant="o2"):
+        return os.path.exists(os.path.join(HERE, cls.FILES[variant]))
+
+    def __init__(self, variant="o2"):
+        path = os.path.join(HERE, self.FILES[variant])
         if not os.path.exists(path):
             build(ref=False)
         L = self.lib = C.CDLL(path)
@@ -241,11 +264,14 @@ class Ref:
     in a container that has /root/reference; the built .so files travel to the GPU box)."""
 
     @staticmethod
-    def available():
-        return os.path.exists(os.path.join(REF_DIR, "libmlmodel_ref.so"))
+    def available(variant="o2"):
+        return os.path.exists(os.path.join(REF_DIR, "libmlmodel_ref.so")) and (
+            variant == "o2" or os.path.exists(os.path.join(REF_DIR, "libbv8_ref_o3.so")))
 
-    def __init__(self):
-        if not self.available():
+    def __init__(self, variant="o2"):
+        """variant "o3": bv.c for WIDTH=8 built with -O3 -march=x86-64-v3 instead of the reference's
+        -O2 (bench.py's faster CPU baseline); everything else is the -O2 build either way."""
+        if not self.available(variant):
             raise RuntimeError("oracle/_ref not built (run `make -C oracle ref` where /root/reference exists)")
         m = self.ml = C.CDLL(os.path.join(REF_DIR, "libmlmodel_ref.so"))
         m.compose_gtr.argtypes = [_dp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]
@@ -259,7 +285,7 @@ class Ref:
         m.shim_last_failure.restype = C.c_char_p
         self.bv = {}
         for w in (8, 16, 32, 64):
-            b = C.CDLL(os.path.join(REF_DIR, "libbv%d_ref.so" % w))
+            b = C.CDLL(os.path.join(REF_DIR, "libbv%d_ref%s.so" % (w, "_o3" if (variant == "o3" and w == 8) else "")))
             b.bv_fitch.argtypes = [C.POINTER(_Vect)] * 3
             b.bv_fitch.restype = C.c_ulong
             b.bv_distance.argtypes = [C.POINTER(_Vect)] * 2

@@ -166,6 +166,24 @@ typedef struct {
   int32_t *scale;
 } lk_job;
 
+/* spec C.2.5 with an invariant-sites class: ln((1-v) l 2^(-256 c) + v pv), evaluated in the scaled
+ * domain as ln((1-v) l + v pv 2^(256 c)) - c 256 ln 2 so that a summed scale counter c >= 4-5
+ * (site likelihood below 2^-1074: deep trees) does not underflow a variable site to -inf. When
+ * v pv 2^(256 c) would overflow it exceeds (1-v) l <= 1 by more than 2^64: the sum is v pv to
+ * rounding. Same statement as lnl_pinvar in phylocaml_b200/csrc/common.cuh. */
+static double lnl_pinvar(double l, int c, double pinvar, double pv)
+{
+  const double ln_scale = ORACLE_SCALE_EXP * 0.6931471805599453094;
+  const double inv_term = pinvar * pv, var = (1.0 - pinvar) * l;
+  if (inv_term == 0.0) return log(var) - (double)c * ln_scale;
+  if (c >= 4) {
+    int ex;
+    (void)frexp(inv_term, &ex);
+    if (ex + ORACLE_SCALE_EXP * c > 64) return log(inv_term);
+  }
+  return log(var + ldexp(inv_term, ORACLE_SCALE_EXP * c)) - (double)c * ln_scale;
+}
+
 static void *lk_worker(void *arg)
 {
   lk_job *J = (lk_job *)arg;
@@ -222,8 +240,7 @@ static void *lk_worker(void *arg)
       for (t = 0; t < J->T; ++t) inv &= load_mask(J->tips, (long)t * N + s, J->mask_bytes);
       for (i = 0; i < S; ++i)
         if ((inv >> i) & 1) pinv += J->pi[i];
-      l = (1.0 - J->pinvar) * ldexp(l, -ORACLE_SCALE_EXP * c) + J->pinvar * pinv;
-      lnl = log(l);
+      lnl = lnl_pinvar(l, c, J->pinvar, pinv);
     } else {
       lnl = log(l) - (double)c * ln_scale;
     }

@@ -54,6 +54,35 @@ __device__ __forceinline__ double block_fold_1024(const double *vals, double *ws
   return r;
 }
 
+// Site log-likelihood with an invariant-sites class (spec C.2.5):
+//   ln( (1 - v) * l * 2^(-256 c) + v * pv ),  l = scaled site likelihood, c = summed scale counter,
+// evaluated in the SCALED domain: ldexp(l, -256 c) underflows to 0 once c reaches 4-5 (site
+// likelihood below 2^-1074, ordinary for deep trees), which would turn a variable site (pv == 0)
+// into -inf. ln( (1-v) l + v pv 2^(256 c) ) - c 256 ln 2 is the same number without that underflow;
+// when v pv 2^(256 c) would overflow it exceeds (1-v) l <= 1 by more than 2^64 and the sum is v pv
+// to rounding. *dscale (may be NULL) = d(site)/d(l) / site, the factor that turns dl/dt, d2l/dt2
+// into the derivative terms of the branch-length loop. oracle/phylo_oracle.c lnl_pinvar is the
+// same statement.
+__device__ __forceinline__ double lnl_pinvar(double l, int c, double pinvar, double pv, double *dscale = nullptr) {
+  const double kLnScale = kScaleExp * 0.6931471805599453094;
+  const double inv_term = pinvar * pv, var = (1.0 - pinvar) * l;
+  if (inv_term == 0.0) {
+    if (dscale) *dscale = 1.0 / l;
+    return log(var) - (double)c * kLnScale;
+  }
+  if (c >= 4) {
+    int ex;
+    (void)frexp(inv_term, &ex);
+    if (ex + kScaleExp * c > 64) {
+      if (dscale) *dscale = 0.0;
+      return log(inv_term);
+    }
+  }
+  const double site = var + ldexp(inv_term, kScaleExp * c);
+  if (dscale) *dscale = (1.0 - pinvar) / site;
+  return log(site) - (double)c * kLnScale;
+}
+
 // operand kinds of a compiled (tree-fused) schedule step
 enum : int { OPK_TIP = 0, OPK_CUR = 1, OPK_POP = 2, OPK_STORED = 3 };
 

@@ -123,9 +123,10 @@ edge_eval_kernel(const double *__restrict__ sum, const int32_t *__restrict__ sum
             double pv = 0.0;
             for (int s = 0; s < S; ++s)
               if ((mk >> s) & 1) pv += pi[s];
-            const double f = (1.0 - pinvar) * ldexp(1.0, -kScaleExp * sc);
-            const double site = f * l0 + pinvar * pv, r1 = f * l1 / site, r2 = f * l2 / site;
-            v0 = w * log(site);
+            double ds;
+            const double lnl = lnl_pinvar(l0, sc, pinvar, pv, &ds);
+            const double r1 = ds * l1, r2 = ds * l2;
+            v0 = w * lnl;
             v1 = w * r1;
             v2 = w * (r2 - r1 * r1);
           } else {

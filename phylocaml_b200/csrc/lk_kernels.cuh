@@ -288,7 +288,7 @@ root4_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
             const int m = inv[p];
             const double pv = (m & 1 ? pi0 : 0.0) + (m & 2 ? pi1 : 0.0) + (m & 4 ? pi2 : 0.0) +
                               (m & 8 ? pi3 : 0.0);
-            lnl = log((1.0 - pinvar) * ldexp(l, -kScaleExp * c) + pinvar * pv);
+            lnl = lnl_pinvar(l, c, pinvar, pv);
           } else {
             lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
           }
@@ -537,7 +537,7 @@ root_any_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
           double pv = 0.0;
           for (int i = 0; i < SS; ++i)
             if ((m >> i) & 1) pv += spi[i];
-          lnl = log((1.0 - pinvar) * ldexp(l, -kScaleExp * c) + pinvar * pv);
+          lnl = lnl_pinvar(l, c, pinvar, pv);
         } else {
           lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
         }
@@ -978,7 +978,7 @@ root_mma_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
             double pv = 0.0;
             for (int i = 0; i < S; ++i)
               if ((m >> i) & 1) pv += spi[i];
-            lnl = log((1.0 - pinvar) * ldexp(l, -kScaleExp * c) + pinvar * pv);
+            lnl = lnl_pinvar(l, c, pinvar, pv);
           } else {
             lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
           }

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kTreeThreads, 4) lk_tree4_kernel(const TreeArg
               if (a.pinvar >= 0.0) {
                 const int m = a.inv[p];
                 const double pv = (m & 1 ? pi0 : 0.0) + (m & 2 ? pi1 : 0.0) + (m & 4 ? pi2 : 0.0) + (m & 8 ? pi3 : 0.0);
-                lnl = log((1.0 - a.pinvar) * ldexp(l, -kScaleExp * c) + a.pinvar * pv);
+                lnl = lnl_pinvar(l, c, a.pinvar, pv);
               } else {
                 lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
               }

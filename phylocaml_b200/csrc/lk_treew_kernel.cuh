@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(R == 1 ? kTreeWMaxWarps * 32 : 256, 1) lk_tree
           if (a.pinvar >= 0.0) {
             const int m = a.inv[pat[r]];
             const double pv = (m & 1 ? pi[0] : 0.0) + (m & 2 ? pi[1] : 0.0) + (m & 4 ? pi[2] : 0.0) + (m & 8 ? pi[3] : 0.0);
-            lnl = log((1.0 - a.pinvar) * ldexp(l, -kScaleExp * c) + a.pinvar * pv);
+            lnl = lnl_pinvar(l, c, a.pinvar, pv);
           } else {
             lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
           }

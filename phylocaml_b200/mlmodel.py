@@ -128,11 +128,16 @@ def gamma_rates_yang_mean(alpha, k):
     return (upper[1:] - upper[:-1]) * k
 
 
-def create(subst, a_size, pi=None, site_var=None, rates="yang_mean"):
+def create(subst, a_size, pi=None, site_var=None, rates="yang_mean", diagonalize=None):
     """subst: ("JC69",) | ("K2P", b) | ("F81",) | ("HKY85", k) | ("F84", k) | ("TN93", a, b) |
     ("GTR", co) | ("Const", matrix).  site_var: None (Constant) | ("gamma", k, alpha) |
-    ("theta", k, alpha, pinvar) | ("custom", rates, probs)."""
-    from . import engine as _engine
+    ("theta", k, alpha, pinvar) | ("custom", rates, probs).  diagonalize(Q, sym) -> (U, D, Ui):
+    the eigen-solver; default = the product's phylo_diagonalize_* (bench.py's CPU arm passes the
+    reference's own so that it does not load the product library)."""
+    if diagonalize is None:
+        from . import engine as _engine
+
+        diagonalize = _engine.diagonalize
 
     pri = priors(pi, a_size)
     kind = subst[0]
@@ -172,7 +177,7 @@ def create(subst, a_size, pi=None, site_var=None, rates="yang_mean"):
         r, p = np.asarray(site_var[1], float), np.asarray(site_var[2], float)
     else:
         raise ValueError(site_var)
-    U, D, Ui = _engine.diagonalize(q, sym)
+    U, D, Ui = diagonalize(q, sym)
     return dict(S=a_size, K=len(r), Q=q, U=U, D=D, Ui=Ui, pi=pri, rates=r, probs=p, pinvar=pinvar, sym=sym)
 
 

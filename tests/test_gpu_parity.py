@@ -106,6 +106,35 @@ def test_lk_dna_rescaling_deep_tree(eng, oracle):
     assert want["scale"].max() >= 1, "test must actually trigger rescaling"
 
 
+@pytest.mark.parametrize("fused", [1, 2, 0])
+def test_lk_pinvar_on_a_deep_tree_stays_finite(eng, oracle, fused):
+    """Invariant-sites class with summed scale counters >= 6 (900-taxon caterpillar): the site value
+    is formed in the scaled domain (lnl_pinvar, common.cuh), so variable sites keep a finite lnL
+    and the branch-length derivatives stay finite. Oracle = the same statement, itself pinned to
+    unscaled 80-bit pruning (tests/test_oracle_cpu.py)."""
+    model = dna_gtr_g4(pinvar=0.2)
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(900, 96, model, seed=2, tree_kind="caterpillar", mean_bl=0.9)
+    tips[:, :8] = tips[0, :8][None, :]
+    eng.set_option(eng.OPT_FUSED_TREE, fused)
+    try:
+        eng.lk_set_model(model)
+        eng.lk_set_tips(tips, capacity=n_nodes)
+        lnl = eng.lk_score_tree(ops, ra, rb, rt)
+        want = oracle.lk_score_tree(model, tips, None, ops, n_nodes, ra, rb, rt, want_clv=True)
+        assert (want["scale"][ra] + want["scale"][rb]).max() >= 6
+        site = eng.lk_get_site_lnl()
+        assert np.all(np.isfinite(site)) and np.isfinite(lnl)
+        assert np.abs(site - want["site_lnl"]).max() <= 1e-9 * np.abs(want["site_lnl"]).max()
+        assert rel_err(lnl, want["lnl"]) <= LNL_RTOL
+        # the sum-table path: same value, finite derivatives
+        eng.lk_edge_prepare(ra, rb)
+        l0, d1, d2 = eng.lk_edge_eval([rt, 0.5 * rt])
+        assert np.all(np.isfinite(l0)) and np.all(np.isfinite(d1)) and np.all(np.isfinite(d2))
+        assert rel_err(l0[0], lnl) <= 1e-11
+    finally:
+        eng.set_option(eng.OPT_FUSED_TREE, 1)
+
+
 def test_lk_jc69_sym_path(eng, oracle):
     m = mlmodel.create(("JC69",), 4, site_var=("gamma", 4, 1.0))
     _check_lk(eng, oracle, m, 14, 3000)
