@@ -118,16 +118,16 @@ int phylo_diagonalize_sym(double *Q_inout_U, double *D, int n);
  * Out: Q overwritten with U, D diagonal matrix, Ui = U^-1, such that Q = U D Ui row-major.
  * Fails with PHYLO_ERR_NUMERIC on complex eigenvalues (mlmodel.c:248-250). */
 int phylo_diagonalize_gtr(double *Q_inout_U, double *D, double *Ui, int n);
-/* Replace compose_sym / compose_gtr (lib/mlmodel.c:280-302, :325-342; lib/mlModel.ml:83-90):
- * P = exp(Q t) from the eigensystem, computed by the pt_build kernel. Same special cases:
- * t == -1.0 -> Q; t < 1e-10 -> I; compose_sym rounds t to float first (mlmodel.c:280).
- * D is the full n*n matrix. P_out: n*n host buffer. */
 /* Discrete-Gamma rate classes (lib/mlModel.ml:93-99, :676-694; the reference computes them with
  * Pareto/GSL, which is neither vendored nor pinned). mode 0 = what the reference's code does:
  * rates[i] = quantile at p = i/k of Gamma(shape = alpha, scale = alpha), so rates[0] = 0;
  * mode 1 = what lib/mlModel.mli:12 documents: Yang's (1994) class means of Gamma(alpha, rate alpha),
  * average 1. probs (may be NULL) = 1/k each. Host-side, self-contained incomplete-gamma code. */
 int phylo_gamma_rates(double alpha, int k, int mode, double *rates, double *probs);
+/* Replace compose_sym / compose_gtr (lib/mlmodel.c:280-302, :325-342; lib/mlModel.ml:83-90):
+ * P = exp(Q t) from the eigensystem, computed by the pt_build kernel. Same special cases:
+ * t == -1.0 -> Q; t < 1e-10 -> I; compose_sym rounds t to float first (mlmodel.c:280).
+ * D is the full n*n matrix. P_out: n*n host buffer. */
 int phylo_compose_sym(phylo_engine *e, const double *U, const double *D, double t, int n,
                       double *P_out);
 int phylo_compose_gtr(phylo_engine *e, const double *U, const double *D, const double *Ui,
@@ -151,10 +151,29 @@ int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int 
  * repacking the alignment on the host. */
 int phylo_lk_set_tips_pitched(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
                               uint64_t host_pitch_bytes, const double *weights, int capacity);
+/* Node-slot lifetime. NodeData.S is functional: every median_2 returns a NEW node value and the old
+ * ones die with the OCaml GC. The reference ties native node data to the GC with a custom block
+ * whose finalizer frees it (lib/bitvector/bv.c:183-189 bv_CAML_free, :229-244 the ops table); here
+ * the custom block (stubs/phylo_stubs.c, `node`) holds a slot taken with phylo_lk_node_alloc and its
+ * finalizer calls phylo_lk_node_release. A released slot keeps its device buffer and is handed out
+ * again first, so a tree search allocates no device memory in steady state; when every slot is
+ * live the slot table grows (total slots double; phylo_lk_node_stats reports it). `generation`
+ * identifies the loaded alignment: releasing a slot of an alignment that has since been replaced
+ * (another shape / alphabet: every slot was dropped) is a no-op, so late finalizers are harmless.
+ * Callers that name slots themselves in a schedule (bench, tests) need none of this. */
+int phylo_lk_node_alloc(phylo_engine *e, int *slot_out, uint64_t *generation_out);
+int phylo_lk_node_release(phylo_engine *e, int slot, uint64_t generation);
+/* any pointer may be NULL. capacity: interior slots in the table (total slots - T); in_use: slots
+ * currently handed out; with_buffers: interior slots that own a device CLV buffer (live or pooled) */
+int phylo_lk_node_stats(phylo_engine *e, int *capacity, int *in_use, int *with_buffers);
 /* Likelihood.median_2 (lib/nodeData.ml:21, lib/likelihood_c.ml:15): CLV of `parent` from its
  * two children with per-site rescaling. */
 int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int right,
                       double t_right);
+/* Likelihood.median_3 (lib/nodeData.ml:22; TODO in lib/likelihood_c.ml:16): the CLV of a node given all
+ * three neighbours, (P_a L_a) o (P_b L_b) o (P_c L_c), rescaled like median_2. Uses the edge sum
+ * table's buffer as scratch (a prepared edge must be re-prepared). */
+int phylo_lk_median_3(phylo_engine *e, int parent, int a, double t_a, int b, double t_b, int c, double t_c);
 /* Whole-tree entry point: run the schedule, join across the root edge (a,b) of length
  * root_t, return lnL. Every interior CLV stays resident in its slot for later
  * phylo_lk_edge_lnl / phylo_lk_get_clv / incremental re-scoring. */
@@ -228,16 +247,28 @@ int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n
 int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
                                  const void *codes, uint64_t host_pitch_bytes, const double *weights,
                                  int capacity);
+/* node-slot lifetime for the state sets: same contract as phylo_lk_node_alloc / _release / _stats
+ * (what bv_CAML_free, lib/bitvector/bv.c:183-189, does for a `vect`) */
+int phylo_fitch_node_alloc(phylo_engine *e, int *slot_out, uint64_t *generation_out);
+int phylo_fitch_node_release(phylo_engine *e, int slot, uint64_t generation);
+int phylo_fitch_node_stats(phylo_engine *e, int *capacity, int *in_use, int *with_buffers);
 /* NonAdditive.median_2 (lib/nonAdditive_c.ml:19-35) == bv_fitch (lib/bitvector/bv.c:148-160;
  * stub bv_CAML_fitch_median2 :463-480): parent set + cost of this node alone. */
 int phylo_fitch_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *cost_out);
+/* NonAdditive.median_3 (lib/nodeData.ml:22; only sketched in the reference: the commented-out
+ * bv_CAML_fitch_median3(vb0, vb1, vb2, vb3) of lib/bitvector/bv.h:94): final state set of a node from
+ * its own preliminary set `prelim`, its parent's final set and its children's preliminary sets
+ * (Fitch's second pass, the rule phylo_fitch_uppass applies to the whole tree). Written to `dst`
+ * as an ordinary node value. */
+int phylo_fitch_median_3(phylo_engine *e, int dst, int prelim, int parent_final, int left, int right);
 /* bv_distance (lib/bitvector/bv.c:46-55; stub :455-461) */
 int phylo_fitch_distance(phylo_engine *e, int a, int b, uint64_t *dist_out);
 /* Whole-tree down-pass: sum of interior median costs + root-edge distance. */
 int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a,
                            int root_b, uint64_t *length_out);
-/* per-node costs of the last score_tree (capacity uint64; Node.cost is node-local,
- * lib/node.ml:191) */
+/* per-node costs of the last score_tree (one uint64 per slot: `capacity` of them, or what
+ * phylo_fitch_node_stats reports (+ T) once phylo_fitch_node_alloc has grown the table; Node.cost is
+ * node-local, lib/node.ml:191) */
 int phylo_fitch_get_node_costs(phylo_engine *e, uint64_t *out);
 /* Up-pass / final state sets (Node.final_states, lib/node.ml:260-268 -- TODO in the
  * reference; rule in DESIGN.md). Requires a preceding down-pass over the same schedule. */
@@ -274,6 +305,8 @@ int phylo_bv_popcount(phylo_engine *e, int a, uint64_t *out);
 int phylo_bv_saturation(phylo_engine *e, int a, uint64_t state_mask, uint64_t *out);
 int phylo_bv_poly_saturation(phylo_engine *e, int a, int n, uint64_t *out);
 int phylo_bv_compare(phylo_engine *e, int a, int b, int *out);
+/* bv_eltcount (lib/bitvector/bv.c:59-69): states in the set of character i */
+int phylo_bv_eltcount(phylo_engine *e, int a, int64_t i, int *out);
 
 /* --------------------------------------- several GPUs behind one handle (one process) ---- */
 /* The reference is a single OCaml process (no threads: no caml_enter_blocking_section anywhere under lib/),

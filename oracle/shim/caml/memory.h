@@ -16,4 +16,5 @@
 #define CAMLlocal3(a,b,c)         value a = 0, b = 0, c = 0
 #define CAMLreturn(x)             return (x)
 #define CAMLreturn0               return
+#define CAMLreturnT(type, x)      return (x)
 #endif

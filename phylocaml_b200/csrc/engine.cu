@@ -124,6 +124,12 @@ struct phylo_engine {
   void *dInv = nullptr;   // N masks: AND over tips
   double *dWeights = nullptr;
   std::vector<LkNode> nodes;
+  // node-slot allocator behind phylo_lk_node_alloc / _release (the OCaml custom blocks' finalizers
+  // return slots here): released slots keep their device buffers, so a search loop does no cudaMalloc
+  std::vector<char> lkOwned;
+  std::vector<int> lkFree;
+  int lkNext = 0, cap0 = 0;        // next never-used slot; the capacity the caller asked for
+  uint64_t lkGen = 0;              // bumped whenever every slot is dropped (new alignment shape / model alphabet)
   double *dP = nullptr;  // transition matrices [branch][K][S][S]
   size_t capP = 0;       // branches
   double *dT = nullptr, *hT = nullptr;  // branch lengths (device / pinned)
@@ -144,6 +150,12 @@ struct phylo_engine {
   int fT = 0, fcap = 0, fNP = 0, fNPdev = 0, felt = 1;
   int64_t fN = 0, fWords = 0;
   std::vector<uint32_t *> fPre, fFin;
+  std::vector<char> fValid;        // slot holds preliminary sets of the LOADED alignment (not a stale buffer)
+  std::vector<char> fFinValid;     // same for the final (up-pass) sets
+  std::vector<char> fOwned;        // allocator state, as for the likelihood slots
+  std::vector<int> fFreeList;
+  int fNext = 0, fcap0 = 0;
+  uint64_t fGen = 0;
   uint32_t **dPreTab = nullptr, **dFinTab = nullptr;
   bool tabDirty = true;
   uint32_t *dFW = nullptr;  // integer weights, padded to fWords*32
@@ -304,6 +316,8 @@ static void lk_free_data(phylo_engine *e) {
   dfree(e->dGroups);
   dfree(e->dPart2);
   e->T = 0; e->N = 0; e->cap = 0; e->lk_evaluated = false;
+  e->lkOwned.clear(); e->lkFree.clear(); e->lkNext = 0; e->cap0 = 0;
+  ++e->lkGen;  // slots handed out so far are gone: late releases of them are ignored
 }
 
 static void fitch_free_data(phylo_engine *e) {
@@ -315,6 +329,8 @@ static void fitch_free_data(phylo_engine *e) {
   dfree(e->dFinTab);
   dfree(e->dFW);
   e->fT = 0; e->fN = 0; e->fcap = 0;
+  e->fValid.clear(); e->fFinValid.clear(); e->fOwned.clear(); e->fFreeList.clear(); e->fNext = 0; e->fcap0 = 0;
+  ++e->fGen;
 }
 
 extern "C" void phylo_engine_destroy(phylo_engine *e) {
@@ -584,7 +600,7 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
     return fail(e, PHYLO_ERR_ARG, "%s: %d-bit masks cannot hold %d states", who, mask_bytes * 8, e->S);
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
-  const bool reuse = e->dTips && e->T == T && e->N == N && e->cap == capacity &&
+  const bool reuse = e->dTips && e->T == T && e->N == N && e->cap0 == capacity &&
                      e->mask_dev_bytes == dev_mask_bytes(e->S) && (weights != nullptr) == (e->dWeights != nullptr);
   const size_t cells = (size_t)T * N;
   if (reuse) {
@@ -593,13 +609,16 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
     e->edge_ready = false;
   } else {
     lk_free_data(e);
-    e->T = T; e->N = N; e->cap = capacity;
+    e->T = T; e->N = N; e->cap = capacity; e->cap0 = capacity;
     e->mask_dev_bytes = dev_mask_bytes(e->S);
     e->nodes.assign(capacity, LkNode());
+    e->lkOwned.assign(capacity, 0);
+    e->lkFree.clear();
+    e->lkNext = T;
     e->tipStride = ((N + kLnlBlock - 1) / kLnlBlock) * kLnlBlock;
     CK(cudaMalloc(&e->dTips, (size_t)T * e->tipStride * e->mask_dev_bytes));
     // padding cells read as "all states" (never used in a sum, but keeps them harmless)
-    CK(cudaMemset(e->dTips, 0xff, (size_t)T * e->tipStride * e->mask_dev_bytes));
+    CK(cudaMemsetAsync(e->dTips, 0xff, (size_t)T * e->tipStride * e->mask_dev_bytes, e->stream));
     if (e->S == 4) CK(cudaMalloc(&e->dTips4, (size_t)T * e->tipStride / 2));
     CK(cudaMalloc(&e->dNodeClv, sizeof(double *) * capacity));
     CK(cudaMalloc(&e->dNodeSc, sizeof(int32_t *) * capacity));
@@ -696,6 +715,77 @@ static int lk_ensure_node(phylo_engine *e, int slot) {
   CK(cudaMalloc(&n.scale, sizeof(int32_t) * (size_t)e->N));
   e->nodeTabDirty = true;
   e->tmapDirty = true;
+  return PHYLO_OK;
+}
+
+// ---- node-slot lifetime (the drop-in's answer to the reference's custom blocks with a finalizer,
+// lib/bitvector/bv.c:183-189,229-244: a node value owns native memory and gives it back when the GC
+// collects it). Slots T..cap-1 name interior nodes; alloc hands out a released slot first (its CLV
+// buffer is still attached), then a never-used one, and only then grows the slot table.
+static int lk_grow_slots(phylo_engine *e, int new_cap) {
+  CK(cudaStreamSynchronize(e->stream));
+  double **nclv = nullptr;
+  int32_t **nsc = nullptr;
+  CUtensorMap *ntm = nullptr;
+  if (cudaMalloc(&nclv, sizeof(double *) * new_cap) != cudaSuccess || cudaMalloc(&nsc, sizeof(int32_t *) * new_cap) != cudaSuccess ||
+      cudaMalloc(&ntm, sizeof(CUtensorMap) * new_cap) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(nclv); cudaFree(nsc); cudaFree(ntm);
+    return fail(e, PHYLO_ERR_CUDA, "lk_node_alloc: cannot grow the slot tables to %d slots", new_cap);
+  }
+  dfree(e->dNodeClv); dfree(e->dNodeSc); dfree(e->dTmaps);
+  e->dNodeClv = nclv; e->dNodeSc = nsc; e->dTmaps = ntm;
+  e->nodes.resize(new_cap);
+  e->lkOwned.resize(new_cap, 0);
+  e->cap = new_cap;
+  e->nodeTabDirty = true;
+  e->tmapDirty = true;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_node_alloc(phylo_engine *e, int *slot_out, uint64_t *generation_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!slot_out) return fail(e, PHYLO_ERR_ARG, "lk_node_alloc: slot_out is NULL");
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_node_alloc: no tips loaded");
+  CK(cudaSetDevice(e->device));
+  int slot = -1;
+  if (!e->lkFree.empty()) {
+    slot = e->lkFree.back();
+    e->lkFree.pop_back();
+  } else {
+    while (e->lkNext < e->cap && (e->lkOwned[e->lkNext] || e->nodes[e->lkNext].valid)) ++e->lkNext;  // slots a schedule named directly
+    if (e->lkNext >= e->cap) {
+      const int rc = lk_grow_slots(e, std::max(e->cap * 2, e->cap + 16));
+      if (rc != PHYLO_OK) return rc;
+    }
+    slot = e->lkNext++;
+  }
+  e->lkOwned[slot] = 1;
+  e->nodes[slot].valid = false;
+  *slot_out = slot;
+  if (generation_out) *generation_out = e->lkGen;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_node_release(phylo_engine *e, int slot, uint64_t generation) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (generation != e->lkGen) return PHYLO_OK;  // the alignment this slot belonged to is gone already
+  if (slot < e->T || slot >= e->cap || !e->lkOwned[slot])
+    return fail(e, PHYLO_ERR_ARG, "lk_node_release: slot %d was not handed out by phylo_lk_node_alloc", slot);
+  e->lkOwned[slot] = 0;
+  e->nodes[slot].valid = false;
+  if (e->edge_a == slot || e->edge_b == slot) e->edge_ready = false;
+  e->lkFree.push_back(slot);
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_node_stats(phylo_engine *e, int *capacity, int *in_use, int *with_buffers) {
+  if (!e) return PHYLO_ERR_ARG;
+  int used = 0, buf = 0;
+  for (int s = e->T; s < e->cap; ++s) { used += e->lkOwned[s] != 0; buf += e->nodes[s].clv != nullptr; }
+  if (capacity) *capacity = e->cap - e->T;
+  if (in_use) *in_use = used;
+  if (with_buffers) *with_buffers = buf;
   return PHYLO_OK;
 }
 
@@ -1327,7 +1417,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   if (fuse) {
     if (!e->dTreeDone) {
       CK(cudaMalloc(&e->dTreeDone, sizeof(unsigned int)));
-      CK(cudaMemset(e->dTreeDone, 0, sizeof(unsigned int)));
+      CK(cudaMemsetAsync(e->dTreeDone, 0, sizeof(unsigned int), e->stream));
     }
     fargs.fuse_reduce = 1;
     fargs.n_part = e->nPart;
@@ -1480,6 +1570,41 @@ extern "C" int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t
   const size_t pk = (size_t)e->K * e->S * e->S;
   rc = lk_launch_prune(e, e->dP, e->dP + pk, l, r, e->nodes[parent].clv, e->nodes[parent].scale);
   if (rc != PHYLO_OK) return rc;
+  e->nodes[parent].valid = true;
+  return PHYLO_OK;
+}
+
+// Likelihood.median_3 (lib/nodeData.ml:22; `failwith "TODO"` in lib/likelihood_c.ml:16): the node's CLV
+// conditioned on all THREE neighbours, L_p = (P_a L_a) o (P_b L_b) o (P_c L_c), with the same per-site
+// rescaling. Two ordinary pruning updates: (a, b) into the engine's scratch CLV, then (scratch over a
+// zero-length branch -- compose's t < 1e-10 -> identity, lib/mlmodel.c:339-341 -- , c) into `parent`.
+extern "C" int phylo_lk_median_3(phylo_engine *e, int parent, int a, double t_a, int b, double t_b, int c, double t_c) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_median_3: no tips loaded");
+  if (parent < e->T || parent >= e->cap)
+    return fail(e, PHYLO_ERR_ARG, "lk_median_3: parent slot %d must be in [%d,%d)", parent, e->T, e->cap);
+  if (parent == a || parent == b || parent == c) return fail(e, PHYLO_ERR_ARG, "lk_median_3: parent aliases a neighbour");
+  CK(cudaSetDevice(e->device));
+  Operand oa, ob, oc;
+  int rc;
+  if ((rc = lk_operand(e, a, &oa, "lk_median_3")) != PHYLO_OK) return rc;
+  if ((rc = lk_operand(e, b, &ob, "lk_median_3")) != PHYLO_OK) return rc;
+  if ((rc = lk_operand(e, c, &oc, "lk_median_3")) != PHYLO_OK) return rc;
+  if ((rc = ensure_pt_capacity(e, 4, e->S, e->K)) != PHYLO_OK) return rc;
+  if ((rc = lk_ensure_node(e, parent)) != PHYLO_OK) return rc;
+  if (!e->dSum) {
+    CK(cudaMalloc(&e->dSum, sizeof(double) * (size_t)e->N * e->K * e->S));
+    CK(cudaMalloc(&e->dSumSc, sizeof(int32_t) * (size_t)e->N));
+  }
+  e->edge_ready = false;  // the scratch CLV is the edge sum table's buffer
+  CK(cudaStreamSynchronize(e->stream));  // hT is about to be rewritten
+  e->hT[0] = t_a; e->hT[1] = t_b; e->hT[2] = 0.0; e->hT[3] = t_c;
+  if ((rc = build_pt(e, 4)) != PHYLO_OK) return rc;
+  const size_t pk = (size_t)e->K * e->S * e->S;
+  if ((rc = lk_launch_prune(e, e->dP, e->dP + pk, oa, ob, e->dSum, e->dSumSc)) != PHYLO_OK) return rc;
+  Operand tmp{e->dSum, e->dSumSc, false};
+  if ((rc = lk_launch_prune(e, e->dP + 2 * pk, e->dP + 3 * pk, tmp, oc, e->nodes[parent].clv, e->nodes[parent].scale)) != PHYLO_OK)
+    return rc;
   e->nodes[parent].valid = true;
   return PHYLO_OK;
 }
@@ -2087,13 +2212,21 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   // same shape as what is loaded: keep the plane buffers and tables, refresh contents only
-  const bool reuse = e->fT == T && e->fN == N && e->fcap == capacity && e->felt == elt_bytes &&
+  const bool reuse = e->fT == T && e->fN == N && e->fcap0 == capacity && e->felt == elt_bytes &&
                      e->fNP == n_states && e->dPreTab && (weights != nullptr) == (e->dFW != nullptr);
   if (reuse) {
+    // the plane buffers stay allocated but what they hold belongs to the previous alignment
     std::fill(e->nodeCost.begin(), e->nodeCost.end(), 0);
+    std::fill(e->fValid.begin(), e->fValid.end(), 0);
+    std::fill(e->fFinValid.begin(), e->fFinValid.end(), 0);
   } else {
     fitch_free_data(e);
-    e->fT = T; e->fN = N; e->fcap = capacity; e->felt = elt_bytes; e->fNP = n_states;
+    e->fT = T; e->fN = N; e->fcap = capacity; e->fcap0 = capacity; e->felt = elt_bytes; e->fNP = n_states;
+    e->fValid.assign(capacity, 0);
+    e->fFinValid.assign(capacity, 0);
+    e->fOwned.assign(capacity, 0);
+    e->fFreeList.clear();
+    e->fNext = T;
     e->fNPdev = np_device(n_states);
     e->fWords = (N + 31) / 32;
     e->fPre.assign(capacity, nullptr);
@@ -2164,13 +2297,85 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
     if (!e->dFW) CK(cudaMalloc(&e->dFW, sizeof(uint32_t) * hw.size()));
     CK(cudaMemcpy(e->dFW, hw.data(), sizeof(uint32_t) * hw.size(), cudaMemcpyHostToDevice));
   }
+  for (int t = 0; t < T; ++t) e->fValid[t] = 1;
+  return PHYLO_OK;
+}
+
+// node-slot lifetime for the Fitch / bitvector sets: same contract as phylo_lk_node_alloc / _release
+static int fitch_grow_slots(phylo_engine *e, int new_cap) {
+  CK(cudaStreamSynchronize(e->stream));
+  uint32_t **np = nullptr, **nf = nullptr;
+  if (cudaMalloc(&np, sizeof(uint32_t *) * new_cap) != cudaSuccess || cudaMalloc(&nf, sizeof(uint32_t *) * new_cap) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(np); cudaFree(nf);
+    return fail(e, PHYLO_ERR_CUDA, "fitch_node_alloc: cannot grow the slot tables to %d slots", new_cap);
+  }
+  dfree(e->dPreTab); dfree(e->dFinTab);
+  e->dPreTab = np; e->dFinTab = nf;
+  e->fPre.resize(new_cap, nullptr);
+  e->fFin.resize(new_cap, nullptr);
+  e->fValid.resize(new_cap, 0);
+  e->fFinValid.resize(new_cap, 0);
+  e->fOwned.resize(new_cap, 0);
+  e->nodeCost.resize(new_cap, 0);
+  e->fcap = new_cap;
+  e->tabDirty = true;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_node_alloc(phylo_engine *e, int *slot_out, uint64_t *generation_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (!slot_out) return fail(e, PHYLO_ERR_ARG, "fitch_node_alloc: slot_out is NULL");
+  if (e->fT == 0) return fail(e, PHYLO_ERR_STATE, "fitch_node_alloc: no Fitch data loaded");
+  CK(cudaSetDevice(e->device));
+  int slot = -1;
+  if (!e->fFreeList.empty()) {
+    slot = e->fFreeList.back();
+    e->fFreeList.pop_back();
+  } else {
+    while (e->fNext < e->fcap && (e->fOwned[e->fNext] || e->fValid[e->fNext])) ++e->fNext;  // slots a schedule named directly
+    if (e->fNext >= e->fcap) {
+      const int rc = fitch_grow_slots(e, std::max(e->fcap * 2, e->fcap + 16));
+      if (rc != PHYLO_OK) return rc;
+    }
+    slot = e->fNext++;
+  }
+  e->fOwned[slot] = 1;
+  e->fValid[slot] = 0;
+  e->fFinValid[slot] = 0;
+  e->nodeCost[slot] = 0;
+  *slot_out = slot;
+  if (generation_out) *generation_out = e->fGen;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_node_release(phylo_engine *e, int slot, uint64_t generation) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (generation != e->fGen) return PHYLO_OK;  // the alignment this slot belonged to is gone already
+  if (slot < e->fT || slot >= e->fcap || !e->fOwned[slot])
+    return fail(e, PHYLO_ERR_ARG, "fitch_node_release: slot %d was not handed out by phylo_fitch_node_alloc", slot);
+  e->fOwned[slot] = 0;
+  e->fValid[slot] = 0;
+  e->fFinValid[slot] = 0;
+  e->fFreeList.push_back(slot);
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_fitch_node_stats(phylo_engine *e, int *capacity, int *in_use, int *with_buffers) {
+  if (!e) return PHYLO_ERR_ARG;
+  int used = 0, buf = 0;
+  for (int s = e->fT; s < e->fcap; ++s) { used += e->fOwned[s] != 0; buf += e->fPre[s] != nullptr; }
+  if (capacity) *capacity = e->fcap - e->fT;
+  if (in_use) *in_use = used;
+  if (with_buffers) *with_buffers = buf;
   return PHYLO_OK;
 }
 
 static int fitch_slot_ok(phylo_engine *e, int slot, bool need_data, const char *who) {
   if (e->fT == 0) return fail(e, PHYLO_ERR_STATE, "%s: no Fitch data loaded", who);
   if (slot < 0 || slot >= e->fcap) return fail(e, PHYLO_ERR_ARG, "%s: node slot %d out of range [0,%d)", who, slot, e->fcap);
-  if (need_data && !e->fPre[slot]) return fail(e, PHYLO_ERR_STATE, "%s: node slot %d holds no state sets", who, slot);
+  if (need_data && (!e->fPre[slot] || !e->fValid[slot]))
+    return fail(e, PHYLO_ERR_STATE, "%s: node slot %d holds no state sets", who, slot);
   return PHYLO_OK;
 }
 
@@ -2201,7 +2406,7 @@ static int fitch_pair(phylo_engine *e, int parent, int left, int right, bool sto
   CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   if (out) *out = e->hCost[0];
-  if (store) e->nodeCost[parent] = e->hCost[0];
+  if (store) { e->nodeCost[parent] = e->hCost[0]; e->fValid[parent] = 1; e->fFinValid[parent] = 0; }
   return PHYLO_OK;
 }
 
@@ -2215,13 +2420,39 @@ extern "C" int phylo_fitch_distance(phylo_engine *e, int a, int b, uint64_t *dis
   return fitch_pair(e, -1, a, b, false, dist_out);
 }
 
+// NonAdditive.median_3 (lib/nodeData.ml:22): final state set of a node from its parent's final set and
+// the preliminary sets of the node itself and its two children (rule: fitch_final_rule). The result is
+// written into dst's preliminary buffer, i.e. it is a node value like any other.
+extern "C" int phylo_fitch_median_3(phylo_engine *e, int dst, int prelim, int parent_final, int left, int right) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  for (int s : {prelim, parent_final, left, right})
+    if ((rc = fitch_slot_ok(e, s, true, "fitch_median_3")) != PHYLO_OK) return rc;
+  if ((rc = fitch_slot_ok(e, dst, false, "fitch_median_3")) != PHYLO_OK) return rc;
+  if (dst < e->fT) return fail(e, PHYLO_ERR_ARG, "fitch_median_3: dst slot %d is a tip", dst);
+  if (dst == prelim || dst == parent_final || dst == left || dst == right)
+    return fail(e, PHYLO_ERR_ARG, "fitch_median_3: dst aliases an operand");
+  CK(cudaSetDevice(e->device));
+  if ((rc = fitch_ensure(e, dst, false)) != PHYLO_OK) return rc;
+  const int g = grid_for(e->fWords, 256, e->sm_count * 8);
+  {
+    ProfScope prof(e, KC_FITCH_UPPASS);
+    NP_DISPATCH(e->fNPdev, (fitch_final1_kernel<NP><<<g, 256, 0, e->stream>>>(e->fPre[prelim], e->fPre[parent_final], e->fPre[left],
+                                                                              e->fPre[right], e->fPre[dst], e->fWords)));
+    LAUNCH_CHECK();
+  }
+  e->fValid[dst] = 1;
+  e->fFinValid[dst] = 0;
+  e->nodeCost[dst] = 0;
+  return PHYLO_OK;
+}
+
 static int fitch_check_schedule(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                                 const char *who) {
   if (e->fT == 0) return fail(e, PHYLO_ERR_STATE, "%s: no Fitch data loaded", who);
   if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(e, PHYLO_ERR_ARG, "%s: bad arguments", who);
   std::vector<char> ready(e->fcap, 0);
-  for (int s = 0; s < e->fcap; ++s) ready[s] = e->fPre[s] != nullptr && (s < e->fT);
-  for (int s = e->fT; s < e->fcap; ++s) ready[s] = e->fPre[s] != nullptr;  // earlier medians stay usable
+  for (int s = 0; s < e->fcap; ++s) ready[s] = e->fPre[s] != nullptr && e->fValid[s];  // earlier medians stay usable
   for (int o = 0; o < n_ops; ++o) {
     const phylo_op &op = ops[o];
     if (op.parent < e->fT || op.parent >= e->fcap)
@@ -2314,7 +2545,7 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     e->capAcc = 0;
     const size_t cap = ((size_t)n_tot + 2) * 2;
     CK(cudaMalloc(&e->dAcc, sizeof(unsigned long long) * cap * kFitchAccCopies));
-    CK(cudaMemset(e->dAcc, 0, sizeof(unsigned long long) * cap * kFitchAccCopies));
+    CK(cudaMemsetAsync(e->dAcc, 0, sizeof(unsigned long long) * cap * kFitchAccCopies, e->stream));
     e->capAcc = cap;
   }
   const bool inl = blob - 64 <= (size_t)kFitchInlineProg;
@@ -2386,7 +2617,7 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     std::atomic_thread_fence(std::memory_order_acquire);
   }
   *length_out = e->hCost[n_tot];
-  for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[pos[o]];
+  for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = e->hCost[pos[o]]; e->fValid[ops[o].parent] = 1; e->fFinValid[ops[o].parent] = 0; }
   if (e->prof_on) prof_resolve_lazy(e);
   *done = true;
   return PHYLO_OK;
@@ -2466,7 +2697,7 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
     CK(cudaStreamSynchronize(e->stream));
     *length_out = e->hCost[n_ops + 1];
     for (int i = 0; i < ns; ++i)
-      if (pl.steps[i].out_slot >= 0) e->nodeCost[pl.steps[i].out_slot] = e->hCost[i];
+      if (pl.steps[i].out_slot >= 0) { e->nodeCost[pl.steps[i].out_slot] = e->hCost[i]; e->fValid[pl.steps[i].out_slot] = 1; e->fFinValid[pl.steps[i].out_slot] = 0; }
     if (e->prof_on) prof_resolve_lazy(e);
     return PHYLO_OK;
   }
@@ -2487,7 +2718,7 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
                      e->stream));
   CK(cudaStreamSynchronize(e->stream));
   *length_out = e->hCost[n_ops + 1];
-  for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[o];
+  for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = e->hCost[o]; e->fValid[ops[o].parent] = 1; e->fFinValid[ops[o].parent] = 0; }
   if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }
@@ -2568,7 +2799,7 @@ extern "C" int phylo_tcm_median_2(phylo_engine *e, int parent, int left, int rig
   CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   if (cost_out) *cost_out = e->hCost[0];
-  if (parent >= 0) e->nodeCost[parent] = e->hCost[0];
+  if (parent >= 0) { e->nodeCost[parent] = e->hCost[0]; e->fValid[parent] = 1; e->fFinValid[parent] = 0; }
   return PHYLO_OK;
 }
 
@@ -2592,7 +2823,7 @@ extern "C" int phylo_tcm_score_tree(phylo_engine *e, const phylo_op *ops, int n_
   CK(cudaStreamSynchronize(e->stream));
   uint64_t total = 0;
   for (int o = 0; o <= n_ops; ++o) total += e->hCost[o];
-  for (int o = 0; o < n_ops; ++o) e->nodeCost[ops[o].parent] = e->hCost[o];
+  for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = e->hCost[o]; e->fValid[ops[o].parent] = 1; e->fFinValid[ops[o].parent] = 0; }
   *length_out = total;
   if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
@@ -2644,6 +2875,7 @@ extern "C" int phylo_fitch_uppass(phylo_engine *e, const phylo_op *ops, int n_op
     LAUNCH_CHECK();
   }
   CK(cudaStreamSynchronize(e->stream));
+  for (int o = 0; o < n_ops; ++o) e->fFinValid[ops[o].parent] = 1;
   return PHYLO_OK;
 }
 
@@ -2653,8 +2885,9 @@ extern "C" int phylo_fitch_get_states(phylo_engine *e, int node, int which, void
   if ((rc = fitch_slot_ok(e, node, true, "fitch_get_states")) != PHYLO_OK) return rc;
   if (!out) return fail(e, PHYLO_ERR_ARG, "fitch_get_states: out is NULL");
   // leaves keep their observed sets as final sets
-  const uint32_t *src = (which == 1 && e->fFin[node]) ? e->fFin[node] : e->fPre[node];
-  if (which == 1 && !e->fFin[node] && node >= e->fT)
+  const bool have_fin = e->fFin[node] && e->fFinValid[node];
+  const uint32_t *src = (which == 1 && have_fin) ? e->fFin[node] : e->fPre[node];
+  if (which == 1 && !have_fin && node >= e->fT)
     return fail(e, PHYLO_ERR_STATE, "fitch_get_states: no final sets for node %d (run fitch_uppass)", node);
   CK(cudaSetDevice(e->device));
   const size_t row = (size_t)e->fN * e->felt;
@@ -2689,6 +2922,8 @@ extern "C" int phylo_fitch_set_states(phylo_engine *e, int node, const void *cod
   CK(cudaMemcpyAsync(e->dStage, codes, row, cudaMemcpyHostToDevice, e->stream));
   if ((rc = fitch_encode(e, e->dStage, e->fPre[node], e->dCost, false)) != PHYLO_OK) return rc;  // codes, never symbols
   CK(cudaStreamSynchronize(e->stream));
+  e->fValid[node] = 1;
+  e->fFinValid[node] = 0;
   return PHYLO_OK;
 }
 
@@ -2706,6 +2941,8 @@ static int bv_binop(phylo_engine *e, int dst, int a, int b, bool is_union) {
   if (is_union) bv_binop_kernel<true><<<g, 256, 0, e->stream>>>(e->fPre[a], e->fPre[b], e->fPre[dst], n);
   else bv_binop_kernel<false><<<g, 256, 0, e->stream>>>(e->fPre[a], e->fPre[b], e->fPre[dst], n);
   LAUNCH_CHECK();
+  e->fValid[dst] = 1;
+  e->fFinValid[dst] = 0;
   return PHYLO_OK;
 }
 
@@ -2748,6 +2985,22 @@ extern "C" int phylo_bv_poly_saturation(phylo_engine *e, int a, int n, uint64_t 
     return PHYLO_OK;
   }
   return bv_count(e, a, 2, 0, n, out, "bv_poly_saturation");
+}
+
+// bv_eltcount (lib/bitvector/bv.c:59-69): number of states in the set of character i
+extern "C" int phylo_bv_eltcount(phylo_engine *e, int a, int64_t i, int *out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = fitch_slot_ok(e, a, true, "bv_eltcount")) != PHYLO_OK) return rc;
+  if (!out || i < 0 || i >= e->fN) return fail(e, PHYLO_ERR_ARG, "bv_eltcount: character %lld out of range", (long long)i);
+  CK(cudaSetDevice(e->device));
+  std::vector<uint32_t> pl(e->fNPdev);
+  CK(cudaMemcpyAsync(pl.data(), e->fPre[a] + (i / 32) * e->fNPdev, sizeof(uint32_t) * e->fNPdev, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  int n = 0;
+  for (int s = 0; s < e->fNPdev; ++s) n += (pl[s] >> (i % 32)) & 1u;
+  *out = n;
+  return PHYLO_OK;
 }
 
 extern "C" int phylo_bv_compare(phylo_engine *e, int a, int b, int *out) {

@@ -458,6 +458,44 @@ struct FitchUpStep {
   int node, parent, left, right;
 };
 
+// Final-state rule of Fitch's second pass for one node (verified against exhaustive
+// MPR sets in tests/golden/fitch_bruteforce.json): A = parent's final set, P = the node's own
+// preliminary set, L / R = the children's preliminary sets.
+//   A subset of P            -> A
+//   else L & R empty (union) -> P | A
+//   else                     -> P | (A & (L | R))
+template <int NP>
+__device__ __forceinline__ Planes<NP> fitch_final_rule(const Planes<NP> &P, const Planes<NP> &A, const Planes<NP> &L,
+                                                       const Planes<NP> &R) {
+  uint32_t notsub = 0, lr = 0;
+#pragma unroll
+  for (int s = 0; s < NP; ++s) {
+    notsub |= A.v[s] & ~P.v[s];
+    lr |= L.v[s] & R.v[s];
+  }
+  Planes<NP> F;
+#pragma unroll
+  for (int s = 0; s < NP; ++s) {
+    const uint32_t f2 = P.v[s] | A.v[s];
+    const uint32_t f3 = P.v[s] | (A.v[s] & (L.v[s] | R.v[s]));
+    F.v[s] = (~notsub & A.v[s]) | (notsub & ((~lr & f2) | (lr & f3)));
+  }
+  return F;
+}
+
+// One node of the up-pass as its own kernel: NodeData.median_3 for the non-additive plugin (the
+// reference only sketches it: `bv_CAML_fitch_median3(vb0, vb1, vb2, vb3)` is commented out in
+// lib/bitvector/bv.h:94). P may alias nothing; out is a different buffer.
+template <int NP>
+__global__ void __launch_bounds__(256)
+fitch_final1_kernel(const uint32_t *__restrict__ P, const uint32_t *__restrict__ A, const uint32_t *__restrict__ L,
+                    const uint32_t *__restrict__ R, uint32_t *__restrict__ out, int64_t nwords) {
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+    const Planes<NP> p = ld_planes<NP>(P, w), a = ld_planes<NP>(A, w), l = ld_planes<NP>(L, w), r = ld_planes<NP>(R, w);
+    st_planes<NP>(out, w, fitch_final_rule<NP>(p, a, l, r));
+  }
+}
+
 template <int NP>
 __global__ void __launch_bounds__(128)
 fitch_uppass_kernel(uint32_t *const *__restrict__ prelim, uint32_t *const *__restrict__ fin,
@@ -475,20 +513,7 @@ fitch_uppass_kernel(uint32_t *const *__restrict__ prelim, uint32_t *const *__res
       const Planes<NP> P = ld_planes<NP>(prelim[st.node], w);
       const Planes<NP> L = ld_planes<NP>(prelim[st.left], w), R = ld_planes<NP>(prelim[st.right], w);
       const Planes<NP> A = st.parent < 0 ? rootset : ld_planes<NP>(fin[st.parent], w);
-      uint32_t notsub = 0, lr = 0;
-#pragma unroll
-      for (int s = 0; s < NP; ++s) {
-        notsub |= A.v[s] & ~P.v[s];
-        lr |= L.v[s] & R.v[s];
-      }
-      Planes<NP> F;
-#pragma unroll
-      for (int s = 0; s < NP; ++s) {
-        const uint32_t f2 = P.v[s] | A.v[s];
-        const uint32_t f3 = P.v[s] | (A.v[s] & (L.v[s] | R.v[s]));
-        F.v[s] = (~notsub & A.v[s]) | (notsub & ((~lr & f2) | (lr & f3)));
-      }
-      st_planes<NP>(fin[st.node], w, F);
+      st_planes<NP>(fin[st.node], w, fitch_final_rule<NP>(P, A, L, R));
     }
   }
 }

@@ -53,7 +53,16 @@ SIGNATURES = {
     "phylo_lk_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
     "phylo_lk_set_tips": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int]),
     "phylo_lk_set_tips_pitched": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_uint64, _dp, C.c_int]),
+    "phylo_lk_node_alloc": (C.c_int, [_vp, C.POINTER(C.c_int), _u64p]),
+    "phylo_lk_node_release": (C.c_int, [_vp, C.c_int, C.c_uint64]),
+    "phylo_lk_node_stats": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "phylo_fitch_node_alloc": (C.c_int, [_vp, C.POINTER(C.c_int), _u64p]),
+    "phylo_fitch_node_release": (C.c_int, [_vp, C.c_int, C.c_uint64]),
+    "phylo_fitch_node_stats": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "phylo_lk_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]),
+    "phylo_lk_median_3": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_double]),
+    "phylo_fitch_median_3": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "phylo_bv_eltcount": (C.c_int, [_vp, C.c_int, _i64, C.POINTER(C.c_int)]),
     "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_plan_compile": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
@@ -339,8 +348,29 @@ class Engine:
         self._ck(self.lib.phylo_lk_set_tips(self.h, T, N, _p(tips), tips.dtype.itemsize, _p(w, _dp), capacity))
         self.lk_shape = (T, N, capacity)
 
+    def node_alloc(self, fitch=False):
+        """(slot, generation) of a fresh interior node slot (phylo_lk_node_alloc / phylo_fitch_node_alloc)."""
+        slot, gen = C.c_int(), C.c_uint64()
+        fn = self.lib.phylo_fitch_node_alloc if fitch else self.lib.phylo_lk_node_alloc
+        self._ck(fn(self.h, C.byref(slot), C.byref(gen)))
+        return slot.value, gen.value
+
+    def node_release(self, slot, generation, fitch=False):
+        fn = self.lib.phylo_fitch_node_release if fitch else self.lib.phylo_lk_node_release
+        self._ck(fn(self.h, int(slot), int(generation)))
+
+    def node_stats(self, fitch=False):
+        """(interior slots in the table, slots handed out, interior slots owning a device buffer)."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        fn = self.lib.phylo_fitch_node_stats if fitch else self.lib.phylo_lk_node_stats
+        self._ck(fn(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def lk_median_2(self, parent, left, t_left, right, t_right):
         self._ck(self.lib.phylo_lk_median_2(self.h, parent, left, float(t_left), right, float(t_right)))
+
+    def lk_median_3(self, parent, a, t_a, b, t_b, c, t_c):
+        self._ck(self.lib.phylo_lk_median_3(self.h, parent, a, float(t_a), b, float(t_b), c, float(t_c)))
 
     def lk_score_tree(self, ops, root_a, root_b, root_t):
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
@@ -457,6 +487,14 @@ class Engine:
         self._ck(self.lib.phylo_fitch_median_2(self.h, parent, left, right, C.byref(out)))
         return out.value
 
+    def fitch_median_3(self, dst, prelim, parent_final, left, right):
+        self._ck(self.lib.phylo_fitch_median_3(self.h, dst, prelim, parent_final, left, right))
+
+    def bv_eltcount(self, a, i):
+        out = C.c_int()
+        self._ck(self.lib.phylo_bv_eltcount(self.h, a, int(i), C.byref(out)))
+        return out.value
+
     def fitch_distance(self, a, b):
         out = C.c_uint64()
         self._ck(self.lib.phylo_fitch_distance(self.h, a, b, C.byref(out)))
@@ -469,7 +507,7 @@ class Engine:
         return out.value
 
     def fitch_get_node_costs(self):
-        out = np.zeros(self.fitch_shape[2], dtype=np.uint64)
+        out = np.zeros(max(self.fitch_shape[2], self.node_stats(fitch=True)[0] + self.fitch_shape[0]), dtype=np.uint64)
         self._ck(self.lib.phylo_fitch_get_node_costs(self.h, _p(out, _u64p)))
         return out
 
