@@ -264,6 +264,21 @@ def build_tips(tree_mod, tr, model, T, n_local, S, lo=0):
     return tips
 
 
+def tile_cols(base, lo, n, out=None, unit=1):
+    """Columns [lo, lo + n) of `base` repeated for ever (both in units of `unit` base columns per
+    array column: packed layouts hold several alignment columns per element)."""
+    bn = base.shape[1]
+    if out is None:
+        out = np.empty((base.shape[0], n), dtype=base.dtype)
+    pos = 0
+    while pos < n:
+        off = (lo + pos) % bn
+        k = min(bn - off, n - pos)
+        out[:, pos:pos + k] = base[:, off:off + k]
+        pos += k
+    return out
+
+
 def fitch_tips(tree_mod, T, n_total, lo, n_local, pinned=True):
     """The global Fitch alignment is one random block of FITCH_BASE characters tiled to n_total; a
     rank holds columns [lo, lo + n_local) of it (one character per byte, the reference's W = 8
@@ -600,9 +615,25 @@ def run_workload(ctx, args, key, wl, primary):
     base = None
     if kind == "fitch":
         model = None
-        tips, base = fitch_tips(tree_mod, T, n_total, lo, n_local)
+        # the host alignment is kept in the engine's compact upload format: bit-sliced planes (0.5 B per
+        # DNA character; phylo_fitch_pack_planes), built from the tiled base block. The one-byte-per-character
+        # form (the reference's W = 8 layout) is only materialised for the CPU leg's sample.
+        base = tree_mod.random_fitch_chars(T, min(n_total, FITCH_BASE), 4, seed=5)
+        planes_base = engine.fitch_pack_planes(base, 4)          # T x (base/32 * 4) uint32
+        if args.upload == "compact" and (base.shape[1] % 32 == 0 or n_local <= base.shape[1]):
+            wpl = 4  # uint32 words per 32 characters
+            tips = engine.pinned_empty((T, ((n_local + 31) // 32) * wpl), np.uint32)
+            tile_cols(planes_base, (lo // 32) * wpl, tips.shape[1], out=tips)
+            set_tips = lambda: eng.fitch_set_tips_planes(tips, n_local, 4, capacity=n_nodes)
+            upload_note = "bit-sliced planes, 0.5 B per character (elt_bytes = 0)"
+        else:
+            tips = engine.pinned_empty((T, n_local), np.uint8)
+            tile_cols(base, lo, n_local, out=tips)
+            set_tips = lambda: eng.fitch_set_tips(tips, 4, capacity=n_nodes)
+            upload_note = "one byte per character (the reference's W = 8 layout), transcoded on the device"
+        sample_of = lambda ns: tile_cols(base, lo, ns)
         eng.set_option(eng.OPT_FITCH_WALK, {"auto": 1, "tile": 3, "regwalk": 2, "l2": 0}[args.fitch_kernel])
-        eng.fitch_set_tips(tips, 4, capacity=n_nodes)
+        set_tips()
         acc = torch.zeros(1, dtype=torch.int64, device="cuda")
 
         def step():
@@ -614,7 +645,7 @@ def run_workload(ctx, args, key, wl, primary):
             return v
 
         def e2e_step():
-            eng.fitch_set_tips(tips, 4, capacity=n_nodes)
+            set_tips()
             return step()
 
         metric, unit, dtype = "fitch_char_ops_per_s", "char-ops/s", "u32 (bit-sliced state planes)"
@@ -622,7 +653,19 @@ def run_workload(ctx, args, key, wl, primary):
         h2d = tips.nbytes
     else:
         model = make_model(wl)
-        tips = build_tips(tree_mod, tr, model, T, n_local, S, lo)
+        base = tree_mod.evolve_tips(tr, model, BASE_PATTERNS, seed=3, dtype=mask_dtype(S))
+        packed_n = None
+        if S == 4 and args.upload == "compact" and lo % 2 == 0:
+            # compact upload format: two 4-bit masks per byte (mask_bytes = 0; phylo_pack_nibbles)
+            tips = engine.pinned_empty((T, (n_local + 1) // 2), np.uint8)
+            tile_cols(engine.pack_nibbles(base), lo // 2, tips.shape[1], out=tips)
+            packed_n = n_local
+            upload_note = "packed 4-bit masks, 0.5 B per cell (mask_bytes = 0)"
+        else:
+            tips = engine.pinned_empty((T, n_local), mask_dtype(S))
+            tile_cols(base, lo, n_local, out=tips)
+            upload_note = "%d-byte state masks" % tips.dtype.itemsize
+        sample_of = lambda ns: tile_cols(base, lo, ns)
         eng.lk_set_model(model)
 
         def set_mode(m):
@@ -630,7 +673,7 @@ def run_workload(ctx, args, key, wl, primary):
             eng.set_option(eng.OPT_RETAIN_CLV, 0 if m == "fused-lnl" else 1)
 
         set_mode(mode)
-        eng.lk_set_tips(tips, capacity=n_nodes)
+        eng.lk_set_tips(tips, capacity=n_nodes, packed_n=packed_n)
         acc = torch.zeros(1, dtype=torch.float64, device="cuda")
 
         def step():
@@ -644,7 +687,7 @@ def run_workload(ctx, args, key, wl, primary):
         def e2e_step():
             # host buffers in, scalar out: upload (pinned -> HBM, overlapped slab by slab with
             # the scoring) + full evaluation + lnL read-back, through one C-ABI call
-            v = eng.lk_score_alignment(tips, ops, ra, rb, rt, capacity=n_nodes)
+            v = eng.lk_score_alignment(tips, ops, ra, rb, rt, capacity=n_nodes, packed_n=packed_n)
             if world > 1:
                 acc[0] = v
                 dist.all_reduce(acc)
@@ -652,7 +695,7 @@ def run_workload(ctx, args, key, wl, primary):
             return v
 
         metric, unit, dtype = "clv_site_updates_per_s", "site-updates/s", "f64"
-        kbytes = lk_bytes(T, S, K, tips.dtype.itemsize, mode)
+        kbytes = lk_bytes(T, S, K, mask_dtype(S)().itemsize, mode)
         h2d = tips.nbytes + ops.nbytes
     units_per_step = (T - 1) * n_total
 
@@ -815,14 +858,14 @@ def run_workload(ctx, args, key, wl, primary):
                     "inside this loop: consecutive evaluations re-read the same %.0f MB table, as the "
                     "optimiser's loop does" % (n_local * S * K * 8 / 1e6),
         }
-        eng.lk_set_tips(tips, capacity=n_nodes)
+        eng.lk_set_tips(tips, capacity=n_nodes, packed_n=packed_n)
         step()  # restore the unmodified tree's state
 
     # ---- CPU baseline + correctness check against the oracle (rank 0, N=1 only)
     cpu, check = None, {"result": result, "result_e2e": result_e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(wl["cpu_sample"], n_local)
-        sample = np.ascontiguousarray(tips[:, :ns])
+        sample = sample_of(ns)
         cpu, res = cpu_legs(wl, kind, ops, ra, rb, rt, n_nodes, model, sample, budget_s=8.0 if primary else 4.0)
         if kind == "fitch":
             check["oracle_length_of_sample"] = int(res["length"])
@@ -852,7 +895,7 @@ def run_workload(ctx, args, key, wl, primary):
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": workload_config(key, wl, n_total, n_local, world, l2_note, ctx.numa_note),
+            "config": dict(workload_config(key, wl, n_total, n_local, world, l2_note, ctx.numa_note), upload_format=upload_note),
             "mode": mode, "modes": modes,
             "roofline": (roof_tensor if roof_tensor and S > 32 else roof),
             "roofline_hbm": roof if roof_tensor and S > 32 else None,
@@ -880,6 +923,9 @@ def main():
     ap.add_argument("--taxa", type=int, default=0, help="override the headline's number of taxa")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--upload", default="compact", choices=["compact", "bytes"],
+                    help="host alignment format of the end-to-end leg: the engine's compact formats (packed 4-bit "
+                         "masks / bit-sliced planes) or one element per cell as the reference holds it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fused", choices=["fused", "fused-lnl", "pernode"],
                     help="likelihood path: tree-fused kernel keeping every CLV (default), tree-fused "

@@ -143,11 +143,17 @@ int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U, const dou
 /* Tip data: T taxa x N site patterns of state masks (bit i <=> state i possible,
  * lib/alphabet.ml:193-196), mask_bytes in {1,2,4,8} like the bitvector widths
  * (lib/bitvector/bv.h:29-55), tip-major. weights: N pattern weights or NULL (all 1).
- * capacity >= T: number of node slots. A mask with none of the low S bits set is rejected. */
+ * capacity >= T: number of node slots. A mask with none of the low S bits set is rejected.
+ * mask_bytes == 0 (4-state models only, no symbol table): PACKED input, two 4-bit masks per byte
+ * (pattern 2j in the low nibble of byte j), rows of ceil(N/2) bytes -- half the PCIe bytes of the
+ * one-byte form and no conversion pass on the device (the nibbles go straight into the tiles the
+ * tree-fused kernel reads). phylo_pack_nibbles is the host-side packer. */
 int phylo_lk_set_tips(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
                       const double *weights, int capacity);
+/* masks (T x N, one byte per cell, tip-major) -> packed (T rows of ceil(N/2) bytes). Host side. */
+int phylo_pack_nibbles(const uint8_t *masks, int T, int64_t N, uint8_t *packed);
 /* Same, for a column slab of a wider host matrix: consecutive taxon rows are host_pitch_bytes
- * apart (0 = N * mask_bytes). This is how phylo_group hands each device its shard without
+ * apart (0 = N * mask_bytes, or ceil(N/2) for packed input; a packed slab must start at an even pattern). This is how phylo_group hands each device its shard without
  * repacking the alignment on the host. */
 int phylo_lk_set_tips_pitched(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
                               uint64_t host_pitch_bytes, const double *weights, int capacity);
@@ -241,9 +247,19 @@ int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const void *masks
  * weights: N non-negative integer-valued doubles (lib/nonAdditive_c.ml:3) or NULL (all 1,
  * the bv_fitch case). On device the characters live bit-sliced (one 32-bit word per state
  * plane per 32 characters). An all-zero element is rejected. */
+/* elt_bytes == 0: `codes` already is that device layout -- per taxon ceil(N/32) words x NP planes of
+ * uint32 (NP = phylo_fitch_plane_count(n_states); DNA: 16 bytes per 32 characters = 0.5 B/char), rows
+ * ceil(N/32)*NP*4 bytes apart, as phylo_fitch_pack_planes writes it. The upload is then a plain copy
+ * into the node buffers plus one checking pass (no transcoding), and phylo_fitch_get_states returns
+ * sets in the narrowest element that holds n_states bits. */
 int phylo_fitch_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
                          const void *codes, const double *weights, int capacity);
-/* column slab of a wider host matrix, rows host_pitch_bytes apart (0 = N * elt_bytes) */
+/* host-side packer: reference layout (one character per element of elt_bytes) -> planes; and the plane
+ * count the device uses for n_states (one of 1,2,3,4,5,6,8,12,16,24,32,64) */
+int phylo_fitch_pack_planes(const void *codes, int elt_bytes, int n_states, int T, int64_t N, uint32_t *planes);
+int phylo_fitch_plane_count(int n_states);
+/* column slab of a wider host matrix, rows host_pitch_bytes apart (0 = N * elt_bytes; plane input: a
+ * slab starts at a multiple of 32 characters and 0 = ceil(N/32) * NP * 4) */
 int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states,
                                  const void *codes, uint64_t host_pitch_bytes, const double *weights,
                                  int capacity);

@@ -113,6 +113,8 @@ struct phylo_engine {
   void *dProg = nullptr, *hProg = nullptr;
   size_t capProg = 0;
   cudaStream_t copyStream = nullptr;   // H2D of alignment slabs, overlapped with compute
+  cudaStream_t copyStream2 = nullptr;  // odd slabs: two DMA queues keep PCIe busier than one
+  bool tips8_valid = false;            // dTips (one byte per cell) is current; false after a packed upload until needed
   cudaStream_t auxStream = nullptr;    // odd slabs compute here so slab kernels overlap their tails
   cudaEvent_t auxDone = nullptr;
   std::vector<cudaEvent_t> slabEvents;
@@ -346,6 +348,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
   if (e->copyStream) cudaStreamDestroy(e->copyStream);
+  if (e->copyStream2) cudaStreamDestroy(e->copyStream2);
   if (e->auxStream) cudaStreamDestroy(e->auxStream);
   if (e->auxDone) cudaEventDestroy(e->auxDone);
   if (e->hT) cudaFreeHost(e->hT);
@@ -591,18 +594,21 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
                             const double *weights, int capacity, const char *who) {
   if (!e->has_model) return fail(e, PHYLO_ERR_STATE, "%s: call phylo_lk_set_model first", who);
   if (T < 2 || N < 1 || !masks || capacity < T ||
-      !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
+      !(mask_bytes == 0 || mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
     return fail(e, PHYLO_ERR_ARG, "%s: bad arguments (T=%d N=%lld mask_bytes=%d capacity=%d)", who, T,
                 (long long)N, mask_bytes, capacity);
+  if (mask_bytes == 0 && (e->S != 4 || e->dSymTab))
+    return fail(e, PHYLO_ERR_ARG, "%s: packed 4-bit masks (mask_bytes 0) need a 4-state model and no symbol table", who);
   if (e->dSymTab && mask_bytes != 1)
     return fail(e, PHYLO_ERR_ARG, "%s: a symbol table is set, the alignment must be 1 byte per cell (got %d)", who, mask_bytes);
-  if (!e->dSymTab && mask_bytes * 8 < e->S)
+  if (!e->dSymTab && mask_bytes > 0 && mask_bytes * 8 < e->S)
     return fail(e, PHYLO_ERR_ARG, "%s: %d-bit masks cannot hold %d states", who, mask_bytes * 8, e->S);
   CK(cudaSetDevice(e->device));
   CK(cudaStreamSynchronize(e->stream));
   const bool reuse = e->dTips && e->T == T && e->N == N && e->cap0 == capacity &&
                      e->mask_dev_bytes == dev_mask_bytes(e->S) && (weights != nullptr) == (e->dWeights != nullptr);
-  const size_t cells = (size_t)T * N;
+  // bytes of the raw upload in its staging buffer (packed rows are padded to 16 bytes)
+  const size_t raw_bytes = mask_bytes ? (size_t)T * N * mask_bytes : (size_t)T * ((((size_t)N + 1) / 2 + 15) & ~(size_t)15);
   if (reuse) {
     for (auto &n : e->nodes) n.valid = false;
     e->lk_evaluated = false;
@@ -634,12 +640,13 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
     CK(cudaMalloc(&e->dSite, sizeof(double) * N));
   }
   // the raw upload lands in a staging buffer; tips_prepare writes the padded device rows
-  if (cells * mask_bytes > e->capRaw) {
+  if (raw_bytes > e->capRaw) {
     dfree(e->dRaw);
     e->capRaw = 0;
-    CK(cudaMalloc(&e->dRaw, cells * mask_bytes));
-    e->capRaw = cells * mask_bytes;
+    CK(cudaMalloc(&e->dRaw, raw_bytes));
+    e->capRaw = raw_bytes;
   }
+  e->tips8_valid = false;
   if (!e->dBad) CK(cudaMalloc(&e->dBad, sizeof(unsigned long long)));
   CK(cudaMemsetAsync(e->dBad, 0, sizeof(unsigned long long), e->stream));
   if (weights) CK(cudaMemcpyAsync(e->dWeights, weights, sizeof(double) * N, cudaMemcpyHostToDevice, e->stream));
@@ -650,6 +657,26 @@ static int lk_prepare_shape(phylo_engine *e, int T, int64_t N, const void *masks
 // own stream), then mask conversion / validation / nibble packing on the engine's stream
 static int lk_upload_slab(phylo_engine *e, const void *masks, int mask_bytes, int64_t p_lo, int64_t p_hi,
                           cudaStream_t copy, cudaEvent_t ready, cudaStream_t cs) {
+  if (mask_bytes == 0) {
+    // packed nibbles: bytes [p_lo / 2, ceil(p_hi / 2)) of every row, then straight into the group-major tiles
+    const size_t nb = ((size_t)e->N + 1) / 2, dpitch = (nb + 15) & ~(size_t)15, host_pitch = e->hostPitch ? e->hostPitch : nb;
+    const size_t b_lo = (size_t)p_lo / 2, b_hi = std::min(nb, ((size_t)p_hi + 1) / 2);
+    CK(cudaMemcpy2DAsync((char *)e->dRaw + b_lo, dpitch, (const char *)masks + b_lo, host_pitch, b_hi - b_lo, e->T,
+                         cudaMemcpyHostToDevice, copy ? copy : cs));
+    if (copy) {
+      CK(cudaEventRecord(ready, copy));
+      CK(cudaStreamWaitEvent(cs, ready, 0));
+    }
+    const int64_t g_lo = p_lo / 32, g_hi = (p_hi >= e->N) ? e->tipStride / 32 : p_hi / 32;
+    ProfScope prof(e, KC_TIPS_PREPARE);
+    dim3 grid((unsigned)((g_hi - g_lo + 31) / 32), (unsigned)((e->T + 31) / 32));
+    tips_nibbles_to_groups_kernel<<<grid, 256, 0, cs>>>((const uint8_t *)e->dRaw, dpitch, e->dTips4, e->T, e->N, g_lo, g_hi);
+    LAUNCH_CHECK();
+    tips_groups_check_kernel<<<grid_for((g_hi - g_lo) * 16, 256, e->sm_count * 8), 256, 0, cs>>>(
+        e->dTips4, e->T, e->N, g_lo, g_hi, (uint8_t *)e->dInv, e->dBad);
+    LAUNCH_CHECK();
+    return PHYLO_OK;
+  }
   const size_t pitch = (size_t)e->N * mask_bytes;
   const size_t host_pitch = e->hostPitch ? e->hostPitch : pitch;
   CK(cudaMemcpy2DAsync((char *)e->dRaw + (size_t)p_lo * mask_bytes, pitch, (const char *)masks + (size_t)p_lo * mask_bytes,
@@ -673,6 +700,18 @@ static int lk_upload_slab(phylo_engine *e, const void *masks, int mask_bytes, in
         (const uint8_t *)e->dTips, e->dTips4, e->T, e->N, e->tipStride, b_lo, b_hi);
     LAUNCH_CHECK();
   }
+  if (p_hi >= e->N) e->tips8_valid = true;  // the last slab of a one-byte-per-cell upload
+  return PHYLO_OK;
+}
+
+// one byte per cell tip rows for the per-node kernels after a packed upload (lazy)
+static int lk_ensure_tips8(phylo_engine *e) {
+  if (e->tips8_valid) return PHYLO_OK;
+  ProfScope prof(e, KC_TIPS_PREPARE);
+  tips_groups_to_bytes_kernel<<<grid_for((int64_t)e->T * e->tipStride / 2, 256, e->sm_count * 8), 256, 0, e->stream>>>(
+      e->dTips4, (uint8_t *)e->dTips, e->T, e->tipStride);
+  LAUNCH_CHECK();
+  e->tips8_valid = true;
   return PHYLO_OK;
 }
 
@@ -691,7 +730,8 @@ static int lk_check_bad(phylo_engine *e, const char *who) {
 extern "C" int phylo_lk_set_tips_pitched(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
                                          uint64_t host_pitch_bytes, const double *weights, int capacity) {
   if (!e) return PHYLO_ERR_ARG;
-  if (host_pitch_bytes != 0 && N > 0 && host_pitch_bytes < (uint64_t)N * (uint64_t)std::max(mask_bytes, 1))
+  if (host_pitch_bytes != 0 && N > 0 &&
+      host_pitch_bytes < (mask_bytes ? (uint64_t)N * (uint64_t)mask_bytes : ((uint64_t)N + 1) / 2))
     return fail(e, PHYLO_ERR_ARG, "lk_set_tips: host pitch %llu is shorter than a row of %lld masks",
                 (unsigned long long)host_pitch_bytes, (long long)N);
   int rc;
@@ -798,6 +838,10 @@ struct Operand {
 static int lk_operand(phylo_engine *e, int slot, Operand *o, const char *who) {
   if (slot < 0 || slot >= e->cap) return fail(e, PHYLO_ERR_ARG, "%s: node slot %d out of range [0,%d)", who, slot, e->cap);
   if (slot < e->T) {
+    if (!e->tips8_valid) {
+      const int rc = lk_ensure_tips8(e);
+      if (rc != PHYLO_OK) return rc;
+    }
     o->src = (const char *)e->dTips + (size_t)slot * e->tipStride * e->mask_dev_bytes;
     o->scale = nullptr;
     o->tip = true;
@@ -1483,6 +1527,7 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     const int64_t blocks = e->nPart;
     int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(16, blocks / 256));
     if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    if (!e->copyStream2) CK(cudaStreamCreateWithFlags(&e->copyStream2, cudaStreamNonBlocking));
     if (!e->auxStream) CK(cudaStreamCreateWithFlags(&e->auxStream, cudaStreamNonBlocking));
     if (!e->auxDone) CK(cudaEventCreateWithFlags(&e->auxDone, cudaEventDisableTiming));
     while ((int)e->slabEvents.size() < nslab + 1) {
@@ -1501,7 +1546,8 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
       cudaStream_t cs = (sidx & 1) ? e->auxStream : e->stream;
       const int64_t b_lo = blocks * sidx / nslab, b_hi = blocks * (sidx + 1) / nslab;
       const int64_t p_lo = b_lo * kLnlBlock, p_hi = std::min<int64_t>(e->N, b_hi * kLnlBlock);
-      if ((rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, e->copyStream, e->slabEvents[sidx], cs)) != PHYLO_OK)
+      if ((rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, (sidx & 1) ? e->copyStream2 : e->copyStream,
+                               e->slabEvents[sidx], cs)) != PHYLO_OK)
         return rc;
       if (useW) a.spill = (double2 *)((char *)e->dSpill + (size_t)(sidx & 1) * (e->capSpill / 2));
       cudaError_t st = useW ? launch_treew_k(e, a, geo, p_lo / tile, (p_hi + tile - 1) / tile, cs)
@@ -2187,7 +2233,16 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
                                             const void *codes, uint64_t host_pitch_bytes, const double *weights,
                                             int capacity) {
   if (!e) return PHYLO_ERR_ARG;
-  if (host_pitch_bytes != 0 && N > 0 && host_pitch_bytes < (uint64_t)N * (uint64_t)std::max(elt_bytes, 1))
+  // elt_bytes == 0: the characters arrive in the device's own bit-sliced layout (phylo_fitch_pack_planes);
+  // sets read back with phylo_fitch_get_states then use the narrowest element that holds n_states bits
+  const bool planes_in = elt_bytes == 0;
+  if (planes_in) {
+    if (n_states < 1 || n_states > 64 || e->dSymTab)
+      return fail(e, PHYLO_ERR_ARG, "fitch_set_tips: plane input needs 1 <= n_states <= 64 and no symbol table");
+    elt_bytes = n_states <= 8 ? 1 : (n_states <= 16 ? 2 : (n_states <= 32 ? 4 : 8));
+  }
+  const size_t plane_row = (size_t)((N + 31) / 32) * np_device(n_states) * sizeof(uint32_t);
+  if (host_pitch_bytes != 0 && N > 0 && host_pitch_bytes < (planes_in ? (uint64_t)plane_row : (uint64_t)N * (uint64_t)std::max(elt_bytes, 1)))
     return fail(e, PHYLO_ERR_ARG, "fitch_set_tips: host pitch %llu is shorter than a row of %lld codes",
                 (unsigned long long)host_pitch_bytes, (long long)N);
   if (e->dSymTab && elt_bytes != 1)
@@ -2242,8 +2297,35 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
   const size_t row = (size_t)N * elt_bytes;
   const size_t host_row = host_pitch_bytes ? (size_t)host_pitch_bytes : row;
   const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, ((size_t)256 << 20) / row));
-  if ((rc = fitch_stage(e, row * chunk)) != PHYLO_OK) return rc;
+  if (!planes_in && (rc = fitch_stage(e, row * chunk)) != PHYLO_OK) return rc;
   CK(cudaMemsetAsync(e->dCost, 0, sizeof(unsigned long long), e->stream));
+  if (planes_in) {
+    // straight into the node buffers from two DMA queues, then one checking pass; nothing to transcode
+    if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    if (!e->copyStream2) CK(cudaStreamCreateWithFlags(&e->copyStream2, cudaStreamNonBlocking));
+    for (int t = 0; t < T; ++t)
+      if ((rc = fitch_ensure(e, t, false)) != PHYLO_OK) return rc;
+    if ((rc = fitch_sync_tables(e)) != PHYLO_OK) return rc;  // also orders the copies after the allocation memsets
+    while (e->slabEvents.size() < 2) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->slabEvents.push_back(ev);
+    }
+    const size_t hp = host_pitch_bytes ? (size_t)host_pitch_bytes : plane_row;
+    for (int t = 0; t < T; ++t)
+      CK(cudaMemcpyAsync(e->fPre[t], (const char *)codes + (size_t)t * hp, plane_row, cudaMemcpyHostToDevice,
+                         (t & 1) ? e->copyStream2 : e->copyStream));
+    CK(cudaEventRecord(e->slabEvents[0], e->copyStream));
+    CK(cudaEventRecord(e->slabEvents[1], e->copyStream2));
+    CK(cudaStreamWaitEvent(e->stream, e->slabEvents[0], 0));
+    CK(cudaStreamWaitEvent(e->stream, e->slabEvents[1], 0));
+    {
+      ProfScope prof(e, KC_FITCH_TRANSCODE);
+      dim3 grid((unsigned)grid_for(e->fWords, 256, e->sm_count * 2), (unsigned)T);
+      fitch_planes_check_kernel<<<grid, 256, 0, e->stream>>>(e->dPreTab, e->fWords, e->fN, e->fNPdev, e->dCost);
+      LAUNCH_CHECK();
+    }
+  } else {
   // Within a chunk the H2D copy runs in pieces of ~8 MB on the copy stream while the pieces
   // that have landed are already being transcoded on the engine's stream.
   if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
@@ -2285,6 +2367,7 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
     if (t0 + chunk < T) {  // staging buffer is reused by the next chunk
       CK(cudaStreamSynchronize(e->stream));
     }
+  }
   }
   CK(cudaMemcpyAsync(e->hCost, e->dCost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));

@@ -610,6 +610,25 @@ fitch_decode_kernel(const uint32_t *__restrict__ buf, Elt *__restrict__ codes, i
   }
 }
 
+// Bit-sliced planes uploaded as they are (phylo_fitch_set_tips with elt_bytes == 0): nothing to transcode,
+// only the checks the encoder would have made: a character with no state at all is invalid input, and
+// lanes beyond N are cleared. blockIdx.y = taxon.
+__global__ void __launch_bounds__(256)
+fitch_planes_check_kernel(uint32_t *const *__restrict__ bufs, int64_t nwords, int64_t N, int NP,
+                          unsigned long long *__restrict__ n_bad) {
+  uint32_t *buf = bufs[blockIdx.y];
+  unsigned long long bad = 0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t valid = valid_mask(w, N);
+    uint32_t any = 0;
+    for (int s = 0; s < NP; ++s) any |= buf[w * NP + s];
+    bad += __popc(~any & valid);
+    if (valid != 0xffffffffu)
+      for (int s = 0; s < NP; ++s) buf[w * NP + s] &= valid;
+  }
+  block_add_u64(bad, n_bad);
+}
+
 // ------------------------------------------------------------------ bitvector set ops ----
 // bv_union / bv_inter (lib/bitvector/bv.c:93-99, :112-118): plane-wise OR / AND.
 template <bool UNION>

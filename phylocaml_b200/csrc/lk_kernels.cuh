@@ -1039,4 +1039,96 @@ tips_pack4_kernel(const uint8_t *__restrict__ tips, uint8_t *__restrict__ tips4,
   }
 }
 
+// ---- packed 4-state input (phylo_lk_set_tips with mask_bytes == 0): the host alignment is already
+// two 4-bit masks per byte, tip-major rows of `in_pitch` bytes. No staging copy at device width, no
+// re-packing: the upload is half the bytes of the one-byte-per-cell form and this kernel only turns
+// the tip-major rows into the group-major tiles the tree-fused kernel bulk-copies
+// ([group of 32 patterns][T][16 bytes]). A CTA moves a tile of 32 taxa x 32 groups through shared
+// memory: rows are read as 512-byte runs (one taxon per warp, 16 bytes per lane), tiles are written
+// as T*16-byte runs per group. Patterns >= N (last byte / trailing groups up to the 1024-padded
+// stride) are forced to "all states". Groups [g_lo, g_hi).
+__global__ void __launch_bounds__(256)
+tips_nibbles_to_groups_kernel(const uint8_t *__restrict__ in, uint64_t in_pitch, uint8_t *__restrict__ tips4, int T,
+                              int64_t N, int64_t g_lo, int64_t g_hi) {
+  __shared__ uint4 tile[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t g0 = g_lo + (int64_t)blockIdx.x * 32;
+  const int t0 = blockIdx.y * 32;
+  const int64_t n_bytes = (N + 1) >> 1;  // valid bytes per input row
+  for (int r = warp; r < 32; r += 8) {   // taxon t0 + r: lane reads the 16 bytes of group g0 + lane
+    const int t = t0 + r;
+    const int64_t g = g0 + lane;
+    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (t < T && g < g_hi) {
+      const int64_t b = g << 4;
+      const uint8_t *src = in + (uint64_t)t * in_pitch + b;
+      if (b + 16 <= n_bytes && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        v = *reinterpret_cast<const uint4 *>(src);
+      } else {
+        uint8_t tmp[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tmp[i] = (b + i < n_bytes) ? src[i] : 0xff;
+        v = *reinterpret_cast<uint4 *>(tmp);
+      }
+      if (2 * (b + 16) > N) {  // the group holds patterns >= N: all states there
+        uint8_t *q = reinterpret_cast<uint8_t *>(&v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int64_t pat = 2 * (b + i);
+          if (pat >= N) q[i] = 0xff;
+          else if (pat + 1 >= N) q[i] |= 0xf0;
+        }
+      }
+    }
+    tile[r][lane] = v;
+  }
+  __syncthreads();
+  for (int gg = warp; gg < 32; gg += 8) {  // group g0 + gg: lane writes taxon t0 + lane's 16 bytes
+    const int64_t g = g0 + gg;
+    const int t = t0 + lane;
+    if (g < g_hi && t < T) *reinterpret_cast<uint4 *>(tips4 + ((uint64_t)g * T + t) * 16) = tile[lane][gg];
+  }
+}
+
+// Validation of the group-major nibble tiles (a nibble with no state bit is an invalid cell) and, when
+// the model has an invariant-sites class, the AND over all tips per pattern (`inv`, one byte per
+// pattern). Thread = one byte (two patterns) of a group; the 16 threads of a group walk its T rows.
+__global__ void __launch_bounds__(256)
+tips_groups_check_kernel(const uint8_t *__restrict__ tips4, int T, int64_t N, int64_t g_lo, int64_t g_hi,
+                         uint8_t *__restrict__ inv, unsigned long long *__restrict__ n_bad) {
+  unsigned long long bad = 0;
+  const int64_t total = (g_hi - g_lo) * 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = g_lo + (i >> 4);
+    const int b = (int)(i & 15);
+    const int64_t p = (g << 5) + 2 * b;
+    if (p >= N) continue;
+    const uint8_t *col = tips4 + (uint64_t)g * T * 16 + b;
+    unsigned all = 0xff;
+    for (int t = 0; t < T; ++t) {
+      const unsigned v = col[(size_t)t * 16];
+      bad += ((v & 15) == 0) + ((p + 1 < N) && ((v >> 4) == 0));
+      all &= v;
+    }
+    if (inv) {
+      inv[p] = (uint8_t)(all & 15);
+      if (p + 1 < N) inv[p + 1] = (uint8_t)(all >> 4);
+    }
+  }
+  if (bad) atomicAdd(n_bad, bad);
+}
+
+// One byte per cell rows (what the per-node kernels and the edge functions read for a tip operand)
+// rebuilt from the group-major nibble tiles: done lazily, only when such a kernel first needs them
+// after a packed upload. Thread = one output byte pair.
+__global__ void __launch_bounds__(256)
+tips_groups_to_bytes_kernel(const uint8_t *__restrict__ tips4, uint8_t *__restrict__ tips, int T, int64_t stride) {
+  const int64_t pairs = stride >> 1, total = pairs * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / pairs, b = i - t * pairs, g = b >> 4;
+    const unsigned v = tips4[((uint64_t)g * T + t) * 16 + (b & 15)];
+    *reinterpret_cast<uchar2 *>(tips + t * stride + 2 * b) = make_uchar2((unsigned char)(v & 15), (unsigned char)(v >> 4));
+  }
+}
+
 }  // namespace phylo

@@ -52,6 +52,9 @@ SIGNATURES = {
     "phylo_compose_gtr": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, C.c_int, _dp]),
     "phylo_lk_set_model": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]),
     "phylo_lk_set_tips": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int]),
+    "phylo_pack_nibbles": (C.c_int, [_vp, C.c_int, _i64, _vp]),
+    "phylo_fitch_pack_planes": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp]),
+    "phylo_fitch_plane_count": (C.c_int, [C.c_int]),
     "phylo_lk_set_tips_pitched": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_uint64, _dp, C.c_int]),
     "phylo_lk_node_alloc": (C.c_int, [_vp, C.POINTER(C.c_int), _u64p]),
     "phylo_lk_node_release": (C.c_int, [_vp, C.c_int, C.c_uint64]),
@@ -216,6 +219,36 @@ def plan_compile(ops, T, capacity, root_a, root_b):
     return steps, depth.value
 
 
+def pack_nibbles(tips, out=None):
+    """T x N one-byte masks -> T x ceil(N/2) packed nibbles (phylo_pack_nibbles), the compact upload
+    format of lk_set_tips(..., packed_n=N). `out`: optional (e.g. pinned) destination."""
+    tips = np.ascontiguousarray(tips, dtype=np.uint8)
+    T, N = tips.shape
+    if out is None:
+        out = np.empty((T, (N + 1) // 2), dtype=np.uint8)
+    assert out.shape == (T, (N + 1) // 2) and out.dtype == np.uint8 and out.flags.c_contiguous
+    rc = load().phylo_pack_nibbles(_p(tips), T, N, _p(out))
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "phylo_pack_nibbles: bad arguments")
+    return out
+
+
+def fitch_pack_planes(codes, n_states, out=None):
+    """T x N characters (one per element) -> the bit-sliced plane layout (T x ceil(N/32)*NP uint32),
+    the compact upload format of fitch_set_tips_planes."""
+    codes = np.ascontiguousarray(codes)
+    T, N = codes.shape
+    NP = load().phylo_fitch_plane_count(int(n_states))
+    shape = (T, ((N + 31) // 32) * NP)
+    if out is None:
+        out = np.empty(shape, dtype=np.uint32)
+    assert out.shape == shape and out.dtype == np.uint32 and out.flags.c_contiguous
+    rc = load().phylo_fitch_pack_planes(_p(codes), codes.dtype.itemsize, int(n_states), T, N, _p(out))
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "phylo_fitch_pack_planes: bad arguments")
+    return out
+
+
 def pinned_empty(shape, dtype):
     """numpy array over page-locked host memory from phylo_host_alloc."""
     lib = load()
@@ -340,12 +373,17 @@ class Engine:
                                              _p(rates, _dp), _p(probs, _dp), pinvar))
         self.S, self.K = S, K
 
-    def lk_set_tips(self, tips, weights=None, capacity=None):
+    def lk_set_tips(self, tips, weights=None, capacity=None, packed_n=None):
+        """packed_n: `tips` is the packed form (pack_nibbles) of an alignment of packed_n patterns."""
         tips = np.ascontiguousarray(tips)
         T, N = tips.shape
+        mask_bytes = tips.dtype.itemsize
+        if packed_n is not None:
+            assert tips.dtype == np.uint8 and N == (packed_n + 1) // 2
+            N, mask_bytes = int(packed_n), 0
         capacity = 2 * T if capacity is None else capacity
         w = None if weights is None else _f64(weights)
-        self._ck(self.lib.phylo_lk_set_tips(self.h, T, N, _p(tips), tips.dtype.itemsize, _p(w, _dp), capacity))
+        self._ck(self.lib.phylo_lk_set_tips(self.h, T, N, _p(tips), mask_bytes, _p(w, _dp), capacity))
         self.lk_shape = (T, N, capacity)
 
     def node_alloc(self, fitch=False):
@@ -379,15 +417,19 @@ class Engine:
                                               C.byref(out)))
         return out.value
 
-    def lk_score_alignment(self, tips, ops, root_a, root_b, root_t, weights=None, capacity=None):
+    def lk_score_alignment(self, tips, ops, root_a, root_b, root_t, weights=None, capacity=None, packed_n=None):
         """set_tips + score_tree with the upload overlapped with the scoring."""
         tips = np.ascontiguousarray(tips)
         T, N = tips.shape
+        mask_bytes = tips.dtype.itemsize
+        if packed_n is not None:
+            assert tips.dtype == np.uint8 and N == (packed_n + 1) // 2
+            N, mask_bytes = int(packed_n), 0
         capacity = 2 * T if capacity is None else capacity
         w = None if weights is None else _f64(weights)
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
         out = C.c_double()
-        self._ck(self.lib.phylo_lk_score_alignment(self.h, T, N, _p(tips), tips.dtype.itemsize, _p(w, _dp), capacity,
+        self._ck(self.lib.phylo_lk_score_alignment(self.h, T, N, _p(tips), mask_bytes, _p(w, _dp), capacity,
                                                    _p(ops), len(ops), root_a, root_b, float(root_t), C.byref(out)))
         self.lk_shape = (T, N, capacity)
         return out.value
@@ -481,6 +523,17 @@ class Engine:
                                                _p(w, _dp), capacity))
         self.fitch_shape = (T, N, capacity)
         self.fitch_dtype = codes.dtype
+
+    def fitch_set_tips_planes(self, planes, N, n_states, weights=None, capacity=None):
+        """Characters already in the bit-sliced device layout (fitch_pack_planes): elt_bytes = 0."""
+        planes = np.ascontiguousarray(planes, dtype=np.uint32)
+        T = planes.shape[0]
+        capacity = 2 * T if capacity is None else capacity
+        w = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_fitch_set_tips(self.h, T, int(N), 0, n_states, _p(planes), _p(w, _dp), capacity))
+        self.fitch_shape = (T, int(N), capacity)
+        self.fitch_dtype = np.dtype(np.uint8 if n_states <= 8 else (np.uint16 if n_states <= 16 else
+                                                                    (np.uint32 if n_states <= 32 else np.uint64)))
 
     def fitch_median_2(self, parent, left, right):
         out = C.c_uint64()

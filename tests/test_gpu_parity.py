@@ -712,3 +712,68 @@ def test_lk_score_alignment_pipelined_equals_two_calls(eng, N):
     with pytest.raises(engine.PhyloError) as ei:
         eng.lk_score_alignment(bad, ops, ra, rb, rt, capacity=n_nodes)
     assert ei.value.code == -4
+
+
+# ------------------------------------------------------------ compact upload formats ----
+@pytest.mark.parametrize("N", [1, 2, 33, 1024, 1025, 70001])
+@pytest.mark.parametrize("pinvar", [None, 0.15])
+def test_lk_packed_nibble_input_equals_byte_input(eng, oracle, N, pinvar):
+    """mask_bytes = 0: two 4-bit masks per byte. Same lnL / site lnL / CLVs bit for bit as the one-byte
+    form under the tree-fused and the per-node paths (the latter rebuilds its byte rows lazily), through
+    set_tips and through the pipelined score_alignment."""
+    model = dna_gtr_g4(pinvar=pinvar)
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(9, N, model, seed=11)
+    packed = engine.pack_nibbles(tips)
+    eng.lk_set_model(model)
+    try:
+        for fused in (1, 0):
+            eng.set_option(eng.OPT_FUSED_TREE, fused)
+            eng.lk_set_tips(tips, capacity=n_nodes)
+            want = eng.lk_score_tree(ops, ra, rb, rt)
+            site = eng.lk_get_site_lnl()
+            clv, sc = eng.lk_get_clv(int(ops[-1]["parent"]))
+            eng.lk_set_tips(packed, capacity=n_nodes, packed_n=N)
+            assert eng.lk_score_tree(ops, ra, rb, rt) == want
+            assert np.array_equal(eng.lk_get_site_lnl(), site)
+            clv2, sc2 = eng.lk_get_clv(int(ops[-1]["parent"]))
+            assert np.array_equal(clv, clv2) and np.array_equal(sc, sc2)
+            assert eng.lk_edge_lnl(0, int(ops[-1]["parent"]), [0.1])[0] == eng.lk_edge_lnl(0, int(ops[-1]["parent"]), [0.1])[0]
+            assert eng.lk_score_alignment(packed, ops, ra, rb, rt, capacity=n_nodes, packed_n=N) == want
+        ref = oracle.lk_score_tree(model, tips, None, ops, n_nodes, ra, rb, rt)["lnl"]
+        assert rel_err(want, ref) <= LNL_RTOL
+    finally:
+        eng.set_option(eng.OPT_FUSED_TREE, 1)
+
+
+def test_lk_packed_input_rejects_empty_nibbles_and_other_alphabets(eng):
+    model = dna_gtr_g4()
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(6, 301, model, seed=2)
+    eng.lk_set_model(model)
+    bad = tips.copy()
+    bad[3, 300] = 0
+    with pytest.raises(engine.PhyloError):
+        eng.lk_set_tips(engine.pack_nibbles(bad), capacity=n_nodes, packed_n=301)
+    eng.lk_set_model(aa_model(1))
+    with pytest.raises(engine.PhyloError):
+        eng.lk_set_tips(engine.pack_nibbles(tips), capacity=n_nodes, packed_n=301)
+    eng.lk_set_model(model)
+
+
+@pytest.mark.parametrize("N,ns,dt", [(1, 4, np.uint8), (33, 4, np.uint8), (4096 + 17, 4, np.uint8), (2000, 6, np.uint8),
+                                     (777, 20, np.uint32), (100, 61, np.uint64)])
+def test_fitch_plane_input_equals_element_input(eng, oracle, N, ns, dt):
+    """elt_bytes = 0: the characters arrive bit-sliced (phylo_fitch_pack_planes); lengths, per-node costs and
+    sets equal the element-wise upload's and the oracle's."""
+    T = 10
+    tr = tree.random_tree(T, seed=6)
+    ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+    chars = tree.random_fitch_chars(T, N, ns, seed=8, ambiguity=0.1, dtype=dt)
+    want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, want_sets=True)
+    eng.fitch_set_tips_planes(engine.fitch_pack_planes(chars, ns), N, ns, capacity=n_nodes)
+    assert eng.fitch_score_tree(ops, ra, rb) == want["length"]
+    for node in (0, T - 1, int(ops[0]["parent"]), int(ops[-1]["parent"])):
+        assert np.array_equal(eng.fitch_get_states(node).astype(np.uint64), want["prelim"][node].astype(np.uint64))
+    bad = chars.copy()
+    bad[2, N - 1] = 0
+    with pytest.raises(engine.PhyloError):
+        eng.fitch_set_tips_planes(engine.fitch_pack_planes(bad, ns), N, ns, capacity=n_nodes)

@@ -503,3 +503,26 @@ def test_ocaml_stubs_compile_and_cover_the_plugin_surface(tmp_path):
     # every C-ABI function the stubs call is declared in the header
     called = set(re.findall(r" U (phylo_\w+)", syms))
     assert called and called <= set(_declared_symbols())
+
+
+def test_host_packers_match_numpy(built):
+    """phylo_pack_nibbles / phylo_fitch_pack_planes (the compact upload formats) against numpy."""
+    rng = np.random.default_rng(5)
+    for N in (1, 2, 31, 32, 33, 1000, 1025):
+        tips = rng.integers(1, 16, size=(5, N), dtype=np.uint8)
+        got = engine.pack_nibbles(tips)
+        pad = np.concatenate([tips, np.full((5, N % 2), 15, np.uint8)], axis=1)
+        assert np.array_equal(got, pad[:, 0::2] | (pad[:, 1::2] << 4))
+    lib = engine.load()
+    assert [lib.phylo_fitch_plane_count(s) for s in (1, 4, 7, 9, 20, 33, 64)] == [1, 4, 8, 12, 24, 64, 64]
+    for N, ns, dt in ((70, 4, np.uint8), (64, 6, np.uint8), (33, 13, np.uint16), (100, 20, np.uint32), (40, 61, np.uint64)):
+        codes = rng.integers(1, 1 << min(ns, 62), size=(3, N), dtype=np.uint64).astype(dt)
+        planes = engine.fitch_pack_planes(codes, ns)
+        NP = lib.phylo_fitch_plane_count(ns)
+        W = (N + 31) // 32
+        assert planes.shape == (3, W * NP)
+        p3 = planes.reshape(3, W, NP)
+        for t in range(3):
+            for i in range(N):
+                v = sum(((int(p3[t, i // 32, s]) >> (i % 32)) & 1) << s for s in range(NP))
+                assert v == int(codes[t, i]) & ((1 << ns) - 1)
