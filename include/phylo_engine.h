@@ -185,6 +185,20 @@ int phylo_lk_median_3(phylo_engine *e, int parent, int a, double t_a, int b, dou
  * phylo_lk_edge_lnl / phylo_lk_get_clv / incremental re-scoring. */
 int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                         double root_t, double *lnl_out);
+/* 3-directional CLVs -- what Node.Make3D keeps per node (lib/node.ml:363-477: one value per excluded
+ * neighbour, `dir`) and readjust_3 consumes (lib/node.ml:239-256). After phylo_lk_score_tree over the same
+ * schedule (CLVs retained), a pre-order pass fills, for every node v below the root edge with
+ * up_slot[v] >= 0, the slot up_slot[v] with up[v]: the CLV of the rest of the tree at the far end of the
+ * branch above v,  up[v] = (P(t_sibling) down[sibling]) o (P(t_parent) up[parent]),  up[a] = down[b] and
+ * up[b] = down[a] across the root edge (their up_slot entries are ignored). up_slot: `capacity` entries
+ * (-1 = not wanted; a wanted node needs its parent's up value, so its ancestors' entries must be set
+ * too); the slots must be interior, distinct, and not used by the schedule. One pruning update per
+ * filled slot (2 T - 4 for a whole tree). Afterwards ANY edge is a root edge:
+ * phylo_lk_edge_lnl / _edge_prepare / _optimize_branch (v, up_slot[v]) work on the branch above v, and for
+ * a reversible model every edge gives the same lnL (pulley principle) -- an SPR / TBR candidate costs one
+ * edge join instead of a re-prune (lib/tree.ml:299-494). */
+int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, double root_t,
+                    const int32_t *up_slot);
 /* Host-only (no GPU needed), for tests and tooling: the compiled form of a schedule as the
  * tree-fused likelihood kernels and the Fitch register walk execute it. One row of 6 int32 per
  * step (n_ops medians in depth-first order + the root-edge join, whose out_slot is -1):

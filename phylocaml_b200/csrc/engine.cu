@@ -23,6 +23,7 @@
 #include "lk_kernels.cuh"
 #include "lk_tree_kernel.cuh"
 #include "lk_treew_kernel.cuh"
+#include "lk_treem_kernel.cuh"
 #include "lk_edge_kernels.cuh"
 #include "compress_kernels.cuh"
 #include "phylo_engine.h"
@@ -134,6 +135,8 @@ struct phylo_engine {
   uint64_t lkGen = 0;              // bumped whenever every slot is dropped (new alignment shape / model alphabet)
   double *dP = nullptr;  // transition matrices [branch][K][S][S]
   size_t capP = 0;       // branches
+  double *dFrag = nullptr;  // the same matrices as DMMA A-fragment tables (tree-fused 20/61-state kernel)
+  size_t capFrag = 0;       // doubles
   double *dT = nullptr, *hT = nullptr;  // branch lengths (device / pinned)
   double *dSite = nullptr, *dWSite = nullptr;
   // branch-length loop (lk_edge_kernels.cuh): eigenvector matrices in the orientation the sum table needs,
@@ -342,7 +345,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   lk_free_data(e);
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
-  dfree(e->dP); dfree(e->dT);
+  dfree(e->dP); dfree(e->dFrag); dfree(e->dT);
   dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
@@ -515,6 +518,7 @@ extern "C" int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U
   for (auto &n : e->nodes) n.valid = false;  // CLVs of the previous model are stale
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); e->capP = 0;
+  dfree(e->dFrag); e->capFrag = 0;
   const size_t ss = (size_t)S * S;
   std::vector<double> lam(S);
   for (int i = 0; i < S; ++i) lam[i] = D[(size_t)i * S + i];
@@ -1371,6 +1375,19 @@ static int lk_build_tmaps(phylo_engine *e) {
                                            : (e->K == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   for (int s = 0; s < e->cap; ++s) {
     if (!e->nodes[s].clv) continue;
+    if (e->S != 4) {
+      // tree-fused 20-state kernel: the CLV [N][K][S] seen as dims (S, N, K); a box (S, 8, K) is one 8-pattern
+      // group in the kernel's shared-memory order [k][pattern][S]
+      const cuuint64_t gdim[3] = {(cuuint64_t)e->S, (cuuint64_t)e->N, (cuuint64_t)e->K};
+      const cuuint64_t gstride[2] = {(cuuint64_t)e->K * e->S * 8, (cuuint64_t)e->S * 8};
+      const cuuint32_t box[3] = {(cuuint32_t)e->S, 8, (cuuint32_t)e->K};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult r = e->encodeTiled(&h[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, e->nodes[s].clv, gdim, gstride, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(e, PHYLO_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed for node slot %d (CUresult %d)", s, (int)r);
+      continue;
+    }
     const cuuint64_t gdim[2] = {(cuuint64_t)(4 * e->K), (cuuint64_t)e->N};
     const cuuint64_t gstride[1] = {(cuuint64_t)(32 * e->K)};
     const cuuint32_t box[2] = {(cuuint32_t)(4 * e->K), 32};
@@ -1595,6 +1612,136 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   return PHYLO_OK;
 }
 
+// ---- tree-fused evaluation for 20 / 61 states (lk_treem_kernel.cuh): one launch for the whole
+// schedule, every interior CLV written once into its node slot, nothing read back from HBM but
+// the (L2-resident) values parked across a subtree.
+template <int S, typename MaskT, int R, int NW, int KT>
+static cudaError_t launch_treem(phylo_engine *e, const TreeMArgs &args, size_t smem) {
+  auto kern = lk_treem_kernel<S, MaskT, R, NW, KT>;
+  cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (st != cudaSuccess) return st;
+  const int64_t ngroups = (e->N + 7) / 8;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(e->sm_count, (ngroups + NW * R - 1) / (NW * R)));
+  kern<<<grid, NW * 32, smem, e->stream>>>(args);
+  return cudaGetLastError();
+}
+
+static int lk_score_tree_fusedm(phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt, bool *done) {
+  *done = false;
+  if (!e->opt_fused || !(e->S == 20 || e->S == 61) || n_ops < 1) return PHYLO_OK;
+  if (e->S == 20 && !e->encodeTiled) return PHYLO_OK;  // its results leave through TMA tensor maps
+  const size_t kMaxSmem = 227 * 1024;
+  int R = 0, NW = 0;
+  NW = 8;
+  for (int r : {4, 2, 1}) {
+    if (e->S == 61 && r > 2) continue;
+    const size_t need = e->S == 20 ? treem_smem_bytes<20>(e->K, r, NW) : treem_smem_bytes<61>(e->K, r, NW);
+    if (need <= kMaxSmem) { R = r; break; }
+  }
+  if (!R || !NW) return PHYLO_OK;  // too many rate classes for the on-chip tables: per-node kernels
+  FusedPlan pl;
+  if (!build_fused_plan(e->cap, e->T, ops, n_ops, ra, rb, rt, pl)) return PHYLO_OK;
+  int rc;
+  const int nb = 2 * n_ops + 1;
+  if ((rc = ensure_pt_capacity(e, nb, e->S, e->K)) != PHYLO_OK) return rc;
+  for (int o = 0; o < n_ops; ++o)
+    if ((rc = lk_ensure_node(e, ops[o].parent)) != PHYLO_OK) return rc;
+  const size_t frag = (e->S == 20) ? TreeMGeom<20>::FRAG : TreeMGeom<61>::FRAG;
+  const size_t need_frag = (size_t)(nb + 1) * e->K * frag;
+  if (need_frag > e->capFrag) {
+    CK(cudaStreamSynchronize(e->stream));
+    dfree(e->dFrag);
+    e->capFrag = 0;
+    CK(cudaMalloc(&e->dFrag, sizeof(double) * need_frag * 2));
+    e->capFrag = need_frag * 2;
+  }
+  const size_t pbytes = sizeof(TreeMInstr) * pl.steps.size();
+  if (pbytes > e->capProg) {
+    CK(cudaStreamSynchronize(e->stream));
+    dfree(e->dProg);
+    if (e->hProg) { cudaFreeHost(e->hProg); e->hProg = nullptr; }
+    e->capProg = 0;
+    CK(cudaMalloc(&e->dProg, pbytes * 2));
+    CK(cudaMallocHost(&e->hProg, pbytes * 2));
+    e->capProg = pbytes * 2;
+  }
+  if (!e->dWSite) CK(cudaMalloc(&e->dWSite, sizeof(double) * (size_t)e->N));
+  CK(cudaStreamSynchronize(e->stream));  // pinned staging (hT, hProg) is about to be rewritten
+  if (e->nodeTabDirty) {
+    std::vector<double *> hc(e->cap);
+    std::vector<int32_t *> hs(e->cap);
+    for (int s = 0; s < e->cap; ++s) { hc[s] = e->nodes[s].clv; hs[s] = e->nodes[s].scale; }
+    CK(cudaMemcpy(e->dNodeClv, hc.data(), sizeof(double *) * e->cap, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->dNodeSc, hs.data(), sizeof(int32_t *) * e->cap, cudaMemcpyHostToDevice));
+    e->nodeTabDirty = false;
+  }
+  if (e->S == 20 && e->tmapDirty && (rc = lk_build_tmaps(e)) != PHYLO_OK) return rc;
+  TreeMInstr *hp = (TreeMInstr *)e->hProg;
+  for (size_t i = 0; i < pl.steps.size(); ++i) {
+    const PlanStep &st = pl.steps[i];
+    auto mode = [](int kind) { return kind == OPK_TIP ? (int)TM_TIP : (kind == OPK_CUR ? (int)TM_CUR : (int)TM_GLB); };
+    int lm = mode(st.lkind), rm = mode(st.rkind), li = st.lidx, ri = st.ridx;
+    double tl = st.t_left, tr = st.t_right;
+    // medians: the step body is compiled per (left mode <= right mode); x * y == y * x bit for bit
+    if (i + 1 < pl.steps.size() && lm > rm) { std::swap(lm, rm); std::swap(li, ri); std::swap(tl, tr); }
+    hp[i] = TreeMInstr{lm | (rm << 2), li, ri, st.out_slot};
+    if (i + 1 < pl.steps.size()) { e->hT[2 * i] = tl; e->hT[2 * i + 1] = tr; }
+    else e->hT[2 * i] = tl;
+  }
+  CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
+  if ((rc = build_pt(e, nb, 0)) != PHYLO_OK) return rc;
+  {
+    ProfScope prof(e, KC_PT_BUILD);
+    const TreeMInstr *dprog = (const TreeMInstr *)e->dProg;
+    if (e->S == 20) pt_frag_kernel<20><<<nb * e->K, 256, 0, e->stream>>>(e->dP, e->dFrag, dprog, n_ops, e->K);
+    else pt_frag_kernel<61><<<nb * e->K, 256, 0, e->stream>>>(e->dP, e->dFrag, dprog, n_ops, e->K);
+    LAUNCH_CHECK();
+  }
+  TreeMArgs a;
+  a.prog = (const TreeMInstr *)e->dProg;
+  a.n_steps = n_ops;
+  a.K = e->K;
+  a.frags = e->dFrag;
+  a.tips = e->dTips;
+  a.tip_stride = e->tipStride;
+  a.N = e->N;
+  a.node_clv = e->dNodeClv;
+  a.node_sc = e->dNodeSc;
+  a.pi = e->dPi;
+  a.probs = e->dProbs;
+  a.weights = e->dWeights;
+  a.inv = e->dInv;
+  a.pinvar = e->pinvar;
+  a.site_lnl = e->dSite;
+  a.wsite = e->dWSite;
+  a.tmaps = (const char *)e->dTmaps;
+  {
+    ProfScope prof(e, KC_TREE_FUSED);
+    cudaError_t st;
+#define TREEM(S_, M_, R_, KT_) launch_treem<S_, M_, R_, 8, KT_>(e, a, treem_smem_bytes<S_>(e->K, R_, 8))
+    if (e->S == 20) {
+      if (e->K == 4) st = R == 4 ? TREEM(20, uint32_t, 4, 4) : (R == 2 ? TREEM(20, uint32_t, 2, 4) : TREEM(20, uint32_t, 1, 4));
+      else st = R == 4 ? TREEM(20, uint32_t, 4, 0) : (R == 2 ? TREEM(20, uint32_t, 2, 0) : TREEM(20, uint32_t, 1, 0));
+    } else {
+      if (e->K == 1) st = R == 2 ? TREEM(61, uint64_t, 2, 1) : TREEM(61, uint64_t, 1, 1);
+      else st = R == 2 ? TREEM(61, uint64_t, 2, 0) : TREEM(61, uint64_t, 1, 0);
+    }
+#undef TREEM
+    if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused (DMMA) launch: %s", cudaGetErrorString(st));
+    ++e->launches;
+  }
+  for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = true;
+  e->fused_result_ready = false;
+  {
+    ProfScope prof(e, KC_REDUCE);
+    reduce1024_kernel<<<(int)e->nPart, 256, 0, e->stream>>>(e->dWSite, e->N, e->dPart);
+    LAUNCH_CHECK();
+  }
+  if ((rc = lk_finish_reduce(e, e->hScalar)) != PHYLO_OK) return rc;
+  *done = true;
+  return PHYLO_OK;
+}
+
 extern "C" int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int right,
                                  double t_right) {
   if (!e) return PHYLO_ERR_ARG;
@@ -1687,6 +1834,7 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
   {
     bool done = false;
     if ((rc = lk_score_tree_fused(e, ops, n_ops, root_a, root_b, root_t, &done)) != PHYLO_OK) return rc;
+    if (!done && (rc = lk_score_tree_fusedm(e, ops, n_ops, root_a, root_b, root_t, &done)) != PHYLO_OK) return rc;
     if (done) {
       if (!e->fused_result_ready) CK(cudaStreamSynchronize(e->stream));
       *lnl_out = e->hScalar[0];
@@ -1723,6 +1871,85 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
   CK(cudaStreamSynchronize(e->stream));
   *lnl_out = e->hScalar[0];
   e->lk_evaluated = true;
+  if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
+}
+
+// 3-directional CLVs (Node.Make3D, lib/node.ml:363-477: a node keeps one value per excluded neighbour;
+// readjust_3, lib/node.ml:239-256). After a down-pass, up[v] -- the CLV of "the rest of the tree" seen from
+// the far end of the branch above v -- is one more pruning update per node, run parent-before-child:
+//   up[v] = (P(t_s) down[s]) o (P(t_p) up[p]),  s = v's sibling, p = their parent,
+// with up[a] = down[b] (and vice versa) across the root edge. The pair (down[v], up[v]) joined over the
+// branch above v is the tree's likelihood seen from that edge, so every edge becomes a root edge.
+extern "C" int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, double root_t,
+                               const int32_t *up_slot) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_uppass: no tips loaded");
+  if (n_ops < 0 || (n_ops > 0 && !ops) || !up_slot) return fail(e, PHYLO_ERR_ARG, "lk_uppass: bad arguments");
+  CK(cudaSetDevice(e->device));
+  int rc;
+  const int cap = e->cap;
+  auto in_range = [&](int s) { return s >= 0 && s < cap; };
+  if (!in_range(root_a) || !in_range(root_b) || root_a == root_b) return fail(e, PHYLO_ERR_ARG, "lk_uppass: bad root edge (%d,%d)", root_a, root_b);
+  std::vector<char> is_down(cap, 0), is_up(cap, 0);
+  for (int s = 0; s < e->T; ++s) is_down[s] = 1;
+  for (int o = 0; o < n_ops; ++o) {
+    const phylo_op &op = ops[o];
+    if (!in_range(op.parent) || op.parent < e->T || !in_range(op.left) || !in_range(op.right))
+      return fail(e, PHYLO_ERR_ARG, "lk_uppass: op %d has bad slots", o);
+    is_down[op.parent] = 1;
+  }
+  for (int o = 0; o < n_ops; ++o)
+    for (int c : {ops[o].left, ops[o].right}) {
+      const int u = up_slot[c];
+      if (u < 0) continue;
+      if (!in_range(u) || u < e->T || is_down[u] || is_up[u])
+        return fail(e, PHYLO_ERR_ARG, "lk_uppass: up_slot[%d] = %d must be a free interior slot of its own", c, u);
+      is_up[u] = 1;
+    }
+  // sources of every update must exist: down CLVs of the siblings, and the parent's up value
+  std::vector<int> upsrc(cap, -1);      // slot holding up[p]
+  std::vector<double> tabove(cap, 0.0); // length of the branch above p
+  upsrc[root_a] = root_b; tabove[root_a] = root_t;
+  upsrc[root_b] = root_a; tabove[root_b] = root_t;
+  struct Upd { int dst, sib, src; double t_sib, t_src; };
+  std::vector<Upd> upd;
+  for (int o = n_ops - 1; o >= 0; --o) {  // reverse post-order = parents first
+    const phylo_op &op = ops[o];
+    const int p = op.parent;
+    const int kids[2] = {op.left, op.right};
+    const double tk[2] = {op.t_left, op.t_right};
+    for (int c = 0; c < 2; ++c) {
+      const int v = kids[c], sib = kids[1 - c];
+      tabove[v] = tk[c];
+      if (up_slot[v] < 0) continue;
+      if (upsrc[p] < 0) return fail(e, PHYLO_ERR_ARG, "lk_uppass: up_slot[%d] is set but its parent %d has no up value (give it a slot, or root the pass there)", v, p);
+      upd.push_back(Upd{up_slot[v], sib, upsrc[p], tk[1 - c], tabove[p]});
+      upsrc[v] = up_slot[v];
+    }
+  }
+  if (upd.empty()) return PHYLO_OK;
+  const int nb = 2 * (int)upd.size();
+  if ((rc = ensure_pt_capacity(e, nb, e->S, e->K)) != PHYLO_OK) return rc;
+  for (const Upd &u : upd)
+    if ((rc = lk_ensure_node(e, u.dst)) != PHYLO_OK) return rc;
+  CK(cudaStreamSynchronize(e->stream));  // hT is about to be rewritten
+  for (size_t i = 0; i < upd.size(); ++i) {
+    e->hT[2 * i] = upd[i].t_sib;
+    e->hT[2 * i + 1] = upd[i].t_src;
+  }
+  if ((rc = build_pt(e, nb)) != PHYLO_OK) return rc;
+  const size_t pk = (size_t)e->K * e->S * e->S;
+  for (size_t i = 0; i < upd.size(); ++i) {
+    Operand l, r;
+    if ((rc = lk_operand(e, upd[i].sib, &l, "lk_uppass")) != PHYLO_OK) return rc;
+    if ((rc = lk_operand(e, upd[i].src, &r, "lk_uppass")) != PHYLO_OK) return rc;
+    LkNode &dst = e->nodes[upd[i].dst];
+    rc = lk_launch_prune(e, e->dP + (size_t)(2 * i) * pk, e->dP + (size_t)(2 * i + 1) * pk, l, r, dst.clv, dst.scale);
+    if (rc != PHYLO_OK) return rc;
+    dst.valid = true;
+  }
+  e->edge_ready = false;
   if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }

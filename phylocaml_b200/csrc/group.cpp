@@ -7,8 +7,10 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -26,6 +28,7 @@ struct Worker {
   std::function<int()> job;
   bool has_job = false, done = false, quit = false;
   int rc = PHYLO_OK;
+  std::string host_error;  // set when the job itself threw (the engine's message is not the cause then)
 
   Worker() {
     th = std::thread([this] {
@@ -37,12 +40,21 @@ struct Worker {
         has_job = false;
         lk.unlock();
         int r;
+        std::string herr;
         try {
           r = j();
-        } catch (...) {  // e.g. std::bad_alloc in a host-side vector: report, never unwind out of the thread
-          r = PHYLO_ERR_STATE;
+        } catch (const std::bad_alloc &) {  // report, never unwind out of the thread
+          r = PHYLO_ERR_CUDA;
+          herr = "host exception in worker: out of memory";
+        } catch (const std::exception &ex) {
+          r = PHYLO_ERR_CUDA;
+          herr = std::string("host exception in worker: ") + ex.what();
+        } catch (...) {
+          r = PHYLO_ERR_CUDA;
+          herr = "host exception in worker";
         }
         lk.lock();
+        host_error = herr;
         rc = r;
         done = true;
         cv.notify_all();
@@ -111,20 +123,30 @@ static int gfail(phylo_group *g, int code, const std::string &msg) {
 static int fan_out(phylo_group *g, const std::function<bool(int)> &active, const std::function<int(int)> &fn,
                    const char *who) {
   const int n = (int)g->eng.size();
-  std::vector<char> posted(n, 0);
-  for (int i = 0; i < n; ++i)
-    if (active(i)) {
-      g->workers[i]->post([&fn, i] { return fn(i); });
-      posted[i] = 1;
-    }
+  std::vector<char> posted;
+  try {  // nothing may unwind through the extern "C" entry points that call this
+    posted.assign(n, 0);
+    for (int i = 0; i < n; ++i)
+      if (active(i)) {
+        g->workers[i]->post([&fn, i] { return fn(i); });
+        posted[i] = 1;
+      }
+  } catch (...) {
+    for (int i = 0; i < (int)posted.size(); ++i)
+      if (posted[i]) g->workers[i]->wait();
+    return gfail(g, PHYLO_ERR_CUDA, std::string(who) + ": host exception while dispatching the shards (out of memory?)");
+  }
   int first_rc = PHYLO_OK, first = -1;
   for (int i = 0; i < n; ++i)
     if (posted[i]) {
       const int rc = g->workers[i]->wait();
       if (rc != PHYLO_OK && first_rc == PHYLO_OK) { first_rc = rc; first = i; }
     }
-  if (first_rc != PHYLO_OK)
-    return gfail(g, first_rc, std::string(who) + ": shard " + std::to_string(first) + ": " + phylo_last_error(g->eng[first]));
+  if (first_rc != PHYLO_OK) {
+    const std::string &herr = g->workers[first]->host_error;
+    return gfail(g, first_rc, std::string(who) + ": shard " + std::to_string(first) + ": " +
+                                  (herr.empty() ? std::string(phylo_last_error(g->eng[first])) : herr));
+  }
   return PHYLO_OK;
 }
 

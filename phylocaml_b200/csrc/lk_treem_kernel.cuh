@@ -1,0 +1,674 @@
+// Tree-fused pruning for 20 / 61 states on the fp64 tensor cores (BASELINE configs 4 and 5).
+//
+// One launch evaluates the whole compiled schedule (build_fused_plan, engine.cu). Where the
+// per-node path (prune_mma_kernel) streams every child CLV back in from HBM -- 3C + 12 bytes per
+// update, 81.5 GB for config 4 -- this kernel keeps the running result of the depth-first walk in
+// shared memory and only WRITES each interior CLV once (C + 4 bytes per update, 40.6 GB): the
+// value a median needs next is, two times out of three, the one the warp has just produced.
+//
+// Organisation (CTA-synchronous, unlike the warp-autonomous 4-state kernel: here the transition
+// matrices are 15-32 KB per branch, so they must be shared by many pattern groups to be affordable):
+//   * a CTA owns a contiguous range of 8-pattern groups and walks it in chunks of NW * R groups
+//     (warp w carries groups w, w + NW, ... of the chunk, so a short last chunk still spreads over
+//     all warps); every chunk runs the whole program, one __syncthreads per step;
+//   * the two DMMA A-fragment tables of a step (pt_frag_kernel lays P out as [k][mt][ks][lane]) arrive
+//     by bulk-TMA into a double buffer, requested one step ahead, completion on an mbarrier
+//     (SASS UBLKCP + SYNCS). They come out of L2: 3.9 MB for all branches of config 4;
+//   * 20 states: the 15 A fragments of a (side, rate class) are loaded into registers ONCE per step
+//     and reused for the warp's R groups -- the per-node kernel re-reads them from shared memory for
+//     every group, which is what kept its LSU 77 % busy next to a 58 % tensor pipe;
+//   * the DMMA chains of a group (row tiles x two sides) are independent accumulators advanced
+//     together k-step by k-step: with 2 warps per scheduler the dependent-issue latency of a chain
+//     would otherwise be the limiter (first version: 32 % of all stall samples on DMMA -> DMMA waits);
+//   * operand kinds are compile-time inside the step body (the host orders every median so that
+//     kind(left) <= kind(right): tip < running value < node slot; x * y is commutative bit for bit):
+//     TIP = state masks (one coalesced load per warp and step, prefetched a step ahead; all-observed
+//     groups take column j of P straight from the A table, no DMMA, bit-identical), CUR = the warp's
+//     own previous result in shared memory ([k][pattern][PITCH], PITCH = 4 mod 16 doubles:
+//     conflict-free B-fragment reads), GLB = a retained CLV read back from its node slot (written a
+//     few steps earlier by this same warp: an L2 hit). There is no separate stack: every result is
+//     retained in its node slot anyway, so "pop" is "read the slot";
+//   * results leave in C-fragment layout exactly as in prune_mma_kernel (128-bit stores for 20
+//     states), per-site rescaling by the same rule (site maximum over all K * S entries < 2^-256
+//     => times 2^256, counter + 1), scale counters of the running value live in registers;
+//   * the root-edge join is the program's last step: site lnL (and weight * lnL) go to global
+//     memory, the canonical 1024-fold runs over them afterwards (reduce1024_kernel) -- the sum does
+//     not depend on how the patterns were cut into groups, CTAs or devices.
+//
+// DMMA chains: the k-steps of a row tile are accumulated in ascending order from zero, contraction
+// index j = 4 ks + fc (prune_mma_kernel uses a different j <-> slot map for 20 states, so CLVs agree
+// with it to rounding, ~1e-16 relative, not bit for bit; tests hold both to the oracle).
+#pragma once
+#include <type_traits>
+
+#include "lk_kernels.cuh"
+
+namespace phylo {
+
+enum : int { TM_TIP = 0, TM_CUR = 1, TM_GLB = 2 };  // operand modes of this kernel
+
+struct __align__(16) TreeMInstr {
+  int kinds;       // lmode | rmode << 2; medians: lmode <= rmode
+  int lidx, ridx;  // tip row (TM_TIP) or node slot (TM_GLB)
+  int out_slot;    // node slot that receives the result; -1: the root-edge join
+};
+
+struct TreeMArgs {
+  const TreeMInstr *prog;
+  int n_steps;  // medians; step n_steps is the root-edge join
+  int K;
+  const double *frags;  // [2 n_steps + 1][K][MT][KS][32]: left, right of step 0, 1, ...; last: root edge
+  const void *tips;     // MaskT [T][tip_stride]
+  int64_t tip_stride, N;
+  double *const *node_clv;
+  int32_t *const *node_sc;
+  const double *pi, *probs, *weights;
+  const void *inv;
+  double pinvar;
+  double *site_lnl, *wsite;
+  const char *tmaps;  // 20 states: CUtensorMap per node slot (128 bytes each), dims (S, N, K), box (S, 8, K)
+};
+
+constexpr int treem_pitch(int cols) {
+  int p = cols;
+  while (p % 16 != 4 && p % 16 != 12) p += 4;
+  return p;
+}
+template <int S>
+struct TreeMGeom {
+  static constexpr int MT = (S + 7) / 8, KS = (S + 3) / 4, FRAG = MT * KS * 32, PITCH = treem_pitch(KS * 4);
+};
+template <int S>
+__host__ __device__ inline size_t treem_smem_bytes(int K, int R, int NW) {
+  using G = TreeMGeom<S>;
+  return 128 + sizeof(double) * (4 * (size_t)K * G::FRAG + ((S + 15) & ~15) + (size_t)NW * R * K * 8 * G::PITCH);
+}
+
+// P ([branch * K + k][i][j], pt_build_kernel) -> the on-chip tables of the tree kernel, FRAG doubles each.
+// DMMA A fragments [mt][ks][lane]: lane (fr = lane / 4, fc = lane % 4) of row tile mt, k-step ks holds
+// P[i_of(mt, fr)][4 ks + fc]. For the TIP side of a median with 20 states the table is the transpose
+// instead, PT[j][24] = P[0..19][j] padded with zeros: an observed tip state j contributes column j of P,
+// which a lane then reads as one 128-bit + one 64-bit access (rows 2 fr, 2 fr + 1 and 16 + fr).
+template <int S>
+__global__ void __launch_bounds__(256) pt_frag_kernel(const double *__restrict__ P, double *__restrict__ frags,
+                                                      const TreeMInstr *__restrict__ prog, int n_steps, int K) {
+  using G = TreeMGeom<S>;
+  const double *src = P + (size_t)blockIdx.x * S * S;
+  double *dst = frags + (size_t)blockIdx.x * G::FRAG;
+  const int branch = blockIdx.x / K, step = branch >> 1;
+  const bool transposed = MmaMap<S>::kVec && step < n_steps && ((prog[step].kinds >> (2 * (branch & 1))) & 3) == TM_TIP;
+  for (int idx = threadIdx.x; idx < G::FRAG; idx += blockDim.x) {
+    if (transposed) {
+      const int j = idx / 24, i = idx % 24;
+      dst[idx] = i < S ? src[i * S + j] : 0.0;
+    } else {
+      const int l = idx & 31, ks = (idx >> 5) % G::KS, mt = (idx >> 5) / G::KS;
+      const int i = MmaMap<S>::i_of(mt, l >> 2), j = ks * 4 + (l & 3);
+      dst[idx] = (i < S && j < S) ? src[i * S + j] : 0.0;
+    }
+  }
+}
+
+template <typename MaskT>
+__device__ __forceinline__ MaskT shfl_mask(MaskT v, int src) {
+  if constexpr (sizeof(MaskT) == 8) return (MaskT)__shfl_sync(0xffffffffu, (unsigned long long)v, src);
+  else return (MaskT)__shfl_sync(0xffffffffu, (unsigned)v, src);
+}
+__device__ __forceinline__ void sts128(double *p, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(smem_u32(p)), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void lds128(const double *p, double &a, double &b) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void tma_store_3d(const void *tmap, const void *smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// not volatile: a pure function of its operands, so independent chains may be interleaved
+__device__ __forceinline__ void dmma_acc(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+template <int S, typename MaskT, int R, int NW, int KT>
+__global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a) {
+  using G = TreeMGeom<S>;
+  using Map = MmaMap<S>;
+  constexpr int MT = G::MT, KS = G::KS, FRAG = G::FRAG, PITCH = G::PITCH;
+  constexpr bool AREG = MT * KS <= 16;  // A fragments of one (side, rate class) fit in registers
+  constexpr bool PF = AREG;             // registers to spare: node-slot operands are fetched one group ahead
+  constexpr bool PT = Map::kVec;        // tip sides read the transposed table (20 states)
+  constexpr bool TMA = Map::kVec;       // results leave by TMA tensor stores from the running-value buffer (16-byte rows)
+  constexpr int MTB = Map::kVec ? MT : (MT % 4 == 0 ? 4 : (MT % 2 == 0 ? 2 : 1));  // row tiles in flight together
+  static_assert(!Map::kVec || MT == 3, "the 128-bit store path expects three row tiles");
+  constexpr unsigned FULL = 0xffffffffu;
+  static_assert(R >= 1 && R <= 4, "a warp's tip masks travel in one register per side: R * 8 <= 32");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int K = KT ? KT : a.K;
+  uint64_t *bar = (uint64_t *)smem_raw;
+  unsigned long long *sptr = (unsigned long long *)(smem_raw + 16);  // [2][6] node-slot pointers of a step
+  double *pbuf = (double *)(smem_raw + 128);
+  const int side = K * FRAG;  // doubles per side
+  double *spi = pbuf + 4 * side;
+  double *curbase = spi + ((S + 15) & ~15);  // 128-byte aligned: the groups' running CLVs are TMA store sources
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int gsz = K * 8 * PITCH;  // doubles of one group's running CLV
+  for (int idx = tid; idx < NW * R * gsz; idx += NW * 32) curbase[idx] = 0.0;  // pad columns stay 0
+  for (int i = tid; i < S; i += NW * 32) spi[i] = a.pi[i];
+  // the six node-slot pointers a step may need (left / right / out CLV, then their scale arrays): fetched by
+  // lanes 0-5 of warp 0 one step ahead and handed over through shared memory, so no warp waits on the
+  // pointer tables (global memory) at the head of a step
+  auto slot_ptr = [&](const TreeMInstr &in) -> unsigned long long {
+    const int which = lane % 3;
+    const int idx = which == 0 ? in.lidx : (which == 1 ? in.ridx : in.out_slot);
+    const bool glb = which == 0 ? (in.kinds & 3) == TM_GLB : (which == 1 ? ((in.kinds >> 2) & 3) == TM_GLB : in.out_slot >= 0);
+    if (!glb) return 0ull;
+    return lane < 3 ? (unsigned long long)a.node_clv[idx] : (unsigned long long)a.node_sc[idx];
+  };
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane < 6) sptr[lane] = slot_ptr(a.prog[0]);
+  __syncthreads();
+
+  const int64_t ngroups = (a.N + 7) / 8;
+  const int64_t g0 = ngroups * blockIdx.x / gridDim.x, g1 = ngroups * (blockIdx.x + 1) / gridDim.x;
+  const int nst = a.n_steps + 1;
+  constexpr int CH = NW * R;
+  const int64_t nchunks = (g1 - g0 + CH - 1) / CH;
+  const uint64_t total_it = (uint64_t)nchunks * nst;
+  const uint32_t side_bytes = (uint32_t)side * 8u;
+  auto issue = [&](uint64_t it) {  // thread 0: request the tables of global step `it`
+    const int s = (int)(it % nst), buf = (int)(it & 1);
+    fence_proxy_async();
+    const bool root = s == a.n_steps;
+    mbar_expect_tx(&bar[buf], root ? side_bytes : 2 * side_bytes);
+    const double *src = a.frags + (size_t)(2 * s) * side;
+    bulk_g2s(pbuf + buf * 2 * side, src, side_bytes, &bar[buf]);
+    if (!root) bulk_g2s(pbuf + buf * 2 * side + side, src + side, side_bytes, &bar[buf]);
+  };
+  if (tid == 0 && total_it > 0) issue(0);
+
+  const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
+  const MaskT *tips = (const MaskT *)a.tips;
+  double *cur = curbase + warp * R * gsz;  // [r][k][8][PITCH]
+  const double kLnScale = kScaleExp * 0.6931471805599453094;
+  uint64_t it = 0;
+  for (int64_t chunk = 0; chunk < nchunks; ++chunk) {
+    const int64_t cbase = g0 + chunk * CH;
+    // groups cbase + r * NW + warp, r < nact, are this warp's; only the alignment's last group can be ragged
+    int nact = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nact += (cbase + (int64_t)r * NW + warp < g1) ? 1 : 0;
+    // lane l < R * 8 fetches the mask of pattern l % 8 of this warp's group l / 8
+    const int64_t mg = cbase + (int64_t)(lane >> 3) * NW + warp;
+    const int64_t mp = mg * 8 + (lane & 7);
+    const bool mok = lane < R * 8 && mg < g1 && mp < a.N;
+    auto load_masks = [&](const TreeMInstr &in, MaskT &ml, MaskT &mr) {  // raw: `& keep` happens at the use
+      ml = 0;
+      mr = 0;
+      if ((in.kinds & 3) == TM_TIP && mok) ml = tips[(size_t)in.lidx * a.tip_stride + mp];
+      if (((in.kinds >> 2) & 3) == TM_TIP && mok) mr = tips[(size_t)in.ridx * a.tip_stride + mp];
+    };
+    TreeMInstr ins = a.prog[0];
+    MaskT ml, mr;
+    load_masks(ins, ml, mr);
+    ml &= keep;
+    mr &= keep;
+    int csc0[R], csc1[R];  // scale counters of the running values (patterns 2 fc, 2 fc + 1 of group r)
+#pragma unroll
+    for (int r = 0; r < R; ++r) csc0[r] = csc1[r] = 0;
+
+#pragma unroll 1
+    for (int s = 0; s < nst; ++s, ++it) {
+      if (tid == 0 && it + 1 < total_it) issue(it + 1);
+      TreeMInstr nins = ins;
+      MaskT nml = 0, nmr = 0;
+      unsigned long long next_ptr = 0;
+      if (s + 1 < nst) {
+        nins = a.prog[s + 1];
+        load_masks(nins, nml, nmr);
+        if (warp == 0 && lane < 6) next_ptr = slot_ptr(nins);
+      } else if (warp == 0 && lane < 6 && it + 1 < total_it) {
+        next_ptr = slot_ptr(a.prog[0]);
+      }
+      const int lk = ins.kinds & 3, rk = (ins.kinds >> 2) & 3;
+      const unsigned long long *sp = sptr + (it & 1) * 6;
+      const double *lg = (const double *)sp[0], *rg = (const double *)sp[1];
+      double *og = (double *)sp[2];
+      const int32_t *lgs = (const int32_t *)sp[3], *rgs = (const int32_t *)sp[4];
+      int32_t *ogs = (int32_t *)sp[5];
+      const unsigned lhotbits = __ballot_sync(FULL, (ml & (ml - 1)) == 0);
+      const unsigned rhotbits = __ballot_sync(FULL, (mr & (mr - 1)) == 0);
+      const int buf = (int)(it & 1);
+      const double *fl = pbuf + buf * 2 * side, *frg = fl + side;
+      mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+
+      // B fragment of an operand for rate class k of group r (lane = pattern fr, columns 4 ks + fc)
+      auto fetch_cur = [&](double (&b)[KS], int r, int k) {
+        const double *row = cur + r * gsz + (k * 8 + fr) * PITCH + fc;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) b[ks] = row[ks * 4];
+      };
+      auto fetch_glb = [&](double (&b)[KS], const double *g, int k, int64_t pbase) {
+        const bool ok = pbase + fr < a.N;
+        const double *row = g + ((size_t)(pbase + fr) * K + k) * S + fc;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) b[ks] = (ok && ks * 4 + fc < S) ? row[ks * 4] : 0.0;
+      };
+      // column of the A table that holds P[.][j] for this lane's row slot: + mt * KS * 32
+      auto hot_col = [&](MaskT m) {
+        int j;
+        if constexpr (sizeof(MaskT) == 8) j = m ? __ffsll((long long)m) - 1 : 0;
+        else j = m ? __ffs((int)m) - 1 : 0;
+        return (j >> 2) * 32 + fr * 4 + (j & 3);
+      };
+
+      if (s < a.n_steps) {
+        // ------------------------------------------------------------------ a median
+        auto median = [&](auto LMc, auto RMc) {
+          constexpr int LM = decltype(LMc)::value, RM = decltype(RMc)::value;
+          int h0[R], h1[R];
+          int colL0[R], colL1[R], colR0[R], colR1[R];
+          MaskT mlb[R], mrb[R];
+          int gs0[R], gs1[R];    // summed scale counters of the node-slot operands (loaded early, used late)
+          unsigned hotmask = 0;  // bit r: left tip all observed; bit 4 + r: right
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            h0[r] = h1[r] = (int)0x80000000;
+            colL0[r] = colL1[r] = colR0[r] = colR1[r] = 0;
+            mlb[r] = mrb[r] = 0;
+            gs0[r] = gs1[r] = 0;
+            if (LM == TM_TIP) {
+              const bool hot = ((lhotbits >> (r * 8)) & 0xffu) == 0xffu;
+              if (hot) hotmask |= 1u << r;
+              if constexpr (PT) {  // colL* hold the MASKS of the lane's two result patterns
+                colL0[r] = (int)shfl_mask(ml, r * 8 + 2 * fc);
+                colL1[r] = (int)shfl_mask(ml, r * 8 + 2 * fc + 1);
+              } else if (hot) {
+                colL0[r] = hot_col(shfl_mask(ml, r * 8 + 2 * fc));
+                colL1[r] = hot_col(shfl_mask(ml, r * 8 + 2 * fc + 1));
+              } else {
+                mlb[r] = shfl_mask(ml, r * 8 + fr);
+              }
+            }
+            if (RM == TM_TIP) {
+              const bool hot = ((rhotbits >> (r * 8)) & 0xffu) == 0xffu;
+              if (hot) hotmask |= 16u << r;
+              if constexpr (PT) {
+                colR0[r] = (int)shfl_mask(mr, r * 8 + 2 * fc);
+                colR1[r] = (int)shfl_mask(mr, r * 8 + 2 * fc + 1);
+              } else if (hot) {
+                colR0[r] = hot_col(shfl_mask(mr, r * 8 + 2 * fc));
+                colR1[r] = hot_col(shfl_mask(mr, r * 8 + 2 * fc + 1));
+              } else {
+                mrb[r] = shfl_mask(mr, r * 8 + fr);
+              }
+            }
+            if ((LM == TM_GLB || RM == TM_GLB) && r < nact) {
+              const int64_t pa0 = (cbase + (int64_t)r * NW + warp) * 8 + 2 * fc;
+              if (RM == TM_GLB) {
+                if (pa0 < a.N) gs0[r] += rgs[pa0];
+                if (pa0 + 1 < a.N) gs1[r] += rgs[pa0 + 1];
+              }
+              if (LM == TM_GLB) {
+                if (pa0 < a.N) gs0[r] += lgs[pa0];
+                if (pa0 + 1 < a.N) gs1[r] += lgs[pa0 + 1];
+              }
+            }
+          }
+          if constexpr (TMA) {
+            // the previous step's tensor stores still read the running-value buffers; a node-slot operand
+            // must also have LANDED (it may be the result of two steps ago)
+            if (lane == 0) {
+              if (LM == TM_GLB || RM == TM_GLB) bulk_wait0();
+              else bulk_wait_read0();
+            }
+            __syncwarp();
+          }
+          double pre[(PF && RM == TM_GLB) ? KS : 1];  // right operand's fragment for the NEXT (k, group)
+          if constexpr (PF && RM == TM_GLB) fetch_glb(pre, rg, 0, (cbase + warp) * 8);
+#pragma unroll 1
+          for (int k = 0; k < K; ++k) {
+            const double *tabL = fl + k * FRAG, *tabR = frg + k * FRAG;
+            double al[(AREG && LM != TM_TIP) ? MT * KS : 1], ar[(AREG && RM != TM_TIP) ? MT * KS : 1];
+            if constexpr (AREG && LM != TM_TIP) {
+#pragma unroll
+              for (int q = 0; q < MT * KS; ++q) al[q] = tabL[q * 32 + lane];
+            }
+            if constexpr (AREG && RM != TM_TIP) {
+#pragma unroll
+              for (int q = 0; q < MT * KS; ++q) ar[q] = tabR[q * 32 + lane];
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (r >= nact) break;  // warp-uniform
+              const int64_t pbase = (cbase + (int64_t)r * NW + warp) * 8, pa0 = pbase + 2 * fc;
+              const bool lhot = LM == TM_TIP && ((hotmask >> r) & 1u), rhot = RM == TM_TIP && ((hotmask >> (4 + r)) & 1u);
+              double bl[LM != TM_TIP ? KS : 1], br[RM != TM_TIP ? KS : 1];
+              if constexpr (LM == TM_CUR) fetch_cur(bl, r, k);
+              if constexpr (LM == TM_GLB) fetch_glb(bl, lg, k, pbase);
+              if constexpr (RM == TM_CUR) fetch_cur(br, r, k);
+              if constexpr (RM == TM_GLB) {
+                if constexpr (PF) {
+#pragma unroll
+                  for (int ks = 0; ks < KS; ++ks) br[ks] = pre[ks];
+                  const bool wrap = r + 1 >= nact;
+                  const int nk = wrap ? k + 1 : k, nr = wrap ? 0 : r + 1;
+                  if (nk < K) fetch_glb(pre, rg, nk, (cbase + (int64_t)nr * NW + warp) * 8);
+                } else {
+                  fetch_glb(br, rg, k, pbase);
+                }
+              }
+              if (LM == TM_CUR || RM == TM_CUR) __syncwarp();  // the result overwrites the running value just read
+              double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH, *c1 = c0 + PITCH;
+              double *o0 = og + ((size_t)pa0 * K + k) * S, *o1 = o0 + (size_t)K * S;
+              const bool pa0_ok = pa0 < a.N, pa1_ok = pa0 + 1 < a.N;
+              // MTB row tiles of both sides advance together: up to 2 MTB independent accumulator chains
+#pragma unroll
+              for (int m0 = 0; m0 < MT; m0 += MTB) {
+                double cx[MTB][2], cy[MTB][2];
+#pragma unroll
+                for (int m = 0; m < MTB; ++m) cx[m][0] = cx[m][1] = cy[m][0] = cy[m][1] = 0.0;
+                if constexpr (PT) {
+                  // tip side, 20 states: column j of P from the transposed table; a pattern with several
+                  // possible states (rare) adds its columns in ascending j -- the oracle's own order
+                  auto tip_side = [&](const double *pt, bool hot, unsigned mk0, unsigned mk1, double (&c)[MTB][2]) {
+                    if (hot) {
+                      const int j0 = mk0 ? __ffs((int)mk0) - 1 : 0, j1 = mk1 ? __ffs((int)mk1) - 1 : 0;
+                      lds128(pt + j0 * 24 + 2 * fr, c[0][0], c[1][0]);
+                      lds128(pt + j1 * 24 + 2 * fr, c[0][1], c[1][1]);
+                      c[2][0] = pt[j0 * 24 + 16 + fr];
+                      c[2][1] = pt[j1 * 24 + 16 + fr];
+                    } else {
+#pragma unroll 1
+                      for (int j = 0; j < S; ++j) {
+                        const double *col = pt + j * 24;
+                        if ((mk0 >> j) & 1) { c[0][0] += col[2 * fr]; c[1][0] += col[2 * fr + 1]; c[2][0] += col[16 + fr]; }
+                        if ((mk1 >> j) & 1) { c[0][1] += col[2 * fr]; c[1][1] += col[2 * fr + 1]; c[2][1] += col[16 + fr]; }
+                      }
+                    }
+                  };
+                  if constexpr (LM == TM_TIP) tip_side(tabL, lhot, (unsigned)colL0[r], (unsigned)colL1[r], cx);
+                  if constexpr (RM == TM_TIP) tip_side(tabR, rhot, (unsigned)colR0[r], (unsigned)colR1[r], cy);
+                } else {
+#pragma unroll
+                  for (int m = 0; m < MTB; ++m) {
+                    if (lhot) {
+                      cx[m][0] = tabL[(m0 + m) * KS * 32 + colL0[r]];
+                      cx[m][1] = tabL[(m0 + m) * KS * 32 + colL1[r]];
+                    }
+                    if (rhot) {
+                      cy[m][0] = tabR[(m0 + m) * KS * 32 + colR0[r]];
+                      cy[m][1] = tabR[(m0 + m) * KS * 32 + colR1[r]];
+                    }
+                  }
+                  // a tip with an ambiguous / missing pattern in this group (rare): fragments from the mask bits,
+                  // A from the table; a rolled loop, so that it stays a branch around and not predicated code
+                  if (LM == TM_TIP && !lhot) {
+#pragma unroll 1
+                    for (int ks = 0; ks < KS; ++ks) {
+                      const double b = ((mlb[r] >> (ks * 4 + fc)) & 1) ? 1.0 : 0.0;
+#pragma unroll
+                      for (int m = 0; m < MTB; ++m) dmma_acc(cx[m], tabL[((m0 + m) * KS + ks) * 32 + lane], b);
+                    }
+                  }
+                  if (RM == TM_TIP && !rhot) {
+#pragma unroll 1
+                    for (int ks = 0; ks < KS; ++ks) {
+                      const double b = ((mrb[r] >> (ks * 4 + fc)) & 1) ? 1.0 : 0.0;
+#pragma unroll
+                      for (int m = 0; m < MTB; ++m) dmma_acc(cy[m], tabR[((m0 + m) * KS + ks) * 32 + lane], b);
+                    }
+                  }
+                }
+                if constexpr (LM != TM_TIP || RM != TM_TIP) {
+#pragma unroll
+                  for (int ks = 0; ks < KS; ++ks) {
+                    if constexpr (LM != TM_TIP) {
+#pragma unroll
+                      for (int m = 0; m < MTB; ++m) {
+                        double av;
+                        if constexpr (AREG) av = al[(m0 + m) * KS + ks];
+                        else av = tabL[((m0 + m) * KS + ks) * 32 + lane];
+                        dmma_acc(cx[m], av, bl[ks]);
+                      }
+                    }
+                    if constexpr (RM != TM_TIP) {
+#pragma unroll
+                      for (int m = 0; m < MTB; ++m) {
+                        double av;
+                        if constexpr (AREG) av = ar[(m0 + m) * KS + ks];
+                        else av = tabR[((m0 + m) * KS + ks) * 32 + lane];
+                        dmma_acc(cy[m], av, br[ks]);
+                      }
+                    }
+                  }
+                }
+                if constexpr (Map::kVec) {
+                  const double a0 = cx[0][0] * cy[0][0], a1 = cx[0][1] * cy[0][1];
+                  const double b0 = cx[1][0] * cy[1][0], b1 = cx[1][1] * cy[1][1];
+                  const double d0 = cx[2][0] * cy[2][0], d1 = cx[2][1] * cy[2][1];
+                  sts128(c0 + 2 * fr, a0, b0);
+                  sts128(c1 + 2 * fr, a1, b1);
+                  h0[r] = max(h0[r], max(hi32(a0), hi32(b0)));
+                  h1[r] = max(h1[r], max(hi32(a1), hi32(b1)));
+                  if (fr < 4) {
+                    c0[16 + fr] = d0;
+                    c1[16 + fr] = d1;
+                    h0[r] = max(h0[r], hi32(d0));
+                    h1[r] = max(h1[r], hi32(d1));
+                  }
+                  if constexpr (!TMA) {
+                    if (pa0_ok) {
+                      st128(o0 + 2 * fr, a0, b0);
+                      if (fr < 4) o0[16 + fr] = d0;
+                    }
+                    if (pa1_ok) {
+                      st128(o1 + 2 * fr, a1, b1);
+                      if (fr < 4) o1[16 + fr] = d1;
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int m = 0; m < MTB; ++m) {
+                    const double v0 = cx[m][0] * cy[m][0], v1 = cx[m][1] * cy[m][1];
+                    const int i = Map::i_of(m0 + m, fr);
+                    if (i < S) {
+                      c0[i] = v0;
+                      c1[i] = v1;
+                      h0[r] = max(h0[r], hi32(v0));
+                      h1[r] = max(h1[r], hi32(v1));
+                      if (pa0_ok) o0[i] = v0;
+                      if (pa1_ok) o1[i] = v1;
+                    }
+                  }
+                }
+              }
+            }
+          }
+          // per-site rescaling and scale counters
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (r >= nact) break;
+            const int64_t pa0 = (cbase + (int64_t)r * NW + warp) * 8 + 2 * fc;
+            const bool pa0_ok = pa0 < a.N, pa1_ok = pa0 + 1 < a.N;
+            int m0 = h0[r], m1 = h1[r];
+#pragma unroll
+            for (int off = 4; off <= 16; off <<= 1) {
+              m0 = max(m0, __shfl_xor_sync(FULL, m0, off));
+              m1 = max(m1, __shfl_xor_sync(FULL, m1, off));
+            }
+            const bool r0 = pa0_ok && m0 < kScaleHiThresh, r1 = pa1_ok && m1 < kScaleHiThresh;
+            if (r0 || r1) {  // rare: every lane rescales what it stored (both copies); rolled loops
+#pragma unroll 1
+              for (int k = 0; k < K; ++k) {
+                double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH, *c1 = c0 + PITCH;
+                double *o0 = og + ((size_t)pa0 * K + k) * S, *o1 = o0 + (size_t)K * S;
+#pragma unroll 1
+                for (int mt = 0; mt < MT; ++mt) {
+                  const int i = Map::i_of(mt, fr);
+                  if (i < S) {
+                    if (r0) { c0[i] *= 0x1p+256; if (!TMA) o0[i] = c0[i]; }
+                    if (r1) { c1[i] *= 0x1p+256; if (!TMA) o1[i] = c1[i]; }
+                  }
+                }
+              }
+            }
+            int s0 = gs0[r], s1 = gs1[r];
+            if (LM == TM_CUR || RM == TM_CUR) { s0 += csc0[r]; s1 += csc1[r]; }
+            s0 += r0 ? 1 : 0;
+            s1 += r1 ? 1 : 0;
+            csc0[r] = s0;
+            csc1[r] = s1;
+            if (fr == 0) {
+              if (pa0_ok) ogs[pa0] = s0;
+              if (pa1_ok) ogs[pa0 + 1] = s1;
+            }
+            if constexpr (TMA) {
+              // the group's finished CLV [k][8][S] -> node slot [pattern][k][S]: one tensor store (rows >= N clipped)
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(a.tmaps + (size_t)ins.out_slot * 128, cur + r * gsz, 0, (int)(pa0 - 2 * fc), 0);
+                bulk_commit();
+              }
+            }
+          }
+        };
+        using I0 = std::integral_constant<int, TM_TIP>;
+        using I1 = std::integral_constant<int, TM_CUR>;
+        using I2 = std::integral_constant<int, TM_GLB>;
+        switch (ins.kinds & 15) {  // lmode | rmode << 2, lmode <= rmode (host-normalised)
+          case TM_TIP | (TM_TIP << 2): median(I0{}, I0{}); break;
+          case TM_TIP | (TM_CUR << 2): median(I0{}, I1{}); break;
+          case TM_TIP | (TM_GLB << 2): median(I0{}, I2{}); break;
+          case TM_CUR | (TM_GLB << 2): median(I1{}, I2{}); break;
+          default: median(I2{}, I2{}); break;
+        }
+      } else {
+        // ------------------------------------------------------ the root-edge join (a = left, b = right)
+        const bool ltip = lk == TM_TIP, rtip = rk == TM_TIP, lcur = lk == TM_CUR, rcur = rk == TM_CUR;
+        const MaskT *inv = (const MaskT *)a.inv;
+        if constexpr (TMA) {
+          if (lane == 0) bulk_wait0();
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int r = 0; r < nact; ++r) {
+          const int64_t pbase = (cbase + (int64_t)r * NW + warp) * 8, pa0 = pbase + 2 * fc;
+          const bool pa0_ok = pa0 < a.N, pa1_ok = pa0 + 1 < a.N;
+          const bool bhot = rtip && ((rhotbits >> (r * 8)) & 0xffu) == 0xffu;
+          int col_b0 = 0, col_b1 = 0;
+          MaskT mbb = 0, ma0 = 0, ma1 = 0;
+          if (rtip) {
+            if (bhot) {
+              col_b0 = hot_col(shfl_mask(mr, r * 8 + 2 * fc));
+              col_b1 = hot_col(shfl_mask(mr, r * 8 + 2 * fc + 1));
+            } else {
+              mbb = shfl_mask(mr, r * 8 + fr);
+            }
+          }
+          if (ltip) {
+            ma0 = shfl_mask(ml, r * 8 + 2 * fc);
+            ma1 = shfl_mask(ml, r * 8 + 2 * fc + 1);
+          }
+          const int sca0 = (r == 0 ? csc0[0] : r == 1 ? csc0[R > 1 ? 1 : 0] : r == 2 ? csc0[R > 2 ? 2 : 0] : csc0[R > 3 ? 3 : 0]);
+          const int sca1 = (r == 0 ? csc1[0] : r == 1 ? csc1[R > 1 ? 1 : 0] : r == 2 ? csc1[R > 2 ? 2 : 0] : csc1[R > 3 ? 3 : 0]);
+          double l0 = 0.0, l1 = 0.0;
+#pragma unroll 1
+          for (int k = 0; k < K; ++k) {
+            const double *fk0 = fl + k * FRAG;
+            double bb[KS];
+            if (!bhot) {
+              if (rtip) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) bb[ks] = ((mbb >> (ks * 4 + fc)) & 1) ? 1.0 : 0.0;
+              } else if (rcur) {
+                fetch_cur(bb, r, k);
+              } else {
+                fetch_glb(bb, rg, k, pbase);
+              }
+            }
+            const double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH, *c1 = c0 + PITCH;
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 2
+            for (int mt = 0; mt < MT; ++mt) {
+              double cy[2] = {0.0, 0.0};
+              if (bhot) {
+                cy[0] = fk0[mt * KS * 32 + col_b0];
+                cy[1] = fk0[mt * KS * 32 + col_b1];
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) dmma_acc(cy, fk0[(mt * KS + ks) * 32 + lane], bb[ks]);
+              }
+              const int i = Map::i_of(mt, fr);
+              if (i < S) {
+                double a0, a1;
+                if (ltip) {
+                  a0 = (double)((ma0 >> i) & 1);
+                  a1 = (double)((ma1 >> i) & 1);
+                } else if (lcur) {
+                  a0 = c0[i];
+                  a1 = c1[i];
+                } else {
+                  a0 = pa0_ok ? lg[((size_t)pa0 * K + k) * S + i] : 0.0;
+                  a1 = pa1_ok ? lg[((size_t)(pa0 + 1) * K + k) * S + i] : 0.0;
+                }
+                acc0 += (spi[i] * a0) * cy[0];
+                acc1 += (spi[i] * a1) * cy[1];
+              }
+            }
+#pragma unroll
+            for (int off = 4; off <= 16; off <<= 1) {
+              acc0 += __shfl_xor_sync(FULL, acc0, off);
+              acc1 += __shfl_xor_sync(FULL, acc1, off);
+            }
+            l0 += a.probs[k] * acc0;
+            l1 += a.probs[k] * acc1;
+          }
+          if (fr == 0) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int64_t p = pa0 + u;
+              if (p < a.N) {
+                const double l = u ? l1 : l0;
+                int c = 0;
+                if (lcur || rcur) c += u ? sca1 : sca0;
+                if (lk == TM_GLB) c += lgs[p];
+                if (rk == TM_GLB) c += rgs[p];
+                double lnl;
+                if (a.pinvar >= 0.0) {
+                  const MaskT m = inv[p];
+                  double pv = 0.0;
+                  for (int i = 0; i < S; ++i)
+                    if ((m >> i) & 1) pv += spi[i];
+                  lnl = lnl_pinvar(l, c, a.pinvar, pv);
+                } else {
+                  lnl = log(l) - (double)c * kLnScale;
+                }
+                if (a.site_lnl) a.site_lnl[p] = lnl;
+                a.wsite[p] = (a.weights ? a.weights[p] : 1.0) * lnl;
+              }
+            }
+          }
+        }
+      }
+      ins = nins;
+      ml = nml & keep;
+      mr = nmr & keep;
+      if (warp == 0 && lane < 6) sptr[((it + 1) & 1) * 6 + lane] = next_ptr;
+      __syncthreads();  // every warp is done with this step's tables (and its global writes are visible CTA-wide)
+    }
+  }
+  if constexpr (TMA) {
+    if (lane == 0) bulk_wait0();
+  }
+}
+
+}  // namespace phylo

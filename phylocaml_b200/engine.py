@@ -67,6 +67,7 @@ SIGNATURES = {
     "phylo_fitch_median_3": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "phylo_bv_eltcount": (C.c_int, [_vp, C.c_int, _i64, C.POINTER(C.c_int)]),
     "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
+    "phylo_lk_uppass": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
     "phylo_plan_compile": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
                                            C.c_int, C.c_int, C.c_double, _dp]),
@@ -409,6 +410,13 @@ class Engine:
 
     def lk_median_3(self, parent, a, t_a, b, t_b, c, t_c):
         self._ck(self.lib.phylo_lk_median_3(self.h, parent, a, float(t_a), b, float(t_b), c, float(t_c)))
+
+    def lk_uppass(self, ops, root_a, root_b, root_t, up_slot):
+        """3-directional CLVs: fill up_slot[v] (one int32 per node slot, -1 = skip) with the CLV of the
+        rest of the tree above v; needs the retained CLVs of a preceding lk_score_tree over `ops`."""
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        up_slot = np.ascontiguousarray(up_slot, dtype=np.int32)
+        self._ck(self.lib.phylo_lk_uppass(self.h, _p(ops), len(ops), root_a, root_b, float(root_t), _p(up_slot)))
 
     def lk_score_tree(self, ops, root_a, root_b, root_t):
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)

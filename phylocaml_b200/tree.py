@@ -173,3 +173,34 @@ def random_fitch_chars(T, N, n_states, seed, ambiguity=0.02, dtype=np.uint8):
     b = rng.integers(0, n_states, size=(T, N))
     codes[amb] |= (1 << b[amb]).astype(np.uint64)
     return codes.astype(dtype)
+
+
+def uppass_plan(ops, root_a, root_b, root_t, first_free_slot):
+    """Slots and schedule of the pre-order pass that phylo_lk_uppass runs (3-directional CLVs,
+    lib/node.ml:363-477): every node below the root edge gets a slot for up[v] = the CLV of the rest of
+    the tree above it. Returns (up_slot int32 array sized `capacity`, capacity, up_ops, edges):
+    up_ops is the same pass as a plain op list (parent = up slot, left = sibling, right = the parent's up
+    value), which the oracle can execute after the down-pass ops; edges = [(v, up_slot[v], t_v)] is every
+    branch below the root edge as a directional pair."""
+    ops = np.asarray(ops)
+    n_up = 2 * len(ops)
+    cap = first_free_slot + n_up
+    up_slot = np.full(cap, -1, dtype=np.int32)
+    nxt = first_free_slot
+    upsrc = {int(root_a): (int(root_b), float(root_t)), int(root_b): (int(root_a), float(root_t))}
+    up_ops = np.zeros(n_up, dtype=ops.dtype)
+    edges, i = [], 0
+    for op in ops[::-1]:
+        p = int(op["parent"])
+        kids = ((int(op["left"]), float(op["t_left"])), (int(op["right"]), float(op["t_right"])))
+        src, t_src = upsrc[p]
+        for c in (0, 1):
+            v, tv = kids[c]
+            sib, ts = kids[1 - c]
+            up_slot[v] = nxt
+            up_ops[i] = (nxt, sib, src, 0, ts, t_src)
+            upsrc[v] = (nxt, tv)
+            edges.append((v, nxt, tv))
+            nxt += 1
+            i += 1
+    return up_slot, cap, up_ops, edges
