@@ -1616,8 +1616,10 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
 // schedule, every interior CLV written once into its node slot, nothing read back from HBM but
 // the (L2-resident) values parked across a subtree.
 template <int S, typename MaskT, int R, int NW, int KT>
-static cudaError_t launch_treem(phylo_engine *e, const TreeMArgs &args, size_t smem) {
+static cudaError_t launch_treem(phylo_engine *e, TreeMArgs args, size_t smem) {
   auto kern = lk_treem_kernel<S, MaskT, R, NW, KT>;
+  args.prog_in_smem = smem + treem_prog_bytes(args.n_steps) <= 227 * 1024;
+  if (args.prog_in_smem) smem += treem_prog_bytes(args.n_steps);
   cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (st != cudaSuccess) return st;
   const int64_t ngroups = (e->N + 7) / 8;
@@ -1631,10 +1633,11 @@ static int lk_score_tree_fusedm(phylo_engine *e, const phylo_op *ops, int n_ops,
   if (!e->opt_fused || !(e->S == 20 || e->S == 61) || n_ops < 1) return PHYLO_OK;
   if (e->S == 20 && !e->encodeTiled) return PHYLO_OK;  // its results leave through TMA tensor maps
   const size_t kMaxSmem = 227 * 1024;
-  int R = 0, NW = 0;
-  NW = 8;
-  for (int r : {4, 2, 1}) {
-    if (e->S == 61 && r > 2) continue;
+  // 20 states: 16 warps x 2 groups (128 registers; A fragments straight from shared memory); 61 states: 8 warps x
+  // 2 groups (the 16 k-steps of B fragments want 255 registers)
+  int R = 0;
+  const int NW = e->S == 20 ? 16 : 8;
+  for (int r : {2, 1}) {
     const size_t need = e->S == 20 ? treem_smem_bytes<20>(e->K, r, NW) : treem_smem_bytes<61>(e->K, r, NW);
     if (need <= kMaxSmem) { R = r; break; }
   }
@@ -1715,20 +1718,39 @@ static int lk_score_tree_fusedm(phylo_engine *e, const phylo_op *ops, int n_ops,
   a.site_lnl = e->dSite;
   a.wsite = e->dWSite;
   a.tmaps = (const char *)e->dTmaps;
+  a.timing = nullptr;
+  static const bool want_timing = [] { const char *v = getenv("PHYLO_TREEM_TIMING"); return v && v[0] == '1'; }();
+  unsigned long long *dTiming = nullptr;
+  if (want_timing) {
+    CK(cudaMalloc(&dTiming, 24 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(dTiming, 0, 24 * sizeof(unsigned long long), e->stream));
+    a.timing = dTiming;
+  }
   {
     ProfScope prof(e, KC_TREE_FUSED);
     cudaError_t st;
-#define TREEM(S_, M_, R_, KT_) launch_treem<S_, M_, R_, 8, KT_>(e, a, treem_smem_bytes<S_>(e->K, R_, 8))
+#define TREEM(S_, M_, R_, NW_, KT_) launch_treem<S_, M_, R_, NW_, KT_>(e, a, treem_smem_bytes<S_>(e->K, R_, NW_))
     if (e->S == 20) {
-      if (e->K == 4) st = R == 4 ? TREEM(20, uint32_t, 4, 4) : (R == 2 ? TREEM(20, uint32_t, 2, 4) : TREEM(20, uint32_t, 1, 4));
-      else st = R == 4 ? TREEM(20, uint32_t, 4, 0) : (R == 2 ? TREEM(20, uint32_t, 2, 0) : TREEM(20, uint32_t, 1, 0));
+      if (e->K == 4) st = R == 2 ? TREEM(20, uint32_t, 2, 16, 4) : TREEM(20, uint32_t, 1, 16, 4);
+      else st = R == 2 ? TREEM(20, uint32_t, 2, 16, 0) : TREEM(20, uint32_t, 1, 16, 0);
     } else {
-      if (e->K == 1) st = R == 2 ? TREEM(61, uint64_t, 2, 1) : TREEM(61, uint64_t, 1, 1);
-      else st = R == 2 ? TREEM(61, uint64_t, 2, 0) : TREEM(61, uint64_t, 1, 0);
+      if (e->K == 1) st = R == 2 ? TREEM(61, uint64_t, 2, 8, 1) : TREEM(61, uint64_t, 1, 8, 1);
+      else st = R == 2 ? TREEM(61, uint64_t, 2, 8, 0) : TREEM(61, uint64_t, 1, 8, 0);
     }
 #undef TREEM
     if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "tree-fused (DMMA) launch: %s", cudaGetErrorString(st));
     ++e->launches;
+  }
+  if (dTiming) {
+    unsigned long long h[24];
+    CK(cudaMemcpy(h, dTiming, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(dTiming);
+    static const char *names[6] = {"tip+tip", "tip+cur", "tip+slot", "cur+slot", "slot+slot", "root"};
+    for (int v = 0; v < 6; ++v)
+      if (h[4 * v + 2])
+        fprintf(stderr, "[treem timing] %-9s steps/CTA-chunk %8llu  body %9.0f cyc (of which table wait %7.0f)  barrier %8.0f cyc\n",
+                names[v], h[4 * v + 2], (double)h[4 * v] / h[4 * v + 2], (double)h[4 * v + 3] / h[4 * v + 2],
+                (double)h[4 * v + 1] / h[4 * v + 2]);
   }
   for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = true;
   e->fused_result_ready = false;

@@ -67,6 +67,10 @@ struct TreeMArgs {
   double pinvar;
   double *site_lnl, *wsite;
   const char *tmaps;  // 20 states: CUtensorMap per node slot (128 bytes each), dims (S, N, K), box (S, 8, K)
+  // measurement only (PHYLO_TREEM_TIMING=1): [variant 0..5][0] cycles of warp 0 inside the step body, [1] cycles
+  // it then spent at the step's barrier, [2] steps, [3] cycles of the body spent waiting for the tables; variants: T+T, T+C, T+G, C+G, G+G, root. NULL = off
+  unsigned long long *timing;
+  int prog_in_smem;  // the launch reserved treem_prog_bytes(n_steps) of shared memory behind the buffers
 };
 
 constexpr int treem_pitch(int cols) {
@@ -83,12 +87,15 @@ __host__ __device__ inline size_t treem_smem_bytes(int K, int R, int NW) {
   using G = TreeMGeom<S>;
   return 128 + sizeof(double) * (4 * (size_t)K * G::FRAG + ((S + 15) & ~15) + (size_t)NW * R * K * 8 * G::PITCH);
 }
+// + the program itself when it fits behind the above (kernel argument prog_in_smem)
+__host__ __device__ inline size_t treem_prog_bytes(int n_steps) { return (size_t)(n_steps + 1) * sizeof(TreeMInstr); }
 
 // P ([branch * K + k][i][j], pt_build_kernel) -> the on-chip tables of the tree kernel, FRAG doubles each.
 // DMMA A fragments [mt][ks][lane]: lane (fr = lane / 4, fc = lane % 4) of row tile mt, k-step ks holds
 // P[i_of(mt, fr)][4 ks + fc]. For the TIP side of a median with 20 states the table is the transpose
-// instead, PT[j][24] = P[0..19][j] padded with zeros: an observed tip state j contributes column j of P,
-// which a lane then reads as one 128-bit + one 64-bit access (rows 2 fr, 2 fr + 1 and 16 + fr).
+// instead, PT[j][S] = P[0..S-1][j] for j < S, PT[S][.] = the row sums of P (a missing cell), zeros after:
+// an observed tip state j contributes column j of P, which a lane then reads as one 128-bit + one 64-bit
+// access (rows 2 fr, 2 fr + 1 and 16 + fr; lanes with fr >= 4 read finite values they never store).
 template <int S>
 __global__ void __launch_bounds__(256) pt_frag_kernel(const double *__restrict__ P, double *__restrict__ frags,
                                                       const TreeMInstr *__restrict__ prog, int n_steps, int K) {
@@ -99,8 +106,14 @@ __global__ void __launch_bounds__(256) pt_frag_kernel(const double *__restrict__
   const bool transposed = MmaMap<S>::kVec && step < n_steps && ((prog[step].kinds >> (2 * (branch & 1))) & 3) == TM_TIP;
   for (int idx = threadIdx.x; idx < G::FRAG; idx += blockDim.x) {
     if (transposed) {
-      const int j = idx / 24, i = idx % 24;
-      dst[idx] = i < S ? src[i * S + j] : 0.0;
+      // rows 0 .. S-1: columns of P; row S: the sum of all columns in ascending j (what a missing /
+      // fully ambiguous tip contributes -- same additions, same order as the oracle's loop over states)
+      const int j = idx / S, i = idx % S;
+      double v = 0.0;
+      if (j < S) v = src[i * S + j];
+      else if (j == S)
+        for (int q = 0; q < S; ++q) v += src[i * S + q];
+      dst[idx] = v;
     } else {
       const int l = idx & 31, ks = (idx >> 5) % G::KS, mt = (idx >> 5) / G::KS;
       const int i = MmaMap<S>::i_of(mt, l >> 2), j = ks * 4 + (l & 3);
@@ -137,12 +150,11 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
   using G = TreeMGeom<S>;
   using Map = MmaMap<S>;
   constexpr int MT = G::MT, KS = G::KS, FRAG = G::FRAG, PITCH = G::PITCH;
-  constexpr bool AREG = MT * KS <= 16;  // A fragments of one (side, rate class) fit in registers
-  constexpr bool PF = AREG;             // registers to spare: node-slot operands are fetched one group ahead
   constexpr bool PT = Map::kVec;        // tip sides read the transposed table (20 states)
   constexpr bool TMA = Map::kVec;       // results leave by TMA tensor stores from the running-value buffer (16-byte rows)
   constexpr int MTB = Map::kVec ? MT : (MT % 4 == 0 ? 4 : (MT % 2 == 0 ? 2 : 1));  // row tiles in flight together
   static_assert(!Map::kVec || MT == 3, "the 128-bit store path expects three row tiles");
+  static_assert(!Map::kVec || (S + 1) * S + 4 <= FRAG, "the transposed tip table (S columns + the row sums) must fit a table slot");
   constexpr unsigned FULL = 0xffffffffu;
   static_assert(R >= 1 && R <= 4, "a warp's tip masks travel in one register per side: R * 8 <= 32");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -172,6 +184,14 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
     fence_mbar_init();
+  }
+  // the program is read three times per step (operands, next step's masks, next step's pointers): a copy
+  // in shared memory takes two dependent global loads off the head of every step
+  const TreeMInstr *prog = a.prog;
+  if (a.prog_in_smem) {
+    TreeMInstr *sprog = (TreeMInstr *)(curbase + NW * R * gsz);
+    for (int i = tid; i <= a.n_steps; i += NW * 32) sprog[i] = a.prog[i];
+    prog = sprog;
   }
   if (warp == 0 && lane < 6) sptr[lane] = slot_ptr(a.prog[0]);
   __syncthreads();
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
       if ((in.kinds & 3) == TM_TIP && mok) ml = tips[(size_t)in.lidx * a.tip_stride + mp];
       if (((in.kinds >> 2) & 3) == TM_TIP && mok) mr = tips[(size_t)in.ridx * a.tip_stride + mp];
     };
-    TreeMInstr ins = a.prog[0];
+    TreeMInstr ins = prog[0];
     MaskT ml, mr;
     load_masks(ins, ml, mr);
     ml &= keep;
@@ -231,13 +251,18 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
       MaskT nml = 0, nmr = 0;
       unsigned long long next_ptr = 0;
       if (s + 1 < nst) {
-        nins = a.prog[s + 1];
+        nins = prog[s + 1];
         load_masks(nins, nml, nmr);
         if (warp == 0 && lane < 6) next_ptr = slot_ptr(nins);
       } else if (warp == 0 && lane < 6 && it + 1 < total_it) {
-        next_ptr = slot_ptr(a.prog[0]);
+        next_ptr = slot_ptr(prog[0]);
+      }
+      if constexpr (TMA) {  // this step's output descriptor: in the descriptor cache by the time the stores are issued
+        if (lane == 0 && ins.out_slot >= 0)
+          asm volatile("prefetch.tensormap [%0];" ::"l"(a.tmaps + (size_t)ins.out_slot * 128) : "memory");
       }
       const int lk = ins.kinds & 3, rk = (ins.kinds >> 2) & 3;
+      const long long t_begin = a.timing ? clock64() : 0;
       const unsigned long long *sp = sptr + (it & 1) * 6;
       const double *lg = (const double *)sp[0], *rg = (const double *)sp[1];
       double *og = (double *)sp[2];
@@ -247,7 +272,9 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
       const unsigned rhotbits = __ballot_sync(FULL, (mr & (mr - 1)) == 0);
       const int buf = (int)(it & 1);
       const double *fl = pbuf + buf * 2 * side, *frg = fl + side;
+      const long long t_w0 = a.timing ? clock64() : 0;
       mbar_wait(&bar[buf], (uint32_t)((it >> 1) & 1));
+      const long long t_w1 = a.timing ? clock64() : 0;
 
       // B fragment of an operand for rate class k of group r (lane = pattern fr, columns 4 ks + fc)
       auto fetch_cur = [&](double (&b)[KS], int r, int k) {
@@ -273,271 +300,231 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
         // ------------------------------------------------------------------ a median
         auto median = [&](auto LMc, auto RMc) {
           constexpr int LM = decltype(LMc)::value, RM = decltype(RMc)::value;
-          int h0[R], h1[R];
-          int colL0[R], colL1[R], colR0[R], colR1[R];
-          MaskT mlb[R], mrb[R];
-          int gs0[R], gs1[R];    // summed scale counters of the node-slot operands (loaded early, used late)
-          unsigned hotmask = 0;  // bit r: left tip all observed; bit 4 + r: right
+          if constexpr (TMA) {
+            // a node-slot operand was stored two or more steps ago: everything but the previous step's R bulk
+            // groups must have landed before it is read back
+            if (LM == TM_GLB || RM == TM_GLB) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group %0;" ::"n"(R) : "memory");
+              __syncwarp();
+            }
+          }
+          // group by group (r outer, rate classes inner): a group's CLV is complete after its K iterations and
+          // leaves at once (TMA), so the drain to HBM overlaps the next group's arithmetic
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            h0[r] = h1[r] = (int)0x80000000;
-            colL0[r] = colL1[r] = colR0[r] = colR1[r] = 0;
-            mlb[r] = mrb[r] = 0;
-            gs0[r] = gs1[r] = 0;
-            if (LM == TM_TIP) {
-              const bool hot = ((lhotbits >> (r * 8)) & 0xffu) == 0xffu;
-              if (hot) hotmask |= 1u << r;
-              if constexpr (PT) {  // colL* hold the MASKS of the lane's two result patterns
-                colL0[r] = (int)shfl_mask(ml, r * 8 + 2 * fc);
-                colL1[r] = (int)shfl_mask(ml, r * 8 + 2 * fc + 1);
-              } else if (hot) {
-                colL0[r] = hot_col(shfl_mask(ml, r * 8 + 2 * fc));
-                colL1[r] = hot_col(shfl_mask(ml, r * 8 + 2 * fc + 1));
-              } else {
-                mlb[r] = shfl_mask(ml, r * 8 + fr);
+            if (r < nact) {
+              const int64_t pbase = (cbase + (int64_t)r * NW + warp) * 8, pa0 = pbase + 2 * fc;
+              const bool pa0_ok = pa0 < a.N, pa1_ok = pa0 + 1 < a.N;
+              int h0 = (int)0x80000000, h1 = (int)0x80000000;
+              int colL0 = 0, colL1 = 0, colR0 = 0, colR1 = 0;  // PT: the MASKS of the lane's two result patterns
+              MaskT mlb = 0, mrb = 0;
+              bool lhot = false, rhot = false;
+              int gs0 = 0, gs1 = 0;  // summed scale counters of the node-slot operands (loaded early, used late)
+              if (LM == TM_TIP) {
+                lhot = ((lhotbits >> (r * 8)) & 0xffu) == 0xffu;
+                if constexpr (PT) {
+                  colL0 = (int)shfl_mask(ml, r * 8 + 2 * fc);
+                  colL1 = (int)shfl_mask(ml, r * 8 + 2 * fc + 1);
+                } else if (lhot) {
+                  colL0 = hot_col(shfl_mask(ml, r * 8 + 2 * fc));
+                  colL1 = hot_col(shfl_mask(ml, r * 8 + 2 * fc + 1));
+                } else {
+                  mlb = shfl_mask(ml, r * 8 + fr);
+                }
               }
-            }
-            if (RM == TM_TIP) {
-              const bool hot = ((rhotbits >> (r * 8)) & 0xffu) == 0xffu;
-              if (hot) hotmask |= 16u << r;
-              if constexpr (PT) {
-                colR0[r] = (int)shfl_mask(mr, r * 8 + 2 * fc);
-                colR1[r] = (int)shfl_mask(mr, r * 8 + 2 * fc + 1);
-              } else if (hot) {
-                colR0[r] = hot_col(shfl_mask(mr, r * 8 + 2 * fc));
-                colR1[r] = hot_col(shfl_mask(mr, r * 8 + 2 * fc + 1));
-              } else {
-                mrb[r] = shfl_mask(mr, r * 8 + fr);
+              if (RM == TM_TIP) {
+                rhot = ((rhotbits >> (r * 8)) & 0xffu) == 0xffu;
+                if constexpr (PT) {
+                  colR0 = (int)shfl_mask(mr, r * 8 + 2 * fc);
+                  colR1 = (int)shfl_mask(mr, r * 8 + 2 * fc + 1);
+                } else if (rhot) {
+                  colR0 = hot_col(shfl_mask(mr, r * 8 + 2 * fc));
+                  colR1 = hot_col(shfl_mask(mr, r * 8 + 2 * fc + 1));
+                } else {
+                  mrb = shfl_mask(mr, r * 8 + fr);
+                }
               }
-            }
-            if ((LM == TM_GLB || RM == TM_GLB) && r < nact) {
-              const int64_t pa0 = (cbase + (int64_t)r * NW + warp) * 8 + 2 * fc;
               if (RM == TM_GLB) {
-                if (pa0 < a.N) gs0[r] += rgs[pa0];
-                if (pa0 + 1 < a.N) gs1[r] += rgs[pa0 + 1];
+                if (pa0_ok) gs0 += rgs[pa0];
+                if (pa1_ok) gs1 += rgs[pa0 + 1];
               }
               if (LM == TM_GLB) {
-                if (pa0 < a.N) gs0[r] += lgs[pa0];
-                if (pa0 + 1 < a.N) gs1[r] += lgs[pa0 + 1];
+                if (pa0_ok) gs0 += lgs[pa0];
+                if (pa1_ok) gs1 += lgs[pa0 + 1];
               }
-            }
-          }
-          if constexpr (TMA) {
-            // the previous step's tensor stores still read the running-value buffers; a node-slot operand
-            // must also have LANDED (it may be the result of two steps ago)
-            if (lane == 0) {
-              if (LM == TM_GLB || RM == TM_GLB) bulk_wait0();
-              else bulk_wait_read0();
-            }
-            __syncwarp();
-          }
-          double pre[(PF && RM == TM_GLB) ? KS : 1];  // right operand's fragment for the NEXT (k, group)
-          if constexpr (PF && RM == TM_GLB) fetch_glb(pre, rg, 0, (cbase + warp) * 8);
-#pragma unroll 1
-          for (int k = 0; k < K; ++k) {
-            const double *tabL = fl + k * FRAG, *tabR = frg + k * FRAG;
-            double al[(AREG && LM != TM_TIP) ? MT * KS : 1], ar[(AREG && RM != TM_TIP) ? MT * KS : 1];
-            if constexpr (AREG && LM != TM_TIP) {
-#pragma unroll
-              for (int q = 0; q < MT * KS; ++q) al[q] = tabL[q * 32 + lane];
-            }
-            if constexpr (AREG && RM != TM_TIP) {
-#pragma unroll
-              for (int q = 0; q < MT * KS; ++q) ar[q] = tabR[q * 32 + lane];
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if (r >= nact) break;  // warp-uniform
-              const int64_t pbase = (cbase + (int64_t)r * NW + warp) * 8, pa0 = pbase + 2 * fc;
-              const bool lhot = LM == TM_TIP && ((hotmask >> r) & 1u), rhot = RM == TM_TIP && ((hotmask >> (4 + r)) & 1u);
-              double bl[LM != TM_TIP ? KS : 1], br[RM != TM_TIP ? KS : 1];
-              if constexpr (LM == TM_CUR) fetch_cur(bl, r, k);
-              if constexpr (LM == TM_GLB) fetch_glb(bl, lg, k, pbase);
-              if constexpr (RM == TM_CUR) fetch_cur(br, r, k);
-              if constexpr (RM == TM_GLB) {
-                if constexpr (PF) {
-#pragma unroll
-                  for (int ks = 0; ks < KS; ++ks) br[ks] = pre[ks];
-                  const bool wrap = r + 1 >= nact;
-                  const int nk = wrap ? k + 1 : k, nr = wrap ? 0 : r + 1;
-                  if (nk < K) fetch_glb(pre, rg, nk, (cbase + (int64_t)nr * NW + warp) * 8);
-                } else {
-                  fetch_glb(br, rg, k, pbase);
-                }
+              if constexpr (TMA) {
+                // the tensor store that last read this group's buffer (previous step, same r) is R - 1 groups back
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(R - 1) : "memory");
+                __syncwarp();
               }
-              if (LM == TM_CUR || RM == TM_CUR) __syncwarp();  // the result overwrites the running value just read
-              double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH, *c1 = c0 + PITCH;
-              double *o0 = og + ((size_t)pa0 * K + k) * S, *o1 = o0 + (size_t)K * S;
-              const bool pa0_ok = pa0 < a.N, pa1_ok = pa0 + 1 < a.N;
-              // MTB row tiles of both sides advance together: up to 2 MTB independent accumulator chains
-#pragma unroll
-              for (int m0 = 0; m0 < MT; m0 += MTB) {
-                double cx[MTB][2], cy[MTB][2];
-#pragma unroll
-                for (int m = 0; m < MTB; ++m) cx[m][0] = cx[m][1] = cy[m][0] = cy[m][1] = 0.0;
-                if constexpr (PT) {
-                  // tip side, 20 states: column j of P from the transposed table; a pattern with several
-                  // possible states (rare) adds its columns in ascending j -- the oracle's own order
-                  auto tip_side = [&](const double *pt, bool hot, unsigned mk0, unsigned mk1, double (&c)[MTB][2]) {
-                    if (hot) {
-                      const int j0 = mk0 ? __ffs((int)mk0) - 1 : 0, j1 = mk1 ? __ffs((int)mk1) - 1 : 0;
-                      lds128(pt + j0 * 24 + 2 * fr, c[0][0], c[1][0]);
-                      lds128(pt + j1 * 24 + 2 * fr, c[0][1], c[1][1]);
-                      c[2][0] = pt[j0 * 24 + 16 + fr];
-                      c[2][1] = pt[j1 * 24 + 16 + fr];
-                    } else {
-#pragma unroll 1
-                      for (int j = 0; j < S; ++j) {
-                        const double *col = pt + j * 24;
-                        if ((mk0 >> j) & 1) { c[0][0] += col[2 * fr]; c[1][0] += col[2 * fr + 1]; c[2][0] += col[16 + fr]; }
-                        if ((mk1 >> j) & 1) { c[0][1] += col[2 * fr]; c[1][1] += col[2 * fr + 1]; c[2][1] += col[16 + fr]; }
-                      }
-                    }
-                  };
-                  if constexpr (LM == TM_TIP) tip_side(tabL, lhot, (unsigned)colL0[r], (unsigned)colL1[r], cx);
-                  if constexpr (RM == TM_TIP) tip_side(tabR, rhot, (unsigned)colR0[r], (unsigned)colR1[r], cy);
-                } else {
-#pragma unroll
-                  for (int m = 0; m < MTB; ++m) {
-                    if (lhot) {
-                      cx[m][0] = tabL[(m0 + m) * KS * 32 + colL0[r]];
-                      cx[m][1] = tabL[(m0 + m) * KS * 32 + colL1[r]];
-                    }
-                    if (rhot) {
-                      cy[m][0] = tabR[(m0 + m) * KS * 32 + colR0[r]];
-                      cy[m][1] = tabR[(m0 + m) * KS * 32 + colR1[r]];
-                    }
-                  }
-                  // a tip with an ambiguous / missing pattern in this group (rare): fragments from the mask bits,
-                  // A from the table; a rolled loop, so that it stays a branch around and not predicated code
-                  if (LM == TM_TIP && !lhot) {
-#pragma unroll 1
-                    for (int ks = 0; ks < KS; ++ks) {
-                      const double b = ((mlb[r] >> (ks * 4 + fc)) & 1) ? 1.0 : 0.0;
-#pragma unroll
-                      for (int m = 0; m < MTB; ++m) dmma_acc(cx[m], tabL[((m0 + m) * KS + ks) * 32 + lane], b);
-                    }
-                  }
-                  if (RM == TM_TIP && !rhot) {
-#pragma unroll 1
-                    for (int ks = 0; ks < KS; ++ks) {
-                      const double b = ((mrb[r] >> (ks * 4 + fc)) & 1) ? 1.0 : 0.0;
-#pragma unroll
-                      for (int m = 0; m < MTB; ++m) dmma_acc(cy[m], tabR[((m0 + m) * KS + ks) * 32 + lane], b);
-                    }
-                  }
-                }
-                if constexpr (LM != TM_TIP || RM != TM_TIP) {
-#pragma unroll
-                  for (int ks = 0; ks < KS; ++ks) {
-                    if constexpr (LM != TM_TIP) {
-#pragma unroll
-                      for (int m = 0; m < MTB; ++m) {
-                        double av;
-                        if constexpr (AREG) av = al[(m0 + m) * KS + ks];
-                        else av = tabL[((m0 + m) * KS + ks) * 32 + lane];
-                        dmma_acc(cx[m], av, bl[ks]);
-                      }
-                    }
-                    if constexpr (RM != TM_TIP) {
-#pragma unroll
-                      for (int m = 0; m < MTB; ++m) {
-                        double av;
-                        if constexpr (AREG) av = ar[(m0 + m) * KS + ks];
-                        else av = tabR[((m0 + m) * KS + ks) * 32 + lane];
-                        dmma_acc(cy[m], av, br[ks]);
-                      }
-                    }
-                  }
-                }
-                if constexpr (Map::kVec) {
-                  const double a0 = cx[0][0] * cy[0][0], a1 = cx[0][1] * cy[0][1];
-                  const double b0 = cx[1][0] * cy[1][0], b1 = cx[1][1] * cy[1][1];
-                  const double d0 = cx[2][0] * cy[2][0], d1 = cx[2][1] * cy[2][1];
-                  sts128(c0 + 2 * fr, a0, b0);
-                  sts128(c1 + 2 * fr, a1, b1);
-                  h0[r] = max(h0[r], max(hi32(a0), hi32(b0)));
-                  h1[r] = max(h1[r], max(hi32(a1), hi32(b1)));
-                  if (fr < 4) {
-                    c0[16 + fr] = d0;
-                    c1[16 + fr] = d1;
-                    h0[r] = max(h0[r], hi32(d0));
-                    h1[r] = max(h1[r], hi32(d1));
-                  }
-                  if constexpr (!TMA) {
-                    if (pa0_ok) {
-                      st128(o0 + 2 * fr, a0, b0);
-                      if (fr < 4) o0[16 + fr] = d0;
-                    }
-                    if (pa1_ok) {
-                      st128(o1 + 2 * fr, a1, b1);
-                      if (fr < 4) o1[16 + fr] = d1;
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int m = 0; m < MTB; ++m) {
-                    const double v0 = cx[m][0] * cy[m][0], v1 = cx[m][1] * cy[m][1];
-                    const int i = Map::i_of(m0 + m, fr);
-                    if (i < S) {
-                      c0[i] = v0;
-                      c1[i] = v1;
-                      h0[r] = max(h0[r], hi32(v0));
-                      h1[r] = max(h1[r], hi32(v1));
-                      if (pa0_ok) o0[i] = v0;
-                      if (pa1_ok) o1[i] = v1;
-                    }
-                  }
-                }
-              }
-            }
-          }
-          // per-site rescaling and scale counters
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            if (r >= nact) break;
-            const int64_t pa0 = (cbase + (int64_t)r * NW + warp) * 8 + 2 * fc;
-            const bool pa0_ok = pa0 < a.N, pa1_ok = pa0 + 1 < a.N;
-            int m0 = h0[r], m1 = h1[r];
-#pragma unroll
-            for (int off = 4; off <= 16; off <<= 1) {
-              m0 = max(m0, __shfl_xor_sync(FULL, m0, off));
-              m1 = max(m1, __shfl_xor_sync(FULL, m1, off));
-            }
-            const bool r0 = pa0_ok && m0 < kScaleHiThresh, r1 = pa1_ok && m1 < kScaleHiThresh;
-            if (r0 || r1) {  // rare: every lane rescales what it stored (both copies); rolled loops
 #pragma unroll 1
               for (int k = 0; k < K; ++k) {
+                const double *tabL = fl + k * FRAG, *tabR = frg + k * FRAG;
+                double bl[LM != TM_TIP ? KS : 1], br[RM != TM_TIP ? KS : 1];
+                if constexpr (LM == TM_CUR) fetch_cur(bl, r, k);
+                if constexpr (LM == TM_GLB) fetch_glb(bl, lg, k, pbase);
+                if constexpr (RM == TM_CUR) fetch_cur(br, r, k);
+                if constexpr (RM == TM_GLB) fetch_glb(br, rg, k, pbase);
+                if (LM == TM_CUR || RM == TM_CUR) __syncwarp();  // the result overwrites the running value just read
                 double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH, *c1 = c0 + PITCH;
                 double *o0 = og + ((size_t)pa0 * K + k) * S, *o1 = o0 + (size_t)K * S;
+                // MTB row tiles of both sides advance together: up to 2 MTB independent accumulator chains
+#pragma unroll
+                for (int m0 = 0; m0 < MT; m0 += MTB) {
+                  double cx[MTB][2], cy[MTB][2];
+#pragma unroll
+                  for (int m = 0; m < MTB; ++m) cx[m][0] = cx[m][1] = cy[m][0] = cy[m][1] = 0.0;
+                  if constexpr (PT) {
+                    // tip side, 20 states: a row of the transposed table (an observed state's column of P, or the
+                    // row sums for a missing cell); a partial ambiguity code (rare, per lane) adds its columns in
+                    // ascending j -- the oracle's own order
+                    auto tip_row = [&](unsigned mk) {
+                      return mk == (unsigned)keep ? S : ((mk & (mk - 1)) == 0 ? (mk ? __ffs((int)mk) - 1 : 0) : -1);
+                    };
+                    auto tip_side = [&](const double *pt, unsigned mk0, unsigned mk1, double (&c)[MTB][2]) {
+                      const int j0 = tip_row(mk0), j1 = tip_row(mk1);
+                      if (j0 >= 0 && j1 >= 0) {
+                        lds128(pt + j0 * S + 2 * fr, c[0][0], c[1][0]);
+                        lds128(pt + j1 * S + 2 * fr, c[0][1], c[1][1]);
+                        c[2][0] = pt[j0 * S + 16 + fr];
+                        c[2][1] = pt[j1 * S + 16 + fr];
+                      } else {
 #pragma unroll 1
-                for (int mt = 0; mt < MT; ++mt) {
-                  const int i = Map::i_of(mt, fr);
-                  if (i < S) {
-                    if (r0) { c0[i] *= 0x1p+256; if (!TMA) o0[i] = c0[i]; }
-                    if (r1) { c1[i] *= 0x1p+256; if (!TMA) o1[i] = c1[i]; }
+                        for (int j = 0; j < S; ++j) {
+                          const double *col = pt + j * S;
+                          if ((mk0 >> j) & 1) { c[0][0] += col[2 * fr]; c[1][0] += col[2 * fr + 1]; c[2][0] += col[16 + fr]; }
+                          if ((mk1 >> j) & 1) { c[0][1] += col[2 * fr]; c[1][1] += col[2 * fr + 1]; c[2][1] += col[16 + fr]; }
+                        }
+                      }
+                    };
+                    if constexpr (LM == TM_TIP) tip_side(tabL, (unsigned)colL0, (unsigned)colL1, cx);
+                    if constexpr (RM == TM_TIP) tip_side(tabR, (unsigned)colR0, (unsigned)colR1, cy);
+                  } else {
+#pragma unroll
+                    for (int m = 0; m < MTB; ++m) {
+                      if (lhot) {
+                        cx[m][0] = tabL[(m0 + m) * KS * 32 + colL0];
+                        cx[m][1] = tabL[(m0 + m) * KS * 32 + colL1];
+                      }
+                      if (rhot) {
+                        cy[m][0] = tabR[(m0 + m) * KS * 32 + colR0];
+                        cy[m][1] = tabR[(m0 + m) * KS * 32 + colR1];
+                      }
+                    }
+                    // a tip with an ambiguous / missing pattern in this group (rare): fragments from the mask bits,
+                    // A from the table; a rolled loop, so that it stays a branch around and not predicated code
+                    if (LM == TM_TIP && !lhot) {
+#pragma unroll 1
+                      for (int ks = 0; ks < KS; ++ks) {
+                        const double b = ((mlb >> (ks * 4 + fc)) & 1) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int m = 0; m < MTB; ++m) dmma_acc(cx[m], tabL[((m0 + m) * KS + ks) * 32 + lane], b);
+                      }
+                    }
+                    if (RM == TM_TIP && !rhot) {
+#pragma unroll 1
+                      for (int ks = 0; ks < KS; ++ks) {
+                        const double b = ((mrb >> (ks * 4 + fc)) & 1) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int m = 0; m < MTB; ++m) dmma_acc(cy[m], tabR[((m0 + m) * KS + ks) * 32 + lane], b);
+                      }
+                    }
+                  }
+                  if constexpr (LM != TM_TIP || RM != TM_TIP) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                      if constexpr (LM != TM_TIP) {
+#pragma unroll
+                        for (int m = 0; m < MTB; ++m) dmma_acc(cx[m], tabL[((m0 + m) * KS + ks) * 32 + lane], bl[ks]);
+                      }
+                      if constexpr (RM != TM_TIP) {
+#pragma unroll
+                        for (int m = 0; m < MTB; ++m) dmma_acc(cy[m], tabR[((m0 + m) * KS + ks) * 32 + lane], br[ks]);
+                      }
+                    }
+                  }
+                  if constexpr (Map::kVec) {
+                    const double a0 = cx[0][0] * cy[0][0], a1 = cx[0][1] * cy[0][1];
+                    const double b0 = cx[1][0] * cy[1][0], b1 = cx[1][1] * cy[1][1];
+                    const double d0 = cx[2][0] * cy[2][0], d1 = cx[2][1] * cy[2][1];
+                    sts128(c0 + 2 * fr, a0, b0);
+                    sts128(c1 + 2 * fr, a1, b1);
+                    h0 = max(h0, max(hi32(a0), hi32(b0)));
+                    h1 = max(h1, max(hi32(a1), hi32(b1)));
+                    if (fr < 4) {
+                      c0[16 + fr] = d0;
+                      c1[16 + fr] = d1;
+                      h0 = max(h0, hi32(d0));
+                      h1 = max(h1, hi32(d1));
+                    }
+                    if constexpr (!TMA) {
+                      if (pa0_ok) {
+                        st128(o0 + 2 * fr, a0, b0);
+                        if (fr < 4) o0[16 + fr] = d0;
+                      }
+                      if (pa1_ok) {
+                        st128(o1 + 2 * fr, a1, b1);
+                        if (fr < 4) o1[16 + fr] = d1;
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int m = 0; m < MTB; ++m) {
+                      const double v0 = cx[m][0] * cy[m][0], v1 = cx[m][1] * cy[m][1];
+                      const int i = Map::i_of(m0 + m, fr);
+                      if (i < S) {
+                        c0[i] = v0;
+                        c1[i] = v1;
+                        h0 = max(h0, hi32(v0));
+                        h1 = max(h1, hi32(v1));
+                        if (pa0_ok) o0[i] = v0;
+                        if (pa1_ok) o1[i] = v1;
+                      }
+                    }
                   }
                 }
               }
-            }
-            int s0 = gs0[r], s1 = gs1[r];
-            if (LM == TM_CUR || RM == TM_CUR) { s0 += csc0[r]; s1 += csc1[r]; }
-            s0 += r0 ? 1 : 0;
-            s1 += r1 ? 1 : 0;
-            csc0[r] = s0;
-            csc1[r] = s1;
-            if (fr == 0) {
-              if (pa0_ok) ogs[pa0] = s0;
-              if (pa1_ok) ogs[pa0 + 1] = s1;
+              // per-site rescaling and scale counters
+#pragma unroll
+              for (int off = 4; off <= 16; off <<= 1) {
+                h0 = max(h0, __shfl_xor_sync(FULL, h0, off));
+                h1 = max(h1, __shfl_xor_sync(FULL, h1, off));
+              }
+              const bool r0 = pa0_ok && h0 < kScaleHiThresh, r1 = pa1_ok && h1 < kScaleHiThresh;
+              if (r0 || r1) {  // rare: every lane rescales what it stored (both copies); rolled loops
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) {
+                  double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH, *c1 = c0 + PITCH;
+                  double *o0 = og + ((size_t)pa0 * K + k) * S, *o1 = o0 + (size_t)K * S;
+#pragma unroll 1
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const int i = Map::i_of(mt, fr);
+                    if (i < S) {
+                      if (r0) { c0[i] *= 0x1p+256; if (!TMA) o0[i] = c0[i]; }
+                      if (r1) { c1[i] *= 0x1p+256; if (!TMA) o1[i] = c1[i]; }
+                    }
+                  }
+                }
+              }
+              int s0 = gs0, s1 = gs1;
+              if (LM == TM_CUR || RM == TM_CUR) { s0 += csc0[r]; s1 += csc1[r]; }
+              s0 += r0 ? 1 : 0;
+              s1 += r1 ? 1 : 0;
+              csc0[r] = s0;
+              csc1[r] = s1;
+              if (fr == 0) {
+                if (pa0_ok) ogs[pa0] = s0;
+                if (pa1_ok) ogs[pa0 + 1] = s1;
+              }
+              if constexpr (TMA) {
+                // the group's finished CLV [k][8][S] -> node slot [pattern][k][S]: one tensor store (rows >= N clipped)
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tma_store_3d(a.tmaps + (size_t)ins.out_slot * 128, cur + r * gsz, 0, (int)pbase, 0);
+              }
             }
             if constexpr (TMA) {
-              // the group's finished CLV [k][8][S] -> node slot [pattern][k][S]: one tensor store (rows >= N clipped)
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_3d(a.tmaps + (size_t)ins.out_slot * 128, cur + r * gsz, 0, (int)(pa0 - 2 * fc), 0);
-                bulk_commit();
-              }
+              if (lane == 0) bulk_commit();  // one bulk group per (step, r), empty for an idle r: the waits count groups
             }
           }
         };
@@ -663,7 +650,16 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
       ml = nml & keep;
       mr = nmr & keep;
       if (warp == 0 && lane < 6) sptr[((it + 1) & 1) * 6 + lane] = next_ptr;
+      const long long t_body = a.timing ? clock64() : 0;
       __syncthreads();  // every warp is done with this step's tables (and its global writes are visible CTA-wide)
+      if (a.timing && tid == 0) {
+        const int kk = lk | (rk << 2);
+        const int v = s == a.n_steps ? 5 : (kk == 0 ? 0 : kk == (TM_CUR << 2) ? 1 : kk == (TM_GLB << 2) ? 2 : kk == (TM_CUR | (TM_GLB << 2)) ? 3 : 4);
+        atomicAdd(a.timing + v * 4, (unsigned long long)(t_body - t_begin));
+        atomicAdd(a.timing + v * 4 + 1, (unsigned long long)(clock64() - t_body));
+        atomicAdd(a.timing + v * 4 + 2, 1ull);
+        atomicAdd(a.timing + v * 4 + 3, (unsigned long long)(t_w1 - t_w0));
+      }
     }
   }
   if constexpr (TMA) {
