@@ -584,6 +584,33 @@ def run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src):
     eng.close()
 
 
+def setup_exchange(ctx, args, eng):
+    """Peer-mapped mailboxes between the ranks' engines (cudaIpc handles travel over the process group).
+    Returns a note for the JSON line; ctx-independent state lives in the engine. Every rank must take the
+    same branch, so the outcome is agreed on with an all-reduce."""
+    if ctx.world == 1:
+        return None
+    if args.exchange != "p2p":
+        return "nccl all-reduce of one scalar (host -> device -> NCCL -> host)"
+    torch, dist = ctx.torch, ctx.dist
+    ok, why = 1, ""
+    try:
+        box, handle = eng.exchange_alloc()
+        handles = [None] * ctx.world
+        dist.all_gather_object(handles, handle)
+        boxes = [box if r == ctx.rank else eng.exchange_open(handles[r]) for r in range(ctx.world)]
+        eng.exchange_set(ctx.rank, boxes)
+    except Exception as ex:  # noqa: BLE001 -- fall back, but say so
+        ok, why = 0, str(ex)
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return "nccl all-reduce (peer-mapped exchange unavailable on some rank: %s)" % (why or "see other ranks")
+    eng.set_option(eng.OPT_DEFER_SCALAR, 1)
+    return ("device-side: block partials into peer-mapped mailboxes (cudaIpc over NVLink), canonical fold in rank "
+            "order by one CTA per rank, no NCCL call and no host round trip before the final scalar")
+
+
 def run_workload(ctx, args, key, wl, primary):
     """One workload on this process's GPU (all ranks call it together). Returns the JSON record on
     rank 0 (None elsewhere). `primary`: the headline -- full step counts, the other likelihood modes,
@@ -608,6 +635,8 @@ def run_workload(ctx, args, key, wl, primary):
     ops, ra, rb, rt, n_nodes = tree_mod.schedule(tr)
     eng = engine.Engine(local)
     launches0 = eng.launch_count
+    xnote = setup_exchange(ctx, args, eng)
+    p2p = xnote is not None and xnote.startswith("device-side")
 
     def needs_flush(m):
         return device_footprint("fitch" if kind == "fitch" else key, T, S, K, mask_dtype(S)().itemsize, m, n_local) < 4 * L2_BYTES
@@ -638,9 +667,11 @@ def run_workload(ctx, args, key, wl, primary):
 
         def step():
             v = eng.fitch_score_tree(ops, ra, rb)
+            if p2p:
+                return eng.exchange_sum_u64(v)  # the path's only exchange: one exact integer
             if world > 1:
                 acc[0] = v
-                dist.all_reduce(acc)  # the path's only exchange: one exact integer
+                dist.all_reduce(acc)
                 return int(acc.item())
             return v
 
@@ -678,9 +709,11 @@ def run_workload(ctx, args, key, wl, primary):
 
         def step():
             v = eng.lk_score_tree(ops, ra, rb, rt)
+            if p2p:
+                return eng.lk_exchange_reduce()  # the path's only exchange; bit-identical for any N
             if world > 1:
                 acc[0] = v
-                dist.all_reduce(acc)  # the path's only exchange: one fp64 scalar
+                dist.all_reduce(acc)  # one fp64 scalar
                 return float(acc.item())
             return v
 
@@ -688,6 +721,8 @@ def run_workload(ctx, args, key, wl, primary):
             # host buffers in, scalar out: upload (pinned -> HBM, overlapped slab by slab with
             # the scoring) + full evaluation + lnL read-back, through one C-ABI call
             v = eng.lk_score_alignment(tips, ops, ra, rb, rt, capacity=n_nodes, packed_n=packed_n)
+            if p2p:
+                return eng.lk_exchange_reduce()
             if world > 1:
                 acc[0] = v
                 dist.all_reduce(acc)
@@ -770,6 +805,25 @@ def run_workload(ctx, args, key, wl, primary):
                                       "note": "SURVEY's dense count for every update; tip sides are table "
                                               "lookups in the engine, so this exceeds the executed flops"}}
         roof_tensor["step_level"]["frac"] = roof_tensor["step_level"]["achieved_tflops"] / FP64_DMMA_TFLOPS
+    if kind == "lk" and S >= 20 and roof_tensor is None and "tree_fused" in kernels:
+        # tree-fused DMMA kernel (lk_treem_kernel): only CLV operands go through the tensor cores (an observed
+        # tip contributes a column of P by table lookup), root edge: one side. Counted twice: the useful
+        # contraction flops (2 S^2 per side, class and pattern) and the DMMA work issued (row tiles padded to 8)
+        sides = int(np.sum(ops["left"] >= T) + np.sum(ops["right"] >= T)) + (1 if rb >= T else 0)
+        mt, ks = (S + 7) // 8, (S + 3) // 4
+        useful = 2.0 * S * S * K * sides * n_local
+        issued = 512.0 * mt * ks * K * sides * ((n_local + 7) // 8)
+        ent = kernels["tree_fused"]
+        t_s = ent["avg_us"] * 1e-6
+        ent["algorithmic_flops_per_launch"] = useful
+        ent["issued_dmma_flops_per_launch"] = issued
+        roof_tensor = {"bound": "tensor", "kernel": "tree_fused", "achieved": useful / t_s / 1e12, "peak": FP64_DMMA_TFLOPS,
+                       "unit": "TFLOP/s", "frac": useful / t_s / 1e12 / FP64_DMMA_TFLOPS, "traffic": None,
+                       "issued_tflops": issued / t_s / 1e12, "issued_frac": issued / t_s / 1e12 / FP64_DMMA_TFLOPS,
+                       "clv_operand_sides": sides,
+                       "peak_source": "fp64 DMMA (mma.sync.m8n8k4.f64) measured by tools/peaks.cu on this pool",
+                       "note": "tip operands are table lookups (no flops counted); the same launch is also held against "
+                               "the HBM roofline (compulsory bytes: every interior CLV written once)"}
     if kind == "lk":
         step_bytes = kbytes["tree"] * n_local
         roof_step = {"bytes_model": "SURVEY 8(d) per-node streaming (what a kernel-per-node engine must move)",
@@ -808,6 +862,8 @@ def run_workload(ctx, args, key, wl, primary):
         set_mode(mode)
         step()  # leave the engine's site lnL / CLVs in the primary mode's state
 
+    if p2p:
+        eng.set_option(eng.OPT_DEFER_SCALAR, 0)  # what follows is per-rank work that reads local values
     # ---- branch-length re-evaluation loop (BASELINE config 5's second half):
     # 50 evaluations of lnL(t) on the root edge as a Brent/Newton driver would issue them (one
     # length per call: each depends on the previous result), then 10 re-prunes of the path to
@@ -895,7 +951,8 @@ def run_workload(ctx, args, key, wl, primary):
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": dict(workload_config(key, wl, n_total, n_local, world, l2_note, ctx.numa_note), upload_format=upload_note),
+            "config": dict(workload_config(key, wl, n_total, n_local, world, l2_note, ctx.numa_note), upload_format=upload_note,
+                           **({"collective": xnote} if xnote else {})),
             "mode": mode, "modes": modes,
             "roofline": (roof_tensor if roof_tensor and S > 32 else roof),
             "roofline_hbm": roof if roof_tensor and S > 32 else None,
@@ -931,6 +988,10 @@ def main():
                     help="likelihood path: tree-fused kernel keeping every CLV (default), tree-fused "
                          "lnL-only (no CLV written), or one streaming kernel per node")
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other modes")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="how the ranks' scalars meet (N > 1): on the device through peer-mapped mailboxes "
+                         "(phylo_lk_exchange_reduce; default) or host -> NCCL all-reduce -> host")
+    ap.add_argument("--no-group", action="store_true", help="skip the single-process phylo_group record (N > 1)")
     ap.add_argument("--fitch-kernel", default="auto", choices=["auto", "tile", "regwalk", "l2"],
                     help="whole-tree Fitch kernel (PHYLO_OPT_FITCH_WALK)")
     args = ap.parse_args()

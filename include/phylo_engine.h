@@ -90,6 +90,10 @@ int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256);
  * 2 = register walk (compiled depth-first plan, tips prefetched several medians ahead, up to
  * 8 planes); 0 = L2 walk (re-reads its own earlier writes through L2, any plane count). */
 #define PHYLO_OPT_FITCH_WALK 3
+/* PHYLO_OPT_DEFER_SCALAR (default 0): 1 = phylo_lk_score_tree leaves the evaluation's level-1 block partials
+ * on the device and returns without waiting for (or computing) the local lnL (*lnl_out = NaN); the caller
+ * combines them across ranks with phylo_lk_exchange_reduce. No host round trip between the two. */
+#define PHYLO_OPT_DEFER_SCALAR 4
 /* Two environment variables exist for measurements only (tools/tune_treew.sh, tools/mma_ab.sh):
  * PHYLO_TREEW_TUNE="slev,R,il" overrides the geometry the warp-autonomous tree kernel picks, and
  * PHYLO_TT_TABLE=0 sends 20-state tip+tip updates through the DMMA kernel instead of the table
@@ -241,6 +245,26 @@ int phylo_lk_get_site_lnl(phylo_engine *e, double *out);
  * reduction of such partials -- what ranks all-gather for a bit-reproducible multi-GPU sum */
 int phylo_lk_get_block_partials(phylo_engine *e, double *out, int64_t *n_out);
 double phylo_reduce_partials(const double *partials, int64_t n);
+
+/* --------------------------- the scalar exchange, on the device over peer-mapped memory ---- */
+/* patterns are sharded over ranks (one engine per GPU) and the ONLY exchange is the final scalar.
+ * Instead of host -> NCCL all-reduce -> host, every engine owns a small mailbox in its HBM that all other
+ * engines map (NVLink / NVSwitch peer access): phylo_exchange_alloc creates it and exports a 64-byte
+ * cudaIpcMemHandle for other PROCESSES (one process per GPU: ship the handles with any host-side
+ * all-gather, open each with phylo_exchange_open); engines of one process pass the raw pointers.
+ * phylo_exchange_set(world, rank, mailboxes[world]) installs the table (mailboxes[rank] = the own one).
+ * phylo_lk_exchange_reduce: call on EVERY rank after phylo_lk_score_tree (best with PHYLO_OPT_DEFER_SCALAR):
+ * one CTA writes the rank's level-1 block partials into every peer's mailbox, waits for all ranks' partials in
+ * its own, and folds their concatenation in rank order with the canonical 1024-fold -- *lnl_out is the
+ * whole alignment's lnL, bit-identical to a single-engine evaluation for any rank count (shards must start
+ * at multiples of PHYLO_LNL_BLOCK patterns; at most 8190 blocks per rank). phylo_exchange_sum_u64: the exact
+ * integer sum of one value per rank (Fitch / TCM lengths). A rank that does not arrive within ~2 s makes the
+ * call fail with PHYLO_ERR_CUDA instead of hanging. bench.py uses these (NCCL all-reduce = --exchange nccl). */
+int phylo_exchange_alloc(phylo_engine *e, void **mailbox_out, unsigned char *ipc_handle64);
+int phylo_exchange_open(phylo_engine *e, const unsigned char *ipc_handle64, void **mailbox_out);
+int phylo_exchange_set(phylo_engine *e, int world, int rank, void *const *mailboxes);
+int phylo_lk_exchange_reduce(phylo_engine *e, double *lnl_out);
+int phylo_exchange_sum_u64(phylo_engine *e, uint64_t value, uint64_t *sum_out);
 
 /* ------------------------------------------------ site-pattern compression (next to the path) ---- */
 /* The step before scoring: identical alignment columns are merged into one site pattern whose

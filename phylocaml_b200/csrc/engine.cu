@@ -26,6 +26,7 @@
 #include "lk_treem_kernel.cuh"
 #include "lk_edge_kernels.cuh"
 #include "compress_kernels.cuh"
+#include "exchange_kernels.cuh"
 #include "phylo_engine.h"
 
 using namespace phylo;
@@ -38,6 +39,8 @@ enum : int {
   HS_BAD = 1,        // invalid-mask counter read-back
   HS_TREE_OUT = 16,  // [0] lnL, [1] sequence number written by the tree kernel's last CTA (mapped)
   HS_EDGE_OUT = 24,  // 3 x kEdgeMaxT folded sums of phylo_lk_edge_eval (mapped)
+  HS_XCHG_OUT = 80,  // [0] result, [1] sequence number of the device-side scalar exchange (mapped)
+  HS_XCHG_IN = 84,   // the uint64 a rank contributes to an integer exchange (mapped, read by the kernel)
   HS_DOUBLES = 128
 };
 
@@ -135,6 +138,13 @@ struct phylo_engine {
   uint64_t lkGen = 0;              // bumped whenever every slot is dropped (new alignment shape / model alphabet)
   double *dP = nullptr;  // transition matrices [branch][K][S][S]
   size_t capP = 0;       // branches
+  // device-side scalar exchange (exchange_kernels.cuh)
+  double *xMailbox = nullptr;   // this engine's mailbox (kXMailboxBytes)
+  XchgPeers xPeers{};           // every rank's mailbox as mapped here
+  std::vector<void *> xOpened;  // mappings opened from IPC handles (closed on destroy)
+  int xWorld = 0, xRank = -1;
+  unsigned long long xSeq = 0;
+  bool defer_scalar = false;    // PHYLO_OPT_DEFER_SCALAR
   double *dFrag = nullptr;  // the same matrices as DMMA A-fragment tables (tree-fused 20/61-state kernel)
   size_t capFrag = 0;       // doubles
   double *dT = nullptr, *hT = nullptr;  // branch lengths (device / pinned)
@@ -346,6 +356,8 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   fitch_free_data(e);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dFrag); dfree(e->dT);
+  for (void *p : e->xOpened) cudaIpcCloseMemHandle(p);
+  dfree(e->xMailbox);
   dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
@@ -1108,6 +1120,7 @@ extern "C" int phylo_engine_set_option(phylo_engine *e, int option, int64_t valu
     case PHYLO_OPT_FUSED_TREE: e->opt_fused = (value == 2) ? 2 : (value != 0); return PHYLO_OK;
     case PHYLO_OPT_RETAIN_CLV: e->opt_retain = value != 0; return PHYLO_OK;
     case PHYLO_OPT_FITCH_WALK: e->opt_fitch_walk = (value < 0 || value > 3) ? 1 : (int)value; return PHYLO_OK;
+    case PHYLO_OPT_DEFER_SCALAR: e->defer_scalar = value != 0; return PHYLO_OK;
     default: return fail(e, PHYLO_ERR_ARG, "set_option: unknown option %d", option);
   }
 }
@@ -1117,6 +1130,7 @@ extern "C" int phylo_engine_get_option(phylo_engine *e, int option, int64_t *val
     case PHYLO_OPT_FUSED_TREE: *value = e->opt_fused; return PHYLO_OK;
     case PHYLO_OPT_RETAIN_CLV: *value = e->opt_retain; return PHYLO_OK;
     case PHYLO_OPT_FITCH_WALK: *value = e->opt_fitch_walk; return PHYLO_OK;
+    case PHYLO_OPT_DEFER_SCALAR: *value = e->defer_scalar; return PHYLO_OK;
     default: return fail(e, PHYLO_ERR_ARG, "get_option: unknown option %d", option);
   }
 }
@@ -1579,6 +1593,10 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   else
     for (int o = 0; o < n_ops; ++o) e->nodes[ops[o].parent].valid = false;
   e->fused_result_ready = false;
+  if (fuse && e->defer_scalar) {  // the caller will combine the block partials on the device (phylo_lk_exchange_reduce)
+    *done = true;
+    return PHYLO_OK;
+  }
   if (fuse) {
     // spin on the sequence number the last CTA writes after lnL (mapped host memory); a
     // blocking stream sync would cost more than these kernels. Fallback after 2 ms.
@@ -1857,6 +1875,11 @@ extern "C" int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_o
     bool done = false;
     if ((rc = lk_score_tree_fused(e, ops, n_ops, root_a, root_b, root_t, &done)) != PHYLO_OK) return rc;
     if (!done && (rc = lk_score_tree_fusedm(e, ops, n_ops, root_a, root_b, root_t, &done)) != PHYLO_OK) return rc;
+    if (done && e->defer_scalar) {
+      *lnl_out = std::nan("");
+      e->lk_evaluated = true;
+      return PHYLO_OK;
+    }
     if (done) {
       if (!e->fused_result_ready) CK(cudaStreamSynchronize(e->stream));
       *lnl_out = e->hScalar[0];
@@ -1973,6 +1996,104 @@ extern "C" int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, 
   }
   e->edge_ready = false;
   if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
+}
+
+// ---- device-side scalar exchange (exchange_kernels.cuh)
+extern "C" int phylo_exchange_alloc(phylo_engine *e, void **mailbox_out, unsigned char *ipc_handle64) {
+  if (!e || !mailbox_out) return PHYLO_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  if (!e->xMailbox) {
+    CK(cudaMalloc(&e->xMailbox, kXMailboxBytes));
+    CK(cudaMemsetAsync(e->xMailbox, 0, kXMailboxBytes, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  *mailbox_out = e->xMailbox;
+  if (ipc_handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries IPC handles as 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->xMailbox));
+    std::memcpy(ipc_handle64, &h, 64);
+  }
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_exchange_open(phylo_engine *e, const unsigned char *ipc_handle64, void **mailbox_out) {
+  if (!e || !ipc_handle64 || !mailbox_out) return PHYLO_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, ipc_handle64, 64);
+  void *p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  e->xOpened.push_back(p);
+  *mailbox_out = p;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_exchange_set(phylo_engine *e, int world, int rank, void *const *mailboxes) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (world < 1 || world > kXMaxWorld || rank < 0 || rank >= world || !mailboxes)
+    return fail(e, PHYLO_ERR_ARG, "exchange_set: need 1 <= world <= %d, 0 <= rank < world", kXMaxWorld);
+  if (!e->xMailbox || mailboxes[rank] != e->xMailbox)
+    return fail(e, PHYLO_ERR_ARG, "exchange_set: mailboxes[rank] must be this engine's own mailbox (phylo_exchange_alloc)");
+  for (int q = 0; q < world; ++q) {
+    if (!mailboxes[q]) return fail(e, PHYLO_ERR_ARG, "exchange_set: mailbox %d is NULL", q);
+    e->xPeers.box[q] = (double *)mailboxes[q];
+  }
+  e->xWorld = world;
+  e->xRank = rank;
+  return PHYLO_OK;
+}
+
+// launches the exchange kernel for `n` doubles at `src` (device) and waits for its result in mapped host memory
+static int exchange_run(phylo_engine *e, const double *src, int n, int mode, double *out_bits, const char *who) {
+  if (e->xWorld < 1) return fail(e, PHYLO_ERR_STATE, "%s: phylo_exchange_set has not been called", who);
+  if (n > kXMaxPartials) return fail(e, PHYLO_ERR_UNSUPPORTED, "%s: %d block partials per rank exceed the mailbox slot (%d)", who, n, kXMaxPartials);
+  double *dev_out = nullptr;
+  CK(cudaHostGetDevicePointer((void **)&dev_out, e->hScalar + HS_XCHG_OUT, 0));
+  const unsigned long long seq = ++e->xSeq;
+  volatile double *out = e->hScalar + HS_XCHG_OUT;
+  out[1] = 0.0;
+  {
+    ProfScope prof(e, KC_REDUCE);
+    exchange_kernel<<<1, 1024, 0, e->stream>>>(src, n, e->xRank, e->xWorld, e->xPeers, seq, mode, dev_out);
+    LAUNCH_CHECK();
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int spin = 0;; ++spin) {
+    double f = out[1];
+    unsigned long long bits;
+    std::memcpy(&bits, &f, 8);
+    if (bits == seq) break;
+    if (bits == ~0ull) return fail(e, PHYLO_ERR_CUDA, "%s: a peer did not arrive within the exchange time-out", who);
+    if ((spin & 4095) == 4095 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) {
+      CK(cudaStreamSynchronize(e->stream));
+      return fail(e, PHYLO_ERR_CUDA, "%s: the exchange kernel did not publish a result", who);
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  *out_bits = out[0];
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_lk_exchange_reduce(phylo_engine *e, double *lnl_out) {
+  if (!e || !lnl_out) return PHYLO_ERR_ARG;
+  if (!e->lk_evaluated) return fail(e, PHYLO_ERR_STATE, "lk_exchange_reduce: no likelihood evaluation to combine");
+  CK(cudaSetDevice(e->device));
+  return exchange_run(e, e->dPart, (int)e->nPart, 0, lnl_out, "lk_exchange_reduce");
+}
+
+extern "C" int phylo_exchange_sum_u64(phylo_engine *e, uint64_t value, uint64_t *sum_out) {
+  if (!e || !sum_out) return PHYLO_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));  // the mapped input word is about to be rewritten
+  std::memcpy(e->hScalar + HS_XCHG_IN, &value, 8);
+  double *dev_in = nullptr;
+  CK(cudaHostGetDevicePointer((void **)&dev_in, e->hScalar + HS_XCHG_IN, 0));
+  double bits = 0.0;
+  const int rc = exchange_run(e, dev_in, 1, 1, &bits, "exchange_sum_u64");
+  if (rc != PHYLO_OK) return rc;
+  std::memcpy(sum_out, &bits, 8);
   return PHYLO_OK;
 }
 

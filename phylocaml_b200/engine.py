@@ -68,6 +68,11 @@ SIGNATURES = {
     "phylo_bv_eltcount": (C.c_int, [_vp, C.c_int, _i64, C.POINTER(C.c_int)]),
     "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_uppass": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
+    "phylo_exchange_alloc": (C.c_int, [_vp, C.POINTER(_vp), _vp]),
+    "phylo_exchange_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "phylo_exchange_set": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "phylo_lk_exchange_reduce": (C.c_int, [_vp, _dp]),
+    "phylo_exchange_sum_u64": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "phylo_plan_compile": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
                                            C.c_int, C.c_int, C.c_double, _dp]),
@@ -312,7 +317,35 @@ class Engine:
     def launch_count(self):
         return int(self.lib.phylo_engine_launch_count(self.h))
 
-    OPT_FUSED_TREE, OPT_RETAIN_CLV, OPT_FITCH_WALK = 1, 2, 3
+    OPT_FUSED_TREE, OPT_RETAIN_CLV, OPT_FITCH_WALK, OPT_DEFER_SCALAR = 1, 2, 3, 4
+
+    # ---- device-side scalar exchange (include/phylo_engine.h)
+    def exchange_alloc(self):
+        """-> (mailbox device pointer, 64-byte cudaIpcMemHandle for other processes)"""
+        ptr = _vp()
+        handle = (C.c_ubyte * 64)()
+        self._ck(self.lib.phylo_exchange_alloc(self.h, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def exchange_open(self, handle):
+        ptr = _vp()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._ck(self.lib.phylo_exchange_open(self.h, buf, C.byref(ptr)))
+        return ptr.value
+
+    def exchange_set(self, rank, mailboxes):
+        arr = (_vp * len(mailboxes))(*mailboxes)
+        self._ck(self.lib.phylo_exchange_set(self.h, len(mailboxes), rank, arr))
+
+    def lk_exchange_reduce(self):
+        out = C.c_double()
+        self._ck(self.lib.phylo_lk_exchange_reduce(self.h, C.byref(out)))
+        return out.value
+
+    def exchange_sum_u64(self, value):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_exchange_sum_u64(self.h, C.c_uint64(int(value)), C.byref(out)))
+        return int(out.value)
 
     def set_symbol_table(self, table):
         """256 state masks by symbol byte (phylocaml_b200.alphabet), or None for plain masks."""
