@@ -584,6 +584,55 @@ def run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src):
     eng.close()
 
 
+def run_group(ctx, args, headline):
+    """N > 1 only, after every rank has released its engine: rank 0 drives ALL N GPUs through one
+    phylo_group handle (the path a single OCaml process would use, include/phylo_engine.h last section) on the
+    headline workload -- host wall clock around the synchronous group call (there is no single stream to put
+    events on) -- while the other ranks wait at a barrier. lnL must equal the per-rank run's to the last bit."""
+    from phylocaml_b200 import engine, tree as tree_mod
+
+    wl = WORKLOADS["dna"]
+    T, S, K = wl["T"], wl["S"], wl["K"]
+    n_total = args.patterns or wl["N"]
+    rec = None
+    ctx.barrier()
+    if ctx.rank == 0:
+        try:
+            tr = tree_mod.random_tree(T, seed=1)
+            ops, ra, rb, rt, n_nodes = tree_mod.schedule(tr)
+            model = make_model(wl)
+            base = tree_mod.evolve_tips(tr, model, BASE_PATTERNS, seed=3, dtype=mask_dtype(S))
+            tips = engine.pinned_empty((T, n_total), mask_dtype(S))
+            tile_cols(base, 0, n_total, out=tips)
+            g = engine.Group(list(range(ctx.world)))
+            g.lk_set_model(model)
+            t0 = time.perf_counter()
+            g.lk_set_tips(tips, capacity=n_nodes)
+            t_up = time.perf_counter() - t0
+            for _ in range(3):
+                lnl = g.lk_score_tree(ops, ra, rb, rt)
+            reps = max(5, min(args.steps, 20))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                lnl = g.lk_score_tree(ops, ra, rb, rt)
+            dt = (time.perf_counter() - t0) / reps
+            rec = {"what": "one process, one phylo_group handle over all %d GPUs (one engine + host worker thread per GPU)" % ctx.world,
+                   "devices": ctx.world, "workload": wl["name"], "patterns_total": n_total,
+                   "ms_per_step": 1e3 * dt, "value": (T - 1) * n_total / dt, "unit": "site-updates/s",
+                   "set_tips_ms": 1e3 * t_up, "upload_format": "%d-byte state masks, column slabs straight out of the caller's matrix" % tips.dtype.itemsize,
+                   "lnl": lnl, "lnl_equals_per_rank_run": bool(headline is not None and lnl == headline.get("check", {}).get("result")),
+                   "timing": "host perf_counter around synchronous group calls (max over devices by construction)",
+                   "kernel_launches": int(g.launch_count)}
+            g.close()
+            engine.pinned_free(tips)
+        except Exception as ex:  # noqa: BLE001 -- a missing record must not cost the headline line
+            rec = {"error": str(ex)[:300]}
+    # the other ranks wait on the HOST (gloo): an NCCL barrier would park a spinning kernel on their GPUs and
+    # time-slice them against the group's engines
+    ctx.dist.barrier(group=ctx.cpu_group)
+    return rec
+
+
 def setup_exchange(ctx, args, eng):
     """Peer-mapped mailboxes between the ranks' engines (cudaIpc handles travel over the process group).
     Returns a note for the JSON line; ctx-independent state lives in the engine. Every rank must take the
@@ -1023,6 +1072,7 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Ctx(torch, dist, world, rank, local, numa_note)
+    ctx.cpu_group = dist.new_group(backend="gloo") if world > 1 else None
 
     if args.workload == "compress":
         run_compress(args, wl, torch, engine, tree_mod, local, ctx.hbm_peak, ctx.peak_src)
@@ -1041,6 +1091,10 @@ def main():
                 recs[key] = rec
         if line is not None:
             line["workloads"] = recs
+    if world > 1 and not args.no_group and args.workload == "dna":
+        grp = run_group(ctx, args, line)
+        if line is not None:
+            line["group"] = grp
     if line is not None:
         line["bench_wall_s"] = time.perf_counter() - t_all
         print(json.dumps(line))

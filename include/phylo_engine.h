@@ -203,6 +203,23 @@ int phylo_lk_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int roo
  * edge join instead of a re-prune (lib/tree.ml:299-494). */
 int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, double root_t,
                     const int32_t *up_slot);
+/* Model-parameter derivatives -- what gen_subst_opt_func / gen_rates_opt_func / gen_prior_opt_func
+ * (lib/mlModel.ml:822-829, all `failwith "todo"`) need from the native side. After phylo_lk_score_tree and
+ * phylo_lk_uppass with EVERY up slot set (so that each branch has its directional pair), returns
+ * grad_out[p] = d lnL / d theta_p for n_params (<= 64) parameters at once. The caller describes a parameter
+ * by its effect on the model record (any pointer may be NULL = no effect):
+ *   dQ     [n_params][S][S]  d Q / d theta_p of the rate matrix the eigensystem was taken from
+ *                            (normalisation included: MlModel.m_meanrate, lib/mlModel.ml:204-213),
+ *   drates [n_params][K]     d rates[k] / d theta_p (the Gamma shape alpha moves only these),
+ *   dpi    [n_params][S]     d priors / d theta_p at the root (not together with an invariant-sites class).
+ * lnL is multilinear in the branches' P(t): d P = dexp_{Q t r}[t (r dQ + dr Q)] is formed per branch on the
+ * host from the eigensystem and applied across the branch's directional pair by one kernel pass per branch
+ * (all parameters together; 2 T - 3 passes of 2 C bytes per pattern -- against 2 n_params full evaluations
+ * for central differences). Reversible models (the pulley principle behind phylo_lk_uppass). *lnl_out (may be
+ * NULL) = the lnL of the preceding phylo_lk_score_tree. */
+int phylo_lk_param_gradient(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, double root_t,
+                            const int32_t *up_slot, int n_params, const double *dQ, const double *drates,
+                            const double *dpi, double *lnl_out, double *grad_out);
 /* Host-only (no GPU needed), for tests and tooling: the compiled form of a schedule as the
  * tree-fused likelihood kernels and the Fitch register walk execute it. One row of 6 int32 per
  * step (n_ops medians in depth-first order + the root-edge join, whose out_slot is -1):

@@ -27,6 +27,7 @@
 #include "lk_edge_kernels.cuh"
 #include "compress_kernels.cuh"
 #include "exchange_kernels.cuh"
+#include "lk_grad_kernels.cuh"
 #include "phylo_engine.h"
 
 using namespace phylo;
@@ -138,6 +139,8 @@ struct phylo_engine {
   uint64_t lkGen = 0;              // bumped whenever every slot is dropped (new alignment shape / model alphabet)
   double *dP = nullptr;  // transition matrices [branch][K][S][S]
   size_t capP = 0;       // branches
+  // host copy of the eigensystem (Q = V diag(lam) Vinv) for the model-parameter derivatives
+  std::vector<double> hV, hVinv, hLam, hPi, hRates, hProbs;
   // device-side scalar exchange (exchange_kernels.cuh)
   double *xMailbox = nullptr;   // this engine's mailbox (kXMailboxBytes)
   XchgPeers xPeers{};           // every rank's mailbox as mapped here
@@ -572,6 +575,16 @@ extern "C" int phylo_lk_set_model(phylo_engine *e, int S, int K, const double *U
     CK(cudaMemcpy(e->dUL, m1.data(), sizeof(double) * K * ss, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->dUR, m2.data(), sizeof(double) * K * ss, cudaMemcpyHostToDevice));
   }
+  e->hV.assign(ss, 0.0); e->hVinv.assign(ss, 0.0);
+  for (int i = 0; i < S; ++i)
+    for (int m = 0; m < S; ++m) {
+      e->hV[(size_t)i * S + m] = Ui ? U[(size_t)i * S + m] : U[(size_t)m * S + i];
+      e->hVinv[(size_t)m * S + i] = Ui ? Ui[(size_t)m * S + i] : U[(size_t)m * S + i];
+    }
+  e->hLam = lam;
+  e->hPi.assign(priors, priors + S);
+  e->hRates.assign(rates, rates + K);
+  e->hProbs.assign(probs, probs + K);
   dfree(e->dSum); dfree(e->dSumSc);
   e->edge_ready = false;
   e->S = S; e->K = K; e->sym = (Ui == nullptr); e->pinvar = pinvar < 0 ? -1.0 : pinvar;
@@ -1625,6 +1638,10 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     fold_groups_kernel<<<(int)e->nPart, 32, 0, e->stream>>>(e->dGroups, (e->N + 31) / 32, e->dPart);
     LAUNCH_CHECK();
   }
+  if (e->defer_scalar) {  // the block partials are what phylo_lk_exchange_reduce needs; no local sum, no D2H
+    *done = true;
+    return PHYLO_OK;
+  }
   if ((rc = lk_finish_reduce(e, e->hScalar)) != PHYLO_OK) return rc;
   *done = true;
   return PHYLO_OK;
@@ -1995,6 +2012,152 @@ extern "C" int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, 
     dst.valid = true;
   }
   e->edge_ready = false;
+  if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
+}
+
+// ---- model-parameter derivatives (lk_grad_kernels.cuh)
+// matrices of one branch for the gradient kernel: P_k = exp(Q t r_k), then for every parameter p
+// d/d theta_p exp(Q t r_k) = dexp_X[D], X = Q t r_k, D = t (r_k dQ_p + drates_p[k] Q)
+static void grad_branch_matrices(const phylo_engine *e, double t, int np, const double *dQ, const double *drates,
+                                 double *out /* [(np+1)][K][S][S] */) {
+  const int S = e->S, K = e->K;
+  const size_t ss = (size_t)S * S;
+  const double *V = e->hV.data(), *Vi = e->hVinv.data(), *lam = e->hLam.data();
+  std::vector<double> G(ss), W(ss), x(S), ex(S);
+  auto sandwich = [&](const double *mid, double *dst) {  // dst = V mid Vinv
+    for (int i = 0; i < S; ++i)
+      for (int n = 0; n < S; ++n) {
+        double a = 0.0;
+        for (int m = 0; m < S; ++m) a += V[(size_t)i * S + m] * mid[(size_t)m * S + n];
+        W[(size_t)i * S + n] = a;
+      }
+    for (int i = 0; i < S; ++i)
+      for (int j = 0; j < S; ++j) {
+        double a = 0.0;
+        for (int n = 0; n < S; ++n) a += W[(size_t)i * S + n] * Vi[(size_t)n * S + j];
+        dst[(size_t)i * S + j] = a;
+      }
+  };
+  // G_p = Vinv dQ_p V, once per parameter (independent of branch and class; recomputed per branch here: S^3, tiny)
+  std::vector<double> Gp((size_t)np * ss, 0.0), mid(ss);
+  for (int p = 0; p < np; ++p) {
+    if (!dQ) break;
+    const double *dq = dQ + (size_t)p * ss;
+    for (int m = 0; m < S; ++m)
+      for (int j = 0; j < S; ++j) {
+        double a = 0.0;
+        for (int i = 0; i < S; ++i) a += Vi[(size_t)m * S + i] * dq[(size_t)i * S + j];
+        W[(size_t)m * S + j] = a;
+      }
+    for (int m = 0; m < S; ++m)
+      for (int n = 0; n < S; ++n) {
+        double a = 0.0;
+        for (int j = 0; j < S; ++j) a += W[(size_t)m * S + j] * V[(size_t)j * S + n];
+        Gp[(size_t)p * ss + (size_t)m * S + n] = a;
+      }
+  }
+  for (int k = 0; k < K; ++k) {
+    const double tau = t * e->hRates[k];
+    for (int m = 0; m < S; ++m) { x[m] = lam[m] * tau; ex[m] = std::exp(x[m]); }
+    std::fill(mid.begin(), mid.end(), 0.0);
+    for (int m = 0; m < S; ++m) mid[(size_t)m * S + m] = ex[m];
+    sandwich(mid.data(), out + (size_t)k * ss);
+    for (int p = 0; p < np; ++p) {
+      const double dr = drates ? drates[(size_t)p * K + k] : 0.0;
+      for (int m = 0; m < S; ++m)
+        for (int n = 0; n < S; ++n) {
+          // direction in eigen-space: t (r_k G_p + dr Lambda); divided difference Phi_mn of exp
+          double d = tau * Gp[(size_t)p * ss + (size_t)m * S + n];
+          if (m == n) d += t * dr * lam[m];
+          const double dx = x[m] - x[n];
+          const double phi = (m == n || std::fabs(dx) < 1e-9) ? 0.5 * (ex[m] + ex[n]) : (ex[m] - ex[n]) / dx;
+          mid[(size_t)m * S + n] = phi * d;
+        }
+      sandwich(mid.data(), out + ((size_t)(1 + p) * K + k) * ss);
+    }
+  }
+}
+
+extern "C" int phylo_lk_param_gradient(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                       double root_t, const int32_t *up_slot, int n_params, const double *dQ,
+                                       const double *drates, const double *dpi, double *lnl_out, double *grad_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0 || !e->has_model) return fail(e, PHYLO_ERR_STATE, "lk_param_gradient: model and tips first");
+  if (n_ops < 0 || (n_ops > 0 && !ops) || !up_slot || n_params < 1 || n_params > 64 || !grad_out || (!dQ && !drates && !dpi))
+    return fail(e, PHYLO_ERR_ARG, "lk_param_gradient: bad arguments (1..64 parameters, at least one of dQ / drates / dpi)");
+  if (e->S > 64) return fail(e, PHYLO_ERR_UNSUPPORTED, "lk_param_gradient: at most 64 states");
+  if (dpi && e->pinvar >= 0.0)
+    return fail(e, PHYLO_ERR_UNSUPPORTED, "lk_param_gradient: prior derivatives together with an invariant-sites class");
+  CK(cudaSetDevice(e->device));
+  int rc;
+  const int S = e->S, K = e->K;
+  const size_t ss = (size_t)S * S, per_branch = (size_t)(n_params + 1) * K * ss;
+  struct Edge { int a, b; double t; bool root; };
+  std::vector<Edge> edges;
+  edges.push_back(Edge{root_a, root_b, root_t, true});
+  for (int o = 0; o < n_ops; ++o) {
+    const int kids[2] = {ops[o].left, ops[o].right};
+    const double tk[2] = {ops[o].t_left, ops[o].t_right};
+    for (int c = 0; c < 2; ++c) {
+      const int v = kids[c];
+      if (v < 0 || v >= e->cap) return fail(e, PHYLO_ERR_ARG, "lk_param_gradient: op %d has bad slots", o);
+      if (up_slot[v] < 0) return fail(e, PHYLO_ERR_ARG, "lk_param_gradient: node %d has no up value (run phylo_lk_uppass with every slot set)", v);
+      edges.push_back(Edge{up_slot[v], v, tk[c], false});  // a = rest of the tree, b = the subtree below the branch
+    }
+  }
+  std::vector<double> hm(per_branch * edges.size());
+  for (size_t i = 0; i < edges.size(); ++i) grad_branch_matrices(e, edges[i].t, n_params, dQ, drates, hm.data() + i * per_branch);
+  double *dM = nullptr, *dG = nullptr, *dDpi = nullptr;
+  const size_t gdoubles = (size_t)n_params * e->nPart;
+  auto cleanup = [&] { cudaFree(dM); cudaFree(dG); cudaFree(dDpi); };
+  if (cudaMalloc(&dM, sizeof(double) * hm.size()) != cudaSuccess || cudaMalloc(&dG, sizeof(double) * gdoubles) != cudaSuccess ||
+      (dpi && cudaMalloc(&dDpi, sizeof(double) * n_params * S) != cudaSuccess)) {
+    cleanup();
+    return fail(e, PHYLO_ERR_CUDA, "lk_param_gradient: out of device memory");
+  }
+  cudaMemcpyAsync(dM, hm.data(), sizeof(double) * hm.size(), cudaMemcpyHostToDevice, e->stream);
+  cudaMemsetAsync(dG, 0, sizeof(double) * gdoubles, e->stream);
+  if (dpi) cudaMemcpyAsync(dDpi, dpi, sizeof(double) * n_params * S, cudaMemcpyHostToDevice, e->stream);
+  // parameters per pass: P + nq derivative matrices must fit shared memory, nq <= 8
+  const size_t fixed = sizeof(double) * ((size_t)K * ss + S + kLnlBlock + 32);
+  int nq_max = 8;
+  while (nq_max > 1 && fixed + sizeof(double) * (size_t)nq_max * (K * ss + S) > 200 * 1024) --nq_max;
+  if (fixed + sizeof(double) * (K * ss + S) > 200 * 1024) { cleanup(); return fail(e, PHYLO_ERR_UNSUPPORTED, "lk_param_gradient: matrices exceed shared memory"); }
+  for (size_t i = 0; i < edges.size(); ++i) {
+    Operand a, b;
+    if ((rc = lk_operand(e, edges[i].a, &a, "lk_param_gradient")) != PHYLO_OK) { cleanup(); return rc; }
+    if ((rc = lk_operand(e, edges[i].b, &b, "lk_param_gradient")) != PHYLO_OK) { cleanup(); return rc; }
+    for (int q0 = 0; q0 < n_params; q0 += nq_max) {
+      const int nq = std::min(nq_max, n_params - q0);
+      const size_t smem = fixed + sizeof(double) * (size_t)nq * (K * ss + S);
+      const double *dpi_edge = edges[i].root ? dDpi : nullptr;  // the prior enters once, at the root edge
+      ProfScope prof(e, KC_EDGE);
+#define GRAD_LAUNCH(ST_, M_)                                                                                              \
+  {                                                                                                                       \
+    auto kern = param_grad_kernel<ST_, M_>;                                                                               \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                   \
+    kern<<<(int)e->nPart, 256, smem, e->stream>>>(dM + i * per_branch, n_params, q0, nq, e->dPi, dpi_edge, e->dProbs,     \
+                                                  e->pinvar, (const M_ *)e->dInv, a.src, a.scale, a.tip, b.src, b.scale,   \
+                                                  b.tip, e->dWeights, dG, e->nPart, e->N, S, K);                          \
+  }
+      if (S == 4) GRAD_LAUNCH(4, uint8_t)
+      else if (e->mask_dev_bytes == 1) GRAD_LAUNCH(0, uint8_t)
+      else if (e->mask_dev_bytes == 4) GRAD_LAUNCH(0, uint32_t)
+      else GRAD_LAUNCH(0, uint64_t)
+#undef GRAD_LAUNCH
+      ++e->launches;
+      const cudaError_t st = cudaGetLastError();
+      if (st != cudaSuccess) { cleanup(); return fail(e, PHYLO_ERR_CUDA, "param_grad launch: %s", cudaGetErrorString(st)); }
+    }
+  }
+  std::vector<double> hg(gdoubles);
+  const cudaError_t st = cudaMemcpyAsync(hg.data(), dG, sizeof(double) * gdoubles, cudaMemcpyDeviceToHost, e->stream);
+  const cudaError_t st2 = cudaStreamSynchronize(e->stream);
+  cleanup();
+  if (st != cudaSuccess || st2 != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "lk_param_gradient: %s", cudaGetErrorString(st != cudaSuccess ? st : st2));
+  for (int p = 0; p < n_params; ++p) grad_out[p] = phylo_reduce_partials(hg.data() + (size_t)p * e->nPart, e->nPart);
+  if (lnl_out) *lnl_out = e->hScalar[0];
   if (e->prof_on) prof_resolve_lazy(e);
   return PHYLO_OK;
 }

@@ -68,6 +68,8 @@ SIGNATURES = {
     "phylo_bv_eltcount": (C.c_int, [_vp, C.c_int, _i64, C.POINTER(C.c_int)]),
     "phylo_lk_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_uppass": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
+    "phylo_lk_param_gradient": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, C.c_int, _dp, _dp, _dp,
+                                          _dp, _dp]),
     "phylo_exchange_alloc": (C.c_int, [_vp, C.POINTER(_vp), _vp]),
     "phylo_exchange_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "phylo_exchange_set": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -450,6 +452,19 @@ class Engine:
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
         up_slot = np.ascontiguousarray(up_slot, dtype=np.int32)
         self._ck(self.lib.phylo_lk_uppass(self.h, _p(ops), len(ops), root_a, root_b, float(root_t), _p(up_slot)))
+
+    def lk_param_gradient(self, ops, root_a, root_b, root_t, up_slot, dQ=None, drates=None, dpi=None):
+        """d lnL / d theta for every parameter described by (dQ[p], drates[p], dpi[p]); needs lk_score_tree +
+        lk_uppass (all up slots) first. Returns the gradient vector."""
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        up_slot = np.ascontiguousarray(up_slot, dtype=np.int32)
+        arrs = [None if a is None else _f64(np.asarray(a)) for a in (dQ, drates, dpi)]
+        n_params = next(a.shape[0] for a in arrs if a is not None)
+        grad = np.empty(n_params)
+        self._ck(self.lib.phylo_lk_param_gradient(
+            self.h, _p(ops), len(ops), root_a, root_b, float(root_t), _p(up_slot), n_params,
+            *[None if a is None else _p(a, _dp) for a in arrs], None, _p(grad, _dp)))
+        return grad
 
     def lk_score_tree(self, ops, root_a, root_b, root_t):
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
