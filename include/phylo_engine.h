@@ -369,6 +369,28 @@ int phylo_tcm_median_2(phylo_engine *e, int parent, int left, int right, uint64_
 int phylo_tcm_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
                          uint64_t *length_out);
 
+/* Cost-vector (Sankoff) parsimony under a general transformation cost matrix -- the weighted-state form of the
+ * NonAdditive path. The reference names the passes but never wrote them (commented-out
+ * bv_CAML_sankoff_median2_downpass / _uppass, lib/bitvector/bv.h:97-98); its set-based medians are
+ * phylo_tcm_* above. Per character and node a vector c[s] = cheapest cost of the subtree given state s;
+ *   median: c_p[s] = min_i (M[s][i] + c_l[i]) + min_j (M[s][j] + c_r[j])   (M[s][i]: parent state s -> child state i),
+ *   tips: 0 for the states of the mask, "infinity" elsewhere; length = sum_chars w min_{i,j} c_a[i] + M[i][j] + c_b[j]
+ * across the root edge. Up to 32 states (amino acids fit), any non-negative integer costs <= 10^6, no metricity
+ * assumed. codes: T x N state masks, one per element of elt_bytes in {1,2,4}; weights: non-negative integers as
+ * doubles or NULL. phylo_sankoff_score_tree runs a plain tree in ONE launch (running vector in registers, parked
+ * vectors on a per-thread stack: only the tip masks are read) and leaves every node's vectors in its slot when
+ * PHYLO_OPT_RETAIN_CLV is set; other schedules go node by node. With the 0/1 matrix the length is the Fitch
+ * length. Loading characters (or a matrix) of another alphabet size drops the matrix (the characters).
+ * phylo_sankoff_median_2 also returns sum_chars w min_s c_p[s], the cost of the subtree below `parent`. */
+int phylo_sankoff_set_matrix(phylo_engine *e, int n_states, const int32_t *M);
+int phylo_sankoff_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states, const void *codes,
+                           const double *weights, int capacity);
+int phylo_sankoff_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *subtree_cost_out);
+int phylo_sankoff_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                             uint64_t *length_out);
+/* out: N x n_states int32, values >= 2^28 mean "impossible" */
+int phylo_sankoff_get_costs(phylo_engine *e, int node, int32_t *out);
+
 /* Bitvector set algebra over node slots (lib/bitvector/bv.c:59-144; stubs :405-453) */
 int phylo_bv_union(phylo_engine *e, int dst, int a, int b);
 int phylo_bv_inter(phylo_engine *e, int dst, int a, int b);

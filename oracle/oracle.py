@@ -416,3 +416,34 @@ class Ref:
         b = np.ascontiguousarray(b, dtype=a.dtype)
         va, vb = self._vect(a), self._vect(b)
         return int(self.bv[a.dtype.itemsize * 8].bv_compare(C.byref(va), C.byref(vb)))
+
+
+SANKOFF_INF = 1 << 28
+
+
+def sankoff_score_tree(tips, M, weights, ops, n_nodes, root_a, root_b):
+    """Cost-vector (Sankoff) parsimony, numpy restatement of the rule in include/phylo_engine.h (the
+    reference only names the passes: commented-out bv_CAML_sankoff_median2_*, lib/bitvector/bv.h:97-98):
+    c_p[s] = min_i (M[s][i] + c_l[i]) + min_j (M[s][j] + c_r[j]); tips 0 / infinity by mask; length =
+    sum_chars w * min_{i,j} (c_a[i] + M[i][j] + c_b[j]). Pinned by exhaustive enumeration in
+    tests/test_oracle_cpu.py. Returns dict(length, vec = {slot: (N, S) int64})."""
+    tips = np.asarray(tips)
+    M = np.asarray(M, dtype=np.int64)
+    T, N = tips.shape
+    S = M.shape[0]
+    vec = {}
+
+    def v(slot):
+        if slot < T:
+            bits = (tips[slot].astype(np.int64)[:, None] >> np.arange(S)) & 1
+            return np.where(bits == 1, 0, SANKOFF_INF).astype(np.int64)
+        return vec[slot]
+
+    def relax(c):  # [n, s] = min_i M[s, i] + c[n, i]
+        return (M[None, :, :] + c[:, None, :]).min(axis=2)
+
+    for op in ops:
+        vec[int(op["parent"])] = np.minimum(relax(v(int(op["left"]))) + relax(v(int(op["right"]))), SANKOFF_INF)
+    join = (v(root_a) + relax(v(root_b))).min(axis=1)
+    w = np.ones(N, dtype=np.int64) if weights is None else np.asarray(weights).astype(np.int64)
+    return dict(length=int((join * w).sum()), vec=vec)

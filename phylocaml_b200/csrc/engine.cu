@@ -28,6 +28,7 @@
 #include "compress_kernels.cuh"
 #include "exchange_kernels.cuh"
 #include "lk_grad_kernels.cuh"
+#include "sankoff_kernels.cuh"
 #include "phylo_engine.h"
 
 using namespace phylo;
@@ -139,6 +140,16 @@ struct phylo_engine {
   uint64_t lkGen = 0;              // bumped whenever every slot is dropped (new alignment shape / model alphabet)
   double *dP = nullptr;  // transition matrices [branch][K][S][S]
   size_t capP = 0;       // branches
+  // ---- Sankoff (cost-vector parsimony, sankoff_kernels.cuh)
+  int skT = 0, skCap = 0, skS = 0;
+  int64_t skN = 0;
+  uint32_t *dSkTips = nullptr, *dSkW = nullptr;  // [T][N] state masks; integer weights or NULL
+  int *dSkM = nullptr;                           // [S][S]
+  std::vector<int *> skVec;                      // per slot: [S][N] cost planes (interior slots, on demand)
+  std::vector<char> skValid;
+  int **dSkTab = nullptr;
+  bool skTabDirty = true, skHasM = false;
+  unsigned long long *dSkTotal = nullptr;
   // host copy of the eigensystem (Q = V diag(lam) Vinv) for the model-parameter derivatives
   std::vector<double> hV, hVinv, hLam, hPi, hRates, hProbs;
   // device-side scalar exchange (exchange_kernels.cuh)
@@ -338,6 +349,14 @@ static void lk_free_data(phylo_engine *e) {
   ++e->lkGen;  // slots handed out so far are gone: late releases of them are ignored
 }
 
+static void sankoff_free_data(phylo_engine *e) {
+  for (auto &v : e->skVec) dfree(v);
+  e->skVec.clear(); e->skValid.clear();
+  dfree(e->dSkTips); dfree(e->dSkW); dfree(e->dSkTab);
+  e->skTabDirty = true;
+  e->skT = 0; e->skN = 0; e->skCap = 0;
+}
+
 static void fitch_free_data(phylo_engine *e) {
   for (auto &p : e->fPre) dfree(p);
   for (auto &p : e->fFin) dfree(p);
@@ -357,6 +376,8 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   cudaStreamSynchronize(e->stream);
   lk_free_data(e);
   fitch_free_data(e);
+  sankoff_free_data(e);
+  dfree(e->dSkM); dfree(e->dSkTotal);
   dfree(e->dU); dfree(e->dLam); dfree(e->dUi); dfree(e->dPi); dfree(e->dRates); dfree(e->dProbs);
   dfree(e->dP); dfree(e->dFrag); dfree(e->dT);
   for (void *p : e->xOpened) cudaIpcCloseMemHandle(p);
@@ -2013,6 +2034,220 @@ extern "C" int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, 
   }
   e->edge_ready = false;
   if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
+}
+
+// ---- Sankoff: cost-vector parsimony under a general cost matrix (sankoff_kernels.cuh)
+extern "C" int phylo_sankoff_set_matrix(phylo_engine *e, int n_states, const int32_t *M) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (n_states < 2 || n_states > 32 || !M) return fail(e, PHYLO_ERR_ARG, "sankoff_set_matrix: 2 <= n_states <= 32 and a matrix");
+  for (int i = 0; i < n_states * n_states; ++i)
+    if (M[i] < 0 || M[i] > 1000000) return fail(e, PHYLO_ERR_DATA, "sankoff_set_matrix: costs must be in [0, 1000000]");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->skT && n_states != e->skS) sankoff_free_data(e);  // another alphabet: the loaded characters go
+  dfree(e->dSkM);
+  CK(cudaMalloc(&e->dSkM, sizeof(int) * n_states * n_states));
+  CK(cudaMemcpy(e->dSkM, M, sizeof(int) * n_states * n_states, cudaMemcpyHostToDevice));
+  e->skS = n_states;
+  e->skHasM = true;
+  for (auto &v : e->skValid) v = 0;
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_sankoff_set_tips(phylo_engine *e, int T, int64_t N, int elt_bytes, int n_states, const void *codes,
+                                      const double *weights, int capacity) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (T < 2 || N < 1 || !codes || capacity < T || n_states < 2 || n_states > 32 ||
+      !(elt_bytes == 1 || elt_bytes == 2 || elt_bytes == 4) || n_states > 8 * elt_bytes)
+    return fail(e, PHYLO_ERR_ARG, "sankoff_set_tips: bad shape (2 <= n_states <= min(32, 8 elt_bytes), elt_bytes in {1,2,4})");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  sankoff_free_data(e);
+  if (e->skHasM && n_states != e->skS) { dfree(e->dSkM); e->skHasM = false; }  // another alphabet: the matrix goes
+  const uint32_t keep = n_states >= 32 ? 0xffffffffu : ((1u << n_states) - 1u);
+  std::vector<uint32_t> h((size_t)T * N);
+  for (size_t i = 0; i < h.size(); ++i) {
+    const uint32_t v = elt_bytes == 1 ? ((const uint8_t *)codes)[i] : (elt_bytes == 2 ? ((const uint16_t *)codes)[i] : ((const uint32_t *)codes)[i]);
+    if ((v & keep) == 0) return fail(e, PHYLO_ERR_DATA, "sankoff_set_tips: taxon %lld character %lld has an empty state set", (long long)(i / N), (long long)(i % N));
+    h[i] = v & keep;
+  }
+  CK(cudaMalloc(&e->dSkTips, sizeof(uint32_t) * h.size()));
+  CK(cudaMemcpy(e->dSkTips, h.data(), sizeof(uint32_t) * h.size(), cudaMemcpyHostToDevice));
+  if (weights) {
+    std::vector<uint32_t> hw(N);
+    for (int64_t i = 0; i < N; ++i) {
+      if (!(weights[i] >= 0.0) || weights[i] != std::floor(weights[i]) || weights[i] > 4e9)
+        return fail(e, PHYLO_ERR_DATA, "sankoff_set_tips: weights must be non-negative integers");
+      hw[i] = (uint32_t)weights[i];
+    }
+    CK(cudaMalloc(&e->dSkW, sizeof(uint32_t) * N));
+    CK(cudaMemcpy(e->dSkW, hw.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice));
+  }
+  if (!e->dSkTotal) CK(cudaMalloc(&e->dSkTotal, sizeof(unsigned long long)));
+  e->skVec.assign(capacity, nullptr);
+  e->skValid.assign(capacity, 0);
+  CK(cudaMalloc(&e->dSkTab, sizeof(int *) * capacity));
+  e->skTabDirty = true;
+  e->skT = T; e->skN = N; e->skCap = capacity; e->skS = n_states;
+  return PHYLO_OK;
+}
+
+static int sk_ready(phylo_engine *e, const char *who) {
+  if (!e->skT) return fail(e, PHYLO_ERR_STATE, "%s: no characters loaded (phylo_sankoff_set_tips)", who);
+  if (!e->skHasM) return fail(e, PHYLO_ERR_STATE, "%s: no cost matrix (phylo_sankoff_set_matrix)", who);
+  return PHYLO_OK;
+}
+static int sk_ensure(phylo_engine *e, int slot) {
+  if (e->skVec[slot]) return PHYLO_OK;
+  CK(cudaMalloc(&e->skVec[slot], sizeof(int) * (size_t)e->skS * e->skN));
+  e->skTabDirty = true;
+  return PHYLO_OK;
+}
+static int sk_st(int S) { return S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : (S <= 20 ? 20 : 32))); }
+
+#define SK_DISPATCH(st, EXPR)                        \
+  switch (st) {                                      \
+    case 4: { constexpr int ST = 4; EXPR; } break;   \
+    case 8: { constexpr int ST = 8; EXPR; } break;   \
+    case 16: { constexpr int ST = 16; EXPR; } break; \
+    case 20: { constexpr int ST = 20; EXPR; } break; \
+    default: { constexpr int ST = 32; EXPR; } break; \
+  }
+
+// parent >= 0: median into the slot; parent < 0: root-edge join. *total += the characters' weighted minimum / join
+static int sk_launch_node(phylo_engine *e, int parent, int left, int right, const char *who) {
+  auto operand = [&](int s, const uint32_t **tip, const int **vec) -> int {
+    *tip = nullptr; *vec = nullptr;
+    if (s < 0 || s >= e->skCap) return fail(e, PHYLO_ERR_ARG, "%s: node slot %d out of range", who, s);
+    if (s < e->skT) { *tip = e->dSkTips + (size_t)s * e->skN; return PHYLO_OK; }
+    if (!e->skValid[s]) return fail(e, PHYLO_ERR_STATE, "%s: node slot %d has no cost vectors yet", who, s);
+    *vec = e->skVec[s];
+    return PHYLO_OK;
+  };
+  const uint32_t *lt, *rt;
+  const int *lv, *rv;
+  int rc;
+  if ((rc = operand(left, &lt, &lv)) != PHYLO_OK) return rc;
+  if ((rc = operand(right, &rt, &rv)) != PHYLO_OK) return rc;
+  int *out = nullptr;
+  if (parent >= 0) {
+    if (parent < e->skT || parent >= e->skCap || parent == left || parent == right)
+      return fail(e, PHYLO_ERR_ARG, "%s: bad parent slot %d", who, parent);
+    if ((rc = sk_ensure(e, parent)) != PHYLO_OK) return rc;
+    out = e->skVec[parent];
+  }
+  const int g = grid_for(e->skN, 128, e->sm_count * 8);
+  ProfScope prof(e, KC_FITCH_NODE);
+  SK_DISPATCH(sk_st(e->skS), (sankoff_node_kernel<ST><<<g, 128, 0, e->stream>>>(e->dSkM, e->skS, e->skN, lt, lv, rt, rv, out, e->dSkW, e->dSkTotal)));
+  LAUNCH_CHECK();
+  if (parent >= 0) e->skValid[parent] = 1;
+  return PHYLO_OK;
+}
+
+static int sk_read_total(phylo_engine *e, uint64_t *out) {
+  CK(cudaMemcpyAsync(e->hScalar + HS_BAD, e->dSkTotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  std::memcpy(out, e->hScalar + HS_BAD, 8);
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_sankoff_median_2(phylo_engine *e, int parent, int left, int right, uint64_t *subtree_cost_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = sk_ready(e, "sankoff_median_2")) != PHYLO_OK) return rc;
+  if (parent < 0) return fail(e, PHYLO_ERR_ARG, "sankoff_median_2: bad parent slot %d", parent);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemsetAsync(e->dSkTotal, 0, sizeof(unsigned long long), e->stream));
+  if ((rc = sk_launch_node(e, parent, left, right, "sankoff_median_2")) != PHYLO_OK) return rc;
+  if (subtree_cost_out) return sk_read_total(e, subtree_cost_out);
+  return PHYLO_OK;
+}
+
+extern "C" int phylo_sankoff_score_tree(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                        uint64_t *length_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  int rc;
+  if ((rc = sk_ready(e, "sankoff_score_tree")) != PHYLO_OK) return rc;
+  if (n_ops < 0 || (n_ops > 0 && !ops) || !length_out) return fail(e, PHYLO_ERR_ARG, "sankoff_score_tree: bad arguments");
+  CK(cudaSetDevice(e->device));
+  std::vector<char> ready(e->skCap, 0);
+  for (int s = 0; s < e->skCap; ++s) ready[s] = s < e->skT || e->skValid[s];
+  for (int o = 0; o < n_ops; ++o) {
+    const phylo_op &op = ops[o];
+    if (op.parent < e->skT || op.parent >= e->skCap || op.left < 0 || op.left >= e->skCap || op.right < 0 || op.right >= e->skCap ||
+        op.left == op.parent || op.right == op.parent)
+      return fail(e, PHYLO_ERR_ARG, "sankoff_score_tree: op %d has bad slots", o);
+    if (!ready[op.left] || !ready[op.right]) return fail(e, PHYLO_ERR_ARG, "sankoff_score_tree: op %d uses a child that is not computed yet", o);
+    ready[op.parent] = 1;
+  }
+  if (root_a < 0 || root_a >= e->skCap || root_b < 0 || root_b >= e->skCap || !ready[root_a] || !ready[root_b])
+    return fail(e, PHYLO_ERR_ARG, "sankoff_score_tree: bad root edge (%d,%d)", root_a, root_b);
+  CK(cudaMemsetAsync(e->dSkTotal, 0, sizeof(unsigned long long), e->stream));
+  FusedPlan pl;
+  const bool fused = e->opt_fused && n_ops > 0 && build_fused_plan(e->skCap, e->skT, ops, n_ops, root_a, root_b, 0.0, pl) &&
+                     pl.depth <= kSkMaxDepth;
+  if (fused) {
+    if (e->opt_retain)
+      for (int o = 0; o < n_ops; ++o)
+        if ((rc = sk_ensure(e, ops[o].parent)) != PHYLO_OK) return rc;
+    const size_t pbytes = sizeof(SkInstr) * pl.steps.size();
+    if (pbytes > e->capProg) {
+      CK(cudaStreamSynchronize(e->stream));
+      dfree(e->dProg);
+      if (e->hProg) { cudaFreeHost(e->hProg); e->hProg = nullptr; }
+      e->capProg = 0;
+      CK(cudaMalloc(&e->dProg, pbytes * 2));
+      CK(cudaMallocHost(&e->hProg, pbytes * 2));
+      e->capProg = pbytes * 2;
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->skTabDirty) {
+      CK(cudaMemcpy(e->dSkTab, e->skVec.data(), sizeof(int *) * e->skCap, cudaMemcpyHostToDevice));
+      e->skTabDirty = false;
+    }
+    SkInstr *hp = (SkInstr *)e->hProg;
+    for (size_t i = 0; i < pl.steps.size(); ++i) {
+      const PlanStep &st = pl.steps[i];
+      hp[i] = SkInstr{st.lkind | (st.rkind << 2) | (st.push_first << 4), st.lidx, st.ridx, e->opt_retain ? st.out_slot : -1};
+    }
+    CK(cudaMemcpyAsync(e->dProg, e->hProg, pbytes, cudaMemcpyHostToDevice, e->stream));
+    const int g = grid_for(e->skN, 128, e->sm_count * 8);
+    {
+      ProfScope prof(e, KC_FITCH_TREE);
+      if (e->opt_retain) {
+        SK_DISPATCH(sk_st(e->skS), (sankoff_tree_kernel<ST, true><<<g, 128, 0, e->stream>>>(
+                                       e->dSkM, e->skS, e->skN, e->dSkTips, e->skN, (const SkInstr *)e->dProg, n_ops, e->dSkTab, e->dSkW, e->dSkTotal)));
+      } else {
+        SK_DISPATCH(sk_st(e->skS), (sankoff_tree_kernel<ST, false><<<g, 128, 0, e->stream>>>(
+                                       e->dSkM, e->skS, e->skN, e->dSkTips, e->skN, (const SkInstr *)e->dProg, n_ops, e->dSkTab, e->dSkW, e->dSkTotal)));
+      }
+      LAUNCH_CHECK();
+    }
+    for (int o = 0; o < n_ops; ++o) e->skValid[ops[o].parent] = e->opt_retain ? 1 : 0;
+  } else {
+    for (int o = 0; o < n_ops; ++o) {
+      // the subtree minima of interior medians are not part of the length: only the root join is summed
+      if ((rc = sk_launch_node(e, ops[o].parent, ops[o].left, ops[o].right, "sankoff_score_tree")) != PHYLO_OK) return rc;
+    }
+    CK(cudaMemsetAsync(e->dSkTotal, 0, sizeof(unsigned long long), e->stream));
+    if ((rc = sk_launch_node(e, -1, root_a, root_b, "sankoff_score_tree")) != PHYLO_OK) return rc;
+  }
+  rc = sk_read_total(e, length_out);
+  if (e->prof_on) prof_resolve_lazy(e);
+  return rc;
+}
+
+extern "C" int phylo_sankoff_get_costs(phylo_engine *e, int node, int32_t *out) {
+  if (!e || !out) return PHYLO_ERR_ARG;
+  if (!e->skT) return fail(e, PHYLO_ERR_STATE, "sankoff_get_costs: no characters loaded");
+  if (node < e->skT || node >= e->skCap || !e->skValid[node]) return fail(e, PHYLO_ERR_STATE, "sankoff_get_costs: node slot %d has no cost vectors", node);
+  CK(cudaSetDevice(e->device));
+  std::vector<int32_t> planes((size_t)e->skS * e->skN);
+  CK(cudaMemcpyAsync(planes.data(), e->skVec[node], sizeof(int) * planes.size(), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (int64_t n = 0; n < e->skN; ++n)
+    for (int s = 0; s < e->skS; ++s) out[(size_t)n * e->skS + s] = planes[(size_t)s * e->skN + n];
   return PHYLO_OK;
 }
 

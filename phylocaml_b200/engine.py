@@ -70,6 +70,11 @@ SIGNATURES = {
     "phylo_lk_uppass": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp]),
     "phylo_lk_param_gradient": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, C.c_int, _dp, _dp, _dp,
                                           _dp, _dp]),
+    "phylo_sankoff_set_matrix": (C.c_int, [_vp, C.c_int, _vp]),
+    "phylo_sankoff_set_tips": (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, _vp, _dp, C.c_int]),
+    "phylo_sankoff_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "phylo_sankoff_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "phylo_sankoff_get_costs": (C.c_int, [_vp, C.c_int, _vp]),
     "phylo_exchange_alloc": (C.c_int, [_vp, C.POINTER(_vp), _vp]),
     "phylo_exchange_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "phylo_exchange_set": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -320,6 +325,36 @@ class Engine:
         return int(self.lib.phylo_engine_launch_count(self.h))
 
     OPT_FUSED_TREE, OPT_RETAIN_CLV, OPT_FITCH_WALK, OPT_DEFER_SCALAR = 1, 2, 3, 4
+
+    # ---- Sankoff cost-vector parsimony
+    def sankoff_set_matrix(self, M):
+        M = np.ascontiguousarray(M, dtype=np.int32)
+        self._ck(self.lib.phylo_sankoff_set_matrix(self.h, M.shape[0], _p(M)))
+
+    def sankoff_set_tips(self, codes, n_states, weights=None, capacity=None):
+        codes = np.ascontiguousarray(codes)
+        T, N = codes.shape
+        capacity = 2 * T if capacity is None else capacity
+        w = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_sankoff_set_tips(self.h, T, N, codes.dtype.itemsize, n_states, _p(codes), _p(w, _dp), capacity))
+        self.sankoff_shape = (T, N, capacity, n_states)
+
+    def sankoff_median_2(self, parent, left, right):
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_sankoff_median_2(self.h, parent, left, right, C.byref(out)))
+        return int(out.value)
+
+    def sankoff_score_tree(self, ops, root_a, root_b):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        out = C.c_uint64()
+        self._ck(self.lib.phylo_sankoff_score_tree(self.h, _p(ops), len(ops), root_a, root_b, C.byref(out)))
+        return int(out.value)
+
+    def sankoff_get_costs(self, node):
+        T, N, cap, S = self.sankoff_shape
+        out = np.empty((N, S), dtype=np.int32)
+        self._ck(self.lib.phylo_sankoff_get_costs(self.h, node, _p(out)))
+        return out
 
     # ---- device-side scalar exchange (include/phylo_engine.h)
     def exchange_alloc(self):
