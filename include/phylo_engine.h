@@ -176,6 +176,9 @@ int phylo_lk_node_release(phylo_engine *e, int slot, uint64_t generation);
 /* any pointer may be NULL. capacity: interior slots in the table (total slots - T); in_use: slots
  * currently handed out; with_buffers: interior slots that own a device CLV buffer (live or pooled) */
 int phylo_lk_node_stats(phylo_engine *e, int *capacity, int *in_use, int *with_buffers);
+/* the loaded likelihood alignment: taxa, site patterns, and the current size of the slot table (tips
+ * included; what an array indexed by slot, like phylo_lk_uppass's up_slot, must cover). NULL = not wanted */
+int phylo_lk_shape(phylo_engine *e, int *n_taxa, int64_t *n_patterns, int *n_slots);
 /* Likelihood.median_2 (lib/nodeData.ml:21, lib/likelihood_c.ml:15): CLV of `parent` from its
  * two children with per-site rescaling. */
 int phylo_lk_median_2(phylo_engine *e, int parent, int left, double t_left, int right,

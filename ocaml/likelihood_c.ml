@@ -40,6 +40,12 @@ external edge_eval_ : engine -> node -> node -> vector -> matrix -> unit = "like
 external score_tree_ : engine -> ids -> matrix -> (int * int * float) -> float * node array
                      = "likelihood_CAML_score_tree"
 
+external uppass_ : engine -> ids -> matrix -> (int * int * float) -> node array -> node array
+                 = "likelihood_CAML_uppass"
+external param_gradient_ : engine -> ids -> matrix -> (int * int * float) -> (node array * node array)
+                           -> (matrix option * matrix option * matrix option) -> vector -> unit
+                         = "likelihood_CAML_param_gradient_bc" "likelihood_CAML_param_gradient"
+
 type m = MlModel.t
 
 type spec = { engine : engine; n_taxa : int; n_patterns : int; }
@@ -167,3 +173,21 @@ let create_spec_text ?(device = 0) (model : m) (alph : Alphabet.t) (text : masks
   set_symbol_table_ e (Some (symbol_table alph (Bigarray.Array2.dim1 model.MlModel.u)));
   set_tips_ e text weights (2 * n_taxa);
   { engine = e; n_taxa; n_patterns = Bigarray.Array2.dim2 text }
+
+
+(* ---- beyond NodeData.S: what Node.Make3D and MlModel's optimisers need from the native side ---- *)
+
+(* Third directions for a whole scored tree (Node.Make3D keeps one value per excluded neighbour,
+   lib/node.ml:363-477): [down] is score_tree's node array for the schedule [ids]/[lens]; the result holds,
+   for op i, the value of the rest of the tree above its left child at 2 i and above its right child at
+   2 i + 1. (child, its up value) is then an ordinary directional pair: root_cost / adjust_3 apply to ANY
+   branch, and for a reversible model every branch gives the same lnL. *)
+let uppass spec ids lens root (down : node array) : node array = uppass_ spec.engine ids lens root down
+
+(* d lnL / d theta for the parameters a model optimiser moves -- the native half of gen_subst_opt_func /
+   gen_rates_opt_func / gen_prior_opt_func (lib/mlModel.ml:822-829). The caller describes each parameter by
+   dQ/dtheta (rows of S*S), d rates/dtheta (rows of K), d priors/dtheta (rows of S). *)
+let param_gradient spec ids lens root ~down ~up ?dq ?drates ?dpriors (n_params : int) : vector =
+  let out = Bigarray.Array1.create Bigarray.float64 Bigarray.c_layout n_params in
+  param_gradient_ spec.engine ids lens root (down, up) (dq, drates, dpriors) out;
+  out

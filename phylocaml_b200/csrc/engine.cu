@@ -879,6 +879,14 @@ extern "C" int phylo_lk_node_stats(phylo_engine *e, int *capacity, int *in_use, 
   return PHYLO_OK;
 }
 
+extern "C" int phylo_lk_shape(phylo_engine *e, int *n_taxa, int64_t *n_patterns, int *n_slots) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (n_taxa) *n_taxa = e->T;
+  if (n_patterns) *n_patterns = e->N;
+  if (n_slots) *n_slots = e->cap;
+  return PHYLO_OK;
+}
+
 struct Operand {
   const void *src;
   const int32_t *scale;

@@ -75,6 +75,7 @@ SIGNATURES = {
     "phylo_sankoff_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_sankoff_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_sankoff_get_costs": (C.c_int, [_vp, C.c_int, _vp]),
+    "phylo_lk_shape": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_i64), C.POINTER(C.c_int)]),
     "phylo_exchange_alloc": (C.c_int, [_vp, C.POINTER(_vp), _vp]),
     "phylo_exchange_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "phylo_exchange_set": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),

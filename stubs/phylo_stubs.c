@@ -397,6 +397,109 @@ CAMLprim value likelihood_CAML_score_tree(value ve, value ids, value lens, value
   CAMLreturn(res);
 }
 
+/* schedule of an already scored tree with the REAL slots: ids as in score_tree, interior id of op i = the
+ * slot of down.(i) (score_tree's node array). Returns malloc'ed ops; *ra / *rb are mapped in place. */
+static phylo_op *ops_of_scored_tree(value ids, value lens, value down, int *ra, int *rb, int *n_out)
+{
+  int n = (int)Bigarray_val(ids)->dim[0], i, max_id = 0;
+  const int32_t *id = (const int32_t *)Data_bigarray_val(ids);
+  const double *tl = (const double *)Data_bigarray_val(lens);
+  phylo_op *ops = (phylo_op *)calloc(n > 0 ? n : 1, sizeof(phylo_op));
+  int *map;
+  for (i = 0; i < 3 * n; ++i) if (id[i] > max_id) max_id = id[i];
+  if (*ra > max_id) max_id = *ra;
+  if (*rb > max_id) max_id = *rb;
+  map = (int *)malloc(sizeof(int) * (size_t)(max_id + 1));
+  for (i = 0; i <= max_id; ++i) map[i] = i;
+  for (i = 0; i < n; ++i) map[id[3 * i]] = Node_slot(Field(down, i));
+  for (i = 0; i < n; ++i) {
+    ops[i].parent = map[id[3 * i]]; ops[i].left = map[id[3 * i + 1]]; ops[i].right = map[id[3 * i + 2]];
+    ops[i].pad_ = 0; ops[i].t_left = tl[2 * i]; ops[i].t_right = tl[2 * i + 1];
+  }
+  *ra = map[*ra];
+  *rb = map[*rb];
+  free(map);
+  *n_out = n;
+  return ops;
+}
+
+/* external uppass : engine -> ids -> lens -> (root_a * root_b * root_t) -> node array (score_tree's) -> node array
+ * The second half of Node.Make3D (lib/node.ml:363-477): for op i the result holds at 2 i (2 i + 1) the value
+ * of the REST OF THE TREE above its left (right) child -- the third direction of that child. Any branch
+ * (child, its up value) can then be handed to edge_lnl / optimize_branch / edge_eval (readjust_3,
+ * lib/node.ml:239-256). Fresh node values; the inputs are not touched. */
+CAMLprim value likelihood_CAML_uppass(value ve, value ids, value lens, value root, value down)
+{
+  CAMLparam5(ve, ids, lens, root, down);
+  CAMLlocal2(arr, nd);
+  phylo_engine *e = Engine_val(ve);
+  int n = (int)Bigarray_val(ids)->dim[0], i, rc, n_slots = 0, n_ops = 0;
+  int ra = Int_val(Field(root, 0)), rb = Int_val(Field(root, 1));
+  double rt = Double_val(Field(root, 2));
+  int *ups = (int *)calloc(2 * (n > 0 ? n : 1), sizeof(int));
+  uint64_t *gens = (uint64_t *)calloc(2 * (n > 0 ? n : 1), sizeof(uint64_t));
+  int32_t *up_slot;
+  phylo_op *ops;
+  for (i = 0; i < 2 * n; ++i) ups[i] = slot_new(ve, 0, &gens[i]); /* may run the GC: Bigarrays are read afterwards */
+  ops = ops_of_scored_tree(ids, lens, down, &ra, &rb, &n_ops);
+  phylo_lk_shape(e, NULL, NULL, &n_slots);
+  up_slot = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_slots > 0 ? n_slots : 1));
+  for (i = 0; i < n_slots; ++i) up_slot[i] = -1;
+  for (i = 0; i < n; ++i) { up_slot[ops[i].left] = ups[2 * i]; up_slot[ops[i].right] = ups[2 * i + 1]; }
+  caml_release_runtime_system();
+  rc = phylo_lk_uppass(e, ops, n, ra, rb, rt, up_slot);
+  caml_acquire_runtime_system();
+  if (rc != PHYLO_OK)
+    for (i = 0; i < 2 * n; ++i) slot_drop(e, 0, ups[i], gens[i]);
+  if (rc == PHYLO_OK) {
+    arr = caml_alloc_tuple(2 * n);
+    for (i = 0; i < 2 * n; ++i) {
+      nd = node_wrap(ve, 0, ups[i], 1, gens[i]);
+      Store_field(arr, i, nd);
+    }
+  }
+  free(ops); free(ups); free(gens); free(up_slot);
+  check(e, rc);
+  CAMLreturn(arr);
+}
+
+/* external param_gradient : engine -> ids -> lens -> (root_a * root_b * root_t) -> (node array * node array)
+ *                           -> (matrix option * matrix option * matrix option) -> vector -> unit
+ * (down, up) = the node arrays of score_tree and uppass; the options are dQ (n_params x S*S), drates
+ * (n_params x K), dpriors (n_params x S); out: n_params. What gen_subst_opt_func / gen_rates_opt_func /
+ * gen_prior_opt_func (lib/mlModel.ml:822-829, `failwith "todo"`) need for a gradient-based optimiser. */
+CAMLprim value likelihood_CAML_param_gradient(value ve, value ids, value lens, value root, value nodes, value dirs, value out)
+{
+  CAMLparam5(ve, ids, lens, root, nodes);
+  CAMLxparam2(dirs, out);
+  phylo_engine *e = Engine_val(ve);
+  value down = Field(nodes, 0), up = Field(nodes, 1);
+  int n = (int)Bigarray_val(ids)->dim[0], i, rc, n_slots = 0, n_ops = 0, n_params = (int)Bigarray_val(out)->dim[0];
+  int ra = Int_val(Field(root, 0)), rb = Int_val(Field(root, 1));
+  double rt = Double_val(Field(root, 2));
+  const double *dq = (Field(dirs, 0) == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(Field(dirs, 0), 0));
+  const double *dr = (Field(dirs, 1) == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(Field(dirs, 1), 0));
+  const double *dp = (Field(dirs, 2) == Val_int(0)) ? NULL : (const double *)Data_bigarray_val(Field(Field(dirs, 2), 0));
+  double *g = (double *)Data_bigarray_val(out);
+  phylo_op *ops = ops_of_scored_tree(ids, lens, down, &ra, &rb, &n_ops);
+  int32_t *up_slot;
+  phylo_lk_shape(e, NULL, NULL, &n_slots);
+  up_slot = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_slots > 0 ? n_slots : 1));
+  for (i = 0; i < n_slots; ++i) up_slot[i] = -1;
+  for (i = 0; i < n; ++i) { up_slot[ops[i].left] = Node_slot(Field(up, 2 * i)); up_slot[ops[i].right] = Node_slot(Field(up, 2 * i + 1)); }
+  caml_release_runtime_system();
+  rc = phylo_lk_param_gradient(e, ops, n, ra, rb, rt, up_slot, n_params, dq, dr, dp, NULL, g);
+  caml_acquire_runtime_system();
+  free(ops); free(up_slot);
+  check(e, rc);
+  CAMLreturn(Val_unit);
+}
+CAMLprim value likelihood_CAML_param_gradient_bc(value *argv, int argn)
+{
+  (void)argn;
+  return likelihood_CAML_param_gradient(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5], argv[6]);
+}
+
 /* external edge_lnl : engine -> node -> node -> vector (lengths) -> vector (out lnL) -> unit
  * Likelihood_c.root_cost / distance_1 (lib/nodeData.ml:29,32) for a batch of lengths */
 CAMLprim value likelihood_CAML_edge_lnl(value ve, value va, value vb, value ts, value out)
