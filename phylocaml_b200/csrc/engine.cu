@@ -7,6 +7,7 @@
 // handle's device.
 #include <cuda.h>  // CUtensorMap types only; the driver entry point is resolved at run time
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a tool is attached
 
 #include <algorithm>
 #include <cmath>
@@ -227,11 +228,14 @@ static int fail(phylo_engine *e, int code, const char *fmt, ...) {
                   cudaGetErrorString(err_), __FILE__, __LINE__);                         \
   } while (0)
 
-// RAII: records an event pair on the engine's stream around the launches in its scope
+// RAII: an NVTX range named after the kernel class around the launches in its scope (nsys / ncu --nvtx
+// timelines show "tree_fused", "prune_inner_inner", "fitch_tree", ... instead of mangled names) and, while
+// the engine's profiler is on, an event pair on the engine's stream
 struct ProfScope {
   phylo_engine *e;
   int idx = -1;
   ProfScope(phylo_engine *e_, int cls) : e(e_) {
+    nvtxRangePushA(kClassNames[cls]);
     if (!e->prof_on) return;
     idx = (int)e->prof_pending.size();
     while (e->prof_pool.size() < (size_t)(2 * idx + 2)) {
@@ -244,6 +248,7 @@ struct ProfScope {
   }
   ~ProfScope() {
     if (idx >= 0) cudaEventRecord(e->prof_pool[2 * idx + 1], e->stream);
+    nvtxRangePop();
   }
 };
 

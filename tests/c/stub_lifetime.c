@@ -28,6 +28,8 @@ value likelihood_CAML_median2(value, value, value, value, value);
 value likelihood_CAML_median3(value, value, value, value);
 value likelihood_CAML_edge_lnl(value, value, value, value, value);
 value likelihood_CAML_score_tree(value, value, value, value);
+value likelihood_CAML_uppass(value, value, value, value, value);
+value likelihood_CAML_param_gradient(value, value, value, value, value, value, value);
 value nonadd_CAML_set_tips(value, value, value, value, value);
 value nonadd_CAML_tip(value, value);
 value nonadd_CAML_median2(value, value, value);
@@ -192,6 +194,34 @@ int main(void)
     value m3 = likelihood_CAML_median3(engine, pair_nf(Field(nodes, T - 4), 0.05), pair_nf(tips[T - 2], 0.1), pair_nf(tips[T - 1], 0.1));
     NOFAIL();
     REQUIRE(Int_val(phylo_CAML_node_slot(m3)) >= T, "median_3 must return an interior slot");
+    /* Make3D's third directions through the stub: every branch below the root edge gives the tree's lnL
+     * (pulley principle; the model here is reversible), and the Gamma-shape-free gradient entry point runs */
+    {
+      value ups = likelihood_CAML_uppass(engine, ba(CAML_BA_INT32, 2, ids, T - 2, 3), ba(CAML_BA_FLOAT64, 2, lens, T - 2, 2), root, nodes);
+      NOFAIL();
+      REQUIRE(Wosize_val(ups) == 2 * (T - 2), "uppass returned %d node values", (int)Wosize_val(ups));
+      for (int i = 0; i < T - 2; ++i) {
+        for (int c = 0; c < 2; ++c) {
+          static double tl1[1], o1[1];
+          value child = (c == 0) ? (i == 0 ? tips[0] : Field(nodes, i - 1)) : tips[i + 1];
+          tl1[0] = lens[2 * i + c];
+          likelihood_CAML_edge_lnl(engine, child, Field(ups, 2 * i + c), ba(CAML_BA_FLOAT64, 1, tl1, 1, 0), ba(CAML_BA_FLOAT64, 1, o1, 1, 0));
+          NOFAIL();
+          REQUIRE(fabs(o1[0] - lnl) <= 1e-10 * fabs(lnl), "edge below op %d side %d: %.17g vs %.17g", i, c, o1[0], lnl);
+        }
+      }
+      static double drates[1] = {1.0}, grad[1];
+      value pair = caml_alloc_tuple(2), dirs = caml_alloc_tuple(3), some = caml_alloc_tuple(1);
+      Store_field(pair, 0, nodes); Store_field(pair, 1, ups);
+      Store_field(some, 0, ba(CAML_BA_FLOAT64, 2, drates, 1, 1));
+      Store_field(dirs, 0, Val_int(0)); Store_field(dirs, 1, some); Store_field(dirs, 2, Val_int(0));
+      likelihood_CAML_param_gradient(engine, ba(CAML_BA_INT32, 2, ids, T - 2, 3), ba(CAML_BA_FLOAT64, 2, lens, T - 2, 2), root, pair, dirs,
+                                     ba(CAML_BA_FLOAT64, 1, grad, 1, 0));
+      NOFAIL();
+      /* one rate class: d lnL / d rate = sum over branches of t * d lnL / d t -- finite and non-zero here */
+      REQUIRE(isfinite(grad[0]) && grad[0] != 0.0, "param_gradient gave %.17g", grad[0]);
+      for (int i = 0; i < 2 * (T - 2); ++i) shim_mark_dead(Field(ups, i));
+    }
     for (int i = 0; i < T - 2; ++i) shim_mark_dead(Field(nodes, i));
     shim_mark_dead(m3);
   }
