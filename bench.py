@@ -633,6 +633,84 @@ def run_group(ctx, args, headline):
     return rec
 
 
+def run_directions(torch, engine, tree_mod, local, wl, model, base, ops, ra, rb, rt, n_nodes, n_sample=131072):
+    """phylo_lk_uppass + edge joins + phylo_lk_param_gradient on the first n_sample patterns of the workload
+    (own engine; one GPU). candidate joins/s: one phylo_lk_edge_lnl per branch of the tree -- what an SPR / TBR
+    neighbourhood costs per candidate once the directional CLVs exist (lib/tree.ml:299-494)."""
+    from phylocaml_b200 import mlmodel
+
+    T, S, K = wl["T"], wl["S"], wl["K"]
+    try:
+        up_slot, cap, _, edges = tree_mod.uppass_plan(ops, ra, rb, rt, n_nodes)
+        tips = tile_cols(base, 0, n_sample)
+        e2 = engine.Engine(local)
+        e2.lk_set_model(model)
+        e2.lk_set_tips(tips, capacity=cap)
+        lnl = e2.lk_score_tree(ops, ra, rb, rt)
+
+        def timed(fn, reps):
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(reps):
+                out = fn()
+            b1.record()
+            torch.cuda.synchronize()
+            return b0.elapsed_time(b1) / reps, out
+
+        e2.lk_uppass(ops, ra, rb, rt, up_slot)
+        up_ms, _ = timed(lambda: e2.lk_uppass(ops, ra, rb, rt, up_slot), 2)
+        down_ms, _ = timed(lambda: e2.lk_score_tree(ops, ra, rb, rt), 2)
+        ea, eb, et = [e[0] for e in edges], [e[1] for e in edges], [e[2] for e in edges]
+        vals = e2.lk_edge_lnl_batch(ea, eb, et)
+        join_ms, vals = timed(lambda: e2.lk_edge_lnl_batch(ea, eb, et), 2)
+        worst = max(abs(x - lnl) / abs(lnl) for x in vals)
+        rec = {"patterns": n_sample, "taxa": T, "edges": len(edges), "down_pass_ms": down_ms, "up_pass_ms": up_ms,
+               "all_edge_joins_ms": join_ms, "candidate_joins_per_s": len(edges) / (join_ms * 1e-3),
+               "join_site_updates_per_s": len(edges) * n_sample / (join_ms * 1e-3),
+               "max_rel_diff_of_edge_lnl_vs_root_edge": worst, "tolerance": 1e-11,
+               "note": "up pass = 2T-4 per-node pruning updates (one per directional CLV); each join reads two CLVs"}
+        if S == 4:  # GTR+G: 5 exchangeabilities + the Gamma shape, against central differences of full evaluations
+            h, alpha = 1e-6, 0.5
+            co = np.array(GTR_CO, dtype=float)
+
+            def mk(c, a):
+                return mlmodel.create(("GTR", list(c)), 4, pi=GTR_PI, site_var=("gamma", K, a))
+
+            dQ, drates = np.zeros((6, 4, 4)), np.zeros((6, K))
+            for p in range(5):
+                e = np.zeros(5)
+                e[p] = h
+                dQ[p] = (mk(co + e, alpha)["Q"] - mk(co - e, alpha)["Q"]) / (2 * h)
+            drates[5] = (mk(co, alpha + h)["rates"] - mk(co, alpha - h)["rates"]) / (2 * h)
+            g = e2.lk_param_gradient(ops, ra, rb, rt, up_slot, dQ=dQ, drates=drates)
+            grad_ms, g = timed(lambda: e2.lk_param_gradient(ops, ra, rb, rt, up_slot, dQ=dQ, drates=drates), 1)
+
+            def f(c, a):
+                e2.lk_set_model(mk(c, a))
+                e2.lk_set_tips(tips, capacity=cap)
+                return e2.lk_score_tree(ops, ra, rb, rt)
+
+            hh = 1e-4
+            t0 = time.perf_counter()
+            fd = []
+            for p in range(6):
+                e = np.zeros(5)
+                if p < 5:
+                    e[p] = hh
+                    fd.append((f(co + e, alpha) - f(co - e, alpha)) / (2 * hh))
+                else:
+                    fd.append((f(co, alpha + hh) - f(co, alpha - hh)) / (2 * hh))
+            fd_ms = 1e3 * (time.perf_counter() - t0)
+            rec["param_gradient"] = {"parameters": "5 GTR exchangeabilities + Gamma shape", "gradient_ms": grad_ms,
+                                     "central_differences_ms_incl_model_setup": fd_ms, "gradient": [float(x) for x in g],
+                                     "max_rel_diff_vs_central_differences": float(max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(g, fd)))}
+        e2.close()
+        return rec
+    except Exception as ex:  # noqa: BLE001 -- a side record must not cost the headline line
+        return {"error": str(ex)[:300]}
+
+
 def setup_exchange(ctx, args, eng):
     """Peer-mapped mailboxes between the ranks' engines (cudaIpc handles travel over the process group).
     Returns a note for the JSON line; ctx-independent state lives in the engine. Every rank must take the
@@ -966,6 +1044,12 @@ def run_workload(ctx, args, key, wl, primary):
         eng.lk_set_tips(tips, capacity=n_nodes, packed_n=packed_n)
         step()  # restore the unmodified tree's state
 
+    # ---- every edge as a root edge (3-directional CLVs) and the model-parameter gradient
+    # (rank 2), on a pattern sample small enough to hold the 2 T - 4 extra CLVs next to the engine above
+    directions = None
+    if kind == "lk" and primary and not args.no_other_modes and rank == 0:
+        directions = run_directions(torch, engine, tree_mod, local, wl, model, base, ops, ra, rb, rt, n_nodes)
+
     # ---- CPU baseline + correctness check against the oracle (rank 0, N=1 only)
     cpu, check = None, {"result": result, "result_e2e": result_e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -1007,7 +1091,7 @@ def run_workload(ctx, args, key, wl, primary):
             "roofline_hbm": roof if roof_tensor and S > 32 else None,
             "roofline_tensor": roof_tensor if roof_tensor and S <= 32 else None,
             "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": e2e, "branch_loop": branch_loop, "gpu_launches": int(step_launches * steps),
+            "e2e": e2e, "branch_loop": branch_loop, "directions": directions, "gpu_launches": int(step_launches * steps),
             "gpu_launches_total_incl_warmup": int(launches), "clocks": clocks, "check": check,
         }
     eng.close()

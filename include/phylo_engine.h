@@ -243,6 +243,11 @@ int phylo_lk_score_alignment(phylo_engine *e, int T, int64_t N, const void *mask
 /* Likelihood.root_cost / distance_1 (lib/nodeData.ml:29,32): lnL of joining the directed
  * CLVs a and b across an edge, for n_t candidate lengths (branch-length loop). */
 int phylo_lk_edge_lnl(phylo_engine *e, int a, int b, const double *t, int n_t, double *lnl_out);
+/* The same join for n_edges different edges (a_slots[i], b_slots[i]) of lengths t[i] in one call: one P(t)
+ * build, one synchronisation. With phylo_lk_uppass's directional CLVs this is the scoring loop of a
+ * neighbourhood search: one entry per candidate (lib/tree.ml:299-494). Values equal phylo_lk_edge_lnl's. */
+int phylo_lk_edge_lnl_batch(phylo_engine *e, int n_edges, const int32_t *a_slots, const int32_t *b_slots,
+                            const double *t, double *lnl_out);
 /* Branch-length loop on the edge (a, b) -- Likelihood.adjust_3 / readjust (lib/nodeData.ml:25,
  * lib/node.ml:239-256; TODO in lib/likelihood_c.ml:19-24). phylo_lk_edge_prepare builds the
  * edge's sum table (one CLV-sized array, eigen-space products of the two CLVs) once;

@@ -2558,6 +2558,39 @@ extern "C" int phylo_lk_edge_lnl(phylo_engine *e, int a_slot, int b_slot, const 
   return PHYLO_OK;
 }
 
+// lnL across many edges in one call: one P(t) build, one root join + fold per edge, results gathered in
+// pinned memory, ONE synchronisation -- the cost of an SPR / TBR candidate once the directional CLVs exist
+extern "C" int phylo_lk_edge_lnl_batch(phylo_engine *e, int n_edges, const int32_t *a_slots, const int32_t *b_slots,
+                                       const double *t, double *lnl_out) {
+  if (!e) return PHYLO_ERR_ARG;
+  if (e->T == 0) return fail(e, PHYLO_ERR_STATE, "lk_edge_lnl_batch: no tips loaded");
+  if (n_edges < 1 || !a_slots || !b_slots || !t || !lnl_out) return fail(e, PHYLO_ERR_ARG, "lk_edge_lnl_batch: bad arguments");
+  CK(cudaSetDevice(e->device));
+  int rc;
+  if ((rc = ensure_pt_capacity(e, n_edges, e->S, e->K)) != PHYLO_OK) return rc;
+  double *hres = nullptr;
+  CK(cudaMallocHost(&hres, sizeof(double) * n_edges));
+  CK(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n_edges; ++i) e->hT[i] = t[i];
+  rc = build_pt(e, n_edges);
+  const size_t pk = (size_t)e->K * e->S * e->S;
+  for (int i = 0; i < n_edges && rc == PHYLO_OK; ++i) {
+    Operand a, b;
+    if ((rc = lk_operand(e, a_slots[i], &a, "lk_edge_lnl_batch")) != PHYLO_OK) break;
+    if ((rc = lk_operand(e, b_slots[i], &b, "lk_edge_lnl_batch")) != PHYLO_OK) break;
+    rc = lk_root_eval(e, e->dP + (size_t)i * pk, a, b, hres + i);
+  }
+  const cudaError_t st = cudaStreamSynchronize(e->stream);
+  if (rc == PHYLO_OK && st == cudaSuccess)
+    for (int i = 0; i < n_edges; ++i) lnl_out[i] = hres[i];
+  cudaFreeHost(hres);
+  if (rc != PHYLO_OK) return rc;
+  if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "lk_edge_lnl_batch: %s", cudaGetErrorString(st));
+  e->lk_evaluated = true;
+  if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
+}
+
 // ---------------------------------------------------------- site-pattern compression ----
 template <int EB>
 static void launch_cmp_transpose(const uint8_t *in, uint8_t *rec, int T, int64_t N, int TP, cudaStream_t st) {

@@ -76,6 +76,7 @@ SIGNATURES = {
     "phylo_sankoff_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_sankoff_get_costs": (C.c_int, [_vp, C.c_int, _vp]),
     "phylo_lk_shape": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_i64), C.POINTER(C.c_int)]),
+    "phylo_lk_edge_lnl_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _dp, _dp]),
     "phylo_exchange_alloc": (C.c_int, [_vp, C.POINTER(_vp), _vp]),
     "phylo_exchange_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "phylo_exchange_set": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -575,6 +576,14 @@ class Engine:
         self._ck(self.lib.phylo_lk_optimize_branch(self.h, a, b, t0, t_min, t_max, tol, max_iter, C.byref(t),
                                                    C.byref(l), C.byref(it)))
         return t.value, l.value, it.value
+
+    def lk_edge_lnl_batch(self, a_slots, b_slots, ts):
+        a = np.ascontiguousarray(a_slots, dtype=np.int32)
+        b = np.ascontiguousarray(b_slots, dtype=np.int32)
+        ts = _f64(ts)
+        out = np.empty(len(a))
+        self._ck(self.lib.phylo_lk_edge_lnl_batch(self.h, len(a), _p(a), _p(b), _p(ts, _dp), _p(out, _dp)))
+        return out
 
     def lk_edge_lnl(self, a, b, ts):
         ts = _f64(np.atleast_1d(ts))

@@ -35,6 +35,9 @@ def test_every_edge_is_a_root_edge(eng, oracle, name, model, T, N):
         assert np.abs(clv - want["clv"][u]).max() <= 1e-12 * np.abs(want["clv"][u]).max()
         got = eng.lk_edge_lnl(v, u, [tv])[0]
         assert rel_err(got, lnl) <= 1e-11, (v, u, got, lnl)  # pulley principle
+    batch = eng.lk_edge_lnl_batch([e[0] for e in edges], [e[1] for e in edges], [e[2] for e in edges])
+    assert all(b == eng.lk_edge_lnl(v, u, [tv])[0] for b, (v, u, tv) in zip(batch[:5], edges[:5]))
+    assert np.max(np.abs(batch - lnl)) <= 1e-11 * abs(lnl)
     # oracle re-rooted on one interior edge: same schedule, root = that directional pair
     v, u, tv = next(e for e in edges if e[0] >= T)
     assert rel_err(oracle.lk_score_tree(model, tips, w, all_ops, cap, v, u, tv)["lnl"], lnl) <= 1e-11

@@ -22,6 +22,12 @@ def one(name, d):
     if d.get("branch_loop"):
         b = d["branch_loop"]
         print("         branch loop: total %.3g ms, eval %.3g ms, reprune %.3g ms" % (b["loop_total_ms"], b["lnl_d1_d2_eval_ms"], b["reprune_ms"]))
+    if d.get("roofline_tensor"):
+        t = d["roofline_tensor"]
+        print("         tensor roofline: %s useful %.3g TF (%.3f of the fp64 DMMA peak), issued %s" % (
+            t.get("kernel"), t.get("achieved") or -1, t.get("frac") or -1, t.get("issued_frac")))
+    if d.get("directions"):
+        print("         directions:", d["directions"])
     if d.get("group"):
         print("         group:", d["group"])
 
