@@ -1603,7 +1603,10 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
   } else {
     // slabs of whole 1024-pattern blocks: >= ~2 waves of tiles each, at most 16 slabs
     const int64_t blocks = e->nPart;
-    int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(16, blocks / 256));
+    // (64 blocks = 2048 warp-groups of 32 patterns, ~1.7 waves of the tree kernel; consecutive slabs run on two
+    // streams, so their tails overlap. A rank of an 8-GPU run holds 512 blocks: 8 slabs instead of the 2 that a
+    // 256-block minimum gave it -- with 2 slabs upload and scoring barely overlapped: e2e 6.2 ms for 3.2 ms of work)
+    int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(16, blocks / 64));
     if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
     if (!e->copyStream2) CK(cudaStreamCreateWithFlags(&e->copyStream2, cudaStreamNonBlocking));
     if (!e->auxStream) CK(cudaStreamCreateWithFlags(&e->auxStream, cudaStreamNonBlocking));

@@ -62,12 +62,12 @@ __global__ void __launch_bounds__(1024) exchange_kernel(const double *__restrict
     double *slot = peers.box[q] + (set + rank) * kXSlotDoubles;
     for (int i = tid; i < n_mine; i += blockDim.x) slot[2 + i] = mine[i];
   }
-  __threadfence_system();
+  // bar.sync makes the CTA's payload stores precede the publishing threads' release (cumulativity): one
+  // system-scope release per peer instead of a system fence in each of the 1024 threads
   __syncthreads();
   if (tid < world) {
     unsigned long long *slot = (unsigned long long *)(peers.box[tid] + (set + rank) * kXSlotDoubles);
     slot[1] = (unsigned long long)n_mine;
-    __threadfence_system();
     st_release_sys(slot, seq);
   }
   // (b) wait for every rank's slot of the own mailbox
@@ -77,12 +77,11 @@ __global__ void __launch_bounds__(1024) exchange_kernel(const double *__restrict
     const long long t0 = clock64();
     while (ld_acquire_sys(slot) != seq) {
       if (clock64() - t0 > kXTimeoutCycles) { timed_out = 1; break; }
-      __nanosleep(100);
+      __nanosleep(20);
     }
     cnt[tid + 1] = (int)ld_acquire_sys(slot + 1);
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // the acquiring threads' view reaches the rest of the CTA through the barrier
   if (timed_out) {
     if (tid == 0) {
       host_out[0] = 0.0;
