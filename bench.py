@@ -812,17 +812,20 @@ def run_workload(ctx, args, key, wl, primary):
     else:
         model = make_model(wl)
         base = tree_mod.evolve_tips(tr, model, BASE_PATTERNS, seed=3, dtype=mask_dtype(S))
-        packed_n = None
-        if S == 4 and args.upload == "compact" and lo % 2 == 0:
-            # compact upload format: two 4-bit masks per byte (mask_bytes = 0; phylo_pack_nibbles)
-            tips = engine.pinned_empty((T, (n_local + 1) // 2), np.uint8)
-            tile_cols(engine.pack_nibbles(base), lo // 2, tips.shape[1], out=tips)
-            packed_n = n_local
-            upload_note = "packed 4-bit masks, 0.5 B per cell (mask_bytes = 0)"
-        else:
-            tips = engine.pinned_empty((T, n_local), mask_dtype(S))
-            tile_cols(base, lo, n_local, out=tips)
-            upload_note = "%d-byte state masks" % tips.dtype.itemsize
+        packed_base = engine.pack_nibbles(base) if S == 4 and args.upload == "compact" else None
+
+        def host_shard(lo_, n_):
+            """this rank's slab of the host alignment in the upload format (pinned)"""
+            if packed_base is not None and lo_ % 2 == 0:
+                # compact upload format: two 4-bit masks per byte (mask_bytes = 0; phylo_pack_nibbles)
+                t = engine.pinned_empty((T, (n_ + 1) // 2), np.uint8)
+                tile_cols(packed_base, lo_ // 2, t.shape[1], out=t)
+                return t, n_, "packed 4-bit masks, 0.5 B per cell (mask_bytes = 0)"
+            t = engine.pinned_empty((T, n_), mask_dtype(S))
+            tile_cols(base, lo_, n_, out=t)
+            return t, None, "%d-byte state masks" % t.dtype.itemsize
+
+        tips, packed_n, upload_note = host_shard(lo, n_local)
         sample_of = lambda ns: tile_cols(base, lo, ns)
         eng.lk_set_model(model)
 
@@ -863,6 +866,41 @@ def run_workload(ctx, args, key, wl, primary):
 
     for _ in range(warmup):
         result = step()
+    # ---- N > 1, --balance (an experiment, off by default): slabs sized to each GPU's measured speed. The ranks
+    # meet at the scalar exchange of every step, so a step costs what the slowest GPU needs, and under the 1 kW
+    # power cap the GPUs of a box run at different clocks (1780-1920 MHz seen). Shares proportional to patterns /
+    # kernel-time of three more warm-up steps, still whole 1024-pattern blocks (lnL stays bit-identical: the
+    # canonical fold does not care where the cuts are). Result on 8 GPUs: no gain (3.45 vs 3.40 ms) -- which GPU
+    # is slow changes from one second to the next.
+    balance = None
+    if world > 1 and kind == "lk" and args.balance and n_total >= 1024 * 64 * world:
+        eng.profile(True, reset=True)
+        for _ in range(3):
+            step()
+        pr = eng.profile_get()
+        eng.profile(False)
+        t_mine = sum(v[0] for k, v in pr.items() if k not in ("reduce1024",)) / 3.0  # the exchange wait is not work
+        every = [None] * world
+        dist.all_gather_object(every, (n_local, t_mine))
+        speed = np.array([n / max(t, 1e-9) for n, t in every])
+        blocks_total = (n_total + 1023) // 1024
+        want = speed / speed.sum() * blocks_total
+        nb = np.maximum(1, np.floor(want).astype(np.int64))
+        for i in np.argsort(-(want - np.floor(want)))[: int(blocks_total - nb.sum())]:
+            nb[i] += 1
+        cuts = np.concatenate([[0], np.cumsum(nb)]) * 1024
+        cuts[-1] = n_total
+        new_lo, new_hi = int(cuts[rank]), int(cuts[rank + 1])
+        balance = {"patterns_per_rank_before": [int(n) for n, _ in every], "kernel_ms_per_rank_before": [float(t) for _, t in every],
+                   "patterns_per_rank": [int(cuts[i + 1] - cuts[i]) for i in range(world)]}
+        if (new_lo, new_hi) != (lo, hi):
+            engine.pinned_free(tips)
+            lo, hi, n_local = new_lo, new_hi, new_hi - new_lo
+            tips, packed_n, upload_note = host_shard(lo, n_local)
+            eng.lk_set_tips(tips, capacity=n_nodes, packed_n=packed_n)
+            h2d = tips.nbytes + ops.nbytes
+        for _ in range(2):
+            result = step()
     eng.profile(True, reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
     flush = needs_flush(mode)
@@ -1085,7 +1123,9 @@ def run_workload(ctx, args, key, wl, primary):
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": dict(workload_config(key, wl, n_total, n_local, world, l2_note, ctx.numa_note), upload_format=upload_note,
-                           **({"collective": xnote} if xnote else {})),
+                           **({"collective": xnote} if xnote else {}),
+                           **({"sharding": "contiguous 1024-aligned pattern slabs sized to each GPU's measured speed "
+                                           "(warm-up kernel times), one process per GPU", "balance": balance} if balance else {})),
             "mode": mode, "modes": modes,
             "roofline": (roof_tensor if roof_tensor and S > 32 else roof),
             "roofline_hbm": roof if roof_tensor and S > 32 else None,
@@ -1124,6 +1164,10 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="how the ranks' scalars meet (N > 1): on the device through peer-mapped mailboxes "
                          "(phylo_lk_exchange_reduce; default) or host -> NCCL all-reduce -> host")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: slabs proportional to each GPU's warm-up kernel speed instead of equal ones "
+                         "(measured on 8 B200s: 3.45 ms against 3.40 ms for equal slabs -- the GPUs' speeds wander "
+                         "under the power cap instead of differing persistently; off by default)")
     ap.add_argument("--no-group", action="store_true", help="skip the single-process phylo_group record (N > 1)")
     ap.add_argument("--fitch-kernel", default="auto", choices=["auto", "tile", "regwalk", "l2"],
                     help="whole-tree Fitch kernel (PHYLO_OPT_FITCH_WALK)")
