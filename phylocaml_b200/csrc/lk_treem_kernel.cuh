@@ -10,7 +10,8 @@
 // matrices are 15-32 KB per branch, so they must be shared by many pattern groups to be affordable):
 //   * a CTA owns a contiguous range of 8-pattern groups and walks it in chunks of NW * R groups
 //     (warp w carries groups w, w + NW, ... of the chunk, so a short last chunk still spreads over
-//     all warps); every chunk runs the whole program, one __syncthreads per step;
+//     all warps); every chunk runs the whole program; the warps are not barrier-synchronised per step (the
+//     last warp to finish with a table buffer refills it for the step after next);
 //   * the two DMMA A-fragment tables of a step (pt_frag_kernel lays P out as [k][mt][ks][lane]) arrive
 //     by bulk-TMA into a double buffer, requested one step ahead, completion on an mbarrier
 //     (SASS UBLKCP + SYNCS). They come out of L2: 3.9 MB for all branches of config 4;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = KT ? KT : a.K;
   uint64_t *bar = (uint64_t *)smem_raw;
-  unsigned long long *sptr = (unsigned long long *)(smem_raw + 16);  // [2][6] node-slot pointers of a step
+  unsigned int *done = (unsigned int *)(smem_raw + 16);  // [2]: warps that have finished with table buffer b
   double *pbuf = (double *)(smem_raw + 128);
   const int side = K * FRAG;  // doubles per side
   double *spi = pbuf + 4 * side;
@@ -171,8 +172,8 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
   for (int idx = tid; idx < NW * R * gsz; idx += NW * 32) curbase[idx] = 0.0;  // pad columns stay 0
   for (int i = tid; i < S; i += NW * 32) spi[i] = a.pi[i];
   // the six node-slot pointers a step may need (left / right / out CLV, then their scale arrays): fetched by
-  // lanes 0-5 of warp 0 one step ahead and handed over through shared memory, so no warp waits on the
-  // pointer tables (global memory) at the head of a step
+  // lanes 0-5 of every warp one step ahead and broadcast by shuffles at the head of the step, so no warp
+  // waits on the pointer tables (global memory) there
   auto slot_ptr = [&](const TreeMInstr &in) -> unsigned long long {
     const int which = lane % 3;
     const int idx = which == 0 ? in.lidx : (which == 1 ? in.ridx : in.out_slot);
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    done[0] = done[1] = 0;
     fence_mbar_init();
   }
   // the program is read three times per step (operands, next step's masks, next step's pointers): a copy
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
     for (int i = tid; i <= a.n_steps; i += NW * 32) sprog[i] = a.prog[i];
     prog = sprog;
   }
-  if (warp == 0 && lane < 6) sptr[lane] = slot_ptr(a.prog[0]);
+  unsigned long long cur_ptr = lane < 6 ? slot_ptr(a.prog[0]) : 0ull;
   __syncthreads();
 
   const int64_t ngroups = (a.N + 7) / 8;
@@ -212,7 +214,14 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
     bulk_g2s(pbuf + buf * 2 * side, src, side_bytes, &bar[buf]);
     if (!root) bulk_g2s(pbuf + buf * 2 * side + side, src + side, side_bytes, &bar[buf]);
   };
-  if (tid == 0 && total_it > 0) issue(0);
+  // The warps of a CTA are NOT barrier-synchronised per step: a warp only needs this step's tables (mbarrier)
+  // and its own data. A table buffer is refilled (for the step after next) by whichever warp is the LAST to
+  // finish with it, so a fast warp runs at most one step ahead of the slowest -- the per-step bar.sync of the
+  // first versions cost 10-20 % in warp-to-warp skew (node-slot reads, tensor-pipe contention).
+  if (tid == 0) {
+    if (total_it > 0) issue(0);
+    if (total_it > 1) issue(1);
+  }
 
   const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
   const MaskT *tips = (const MaskT *)a.tips;
@@ -246,15 +255,14 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
 
 #pragma unroll 1
     for (int s = 0; s < nst; ++s, ++it) {
-      if (tid == 0 && it + 1 < total_it) issue(it + 1);
       TreeMInstr nins = ins;
       MaskT nml = 0, nmr = 0;
       unsigned long long next_ptr = 0;
       if (s + 1 < nst) {
         nins = prog[s + 1];
         load_masks(nins, nml, nmr);
-        if (warp == 0 && lane < 6) next_ptr = slot_ptr(nins);
-      } else if (warp == 0 && lane < 6 && it + 1 < total_it) {
+        if (lane < 6) next_ptr = slot_ptr(nins);
+      } else if (lane < 6 && it + 1 < total_it) {
         next_ptr = slot_ptr(prog[0]);
       }
       if constexpr (TMA) {  // this step's output descriptor: in the descriptor cache by the time the stores are issued
@@ -263,11 +271,10 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
       }
       const int lk = ins.kinds & 3, rk = (ins.kinds >> 2) & 3;
       const long long t_begin = a.timing ? clock64() : 0;
-      const unsigned long long *sp = sptr + (it & 1) * 6;
-      const double *lg = (const double *)sp[0], *rg = (const double *)sp[1];
-      double *og = (double *)sp[2];
-      const int32_t *lgs = (const int32_t *)sp[3], *rgs = (const int32_t *)sp[4];
-      int32_t *ogs = (int32_t *)sp[5];
+      const double *lg = (const double *)__shfl_sync(FULL, cur_ptr, 0), *rg = (const double *)__shfl_sync(FULL, cur_ptr, 1);
+      double *og = (double *)__shfl_sync(FULL, cur_ptr, 2);
+      const int32_t *lgs = (const int32_t *)__shfl_sync(FULL, cur_ptr, 3), *rgs = (const int32_t *)__shfl_sync(FULL, cur_ptr, 4);
+      int32_t *ogs = (int32_t *)__shfl_sync(FULL, cur_ptr, 5);
       const unsigned lhotbits = __ballot_sync(FULL, (ml & (ml - 1)) == 0);
       const unsigned rhotbits = __ballot_sync(FULL, (mr & (mr - 1)) == 0);
       const int buf = (int)(it & 1);
@@ -649,9 +656,20 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
       ins = nins;
       ml = nml & keep;
       mr = nmr & keep;
-      if (warp == 0 && lane < 6) sptr[((it + 1) & 1) * 6 + lane] = next_ptr;
+      cur_ptr = next_ptr;
       const long long t_body = a.timing ? clock64() : 0;
-      __syncthreads();  // every warp is done with this step's tables (and its global writes are visible CTA-wide)
+      // done with this step's tables: the last warp to say so refills the buffer for the step after next
+      // (release / acquire at CTA scope around the counter: every warp's table reads precede the refill.
+      // compute-sanitizer's racecheck models barriers only and reports this hand-over as a potential WAR.)
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&done[buf], 1u) == (unsigned)NW - 1u) {
+          __threadfence_block();
+          done[buf] = 0;
+          if (it + 2 < total_it) issue(it + 2);
+        }
+      }
       if (a.timing && tid == 0) {
         const int kk = lk | (rk << 2);
         const int v = s == a.n_steps ? 5 : (kk == 0 ? 0 : kk == (TM_CUR << 2) ? 1 : kk == (TM_GLB << 2) ? 2 : kk == (TM_CUR | (TM_GLB << 2)) ? 3 : 4);
