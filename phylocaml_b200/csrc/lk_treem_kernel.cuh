@@ -6,35 +6,45 @@
 // shared memory and only WRITES each interior CLV once (C + 4 bytes per update, 40.6 GB): the
 // value a median needs next is, two times out of three, the one the warp has just produced.
 //
-// Organisation (CTA-synchronous, unlike the warp-autonomous 4-state kernel: here the transition
-// matrices are 15-32 KB per branch, so they must be shared by many pattern groups to be affordable):
-//   * a CTA owns a contiguous range of 8-pattern groups and walks it in chunks of NW * R groups
+// Organisation (unlike the warp-autonomous 4-state kernel the transition matrices are 15-32 KB per
+// branch here, so a step's tables must be shared by many pattern groups to be affordable):
+//   * one CTA per SM owns a contiguous range of 8-pattern groups and walks it in chunks of NW * R groups
 //     (warp w carries groups w, w + NW, ... of the chunk, so a short last chunk still spreads over
-//     all warps); every chunk runs the whole program; the warps are not barrier-synchronised per step (the
-//     last warp to finish with a table buffer refills it for the step after next);
+//     all warps); every chunk runs the whole program;
 //   * the two DMMA A-fragment tables of a step (pt_frag_kernel lays P out as [k][mt][ks][lane]) arrive
-//     by bulk-TMA into a double buffer, requested one step ahead, completion on an mbarrier
-//     (SASS UBLKCP + SYNCS). They come out of L2: 3.9 MB for all branches of config 4;
-//   * 20 states: the 15 A fragments of a (side, rate class) are loaded into registers ONCE per step
-//     and reused for the warp's R groups -- the per-node kernel re-reads them from shared memory for
-//     every group, which is what kept its LSU 77 % busy next to a 58 % tensor pipe;
+//     by bulk-TMA into a double buffer, completion on an mbarrier (SASS UBLKCP + SYNCS). They come out
+//     of L2: 3.9 MB for all branches of config 4. There is NO per-step CTA barrier: a warp needs only the
+//     step's tables and its own data; the LAST warp to finish with a buffer (shared-memory counter) refills
+//     it for the step after next, so a fast warp runs at most one step ahead of the slowest (the bar.sync
+//     of the first versions cost 10-20 % in warp-to-warp skew);
 //   * the DMMA chains of a group (row tiles x two sides) are independent accumulators advanced
-//     together k-step by k-step: with 2 warps per scheduler the dependent-issue latency of a chain
-//     would otherwise be the limiter (first version: 32 % of all stall samples on DMMA -> DMMA waits);
+//     together k-step by k-step (non-volatile asm): dependent-issue latency of DMMA is 26 cycles,
+//     4 warps x 2 chains saturate the pipe (tools/ubench/dmma_lat.cu);
 //   * operand kinds are compile-time inside the step body (the host orders every median so that
 //     kind(left) <= kind(right): tip < running value < node slot; x * y is commutative bit for bit):
-//     TIP = state masks (one coalesced load per warp and step, prefetched a step ahead; all-observed
-//     groups take column j of P straight from the A table, no DMMA, bit-identical), CUR = the warp's
-//     own previous result in shared memory ([k][pattern][PITCH], PITCH = 4 mod 16 doubles:
-//     conflict-free B-fragment reads), GLB = a retained CLV read back from its node slot (written a
-//     few steps earlier by this same warp: an L2 hit). There is no separate stack: every result is
-//     retained in its node slot anyway, so "pop" is "read the slot";
-//   * results leave in C-fragment layout exactly as in prune_mma_kernel (128-bit stores for 20
-//     states), per-site rescaling by the same rule (site maximum over all K * S entries < 2^-256
-//     => times 2^256, counter + 1), scale counters of the running value live in registers;
+//     TIP = state masks (one coalesced load per warp and step, prefetched a step ahead). 20 states: the
+//     tip side's table is the TRANSPOSE of P plus a row of row sums; an observed state (or a missing
+//     cell) is one row, read with one LDS.128 + one LDS.64 per pattern -- no DMMA; a partial ambiguity
+//     code (rare, per lane) adds its columns in ascending j, the oracle's own order. 61 states: all-
+//     observed groups take column j straight from the A table, others build B fragments from the mask.
+//     CUR = the warp's own previous result in shared memory ([k][pattern][PITCH], PITCH = 4 mod 16
+//     doubles: conflict-free B-fragment reads). GLB = a retained CLV read back from its node slot
+//     (written a few steps earlier by this same warp: an L2 hit). There is no separate stack: every
+//     result is retained in its node slot anyway, so "pop" is "read the slot";
+//   * results: group-outer loops -- a group's CLV is complete after its K rate classes; 20 states: it
+//     leaves at once through ONE cp.async.bulk.tensor.3d (3-D tensor map (S, N, K) per node slot, box
+//     (S, 8, K) = the buffer's [k][pattern][S] order; rows >= N clipped), so the drain to HBM overlaps the
+//     next group's arithmetic (wait_group.read R - 1 before the buffer is rewritten, wait_group R before
+//     a slot written by TMA is read back); 61 states (488-byte rows: no 16-byte strides) store from the
+//     C fragments like prune_mma_kernel. Per-site rescaling by the same rule (site maximum over all
+//     K * S entries < 2^-256 => times 2^256, counter + 1), scale counters of the running value in registers;
 //   * the root-edge join is the program's last step: site lnL (and weight * lnL) go to global
 //     memory, the canonical 1024-fold runs over them afterwards (reduce1024_kernel) -- the sum does
 //     not depend on how the patterns were cut into groups, CTAs or devices.
+// Geometry: 20 states 16 warps x 2 groups (126 registers, A fragments straight from shared memory -- holding
+// them in registers with 8 warps x 4 groups was latency-bound at 2 warps per scheduler), 61 states 8 warps x
+// 2 groups (the 16 k-steps of B fragments want ~250 registers). profiles/README.md has the measurements
+// behind each of these choices (v1 32 ms -> v8 14.2 ms for config 4).
 //
 // DMMA chains: the k-steps of a row tile are accumulated in ascending order from zero, contraction
 // index j = 4 ks + fc (prune_mma_kernel uses a different j <-> slot map for 20 states, so CLVs agree
