@@ -138,6 +138,13 @@ __device__ __forceinline__ MaskT shfl_mask(MaskT v, int src) {
   if constexpr (sizeof(MaskT) == 8) return (MaskT)__shfl_sync(0xffffffffu, (unsigned long long)v, src);
   else return (MaskT)__shfl_sync(0xffffffffu, (unsigned)v, src);
 }
+// the same with a 32-bit shared-window address (one cvta per kernel instead of one per access)
+__device__ __forceinline__ void sts128_s(uint32_t addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void lds128_s(uint32_t addr, double &a, double &b) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
 __device__ __forceinline__ void sts128(double *p, double a, double b) {
   asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(smem_u32(p)), "d"(a), "d"(b) : "memory");
 }
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
   const MaskT keep = (S >= 64) ? ~(MaskT)0 : (MaskT)(((uint64_t)1 << S) - 1);
   const MaskT *tips = (const MaskT *)a.tips;
   double *cur = curbase + warp * R * gsz;  // [r][k][8][PITCH]
+  const uint32_t cur_s = smem_u32(cur), pbuf_s = smem_u32(pbuf);
   const double kLnScale = kScaleExp * 0.6931471805599453094;
   uint64_t it = 0;
   for (int64_t chunk = 0; chunk < nchunks; ++chunk) {
@@ -401,8 +409,9 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
                     auto tip_side = [&](const double *pt, unsigned mk0, unsigned mk1, double (&c)[MTB][2]) {
                       const int j0 = tip_row(mk0), j1 = tip_row(mk1);
                       if (j0 >= 0 && j1 >= 0) {
-                        lds128(pt + j0 * S + 2 * fr, c[0][0], c[1][0]);
-                        lds128(pt + j1 * S + 2 * fr, c[0][1], c[1][1]);
+                        const uint32_t pt_s = pbuf_s + (uint32_t)(pt - pbuf) * 8u;
+                        lds128_s(pt_s + (uint32_t)(j0 * S + 2 * fr) * 8u, c[0][0], c[1][0]);
+                        lds128_s(pt_s + (uint32_t)(j1 * S + 2 * fr) * 8u, c[0][1], c[1][1]);
                         c[2][0] = pt[j0 * S + 16 + fr];
                         c[2][1] = pt[j1 * S + 16 + fr];
                       } else {
@@ -464,8 +473,9 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
                     const double a0 = cx[0][0] * cy[0][0], a1 = cx[0][1] * cy[0][1];
                     const double b0 = cx[1][0] * cy[1][0], b1 = cx[1][1] * cy[1][1];
                     const double d0 = cx[2][0] * cy[2][0], d1 = cx[2][1] * cy[2][1];
-                    sts128(c0 + 2 * fr, a0, b0);
-                    sts128(c1 + 2 * fr, a1, b1);
+                    const uint32_t c0_s = cur_s + (uint32_t)(r * gsz + (k * 8 + 2 * fc) * PITCH + 2 * fr) * 8u;
+                    sts128_s(c0_s, a0, b0);
+                    sts128_s(c0_s + PITCH * 8u, a1, b1);
                     h0 = max(h0, max(hi32(a0), hi32(b0)));
                     h1 = max(h1, max(hi32(a1), hi32(b1)));
                     if (fr < 4) {
