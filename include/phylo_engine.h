@@ -83,11 +83,11 @@ int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256);
  * re-scoring); 0 = lnL only, the tree-fused kernel then writes no CLV at all. */
 #define PHYLO_OPT_FUSED_TREE 1
 #define PHYLO_OPT_RETAIN_CLV 2
-/* PHYLO_OPT_FITCH_WALK selects the whole-tree Fitch kernel: 1 (default) = automatic (below
- * ~8 M characters the on-chip tile kernel for 4 planes / the register walk for up to 8 planes,
- * which are latency-optimised; the bandwidth-optimised L2 walk above); 3 = on-chip tile kernel
- * (4 planes: level-parallel medians out of shared memory, results published by the last CTA);
- * 2 = register walk (compiled depth-first plan, tips prefetched several medians ahead, up to
+/* PHYLO_OPT_FITCH_WALK selects the whole-tree Fitch kernel: 1 (default) = automatic (4 planes:
+ * the on-chip tile kernel at every size; up to 8 planes below ~8 M characters: the register walk;
+ * otherwise the L2 walk); 3 = on-chip tile kernel (4 planes: subtrees dealt to the warps of a CTA,
+ * medians out of shared memory with the running set in registers, results published by the last
+ * CTA); 2 = register walk (compiled depth-first plan, tips prefetched several medians ahead, up to
  * 8 planes); 0 = L2 walk (re-reads its own earlier writes through L2, any plane count). */
 #define PHYLO_OPT_FITCH_WALK 3
 /* PHYLO_OPT_DEFER_SCALAR (default 0): 1 = phylo_lk_score_tree leaves the evaluation's level-1 block partials

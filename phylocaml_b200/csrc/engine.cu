@@ -62,6 +62,18 @@ static const char *kClassNames[KC_COUNT] = {
     "pt_build", "tree_fused", "prune_inner_inner", "prune_tip_inner", "prune_tip_tip", "root_lnl", "reduce1024",
     "tips_prepare", "fitch_tree", "fitch_median2", "fitch_uppass", "fitch_transcode", "bv_setops", "edge_loop", "compress"};
 
+// compiled program of the last tile-kernel call (fitch_tile_compile) and what it depends on
+struct FitchTileCache {
+  bool valid = false, weighted = false;
+  std::vector<phylo_op> ops;
+  int root_a = -1, root_b = -1;
+  std::vector<int> pos;                  // schedule op -> position in the program (= index of its cost)
+  std::vector<int> slots;                // every node slot the program reads or writes ...
+  std::vector<const uint32_t *> ptrs;    // ... and the buffer it had when the program was compiled
+  size_t smem = 0;
+  FitchTileArgs a;
+};
+
 struct phylo_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -90,6 +102,9 @@ struct phylo_engine {
   uint32_t *dTcm = nullptr;            // general-TCM median table: 2^S x 2^S entries (cost | median << 16)
   int tcmS = 0;
   size_t capAcc = 0, tileSmem = 0;
+  FitchTileCache tileCache;                // compiled tile-kernel program of the last fitch_score_tree call
+  unsigned long long *hCostDev = nullptr;  // device view of the mapped hCost
+  unsigned long long *dStamps = nullptr;   // PHYLO_FITCH_TIMING=1 only
   unsigned long long tileSeq = 0, treeSeq = 0;
   unsigned int *dTreeDone = nullptr;  // CTA counter of the fused final fold (zero between calls)
   bool fused_result_ready = false;    // the last fused evaluation already left lnL in hScalar[0]
@@ -387,7 +402,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   dfree(e->dP); dfree(e->dFrag); dfree(e->dT);
   for (void *p : e->xOpened) cudaIpcCloseMemHandle(p);
   dfree(e->xMailbox);
-  dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
+  dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dStamps); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -3005,6 +3020,7 @@ static int fitch_cost_capacity(phylo_engine *e, size_t n) {
   CK(cudaStreamSynchronize(e->stream));
   dfree(e->dCost);
   if (e->hCost) { cudaFreeHost(e->hCost); e->hCost = nullptr; }
+  e->hCostDev = nullptr;
   e->capCost = 0;
   CK(cudaMalloc(&e->dCost, sizeof(unsigned long long) * n));
   CK(cudaMallocHost(&e->hCost, sizeof(unsigned long long) * n));
@@ -3369,18 +3385,55 @@ static int fitch_check_schedule(phylo_engine *e, const phylo_op *ops, int n_ops,
   return PHYLO_OK;
 }
 
-// Characters per tree evaluation below which the on-chip tile kernel is used in auto mode
-// (measured cross-over with the register walk, profiles/README.md).
+// Words (32 characters) per tree evaluation below which the latency-optimised register walk is used for
+// 5..8 planes in auto mode, and below which the host spins on the tile kernel's mapped results instead of
+// blocking in a stream sync. 4 planes: the tile kernel at every size (profiles/README.md: it also beats the
+// L2 walk at 16 M and 64 M characters).
 static const int64_t kFitchTileMaxWords = 1 << 18;
+static const int64_t kFitchSpinMaxWords = 1 << 18;
 
-// On-chip tile kernel (fitch_tile_kernel): level-sorted program, results straight into mapped
-// host memory. Returns PHYLO_OK with *done = false when the schedule does not fit.
-static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
-                                 uint64_t *length_out, bool *done) {
-  *done = false;
+// measurement only: PHYLO_FITCH_TIMING=1 makes the tile / warp-tile kernels leave %globaltimer stamps per CTA;
+// the call prints where the time of the LAST call went (host and device clocks are separate: durations only).
+static bool fitch_timing_on() {
+  static const bool on = [] { const char *v = getenv("PHYLO_FITCH_TIMING"); return v && v[0] == '1'; }();
+  return on;
+}
+static void fitch_timing_report(phylo_engine *e, unsigned long long *dStamps, int grid, const char *who, double host_plan_us,
+                                double host_launch_us, double host_wait_us) {
+  cudaStreamSynchronize(e->stream);
+  std::vector<unsigned long long> h((size_t)grid * 8);
+  cudaMemcpy(h.data(), dStamps, h.size() * 8, cudaMemcpyDeviceToHost);
+  unsigned long long t0 = ~0ull;
+  for (int b = 0; b < grid; ++b) t0 = std::min(t0, h[(size_t)b * 8]);
+  static int calls = 0;
+  if ((++calls % 8) != 0) return;
+  fprintf(stderr, "[fitch timing %s] grid %d host: plan %.1f us, launch call %.1f us, wait %.1f us | device (us after first CTA start; min..max over CTAs):",
+          who, grid, host_plan_us, host_launch_us, host_wait_us);
+  const char *names[8] = {"start", "inputs", "phase1/steps", "phase2", "tiles done", "fold", "counter", "published"};
+  for (int i = 0; i < 8; ++i) {
+    unsigned long long lo = ~0ull, hi = 0;
+    for (int b = 0; b < grid; ++b) {
+      const unsigned long long t = h[(size_t)b * 8 + i];
+      if (t == 0) continue;
+      lo = std::min(lo, t); hi = std::max(hi, t);
+    }
+    if (hi) fprintf(stderr, " %s %.1f..%.1f", names[i], (lo - t0) / 1e3, (hi - t0) / 1e3);
+  }
+  fprintf(stderr, "\n");
+}
+
+// On-chip tile kernel (fitch_tile_kernel): per-warp subtree lists + the medians above the cut,
+// results straight into mapped host memory. Returns PHYLO_OK with *done = false when the
+// schedule does not fit. The compiled program of the last call is kept: scoring the same
+// schedule again (another character set on the same tree, new weights, a benchmark loop) skips
+// the compilation after a memcmp of the ops and a check of every buffer pointer it refers to.
+static int fitch_tile_compile(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, bool *ok) {
+  *ok = false;
+  FitchTileCache &tc = e->tileCache;
+  tc.valid = false;
   const int n_tot = n_ops + 1;  // + root-edge join
   // operands: >= 0 = index into the tile's input rows; < 0 = -1 - (op that produces it)
-  std::vector<int> produced(e->fcap, -1), in_index(e->fcap, -1), inputs;
+  std::vector<int> produced(e->fcap, -1), inputs;
   struct Raw { int l, r, out_slot; };
   std::vector<Raw> raw(n_tot);
   auto operand = [&](int slot) {  // every use of a resident set gets its own table row (results overwrite rows)
@@ -3425,16 +3478,27 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     load[w] += size[t];
   }
   // program order: phase-1 ops of warp 0, 1, ... (each in schedule order), then phase 2
-  std::vector<int> order, pos(n_tot), tstart(kFitchTileWarps + 2, 0);
+  std::vector<int> order, tstart(kFitchTileWarps + 2, 0);
+  tc.pos.assign(n_tot, 0);
   order.reserve(n_tot);
   for (int w = 0; w <= kFitchTileWarps; ++w) {
     tstart[w] = (int)order.size();
     for (int o = 0; o < n_tot; ++o) {
       const bool mine = w < kFitchTileWarps ? (task_of[o] >= 0 && warp_of_task[task_of[o]] == w) : task_of[o] < 0;
-      if (mine) { pos[o] = (int)order.size(); order.push_back(o); }
+      if (mine) { tc.pos[o] = (int)order.size(); order.push_back(o); }
     }
   }
   tstart[kFitchTileWarps + 1] = (int)order.size();
+  // An operand produced by the median the same warp evaluated just before stays in registers: it
+  // becomes the left operand (the rule is symmetric) and is flagged in bit 0 of l_off.
+  std::vector<char> from_regs(n_tot, 0);
+  for (int w = 0; w <= kFitchTileWarps; ++w)
+    for (int i = tstart[w] + 1; i < tstart[w + 1]; ++i) {
+      Raw &rw = raw[order[i]];
+      const int prev = -1 - order[i - 1];
+      if (rw.r == prev) std::swap(rw.l, rw.r);
+      if (rw.l == prev) from_regs[order[i]] = 1;
+    }
   int rc;
   const size_t blob = sizeof(FitchTileOp) * n_tot + 8 * (size_t)n_in + 4 * (size_t)(kFitchTileWarps + 2) + 64;
   if ((rc = fitch_sched_capacity(e, blob)) != PHYLO_OK) return rc;
@@ -3443,13 +3507,13 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     CK(cudaStreamSynchronize(e->stream));
     dfree(e->dAcc);
     e->capAcc = 0;
-    const size_t cap = ((size_t)n_tot + 2) * 2;
-    CK(cudaMalloc(&e->dAcc, sizeof(unsigned long long) * cap * kFitchAccCopies));
-    CK(cudaMemsetAsync(e->dAcc, 0, sizeof(unsigned long long) * cap * kFitchAccCopies, e->stream));
-    e->capAcc = cap;
+    const size_t cap2 = ((size_t)n_tot + 2) * 2;
+    CK(cudaMalloc(&e->dAcc, sizeof(unsigned long long) * cap2 * kFitchAccCopies));
+    CK(cudaMemsetAsync(e->dAcc, 0, sizeof(unsigned long long) * cap2 * kFitchAccCopies, e->stream));
+    e->capAcc = cap2;
   }
   const bool inl = blob - 64 <= (size_t)kFitchInlineProg;
-  FitchTileArgs a;
+  FitchTileArgs &a = tc.a;
   if (!inl) CK(cudaStreamSynchronize(e->stream));  // pinned staging is about to be rewritten
   char *hb = inl ? (char *)a.prog : (char *)e->hSched;
   FitchTileOp *hops = (FitchTileOp *)hb;
@@ -3458,19 +3522,21 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   std::vector<int> res_row(n_tot, -1);  // table row holding op o's result (schedule order: producers first)
   auto row_of = [&](int c) { return c >= 0 ? c : res_row[-1 - c]; };
   for (int o = 0; o < n_tot; ++o) res_row[o] = row_of(raw[o].l);
+  tc.slots.clear();
+  tc.ptrs.clear();
+  auto remember = [&](int slot) { tc.slots.push_back(slot); tc.ptrs.push_back(e->fPre[slot]); };
   for (int i = 0; i < n_tot; ++i) {
     const Raw &rw = raw[order[i]];
     // rows: an input use has its own row; a result lives in the row of its producer's left operand
-    hops[i].l_off = 512u * (uint32_t)row_of(rw.l);
+    hops[i].l_off = 512u * (uint32_t)row_of(rw.l) | (from_regs[order[i]] ? 1u : 0u);
     hops[i].r_off = 512u * (uint32_t)row_of(rw.r);
     hops[i].out = rw.out_slot >= 0 ? e->fPre[rw.out_slot] : nullptr;
+    if (rw.out_slot >= 0) remember(rw.out_slot);
   }
-  for (int i = 0; i < n_in; ++i) hin[i] = e->fPre[inputs[i]];
+  for (int i = 0; i < n_in; ++i) { hin[i] = e->fPre[inputs[i]]; remember(inputs[i]); }
   for (int w = 0; w < kFitchTileWarps + 2; ++w) hlev[w] = tstart[w];
   if (!inl) CK(cudaMemcpyAsync(e->dSched, hb, blob - 64, cudaMemcpyHostToDevice, e->stream));
   a.inline_prog = inl;
-  a.seq = ++e->tileSeq;
-  e->hCost[n_tot + 1] = ~0ull;  // the slot the last CTA overwrites with a.seq
   char *db = (char *)e->dSched;
   a.ops = (const FitchTileOp *)db;
   a.in_ptr = (const uint32_t *const *)(db + sizeof(FitchTileOp) * n_tot);
@@ -3478,7 +3544,61 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   a.n_in = n_in; a.n_ops = n_tot;
   a.nwords = e->fWords; a.N = e->fN; a.wt = e->dFW;
   a.acc = e->dAcc;
-  CK(cudaHostGetDevicePointer((void **)&a.host_out, e->hCost, 0));
+  if (!e->hCostDev) CK(cudaHostGetDevicePointer((void **)&e->hCostDev, e->hCost, 0));
+  a.host_out = e->hCostDev;
+  a.stamps = nullptr;
+  tc.smem = smem;
+  tc.weighted = weighted;
+  tc.ops.assign(ops, ops + n_ops);
+  tc.root_a = root_a; tc.root_b = root_b;
+  tc.valid = inl;  // a program staged through dSched is overwritten by other calls: compiled again next time
+  *ok = true;
+  return PHYLO_OK;
+}
+
+static bool fitch_tile_cache_hit(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b) {
+  const FitchTileCache &tc = e->tileCache;
+  if (!tc.valid || (int)tc.ops.size() != n_ops || tc.root_a != root_a || tc.root_b != root_b) return false;
+  if (tc.a.nwords != e->fWords || tc.a.N != e->fN || tc.a.wt != e->dFW || tc.a.acc != e->dAcc || tc.a.host_out != e->hCostDev ||
+      e->hCostDev == nullptr)
+    return false;
+  for (int o = 0; o < n_ops; ++o)  // field by field: the struct has padding
+    if (ops[o].parent != tc.ops[o].parent || ops[o].left != tc.ops[o].left || ops[o].right != tc.ops[o].right) return false;
+  for (size_t i = 0; i < tc.slots.size(); ++i)
+    if (e->fPre[tc.slots[i]] != tc.ptrs[i]) return false;
+  return true;
+}
+
+static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+                                 uint64_t *length_out, bool *done) {
+  *done = false;
+  const auto ht0 = std::chrono::steady_clock::now();
+  auto ht1 = ht0, ht2 = ht0;
+  int grid_used = 0, rc;
+  if (!fitch_tile_cache_hit(e, ops, n_ops, root_a, root_b)) {
+    bool ok = false;
+    if ((rc = fitch_tile_compile(e, ops, n_ops, root_a, root_b, &ok)) != PHYLO_OK) return rc;
+    if (!ok) return PHYLO_OK;
+  }
+  FitchTileCache &tc = e->tileCache;
+  FitchTileArgs &a = tc.a;
+  const int n_tot = n_ops + 1;
+  const bool weighted = tc.weighted;
+  const size_t smem = tc.smem;
+  // unweighted costs fit 48 bits: every published word carries the call's 16-bit tag, the host waits for the
+  // tags (no ordering between words needed); weighted costs may need 64 bits: results, fence, sequence number
+  a.seq = ++e->tileSeq;
+  a.tag = weighted ? 0ull : (((a.seq & 0x7fffull) | 0x8000ull) << 48);
+  if (a.tag) for (int i = 0; i < n_tot; ++i) e->hCost[i] = 0;
+  e->hCost[n_tot + 1] = ~0ull;  // untagged protocol: the slot the last CTA overwrites with a.seq
+  a.stamps = nullptr;
+  if (fitch_timing_on()) {
+    if (!e->dStamps) CK(cudaMalloc(&e->dStamps, 8 * 8 * 8192));
+    CK(cudaMemsetAsync(e->dStamps, 0, 8 * 8 * 8192, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    a.stamps = e->dStamps;
+  }
+  ht1 = std::chrono::steady_clock::now();
   {
     ProfScope prof(e, KC_FITCH_TREE);
     auto kern = weighted ? fitch_tile_kernel<unsigned long long> : fitch_tile_kernel<uint16_t>;
@@ -3497,27 +3617,44 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     if (!weighted && waves > 2000) return PHYLO_OK;  // 16-bit per-lane counters: the other kernels take it
     kern<<<g, 256, smem, e->stream>>>(a);
     LAUNCH_CHECK();
+    grid_used = g;
+    ht2 = std::chrono::steady_clock::now();
   }
-  // small alignments: spin on the sequence number the last CTA writes after the results (a
-  // blocking stream sync costs more than the kernel); otherwise, or after 2 ms, a stream sync
+  // small alignments: spin on what the last CTA writes into mapped host memory (a blocking stream
+  // sync costs more than the kernel); otherwise, or after 2 ms, a stream sync
   {
-    volatile unsigned long long *flag = (volatile unsigned long long *)&e->hCost[n_tot + 1];
+    volatile unsigned long long *hc = (volatile unsigned long long *)e->hCost;
+    const unsigned long long want = a.tag >> 48;
+    auto published = [&]() {
+      if (!a.tag) return hc[n_tot + 1] == a.seq;
+      for (int i = 0; i < n_tot; ++i)
+        if ((hc[i] >> 48) != want) return false;
+      return true;
+    };
     bool seen = false;
-    if (e->fWords <= kFitchTileMaxWords) {
+    if (e->fWords <= kFitchSpinMaxWords) {
       const auto t0 = std::chrono::steady_clock::now();
       for (int spin = 0;; ++spin) {
-        if (*flag == a.seq) { seen = true; break; }
+        if (published()) { seen = true; break; }
         if ((spin & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
       }
     }
     if (!seen) {
       CK(cudaStreamSynchronize(e->stream));
-      if (*flag != a.seq) return fail(e, PHYLO_ERR_CUDA, "fitch_score_tree: the tile kernel did not publish its result");
+      if (!published()) return fail(e, PHYLO_ERR_CUDA, "fitch_score_tree: the tile kernel did not publish its result");
     }
     std::atomic_thread_fence(std::memory_order_acquire);
   }
-  *length_out = e->hCost[n_tot];
-  for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = e->hCost[pos[o]]; e->fValid[ops[o].parent] = 1; e->fFinValid[ops[o].parent] = 0; }
+  const unsigned long long mask = a.tag ? 0x0000ffffffffffffull : ~0ull;
+  uint64_t length = 0;
+  for (int i = 0; i < n_tot; ++i) length += e->hCost[i] & mask;
+  *length_out = length;
+  for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = e->hCost[tc.pos[o]] & mask; e->fValid[ops[o].parent] = 1; e->fFinValid[ops[o].parent] = 0; }
+  if (a.stamps) {
+    const auto ht3 = std::chrono::steady_clock::now();
+    auto us = [](auto x, auto y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
+    fitch_timing_report(e, e->dStamps, std::min(grid_used, 8192), "tile", us(ht0, ht1), us(ht1, ht2), us(ht2, ht3));
+  }
   if (e->prof_on) prof_resolve_lazy(e);
   *done = true;
   return PHYLO_OK;
@@ -3532,7 +3669,7 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
   CK(cudaSetDevice(e->device));
   for (int o = 0; o < n_ops; ++o)
     if ((rc = fitch_ensure(e, ops[o].parent, false)) != PHYLO_OK) return rc;
-  if (e->fNPdev == 4 && (e->opt_fitch_walk == 3 || (e->opt_fitch_walk == 1 && e->fWords <= kFitchTileMaxWords))) {
+  if (e->fNPdev == 4 && (e->opt_fitch_walk == 3 || e->opt_fitch_walk == 1)) {
     bool done = false;
     if ((rc = fitch_score_tree_tile(e, ops, n_ops, root_a, root_b, length_out, &done)) != PHYLO_OK) return rc;
     if (done) return PHYLO_OK;

@@ -81,6 +81,15 @@ __device__ __forceinline__ void block_add_u64(unsigned long long v, unsigned lon
   if (threadIdx.x == 0 && acc) atomicAdd(dst, acc);
 }
 
+// measurement only (PHYLO_FITCH_TIMING=1): thread 0 of every CTA leaves %globaltimer stamps
+__device__ __forceinline__ void fitch_stamp(unsigned long long *stamps, int i) {
+  if (stamps != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    stamps[(size_t)blockIdx.x * 8 + i] = t;
+  }
+}
+
 // ------------------------------------------------------- per-node median / distance ----
 // STORE=true: bv_fitch (writes the parent set); STORE=false: bv_distance
 // (lib/bitvector/bv.c:46-55). One thread per 32-character word, grid-strided.
@@ -305,42 +314,51 @@ fitch_treep_kernel(const FitchInstr *__restrict__ prog, int n_steps, int depth, 
 }
 
 // ----------------------------------------------- whole-tree down-pass, on-chip tiles ----
-// Latency-optimised variant for 4 state planes (DNA) and alignments too small to hide a
-// 60-deep dependent walk behind other warps (BASELINE config 2: 1 M characters = 31 k
-// columns). A CTA owns a tile of 32 columns; ALL input sets of the tile (tips and sets
-// already resident) are fetched at once with cp.async (n_in independent 512-byte rows in
-// flight per CTA), then the medians are evaluated out of shared memory in two phases: the
-// host cuts the tree into whole subtrees of at most ~n/8 medians, deals them to the 8 warps
-// (phase 1; a lane only ever touches its own column, so a warp runs its list without any
-// synchronisation), and the few medians above the cut run on warp 0 after ONE __syncthreads
-// (phase 2). (A first version synchronised once per tree level: 27 barriers for the bench
-// tree, 12 k cycles per tile.) Results go to shared memory (for the parent) and to HBM (once).
-// The last CTA to finish publishes the per-op costs and the length straight into mapped
-// host memory and re-zeroes the accumulators: one kernel launch is the whole call.
+// The whole-tree kernel for 4 state planes (DNA). A CTA owns a tile of 32 columns; ALL input
+// sets of the tile (tips and sets already resident) are fetched at once with cp.async (n_in
+// independent 512-byte rows in flight per CTA), then the medians are evaluated out of shared
+// memory in two phases: the host cuts the tree into whole subtrees of at most ~n/8 medians,
+// deals them to the 8 warps (phase 1; a lane only ever touches its own column, so a warp runs
+// its list without any synchronisation), and the few medians above the cut run on warp 0 after
+// ONE __syncthreads (phase 2). (A first version synchronised once per tree level: 27 barriers
+// for the bench tree, 12 k cycles per tile.) Results go to shared memory (for the parent) and to
+// HBM (once). What sits on the chain of dependent medians is kept to the boolean rule itself:
+// where an operand is the result of the warp's previous median it is taken from registers (the
+// host flags it; the shared-memory copy is still written for any later reader), the table rows,
+// the cost counter and the descriptor of the NEXT median are fetched before the current one is
+// evaluated (descriptors run two ahead). Measured per median on the spine: 180 cycles when every
+// operand made the shared-memory round trip, see profiles/README.md for this version.
+// The last CTA to finish publishes the per-op costs straight into mapped host memory -- every
+// 64-bit word carries the call's tag in its top 16 bits, so the host needs no ordering between
+// words and the kernel no system-scope fence -- and re-zeroes the accumulators: one kernel
+// launch is the whole call.
 constexpr int kFitchTileWarps = 8;
 constexpr int kFitchInlineProg = 3200;  // bytes of program that fit into the kernel parameters
 constexpr int kFitchAccCopies = 16;  // CTAs spread their atomics over this many accumulator sets (L2 serialises same-address atomics)
 struct __align__(16) FitchTileOp {
-  uint32_t l_off, r_off;  // byte offsets of the operands' rows in the tile table; the result replaces the left row
+  uint32_t l_off, r_off;  // byte offsets of the operands' rows in the tile table; the result replaces the left row.
+                          // l_off bit 0: the left operand is the result of the warp's previous median (registers)
   uint32_t *out;          // parent set in HBM, or NULL (root-edge join)
 };
 struct FitchTileArgs {
   const uint32_t *const *in_ptr;   // [n_in]
-  const FitchTileOp *ops;          // [n_ops] sorted by level, the root join last
+  const FitchTileOp *ops;          // [n_ops] phase-1 lists of warp 0, 1, ..., then phase 2 (the root join last)
   const int *task_start;           // [kFitchTileWarps + 2]: phase-1 op ranges per warp, then the phase-2 range
   int n_in, n_ops;
   int64_t nwords, N;
   const uint32_t *wt;
-  unsigned long long *acc;         // [kFitchAccCopies][n_ops + 2]: per-op costs, total, CTA counter (all zero between calls)
-  unsigned long long *host_out;    // mapped host memory [n_ops + 2]: per-op costs, total, then the call's sequence number
-  unsigned long long seq;          // written last: the host spins on it instead of a stream sync
+  unsigned long long *acc;         // [kFitchAccCopies][n_ops + 2]: per-op costs, (unused), CTA counter (all zero between calls)
+  unsigned long long *host_out;    // mapped host memory [n_ops + 2]: per-op costs (tagged), (unused), then the call's sequence number
+  unsigned long long seq;          // untagged protocol: written last, the host spins on it instead of a stream sync
+  unsigned long long tag;          // != 0: every published word is cost | tag (tag = 16 bits << 48); no fences, no seq word
   int inline_prog;                 // 1: the program travels in `prog` (kernel parameter space), no H2D copy
+  unsigned long long *stamps;      // measurement only (PHYLO_FITCH_TIMING=1), else NULL
   __align__(16) unsigned char prog[kFitchInlineProg];  // ops | in_ptr | task_start
 };
 
 // Every operand is consumed exactly once (the host checks the schedule is a forest and gives
 // every use of an input its own row), so a median is written over its left operand: the table
-// holds only the n_in input rows (T x 512 bytes for a whole tree), 6 CTAs per SM for 64 taxa.
+// holds only the n_in input rows (T x 512 bytes for a whole tree), 5-6 CTAs per SM for 64 taxa.
 // CNT = uint16_t (unweighted: <= 32 per tile and op, <= 2047 tiles per CTA) or unsigned long long (weighted)
 template <typename CNT>
 __global__ void __launch_bounds__(256)
@@ -355,6 +373,7 @@ fitch_tile_kernel(const FitchTileArgs a) {
   __shared__ bool is_last;
   __shared__ int stask[kFitchTileWarps + 2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFitchTileWarps;
+  fitch_stamp(a.stamps, 0);
   {
     const FitchTileOp *gops = a.inline_prog ? reinterpret_cast<const FitchTileOp *>(a.prog) : a.ops;
     const uint32_t *const *gin = a.inline_prog ? reinterpret_cast<const uint32_t *const *>(a.prog + sizeof(FitchTileOp) * a.n_ops) : a.in_ptr;
@@ -366,84 +385,119 @@ fitch_tile_kernel(const FitchTileArgs a) {
   for (int i = tid; i < a.n_ops * 32; i += blockDim.x) sh_cnt[i] = 0;
   __syncthreads();
   const int64_t ntiles = (a.nwords + 31) / 32;
-  unsigned char *mine = table + lane * 16;                 // this lane's column inside any table row
+  const uint32_t mine = smem_u32(table) + lane * 16;                 // this lane's column inside any table row
+  const uint32_t ops_s = smem_u32(sops);
   const int p1_lo = stask[warp], p1_hi = stask[warp + 1], p2_lo = stask[kFitchTileWarps], p2_hi = stask[kFitchTileWarps + 1];
+  auto lds = [](uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+  };
+  auto sts = [](uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  };
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t w = tile * 32 + lane;  // buffers are padded to whole tiles: always in bounds
     const uint32_t valid = valid_mask(w, a.N);
-    for (int i = warp; i < a.n_in; i += nwarps) cp_async16(mine + i * 512, sin[i] + w * 4);
+    for (int i = warp; i < a.n_in; i += nwarps)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mine + (uint32_t)i * 512u), "l"(sin[i] + w * 4) : "memory");
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    // a run of ops executed by this warp in order; the next descriptor is fetched one op ahead
+    if (tile == blockIdx.x) fitch_stamp(a.stamps, 1);
+    // a run of ops executed by this warp in order; op = {l_off, r_off, out lo, out hi}
     auto run = [&](int lo, int hi) {
       if (lo >= hi) return;
-      FitchTileOp op = sops[lo];
-      for (int o = lo; o < hi; ++o) {
-        const FitchTileOp nxt = sops[min(o + 1, hi - 1)];
-        const uint4 ua = *reinterpret_cast<const uint4 *>(mine + op.l_off), ub = *reinterpret_cast<const uint4 *>(mine + op.r_off);
-        Planes<4> pa, pb, pc;
-        pa.v[0] = ua.x; pa.v[1] = ua.y; pa.v[2] = ua.z; pa.v[3] = ua.w;
-        pb.v[0] = ub.x; pb.v[1] = ub.y; pb.v[2] = ub.z; pb.v[3] = ub.w;
-        const uint32_t chg = fitch_rule<4>(pa, pb, pc) & valid;
-        const uint4 uc = make_uint4(pc.v[0], pc.v[1], pc.v[2], pc.v[3]);
-        *reinterpret_cast<uint4 *>(mine + op.l_off) = uc;
-        if (op.out != nullptr) *reinterpret_cast<uint4 *>(op.out + w * 4) = uc;
-        if (sizeof(CNT) == 8) sh_cnt[o * 32 + lane] += (CNT)weighted_cost(chg, w, a.wt);
-        else sh_cnt[o * 32 + lane] += (CNT)__popc(chg);
-        op = nxt;
+      const int last = hi - 1;
+      uint4 op = lds(ops_s + lo * 16), nx = lds(ops_s + min(lo + 1, last) * 16);
+      uint4 cur = make_uint4(0, 0, 0, 0);
+      uint4 pa = lds(mine + op.x), pb = lds(mine + op.y);  // the first op of a run never takes the register operand
+      CNT cn = sh_cnt[lo * 32 + lane];
+      for (int o = lo; o <= last; ++o) {
+        const uint4 nn = lds(ops_s + min(o + 2, last) * 16);
+        const bool lcur = (op.x & 1u) != 0;
+        const uint4 x = lcur ? cur : pa, y = pb;
+        // the next median's rows and counter: none of them is written by this median (the host flags that case)
+        if (!(nx.x & 1u)) pa = lds(mine + nx.x);
+        pb = lds(mine + nx.y);
+        const CNT cnext = sh_cnt[min(o + 1, last) * 32 + lane];
+        const uint32_t any = (x.x & y.x) | (x.y & y.y) | (x.z & y.z) | (x.w & y.w);
+        cur.x = (x.x & y.x) | (~any & (x.x | y.x));
+        cur.y = (x.y & y.y) | (~any & (x.y | y.y));
+        cur.z = (x.z & y.z) | (~any & (x.z | y.z));
+        cur.w = (x.w & y.w) | (~any & (x.w | y.w));
+        sts(mine + (op.x & ~1u), cur);
+        if ((op.z | op.w) != 0u) {
+          const unsigned long long out = ((unsigned long long)op.z | ((unsigned long long)op.w << 32)) + (unsigned long long)w * 16ull;
+          asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(out), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w) : "memory");
+        }
+        const uint32_t chg = ~any & valid;
+        if (sizeof(CNT) == 8) sh_cnt[o * 32 + lane] = cn + (CNT)weighted_cost(chg, w, a.wt);
+        else sh_cnt[o * 32 + lane] = cn + (CNT)__popc(chg);
+        cn = cnext;
+        op = nx;
+        nx = nn;
       }
     };
     run(p1_lo, p1_hi);
     __syncthreads();
+    if (tile == blockIdx.x) fitch_stamp(a.stamps, 2);
     if (warp == 0) run(p2_lo, p2_hi);
     __syncthreads();  // the table is rewritten by the next tile's inputs
+    if (tile == blockIdx.x) fitch_stamp(a.stamps, 3);
   }
-  // per-op totals: one warp per op folds its 32 lane counters
+  fitch_stamp(a.stamps, 4);
+  // per-op totals: one warp per op folds its 32 lane counters (four ops at a time: the reductions overlap)
   unsigned long long *acc = a.acc + (size_t)(blockIdx.x % kFitchAccCopies) * (a.n_ops + 2);
-  unsigned long long t = 0;
-  for (int o = warp; o < a.n_ops; o += nwarps) {
-    unsigned long long c;
-    if (sizeof(CNT) == 8) {
-      c = sh_cnt[o * 32 + lane];
+  for (int o0 = warp; o0 < a.n_ops; o0 += 4 * nwarps) {
+    unsigned long long c[4];
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
-    } else {
-      c = __reduce_add_sync(0xffffffffu, (unsigned)sh_cnt[o * 32 + lane]);
+    for (int k = 0; k < 4; ++k) {
+      const int o = o0 + k * nwarps;
+      c[k] = 0;
+      if (o < a.n_ops) {
+        if (sizeof(CNT) == 8) {
+          c[k] = sh_cnt[o * 32 + lane];
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) c[k] += __shfl_down_sync(0xffffffffu, c[k], off);
+        } else {
+          c[k] = __reduce_add_sync(0xffffffffu, (unsigned)sh_cnt[o * 32 + lane]);
+        }
+      }
     }
-    if (lane == 0 && c) {
-      atomicAdd(&acc[o], c);
-      t += c;
-    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane == 0 && c[k]) atomicAdd(&acc[o0 + k * nwarps], c[k]);
   }
-  if (lane == 0 && t) atomicAdd(&acc[a.n_ops], t);
   // ---- last CTA publishes to mapped host memory and restores the all-zero invariant.
   // bar.sync orders the CTA's atomics before thread 0's fence + counter increment
   // (cumulativity), so only one thread pays for the fence.
   __syncthreads();
+  fitch_stamp(a.stamps, 5);
   if (tid == 0) {
     __threadfence();
     is_last = atomicAdd(&a.acc[a.n_ops + 1], 1ull) == (unsigned long long)gridDim.x - 1;
   }
   __syncthreads();
+  fitch_stamp(a.stamps, 6);
   if (is_last) {
     __threadfence();
-    for (int o = tid; o <= a.n_ops; o += blockDim.x) {
+    for (int o = tid; o < a.n_ops; o += blockDim.x) {
       unsigned long long v = 0;
 #pragma unroll
       for (int c = 0; c < kFitchAccCopies; ++c) {
         v += __ldcg(&a.acc[(size_t)c * (a.n_ops + 2) + o]);
         a.acc[(size_t)c * (a.n_ops + 2) + o] = 0;
       }
-      a.host_out[o] = v;
+      *reinterpret_cast<volatile unsigned long long *>(&a.host_out[o]) = v | a.tag;
     }
     if (tid == 0) a.acc[a.n_ops + 1] = 0;
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      *reinterpret_cast<volatile unsigned long long *>(&a.host_out[a.n_ops + 1]) = a.seq;
+    if (a.tag == 0) {  // untagged (weighted costs may need all 64 bits): results, system fence, then the sequence number
       __threadfence_system();
+      __syncthreads();
+      if (tid == 0) *reinterpret_cast<volatile unsigned long long *>(&a.host_out[a.n_ops + 1]) = a.seq;
     }
+    fitch_stamp(a.stamps, 7);
   }
 }
 

@@ -171,7 +171,7 @@ def test_scoring_on_a_non_blocking_stream(built, oracle):
                 assert rel_err(e.lk_score_tree(ops, ra, rb, rt), want) <= 1e-12
         chars = tree.random_fitch_chars(10, 5000, 4, seed=3)
         fw = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb)["length"]
-        for walk in (1, 2, 0):
+        for walk in (1, 3, 2, 0):
             e.set_option(e.OPT_FITCH_WALK, walk)
             e.fitch_set_tips(chars, 4, capacity=n_nodes)
             assert e.fitch_score_tree(ops, ra, rb) == fw
