@@ -182,6 +182,8 @@ struct phylo_engine {
   // branch-length loop (lk_edge_kernels.cuh): eigenvector matrices in the orientation the sum table needs,
   // the sum table of the prepared edge, per-(t, derivative) block partials
   double *dUL = nullptr, *dUR = nullptr, *dSum = nullptr, *dEdgePart = nullptr, *dEdgeOut = nullptr, *dEdgeT = nullptr;
+  char *dEdgeArena = nullptr;  // lk_edge_lnl_batch: edge descriptors + fold levels
+  size_t capEdgeArena = 0;
   int32_t *dSumSc = nullptr;
   bool edge_ready = false;
   int edge_a = -1, edge_b = -1;
@@ -402,7 +404,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   dfree(e->dP); dfree(e->dFrag); dfree(e->dT);
   for (void *p : e->xOpened) cudaIpcCloseMemHandle(p);
   dfree(e->xMailbox);
-  dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dStamps); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT);
+  dfree(e->dTT); dfree(e->dTTsc); dfree(e->dSymTab); dfree(e->dCost); dfree(e->dSched); dfree(e->dStage); dfree(e->dProg); dfree(e->dRaw); dfree(e->dBad); dfree(e->dSpill); dfree(e->dAcc); dfree(e->dStamps); dfree(e->dTreeDone); dfree(e->dTcm); dfree(e->dUL); dfree(e->dUR); dfree(e->dEdgeOut); dfree(e->dEdgeT); dfree(e->dEdgeArena);
   if (e->hProg) cudaFreeHost(e->hProg);
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (auto ev : e->slabEvents) cudaEventDestroy(ev);
@@ -1705,6 +1707,8 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
 template <int S, typename MaskT, int R, int NW, int KT>
 static cudaError_t launch_treem(phylo_engine *e, TreeMArgs args, size_t smem) {
   auto kern = lk_treem_kernel<S, MaskT, R, NW, KT>;
+  static const bool paired = [] { const char *v = getenv("PHYLO_TREEM_PAIRED"); return !(v && v[0] == '0'); }();
+  args.paired = paired ? 1 : 0;
   args.prog_in_smem = smem + treem_prog_bytes(args.n_steps) <= 227 * 1024;
   if (args.prog_in_smem) smem += treem_prog_bytes(args.n_steps);
   cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2592,6 +2596,78 @@ extern "C" int phylo_lk_edge_lnl_batch(phylo_engine *e, int n_edges, const int32
   for (int i = 0; i < n_edges; ++i) e->hT[i] = t[i];
   rc = build_pt(e, n_edges);
   const size_t pk = (size_t)e->K * e->S * e->S;
+  // 4 states: every (edge, 1024-pattern block) pair is a work item of ONE launch, then the
+  // remaining fold levels for all edges at once (y grid dimension <= 65535 edges per launch)
+  if (rc == PHYLO_OK && e->S == 4 && (e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8 || e->K == 16) && n_edges <= 65535) {
+    std::vector<EdgeJoin> he(n_edges);
+    for (int i = 0; i < n_edges; ++i) {
+      Operand a, b;
+      if ((rc = lk_operand(e, a_slots[i], &a, "lk_edge_lnl_batch")) != PHYLO_OK) break;
+      if ((rc = lk_operand(e, b_slots[i], &b, "lk_edge_lnl_batch")) != PHYLO_OK) break;
+      he[i] = EdgeJoin{a.src, b.src, a.scale, b.scale, a.tip ? 1 : 0, b.tip ? 1 : 0};
+    }
+    const int64_t nb1 = e->nPart, nb2 = (nb1 + kLnlBlock - 1) / kLnlBlock, nb3 = (nb2 + kLnlBlock - 1) / kLnlBlock;
+    const size_t descBytes = (sizeof(EdgeJoin) * n_edges + 255) & ~(size_t)255;
+    const size_t bytes = descBytes + sizeof(double) * (size_t)n_edges * (size_t)(nb1 + nb2 + nb3 + 1);
+    if (rc == PHYLO_OK && bytes > e->capEdgeArena) {  // grow-only scratch kept across calls (a search calls this per candidate set)
+      dfree(e->dEdgeArena);
+      e->capEdgeArena = 0;
+      if (cudaMalloc(&e->dEdgeArena, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        rc = fail(e, PHYLO_ERR_CUDA, "lk_edge_lnl_batch: cannot allocate %zu bytes of device memory", bytes);
+      } else {
+        e->capEdgeArena = bytes;
+      }
+    }
+    char *arena = e->dEdgeArena;
+    if (rc == PHYLO_OK) {
+      EdgeJoin *dE = (EdgeJoin *)arena;
+      double *p1 = (double *)(arena + descBytes), *p2 = p1 + (size_t)n_edges * nb1, *p3 = p2 + (size_t)n_edges * nb2;
+      cudaMemcpyAsync(dE, he.data(), sizeof(EdgeJoin) * n_edges, cudaMemcpyHostToDevice, e->stream);
+      {
+        ProfScope prof(e, KC_ROOT);
+        const int g = (int)std::min<int64_t>(nb1 * n_edges, (int64_t)e->sm_count * 8);
+#define RB(KV) root4_batch_kernel<KV><<<g, 256, 0, e->stream>>>(dE, n_edges, e->dP, e->dPi, e->dProbs, e->pinvar, \
+                                                                (const uint8_t *)e->dInv, e->dWeights, p1, e->N)
+        switch (e->K) {
+          case 1: RB(1); break;
+          case 2: RB(2); break;
+          case 4: RB(4); break;
+          case 8: RB(8); break;
+          default: RB(16);
+        }
+#undef RB
+        ++e->launches;
+      }
+      {
+        ProfScope prof(e, KC_REDUCE);
+        const double *cur = p1;
+        int64_t n = nb1;
+        double *outs[2] = {p2, p3};
+        int lvl = 0;
+        do {
+          const int64_t nb = (n + kLnlBlock - 1) / kLnlBlock;
+          reduce1024_rows_kernel<<<dim3((unsigned)nb, (unsigned)n_edges), 256, 0, e->stream>>>(cur, n, outs[lvl & 1]);
+          ++e->launches;
+          cur = outs[lvl & 1];
+          ++lvl;
+          n = nb;
+        } while (n > 1);
+        cudaMemcpyAsync(hres, cur, sizeof(double) * n_edges, cudaMemcpyDeviceToHost, e->stream);
+      }
+    }
+    const cudaError_t st = cudaStreamSynchronize(e->stream);
+    const cudaError_t le = cudaGetLastError();
+    if (rc == PHYLO_OK && st == cudaSuccess && le == cudaSuccess)
+      for (int i = 0; i < n_edges; ++i) lnl_out[i] = hres[i];
+    cudaFreeHost(hres);
+    if (rc != PHYLO_OK) return rc;
+    if (st != cudaSuccess || le != cudaSuccess)
+      return fail(e, PHYLO_ERR_CUDA, "lk_edge_lnl_batch: %s", cudaGetErrorString(st != cudaSuccess ? st : le));
+    // (site lnL / level-1 partials of the last whole evaluation are left as they were)
+    if (e->prof_on) prof_resolve_lazy(e);
+    return PHYLO_OK;
+  }
   for (int i = 0; i < n_edges && rc == PHYLO_OK; ++i) {
     Operand a, b;
     if ((rc = lk_operand(e, a_slots[i], &a, "lk_edge_lnl_batch")) != PHYLO_OK) break;

@@ -317,6 +317,106 @@ reduce1024_kernel(const double *__restrict__ in, int64_t n, double *__restrict__
   if (threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
+// ------------------------------------------------ many root-edge joins in one launch ----
+// phylo_lk_edge_lnl_batch for 4 states: one work item = (edge, block of 1024 patterns). The edge's
+// two operands (CLV + scale counters, or tip masks) and its K transition matrices come from a
+// descriptor table; the arithmetic and the fold are root4_kernel's, so an edge's lnL is
+// bit-identical to a single phylo_lk_edge_lnl call. partials[edge * nblocks + blk].
+struct EdgeJoin {
+  const void *asrc, *bsrc;
+  const int32_t *asc, *bsc;
+  int atip, btip;
+};
+template <int K>
+__global__ void __launch_bounds__(256)
+root4_batch_kernel(const EdgeJoin *__restrict__ edges, int n_edges, const double *__restrict__ Pall,
+                   const double *__restrict__ pi, const double *__restrict__ probs, double pinvar,
+                   const uint8_t *__restrict__ inv, const double *__restrict__ weights,
+                   double *__restrict__ partials, int64_t N) {
+  __shared__ double vals[kLnlBlock];
+  __shared__ double wsum[32];
+  const int k = threadIdx.x % K;
+  const double pi0 = pi[0], pi1 = pi[1], pi2 = pi[2], pi3 = pi[3], pk = probs[k];
+  const int64_t nblocks = (N + kLnlBlock - 1) / kLnlBlock, items = nblocks * n_edges;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int edge = (int)(item / nblocks);
+    const int64_t blk = item - (int64_t)edge * nblocks;
+    const EdgeJoin ej = edges[edge];
+    double pm[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) pm[e] = __ldg(Pall + ((size_t)edge * K + k) * 16 + e);
+    const double *aclv = (const double *)ej.asrc, *bclv = (const double *)ej.bsrc;
+    const uint8_t *atip = (const uint8_t *)ej.asrc, *btip = (const uint8_t *)ej.bsrc;
+    for (int it = 0; it < kLnlBlock * K; it += blockDim.x) {
+      const int ql = it + threadIdx.x;
+      const int plocal = ql / K;
+      const int64_t p = blk * kLnlBlock + plocal;
+      const bool act = p < N;
+      d4 a{0, 0, 0, 0}, b{0, 0, 0, 0};
+      int c = 0;
+      if (act) {
+        const int64_t q = p * K + k;
+        if (ej.atip) {
+          const int m = atip[p];
+          a = d4{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
+        } else {
+          a = ld256_stream(aclv + q * 4);
+          if (k == 0) c += ej.asc[p];
+        }
+        if (ej.btip) {
+          const int m = btip[p];
+          b = d4{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
+        } else {
+          b = ld256_stream(bclv + q * 4);
+          if (k == 0) c += ej.bsc[p];
+        }
+      }
+      double y0 = ((pm[0] * b.x + pm[1] * b.y) + pm[2] * b.z) + pm[3] * b.w;
+      double y1 = ((pm[4] * b.x + pm[5] * b.y) + pm[6] * b.z) + pm[7] * b.w;
+      double y2 = ((pm[8] * b.x + pm[9] * b.y) + pm[10] * b.z) + pm[11] * b.w;
+      double y3 = ((pm[12] * b.x + pm[13] * b.y) + pm[14] * b.z) + pm[15] * b.w;
+      double lk = (((pi0 * a.x) * y0 + (pi1 * a.y) * y1) + (pi2 * a.z) * y2) + (pi3 * a.w) * y3;
+      double l = pk * lk;
+#pragma unroll
+      for (int off = 1; off < K; off <<= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+      if (k == 0) {
+        double wl = 0.0;
+        if (act) {
+          double lnl;
+          if (pinvar >= 0.0) {
+            const int m = inv[p];
+            const double pv = (m & 1 ? pi0 : 0.0) + (m & 2 ? pi1 : 0.0) + (m & 4 ? pi2 : 0.0) +
+                              (m & 8 ? pi3 : 0.0);
+            lnl = lnl_pinvar(l, c, pinvar, pv);
+          } else {
+            lnl = log(l) - (double)c * (kScaleExp * 0.6931471805599453094);
+          }
+          wl = (weights ? weights[p] : 1.0) * lnl;
+        }
+        vals[plocal] = wl;
+      }
+    }
+    __syncthreads();
+    const double r = block_fold_1024(vals, wsum);
+    if (threadIdx.x == 0) partials[item] = r;
+    __syncthreads();
+  }
+}
+
+// One more level of the canonical reduction for many rows at once: row = blockIdx.y,
+// out[row * nb + b] = fold(in[row * n + b*1024 .. ]) with nb = gridDim.x.
+__global__ void __launch_bounds__(256)
+reduce1024_rows_kernel(const double *__restrict__ in, int64_t n, double *__restrict__ out) {
+  __shared__ double vals[kLnlBlock];
+  __shared__ double wsum[32];
+  const double *row = in + (size_t)blockIdx.y * n;
+  const int64_t lo = (int64_t)blockIdx.x * kLnlBlock;
+  for (int i = threadIdx.x; i < kLnlBlock; i += blockDim.x) vals[i] = (lo + i < n) ? row[lo + i] : 0.0;
+  __syncthreads();
+  const double r = block_fold_1024(vals, wsum);
+  if (threadIdx.x == 0) out[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = r;
+}
+
 // -------------------------------------------------- any-S pruning update (20, 61, ...) ----
 // One CTA = a tile of TP patterns (one per thread), looping over rate classes. Per class the
 // two transition matrices (stored transposed, rows padded to a multiple of 4, so a thread

@@ -82,6 +82,7 @@ struct TreeMArgs {
   // it then spent at the step's barrier, [2] steps, [3] cycles of the body spent waiting for the tables; variants: T+T, T+C, T+G, C+G, G+G, root. NULL = off
   unsigned long long *timing;
   int prog_in_smem;  // the launch reserved treem_prog_bytes(n_steps) of shared memory behind the buffers
+  int paired;        // 20 states: CLV+CLV steps share every A-fragment read between the warp's two groups (measurement switch PHYLO_TREEM_PAIRED=0)
 };
 
 constexpr int treem_pitch(int cols) {
@@ -332,6 +333,198 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
               if (lane == 0) asm volatile("cp.async.bulk.wait_group %0;" ::"n"(R) : "memory");
               __syncwarp();
             }
+          }
+          if (PT && R == 2 && LM != TM_TIP && RM != TM_TIP && a.paired) {
+            // ---- 20 states, both operands CLVs: rate classes outer, the warp's two groups inner. Every A fragment
+            // read from shared memory feeds the DMMAs of both groups: these steps were bound by shared-memory traffic
+            // (LSU 78 % busy, 60 of ~85 wavefronts per (rate class, group) were A fragments), not by the tensor
+            // pipe. Both CLVs are complete after the last rate class; their tensor stores are read out by the TMA
+            // unit while the next step's first rate class is computed (wait_group.read sits just before that step's
+            // first store into the running-value buffer). Measured (PHYLO_TREEM_TIMING): CLV+CLV steps 22.7 k ->
+            // 19.6 k cycles per chunk; steps with a tip side lose more from the late stores than they gain (tip+tip
+            // 7.7 k -> 11.3 k, tip+CLV 12.0 k -> 13.9 k) and keep the group-outer order below.
+            constexpr int R2 = 2;
+            int64_t pbase2[R2], pa02[R2];
+            bool ok0[R2], ok1[R2], act[R2];
+            int hh0[R2], hh1[R2], gsa[R2], gsb[R2];
+            unsigned mL0[R2], mL1[R2], mR0[R2], mR1[R2];
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+              act[r] = r < nact;
+              pbase2[r] = (cbase + (int64_t)r * NW + warp) * 8;
+              pa02[r] = pbase2[r] + 2 * fc;
+              ok0[r] = act[r] && pa02[r] < a.N;
+              ok1[r] = act[r] && pa02[r] + 1 < a.N;
+              hh0[r] = hh1[r] = (int)0x80000000;
+              gsa[r] = gsb[r] = 0;
+              mL0[r] = mL1[r] = mR0[r] = mR1[r] = 0;
+              if (LM == TM_TIP) {
+                mL0[r] = (unsigned)shfl_mask(ml, r * 8 + 2 * fc);
+                mL1[r] = (unsigned)shfl_mask(ml, r * 8 + 2 * fc + 1);
+              }
+              if (RM == TM_TIP) {
+                mR0[r] = (unsigned)shfl_mask(mr, r * 8 + 2 * fc);
+                mR1[r] = (unsigned)shfl_mask(mr, r * 8 + 2 * fc + 1);
+              }
+              if (RM == TM_GLB) {
+                if (ok0[r]) gsa[r] += rgs[pa02[r]];
+                if (ok1[r]) gsb[r] += rgs[pa02[r] + 1];
+              }
+              if (LM == TM_GLB) {
+                if (ok0[r]) gsa[r] += lgs[pa02[r]];
+                if (ok1[r]) gsb[r] += lgs[pa02[r] + 1];
+              }
+            }
+            auto tip_row = [&](unsigned mk) {
+              return mk == (unsigned)keep ? S : ((mk & (mk - 1)) == 0 ? (mk ? __ffs((int)mk) - 1 : 0) : -1);
+            };
+            auto tip_side = [&](const double *pt, unsigned mk0, unsigned mk1, double (&c)[MT][2]) {
+              const int j0 = tip_row(mk0), j1 = tip_row(mk1);
+              if (j0 >= 0 && j1 >= 0) {
+                const uint32_t pt_s = pbuf_s + (uint32_t)(pt - pbuf) * 8u;
+                lds128_s(pt_s + (uint32_t)(j0 * S + 2 * fr) * 8u, c[0][0], c[1][0]);
+                lds128_s(pt_s + (uint32_t)(j1 * S + 2 * fr) * 8u, c[0][1], c[1][1]);
+                c[2][0] = pt[j0 * S + 16 + fr];
+                c[2][1] = pt[j1 * S + 16 + fr];
+              } else {
+#pragma unroll 1
+                for (int j = 0; j < S; ++j) {
+                  const double *col = pt + j * S;
+                  if ((mk0 >> j) & 1) { c[0][0] += col[2 * fr]; c[1][0] += col[2 * fr + 1]; c[2][0] += col[16 + fr]; }
+                  if ((mk1 >> j) & 1) { c[0][1] += col[2 * fr]; c[1][1] += col[2 * fr + 1]; c[2][1] += col[16 + fr]; }
+                }
+              }
+            };
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+              const double *tabL = fl + k * FRAG, *tabR = frg + k * FRAG;
+              double cx[R2][MT][2], cy[R2][MT][2];
+#pragma unroll
+              for (int r = 0; r < R2; ++r)
+#pragma unroll
+                for (int m = 0; m < MT; ++m) cx[r][m][0] = cx[r][m][1] = cy[r][m][0] = cy[r][m][1] = 0.0;
+              if constexpr (LM == TM_TIP) {
+#pragma unroll
+                for (int r = 0; r < R2; ++r)
+                  if (act[r]) tip_side(tabL, mL0[r], mL1[r], cx[r]);
+              }
+              if constexpr (RM == TM_TIP) {
+#pragma unroll
+                for (int r = 0; r < R2; ++r)
+                  if (act[r]) tip_side(tabR, mR0[r], mR1[r], cy[r]);
+              }
+              if constexpr (LM != TM_TIP || RM != TM_TIP) {
+                // operand rows: CUR in shared memory ([k][pattern fr][PITCH] + fc), GLB in the node slot
+                const double *rowL[R2], *rowR[R2];
+                bool gokL[R2], gokR[R2];
+#pragma unroll
+                for (int r = 0; r < R2; ++r) {
+                  gokL[r] = gokR[r] = act[r];
+                  rowL[r] = rowR[r] = cur + r * gsz + (k * 8 + fr) * PITCH + fc;
+                  if constexpr (LM == TM_GLB) {
+                    gokL[r] = act[r] && pbase2[r] + fr < a.N;
+                    rowL[r] = lg + ((size_t)(pbase2[r] + fr) * K + k) * S + fc;
+                  }
+                  if constexpr (RM == TM_GLB) {
+                    gokR[r] = act[r] && pbase2[r] + fr < a.N;
+                    rowR[r] = rg + ((size_t)(pbase2[r] + fr) * K + k) * S + fc;
+                  }
+                }
+                double bl[R2][KS], br[R2][KS];
+#pragma unroll
+                for (int r = 0; r < R2; ++r)
+#pragma unroll
+                  for (int ks = 0; ks < KS; ++ks) {
+                    if constexpr (LM == TM_CUR) bl[r][ks] = rowL[r][ks * 4];
+                    if constexpr (LM == TM_GLB) bl[r][ks] = (gokL[r] && ks * 4 + fc < S) ? rowL[r][ks * 4] : 0.0;
+                    if constexpr (RM == TM_CUR) br[r][ks] = rowR[r][ks * 4];
+                    if constexpr (RM == TM_GLB) br[r][ks] = (gokR[r] && ks * 4 + fc < S) ? rowR[r][ks * 4] : 0.0;
+                  }
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                  for (int m = 0; m < MT; ++m) {
+                    if constexpr (LM != TM_TIP) {
+                      const double av = tabL[(m * KS + ks) * 32 + lane];
+#pragma unroll
+                      for (int r = 0; r < R2; ++r) dmma_acc(cx[r][m], av, bl[r][ks]);
+                    }
+                    if constexpr (RM != TM_TIP) {
+                      const double av = tabR[(m * KS + ks) * 32 + lane];
+#pragma unroll
+                      for (int r = 0; r < R2; ++r) dmma_acc(cy[r][m], av, br[r][ks]);
+                    }
+                  }
+                }
+              }
+              if (k == 0) {
+                // the previous step's two tensor stores must have read these buffers before they are rewritten
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              __syncwarp();  // (and every lane has read this rate class of the running values)
+#pragma unroll
+              for (int r = 0; r < R2; ++r) {
+                if (act[r]) {
+                  const double a0 = cx[r][0][0] * cy[r][0][0], a1 = cx[r][0][1] * cy[r][0][1];
+                  const double b0 = cx[r][1][0] * cy[r][1][0], b1 = cx[r][1][1] * cy[r][1][1];
+                  const double d0 = cx[r][2][0] * cy[r][2][0], d1 = cx[r][2][1] * cy[r][2][1];
+                  const uint32_t c0_s = cur_s + (uint32_t)(r * gsz + (k * 8 + 2 * fc) * PITCH + 2 * fr) * 8u;
+                  sts128_s(c0_s, a0, b0);
+                  sts128_s(c0_s + PITCH * 8u, a1, b1);
+                  hh0[r] = max(hh0[r], max(hi32(a0), hi32(b0)));
+                  hh1[r] = max(hh1[r], max(hi32(a1), hi32(b1)));
+                  if (fr < 4) {
+                    double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH;
+                    c0[16 + fr] = d0;
+                    c0[PITCH + 16 + fr] = d1;
+                    hh0[r] = max(hh0[r], hi32(d0));
+                    hh1[r] = max(hh1[r], hi32(d1));
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+              if (act[r]) {
+                int h0 = hh0[r], h1 = hh1[r];
+#pragma unroll
+                for (int off = 4; off <= 16; off <<= 1) {
+                  h0 = max(h0, __shfl_xor_sync(FULL, h0, off));
+                  h1 = max(h1, __shfl_xor_sync(FULL, h1, off));
+                }
+                const bool r0 = ok0[r] && h0 < kScaleHiThresh, r1 = ok1[r] && h1 < kScaleHiThresh;
+                if (r0 || r1) {  // rare: every lane rescales what it stored; rolled loops
+#pragma unroll 1
+                  for (int k = 0; k < K; ++k) {
+                    double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH, *c1 = c0 + PITCH;
+#pragma unroll 1
+                    for (int mt = 0; mt < MT; ++mt) {
+                      const int i = Map::i_of(mt, fr);
+                      if (i < S) {
+                        if (r0) c0[i] *= 0x1p+256;
+                        if (r1) c1[i] *= 0x1p+256;
+                      }
+                    }
+                  }
+                }
+                int s0 = gsa[r], s1 = gsb[r];
+                if (LM == TM_CUR || RM == TM_CUR) { s0 += csc0[r]; s1 += csc1[r]; }
+                s0 += r0 ? 1 : 0;
+                s1 += r1 ? 1 : 0;
+                csc0[r] = s0;
+                csc1[r] = s1;
+                if (fr == 0) {
+                  if (ok0[r]) ogs[pa02[r]] = s0;
+                  if (ok1[r]) ogs[pa02[r] + 1] = s1;
+                }
+                // the group's finished CLV [k][8][S] -> node slot [pattern][k][S]: one tensor store (rows >= N clipped)
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tma_store_3d(a.tmaps + (size_t)ins.out_slot * 128, cur + r * gsz, 0, (int)pbase2[r], 0);
+              }
+              if (lane == 0) bulk_commit();  // one bulk group per (step, r), empty for an idle r: the waits count groups
+            }
+            return;
           }
           // group by group (r outer, rate classes inner): a group's CLV is complete after its K iterations and
           // leaves at once (TMA), so the drain to HBM overlaps the next group's arithmetic
