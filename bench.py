@@ -907,8 +907,16 @@ def run_workload(ctx, args, key, wl, primary):
     ms, result = ctx.timed_steps(step, steps, flush)
     prof = eng.profile_get()
     eng.profile(False)
+    ms_with_kernel_events = None
+    if flush:
+        # microsecond steps (working set near the L2 size: one or two launches per step): the engine profiler's
+        # event pair around every launch costs ~3 us per event boundary on the device, a fifth of such a step.
+        # The per-kernel durations come from the pass above; the step time from a second pass of the same K
+        # steps without those inner events (both reported).
+        ms_with_kernel_events = ms / steps
+        ms, result = ctx.timed_steps(step, steps, flush)
     launches = eng.launch_count - launches0
-    step_launches = (eng.launch_count - launches0) // (steps + warmup)
+    step_launches = (eng.launch_count - launches0) // ((2 if flush else 1) * steps + warmup)
     # a timed region shorter than a few nvidia-smi samples (50 ms apart): keep the same load running,
     # untimed, so that the clocks / throttle reasons are sampled under it (the count is derived from
     # the all-reduced time, so every rank runs the same number of steps)
@@ -1131,7 +1139,7 @@ def run_workload(ctx, args, key, wl, primary):
             "roofline_hbm": roof if roof_tensor and S > 32 else None,
             "roofline_tensor": roof_tensor if roof_tensor and S <= 32 else None,
             "roofline_step": roof_step, "kernels": kernels, "cpu_baseline": cpu,
-            "e2e": e2e, "branch_loop": branch_loop, "directions": directions, "gpu_launches": int(step_launches * steps),
+            "e2e": e2e, "ms_per_step_with_kernel_events": ms_with_kernel_events, "branch_loop": branch_loop, "directions": directions, "gpu_launches": int(step_launches * steps),
             "gpu_launches_total_incl_warmup": int(launches), "clocks": clocks, "check": check,
         }
     eng.close()

@@ -3691,6 +3691,7 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
     const int64_t waves = (ntiles + maxg - 1) / maxg;
     const int g = (int)((ntiles + waves - 1) / waves);
     if (!weighted && waves > 2000) return PHYLO_OK;  // 16-bit per-lane counters: the other kernels take it
+    a.prefetch_next = (waves >= 2 && waves <= 4) ? 1 : 0;
     kern<<<g, 256, smem, e->stream>>>(a);
     LAUNCH_CHECK();
     grid_used = g;

@@ -352,6 +352,7 @@ struct FitchTileArgs {
   unsigned long long seq;          // untagged protocol: written last, the host spins on it instead of a stream sync
   unsigned long long tag;          // != 0: every published word is cost | tag (tag = 16 bits << 48); no fences, no seq word
   int inline_prog;                 // 1: the program travels in `prog` (kernel parameter space), no H2D copy
+  int prefetch_next;               // 1: a CTA has only a few tiles: prefetch the next tile's rows into L2
   unsigned long long *stamps;      // measurement only (PHYLO_FITCH_TIMING=1), else NULL
   __align__(16) unsigned char prog[kFitchInlineProg];  // ops | in_ptr | task_start
 };
@@ -374,19 +375,26 @@ fitch_tile_kernel(const FitchTileArgs a) {
   __shared__ int stask[kFitchTileWarps + 2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kFitchTileWarps;
   fitch_stamp(a.stamps, 0);
+  const int64_t ntiles = (a.nwords + 31) / 32;
+  const uint32_t mine = smem_u32(table) + lane * 16;                 // this lane's column inside any table row
+  const uint32_t ops_s = smem_u32(sops);
   {
     const FitchTileOp *gops = a.inline_prog ? reinterpret_cast<const FitchTileOp *>(a.prog) : a.ops;
     const uint32_t *const *gin = a.inline_prog ? reinterpret_cast<const uint32_t *const *>(a.prog + sizeof(FitchTileOp) * a.n_ops) : a.in_ptr;
     const int *gts = a.inline_prog ? reinterpret_cast<const int *>(a.prog + sizeof(FitchTileOp) * a.n_ops + 8 * (size_t)a.n_in) : a.task_start;
+    // the first tile's rows are requested before anything else: the program copy below runs under their latency
+    if ((int64_t)blockIdx.x < ntiles) {
+      const int64_t w = (int64_t)blockIdx.x * 32 + lane;
+      for (int i = warp; i < a.n_in; i += nwarps)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mine + (uint32_t)i * 512u), "l"(gin[i] + w * 4) : "memory");
+    }
+    cp_async_commit();
     for (int i = tid; i < a.n_ops; i += blockDim.x) sops[i] = gops[i];
     for (int i = tid; i < a.n_in; i += blockDim.x) sin[i] = gin[i];
     if (tid < kFitchTileWarps + 2) stask[tid] = gts[tid];
   }
   for (int i = tid; i < a.n_ops * 32; i += blockDim.x) sh_cnt[i] = 0;
   __syncthreads();
-  const int64_t ntiles = (a.nwords + 31) / 32;
-  const uint32_t mine = smem_u32(table) + lane * 16;                 // this lane's column inside any table row
-  const uint32_t ops_s = smem_u32(sops);
   const int p1_lo = stask[warp], p1_hi = stask[warp + 1], p2_lo = stask[kFitchTileWarps], p2_hi = stask[kFitchTileWarps + 1];
   auto lds = [](uint32_t addr) {
     uint4 v;
@@ -399,12 +407,20 @@ fitch_tile_kernel(const FitchTileArgs a) {
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t w = tile * 32 + lane;  // buffers are padded to whole tiles: always in bounds
     const uint32_t valid = valid_mask(w, a.N);
-    for (int i = warp; i < a.n_in; i += nwarps)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mine + (uint32_t)i * 512u), "l"(sin[i] + w * 4) : "memory");
-    cp_async_commit();
+    if (tile != blockIdx.x) {
+      for (int i = warp; i < a.n_in; i += nwarps)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mine + (uint32_t)i * 512u), "l"(sin[i] + w * 4) : "memory");
+      cp_async_commit();
+    }
     cp_async_wait<0>();
     __syncthreads();
     if (tile == blockIdx.x) fitch_stamp(a.stamps, 1);
+    // few tiles per CTA (latency regime): the next tile's rows are pulled into L2 while this one is evaluated
+    if (a.prefetch_next && tile + gridDim.x < ntiles) {
+      const size_t off = (size_t)(tile + gridDim.x) * 512;  // a tile's share of a row: 32 columns x 16 bytes
+      for (int i = tid; i < a.n_in * 4; i += blockDim.x)
+        prefetch_l2(reinterpret_cast<const char *>(sin[i >> 2]) + off + (i & 3) * 128);
+    }
     // a run of ops executed by this warp in order; op = {l_off, r_off, out lo, out hi}
     auto run = [&](int lo, int hi) {
       if (lo >= hi) return;
