@@ -507,6 +507,42 @@ def test_fitch_caterpillar_and_partial_schedule(eng, oracle, fitch_walk):
         assert np.array_equal(eng.fitch_get_states(p), want["prelim"][p])
 
 
+def test_fitch_tile_program_cache(eng, oracle):
+    """The tile kernel keeps the compiled program of the last schedule. Same schedule again (hit), another
+    topology (miss), the first one again, new characters of another length (buffers move), weights switched
+    on and off (another kernel variant and publication protocol): always the oracle's numbers."""
+    eng.set_option(eng.OPT_FITCH_WALK, 3)
+    try:
+        T = 40
+        scheds = []
+        for seed in (1, 2):
+            tr = tree.random_tree(T, seed)
+            scheds.append(tree.schedule(tr))
+        for N, cseed in ((5000, 3), (70001, 4)):
+            chars = tree.random_fitch_chars(T, N, 4, cseed, dtype=np.uint8)
+            n_nodes = scheds[0][4]
+            eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+            wants = [oracle.fitch_score_tree(chars, None, s[0], s[4], s[1], s[2], want_sets=True) for s in scheds]
+            for which in (0, 0, 1, 0, 1, 1):
+                ops, ra, rb, rt, nn = scheds[which]
+                assert eng.fitch_score_tree(ops, ra, rb) == wants[which]["length"], (N, which)
+                costs = eng.fitch_get_node_costs()
+                for op in ops:
+                    assert costs[int(op["parent"])] == wants[which]["node_cost"][int(op["parent"])]
+                p = int(ops[-1]["parent"])
+                assert np.array_equal(eng.fitch_get_states(p), wants[which]["prelim"][p])
+            w = np.random.default_rng(N).integers(0, 5, N).astype(float)
+            ops, ra, rb, rt, nn = scheds[0]
+            eng.fitch_set_tips(chars, 4, weights=w, capacity=n_nodes)
+            for _ in range(2):
+                assert eng.fitch_score_tree(ops, ra, rb) == oracle.fitch_score_tree(chars, w, ops, nn, ra, rb)["length"]
+            eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+            for _ in range(2):
+                assert eng.fitch_score_tree(ops, ra, rb) == wants[0]["length"]
+    finally:
+        eng.set_option(eng.OPT_FITCH_WALK, 1)
+
+
 def test_fitch_uppass_final_sets(eng, oracle, fitch_walk):
     ops, ra, rb, n_nodes, chars = _fitch_setup(24, 4099, 4, np.uint8, seed=6)
     eng.fitch_set_tips(chars, 4, capacity=n_nodes)
