@@ -1035,6 +1035,25 @@ def run_workload(ctx, args, key, wl, primary):
         set_mode(mode)
         step()  # leave the engine's site lnL / CLVs in the primary mode's state
 
+    # ---- Fitch, length only (PHYLO_OPT_RETAIN_CLV = 0): what config 2 literally asks for -- no interior set is
+    # written (compulsory bytes: the tips once) and the tree is evaluated from its centre edge (phylo_fitch_reroot)
+    if kind == "fitch" and not args.no_other_modes:
+        modes = {"retain": {"value": value, "ms_per_step": ms / steps, "length": result,
+                            "note": "every interior set written once (the primary figures of this record)"}}
+        eng.set_option(eng.OPT_RETAIN_CLV, 0)
+        for _ in range(3):
+            r_m = step()
+        fl = device_footprint("fitch", T, S, K, mask_dtype(S)().itemsize, mode, n_local) < 8 * L2_BYTES
+        tm, r_m = ctx.timed_steps(step, steps, fl)
+        eng.set_option(eng.OPT_RETAIN_CLV, 1)
+        by = T * 0.5 * n_local
+        modes["length-only"] = {"value": units_per_step * steps / (tm * 1e-3), "ms_per_step": tm / steps, "length": r_m,
+                                "l2_flushed_between_steps": fl, "algorithmic_bytes_per_step": by,
+                                "achieved_gbs_step": by / (tm / steps * 1e-3) / 1e9,
+                                "frac_step": by / (tm / steps * 1e-3) / 1e9 / hbm_peak,
+                                "note": "whole step (launch + result read-back included) against the tips read once"}
+        step()  # leave the interior sets resident again
+
     if p2p:
         eng.set_option(eng.OPT_DEFER_SCALAR, 0)  # what follows is per-rank work that reads local values
     # ---- branch-length re-evaluation loop (BASELINE config 5's second half):

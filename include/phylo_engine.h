@@ -80,7 +80,10 @@ int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256);
  * (warp-autonomous kernel for K <= 4, tile kernel otherwise); 2 = tile kernel only;
  * 0 = one kernel per node. PHYLO_OPT_RETAIN_CLV (default 1): every interior CLV of a
  * score_tree call is left in its node slot (for phylo_lk_get_clv / edge_lnl / incremental
- * re-scoring); 0 = lnL only, the tree-fused kernel then writes no CLV at all. */
+ * re-scoring); 0 = lnL only, the tree-fused kernel then writes no CLV at all. The same option
+ * governs phylo_fitch_score_tree (4 planes, tile kernel): 0 = the length only -- no interior set
+ * is written (the parents' slots are left invalid, their node costs 0) and the tree is evaluated
+ * from its centre edge (phylo_fitch_reroot). */
 #define PHYLO_OPT_FUSED_TREE 1
 #define PHYLO_OPT_RETAIN_CLV 2
 /* PHYLO_OPT_FITCH_WALK selects the whole-tree Fitch kernel: 1 (default) = automatic (4 planes:
@@ -234,6 +237,12 @@ int phylo_lk_param_gradient(phylo_engine *e, const phylo_op *ops, int n_ops, int
  * schedules. */
 int phylo_plan_compile(const phylo_op *ops, int n_ops, int T, int capacity, int root_a, int root_b,
                        int32_t *steps_out, int *depth_out);
+/* Host-only (no GPU needed), for tests and tooling: the schedule phylo_fitch_score_tree evaluates for a
+ * length-only call (PHYLO_OPT_RETAIN_CLV = 0) -- the same unrooted tree, re-rooted on the edge that minimises
+ * the height of its two halves (Fitch length does not depend on the root; the chain of dependent medians
+ * does). ops_out has room for n_ops ops; a schedule that is not one tree comes back unchanged. */
+int phylo_fitch_reroot(const phylo_op *ops, int n_ops, int capacity, int root_a, int root_b, phylo_op *ops_out,
+                       int *root_a_out, int *root_b_out);
 /* phylo_lk_set_tips + phylo_lk_score_tree in one call for an alignment that is still in host
  * memory: the upload is cut into pattern slabs on a second stream and each slab is scored
  * (tree-fused kernel) while the next one is still crossing PCIe. Same result, bit for bit. */

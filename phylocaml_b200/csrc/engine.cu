@@ -64,7 +64,7 @@ static const char *kClassNames[KC_COUNT] = {
 
 // compiled program of the last tile-kernel call (fitch_tile_compile) and what it depends on
 struct FitchTileCache {
-  bool valid = false, weighted = false;
+  bool valid = false, weighted = false, retain = true;
   std::vector<phylo_op> ops;
   int root_a = -1, root_b = -1;
   std::vector<int> pos;                  // schedule op -> position in the program (= index of its cost)
@@ -3498,16 +3498,120 @@ static void fitch_timing_report(phylo_engine *e, unsigned long long *dStamps, in
   fprintf(stderr, "\n");
 }
 
+// Fitch length is independent of where the tree is rooted (a median's cost is symmetric and the total is the
+// minimum number of changes). For a length-only evaluation (PHYLO_OPT_RETAIN_CLV = 0) the schedule is re-rooted on
+// the edge that minimises the height of the two halves: the chain of dependent medians -- what bounds a small
+// alignment -- shrinks from the tree's height under the caller's root (25 for the 64-taxon bench tree) to about
+// half its diameter. The nodes on the path between the new and the old root edge are re-used for the "rest of the
+// tree" sets seen from below; every interior node still gets exactly one median. Returns false (schedule left
+// alone) when a result is never consumed or consumed twice (not one tree).
+static bool fitch_reroot_center(const phylo_op *ops, int n_ops, int ra, int rb, int cap, std::vector<phylo_op> &out,
+                                int *nra, int *nrb) {
+  if (n_ops < 2 || ra == rb) return false;
+  std::vector<int> prod(cap, -1), up(cap, -1), hd(cap, 0), hu(cap, 0);
+  for (int o = 0; o < n_ops; ++o) {
+    const phylo_op &op = ops[o];
+    if (prod[op.parent] >= 0 || up[op.left] >= 0 || up[op.right] >= 0 || op.left == op.right) return false;
+    if (prod[op.left] > o || prod[op.right] > o) return false;
+    prod[op.parent] = o;
+    up[op.left] = op.parent;
+    up[op.right] = op.parent;
+    hd[op.parent] = 1 + std::max(hd[op.left], hd[op.right]);
+  }
+  if (up[ra] >= 0 || up[rb] >= 0) return false;
+  for (int o = 0; o < n_ops; ++o)
+    if (up[ops[o].parent] < 0 && ops[o].parent != ra && ops[o].parent != rb) return false;  // a result nobody consumes
+  up[ra] = rb;
+  up[rb] = ra;
+  hu[ra] = hd[rb];
+  hu[rb] = hd[ra];
+  int best = ra, best_h = std::max(hd[ra], hu[ra]);
+  for (int o = n_ops - 1; o >= 0; --o) {  // parents before children
+    const phylo_op &op = ops[o];
+    hu[op.left] = 1 + std::max(hu[op.parent], hd[op.right]);
+    hu[op.right] = 1 + std::max(hu[op.parent], hd[op.left]);
+    for (int c : {op.left, op.right}) {
+      const int h = std::max(hd[c], hu[c]);
+      if (h < best_h) { best_h = h; best = c; }
+    }
+  }
+  if (best == ra || best == rb) return false;  // already rooted as well as it can be
+  // path best -> p1 -> ... -> pk (pk = ra or rb)
+  std::vector<int> path;
+  std::vector<char> on_path(cap, 0);
+  for (int v = up[best]; ; v = up[v]) {
+    path.push_back(v);
+    on_path[v] = 1;
+    if (v == ra || v == rb) break;
+  }
+  out.clear();
+  out.reserve(n_ops);
+  for (int o = 0; o < n_ops; ++o)
+    if (!on_path[ops[o].parent]) out.push_back(ops[o]);
+  const int top = path.back(), other = top == ra ? rb : ra;
+  int below = path.size() >= 2 ? path[path.size() - 2] : best;  // the path's child of `top`
+  {
+    const phylo_op &op = ops[prod[top]];
+    phylo_op n = op;
+    n.parent = top;
+    n.left = other;
+    n.right = op.left == below ? op.right : op.left;
+    out.push_back(n);
+  }
+  for (int i = (int)path.size() - 2; i >= 0; --i) {
+    const int p = path[i];
+    below = i >= 1 ? path[i - 1] : best;
+    const phylo_op &op = ops[prod[p]];
+    phylo_op n = op;
+    n.parent = p;
+    n.left = path[i + 1];  // holds the set of everything above p
+    n.right = op.left == below ? op.right : op.left;
+    out.push_back(n);
+  }
+  *nra = best;
+  *nrb = path[0];
+  return (int)out.size() == n_ops;
+}
+
+// Host-only view of the re-rooting for tests (no CUDA call).
+extern "C" int phylo_fitch_reroot(const phylo_op *ops, int n_ops, int capacity, int root_a, int root_b, phylo_op *ops_out,
+                                  int *root_a_out, int *root_b_out) {
+  if (n_ops < 0 || (n_ops > 0 && !ops) || capacity < 2 || !ops_out || !root_a_out || !root_b_out) return PHYLO_ERR_ARG;
+  if (root_a < 0 || root_a >= capacity || root_b < 0 || root_b >= capacity) return PHYLO_ERR_ARG;
+  for (int o = 0; o < n_ops; ++o)
+    if (ops[o].parent < 0 || ops[o].parent >= capacity || ops[o].left < 0 || ops[o].left >= capacity || ops[o].right < 0 ||
+        ops[o].right >= capacity)
+      return PHYLO_ERR_ARG;
+  std::vector<phylo_op> out;
+  int a = root_a, b = root_b;
+  if (!fitch_reroot_center(ops, n_ops, root_a, root_b, capacity, out, &a, &b)) {
+    for (int o = 0; o < n_ops; ++o) ops_out[o] = ops[o];
+    *root_a_out = root_a;
+    *root_b_out = root_b;
+    return PHYLO_OK;
+  }
+  for (int o = 0; o < n_ops; ++o) ops_out[o] = out[o];
+  *root_a_out = a;
+  *root_b_out = b;
+  return PHYLO_OK;
+}
+
 // On-chip tile kernel (fitch_tile_kernel): per-warp subtree lists + the medians above the cut,
 // results straight into mapped host memory. Returns PHYLO_OK with *done = false when the
 // schedule does not fit. The compiled program of the last call is kept: scoring the same
 // schedule again (another character set on the same tree, new weights, a benchmark loop) skips
 // the compilation after a memcmp of the ops and a check of every buffer pointer it refers to.
-static int fitch_tile_compile(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, bool *ok) {
+static int fitch_tile_compile(phylo_engine *e, const phylo_op *ops_in, int n_ops, int root_a_in, int root_b_in, bool retain,
+                              bool *ok) {
   *ok = false;
   FitchTileCache &tc = e->tileCache;
   tc.valid = false;
   const int n_tot = n_ops + 1;  // + root-edge join
+  // length only: no set leaves the chip, so the tree may be evaluated from the edge that makes it shallowest
+  const phylo_op *ops = ops_in;
+  int root_a = root_a_in, root_b = root_b_in;
+  std::vector<phylo_op> rerooted;
+  if (!retain && fitch_reroot_center(ops_in, n_ops, root_a_in, root_b_in, e->fcap, rerooted, &root_a, &root_b)) ops = rerooted.data();
   // operands: >= 0 = index into the tile's input rows; < 0 = -1 - (op that produces it)
   std::vector<int> produced(e->fcap, -1), inputs;
   struct Raw { int l, r, out_slot; };
@@ -3606,8 +3710,8 @@ static int fitch_tile_compile(phylo_engine *e, const phylo_op *ops, int n_ops, i
     // rows: an input use has its own row; a result lives in the row of its producer's left operand
     hops[i].l_off = 512u * (uint32_t)row_of(rw.l) | (from_regs[order[i]] ? 1u : 0u);
     hops[i].r_off = 512u * (uint32_t)row_of(rw.r);
-    hops[i].out = rw.out_slot >= 0 ? e->fPre[rw.out_slot] : nullptr;
-    if (rw.out_slot >= 0) remember(rw.out_slot);
+    hops[i].out = (retain && rw.out_slot >= 0) ? e->fPre[rw.out_slot] : nullptr;
+    if (retain && rw.out_slot >= 0) remember(rw.out_slot);
   }
   for (int i = 0; i < n_in; ++i) { hin[i] = e->fPre[inputs[i]]; remember(inputs[i]); }
   for (int w = 0; w < kFitchTileWarps + 2; ++w) hlev[w] = tstart[w];
@@ -3625,16 +3729,17 @@ static int fitch_tile_compile(phylo_engine *e, const phylo_op *ops, int n_ops, i
   a.stamps = nullptr;
   tc.smem = smem;
   tc.weighted = weighted;
-  tc.ops.assign(ops, ops + n_ops);
-  tc.root_a = root_a; tc.root_b = root_b;
+  tc.ops.assign(ops_in, ops_in + n_ops);
+  tc.root_a = root_a_in; tc.root_b = root_b_in;
+  tc.retain = retain;
   tc.valid = inl;  // a program staged through dSched is overwritten by other calls: compiled again next time
   *ok = true;
   return PHYLO_OK;
 }
 
-static bool fitch_tile_cache_hit(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b) {
+static bool fitch_tile_cache_hit(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, bool retain) {
   const FitchTileCache &tc = e->tileCache;
-  if (!tc.valid || (int)tc.ops.size() != n_ops || tc.root_a != root_a || tc.root_b != root_b) return false;
+  if (!tc.valid || (int)tc.ops.size() != n_ops || tc.root_a != root_a || tc.root_b != root_b || tc.retain != retain) return false;
   if (tc.a.nwords != e->fWords || tc.a.N != e->fN || tc.a.wt != e->dFW || tc.a.acc != e->dAcc || tc.a.host_out != e->hCostDev ||
       e->hCostDev == nullptr)
     return false;
@@ -3645,15 +3750,15 @@ static bool fitch_tile_cache_hit(phylo_engine *e, const phylo_op *ops, int n_ops
   return true;
 }
 
-static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
+static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, bool retain,
                                  uint64_t *length_out, bool *done) {
   *done = false;
   const auto ht0 = std::chrono::steady_clock::now();
   auto ht1 = ht0, ht2 = ht0;
   int grid_used = 0, rc;
-  if (!fitch_tile_cache_hit(e, ops, n_ops, root_a, root_b)) {
+  if (!fitch_tile_cache_hit(e, ops, n_ops, root_a, root_b, retain)) {
     bool ok = false;
-    if ((rc = fitch_tile_compile(e, ops, n_ops, root_a, root_b, &ok)) != PHYLO_OK) return rc;
+    if ((rc = fitch_tile_compile(e, ops, n_ops, root_a, root_b, retain, &ok)) != PHYLO_OK) return rc;
     if (!ok) return PHYLO_OK;
   }
   FitchTileCache &tc = e->tileCache;
@@ -3726,7 +3831,11 @@ static int fitch_score_tree_tile(phylo_engine *e, const phylo_op *ops, int n_ops
   uint64_t length = 0;
   for (int i = 0; i < n_tot; ++i) length += e->hCost[i] & mask;
   *length_out = length;
-  for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = e->hCost[tc.pos[o]] & mask; e->fValid[ops[o].parent] = 1; e->fFinValid[ops[o].parent] = 0; }
+  if (retain) {
+    for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = e->hCost[tc.pos[o]] & mask; e->fValid[ops[o].parent] = 1; e->fFinValid[ops[o].parent] = 0; }
+  } else {  // length only: the parents' sets were not written (and the medians may belong to another rooting)
+    for (int o = 0; o < n_ops; ++o) { e->nodeCost[ops[o].parent] = 0; e->fValid[ops[o].parent] = 0; e->fFinValid[ops[o].parent] = 0; }
+  }
   if (a.stamps) {
     const auto ht3 = std::chrono::steady_clock::now();
     auto us = [](auto x, auto y) { return std::chrono::duration<double, std::micro>(y - x).count(); };
@@ -3744,11 +3853,17 @@ extern "C" int phylo_fitch_score_tree(phylo_engine *e, const phylo_op *ops, int 
   if ((rc = fitch_check_schedule(e, ops, n_ops, root_a, root_b, "fitch_score_tree")) != PHYLO_OK) return rc;
   if (!length_out) return fail(e, PHYLO_ERR_ARG, "fitch_score_tree: length_out is NULL");
   CK(cudaSetDevice(e->device));
+  const bool tile_ok = e->fNPdev == 4 && (e->opt_fitch_walk == 3 || e->opt_fitch_walk == 1);
+  if (tile_ok && !e->opt_retain) {  // PHYLO_OPT_RETAIN_CLV = 0: the length only; no interior set is written
+    bool done = false;
+    if ((rc = fitch_score_tree_tile(e, ops, n_ops, root_a, root_b, false, length_out, &done)) != PHYLO_OK) return rc;
+    if (done) return PHYLO_OK;
+  }
   for (int o = 0; o < n_ops; ++o)
     if ((rc = fitch_ensure(e, ops[o].parent, false)) != PHYLO_OK) return rc;
-  if (e->fNPdev == 4 && (e->opt_fitch_walk == 3 || e->opt_fitch_walk == 1)) {
+  if (tile_ok) {
     bool done = false;
-    if ((rc = fitch_score_tree_tile(e, ops, n_ops, root_a, root_b, length_out, &done)) != PHYLO_OK) return rc;
+    if ((rc = fitch_score_tree_tile(e, ops, n_ops, root_a, root_b, true, length_out, &done)) != PHYLO_OK) return rc;
     if (done) return PHYLO_OK;
   }
   if ((rc = fitch_sync_tables(e)) != PHYLO_OK) return rc;

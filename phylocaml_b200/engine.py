@@ -83,6 +83,7 @@ SIGNATURES = {
     "phylo_lk_exchange_reduce": (C.c_int, [_vp, _dp]),
     "phylo_exchange_sum_u64": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "phylo_plan_compile": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int)]),
+    "phylo_fitch_reroot": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "phylo_lk_score_alignment": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, C.c_int, _vp, C.c_int,
                                            C.c_int, C.c_int, C.c_double, _dp]),
     "phylo_lk_edge_lnl": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
@@ -232,6 +233,18 @@ def plan_compile(ops, T, capacity, root_a, root_b):
     if rc != PHYLO_OK:
         raise PhyloError(rc, "phylo_plan_compile: bad arguments")
     return steps, depth.value
+
+
+def fitch_reroot(ops, capacity, root_a, root_b):
+    """(ops', root_a', root_b'): the schedule a length-only phylo_fitch_score_tree evaluates -- the same
+    unrooted tree rooted on its centre edge (host-only; see phylo_fitch_reroot)."""
+    ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+    out = np.zeros(len(ops), dtype=OP_DTYPE)
+    a, b = C.c_int(), C.c_int()
+    rc = load().phylo_fitch_reroot(_p(ops), len(ops), capacity, root_a, root_b, _p(out), C.byref(a), C.byref(b))
+    if rc != PHYLO_OK:
+        raise PhyloError(rc, "phylo_fitch_reroot: bad arguments")
+    return out, a.value, b.value
 
 
 def pack_nibbles(tips, out=None):

@@ -543,6 +543,37 @@ def test_fitch_tile_program_cache(eng, oracle):
         eng.set_option(eng.OPT_FITCH_WALK, 1)
 
 
+def test_fitch_length_only_mode(eng, oracle):
+    """PHYLO_OPT_RETAIN_CLV = 0 for Fitch: the length alone (tree evaluated from its centre edge, no interior
+    set written); the parents' slots are invalid afterwards and a retaining call brings them back."""
+    for T, N, seed in ((64, 100003, 1), (16, 4099, 2), (3, 77, 3), (40, 1, 4)):
+        ops, ra, rb, n_nodes, chars = _fitch_setup(T, N, 4, np.uint8, seed=seed)
+        want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb, want_sets=True)
+        eng.fitch_set_tips(chars, 4, capacity=n_nodes)
+        eng.set_option(eng.OPT_RETAIN_CLV, 0)
+        try:
+            for _ in range(2):
+                assert eng.fitch_score_tree(ops, ra, rb) == want["length"]
+            if len(ops):
+                with pytest.raises(engine.PhyloError):
+                    eng.fitch_get_states(int(ops[-1]["parent"]))
+        finally:
+            eng.set_option(eng.OPT_RETAIN_CLV, 1)
+        assert eng.fitch_score_tree(ops, ra, rb) == want["length"]
+        for op in ops[-3:]:
+            p = int(op["parent"])
+            assert np.array_equal(eng.fitch_get_states(p), want["prelim"][p])
+    # weighted
+    ops, ra, rb, n_nodes, chars = _fitch_setup(20, 9000, 4, np.uint8, seed=9)
+    w = np.random.default_rng(5).integers(0, 7, 9000).astype(float)
+    eng.fitch_set_tips(chars, 4, weights=w, capacity=n_nodes)
+    eng.set_option(eng.OPT_RETAIN_CLV, 0)
+    try:
+        assert eng.fitch_score_tree(ops, ra, rb) == oracle.fitch_score_tree(chars, w, ops, n_nodes, ra, rb)["length"]
+    finally:
+        eng.set_option(eng.OPT_RETAIN_CLV, 1)
+
+
 def test_fitch_uppass_final_sets(eng, oracle, fitch_walk):
     ops, ra, rb, n_nodes, chars = _fitch_setup(24, 4099, 4, np.uint8, seed=6)
     eng.fitch_set_tips(chars, 4, capacity=n_nodes)

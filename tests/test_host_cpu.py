@@ -526,3 +526,35 @@ def test_host_packers_match_numpy(built):
             for i in range(N):
                 v = sum(((int(p3[t, i // 32, s]) >> (i % 32)) & 1) << s for s in range(NP))
                 assert v == int(codes[t, i]) & ((1 << ns) - 1)
+
+
+def test_fitch_reroot_keeps_the_length_and_halves_the_height(oracle):
+    """phylo_fitch_reroot (what a length-only phylo_fitch_score_tree evaluates): the same unrooted tree, every
+    interior node with exactly one median, in post-order, the oracle's Fitch length unchanged, and the chain
+    of dependent medians no longer than before (much shorter for a caterpillar)."""
+    def height(ops, ra, rb):
+        h = {}
+        for op in ops:
+            h[int(op["parent"])] = 1 + max(h.get(int(op["left"]), 0), h.get(int(op["right"]), 0))
+        return max(h.get(ra, 0), h.get(rb, 0))
+
+    cases = [(tree.random_tree(T, seed), T) for T, seed in ((5, 1), (16, 2), (64, 1), (64, 7), (33, 3))]
+    cases += [(tree.caterpillar_tree(40), 40)]
+    for tr, T in cases:
+        ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+        ops2, ra2, rb2 = engine.fitch_reroot(ops, n_nodes, ra, rb)
+        assert sorted(int(p) for p in ops2["parent"]) == sorted(int(p) for p in ops["parent"])
+        done = set(range(T))
+        for op in ops2:
+            assert int(op["left"]) in done and int(op["right"]) in done and int(op["parent"]) not in done
+            done.add(int(op["parent"]))
+        assert ra2 in done and rb2 in done and ra2 != rb2
+        chars = tree.random_fitch_chars(T, 1500, 4, seed=T, dtype=np.uint8)
+        want = oracle.fitch_score_tree(chars, None, ops, n_nodes, ra, rb)["length"]
+        assert oracle.fitch_score_tree(chars, None, ops2, n_nodes, ra2, rb2)["length"] == want
+        assert height(ops2, ra2, rb2) <= height(ops, ra, rb)
+    tr = tree.caterpillar_tree(40)
+    ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+    ops2, ra2, rb2 = engine.fitch_reroot(ops, n_nodes, ra, rb)
+    assert height(ops2, ra2, rb2) <= height(ops, ra, rb) // 2 + 1
+
