@@ -23,6 +23,8 @@ type ids    = (int32, Bigarray.int32_elt, Bigarray.c_layout) Bigarray.Array2.t
 
 external engine_create : int -> engine = "phylo_CAML_engine_create"
 external custom_max : int -> unit = "phylo_CAML_custom_max"      (* cf. bv_CAML_custom_max, bv.c:250-256 *)
+(* PHYLO_OPT_* of include/phylo_engine.h: 2 = retain interior CLVs / state sets (1) or score only (0) *)
+external engine_set_option : engine -> int -> int -> unit = "phylo_CAML_engine_set_option"
 external node_slot : node -> int = "phylo_CAML_node_slot"
 external node_stats : engine -> bool -> int * int * int = "phylo_CAML_node_stats"
 external set_model_ : engine -> matrix -> matrix -> matrix option

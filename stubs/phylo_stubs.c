@@ -81,6 +81,17 @@ CAMLprim value phylo_CAML_engine_create(value vdev)
   CAMLreturn(res);
 }
 
+/* external engine_set_option : engine -> int -> int -> unit = "phylo_CAML_engine_set_option"
+ * (PHYLO_OPT_*: 2 = retain interior CLVs / state sets (1, default) or score only (0: lnL / Fitch length alone,
+ * the fastest form of a candidate evaluation), 1 = tree-fused kernels, 3 = whole-tree Fitch kernel) */
+CAMLprim value phylo_CAML_engine_set_option(value ve, value vopt, value vval)
+{
+  CAMLparam3(ve, vopt, vval);
+  phylo_engine *e = Engine_val(ve);
+  check(e, phylo_engine_set_option(e, Int_val(vopt), (int64_t)Long_val(vval)));
+  CAMLreturn(Val_unit);
+}
+
 /* one process-wide default engine for the reference-named entry points that carry no
  * engine argument (compose_*): created on first use on device 0 */
 static phylo_engine *default_engine(void)
