@@ -813,6 +813,23 @@ def run_workload(ctx, args, key, wl, primary):
         model = make_model(wl)
         base = tree_mod.evolve_tips(tr, model, BASE_PATTERNS, seed=3, dtype=mask_dtype(S))
         packed_base = engine.pack_nibbles(base) if S == 4 and args.upload == "compact" else None
+        # 20 / 61 states, compact upload: one byte per cell -- the alphabet symbol (state index, or S for a missing
+        # cell) -- translated to state masks on the device through the engine's symbol table
+        # (phylo_engine_set_symbol_table, what an Alphabet.t supplies); 4 / 8 times fewer PCIe bytes than the masks
+        sym_base, sym_table = None, None
+        if S > 4 and S < 255 and args.upload == "compact":
+            b64 = base.astype(np.uint64)
+            full = np.uint64((1 << S) - 1)
+            idx = np.full(b64.shape, 255, dtype=np.uint8)
+            for st in range(S):
+                idx[b64 == np.uint64(1 << st)] = st
+            idx[b64 == full] = S
+            if not np.any(idx == 255):  # no partial ambiguity codes in this alignment
+                sym_base = idx
+                sym_table = np.zeros(256, dtype=np.uint64)
+                for st in range(S):
+                    sym_table[st] = np.uint64(1 << st)
+                sym_table[S] = full
 
         def host_shard(lo_, n_):
             """this rank's slab of the host alignment in the upload format (pinned)"""
@@ -821,6 +838,10 @@ def run_workload(ctx, args, key, wl, primary):
                 t = engine.pinned_empty((T, (n_ + 1) // 2), np.uint8)
                 tile_cols(packed_base, lo_ // 2, t.shape[1], out=t)
                 return t, n_, "packed 4-bit masks, 0.5 B per cell (mask_bytes = 0)"
+            if sym_base is not None:
+                t = engine.pinned_empty((T, n_), np.uint8)
+                tile_cols(sym_base, lo_, n_, out=t)
+                return t, None, "1-byte alphabet symbols, translated by the engine's symbol table (phylo_engine_set_symbol_table)"
             t = engine.pinned_empty((T, n_), mask_dtype(S))
             tile_cols(base, lo_, n_, out=t)
             return t, None, "%d-byte state masks" % t.dtype.itemsize
@@ -828,6 +849,8 @@ def run_workload(ctx, args, key, wl, primary):
         tips, packed_n, upload_note = host_shard(lo, n_local)
         sample_of = lambda ns: tile_cols(base, lo, ns)
         eng.lk_set_model(model)
+        if sym_table is not None:
+            eng.set_symbol_table(sym_table)
 
         def set_mode(m):
             eng.set_option(eng.OPT_FUSED_TREE, 0 if m == "pernode" else 1)

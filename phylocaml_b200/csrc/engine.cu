@@ -102,6 +102,7 @@ struct phylo_engine {
   uint32_t *dTcm = nullptr;            // general-TCM median table: 2^S x 2^S entries (cost | median << 16)
   int tcmS = 0;
   size_t capAcc = 0, tileSmem = 0;
+  uint32_t *dTipSlab = nullptr;            // Fitch: the T tip plane buffers as rows of one allocation (one 2-D upload)
   FitchTileCache tileCache;                // compiled tile-kernel program of the last fitch_score_tree call
   unsigned long long *hCostDev = nullptr;  // device view of the mapped hCost
   unsigned long long *dStamps = nullptr;   // PHYLO_FITCH_TIMING=1 only
@@ -380,6 +381,9 @@ static void sankoff_free_data(phylo_engine *e) {
 }
 
 static void fitch_free_data(phylo_engine *e) {
+  if (e->dTipSlab)  // the tips' plane buffers are rows of one allocation
+    for (int t = 0; t < e->fT && t < (int)e->fPre.size(); ++t) e->fPre[t] = nullptr;
+  dfree(e->dTipSlab);
   for (auto &p : e->fPre) dfree(p);
   for (auto &p : e->fFin) dfree(p);
   e->fPre.clear();
@@ -3198,6 +3202,12 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
     e->nodeCost.assign(capacity, 0);
     CK(cudaMalloc(&e->dPreTab, sizeof(uint32_t *) * capacity));
     CK(cudaMalloc(&e->dFinTab, sizeof(uint32_t *) * capacity));
+    // the tips' buffers: rows of one slab (padded to whole 32-word tiles like fitch_ensure's), so that an upload in
+    // the device layout is two 2-D copies instead of T small ones
+    const size_t tip_row_words = (size_t)((e->fWords + 31) / 32) * 32 * e->fNPdev;
+    CK(cudaMalloc(&e->dTipSlab, sizeof(uint32_t) * tip_row_words * (size_t)T));
+    CK(cudaMemsetAsync(e->dTipSlab, 0, sizeof(uint32_t) * tip_row_words * (size_t)T, e->stream));
+    for (int t = 0; t < T; ++t) e->fPre[t] = e->dTipSlab + (size_t)t * tip_row_words;
     e->tabDirty = true;
   }
   int rc;
@@ -3221,9 +3231,20 @@ extern "C" int phylo_fitch_set_tips_pitched(phylo_engine *e, int T, int64_t N, i
       e->slabEvents.push_back(ev);
     }
     const size_t hp = host_pitch_bytes ? (size_t)host_pitch_bytes : plane_row;
-    for (int t = 0; t < T; ++t)
-      CK(cudaMemcpyAsync(e->fPre[t], (const char *)codes + (size_t)t * hp, plane_row, cudaMemcpyHostToDevice,
-                         (t & 1) ? e->copyStream2 : e->copyStream));
+    const size_t dev_pitch = sizeof(uint32_t) * (size_t)((e->fWords + 31) / 32) * 32 * e->fNPdev;
+    if (e->dTipSlab && e->fPre[0] == e->dTipSlab && plane_row * (size_t)T <= ((size_t)64 << 20)) {
+      // small alignments: T copies of a few hundred KB each pay ~3 us of DMA set-up apiece; two 2-D copies of
+      // T/2 rows (one per queue) do not
+      const int h = (T + 1) / 2;
+      CK(cudaMemcpy2DAsync(e->dTipSlab, dev_pitch, codes, hp, plane_row, (size_t)h, cudaMemcpyHostToDevice, e->copyStream));
+      if (T > h)
+        CK(cudaMemcpy2DAsync((char *)e->dTipSlab + (size_t)h * dev_pitch, dev_pitch, (const char *)codes + (size_t)h * hp, hp,
+                             plane_row, (size_t)(T - h), cudaMemcpyHostToDevice, e->copyStream2));
+    } else {
+      for (int t = 0; t < T; ++t)
+        CK(cudaMemcpyAsync(e->fPre[t], (const char *)codes + (size_t)t * hp, plane_row, cudaMemcpyHostToDevice,
+                           (t & 1) ? e->copyStream2 : e->copyStream));
+    }
     CK(cudaEventRecord(e->slabEvents[0], e->copyStream));
     CK(cudaEventRecord(e->slabEvents[1], e->copyStream2));
     CK(cudaStreamWaitEvent(e->stream, e->slabEvents[0], 0));
