@@ -512,8 +512,8 @@ class Ctx:
 
 def run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src):
     """raw alignment (host) -> unique site patterns + weights (host), through
-    phylo_compress_patterns. A step = one whole alignment; single GPU (sites could be sharded, but
-    the merge of per-shard tables is not built)."""
+    phylo_compress_patterns. A step = one whole alignment on one GPU; with several GPUs visible the record
+    gains a `group` block (phylo_group_compress_patterns: slabs of sites per device, tables merged on device 0)."""
     T, N = wl["T"], args.patterns or wl["N"]
     if args.taxa:
         T = args.taxa
@@ -580,6 +580,19 @@ def run_compress(args, wl, torch, engine, tree_mod, local, hbm_peak, peak_src):
         "gpu_launches": int(eng.launch_count - l0), "clocks": clocks,
         "check": {"patterns": int(P), "weights_sum": float(wt.sum()), "equals_oracle_on_first_1M_sites": full_ok},
     }
+    # several GPUs in this process: the same alignment through phylo_group_compress_patterns (slabs of sites on
+    # every device, per-slab tables merged on device 0); must reproduce the single-device result exactly
+    ndev = torch.cuda.device_count()
+    if ndev > 1:
+        g = engine.Group(list(range(ndev)))
+        gp, gw, gs = g.compress_patterns(raw)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            gp, gw, gs = g.compress_patterns(raw)
+        gms = 1e3 * (time.perf_counter() - t0) / steps
+        line["group"] = {"devices": ndev, "ms_per_step_end_to_end": gms, "sites_per_s": N / (gms * 1e-3),
+                         "equals_single_device": bool(np.array_equal(gp, pats) and np.array_equal(gw, wt) and np.array_equal(gs, s2p))}
+        g.close()
     print(json.dumps(line))
     eng.close()
 

@@ -312,6 +312,11 @@ int phylo_exchange_sum_u64(phylo_engine *e, uint64_t value, uint64_t *sum_out);
 int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
                             const double *weights_in, void *patterns_out, double *weights_out,
                             int32_t *site_to_pattern, int64_t *n_patterns);
+/* The same for a column slab of a wider host matrix: row t starts at masks + t * host_pitch_bytes
+ * (0 = dense rows). */
+int phylo_compress_patterns_pitched(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                    uint64_t host_pitch_bytes, const double *weights_in, void *patterns_out,
+                                    double *weights_out, int32_t *site_to_pattern, int64_t *n_patterns);
 
 /* -------------------------- NonAdditive node data / Bitvector (lib/nonAdditive_c.ml) ---- */
 /* T taxa x N characters, one character per element of elt_bytes (W/8, W in {8,16,32,64},
@@ -464,6 +469,12 @@ int phylo_group_fitch_score_tree(phylo_group *g, const phylo_op *ops, int n_ops,
                                  int root_b, uint64_t *length_out);
 int phylo_group_fitch_uppass(phylo_group *g, const phylo_op *ops, int n_ops, int root_a, int root_b);
 int phylo_group_fitch_get_states(phylo_group *g, int node, int which, void *out);
+/* phylo_compress_patterns over all devices of the group: every device compresses a contiguous slab of sites,
+ * device 0 merges the slabs' pattern tables (a second pass with their weights as input). Patterns, weights and the
+ * site map are identical to those of one device for the whole alignment. */
+int phylo_group_compress_patterns(phylo_group *g, int T, int64_t N, const void *masks, int mask_bytes,
+                                  const double *weights_in, void *patterns_out, double *weights_out,
+                                  int32_t *site_to_pattern, int64_t *n_patterns);
 
 #ifdef __cplusplus
 }

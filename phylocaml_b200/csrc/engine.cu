@@ -2714,7 +2714,19 @@ static void launch_cmp_gather(const uint8_t *in, int T, int64_t N, const int *re
 extern "C" int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
                                        const double *weights_in, void *patterns_out, double *weights_out,
                                        int32_t *site_to_pattern, int64_t *n_patterns) {
+  return phylo_compress_patterns_pitched(e, T, N, masks, mask_bytes, 0, weights_in, patterns_out, weights_out,
+                                         site_to_pattern, n_patterns);
+}
+
+// host_pitch_bytes != 0: row t of the host alignment starts at masks + t * host_pitch_bytes (a column slab of a
+// wider matrix: what phylo_group_compress_patterns hands each device)
+extern "C" int phylo_compress_patterns_pitched(phylo_engine *e, int T, int64_t N, const void *masks, int mask_bytes,
+                                               uint64_t host_pitch_bytes, const double *weights_in, void *patterns_out,
+                                               double *weights_out, int32_t *site_to_pattern, int64_t *n_patterns) {
   if (!e) return PHYLO_ERR_ARG;
+  if (host_pitch_bytes != 0 && N > 0 && mask_bytes > 0 && host_pitch_bytes < (uint64_t)N * (uint64_t)mask_bytes)
+    return fail(e, PHYLO_ERR_ARG, "compress_patterns: host pitch %llu is shorter than a row of %lld cells",
+                (unsigned long long)host_pitch_bytes, (long long)N);
   if (T < 1 || N < 1 || N > 2000000000ll || !masks || !patterns_out || !weights_out || !n_patterns ||
       !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
     return fail(e, PHYLO_ERR_ARG, "compress_patterns: bad arguments (T=%d N=%lld mask_bytes=%d)", T, (long long)N, mask_bytes);
@@ -2750,7 +2762,10 @@ extern "C" int phylo_compress_patterns(phylo_engine *e, int T, int64_t N, const 
   uint32_t *dSlot = (uint32_t *)(arena + pSlot.off);
   double *dWout = (double *)(arena + pWout.off), *dWin = weights_in ? (double *)(arena + pWin.off) : nullptr;
   cudaStream_t st = e->stream;
-  CK(cudaMemcpyAsync(dIn, masks, (size_t)T * N * EB, cudaMemcpyHostToDevice, st));
+  if (host_pitch_bytes == 0 || host_pitch_bytes == (uint64_t)N * EB)
+    CK(cudaMemcpyAsync(dIn, masks, (size_t)T * N * EB, cudaMemcpyHostToDevice, st));
+  else
+    CK(cudaMemcpy2DAsync(dIn, (size_t)N * EB, masks, (size_t)host_pitch_bytes, (size_t)N * EB, (size_t)T, cudaMemcpyHostToDevice, st));
   if (weights_in) CK(cudaMemcpyAsync(dWin, weights_in, 8 * (size_t)N, cudaMemcpyHostToDevice, st));
   if (e->dSymTab) {  // the cells are alphabet symbols: translate in place, patterns come out as state masks
     ProfScope prof(e, KC_COMPRESS);

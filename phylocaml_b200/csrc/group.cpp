@@ -409,3 +409,73 @@ extern "C" int phylo_group_fitch_get_states(phylo_group *g, int node, int which,
     return phylo_fitch_get_states(g->eng[i], node, which, (char *)out + (size_t)g->fitch.lo[i] * g->felt);
   }, "group_fitch_get_states");
 }
+
+// Site-pattern compression over all devices: every device compresses a contiguous slab of
+// sites (first stage, concurrently), then the per-slab pattern tables -- tiny next to the alignment -- are merged by
+// one more pass on device 0 with the slabs' weights as input weights (second stage). Slabs are in site order and each
+// table is in first-occurrence order, so the merged table is in the alignment's first-occurrence order: patterns,
+// weights (exact for the integer-valued weights the reference uses) and the site map are identical to what one
+// device returns for the whole alignment.
+extern "C" int phylo_group_compress_patterns(phylo_group *g, int T, int64_t N, const void *masks, int mask_bytes,
+                                             const double *weights_in, void *patterns_out, double *weights_out,
+                                             int32_t *site_to_pattern, int64_t *n_patterns) {
+  if (!g) return PHYLO_ERR_ARG;
+  if (T < 1 || N < 1 || !masks || !patterns_out || !weights_out || !n_patterns ||
+      !(mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4 || mask_bytes == 8))
+    return gfail(g, PHYLO_ERR_ARG, "group_compress_patterns: bad arguments");
+  const int n = (int)g->eng.size();
+  if (n == 1 || N < 4096 * (int64_t)n)
+    return phylo_compress_patterns(g->eng[0], T, N, masks, mask_bytes, weights_in, patterns_out, weights_out,
+                                   site_to_pattern, n_patterns) == PHYLO_OK
+               ? PHYLO_OK
+               : gfail(g, PHYLO_ERR_CUDA, std::string("group_compress_patterns: ") + phylo_last_error(g->eng[0]));
+  try {
+    Shards sh;
+    cut(sh, N, n, 1024);
+    const size_t EB = (size_t)mask_bytes, pitch = (size_t)N * EB;
+    std::vector<std::vector<unsigned char>> pats(n);
+    std::vector<std::vector<double>> wts(n);
+    std::vector<std::vector<int32_t>> maps(n);
+    std::vector<int64_t> np(n, 0);
+    int rc = fan_out(g, [&](int i) { return sh.hi[i] > sh.lo[i]; }, [&](int i) {
+      const int64_t ns = sh.hi[i] - sh.lo[i];
+      pats[i].resize((size_t)T * ns * EB);
+      wts[i].resize((size_t)ns);
+      maps[i].resize((size_t)ns);
+      return phylo_compress_patterns_pitched(g->eng[i], T, ns, (const char *)masks + (size_t)sh.lo[i] * EB, mask_bytes, pitch,
+                                             weights_in ? weights_in + sh.lo[i] : nullptr, pats[i].data(), wts[i].data(),
+                                             maps[i].data(), &np[i]);
+    }, "group_compress_patterns");
+    if (rc != PHYLO_OK) return rc;
+    // second stage: the slabs' tables side by side ([T][sum of P_i]), their weights as input weights
+    int64_t tot = 0;
+    std::vector<int64_t> off(n + 1, 0);
+    for (int i = 0; i < n; ++i) { off[i] = tot; tot += np[i]; }
+    off[n] = tot;
+    std::vector<unsigned char> cat((size_t)T * tot * EB);
+    std::vector<double> wcat((size_t)tot);
+    for (int i = 0; i < n; ++i) {
+      for (int t = 0; t < T; ++t)
+        std::memcpy(cat.data() + ((size_t)t * tot + off[i]) * EB, pats[i].data() + (size_t)t * np[i] * EB, (size_t)np[i] * EB);
+      std::copy(wts[i].begin(), wts[i].begin() + np[i], wcat.begin() + off[i]);
+    }
+    std::vector<int32_t> map2((size_t)tot);
+    std::vector<unsigned char> out2((size_t)T * tot * EB);
+    std::vector<double> w2((size_t)tot);
+    int64_t P = 0;
+    rc = fan_out(g, [&](int i) { return i == 0; }, [&](int) {
+      return phylo_compress_patterns(g->eng[0], T, tot, cat.data(), mask_bytes, wcat.data(), out2.data(), w2.data(), map2.data(), &P);
+    }, "group_compress_patterns");
+    if (rc != PHYLO_OK) return rc;
+    std::memcpy(patterns_out, out2.data(), (size_t)T * P * EB);
+    std::copy(w2.begin(), w2.begin() + P, weights_out);
+    if (site_to_pattern)
+      for (int i = 0; i < n; ++i)
+        for (int64_t s = sh.lo[i]; s < sh.hi[i]; ++s) site_to_pattern[s] = map2[(size_t)(off[i] + maps[i][(size_t)(s - sh.lo[i])])];
+    *n_patterns = P;
+    return PHYLO_OK;
+  } catch (const std::exception &ex) {
+    return gfail(g, PHYLO_ERR_CUDA, std::string("group_compress_patterns: host exception: ") + ex.what());
+  }
+}
+

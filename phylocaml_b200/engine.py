@@ -92,6 +92,8 @@ SIGNATURES = {
     "phylo_tcm_median_2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_tcm_score_tree": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "phylo_compress_patterns": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, _vp, _dp, _vp, C.POINTER(_i64)]),
+    "phylo_compress_patterns_pitched": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, C.c_uint64, _dp, _vp, _dp, _vp, C.POINTER(_i64)]),
+    "phylo_group_compress_patterns": (C.c_int, [_vp, C.c_int, _i64, _vp, C.c_int, _dp, _vp, _dp, _vp, C.POINTER(_i64)]),
     "phylo_lk_edge_prepare": (C.c_int, [_vp, C.c_int, C.c_int]),
     "phylo_lk_edge_eval": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp, _dp]),
     "phylo_lk_optimize_branch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -845,3 +847,18 @@ class Group:
         out = np.empty(self.fitch_shape[1], dtype=self.fitch_dtype)
         self._ck(self.lib.phylo_group_fitch_get_states(self.h, node, 1 if final else 0, _p(out)))
         return out
+
+    def compress_patterns(self, masks, weights=None):
+        """Engine.compress_patterns over all devices of the group (slabs of sites, merged on device 0)."""
+        masks = np.ascontiguousarray(masks)
+        T, N = masks.shape
+        out = np.empty((T, N), dtype=masks.dtype)
+        w_out = np.empty(N)
+        s2p = np.empty(N, dtype=np.int32)
+        n = _i64()
+        w_in = None if weights is None else _f64(weights)
+        self._ck(self.lib.phylo_group_compress_patterns(self.h, T, N, _p(masks), masks.dtype.itemsize,
+                                                        None if w_in is None else _p(w_in, _dp), _p(out), _p(w_out, _dp),
+                                                        _p(s2p), C.byref(n)))
+        P = n.value
+        return np.ascontiguousarray(out.reshape(-1)[:T * P].reshape(T, P)), w_out[:P].copy(), s2p

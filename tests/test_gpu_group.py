@@ -114,3 +114,21 @@ def test_group_over_all_visible_gpus(oracle, built):
     finally:
         g.close()
         e.close()
+
+
+@pytest.mark.parametrize("dtype,T,N", [(np.uint8, 24, 50000), (np.uint32, 9, 20011), (np.uint8, 5, 3000)])
+def test_group_compression_equals_one_engine(eng, group3, dtype, T, N):
+    """phylo_group_compress_patterns (slabs of sites on every device, tables merged on device 0) returns the same
+    patterns (first-occurrence order), weights and site map as one engine on the whole alignment -- and as the
+    numpy oracle; N = 3000 is below the sharding threshold (one engine does it)."""
+    from oracle.oracle import compress_patterns
+
+    rng = np.random.default_rng(N)
+    distinct = rng.integers(1, 16, (T, 700)).astype(dtype)
+    masks = np.ascontiguousarray(distinct[:, rng.integers(0, 700, N)])
+    for weights in (None, rng.integers(1, 4, N).astype(float)):
+        one = eng.compress_patterns(masks, weights)
+        many = group3.compress_patterns(masks, weights)
+        orc = compress_patterns(masks, weights)
+        for a, b, c in zip(one, many, orc):
+            assert np.array_equal(a, b) and np.array_equal(b, c)

@@ -80,3 +80,29 @@ def test_uppass_argument_errors(eng):
     bad[parent] = -1
     with pytest.raises(RuntimeError):
         eng.lk_uppass(ops, ra, rb, rt, bad)
+
+
+@pytest.mark.parametrize("K,N", [(1, 777), (2, 3000), (4, 1024 * 1024 + 5), (8, 2100)])
+def test_batched_joins_equal_single_joins_bitwise(eng, oracle, K, N):
+    """phylo_lk_edge_lnl_batch for 4 states is one launch over all (edge, 1024-pattern block) work items; every
+    edge's lnL must be the single-join value bit for bit (same arithmetic, same canonical fold), for every rate-class
+    count the batch kernel is instantiated for, tip and CLV operands, ragged N, and more than one fold level
+    (N > 1024 * 1024 patterns: the level-1 partials of one edge no longer fit one block)."""
+    from helpers import GTR_CO, GTR_PI
+    from phylocaml_b200 import mlmodel
+    model = mlmodel.create(("GTR", GTR_CO), 4, pi=GTR_PI, site_var=("gamma", K, 0.5) if K > 1 else None)
+    T = 6 if N > 100000 else 11
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(T, N, model, seed=13, mean_bl=0.2)
+    up_slot, cap, up_ops, edges = tree.uppass_plan(ops, ra, rb, rt, n_nodes)
+    w = np.random.default_rng(4).integers(1, 3, N).astype(float)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, weights=w, capacity=cap)
+    lnl = eng.lk_score_tree(ops, ra, rb, rt)
+    eng.lk_uppass(ops, ra, rb, rt, up_slot)
+    ea, eb = [e[0] for e in edges], [e[1] for e in edges]
+    ts = [e[2] * (1.0 + 0.1 * i) for i, e in enumerate(edges)]  # not the tree's own lengths: every edge a different P(t)
+    batch = eng.lk_edge_lnl_batch(ea, eb, ts)
+    for i, (v, u, _) in enumerate(edges):
+        assert batch[i] == eng.lk_edge_lnl(v, u, [ts[i]])[0], (K, i)
+    own = eng.lk_edge_lnl_batch(ea, eb, [e[2] for e in edges])
+    assert np.max(np.abs(own - lnl)) <= 1e-11 * abs(lnl)
