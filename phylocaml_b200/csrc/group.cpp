@@ -4,12 +4,16 @@
 // on PHYLO_LNL_BLOCK boundaries, scalar results combined on the host (block partials folded by
 // phylo_reduce_partials => lnL bit-identical to one engine; integer lengths summed exactly).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
 #include <exception>
 #include <functional>
 #include <mutex>
+#include <memory>
 #include <new>
 #include <string>
 #include <thread>
@@ -430,23 +434,30 @@ extern "C" int phylo_group_compress_patterns(phylo_group *g, int T, int64_t N, c
                ? PHYLO_OK
                : gfail(g, PHYLO_ERR_CUDA, std::string("group_compress_patterns: ") + phylo_last_error(g->eng[0]));
   try {
+    static const bool timing = [] { const char *v = getenv("PHYLO_GROUP_TIMING"); return v && v[0] == '1'; }();
+    const auto tt0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+      if (timing) fprintf(stderr, "[group compress] %s: +%.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count());
+    };
     Shards sh;
     cut(sh, N, n, 1024);
     const size_t EB = (size_t)mask_bytes, pitch = (size_t)N * EB;
-    std::vector<std::vector<unsigned char>> pats(n);
-    std::vector<std::vector<double>> wts(n);
-    std::vector<std::vector<int32_t>> maps(n);
+    // worst-case sized but never zero-filled: only the P_i patterns a slab really has are ever touched
+    std::vector<std::unique_ptr<unsigned char[]>> pats(n);
+    std::vector<std::unique_ptr<double[]>> wts(n);
+    std::vector<std::unique_ptr<int32_t[]>> maps(n);
     std::vector<int64_t> np(n, 0);
     int rc = fan_out(g, [&](int i) { return sh.hi[i] > sh.lo[i]; }, [&](int i) {
       const int64_t ns = sh.hi[i] - sh.lo[i];
-      pats[i].resize((size_t)T * ns * EB);
-      wts[i].resize((size_t)ns);
-      maps[i].resize((size_t)ns);
+      pats[i].reset(new unsigned char[(size_t)T * ns * EB]);
+      wts[i].reset(new double[(size_t)ns]);
+      maps[i].reset(new int32_t[(size_t)ns]);
       return phylo_compress_patterns_pitched(g->eng[i], T, ns, (const char *)masks + (size_t)sh.lo[i] * EB, mask_bytes, pitch,
-                                             weights_in ? weights_in + sh.lo[i] : nullptr, pats[i].data(), wts[i].data(),
-                                             maps[i].data(), &np[i]);
+                                             weights_in ? weights_in + sh.lo[i] : nullptr, pats[i].get(), wts[i].get(),
+                                             maps[i].get(), &np[i]);
     }, "group_compress_patterns");
     if (rc != PHYLO_OK) return rc;
+    lap("stage 1 done");
     // second stage: the slabs' tables side by side ([T][sum of P_i]), their weights as input weights
     int64_t tot = 0;
     std::vector<int64_t> off(n + 1, 0);
@@ -456,9 +467,10 @@ extern "C" int phylo_group_compress_patterns(phylo_group *g, int T, int64_t N, c
     std::vector<double> wcat((size_t)tot);
     for (int i = 0; i < n; ++i) {
       for (int t = 0; t < T; ++t)
-        std::memcpy(cat.data() + ((size_t)t * tot + off[i]) * EB, pats[i].data() + (size_t)t * np[i] * EB, (size_t)np[i] * EB);
-      std::copy(wts[i].begin(), wts[i].begin() + np[i], wcat.begin() + off[i]);
+        std::memcpy(cat.data() + ((size_t)t * tot + off[i]) * EB, pats[i].get() + (size_t)t * np[i] * EB, (size_t)np[i] * EB);
+      std::copy(wts[i].get(), wts[i].get() + np[i], wcat.begin() + off[i]);
     }
+    lap("tables concatenated");
     std::vector<int32_t> map2((size_t)tot);
     std::vector<unsigned char> out2((size_t)T * tot * EB);
     std::vector<double> w2((size_t)tot);
@@ -467,12 +479,14 @@ extern "C" int phylo_group_compress_patterns(phylo_group *g, int T, int64_t N, c
       return phylo_compress_patterns(g->eng[0], T, tot, cat.data(), mask_bytes, wcat.data(), out2.data(), w2.data(), map2.data(), &P);
     }, "group_compress_patterns");
     if (rc != PHYLO_OK) return rc;
+    lap("stage 2 done");
     std::memcpy(patterns_out, out2.data(), (size_t)T * P * EB);
     std::copy(w2.begin(), w2.begin() + P, weights_out);
     if (site_to_pattern)
       for (int i = 0; i < n; ++i)
         for (int64_t s = sh.lo[i]; s < sh.hi[i]; ++s) site_to_pattern[s] = map2[(size_t)(off[i] + maps[i][(size_t)(s - sh.lo[i])])];
     *n_patterns = P;
+    lap("site map merged");
     return PHYLO_OK;
   } catch (const std::exception &ex) {
     return gfail(g, PHYLO_ERR_CUDA, std::string("group_compress_patterns: host exception: ") + ex.what());
