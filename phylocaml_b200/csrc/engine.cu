@@ -1723,6 +1723,8 @@ static cudaError_t launch_treem(phylo_engine *e, TreeMArgs args, size_t smem) {
   auto kern = lk_treem_kernel<S, MaskT, R, NW, KT>;
   static const bool paired = [] { const char *v = getenv("PHYLO_TREEM_PAIRED"); return !(v && v[0] == '0'); }();
   args.paired = paired ? 1 : 0;
+  static const bool st_swap = [] { const char *v = getenv("PHYLO_TREEM_STSWAP"); return !(v && v[0] == '0'); }();
+  args.st_swap = st_swap ? 1 : 0;
   args.prog_in_smem = smem + treem_prog_bytes(args.n_steps) <= 227 * 1024;
   if (args.prog_in_smem) smem += treem_prog_bytes(args.n_steps);
   cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

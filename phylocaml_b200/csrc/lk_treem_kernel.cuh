@@ -82,6 +82,7 @@ struct TreeMArgs {
   // it then spent at the step's barrier, [2] steps, [3] cycles of the body spent waiting for the tables; variants: T+T, T+C, T+G, C+G, G+G, root. NULL = off
   unsigned long long *timing;
   int prog_in_smem;  // the launch reserved treem_prog_bytes(n_steps) of shared memory behind the buffers
+  int st_swap;       // 20 states: conflict-free order of the result stores (measurement switch PHYLO_TREEM_STSWAP=0)
   int paired;        // 20 states: CLV+CLV steps share every A-fragment read between the warp's two groups (measurement switch PHYLO_TREEM_PAIRED=0)
 };
 
@@ -186,6 +187,13 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
   double *curbase = spi + ((S + 15) & ~15);  // 128-byte aligned: the groups' running CLVs are TMA store sources
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fc = lane & 3;
+  // st_order: a lane stores its two pattern rows (2 fc, 2 fc + 1 of the dense [k][8][PITCH] TMA source) with two
+  // 128-bit stores. In row order the eight lanes of a quarter warp hit 16-byte bank groups (4 fc + fr) mod 8:
+  // fc = 0 / 2 and fc = 1 / 3 collide (2-way conflicts: 815 M extra wavefronts in r02_ncu_treem_aa_v9.txt). With the
+  // lanes fc >= 2 storing the odd row first the groups are 0, 4, 2, 6 (+ fr), then 2, 6, 0, 4: conflict-free, same
+  // bytes to the same addresses.
+  const bool st_swap = fc >= 2 && a.st_swap;
+  const uint32_t st_first = st_swap ? (uint32_t)PITCH * 8u : 0u, st_second = (uint32_t)PITCH * 8u - st_first;
   const int gsz = K * 8 * PITCH;  // doubles of one group's running CLV
   for (int idx = tid; idx < NW * R * gsz; idx += NW * 32) curbase[idx] = 0.0;  // pad columns stay 0
   for (int i = tid; i < S; i += NW * 32) spi[i] = a.pi[i];
@@ -469,14 +477,15 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
                   const double b0 = cx[r][1][0] * cy[r][1][0], b1 = cx[r][1][1] * cy[r][1][1];
                   const double d0 = cx[r][2][0] * cy[r][2][0], d1 = cx[r][2][1] * cy[r][2][1];
                   const uint32_t c0_s = cur_s + (uint32_t)(r * gsz + (k * 8 + 2 * fc) * PITCH + 2 * fr) * 8u;
-                  sts128_s(c0_s, a0, b0);
-                  sts128_s(c0_s + PITCH * 8u, a1, b1);
+                  // lanes with fc >= 2 store their odd pattern row first (see st_order below): conflict-free banks
+                  sts128_s(c0_s + st_first, st_swap ? a1 : a0, st_swap ? b1 : b0);
+                  sts128_s(c0_s + st_second, st_swap ? a0 : a1, st_swap ? b0 : b1);
                   hh0[r] = max(hh0[r], max(hi32(a0), hi32(b0)));
                   hh1[r] = max(hh1[r], max(hi32(a1), hi32(b1)));
                   if (fr < 4) {
                     double *c0 = cur + r * gsz + (k * 8 + 2 * fc) * PITCH;
-                    c0[16 + fr] = d0;
-                    c0[PITCH + 16 + fr] = d1;
+                    c0[(st_first >> 3) + 16 + fr] = st_swap ? d1 : d0;
+                    c0[(st_second >> 3) + 16 + fr] = st_swap ? d0 : d1;
                     hh0[r] = max(hh0[r], hi32(d0));
                     hh1[r] = max(hh1[r], hi32(d1));
                   }
@@ -667,13 +676,13 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
                     const double b0 = cx[1][0] * cy[1][0], b1 = cx[1][1] * cy[1][1];
                     const double d0 = cx[2][0] * cy[2][0], d1 = cx[2][1] * cy[2][1];
                     const uint32_t c0_s = cur_s + (uint32_t)(r * gsz + (k * 8 + 2 * fc) * PITCH + 2 * fr) * 8u;
-                    sts128_s(c0_s, a0, b0);
-                    sts128_s(c0_s + PITCH * 8u, a1, b1);
+                    sts128_s(c0_s + st_first, st_swap ? a1 : a0, st_swap ? b1 : b0);
+                    sts128_s(c0_s + st_second, st_swap ? a0 : a1, st_swap ? b0 : b1);
                     h0 = max(h0, max(hi32(a0), hi32(b0)));
                     h1 = max(h1, max(hi32(a1), hi32(b1)));
                     if (fr < 4) {
-                      c0[16 + fr] = d0;
-                      c1[16 + fr] = d1;
+                      c0[(st_first >> 3) + 16 + fr] = st_swap ? d1 : d0;
+                      c0[(st_second >> 3) + 16 + fr] = st_swap ? d0 : d1;
                       h0 = max(h0, hi32(d0));
                       h1 = max(h1, hi32(d1));
                     }
