@@ -700,6 +700,44 @@ def test_fused_tree_kernel_variants_bitwise(eng, tune, K, monkeypatch):
         assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
 
 
+@pytest.mark.parametrize("tune", [None, "1,2,0", "1,1,1"])
+@pytest.mark.parametrize("K,codes,missing", [(4, 0.3, 0.05), (4, 0.0, 0.0), (4, 0.0, 0.6), (4, 0.002, 0.01),
+                                             (2, 0.2, 0.1), (1, 0.2, 0.1)])
+def test_fused_tree_tip_tables_any_state_set_bitwise(eng, oracle, K, codes, missing, tune, monkeypatch):
+    """A TIP operand of the warp-autonomous kernel is a lookup in the branch's tip table (single states and the
+    missing cell) or, for other IUPAC-style state sets, the general expression read from the same table: every mix
+    of the three -- none missing, mostly missing, a few partial sets among single states (one such lane sends its
+    warp down the arithmetic path), many partial sets -- gives the per-node path's lnL, site lnL, CLVs and scale
+    counters bit for bit, and the oracle's lnL."""
+    sv = ("gamma", K, 0.6) if K > 1 else None
+    m = mlmodel.create(("GTR", [1.0, 2.5, 0.8, 1.2, 3.0]), 4, pi=[0.3, 0.2, 0.25, 0.25], site_var=sv)
+    T, N = 48, 9000 + 37
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(T, N, m, seed=52, mean_bl=0.25, missing=missing)
+    rng = np.random.default_rng(9)
+    amb = rng.random((T, N)) < codes
+    tips = np.where(amb, tips | rng.integers(1, 16, size=(T, N), dtype=np.uint8), tips).astype(np.uint8)
+    if tune:
+        monkeypatch.setenv("PHYLO_TREEW_TUNE", tune)
+    eng.profile(True)
+    try:
+        a, fa = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=1)
+        site_a = eng.lk_get_site_lnl()
+        clv_a = [eng.lk_get_clv(int(op["parent"])) for op in ops]
+        c, fc = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=1, retain=0)
+        if tune:
+            monkeypatch.delenv("PHYLO_TREEW_TUNE")
+        b, fb = _score(eng, m, tips, ops, ra, rb, rt, n_nodes, fused=0, retain=1)
+        site_b = eng.lk_get_site_lnl()
+        clv_b = [eng.lk_get_clv(int(op["parent"])) for op in ops]
+    finally:
+        eng.profile(False)
+    assert fa and fc and not fb and a == b == c
+    assert np.array_equal(site_a, site_b)
+    for (ca, sa), (cb, sb) in zip(clv_a, clv_b):
+        assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
+    assert rel_err(a, oracle.lk_score_tree(m, tips, None, ops, n_nodes, ra, rb, rt)["lnl"]) <= LNL_RTOL
+
+
 @pytest.mark.parametrize("K", [1, 2, 8])
 def test_fused_tree_other_rate_counts(eng, oracle, K):
     sv = ("gamma", K, 0.8) if K > 1 else None
