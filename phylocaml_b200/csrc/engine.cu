@@ -18,6 +18,7 @@
 #include <atomic>
 #include <chrono>
 #include <string>
+#include <numeric>
 #include <vector>
 
 #include "fitch_kernels.cuh"
@@ -1638,6 +1639,21 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     // streams, so their tails overlap. A rank of an 8-GPU run holds 512 blocks: 8 slabs instead of the 2 that a
     // 256-block minimum gave it -- with 2 slabs upload and scoring barely overlapped: e2e 6.2 ms for 3.2 ms of work)
     int nslab = (int)std::max<int64_t>(1, std::min<int64_t>(16, blocks / 64));
+    // The warp-autonomous kernel hands a launch's units (R groups of 32 patterns) to sm_count x warps warps in
+    // rounds; a CTA leaves when its slowest warp is done. A slab of 244 blocks (4 M patterns in 16 slabs) is 3.3
+    // rounds: every CTA stays for 4 while 5 of its 8 warps idle through the last one. So a slab is a whole number
+    // of rounds (74 blocks each with 148 SMs x 8 warps x 2 groups) whenever that is close to the size wanted.
+    int64_t slab_blocks = 0;  // 0: nslab equal parts
+    if (useW) {
+      const int64_t round_units = (int64_t)e->sm_count * geo.warps, block_units = kLnlBlock / (32 * geo.R);
+      const int64_t q = round_units / std::gcd(round_units, block_units);  // blocks in the smallest whole-round slab
+      const int64_t want = blocks / nslab;
+      if (nslab > 1 && q <= want + want / 2) {
+        slab_blocks = std::max<int64_t>(1, (want + q / 2) / q) * q;
+        nslab = (int)((blocks + slab_blocks - 1) / slab_blocks);
+        if (nslab > 1 && blocks - (int64_t)(nslab - 1) * slab_blocks < q / 2) --nslab;  // a small rest joins the last slab
+      }
+    }
     if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
     if (!e->copyStream2) CK(cudaStreamCreateWithFlags(&e->copyStream2, cudaStreamNonBlocking));
     if (!e->auxStream) CK(cudaStreamCreateWithFlags(&e->auxStream, cudaStreamNonBlocking));
@@ -1656,7 +1672,8 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
       // consecutive slabs alternate between two compute streams so that the tail of one
       // slab's kernel overlaps the head of the next
       cudaStream_t cs = (sidx & 1) ? e->auxStream : e->stream;
-      const int64_t b_lo = blocks * sidx / nslab, b_hi = blocks * (sidx + 1) / nslab;
+      const int64_t b_lo = slab_blocks ? slab_blocks * sidx : blocks * sidx / nslab;
+      const int64_t b_hi = slab_blocks ? (sidx + 1 == nslab ? blocks : slab_blocks * (sidx + 1)) : blocks * (sidx + 1) / nslab;
       const int64_t p_lo = b_lo * kLnlBlock, p_hi = std::min<int64_t>(e->N, b_hi * kLnlBlock);
       if ((rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, (sidx & 1) ? e->copyStream2 : e->copyStream,
                                e->slabEvents[sidx], cs)) != PHYLO_OK)
