@@ -1746,13 +1746,16 @@ static cudaError_t launch_treem(phylo_engine *e, TreeMArgs args, size_t smem) {
   if (args.prog_in_smem) smem += treem_prog_bytes(args.n_steps);
   cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (st != cudaSuccess) return st;
-  const int64_t ngroups = (e->N + 7) / 8;
+  const int64_t ngroups = args.g_end - args.g_begin;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(e->sm_count, (ngroups + NW * R - 1) / (NW * R)));
   kern<<<grid, NW * 32, smem, e->stream>>>(args);
   return cudaGetLastError();
 }
 
-static int lk_score_tree_fusedm(phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt, bool *done) {
+// host_masks != NULL (phylo_lk_score_alignment): the alignment is still on the host; it is uploaded in three slabs
+// on a copy stream while the slabs before are scored.
+static int lk_score_tree_fusedm(phylo_engine *e, const phylo_op *ops, int n_ops, int ra, int rb, double rt, bool *done,
+                                const void *host_masks = nullptr, int mask_bytes = 0) {
   *done = false;
   if (!e->opt_fused || !(e->S == 20 || e->S == 61) || n_ops < 1) return PHYLO_OK;
   if (e->S == 20 && !e->encodeTiled) return PHYLO_OK;  // its results leave through TMA tensor maps
@@ -1850,7 +1853,35 @@ static int lk_score_tree_fusedm(phylo_engine *e, const phylo_op *ops, int n_ops,
     CK(cudaMemsetAsync(dTiming, 0, 24 * sizeof(unsigned long long), e->stream));
     a.timing = dTiming;
   }
-  {
+  // Slabs (host_masks): whole rounds of the kernel's CTA chunks (NW x R groups of 8 patterns on every SM), so that no
+  // slab ends on a partly filled round: q = blocks of 1024 patterns in the smallest such slab. The link is ~10 times
+  // faster than the scoring (config 4: 4.8 MB against 1.1 ms per round), so a short first slab is all that stays
+  // exposed: slabs of q, 2 q and the rest.
+  const int64_t ng_all = (e->N + 7) / 8, blocks = e->nPart;
+  int64_t slab_end[3] = {blocks, blocks, blocks};
+  int nslab = 1;
+  if (host_masks) {
+    const int64_t round_pats = (int64_t)e->sm_count * NW * R * 8;
+    const int64_t q = round_pats / std::gcd(round_pats, (int64_t)kLnlBlock);
+    if (blocks >= 4 * q) {
+      nslab = 3;
+      slab_end[0] = q;
+      slab_end[1] = 3 * q;
+    }
+    if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+    while ((int)e->slabEvents.size() < nslab) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->slabEvents.push_back(ev);
+    }
+  }
+  for (int sidx = 0; sidx < nslab; ++sidx) {
+    const int64_t p_lo = sidx ? slab_end[sidx - 1] * kLnlBlock : 0, p_hi = std::min<int64_t>(e->N, slab_end[sidx] * kLnlBlock);
+    if (host_masks &&
+        (rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, e->copyStream, e->slabEvents[sidx], e->stream)) != PHYLO_OK)
+      return rc;
+    a.g_begin = p_lo / 8;
+    a.g_end = sidx + 1 == nslab ? ng_all : p_hi / 8;
     ProfScope prof(e, KC_TREE_FUSED);
     cudaError_t st;
 #define TREEM(S_, M_, R_, NW_, KT_) launch_treem<S_, M_, R_, NW_, KT_>(e, a, treem_smem_bytes<S_>(e->K, R_, NW_))
@@ -2576,7 +2607,11 @@ extern "C" int phylo_lk_score_alignment(phylo_engine *e, int T, int64_t N, const
     lk_free_data(e);
     return rc;
   }
-  if (!done) {  // not eligible for the fused kernel: plain upload, then the per-node path
+  if (!done && (rc = lk_score_tree_fusedm(e, ops, n_ops, root_a, root_b, root_t, &done, masks, mask_bytes)) != PHYLO_OK) {
+    lk_free_data(e);  // (20 / 61 states: the tree-fused DMMA kernel, slabs uploaded while the ones before are scored)
+    return rc;
+  }
+  if (!done) {  // not eligible for the fused kernels: plain upload, then the per-node path
     if ((rc = lk_upload_slab(e, masks, mask_bytes, 0, N, nullptr, nullptr, e->stream)) != PHYLO_OK) { lk_free_data(e); return rc; }
     if ((rc = lk_check_bad(e, "lk_score_alignment")) != PHYLO_OK) return rc;
     return phylo_lk_score_tree(e, ops, n_ops, root_a, root_b, root_t, lnl_out);

@@ -71,6 +71,7 @@ struct TreeMArgs {
   const double *frags;  // [2 n_steps + 1][K][MT][KS][32]: left, right of step 0, 1, ...; last: root edge
   const void *tips;     // MaskT [T][tip_stride]
   int64_t tip_stride, N;
+  int64_t g_begin, g_end;  // this launch's 8-pattern groups (a slab of phylo_lk_score_alignment; the whole alignment: 0, ceil(N / 8))
   double *const *node_clv;
   int32_t *const *node_sc;
   const double *pi, *probs, *weights;
@@ -224,8 +225,8 @@ __global__ void __launch_bounds__(NW * 32, 1) lk_treem_kernel(const TreeMArgs a)
   unsigned long long cur_ptr = lane < 6 ? slot_ptr(a.prog[0]) : 0ull;
   __syncthreads();
 
-  const int64_t ngroups = (a.N + 7) / 8;
-  const int64_t g0 = ngroups * blockIdx.x / gridDim.x, g1 = ngroups * (blockIdx.x + 1) / gridDim.x;
+  const int64_t ngroups = a.g_end - a.g_begin;
+  const int64_t g0 = a.g_begin + ngroups * blockIdx.x / gridDim.x, g1 = a.g_begin + ngroups * (blockIdx.x + 1) / gridDim.x;
   const int nst = a.n_steps + 1;
   constexpr int CH = NW * R;
   const int64_t nchunks = (g1 - g0 + CH - 1) / CH;

@@ -819,6 +819,37 @@ def test_lk_score_alignment_pipelined_equals_two_calls(eng, N):
     assert ei.value.code == -4
 
 
+@pytest.mark.parametrize("S,N", [(20, 2100), (20, 160000 + 13), (61, 152000 + 5)])
+def test_lk_score_alignment_large_alphabets_slabs_equal_two_calls(eng, S, N):
+    """20 / 61 states through phylo_lk_score_alignment: the tree-fused DMMA kernel launched slab by slab (whole rounds
+    of its CTA chunks: 37 blocks, 74, the rest) while the later slabs are still being uploaded == set_tips + score_tree,
+    bit for bit (lnL, site lnL, the last CLV and its scale counters); a bad cell in the last slab is still reported."""
+    from helpers import aa_model, codon_model
+    model = aa_model(4) if S == 20 else codon_model()
+    T = 6
+    tr = tree.random_tree(T, 3)
+    ops, ra, rb, rt, n_nodes = tree.schedule(tr)
+    base = tree.evolve_tips(tr, model, 3000, seed=4, dtype=mask_dtype(S))
+    tips = np.ascontiguousarray(np.tile(base, (1, N // 3000 + 1))[:, :N])
+    w = np.random.default_rng(1).integers(1, 4, N).astype(float)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, weights=w, capacity=n_nodes)
+    two = eng.lk_score_tree(ops, ra, rb, rt)
+    site_two = eng.lk_get_site_lnl()
+    clv_two = eng.lk_get_clv(int(ops[-1]["parent"]))
+    eng.lk_set_tips(np.ascontiguousarray(tips[:, ::-1]), weights=w, capacity=n_nodes)  # clobber device state
+    one = eng.lk_score_alignment(tips, ops, ra, rb, rt, weights=w, capacity=n_nodes)
+    assert one == two
+    assert np.array_equal(eng.lk_get_site_lnl(), site_two)
+    clv_one = eng.lk_get_clv(int(ops[-1]["parent"]))
+    assert np.array_equal(clv_one[0], clv_two[0]) and np.array_equal(clv_one[1], clv_two[1])
+    bad = tips.copy()
+    bad[3, N - 5] = 0
+    with pytest.raises(engine.PhyloError) as ei:
+        eng.lk_score_alignment(bad, ops, ra, rb, rt, capacity=n_nodes)
+    assert ei.value.code == -4
+
+
 # ------------------------------------------------------------ compact upload formats ----
 @pytest.mark.parametrize("N", [1, 2, 33, 1024, 1025, 70001])
 @pytest.mark.parametrize("pinvar", [None, 0.15])
