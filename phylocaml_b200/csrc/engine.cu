@@ -1643,15 +1643,21 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
     // rounds; a CTA leaves when its slowest warp is done. A slab of 244 blocks (4 M patterns in 16 slabs) is 3.3
     // rounds: every CTA stays for 4 while 5 of its 8 warps idle through the last one. So a slab is a whole number
     // of rounds (74 blocks each with 148 SMs x 8 warps x 2 groups) whenever that is close to the size wanted.
-    int64_t slab_blocks = 0;  // 0: nslab equal parts
+    // The first slab's upload is the part of the transfer nothing hides: the slabs grow from one round to the
+    // size wanted (q, 2 q, ... blocks).
+    std::vector<int64_t> slab_end;  // empty: nslab equal parts
     if (useW) {
       const int64_t round_units = (int64_t)e->sm_count * geo.warps, block_units = kLnlBlock / (32 * geo.R);
       const int64_t q = round_units / std::gcd(round_units, block_units);  // blocks in the smallest whole-round slab
       const int64_t want = blocks / nslab;
       if (nslab > 1 && q <= want + want / 2) {
-        slab_blocks = std::max<int64_t>(1, (want + q / 2) / q) * q;
-        nslab = (int)((blocks + slab_blocks - 1) / slab_blocks);
-        if (nslab > 1 && blocks - (int64_t)(nslab - 1) * slab_blocks < q / 2) --nslab;  // a small rest joins the last slab
+        const int64_t full = std::max<int64_t>(1, (want + q / 2) / q) * q;
+        for (int64_t cur = 0, step = q; cur < blocks; step = std::min(step + q, full)) {
+          cur = std::min(blocks, cur + step);
+          if (blocks - cur < q / 2) cur = blocks;  // a small rest joins the last slab
+          slab_end.push_back(cur);
+        }
+        nslab = (int)slab_end.size();
       }
     }
     if (!e->copyStream) CK(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
@@ -1672,8 +1678,8 @@ static int lk_score_tree_fused(phylo_engine *e, const phylo_op *ops, int n_ops, 
       // consecutive slabs alternate between two compute streams so that the tail of one
       // slab's kernel overlaps the head of the next
       cudaStream_t cs = (sidx & 1) ? e->auxStream : e->stream;
-      const int64_t b_lo = slab_blocks ? slab_blocks * sidx : blocks * sidx / nslab;
-      const int64_t b_hi = slab_blocks ? (sidx + 1 == nslab ? blocks : slab_blocks * (sidx + 1)) : blocks * (sidx + 1) / nslab;
+      const int64_t b_lo = slab_end.empty() ? blocks * sidx / nslab : (sidx ? slab_end[sidx - 1] : 0);
+      const int64_t b_hi = slab_end.empty() ? blocks * (sidx + 1) / nslab : slab_end[sidx];
       const int64_t p_lo = b_lo * kLnlBlock, p_hi = std::min<int64_t>(e->N, b_hi * kLnlBlock);
       if ((rc = lk_upload_slab(e, host_masks, mask_bytes, p_lo, p_hi, (sidx & 1) ? e->copyStream2 : e->copyStream,
                                e->slabEvents[sidx], cs)) != PHYLO_OK)
