@@ -2359,17 +2359,44 @@ extern "C" int phylo_sankoff_get_costs(phylo_engine *e, int node, int32_t *out) 
 // ---- model-parameter derivatives (lk_grad_kernels.cuh)
 // matrices of one branch for the gradient kernel: P_k = exp(Q t r_k), then for every parameter p
 // d/d theta_p exp(Q t r_k) = dexp_X[D], X = Q t r_k, D = t (r_k dQ_p + drates_p[k] Q)
-static void grad_branch_matrices(const phylo_engine *e, double t, int np, const double *dQ, const double *drates,
+struct GradHost {  // per-call constants of grad_branch_matrices: G_p = Vinv dQ_p V and scratch
+  std::vector<double> Gp, W, mid, x, ex;
+  GradHost(const phylo_engine *e, int np, const double *dQ) {
+    const int S = e->S;
+    const size_t ss = (size_t)S * S;
+    const double *V = e->hV.data(), *Vi = e->hVinv.data();
+    Gp.assign((size_t)np * ss, 0.0);
+    W.resize(ss); mid.resize(ss); x.resize(S); ex.resize(S);
+    for (int p = 0; p < np && dQ; ++p) {
+      const double *dq = dQ + (size_t)p * ss;
+      for (int m = 0; m < S; ++m)
+        for (int j = 0; j < S; ++j) {
+          double a = 0.0;
+          for (int i = 0; i < S; ++i) a += Vi[(size_t)m * S + i] * dq[(size_t)i * S + j];
+          W[(size_t)m * S + j] = a;
+        }
+      for (int m = 0; m < S; ++m)
+        for (int n = 0; n < S; ++n) {
+          double a = 0.0;
+          for (int j = 0; j < S; ++j) a += W[(size_t)m * S + j] * V[(size_t)j * S + n];
+          Gp[(size_t)p * ss + (size_t)m * S + n] = a;
+        }
+    }
+  }
+};
+
+static void grad_branch_matrices(const phylo_engine *e, GradHost &h, double t, int np, const double *drates,
                                  double *out /* [(np+1)][K][S][S] */) {
   const int S = e->S, K = e->K;
   const size_t ss = (size_t)S * S;
   const double *V = e->hV.data(), *Vi = e->hVinv.data(), *lam = e->hLam.data();
-  std::vector<double> G(ss), W(ss), x(S), ex(S);
-  auto sandwich = [&](const double *mid, double *dst) {  // dst = V mid Vinv
+  double *W = h.W.data(), *mid = h.mid.data(), *x = h.x.data(), *ex = h.ex.data();
+  const double *Gp = h.Gp.data();
+  auto sandwich = [&](const double *md, double *dst) {  // dst = V md Vinv
     for (int i = 0; i < S; ++i)
       for (int n = 0; n < S; ++n) {
         double a = 0.0;
-        for (int m = 0; m < S; ++m) a += V[(size_t)i * S + m] * mid[(size_t)m * S + n];
+        for (int m = 0; m < S; ++m) a += V[(size_t)i * S + m] * md[(size_t)m * S + n];
         W[(size_t)i * S + n] = a;
       }
     for (int i = 0; i < S; ++i)
@@ -2379,30 +2406,12 @@ static void grad_branch_matrices(const phylo_engine *e, double t, int np, const 
         dst[(size_t)i * S + j] = a;
       }
   };
-  // G_p = Vinv dQ_p V, once per parameter (independent of branch and class; recomputed per branch here: S^3, tiny)
-  std::vector<double> Gp((size_t)np * ss, 0.0), mid(ss);
-  for (int p = 0; p < np; ++p) {
-    if (!dQ) break;
-    const double *dq = dQ + (size_t)p * ss;
-    for (int m = 0; m < S; ++m)
-      for (int j = 0; j < S; ++j) {
-        double a = 0.0;
-        for (int i = 0; i < S; ++i) a += Vi[(size_t)m * S + i] * dq[(size_t)i * S + j];
-        W[(size_t)m * S + j] = a;
-      }
-    for (int m = 0; m < S; ++m)
-      for (int n = 0; n < S; ++n) {
-        double a = 0.0;
-        for (int j = 0; j < S; ++j) a += W[(size_t)m * S + j] * V[(size_t)j * S + n];
-        Gp[(size_t)p * ss + (size_t)m * S + n] = a;
-      }
-  }
   for (int k = 0; k < K; ++k) {
     const double tau = t * e->hRates[k];
     for (int m = 0; m < S; ++m) { x[m] = lam[m] * tau; ex[m] = std::exp(x[m]); }
-    std::fill(mid.begin(), mid.end(), 0.0);
+    std::fill(mid, mid + ss, 0.0);
     for (int m = 0; m < S; ++m) mid[(size_t)m * S + m] = ex[m];
-    sandwich(mid.data(), out + (size_t)k * ss);
+    sandwich(mid, out + (size_t)k * ss);
     for (int p = 0; p < np; ++p) {
       const double dr = drates ? drates[(size_t)p * K + k] : 0.0;
       for (int m = 0; m < S; ++m)
@@ -2414,9 +2423,119 @@ static void grad_branch_matrices(const phylo_engine *e, double t, int np, const 
           const double phi = (m == n || std::fabs(dx) < 1e-9) ? 0.5 * (ex[m] + ex[n]) : (ex[m] - ex[n]) / dx;
           mid[(size_t)m * S + n] = phi * d;
         }
-      sandwich(mid.data(), out + ((size_t)(1 + p) * K + k) * ss);
+      sandwich(mid, out + ((size_t)(1 + p) * K + k) * ss);
     }
   }
+}
+
+// A fragments of param_grad4_mma_kernel for parameters q0 .. q0 + nq - 1 of every branch: [branch][K][4][32], lane
+// (row = lane / 4, c = lane % 4) of k-step (k, s) holds row's coefficient of a_k[s] b_k[c]; row 0 = the likelihood,
+// row 1 + q = parameter q0 + q (the prior's derivative enters at branch 0 = the root edge), other rows zero.
+static void grad_fill_afrag(const phylo_engine *e, const std::vector<double> &hm, size_t per_branch, int n_edges, int q0,
+                            int nq, const double *dpi, double *out) {
+  const int K = e->K;
+  for (int i = 0; i < n_edges; ++i) {
+    const double *m = hm.data() + (size_t)i * per_branch;
+    for (int k = 0; k < K; ++k)
+      for (int s = 0; s < 4; ++s)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int row = lane >> 2, c = lane & 3;
+          const double P = m[(size_t)k * 16 + s * 4 + c];
+          double v = 0.0;
+          if (row == 0) {
+            v = e->hProbs[k] * (e->hPi[s] * P);
+          } else if (row <= nq) {
+            const int q = q0 + row - 1;
+            v = e->hPi[s] * m[((size_t)(1 + q) * K + k) * 16 + s * 4 + c];
+            if (i == 0 && dpi) v += dpi[(size_t)q * 4 + s] * P;
+            v *= e->hProbs[k];
+          }
+          out[(((size_t)i * K + k) * 4 + s) * 32 + lane] = v;
+        }
+  }
+}
+
+template <typename GetOperands>
+static int grad4_mma_path(phylo_engine *e, const std::vector<double> &hm, size_t per_branch, int n_edges, int n_params,
+                          const double *dpi, double *lnl_out, double *grad_out, GetOperands operands) {
+  const int K = e->K;
+  const int64_t nb = e->nPart;
+  std::vector<EdgeJoin> he(n_edges);
+  for (int i = 0; i < n_edges; ++i) {
+    Operand a, b;
+    const int rc = operands(i, &a, &b);
+    if (rc != PHYLO_OK) return rc;
+    he[i] = EdgeJoin{a.src, b.src, a.scale, b.scale, a.tip ? 1 : 0, b.tip ? 1 : 0};
+  }
+  constexpr int kRows = 7;  // parameters per pass (row 0 of the 8-row tile is the likelihood)
+  const int nq_max = std::min(n_params, kRows);
+  // branches per launch: the per-branch block results stay below 256 MB
+  const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(n_edges, ((int64_t)256 << 20) / (8 * nq_max * nb)));
+  auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t descBytes = up256(sizeof(EdgeJoin) * n_edges), fragBytes = up256(sizeof(double) * (size_t)n_edges * K * 128),
+               gpBytes = up256(sizeof(double) * (size_t)chunk * nq_max * nb), outBytes = up256(sizeof(double) * (size_t)n_params * nb);
+  const size_t bytes = descBytes + fragBytes + gpBytes + outBytes;
+  if (bytes > e->capEdgeArena) {
+    dfree(e->dEdgeArena);
+    e->capEdgeArena = 0;
+    if (cudaMalloc(&e->dEdgeArena, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(e, PHYLO_ERR_CUDA, "lk_param_gradient: cannot allocate %zu bytes of device memory", bytes);
+    }
+    e->capEdgeArena = bytes;
+  }
+  char *arena = e->dEdgeArena;
+  EdgeJoin *dE = (EdgeJoin *)arena;
+  double *dA = (double *)(arena + descBytes), *dGp = (double *)(arena + descBytes + fragBytes),
+         *dOut = (double *)(arena + descBytes + fragBytes + gpBytes);
+  cudaMemcpyAsync(dE, he.data(), sizeof(EdgeJoin) * n_edges, cudaMemcpyHostToDevice, e->stream);
+  cudaMemsetAsync(dOut, 0, sizeof(double) * (size_t)n_params * nb, e->stream);
+  std::vector<double> ha((size_t)n_edges * K * 128);
+  for (int q0 = 0; q0 < n_params; q0 += kRows) {
+    const int nq = std::min(kRows, n_params - q0);
+    if (q0 > 0) CK(cudaStreamSynchronize(e->stream));  // `ha` is reused by the next pass
+    grad_fill_afrag(e, hm, per_branch, n_edges, q0, nq, dpi, ha.data());
+    cudaMemcpyAsync(dA, ha.data(), sizeof(double) * ha.size(), cudaMemcpyHostToDevice, e->stream);
+    const size_t smem = sizeof(double) * ((size_t)nq * kLnlBlock + 32);
+    for (int e0 = 0; e0 < n_edges; e0 += chunk) {
+      const int ne = std::min(chunk, n_edges - e0);
+      {
+        ProfScope prof(e, KC_EDGE);
+        const int g = (int)std::min<int64_t>(nb * ne, (int64_t)e->sm_count * 16);
+#define GM(KV)                                                                                                            \
+  {                                                                                                                       \
+    auto kern = param_grad4_mma_kernel<KV>;                                                                               \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                   \
+    kern<<<g, 256, smem, e->stream>>>(dE + e0, ne, dA + (size_t)e0 * KV * 128, nq, e->dPi, e->pinvar,                     \
+                                      (const uint8_t *)e->dInv, e->dWeights, dGp, e->N);                                  \
+  }
+        switch (K) {
+          case 1: GM(1) break;
+          case 2: GM(2) break;
+          case 4: GM(4) break;
+          default: GM(8)
+        }
+#undef GM
+        ++e->launches;
+      }
+      {
+        ProfScope prof(e, KC_REDUCE);
+        const int64_t cols = (int64_t)nq * nb;
+        grad_sum_branches_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, e->stream>>>(dGp, ne, cols, dOut + (size_t)q0 * nb);
+        ++e->launches;
+      }
+    }
+  }
+  std::vector<double> hg((size_t)n_params * nb);
+  const cudaError_t st = cudaMemcpyAsync(hg.data(), dOut, sizeof(double) * hg.size(), cudaMemcpyDeviceToHost, e->stream);
+  const cudaError_t st2 = cudaStreamSynchronize(e->stream);
+  const cudaError_t le = cudaGetLastError();
+  if (st != cudaSuccess || st2 != cudaSuccess || le != cudaSuccess)
+    return fail(e, PHYLO_ERR_CUDA, "lk_param_gradient: %s", cudaGetErrorString(st != cudaSuccess ? st : st2 != cudaSuccess ? st2 : le));
+  for (int p = 0; p < n_params; ++p) grad_out[p] = phylo_reduce_partials(hg.data() + (size_t)p * nb, nb);
+  if (lnl_out) *lnl_out = e->hScalar[0];
+  if (e->prof_on) prof_resolve_lazy(e);
+  return PHYLO_OK;
 }
 
 extern "C" int phylo_lk_param_gradient(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b,
@@ -2447,7 +2566,21 @@ extern "C" int phylo_lk_param_gradient(phylo_engine *e, const phylo_op *ops, int
     }
   }
   std::vector<double> hm(per_branch * edges.size());
-  for (size_t i = 0; i < edges.size(); ++i) grad_branch_matrices(e, edges[i].t, n_params, dQ, drates, hm.data() + i * per_branch);
+  {
+    GradHost gh(e, n_params, dQ);  // (G_p once per call, not per branch)
+    for (size_t i = 0; i < edges.size(); ++i) grad_branch_matrices(e, gh, edges[i].t, n_params, drates, hm.data() + i * per_branch);
+  }
+  // 4 states: all branches in one launch on the fp64 tensor cores (param_grad4_mma_kernel), seven parameters per
+  // pass; PHYLO_GRAD_MMA=0 keeps the scalar per-branch kernel below (measurement / cross-check only)
+  {
+    const char *sw = std::getenv("PHYLO_GRAD_MMA");
+    if (S == 4 && (K == 1 || K == 2 || K == 4 || K == 8) && e->mask_dev_bytes == 1 && !(sw && sw[0] == '0'))
+      return grad4_mma_path(e, hm, per_branch, (int)edges.size(), n_params, dpi, lnl_out, grad_out,
+                            [&](int i, Operand *a, Operand *b) {
+                              int r = lk_operand(e, edges[i].a, a, "lk_param_gradient");
+                              return r != PHYLO_OK ? r : lk_operand(e, edges[i].b, b, "lk_param_gradient");
+                            });
+  }
   double *dM = nullptr, *dG = nullptr, *dDpi = nullptr;
   const size_t gdoubles = (size_t)n_params * e->nPart;
   auto cleanup = [&] { cudaFree(dM); cudaFree(dG); cudaFree(dDpi); };

@@ -114,3 +114,37 @@ def test_gradient_20_states_generic_kernel(eng):
 
     fd = richardson(f, 2e-4)
     assert abs(grad[0] - fd) <= 2e-6 * max(1.0, abs(fd)), (grad[0], fd)
+
+
+@pytest.mark.parametrize("K,pinvar,N", [(4, None, 2999), (4, 0.2, 1025), (1, None, 700), (2, None, 1024), (8, None, 333)])
+def test_tensor_core_gradient_equals_the_scalar_kernel(eng, monkeypatch, K, pinvar, N):
+    """4 states: param_grad4_mma_kernel (every branch in one launch, DMMA, seven parameters per pass) against the
+    scalar per-branch kernel (PHYLO_GRAD_MMA=0) -- nine parameters (two passes) mixing rate-matrix, rate and
+    prior directions, weights, ragged pattern counts, tip and interior branches. Only the summation order inside
+    a DMMA differs."""
+    rng = np.random.default_rng(K * 100 + N)
+    sv = ("gamma", K, 0.6) if pinvar is None else ("theta", K, 0.6, pinvar)
+    model = mlmodel.create(("GTR", list(GTR_CO)), 4, pi=list(GTR_PI), site_var=sv) if K > 1 else \
+        mlmodel.create(("GTR", list(GTR_CO)), 4, pi=list(GTR_PI))
+    ops, ra, rb, rt, up_slot, tips, w, cap = _prepare(eng, model, 13, N, seed=K + N)
+    n_params = 9
+    dQ = rng.standard_normal((n_params, 4, 4))
+    dQ -= dQ.sum(axis=2, keepdims=True) * np.eye(4)  # rows of a rate-matrix direction sum to zero
+    drates = rng.standard_normal((n_params, K))
+    dpi = None
+    if pinvar is None:
+        dpi = rng.standard_normal((n_params, 4))
+        dpi -= dpi.mean(axis=1, keepdims=True)
+    eng.lk_score_tree(ops, ra, rb, rt)
+    eng.lk_uppass(ops, ra, rb, rt, up_slot)
+    monkeypatch.setenv("PHYLO_GRAD_MMA", "0")
+    want = eng.lk_param_gradient(ops, ra, rb, rt, up_slot, dQ=dQ, drates=drates, dpi=dpi)
+    monkeypatch.setenv("PHYLO_GRAD_MMA", "1")
+    launches = eng.launch_count
+    got = eng.lk_param_gradient(ops, ra, rb, rt, up_slot, dQ=dQ, drates=drates, dpi=dpi)
+    assert eng.launch_count - launches == 4  # two passes: gradient kernel + branch sum each
+    assert np.all(np.isfinite(got))
+    scale = np.maximum(1.0, np.abs(want))
+    assert np.max(np.abs(got - want) / scale) <= 1e-10, (got, want)
+    # deterministic: the same call returns the same bits
+    assert np.array_equal(got, eng.lk_param_gradient(ops, ra, rb, rt, up_slot, dQ=dQ, drates=drates, dpi=dpi))
