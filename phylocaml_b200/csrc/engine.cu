@@ -2496,19 +2496,14 @@ static int grad4_mma_path(phylo_engine *e, const std::vector<double> &hm, size_t
     if (q0 > 0) CK(cudaStreamSynchronize(e->stream));  // `ha` is reused by the next pass
     grad_fill_afrag(e, hm, per_branch, n_edges, q0, nq, dpi, ha.data());
     cudaMemcpyAsync(dA, ha.data(), sizeof(double) * ha.size(), cudaMemcpyHostToDevice, e->stream);
-    const size_t smem = sizeof(double) * ((size_t)nq * kLnlBlock + 32);
     for (int e0 = 0; e0 < n_edges; e0 += chunk) {
       const int ne = std::min(chunk, n_edges - e0);
       {
         ProfScope prof(e, KC_EDGE);
         const int g = (int)std::min<int64_t>(nb * ne, (int64_t)e->sm_count * 16);
 #define GM(KV)                                                                                                            \
-  {                                                                                                                       \
-    auto kern = param_grad4_mma_kernel<KV>;                                                                               \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                   \
-    kern<<<g, 256, smem, e->stream>>>(dE + e0, ne, dA + (size_t)e0 * KV * 128, nq, e->dPi, e->pinvar,                     \
-                                      (const uint8_t *)e->dInv, e->dWeights, dGp, e->N);                                  \
-  }
+  param_grad4_mma_kernel<KV><<<g, 256, 0, e->stream>>>(dE + e0, ne, dA + (size_t)e0 * KV * 128, nq, e->dPi, e->pinvar,    \
+                                                       (const uint8_t *)e->dInv, e->dWeights, dGp, e->N);
         switch (K) {
           case 1: GM(1) break;
           case 2: GM(2) break;

@@ -132,20 +132,61 @@ param_grad_kernel(const double *__restrict__ mats, int np, int q0, int nq, const
 // multiply, and 4K chained DMMAs leave (row lane / 4; patterns 2c, 2c + 1) in two registers -- 16 DMMA + 16 DMUL
 // per 8 patterns instead of 5 k FMAs + 3.6 k shared-memory reads, and the A fragments live in registers for a
 // whole 1024-pattern block. Work item = (branch, block), all branches of a tree in one launch (descriptor table
-// as in root4_batch_kernel); each item writes its canonical block fold to gp[branch][q][block], and
+// as in root4_batch_kernel); each item writes its block sum (fixed order, see the kernel) to gp[branch][q][block], and
 // grad_sum_branches_kernel adds the branches in schedule order, so the result does not depend on the grid.
-// afrag: [branch][K][4][32] (host: grad_fill_afrag). Dynamic shared memory: (nq * 1024 + 32) doubles.
+// afrag: [branch][K][4][32] (host: grad_fill_afrag).
+// (non-volatile forms: read-only data and pure arithmetic, so the compiler is free to hoist the loads of a group
+// above the DMMA chain of the previous one -- with the volatile helpers of lk_kernels.cuh every load waited
+// for the DMMAs issued before it: 2.2 TB/s)
+__device__ __forceinline__ d4 grad_ld256(const double *p) {
+  d4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void grad_dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
 template <int K>
-__global__ void __launch_bounds__(256)
+struct GradPair {  // one lane's operands of an 8-pattern group: a_k (all four states) and b_k[c], every class
+  d4 a[K];
+  double b[K];
+};
+
+// (p is clamped to the last pattern by the caller: a group past N loads valid addresses and its results are
+// dropped with f = 0, so no load is predicated)
+template <int K>
+__device__ __forceinline__ void grad_load_pair(GradPair<K> &o, const EdgeJoin &ej, int64_t p, int c) {
+  if (ej.atip) {
+    const int m = ((const uint8_t *)ej.asrc)[p];
+    const d4 v{(double)(m & 1), (double)((m >> 1) & 1), (double)((m >> 2) & 1), (double)((m >> 3) & 1)};
+#pragma unroll
+    for (int k = 0; k < K; ++k) o.a[k] = v;
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) o.a[k] = grad_ld256((const double *)ej.asrc + ((size_t)p * K + k) * 4);
+  }
+  if (ej.btip) {
+    const int m = ((const uint8_t *)ej.bsrc)[p];
+#pragma unroll
+    for (int k = 0; k < K; ++k) o.b[k] = (double)((m >> c) & 1);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) o.b[k] = __ldg((const double *)ej.bsrc + ((size_t)p * K + k) * 4 + c);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, K <= 4 ? 2 : 1)  // (K = 8: two operand buffers + 32 A fragments need > 128 registers)
 param_grad4_mma_kernel(const EdgeJoin *__restrict__ edges, int n_edges, const double *__restrict__ afrag, int nq,
                        const double *__restrict__ pi, double pinvar, const uint8_t *__restrict__ inv,
                        const double *__restrict__ weights, double *__restrict__ gp, int64_t N) {
-  extern __shared__ __align__(16) double gsm[];
-  double *vals = gsm;                          // [nq][1024]
-  double *wsum = gsm + (size_t)nq * kLnlBlock;  // [32]
+  __shared__ double wsum[2][8][8];  // [item parity][warp][row]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pg = lane >> 2, c = lane & 3;
+  constexpr int kGroups = kLnlBlock / 8 / 8;  // 8-pattern groups per warp and block (even)
   const int64_t nblocks = (N + kLnlBlock - 1) / kLnlBlock, items = nblocks * n_edges;
-  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+  int parity = 0;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x, parity ^= 1) {
     const int edge = (int)(item / nblocks);
     const int64_t blk = item - (int64_t)edge * nblocks;
     const EdgeJoin ej = edges[edge];
@@ -154,30 +195,25 @@ param_grad4_mma_kernel(const EdgeJoin *__restrict__ edges, int n_edges, const do
     for (int k = 0; k < K; ++k)
 #pragma unroll
       for (int s = 0; s < 4; ++s) A[k][s] = __ldg(afrag + (((size_t)edge * K + k) * 4 + s) * 32 + lane);
-    const double *aclv = (const double *)ej.asrc, *bclv = (const double *)ej.bsrc;
-    const uint8_t *atip = (const uint8_t *)ej.asrc, *btip = (const uint8_t *)ej.bsrc;
-#pragma unroll 2
-    for (int g = warp; g < kLnlBlock / 8; g += 8) {
-      const int pl0 = g * 8;
-      const int64_t p = blk * kLnlBlock + pl0 + pg;
-      const bool act = p < N;
-      double acc[2] = {0.0, 0.0};
-      int ma = 0, mb = 0;
-      if (act && ej.atip) ma = atip[p];
-      if (act && ej.btip) mb = btip[p];
+    const int64_t pbase = blk * kLnlBlock + pg;
+    // this lane's running sums of w (d lnL_s / d l_s) d l_s: row pg, patterns 2c and 2c + 1 of the warp's groups.
+    // The block result is built in a fixed order (groups in sequence per lane, the two columns, the row's four
+    // lanes by xor 1 and 2, the eight warps in sequence), so it depends on the block alone -- not on the grid
+    // or on which device scores the block.
+    double g0 = 0.0, g1 = 0.0;
+    auto step = [&](const GradPair<K> &d, int pl0) {
+      // two accumulator chains (even / odd k-steps), added at the end: DMMA latency is 26 cycles
+      double acc[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        d4 a{0, 0, 0, 0};
-        double b = 0.0;
-        if (ej.atip) a = d4{(double)(ma & 1), (double)((ma >> 1) & 1), (double)((ma >> 2) & 1), (double)((ma >> 3) & 1)};
-        else if (act) a = ld256_stream(aclv + ((size_t)p * K + k) * 4);
-        if (ej.btip) b = (double)((mb >> c) & 1);
-        else if (act) b = __ldg(bclv + ((size_t)p * K + k) * 4 + c);
-        dmma_8x8x4(acc, A[k][0], a.x * b);
-        dmma_8x8x4(acc, A[k][1], a.y * b);
-        dmma_8x8x4(acc, A[k][2], a.z * b);
-        dmma_8x8x4(acc, A[k][3], a.w * b);
+        const double b = d.b[k];
+        grad_dmma(acc, A[k][0], d.a[k].x * b);
+        grad_dmma(acc2, A[k][1], d.a[k].y * b);
+        grad_dmma(acc, A[k][2], d.a[k].z * b);
+        grad_dmma(acc2, A[k][3], d.a[k].w * b);
       }
+      acc[0] += acc2[0];
+      acc[1] += acc2[1];
       // row 0 (lanes 0-3) holds l of patterns pl0 + 2c, + 1: those lanes turn it into w * d lnL_s / d l_s
       double f0 = 0.0, f1 = 0.0;
       if (pg == 0) {
@@ -202,18 +238,29 @@ param_grad4_mma_kernel(const EdgeJoin *__restrict__ edges, int n_edges, const do
       }
       f0 = __shfl_sync(0xffffffffu, f0, c);
       f1 = __shfl_sync(0xffffffffu, f1, c);
-      if (pg >= 1 && pg <= nq) {
-        double2 v;
-        v.x = f0 == 0.0 ? 0.0 : f0 * acc[0];  // (patterns past N: f = 0)
-        v.y = f1 == 0.0 ? 0.0 : f1 * acc[1];
-        *reinterpret_cast<double2 *>(vals + (size_t)(pg - 1) * kLnlBlock + pl0 + 2 * c) = v;
-      }
+      if (f0 != 0.0) g0 += f0 * acc[0];  // (patterns past N: f = 0, and acc is the clamped pattern's)
+      if (f1 != 0.0) g1 += f1 * acc[1];
+    };
+    GradPair<K> d0, d1;  // ping-pong: the loads of a group are in flight during the DMMA chain of the one before
+    grad_load_pair<K>(d0, ej, min(pbase + warp * 8, N - 1), c);
+#pragma unroll 1
+    for (int it = 0; it < kGroups; it += 2) {
+      const int pl0 = (warp + 8 * it) * 8;
+      grad_load_pair<K>(d1, ej, min(pbase + pl0 + 64, N - 1), c);
+      step(d0, pl0);
+      if (it + 2 < kGroups) grad_load_pair<K>(d0, ej, min(pbase + pl0 + 128, N - 1), c);
+      step(d1, pl0 + 64);
     }
-    __syncthreads();
-    for (int q = 0; q < nq; ++q) {
-      const double r = block_fold_1024(vals + (size_t)q * kLnlBlock, wsum);
-      if (threadIdx.x == 0) gp[((size_t)edge * nq + q) * nblocks + blk] = r;
-      __syncthreads();
+    double g = g0 + g1;
+    g += __shfl_xor_sync(0xffffffffu, g, 1);
+    g += __shfl_xor_sync(0xffffffffu, g, 2);
+    if (c == 0) wsum[parity][warp][pg] = g;
+    __syncthreads();  // (one barrier per item: the next item writes the other half of wsum)
+    if (threadIdx.x < nq) {
+      double r = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) r += wsum[parity][w][1 + threadIdx.x];
+      gp[((size_t)edge * nq + threadIdx.x) * nblocks + blk] = r;
     }
   }
 }
