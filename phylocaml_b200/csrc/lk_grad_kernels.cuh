@@ -176,42 +176,50 @@ __device__ __forceinline__ void grad_load_pair(GradPair<K> &o, const EdgeJoin &e
   }
 }
 
+// Occupancy, not prefetch depth, hides the latencies here (ncu of the ping-pong version with the A fragments in
+// registers, 128 registers = 4 warps per scheduler: tensor + fp64 pipe 47 % busy, every warp serialised on its own
+// DMMA chain -> reciprocal -> shuffle sequence): the A fragments live in shared memory (one conflict-free 8-byte
+// read per DMMA), a warp holds one group's operands, and 3-4 CTAs share an SM.
 template <int K>
-__global__ void __launch_bounds__(256, K <= 4 ? 2 : 1)  // (K = 8: two operand buffers + 32 A fragments need > 128 registers)
+__global__ void __launch_bounds__(256, K <= 4 ? 3 : 2)
 param_grad4_mma_kernel(const EdgeJoin *__restrict__ edges, int n_edges, const double *__restrict__ afrag, int nq,
                        const double *__restrict__ pi, double pinvar, const uint8_t *__restrict__ inv,
                        const double *__restrict__ weights, double *__restrict__ gp, int64_t N) {
-  __shared__ double wsum[2][8][8];  // [item parity][warp][row]
+  __shared__ double sA[2][K * 4 * 32];  // [item parity][k][s][lane]
+  __shared__ double wsum[2][8][8];      // [item parity][warp][row]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pg = lane >> 2, c = lane & 3;
-  constexpr int kGroups = kLnlBlock / 8 / 8;  // 8-pattern groups per warp and block (even)
+  constexpr int kGroups = kLnlBlock / 8 / 8;  // 8-pattern groups per warp and block
   const int64_t nblocks = (N + kLnlBlock - 1) / kLnlBlock, items = nblocks * n_edges;
   int parity = 0;
   for (int64_t item = blockIdx.x; item < items; item += gridDim.x, parity ^= 1) {
     const int edge = (int)(item / nblocks);
     const int64_t blk = item - (int64_t)edge * nblocks;
     const EdgeJoin ej = edges[edge];
-    double A[K][4];
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-#pragma unroll
-      for (int s = 0; s < 4; ++s) A[k][s] = __ldg(afrag + (((size_t)edge * K + k) * 4 + s) * 32 + lane);
+    for (int i = threadIdx.x; i < K * 128; i += 256) sA[parity][i] = __ldg(afrag + (size_t)edge * K * 128 + i);
+    const double *A = sA[parity] + lane;
     const int64_t pbase = blk * kLnlBlock + pg;
+    GradPair<K> d;
+    grad_load_pair<K>(d, ej, min(pbase + warp * 8, N - 1), c);
+    __syncthreads();  // A fragments of this item (the other half of sA / wsum belongs to the previous item's readers)
     // this lane's running sums of w (d lnL_s / d l_s) d l_s: row pg, patterns 2c and 2c + 1 of the warp's groups.
     // The block result is built in a fixed order (groups in sequence per lane, the two columns, the row's four
     // lanes by xor 1 and 2, the eight warps in sequence), so it depends on the block alone -- not on the grid
     // or on which device scores the block.
     double g0 = 0.0, g1 = 0.0;
-    auto step = [&](const GradPair<K> &d, int pl0) {
+#pragma unroll 1
+    for (int it = 0; it < kGroups; ++it) {
+      const int pl0 = (warp + 8 * it) * 8;
       // two accumulator chains (even / odd k-steps), added at the end: DMMA latency is 26 cycles
       double acc[2] = {0.0, 0.0}, acc2[2] = {0.0, 0.0};
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const double b = d.b[k];
-        grad_dmma(acc, A[k][0], d.a[k].x * b);
-        grad_dmma(acc2, A[k][1], d.a[k].y * b);
-        grad_dmma(acc, A[k][2], d.a[k].z * b);
-        grad_dmma(acc2, A[k][3], d.a[k].w * b);
+        grad_dmma(acc, A[(k * 4 + 0) * 32], d.a[k].x * b);
+        grad_dmma(acc2, A[(k * 4 + 1) * 32], d.a[k].y * b);
+        grad_dmma(acc, A[(k * 4 + 2) * 32], d.a[k].z * b);
+        grad_dmma(acc2, A[(k * 4 + 3) * 32], d.a[k].w * b);
       }
+      if (it + 1 < kGroups) grad_load_pair<K>(d, ej, min(pbase + pl0 + 64, N - 1), c);  // (in flight during the epilogue)
       acc[0] += acc2[0];
       acc[1] += acc2[1];
       // row 0 (lanes 0-3) holds l of patterns pl0 + 2c, + 1: those lanes turn it into w * d lnL_s / d l_s
@@ -240,22 +248,12 @@ param_grad4_mma_kernel(const EdgeJoin *__restrict__ edges, int n_edges, const do
       f1 = __shfl_sync(0xffffffffu, f1, c);
       if (f0 != 0.0) g0 += f0 * acc[0];  // (patterns past N: f = 0, and acc is the clamped pattern's)
       if (f1 != 0.0) g1 += f1 * acc[1];
-    };
-    GradPair<K> d0, d1;  // ping-pong: the loads of a group are in flight during the DMMA chain of the one before
-    grad_load_pair<K>(d0, ej, min(pbase + warp * 8, N - 1), c);
-#pragma unroll 1
-    for (int it = 0; it < kGroups; it += 2) {
-      const int pl0 = (warp + 8 * it) * 8;
-      grad_load_pair<K>(d1, ej, min(pbase + pl0 + 64, N - 1), c);
-      step(d0, pl0);
-      if (it + 2 < kGroups) grad_load_pair<K>(d0, ej, min(pbase + pl0 + 128, N - 1), c);
-      step(d1, pl0 + 64);
     }
     double g = g0 + g1;
     g += __shfl_xor_sync(0xffffffffu, g, 1);
     g += __shfl_xor_sync(0xffffffffu, g, 2);
     if (c == 0) wsum[parity][warp][pg] = g;
-    __syncthreads();  // (one barrier per item: the next item writes the other half of wsum)
+    __syncthreads();
     if (threadIdx.x < nq) {
       double r = 0.0;
 #pragma unroll
