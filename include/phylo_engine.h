@@ -219,10 +219,12 @@ int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a,
  *   drates [n_params][K]     d rates[k] / d theta_p (the Gamma shape alpha moves only these),
  *   dpi    [n_params][S]     d priors / d theta_p at the root (not together with an invariant-sites class).
  * lnL is multilinear in the branches' P(t): d P = dexp_{Q t r}[t (r dQ + dr Q)] is formed per branch on the
- * host from the eigensystem and applied across the branch's directional pair by one kernel pass per branch
- * (all parameters together; 2 T - 3 passes of 2 C bytes per pattern -- against 2 n_params full evaluations
- * for central differences). Reversible models (the pulley principle behind phylo_lk_uppass). *lnl_out (may be
- * NULL) = the lnL of the preceding phylo_lk_score_tree. */
+ * host from the eigensystem and applied across the branch's directional pair (all parameters together;
+ * 2 T - 3 pairs of 2 C bytes per pattern -- against 2 n_params full evaluations for central differences).
+ * 4 states: ONE launch over all (branch, 1024-pattern block) items on the fp64 tensor cores, seven
+ * parameters per pass (param_grad4_mma_kernel); other alphabets: one scalar kernel pass per branch.
+ * Reversible models (the pulley principle behind phylo_lk_uppass). *lnl_out (may be NULL) = the lnL of the
+ * preceding phylo_lk_score_tree. */
 int phylo_lk_param_gradient(phylo_engine *e, const phylo_op *ops, int n_ops, int root_a, int root_b, double root_t,
                             const int32_t *up_slot, int n_params, const double *dQ, const double *drates,
                             const double *dpi, double *lnl_out, double *grad_out);
