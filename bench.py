@@ -682,7 +682,7 @@ def run_directions(torch, engine, tree_mod, local, wl, model, base, ops, ra, rb,
                "all_edge_joins_ms": join_ms, "candidate_joins_per_s": len(edges) / (join_ms * 1e-3),
                "join_site_updates_per_s": len(edges) * n_sample / (join_ms * 1e-3),
                "max_rel_diff_of_edge_lnl_vs_root_edge": worst, "tolerance": 1e-11,
-               "note": "up pass = 2T-4 per-node pruning updates (one per directional CLV); each join reads two CLVs"}
+               "note": "up pass = 2T-4 pruning updates (one per directional CLV), one launch per tree level for 4 states; each join reads two CLVs; gradient: every branch in one DMMA launch for 4 states"}
         if S == 4:  # GTR+G: 5 exchangeabilities + the Gamma shape, against central differences of full evaluations
             h, alpha = 1e-6, 0.5
             co = np.array(GTR_CO, dtype=float)

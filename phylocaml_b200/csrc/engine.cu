@@ -2128,6 +2128,85 @@ extern "C" int phylo_lk_uppass(phylo_engine *e, const phylo_op *ops, int n_ops, 
   }
   if ((rc = build_pt(e, nb)) != PHYLO_OK) return rc;
   const size_t pk = (size_t)e->K * e->S * e->S;
+  // 4 states: the updates of one tree level are independent (each needs only its parent's up value), so a level
+  // is ONE launch over (update, pattern range) items -- 2T - 4 launches become one per level. The values are the
+  // per-node kernels' bit for bit (same body). PHYLO_UPPASS_BATCH=0 keeps one launch per update (cross-check).
+  const char *sw = std::getenv("PHYLO_UPPASS_BATCH");
+  if (e->S == 4 && (e->K == 1 || e->K == 2 || e->K == 4 || e->K == 8 || e->K == 16) && !(sw && sw[0] == '0')) {
+    std::vector<int> lvl_of_slot(cap, 0), lvl(upd.size());
+    int n_lvl = 0;
+    for (size_t i = 0; i < upd.size(); ++i) {  // parents first: the level of the source is known
+      lvl[i] = lvl_of_slot[upd[i].src] + (upd[i].src == root_a || upd[i].src == root_b ? 0 : 1);
+      lvl_of_slot[upd[i].dst] = lvl[i];
+      n_lvl = std::max(n_lvl, lvl[i] + 1);
+    }
+    auto undo = [&](int code) {  // nothing was launched for these slots, or the launch failed
+      for (const Upd &u : upd) e->nodes[u.dst].valid = false;
+      return code;
+    };
+    std::vector<std::vector<int>> by_lvl(n_lvl);
+    for (size_t i = 0; i < upd.size(); ++i) by_lvl[lvl[i]].push_back((int)i);
+    std::vector<PruneItem> items;
+    items.reserve(upd.size());
+    struct Launch { int first, count, tt_update; };  // tt_update >= 0: a tip + tip update through its own kernel
+    std::vector<Launch> launches;
+    for (int L = 0; L < n_lvl; ++L) {
+      const int first = (int)items.size();
+      for (int i : by_lvl[L]) {
+        Operand l, r;
+        if ((rc = lk_operand(e, upd[i].sib, &l, "lk_uppass")) != PHYLO_OK) return undo(rc);
+        if ((rc = lk_operand(e, upd[i].src, &r, "lk_uppass")) != PHYLO_OK) return undo(rc);
+        LkNode &dst = e->nodes[upd[i].dst];
+        dst.valid = true;  // (a source of the next level; cleared again below if the call fails)
+        if (l.tip && r.tip) { launches.push_back(Launch{0, 0, i}); continue; }
+        items.push_back(PruneItem{e->dP + (size_t)(2 * i) * pk, e->dP + (size_t)(2 * i + 1) * pk, l.src, r.src, l.scale, r.scale,
+                                  dst.clv, dst.scale, l.tip ? 1 : 0, r.tip ? 1 : 0});
+      }
+      if ((int)items.size() > first) launches.push_back(Launch{first, (int)items.size() - first, -1});
+    }
+    const size_t bytes = (sizeof(PruneItem) * std::max<size_t>(1, items.size()) + 255) & ~(size_t)255;
+    if (bytes > e->capEdgeArena) {
+      dfree(e->dEdgeArena);
+      e->capEdgeArena = 0;
+      if (cudaMalloc(&e->dEdgeArena, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return undo(fail(e, PHYLO_ERR_CUDA, "lk_uppass: cannot allocate %zu bytes of device memory", bytes));
+      }
+      e->capEdgeArena = bytes;
+    }
+    PruneItem *dItems = (PruneItem *)e->dEdgeArena;
+    if (!items.empty()) CK(cudaMemcpyAsync(dItems, items.data(), sizeof(PruneItem) * items.size(), cudaMemcpyHostToDevice, e->stream));
+    const int64_t per_node = (e->N * e->K + 256 * 2 - 1) / (256 * 2);  // CTAs that cover a node at U = 2
+    for (const Launch &la : launches) {
+      if (la.tt_update >= 0) {
+        const int i = la.tt_update;
+        Operand l, r;
+        if ((rc = lk_operand(e, upd[i].sib, &l, "lk_uppass")) != PHYLO_OK) return rc;
+        if ((rc = lk_operand(e, upd[i].src, &r, "lk_uppass")) != PHYLO_OK) return rc;
+        LkNode &dst = e->nodes[upd[i].dst];
+        if ((rc = lk_launch_prune(e, e->dP + (size_t)(2 * i) * pk, e->dP + (size_t)(2 * i + 1) * pk, l, r, dst.clv, dst.scale)) != PHYLO_OK) return rc;
+        continue;
+      }
+      // about 8 CTAs per SM in flight over the whole level, at least one and at most `per_node` per update
+      const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(per_node, ((int64_t)e->sm_count * 8 + la.count - 1) / la.count));
+      for (int y0 = 0; y0 < la.count; y0 += 65535) {
+        const int ny = std::min(65535, la.count - y0);
+        ProfScope prof(e, KC_PRUNE_II);
+        const dim3 grid((unsigned)gx, (unsigned)ny);
+        switch (e->K) {
+          case 1: prune4_level_kernel<1><<<grid, 256, 0, e->stream>>>(dItems + la.first + y0, e->N); break;
+          case 2: prune4_level_kernel<2><<<grid, 256, 0, e->stream>>>(dItems + la.first + y0, e->N); break;
+          case 4: prune4_level_kernel<4><<<grid, 256, 0, e->stream>>>(dItems + la.first + y0, e->N); break;
+          case 8: prune4_level_kernel<8><<<grid, 256, 0, e->stream>>>(dItems + la.first + y0, e->N); break;
+          default: prune4_level_kernel<16><<<grid, 256, 0, e->stream>>>(dItems + la.first + y0, e->N);
+        }
+        LAUNCH_CHECK();
+      }
+    }
+    e->edge_ready = false;
+    if (e->prof_on) prof_resolve_lazy(e);
+    return PHYLO_OK;
+  }
   for (size_t i = 0; i < upd.size(); ++i) {
     Operand l, r;
     if ((rc = lk_operand(e, upd[i].sib, &l, "lk_uppass")) != PHYLO_OK) return rc;

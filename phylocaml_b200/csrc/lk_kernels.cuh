@@ -73,12 +73,14 @@ __device__ __forceinline__ void tip_contrib(const double (&pm)[16], int m, doubl
   }
 }
 
+// (body shared by prune4_kernel and prune4_level_kernel: bx / gx = this CTA's index and the number of CTAs
+// that share the node)
 template <int K, bool LTIP, bool RTIP, int U>
-__global__ void __launch_bounds__(256)
-prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
-              const void *__restrict__ lsrc, const int32_t *__restrict__ lsc,
-              const void *__restrict__ rsrc, const int32_t *__restrict__ rsc,
-              double *__restrict__ out, int32_t *__restrict__ osc, int64_t N) {
+__device__ __forceinline__ void
+prune4_body(const double *__restrict__ Pl, const double *__restrict__ Pr,
+            const void *__restrict__ lsrc, const int32_t *__restrict__ lsc,
+            const void *__restrict__ rsrc, const int32_t *__restrict__ rsc,
+            double *__restrict__ out, int32_t *__restrict__ osc, int64_t N, int bx, int gx) {
   static_assert(K == 1 || K == 2 || K == 4 || K == 8 || K == 16, "K must divide the warp");
   const int k = threadIdx.x % K;
   double pl[16], pr[16];
@@ -88,11 +90,11 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
   for (int e = 0; e < 16; ++e) pr[e] = Pr[k * 16 + e];
 
   const int64_t total = N * K;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+  const int64_t stride = (int64_t)gx * blockDim.x * U;
   const double *lclv = (const double *)lsrc, *rclv = (const double *)rsrc;
   const uint8_t *ltip = (const uint8_t *)lsrc, *rtip = (const uint8_t *)rsrc;
 
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U; base < total; base += stride) {
+  for (int64_t base = (int64_t)bx * blockDim.x * U; base < total; base += stride) {
     d4 l[U], r[U];
     int ml[U], mr[U], sc[U];
     bool act[U];
@@ -158,6 +160,35 @@ prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
       }
     }
   }
+}
+
+template <int K, bool LTIP, bool RTIP, int U>
+__global__ void __launch_bounds__(256)
+prune4_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
+              const void *__restrict__ lsrc, const int32_t *__restrict__ lsc,
+              const void *__restrict__ rsrc, const int32_t *__restrict__ rsc,
+              double *__restrict__ out, int32_t *__restrict__ osc, int64_t N) {
+  prune4_body<K, LTIP, RTIP, U>(Pl, Pr, lsrc, lsc, rsrc, rsc, out, osc, N, blockIdx.x, gridDim.x);
+}
+
+// Many independent pruning updates in one launch (the pre-order pass: every update of one tree level):
+// blockIdx.y picks the update from a descriptor table, the CTAs along x share it. Same body, so the values
+// are those of the per-node launches bit for bit. Tip + tip updates keep their own kernel (prune4_tt_kernel).
+struct PruneItem {
+  const double *Pl, *Pr;
+  const void *lsrc, *rsrc;
+  const int32_t *lsc, *rsc;
+  double *out;
+  int32_t *osc;
+  int ltip, rtip;
+};
+template <int K>
+__global__ void __launch_bounds__(256)
+prune4_level_kernel(const PruneItem *__restrict__ items, int64_t N) {
+  const PruneItem it = items[blockIdx.y];
+  if (it.ltip) prune4_body<K, true, false, 4>(it.Pl, it.Pr, it.lsrc, it.lsc, it.rsrc, it.rsc, it.out, it.osc, N, blockIdx.x, gridDim.x);
+  else if (it.rtip) prune4_body<K, false, true, 4>(it.Pl, it.Pr, it.lsrc, it.lsc, it.rsrc, it.rsc, it.out, it.osc, N, blockIdx.x, gridDim.x);
+  else prune4_body<K, false, false, 2>(it.Pl, it.Pr, it.lsrc, it.lsc, it.rsrc, it.rsc, it.out, it.osc, N, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------- 4-state update, both children tips ----

@@ -106,3 +106,38 @@ def test_batched_joins_equal_single_joins_bitwise(eng, oracle, K, N):
         assert batch[i] == eng.lk_edge_lnl(v, u, [ts[i]])[0], (K, i)
     own = eng.lk_edge_lnl_batch(ea, eb, [e[2] for e in edges])
     assert np.max(np.abs(own - lnl)) <= 1e-11 * abs(lnl)
+
+
+@pytest.mark.parametrize("K,N,T", [(4, 2500, 40), (1, 1025, 17), (8, 700, 12), (2, 90000, 24)])
+def test_level_batched_uppass_equals_per_update_launches_bitwise(eng, monkeypatch, K, N, T):
+    """4 states: one launch per tree level (prune4_level_kernel) against one launch per update
+    (PHYLO_UPPASS_BATCH=0): every directional CLV and scale counter bit for bit, fewer launches."""
+    from phylocaml_b200 import mlmodel
+    from helpers import GTR_CO, GTR_PI
+
+    sv = ("gamma", K, 0.5) if K > 1 else None
+    model = mlmodel.create(("GTR", list(GTR_CO)), 4, pi=list(GTR_PI), site_var=sv)
+    tr, ops, ra, rb, rt, n_nodes, tips = setup_lk(T, N, model, seed=K + T, mean_bl=0.4)
+    up_slot, cap, up_ops, edges = tree.uppass_plan(ops, ra, rb, rt, n_nodes)
+    eng.lk_set_model(model)
+    eng.lk_set_tips(tips, capacity=cap)
+    lnl = eng.lk_score_tree(ops, ra, rb, rt)
+    monkeypatch.setenv("PHYLO_UPPASS_BATCH", "0")
+    l0 = eng.launch_count
+    eng.lk_uppass(ops, ra, rb, rt, up_slot)
+    per_update = eng.launch_count - l0
+    want = {u: eng.lk_get_clv(u) for v, u, tv in edges}
+    # a fresh down pass invalidates nothing the up pass needs, but rewrite the up slots from scratch anyway
+    monkeypatch.setenv("PHYLO_UPPASS_BATCH", "1")
+    eng.lk_set_tips(tips, capacity=cap)
+    assert eng.lk_score_tree(ops, ra, rb, rt) == lnl
+    l0 = eng.launch_count
+    eng.lk_uppass(ops, ra, rb, rt, up_slot)
+    batched = eng.launch_count - l0
+    assert batched < per_update, (batched, per_update)
+    for v, u, tv in edges:
+        clv, sc = eng.lk_get_clv(u)
+        assert np.array_equal(sc, want[u][1]), (v, u)
+        assert np.array_equal(clv, want[u][0]), (v, u)
+    joins = eng.lk_edge_lnl_batch([e[0] for e in edges], [e[1] for e in edges], [e[2] for e in edges])
+    assert np.max(np.abs(joins - lnl)) <= 1e-11 * abs(lnl)
