@@ -188,6 +188,8 @@ struct phylo_engine {
   double *dUL = nullptr, *dUR = nullptr, *dSum = nullptr, *dEdgePart = nullptr, *dEdgeOut = nullptr, *dEdgeT = nullptr;
   char *dEdgeArena = nullptr;  // lk_edge_lnl_batch: edge descriptors + fold levels
   size_t capEdgeArena = 0;
+  double *hEdgeRes = nullptr;  // pinned results of lk_edge_lnl_batch, grow-only (a pinned allocation per call cost more than the joins of a small neighbourhood)
+  int capEdgeRes = 0;
   int32_t *dSumSc = nullptr;
   bool edge_ready = false;
   int edge_a = -1, edge_b = -1;
@@ -421,6 +423,7 @@ extern "C" void phylo_engine_destroy(phylo_engine *e) {
   if (e->auxDone) cudaEventDestroy(e->auxDone);
   if (e->hT) cudaFreeHost(e->hT);
   if (e->hScalar) cudaFreeHost(e->hScalar);
+  if (e->hEdgeRes) cudaFreeHost(e->hEdgeRes);
   if (e->hSched) cudaFreeHost(e->hSched);
   if (e->hCost) cudaFreeHost(e->hCost);
   delete e;
@@ -2877,8 +2880,13 @@ extern "C" int phylo_lk_edge_lnl_batch(phylo_engine *e, int n_edges, const int32
   CK(cudaSetDevice(e->device));
   int rc;
   if ((rc = ensure_pt_capacity(e, n_edges, e->S, e->K)) != PHYLO_OK) return rc;
-  double *hres = nullptr;
-  CK(cudaMallocHost(&hres, sizeof(double) * n_edges));
+  if (n_edges > e->capEdgeRes) {
+    if (e->hEdgeRes) { cudaFreeHost(e->hEdgeRes); e->hEdgeRes = nullptr; }
+    e->capEdgeRes = 0;
+    CK(cudaMallocHost(&e->hEdgeRes, sizeof(double) * std::max(n_edges, 1024)));
+    e->capEdgeRes = std::max(n_edges, 1024);
+  }
+  double *hres = e->hEdgeRes;
   CK(cudaStreamSynchronize(e->stream));
   for (int i = 0; i < n_edges; ++i) e->hT[i] = t[i];
   rc = build_pt(e, n_edges);
@@ -2947,7 +2955,6 @@ extern "C" int phylo_lk_edge_lnl_batch(phylo_engine *e, int n_edges, const int32
     const cudaError_t le = cudaGetLastError();
     if (rc == PHYLO_OK && st == cudaSuccess && le == cudaSuccess)
       for (int i = 0; i < n_edges; ++i) lnl_out[i] = hres[i];
-    cudaFreeHost(hres);
     if (rc != PHYLO_OK) return rc;
     if (st != cudaSuccess || le != cudaSuccess)
       return fail(e, PHYLO_ERR_CUDA, "lk_edge_lnl_batch: %s", cudaGetErrorString(st != cudaSuccess ? st : le));
@@ -2964,7 +2971,6 @@ extern "C" int phylo_lk_edge_lnl_batch(phylo_engine *e, int n_edges, const int32
   const cudaError_t st = cudaStreamSynchronize(e->stream);
   if (rc == PHYLO_OK && st == cudaSuccess)
     for (int i = 0; i < n_edges; ++i) lnl_out[i] = hres[i];
-  cudaFreeHost(hres);
   if (rc != PHYLO_OK) return rc;
   if (st != cudaSuccess) return fail(e, PHYLO_ERR_CUDA, "lk_edge_lnl_batch: %s", cudaGetErrorString(st));
   e->lk_evaluated = true;
