@@ -359,7 +359,7 @@ struct EdgeJoin {
   int atip, btip;
 };
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 root4_batch_kernel(const EdgeJoin *__restrict__ edges, int n_edges, const double *__restrict__ Pall,
                    const double *__restrict__ pi, const double *__restrict__ probs, double pinvar,
                    const uint8_t *__restrict__ inv, const double *__restrict__ weights,
