@@ -260,7 +260,7 @@ prune4_tt_kernel(const double *__restrict__ Pl, const double *__restrict__ Pr,
 // ln l_s - c_s*256 ln2 (or the +pinvar form), times the pattern weight, folded per block of
 // 1024 patterns in the canonical shape. One CTA per 1024-pattern block (grid-strided).
 template <int K, bool ATIP, bool BTIP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 root4_kernel(const double *__restrict__ Proot, const double *__restrict__ pi,
              const double *__restrict__ probs, double pinvar, const uint8_t *__restrict__ inv,
              const void *__restrict__ asrc, const int32_t *__restrict__ asc,
