@@ -2557,8 +2557,11 @@ static int grad4_mma_path(phylo_engine *e, const std::vector<double> &hm, size_t
   }
   constexpr int kRows = 7;  // parameters per pass (row 0 of the 8-row tile is the likelihood)
   const int nq_max = std::min(n_params, kRows);
-  // branches per launch: the per-branch block results stay below 256 MB
-  const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(n_edges, ((int64_t)256 << 20) / (8 * nq_max * nb)));
+  // branches per launch: the per-branch block results stay below 256 MB (PHYLO_GRAD_CHUNK_BYTES: another budget, so
+  // that a test can drive the several-launches path on a small tree)
+  int64_t budget = (int64_t)256 << 20;
+  if (const char *v = std::getenv("PHYLO_GRAD_CHUNK_BYTES")) budget = std::max<int64_t>(1, std::atoll(v));
+  const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(n_edges, budget / (8 * nq_max * nb)));
   auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t descBytes = up256(sizeof(EdgeJoin) * n_edges), fragBytes = up256(sizeof(double) * (size_t)n_edges * K * 128),
                gpBytes = up256(sizeof(double) * (size_t)chunk * nq_max * nb), outBytes = up256(sizeof(double) * (size_t)n_params * nb);

@@ -146,5 +146,13 @@ def test_tensor_core_gradient_equals_the_scalar_kernel(eng, monkeypatch, K, pinv
     assert np.all(np.isfinite(got))
     scale = np.maximum(1.0, np.abs(want))
     assert np.max(np.abs(got - want) / scale) <= 1e-10, (got, want)
+    # branches in several launches (the per-branch block results are capped at 256 MB; here: three branches per launch)
+    nblocks = (N + 1023) // 1024
+    monkeypatch.setenv("PHYLO_GRAD_CHUNK_BYTES", str(3 * 8 * 7 * nblocks))
+    l0 = eng.launch_count
+    chunked = eng.lk_param_gradient(ops, ra, rb, rt, up_slot, dQ=dQ, drates=drates, dpi=dpi)
+    assert eng.launch_count - l0 == 2 * 2 * ((2 * 13 - 3 + 2) // 3)
+    assert np.array_equal(chunked, got)
+    monkeypatch.delenv("PHYLO_GRAD_CHUNK_BYTES")
     # deterministic: the same call returns the same bits
     assert np.array_equal(got, eng.lk_param_gradient(ops, ra, rb, rt, up_slot, dQ=dQ, drates=drates, dpi=dpi))
