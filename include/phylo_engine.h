@@ -97,11 +97,18 @@ int phylo_engine_set_symbol_table(phylo_engine *e, const uint64_t *table256);
  * on the device and returns without waiting for (or computing) the local lnL (*lnl_out = NaN); the caller
  * combines them across ranks with phylo_lk_exchange_reduce. No host round trip between the two. */
 #define PHYLO_OPT_DEFER_SCALAR 4
-/* Two environment variables exist for measurements only (tools/tune_treew.sh, tools/mma_ab.sh):
+/* Environment variables exist for measurements and cross-checks only, never as configuration
+ * (tools/tune_treew.sh, tools/mma_ab.sh, tools/grad_mma_ab.sh, tools/uppass_ab.sh):
  * PHYLO_TREEW_TUNE="slev,R,il" overrides the geometry the warp-autonomous tree kernel picks, and
  * PHYLO_TT_TABLE=0 sends 20-state tip+tip updates through the DMMA kernel instead of the table
  * copy. PHYLO_TREEW_TUNE never changes a bit of the result; the two tip+tip paths give identical
- * CLVs for observed tips and agree to rounding (1e-16 relative) where a tip is ambiguous. */
+ * CLVs for observed tips and agree to rounding (1e-16 relative) where a tip is ambiguous.
+ * PHYLO_TREEM_PAIRED / PHYLO_TREEM_STSWAP / PHYLO_TREEM_TIMING / PHYLO_FITCH_TIMING: A/B switches and
+ * per-CTA timelines of the tree-fused DMMA and Fitch tile kernels (bit-identical results).
+ * PHYLO_UPPASS_BATCH=0: phylo_lk_uppass launches one kernel per update instead of one per tree
+ * level (bit-identical). PHYLO_GRAD_MMA=0: phylo_lk_param_gradient runs the scalar per-branch kernel
+ * for 4 states instead of the tensor-core kernel (agreement 1e-14 relative); PHYLO_GRAD_CHUNK_BYTES
+ * caps the scratch of that kernel (tests drive the several-launches path with it; bit-identical). */
 int phylo_engine_set_option(phylo_engine *e, int option, int64_t value);
 int phylo_engine_get_option(phylo_engine *e, int option, int64_t *value);
 /* CUDA-event profiler: while enabled, every kernel launch is bracketed by an event pair on
